@@ -1,0 +1,298 @@
+/*
+ * pbrt_b200.h -- C ABI of the B200 wavefront path tracer that stands in for
+ * pbrt-rust's PathIntegrator hot path.
+ *
+ * Every entry point names the reference interface (file:line under the
+ * pbrt-rust tree) it replaces.  The reference has no FFI today: the binding a
+ * maintainer would add (a new `Integrators` variant whose `render` flattens the
+ * `Scene` and calls these functions) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C structs, pointers and sizes only; no C++/torch types.
+ *   - all input arrays are caller-owned host memory unless a function name ends
+ *     in `_dev` (then they are device pointers on the scene's device).
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from pbrt_b200_last_error() (thread-local).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with PBRT_B200_ERR_NO_DEVICE.
+ */
+#ifndef PBRT_B200_H
+#define PBRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBRT_B200_ABI_VERSION 1
+
+enum {
+    PBRT_B200_OK = 0,
+    PBRT_B200_ERR_INVALID = 1,   /* bad argument / inconsistent scene tables      */
+    PBRT_B200_ERR_NO_DEVICE = 2, /* no CUDA device (there is no CPU fallback)      */
+    PBRT_B200_ERR_CUDA = 3,      /* a CUDA runtime call failed                     */
+    PBRT_B200_ERR_UNSUPPORTED = 4/* feature outside the hot path    */
+};
+
+/* ---- BVH -------------------------------------------------------------- */
+
+/* = LinearBVHNode, src/accelerators/bvh.rs:89-95 (32 bytes, reference order:
+ * first child of an interior node is at index+1, second child at `offset`). */
+typedef struct pbrt_b200_bvh_node {
+    float    bounds[6];  /* p_min.xyz, p_max.xyz                                 */
+    uint32_t offset;     /* leaf: first index into prims[]; interior: 2nd child  */
+    uint16_t n_prims;    /* 0 => interior                                        */
+    uint8_t  axis;       /* interior: split axis                                 */
+    uint8_t  pad;
+} pbrt_b200_bvh_node;
+
+enum { PBRT_B200_SPLIT_SAH = 0, PBRT_B200_SPLIT_MIDDLE = 2, PBRT_B200_SPLIT_EQUAL = 3 };
+
+/* Host-side mirror of BVHAccel::new + recursive_build + flatten_bvhtree
+ * (src/accelerators/bvh.rs:145-375,662-693).  In a real integration the Rust
+ * host already owns `BVHAccel.nodes`/`primitives` and skips this call.
+ *   prim_bounds : n x 6 floats (world bounds of primitive i)
+ *   nodes_out   : capacity >= 2n-1 ; ordered_out : n entries, ordered_out[k] =
+ *                 original primitive index stored at BVH slot k
+ *   n_nodes_out : number of nodes written                                        */
+int pbrt_b200_bvh_build(const float *prim_bounds, uint64_t n, int max_prims_in_node,
+                        int split_method, pbrt_b200_bvh_node *nodes_out,
+                        uint32_t *ordered_out, uint64_t *n_nodes_out);
+
+/* ---- scene tables ------------------------------------------------------ */
+
+enum { PBRT_B200_SHAPE_TRIANGLE = 0, PBRT_B200_SHAPE_SPHERE = 1 };
+enum {
+    PBRT_B200_PRIM_REVERSE_ORIENTATION = 1u << 0, /* Shape::reverse_orientation          */
+    PBRT_B200_PRIM_SWAPS_HANDEDNESS    = 1u << 1, /* Shape::transform_swapshandedness    */
+    PBRT_B200_PRIM_HAS_N               = 1u << 2, /* mesh has per-vertex normals         */
+    PBRT_B200_PRIM_HAS_S               = 1u << 3, /* mesh has per-vertex tangents        */
+    PBRT_B200_PRIM_HAS_UV              = 1u << 4  /* mesh has per-vertex uv              */
+};
+
+/* = GeometricPrimitive (src/core/primitive.rs:106-111), in `ordered_prims`
+ * order (BVH leaf order).  24 bytes.                                          */
+typedef struct pbrt_b200_prim {
+    uint32_t shape_kind;     /* PBRT_B200_SHAPE_*                                    */
+    uint32_t shape_index;    /* triangle number (into tri_indices/3) or sphere index */
+    int32_t  material;       /* index into materials[], -1 = none (pass-through)     */
+    int32_t  area_light;     /* index into lights[], -1 = not emissive               */
+    uint32_t flags;          /* PBRT_B200_PRIM_*                                     */
+    uint32_t creation_index; /* index before BVH reordering (what hit records carry) */
+} pbrt_b200_prim;
+
+/* = Sphere (src/shapes/sphere.rs:19-57); full spheres only on the hot path.   */
+typedef struct pbrt_b200_sphere {
+    float object_to_world[16]; /* row-major m                                        */
+    float world_to_object[16];
+    float radius;
+    uint32_t flags;            /* PBRT_B200_PRIM_REVERSE_ORIENTATION|SWAPS_HANDEDNESS */
+    float pad[2];
+} pbrt_b200_sphere;
+
+enum {
+    PBRT_B200_MAT_MATTE = 0,   /* src/materials/matte.rs:28-52   a=Kd  f0=sigma            */
+    PBRT_B200_MAT_PLASTIC = 1, /* src/materials/plastic.rs:34-69 a=Kd b=Ks f0=roughness   */
+    PBRT_B200_MAT_MIRROR = 2,  /* src/materials/mirror.rs:23-41  a=Kr                      */
+    PBRT_B200_MAT_GLASS = 3,   /* src/materials/glass.rs:35-92   a=Kr b=Kt f0=urough f1=vrough f2=index */
+    PBRT_B200_MAT_METAL = 4    /* src/materials/metal.rs:78-112  a=eta b=k f0=urough f1=vrough */
+};
+
+typedef struct pbrt_b200_material {
+    uint32_t type;
+    uint32_t remap_roughness;
+    float a[3];
+    float b[3];
+    float f0, f1, f2;
+    float pad;
+} pbrt_b200_material; /* 48 bytes */
+
+enum {
+    PBRT_B200_LIGHT_POINT = 0,    /* src/lights/point.rs:30-97    pos, I=L            */
+    PBRT_B200_LIGHT_DISTANT = 1,  /* src/lights/distant.rs:32-122 dir=wlight, L       */
+    PBRT_B200_LIGHT_SPOT = 2,     /* src/lights/spot.rs:31-119                        */
+    PBRT_B200_LIGHT_DIFFUSE = 3,  /* src/lights/diffuse.rs:20-176 one per emissive shape */
+    PBRT_B200_LIGHT_INFINITE = 4  /* src/lights/infinite.rs:120-177, constant radiance */
+};
+
+typedef struct pbrt_b200_light {
+    uint32_t type;
+    uint32_t two_sided;        /* diffuse                                            */
+    float L[3];                /* I (point/spot), L (distant), Lemit (diffuse), Lmap*scale (infinite) */
+    float pos[3];              /* point/spot: plight (world)                         */
+    float dir[3];              /* distant: wlight (world, normalised)                */
+    uint32_t shape_kind;       /* diffuse: emitting shape                            */
+    uint32_t shape_index;
+    uint32_t shape_flags;      /* PBRT_B200_PRIM_* of the emitting shape             */
+    float area;                /* diffuse: Shape::area()                             */
+    float cos_total_width;     /* spot                                               */
+    float cos_falloff_start;   /* spot                                               */
+    float world_to_light[16];  /* spot                                               */
+} pbrt_b200_light; /* 132 bytes */
+
+/* = PerspectiveCamera (src/cameras/perspective.rs:22-37); matrices row-major. */
+typedef struct pbrt_b200_camera {
+    float raster_to_camera[16];
+    float camera_to_world[16];
+    float lens_radius;
+    float focal_distance;
+    float shutter_open;
+    float shutter_close;
+} pbrt_b200_camera;
+
+/* = Film (src/core/film.rs:43-53).  Bounds are [x0,y0,x1,y1), pixels.        */
+typedef struct pbrt_b200_film {
+    int32_t full_resolution[2];
+    int32_t cropped_pixel_bounds[4];
+    float   filter_radius[2];
+    float   filter_table[256];     /* FILTER_TABLE_WIDTH^2, film.rs:16,77-89        */
+    float   scale;
+    float   max_sample_luminance;  /* +inf = off                                    */
+} pbrt_b200_film;
+
+enum { PBRT_B200_SAMPLER_SOBOL = 0, PBRT_B200_SAMPLER_HALTON = 1, PBRT_B200_SAMPLER_ZEROTWO = 2 };
+
+/* Sampler state the host owns (src/samplers/{sobol,halton,zerotwosequence}.rs).
+ * Tables are the reference crate's own constants, passed by pointer.          */
+typedef struct pbrt_b200_sampler {
+    uint32_t kind;
+    uint32_t samples_per_pixel;
+    int32_t  sample_bounds[4];       /* Film::get_sample_bounds, film.rs:104-111      */
+    uint32_t n_sampled_dimensions;   /* 02-sequence `dimensions` (default 4)          */
+    uint32_t pad;
+    const uint32_t *sobol_matrices32;/* [1024*52]  sobolmatrices.rs:5                 */
+    const uint64_t *vdc_matrices;    /* [25*52]    rows padded, sobolmatrices.rs:26842 */
+    const uint64_t *vdc_matrices_inv;/* [26*52]    sobolmatrices.rs:27534             */
+} pbrt_b200_sampler;
+
+enum { PBRT_B200_LIGHTS_UNIFORM = 0, PBRT_B200_LIGHTS_POWER = 1, PBRT_B200_LIGHTS_SPATIAL = 2 };
+
+/* = PathIntegrator (src/integrators/path.rs:32-40,228-249).                  */
+typedef struct pbrt_b200_integrator {
+    int32_t  max_depth;
+    float    rr_threshold;
+    int32_t  pixel_bounds[4];
+    uint32_t light_sample_strategy;
+    uint32_t pad;
+} pbrt_b200_integrator;
+
+/* Flattened Scene (src/core/scene.rs:23-29 + what hangs off it).              */
+typedef struct pbrt_b200_scene_desc {
+    uint32_t abi_version;            /* PBRT_B200_ABI_VERSION                         */
+    uint32_t pad;
+    const pbrt_b200_bvh_node *nodes; uint64_t n_nodes;   /* BVHAccel.nodes            */
+    const pbrt_b200_prim *prims;     uint64_t n_prims;   /* BVHAccel.primitives order */
+    /* TriangleMesh SoA, world space (src/shapes/triangle.rs:21-48) */
+    const float *vertex_p;           /* 3*n_vertices                                  */
+    const float *vertex_n;           /* 3*n_vertices or NULL                          */
+    const float *vertex_s;           /* 3*n_vertices or NULL                          */
+    const float *vertex_uv;          /* 2*n_vertices or NULL                          */
+    uint64_t n_vertices;
+    const uint32_t *tri_indices;     /* 3*n_triangles                                 */
+    uint64_t n_triangles;
+    const pbrt_b200_sphere *spheres; uint64_t n_spheres;
+    const pbrt_b200_material *materials; uint64_t n_materials;
+    const pbrt_b200_light *lights;   uint64_t n_lights;  /* Scene.lights order        */
+} pbrt_b200_scene_desc;
+
+typedef struct pbrt_b200_scene pbrt_b200_scene; /* opaque; owns device memory */
+
+/* ---- rays --------------------------------------------------------------- */
+
+/* Ray as the batch entry points see it (src/core/geometry/ray.rs:9-16). 32 B. */
+typedef struct pbrt_b200_ray {
+    float o[3];
+    float t_max;
+    float d[3];
+    float time;
+} pbrt_b200_ray;
+
+/* Closest-hit record.  prim = creation_index of the hit GeometricPrimitive, or
+ * 0xffffffff on a miss; t = r.t_max after the hit (primitive.rs:137);
+ * b0,b1 = first two barycentrics (triangle.rs:209-213; b2 = 1-b0-b1 is NOT how
+ * the reference computes it, so shading recomputes e2/det from the slot).  16 B. */
+typedef struct pbrt_b200_hit {
+    uint32_t prim;
+    float t;
+    float b0;
+    float b1;
+} pbrt_b200_hit;
+
+#define PBRT_B200_NO_HIT 0xffffffffu
+
+/* ---- entry points -------------------------------------------------------- */
+
+const char *pbrt_b200_last_error(void);
+int pbrt_b200_abi_version(void);
+/* number of visible CUDA devices (0 => every compute call fails) */
+int pbrt_b200_device_count(void);
+
+/* Scene::new (src/core/scene.rs:32-52) + upload.  `device` = CUDA ordinal.     */
+int pbrt_b200_scene_create(const pbrt_b200_scene_desc *desc, int device, pbrt_b200_scene **out);
+void pbrt_b200_scene_destroy(pbrt_b200_scene *scene);
+/* Scene.wb (scene.rs:27): root bounds, 6 floats. */
+int pbrt_b200_scene_world_bound(const pbrt_b200_scene *scene, float *bounds6);
+
+/* Scene::intersect (src/core/scene.rs:54-59) over a batch: BVHAccel::intersect
+ * (bvh.rs:705-760) + Triangle::intersect (triangle.rs:136-233) / Sphere.        */
+int pbrt_b200_intersect(pbrt_b200_scene *scene, const pbrt_b200_ray *rays, uint64_t n,
+                        pbrt_b200_hit *hits);
+/* Scene::intersect_p (scene.rs:61-66): out[i] = 1 if occluded.                  */
+int pbrt_b200_intersect_p(pbrt_b200_scene *scene, const pbrt_b200_ray *rays, uint64_t n,
+                          uint8_t *occluded);
+/* Same, buffers already resident on the scene's device; asynchronous on
+ * `stream` (a cudaStream_t passed as void*, NULL = legacy default stream).      */
+int pbrt_b200_intersect_dev(pbrt_b200_scene *scene, const pbrt_b200_ray *rays_dev, uint64_t n,
+                            pbrt_b200_hit *hits_dev, void *stream);
+int pbrt_b200_intersect_p_dev(pbrt_b200_scene *scene, const pbrt_b200_ray *rays_dev, uint64_t n,
+                              uint8_t *occluded_dev, void *stream);
+
+/* Render job = Integrator + Camera + Film + Sampler bound to a scene.          */
+typedef struct pbrt_b200_render_desc {
+    pbrt_b200_camera camera;
+    pbrt_b200_film film;
+    pbrt_b200_sampler sampler;
+    pbrt_b200_integrator integrator;
+    /* Work window for multi-GPU / batched runs: only tiles (16x16 over the sample
+     * bounds, integrator.rs:274-279) with index in [tile_begin, tile_end) and
+     * pixel samples in [sample_begin, sample_end) are rendered.  0,0 => all.    */
+    uint32_t tile_begin, tile_end;
+    uint32_t sample_begin, sample_end;
+    uint32_t paths_in_flight;   /* 0 => library default                          */
+    uint32_t flags;             /* PBRT_B200_RENDER_*                            */
+} pbrt_b200_render_desc;
+
+enum {
+    PBRT_B200_RENDER_KEEP_ON_DEVICE = 1u << 0 /* rgbw_out is a device pointer      */
+};
+
+/* Counters mirroring the reference's stats (integrator.rs:36, scene.rs:14-15,
+ * path.rs:24-25).                                                              */
+typedef struct pbrt_b200_render_stats {
+    uint64_t camera_rays;
+    uint64_t intersection_tests;   /* closest-hit rays (path + MIS)                 */
+    uint64_t shadow_tests;         /* any-hit rays                                  */
+    uint64_t zero_radiance_paths;
+    uint64_t kernel_launches;      /* kernels this library launched for the call    */
+    double   device_ms;            /* CUDA-event time of the wavefront loop          */
+    double   trace_closest_ms;     /* of which: closest-hit traversal kernel         */
+    double   trace_any_ms;         /* of which: any-hit traversal kernel             */
+} pbrt_b200_render_stats;
+
+/* SamplerIntegrator::render (src/core/integrator.rs:263-403) minus file output:
+ * accumulates filter-weighted samples (FilmTile::add_sample, film.rs:292-331)
+ * into rgbw_out[4 * width * height] over film.cropped_pixel_bounds as
+ * {sum r, sum g, sum b, sum filter weight}; the buffer is ADDED to, so a caller
+ * may split a render into several calls (or GPUs) and sum.  `stats` may be NULL. */
+int pbrt_b200_render(pbrt_b200_scene *scene, const pbrt_b200_render_desc *desc,
+                     float *rgbw_out, pbrt_b200_render_stats *stats);
+
+/* Film::write_image arithmetic (src/core/film.rs:217-264): RGB->XYZ->RGB,
+ * divide by weight, clamp at 0, scale.  rgb_out[3*npixels].  Host buffers.      */
+int pbrt_b200_film_resolve(const float *rgbw, uint64_t npixels, float scale, float *rgb_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRT_B200_H */

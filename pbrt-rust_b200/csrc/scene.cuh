@@ -1,0 +1,65 @@
+// Device-resident scene: HBM layout of the flattened pbrt-rust Scene.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pbrt_b200.h"
+
+namespace pb {
+
+// Child reference inside a fat node / on the traversal stack:
+//   bit 31 set  -> leaf, low 31 bits = first BVH slot (run ends at a record with TRI_LAST)
+//   bit 31 clear-> interior, low bits = fat-node index
+#define PB_LEAF_BIT 0x80000000u
+#define PB_REF_NONE 0xffffffffu
+
+// flags in TriRec.v1.w (as uint)
+#define PB_TRI_LAST 0x80000000u     /* last primitive of its leaf            */
+#define PB_TRI_SPHERE 0x40000000u   /* slot is a sphere, v2.w = sphere index */
+#define PB_TRI_FLAGS_MASK 0x000000ffu /* PBRT_B200_PRIM_* of the primitive     */
+
+struct DevScene {
+    // Fat BVH2: per INTERIOR node of the reference's LinearBVHNode array, the exact f32
+    // boxes of both children (48 B) + child refs + split axis = 64 B = 4 x float4:
+    //  q0 = {c0.min.x, c0.min.y, c0.min.z, c0.max.x}
+    //  q1 = {c0.max.y, c0.max.z, c1.min.x, c1.min.y}
+    //  q2 = {c1.min.z, c1.max.x, c1.max.y, c1.max.z}
+    //  q3 = {ref0, ref1, axis, 0} (bit patterns)
+    // c0 = reference child at index+1, c1 = reference child at `offset` (bvh.rs:662-693).
+    const float4* nodes;
+    uint32_t n_fat;
+    uint32_t root_ref;      // PB_REF_NONE when the scene is empty
+    float root_box[6];      // LinearBVHNode[0].bounds = Scene.wb
+    // Leaf primitives in BVH slot order, vertices pre-gathered (3 x float4 = 48 B):
+    //  v0 = {p0.xyz, creation_index}  v1 = {p1.xyz, flags}  v2 = {p2.xyz, shape_index}
+    const float4* tris;
+    uint32_t n_slots;
+    const pbrt_b200_prim* prims;      // slot order
+    const float* vertex_p;
+    const float* vertex_n;
+    const float* vertex_s;
+    const float* vertex_uv;
+    const uint32_t* tri_indices;
+    const pbrt_b200_sphere* spheres;
+    const pbrt_b200_material* materials;
+    const pbrt_b200_light* lights;
+    uint32_t n_lights;
+    uint32_t n_materials;
+    // Scene::new preprocessing (scene.rs:32-52, distant.rs:53-60)
+    float world_center[3];
+    float world_radius;
+};
+
+}  // namespace pb
+
+// Host-side owner.  Opaque to C callers.
+struct pbrt_b200_scene {
+    int device = 0;
+    pb::DevScene dev;            // pointers are device pointers
+    void* allocs[16] = {nullptr};
+    int n_allocs = 0;
+    uint64_t n_prims = 0, n_nodes = 0;
+    uint64_t device_bytes = 0;
+    void* scratch = nullptr;     // reusable staging for the host-buffer batch API
+    uint64_t scratch_bytes = 0;
+    void* light_distrib = nullptr;  // owned by render.cu
+};

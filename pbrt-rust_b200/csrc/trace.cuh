@@ -1,0 +1,285 @@
+// Software BVH traversal + watertight triangle test + sphere quadric (device).
+//
+// Replaces BVHAccel::intersect / intersect_p (accelerators/bvh.rs:705-814),
+// Bounds3f::intersect_p2 (core/geometry/bounds.rs:559-580), Triangle::intersect /
+// intersect_p (shapes/triangle.rs:136-233, 400-495) and Sphere::intersect root
+// selection (shapes/sphere.rs:59-108).
+//
+// Exactness contract: the same boxes are tested in the same order with the same f32
+// arithmetic as the reference's binary traversal, so primitive IDs, t and the
+// barycentrics are bit-identical.  The layout differs (child boxes live in the parent:
+// one 64-byte fetch per step, four 128-bit loads): a child box is slab-tested when its
+// parent is visited and only the t_max-dependent part of the reference's test
+// (`tmin < ray.t_max`) is re-evaluated when the entry is popped -- which is when the
+// reference would have tested that node.
+#pragma once
+#include "scene.cuh"
+#include "vecmath.cuh"
+
+namespace pb {
+
+struct RayHit {
+    uint32_t slot;  // BVH slot of the hit primitive or PBRT_B200_NO_HIT
+    float t, b0, b1, b2;
+};
+
+// --- Triangle::intersect, triangle.rs:136-233 (+ :236-263 rejection for closest hits)
+template <bool CLOSEST>
+PB_D bool triangle_test(f3 o, f3 dir, float t_max, f3 p0, f3 p1, f3 p2, int kx, int ky, int kz, float Sx, float Sy, float Sz,
+                        float* t_out, float* b0_out, float* b1_out, float* b2_out) {
+    f3 q0 = p0 - o, q1 = p1 - o, q2 = p2 - o;
+    f3 p0t(comp(q0, kx), comp(q0, ky), comp(q0, kz));
+    f3 p1t(comp(q1, kx), comp(q1, ky), comp(q1, kz));
+    f3 p2t(comp(q2, kx), comp(q2, ky), comp(q2, kz));
+    p0t.x += Sx * p0t.z; p0t.y += Sy * p0t.z;
+    p1t.x += Sx * p1t.z; p1t.y += Sy * p1t.z;
+    p2t.x += Sx * p2t.z; p2t.y += Sy * p2t.z;
+    float e0 = p1t.x * p2t.y - p1t.y * p2t.x;
+    float e1 = p2t.x * p0t.y - p2t.y * p0t.x;
+    float e2 = p0t.x * p1t.y - p0t.y * p1t.x;
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {  // f64 fallback at triangle edges
+        e0 = (float)__dsub_rn(__dmul_rn((double)p2t.y, (double)p1t.x), __dmul_rn((double)p2t.x, (double)p1t.y));
+        e1 = (float)__dsub_rn(__dmul_rn((double)p0t.y, (double)p2t.x), __dmul_rn((double)p0t.x, (double)p2t.y));
+        e2 = (float)__dsub_rn(__dmul_rn((double)p1t.y, (double)p0t.x), __dmul_rn((double)p1t.x, (double)p0t.y));
+    }
+    if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0.0f) return false;
+    p0t.z *= Sz; p1t.z *= Sz; p2t.z *= Sz;
+    float tscaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+    if (det < 0.0f && (tscaled >= 0.0f || tscaled < t_max * det)) return false;
+    else if (det > 0.0f && (tscaled <= 0.0f || tscaled >= t_max * det)) return false;
+    float invdet = 1.0f / det;
+    float b0 = e0 * invdet, b1 = e1 * invdet, b2 = e2 * invdet;
+    float t = tscaled * invdet;
+    float maxzt = fmaxf(fabsf(p0t.z), fmaxf(fabsf(p1t.z), fabsf(p2t.z)));
+    float deltaz = gamma_n(3) * maxzt;
+    float maxxt = fmaxf(fabsf(p0t.x), fmaxf(fabsf(p1t.x), fabsf(p2t.x)));
+    float maxyt = fmaxf(fabsf(p0t.y), fmaxf(fabsf(p1t.y), fabsf(p2t.y)));
+    float deltax = gamma_n(5) * (maxxt + maxzt);
+    float deltay = gamma_n(5) * (maxyt + maxzt);
+    float deltae = 2.0f * (gamma_n(2) * maxxt * maxyt + deltay * maxxt + deltax * maxyt);
+    float maxe = fmaxf(fabsf(e0), fmaxf(fabsf(e1), fabsf(e2)));
+    float deltat = 3.0f * (gamma_n(3) * maxe * maxzt + deltae * maxzt + deltaz * maxe) * fabsf(invdet);
+    if (t <= deltat) return false;
+    *t_out = t; *b0_out = b0; *b1_out = b1; *b2_out = b2;
+    return true;
+}
+
+// triangle.rs:236-263: after the t tests a closest-hit candidate is still rejected when
+// both dpdu x dpdv and the geometric normal vanish.  uv = per-vertex (u,v) or the default
+// parameterisation (triangle.rs:109-115).
+__device__ __noinline__ bool triangle_bogus(f3 p0, f3 p1, f3 p2, float2 uv0, float2 uv1, float2 uv2) {
+    float2 duv02 = make_float2(uv0.x - uv2.x, uv0.y - uv2.y), duv12 = make_float2(uv1.x - uv2.x, uv1.y - uv2.y);
+    f3 dp02 = p0 - p2, dp12 = p1 - p2;
+    float determinant = duv02.x * duv12.y - duv02.y * duv12.x;
+    bool degenerateuv = fabsf(determinant) < 1.0e-8f;
+    f3 dpdu(0.f, 0.f, 0.f), dpdv(0.f, 0.f, 0.f);
+    if (!degenerateuv) {
+        float inv = 1.0f / determinant;
+        dpdu = (dp02 * duv12.y - dp12 * duv02.y) * inv;
+        dpdv = (dp02 * -duv12.x + dp12 * duv02.x) * inv;
+    }
+    if (degenerateuv || len2(cross(dpdu, dpdv)) == 0.0f) {
+        f3 ng = cross(p2 - p0, p1 - p0);
+        if (len2(ng) == 0.0f) return true;
+    }
+    return false;
+}
+
+PB_D void fetch_uv(const DevScene& s, uint32_t flags, uint32_t shape_index, float2* uv0, float2* uv1, float2* uv2) {
+    if ((flags & PBRT_B200_PRIM_HAS_UV) && s.vertex_uv) {
+        const uint32_t* idx = s.tri_indices + 3ull * shape_index;
+        const float2* uv = reinterpret_cast<const float2*>(s.vertex_uv);
+        *uv0 = uv[idx[0]]; *uv1 = uv[idx[1]]; *uv2 = uv[idx[2]];
+    } else {
+        *uv0 = make_float2(0.f, 0.f); *uv1 = make_float2(1.f, 0.f); *uv2 = make_float2(1.f, 1.f);
+    }
+}
+
+// --- EFloat (core/efloat.rs) ------------------------------------------------
+struct EF { float v, lo, hi; };
+PB_D EF ef(float v, float err) {
+    EF r; r.v = v;
+    if (err == 0.0f) { r.lo = v; r.hi = v; } else { r.lo = next_down(v - err); r.hi = next_up(v + err); }
+    return r;
+}
+PB_D EF ef_add(EF a, EF b) { EF r; r.v = a.v + b.v; r.lo = next_down(a.lo + b.lo); r.hi = next_up(a.hi + b.hi); return r; }
+PB_D EF ef_sub(EF a, EF b) { EF r; r.v = a.v - b.v; r.lo = next_down(a.lo - b.hi); r.hi = next_up(a.hi - b.lo); return r; }
+PB_D EF ef_mul(EF a, EF b) {
+    EF r; r.v = a.v * b.v;
+    float p0 = a.lo * b.lo, p1 = a.hi * b.lo, p2 = a.lo * b.hi, p3 = a.hi * b.hi;
+    r.lo = next_down(fminf(fminf(p0, p1), fminf(p2, p3)));
+    r.hi = next_up(fmaxf(fmaxf(p0, p1), fmaxf(p2, p3)));
+    return r;
+}
+PB_D EF ef_div(EF a, EF b) {  // efloat.rs:134-156: the NUMERATOR is tested for straddling zero
+    EF r; r.v = a.v / b.v;
+    if (a.lo < 0.0f && a.hi > 0.0f) { r.lo = -PB_INF; r.hi = PB_INF; }
+    else {
+        float q0 = a.lo / b.lo, q1 = a.hi / b.lo, q2 = a.lo / b.hi, q3 = a.hi / b.hi;
+        r.lo = next_down(fminf(fminf(q0, q1), fminf(q2, q3)));
+        r.hi = next_up(fmaxf(fmaxf(q0, q1), fmaxf(q2, q3)));
+    }
+    return r;
+}
+
+// World ray -> object space with error bounds, transform.rs:579-591
+PB_D void sphere_object_ray(const pbrt_b200_sphere& sp, f3 o, f3 d, f3* oo, f3* od, f3* oerr, f3* derr) {
+    *oo = xf_point_err(sp.world_to_object, o, oerr);
+    *od = xf_vector_err(sp.world_to_object, d, derr);
+    float l2 = len2(*od);
+    if (l2 > 0.0f) {
+        float dt = dot(vabs(*od), *oerr) / l2;
+        *oo = *oo + *od * dt;
+    }
+}
+
+// Sphere::intersect / intersect_p up to the choice of t_shape_hit, sphere.rs:59-108
+// (full spheres; the partial-sphere clipping branch cannot trigger).
+__device__ __noinline__ bool sphere_test(const pbrt_b200_sphere* spp, f3 o, f3 d, float t_max, float* t_out) {
+    const pbrt_b200_sphere& sp = *spp;
+    f3 oo, od, oe, de;
+    sphere_object_ray(sp, o, d, &oo, &od, &oe, &de);
+    EF ox = ef(oo.x, oe.x), oy = ef(oo.y, oe.y), oz = ef(oo.z, oe.z);
+    EF dx = ef(od.x, de.x), dy = ef(od.y, de.y), dz = ef(od.z, de.z);
+    EF a = ef_add(ef_add(ef_mul(dx, dx), ef_mul(dy, dy)), ef_mul(dz, dz));
+    EF b = ef_mul(ef(2.0f, 0.f), ef_add(ef_add(ef_mul(dx, ox), ef_mul(dy, oy)), ef_mul(dz, oz)));
+    EF rr = ef(sp.radius, 0.f);
+    EF c = ef_sub(ef_add(ef_add(ef_mul(ox, ox), ef_mul(oy, oy)), ef_mul(oz, oz)), ef_mul(rr, rr));
+    // efloat.rs:211-231
+    double discrim = __dsub_rn(__dmul_rn((double)b.v, (double)b.v), __dmul_rn(__dmul_rn(4.0, (double)a.v), (double)c.v));
+    if (discrim < 0.0) return false;
+    double root = sqrt(discrim);
+    EF frd = ef((float)root, (float)__dmul_rn((double)PB_MACHINE_EPSILON, root));
+    EF q = (b.v < 0.0f) ? ef_mul(ef(-0.5f, 0.f), ef_sub(b, frd)) : ef_mul(ef(-0.5f, 0.f), ef_add(b, frd));
+    EF t0 = ef_div(q, a), t1 = ef_div(c, q);
+    if (t0.v > t1.v) { EF tmp = t0; t0 = t1; t1 = tmp; }
+    if (t0.hi > t_max || t1.lo <= 0.0f) return false;
+    EF ts = t0;
+    if (ts.lo <= 0.0f) {
+        ts = t1;
+        if (ts.hi > t_max) return false;
+    }
+    *t_out = ts.v;
+    return true;
+}
+
+// --- Bounds3f::intersect_p2, bounds.rs:559-580, minus the final t_max comparison.
+// Returns true when the slab tests pass and tmax > 0; *tmin_out is the value the
+// reference compares against ray.t_max.
+PB_D bool slab_test(float nx, float ny, float nz, float fx, float fy, float fz, f3 o, f3 inv, float* tmin_out) {
+    const float widen = 1.0f + 2.0f * gamma_n(3);
+    float tmin = (nx - o.x) * inv.x;
+    float tmax = (fx - o.x) * inv.x;
+    float tymin = (ny - o.y) * inv.y;
+    float tymax = (fy - o.y) * inv.y;
+    tmax *= widen;
+    tymax *= widen;
+    bool ok = !(tmin > tymax || tymin > tmax);
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = (nz - o.z) * inv.z;
+    float tzmax = (fz - o.z) * inv.z;
+    tzmax *= widen;
+    ok = ok && !(tmin > tzmax || tzmin > tmax);
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    *tmin_out = tmin;
+    return ok && (tmax > 0.0f);
+}
+
+#define PB_STACK_DEPTH 64  /* bvh.rs:722 nodes_tovisit = vec![0; 64] */
+
+// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray.
+template <bool ANY>
+PB_D bool traverse(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
+    hit->slot = PBRT_B200_NO_HIT;
+    hit->t = t_max;
+    if (s.root_ref == PB_REF_NONE) return false;
+    const f3 inv(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const bool ngx = inv.x < 0.0f, ngy = inv.y < 0.0f, ngz = inv.z < 0.0f;
+    // ray-constant part of the watertight test (triangle.rs:151-165)
+    f3 ad = vabs(d);
+    const int kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
+    const int kx = (kz + 1 == 3) ? 0 : kz + 1;
+    const int ky = (kx + 1 == 3) ? 0 : kx + 1;
+    const float dpx = comp(d, kx), dpy = comp(d, ky), dpz = comp(d, kz);
+    const float Sx = -dpx / dpz, Sy = -dpy / dpz, Sz = 1.0f / dpz;
+
+    uint2 stack[PB_STACK_DEPTH];
+    int sp = 0;
+    bool found = false;
+    uint32_t cur;
+    {
+        float tmin;
+        const float* rb = s.root_box;
+        bool ok = slab_test(ngx ? rb[3] : rb[0], ngy ? rb[4] : rb[1], ngz ? rb[5] : rb[2], ngx ? rb[0] : rb[3], ngy ? rb[1] : rb[4],
+                            ngz ? rb[2] : rb[5], o, inv, &tmin);
+        if (!(ok && tmin < t_max)) return false;
+        cur = s.root_ref;
+    }
+    for (;;) {
+        if (cur & PB_LEAF_BIT) {
+            uint32_t slot = cur & ~PB_LEAF_BIT;
+            uint32_t fl;
+            do {
+                const float4* tp = s.tris + 3ull * slot;
+                float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                fl = __float_as_uint(v1.w);
+                float t, b0, b1, b2;
+                bool h;
+                if (fl & PB_TRI_SPHERE) {
+                    h = sphere_test(s.spheres + __float_as_uint(v2.w), o, d, t_max, &t);
+                    b0 = b1 = b2 = 0.0f;
+                } else {
+                    f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
+                    h = triangle_test<!ANY>(o, d, t_max, p0, p1, p2, kx, ky, kz, Sx, Sy, Sz, &t, &b0, &b1, &b2);
+                    if (!ANY && h) {
+                        float2 uv0, uv1, uv2;
+                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2);
+                        if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) h = false;
+                    }
+                }
+                if (h) {
+                    if (ANY) { hit->slot = slot; hit->t = t; return true; }
+                    t_max = t;  // primitive.rs:137
+                    hit->slot = slot; hit->t = t; hit->b0 = b0; hit->b1 = b1; hit->b2 = b2;
+                    found = true;
+                }
+                ++slot;
+            } while (!(fl & PB_TRI_LAST));
+        } else {
+            const float4* np = s.nodes + 4ull * cur;
+            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+            uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z);
+            float tmin0, tmin1;
+            bool ok0 = slab_test(ngx ? q0.w : q0.x, ngy ? q1.x : q0.y, ngz ? q1.y : q0.z, ngx ? q0.x : q0.w, ngy ? q0.y : q1.x,
+                                 ngz ? q0.z : q1.y, o, inv, &tmin0);
+            bool ok1 = slab_test(ngx ? q2.y : q1.z, ngy ? q2.z : q1.w, ngz ? q2.w : q2.x, ngx ? q1.z : q2.y, ngy ? q1.w : q2.z,
+                                 ngz ? q2.x : q2.w, o, inv, &tmin1);
+            // near child = second child when the ray is negative along the split axis (bvh.rs:743-751)
+            bool second_first = (axis == 0) ? ngx : ((axis == 1) ? ngy : ngz);
+            uint32_t nref = second_first ? ref1 : ref0, fref = second_first ? ref0 : ref1;
+            float ntmin = second_first ? tmin1 : tmin0, ftmin = second_first ? tmin0 : tmin1;
+            bool nok = second_first ? ok1 : ok0, fok = second_first ? ok0 : ok1;
+            bool nhit = nok && (ntmin < t_max);
+            if (ANY) fok = fok && (ftmin < t_max);  // t_max never changes for any-hit rays
+            if (nhit) {
+                if (fok) { stack[sp] = make_uint2(fref, __float_as_uint(ftmin)); ++sp; }
+                cur = nref;
+                continue;
+            }
+            if (fok && (ftmin < t_max)) { cur = fref; continue; }
+        }
+        // pop: the reference tests the popped node's box against the *current* t_max
+        for (;;) {
+            if (sp == 0) return found;
+            --sp;
+            uint2 e = stack[sp];
+            if (__uint_as_float(e.y) < t_max) { cur = e.x; break; }
+        }
+    }
+}
+
+}  // namespace pb

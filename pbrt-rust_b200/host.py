@@ -1,0 +1,806 @@
+"""Host side of the B200 path tracer: ctypes binding of include/pbrt_b200.h plus a
+Python mirror of the pbrt-rust scene API for the PathIntegrator hot path.
+
+The reference's host is Rust (`API::shape`, `API::world_end`, `make_scene`,
+`RenderOptions::make_integrator`: src/core/api.rs:244-300,1493-1771); no Rust
+toolchain exists in this image, so this module plays that role: it keeps graphics
+state (CTM, current material, area light), flattens shapes into the SoA tables of
+`pbrt_b200_scene_desc`, asks the library's host-side `pbrt_b200_bvh_build`
+(mirror of BVHAccel::new) for the node array and hands everything to CUDA through
+the C ABI.  Nothing here computes a hit or a pixel: without the CUDA library and a
+GPU every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libpbrt_b200.so"
+TABLES_PATH = _HERE / "tables" / "sobol_tables.npz"
+
+f32 = np.float32
+NO_HIT = 0xFFFFFFFF
+
+# ---------------------------------------------------------------------------
+# ctypes mirrors of include/pbrt_b200.h
+# ---------------------------------------------------------------------------
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("bounds", C.c_float * 6), ("offset", C.c_uint32), ("n_prims", C.c_uint16), ("axis", C.c_uint8), ("pad", C.c_uint8)]
+
+
+NODE_DTYPE = np.dtype([("bounds", "<f4", 6), ("offset", "<u4"), ("n_prims", "<u2"), ("axis", "u1"), ("pad", "u1")])
+PRIM_DTYPE = np.dtype([("shape_kind", "<u4"), ("shape_index", "<u4"), ("material", "<i4"), ("area_light", "<i4"), ("flags", "<u4"), ("creation_index", "<u4")])
+SPHERE_DTYPE = np.dtype([("object_to_world", "<f4", 16), ("world_to_object", "<f4", 16), ("radius", "<f4"), ("flags", "<u4"), ("pad", "<f4", 2)])
+MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("remap_roughness", "<u4"), ("a", "<f4", 3), ("b", "<f4", 3), ("f0", "<f4"), ("f1", "<f4"), ("f2", "<f4"), ("pad", "<f4")])
+LIGHT_DTYPE = np.dtype([("type", "<u4"), ("two_sided", "<u4"), ("L", "<f4", 3), ("pos", "<f4", 3), ("dir", "<f4", 3), ("shape_kind", "<u4"),
+                        ("shape_index", "<u4"), ("shape_flags", "<u4"), ("area", "<f4"), ("cos_total_width", "<f4"), ("cos_falloff_start", "<f4"),
+                        ("world_to_light", "<f4", 16)])
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("t_max", "<f4"), ("d", "<f4", 3), ("time", "<f4")])
+HIT_DTYPE = np.dtype([("prim", "<u4"), ("t", "<f4"), ("b0", "<f4"), ("b1", "<f4")])
+assert NODE_DTYPE.itemsize == 32 and PRIM_DTYPE.itemsize == 24 and SPHERE_DTYPE.itemsize == 144
+assert MATERIAL_DTYPE.itemsize == 48 and LIGHT_DTYPE.itemsize == 132 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16
+
+SHAPE_TRIANGLE, SHAPE_SPHERE = 0, 1
+PRIM_REVERSE_ORIENTATION, PRIM_SWAPS_HANDEDNESS, PRIM_HAS_N, PRIM_HAS_S, PRIM_HAS_UV = 1, 2, 4, 8, 16
+MAT_MATTE, MAT_PLASTIC, MAT_MIRROR, MAT_GLASS, MAT_METAL = range(5)
+LIGHT_POINT, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_DIFFUSE, LIGHT_INFINITE = range(5)
+SAMPLER_SOBOL, SAMPLER_HALTON, SAMPLER_ZEROTWO = range(3)
+LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = range(3)
+SPLIT = {"sah": 0, "middle": 2, "equal": 3}
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("pad", C.c_uint32),
+                ("nodes", C.c_void_p), ("n_nodes", C.c_uint64),
+                ("prims", C.c_void_p), ("n_prims", C.c_uint64),
+                ("vertex_p", C.c_void_p), ("vertex_n", C.c_void_p), ("vertex_s", C.c_void_p), ("vertex_uv", C.c_void_p), ("n_vertices", C.c_uint64),
+                ("tri_indices", C.c_void_p), ("n_triangles", C.c_uint64),
+                ("spheres", C.c_void_p), ("n_spheres", C.c_uint64),
+                ("materials", C.c_void_p), ("n_materials", C.c_uint64),
+                ("lights", C.c_void_p), ("n_lights", C.c_uint64)]
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16), ("lens_radius", C.c_float), ("focal_distance", C.c_float),
+                ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+
+
+class FilmDesc(C.Structure):
+    _fields_ = [("full_resolution", C.c_int32 * 2), ("cropped_pixel_bounds", C.c_int32 * 4), ("filter_radius", C.c_float * 2),
+                ("filter_table", C.c_float * 256), ("scale", C.c_float), ("max_sample_luminance", C.c_float)]
+
+
+class SamplerDesc(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("samples_per_pixel", C.c_uint32), ("sample_bounds", C.c_int32 * 4), ("n_sampled_dimensions", C.c_uint32),
+                ("pad", C.c_uint32), ("sobol_matrices32", C.c_void_p), ("vdc_matrices", C.c_void_p), ("vdc_matrices_inv", C.c_void_p)]
+
+
+class IntegratorDesc(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4), ("light_sample_strategy", C.c_uint32),
+                ("pad", C.c_uint32)]
+
+
+class RenderDesc(C.Structure):
+    _fields_ = [("camera", CameraDesc), ("film", FilmDesc), ("sampler", SamplerDesc), ("integrator", IntegratorDesc),
+                ("tile_begin", C.c_uint32), ("tile_end", C.c_uint32), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
+                ("paths_in_flight", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("camera_rays", C.c_uint64), ("intersection_tests", C.c_uint64), ("shadow_tests", C.c_uint64), ("zero_radiance_paths", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("trace_closest_ms", C.c_double), ("trace_any_ms", C.c_double)]
+
+
+RENDER_KEEP_ON_DEVICE = 1
+
+EXPORTS = ["pbrt_b200_last_error", "pbrt_b200_abi_version", "pbrt_b200_device_count", "pbrt_b200_bvh_build", "pbrt_b200_scene_create",
+           "pbrt_b200_scene_destroy", "pbrt_b200_scene_world_bound", "pbrt_b200_intersect", "pbrt_b200_intersect_p", "pbrt_b200_intersect_dev",
+           "pbrt_b200_intersect_p_dev", "pbrt_b200_render", "pbrt_b200_film_resolve"]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.pbrt_b200_last_error.restype = C.c_char_p
+    lib.pbrt_b200_bvh_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.pbrt_b200_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pbrt_b200_scene_destroy.argtypes = [C.c_void_p]
+    lib.pbrt_b200_scene_destroy.restype = None
+    lib.pbrt_b200_scene_world_bound.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pbrt_b200_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.pbrt_b200_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.pbrt_b200_intersect_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.pbrt_b200_intersect_p_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.pbrt_b200_render.argtypes = [C.c_void_p, C.POINTER(RenderDesc), C.c_void_p, C.POINTER(RenderStats)]
+    lib.pbrt_b200_film_resolve.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load_library().pbrt_b200_last_error().decode("utf-8", "replace")
+        raise B200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+_tables = None
+
+
+def sampler_tables():
+    """The reference crate's Sobol tables (src/core/sobolmatrices.rs), see tools/convert_tables.py."""
+    global _tables
+    if _tables is None:
+        t = np.load(TABLES_PATH)
+        _tables = {k: np.ascontiguousarray(t[k]) for k in ("sobol32", "vdc", "vdc_inv")}
+    return _tables
+
+
+# ---------------------------------------------------------------------------
+# Transform (src/core/transform.rs), f32 arithmetic via numpy scalars
+# ---------------------------------------------------------------------------
+
+
+def _m4_inverse(m):
+    """Matrix4x4::inverse, transform.rs:78-145 (Gauss-Jordan, full pivoting, f32)."""
+    minv = np.array(m, dtype=f32).copy()
+    indxc, indxr, ipiv = [0] * 4, [0] * 4, [0] * 4
+    for i in range(4):
+        irow = icol = 0
+        big = f32(0)
+        for j in range(4):
+            if ipiv[j] != 1:
+                for k in range(4):
+                    if ipiv[k] == 0:
+                        a = abs(minv[j, k])
+                        if a >= big:
+                            big, irow, icol = a, j, k
+        ipiv[icol] += 1
+        if irow != icol:
+            minv[[irow, icol]] = minv[[icol, irow]]
+        indxr[i], indxc[i] = irow, icol
+        pivinv = f32(1) / minv[icol, icol]
+        minv[icol, icol] = f32(1)
+        minv[icol, :] = minv[icol, :] * pivinv
+        for j in range(4):
+            if j != icol:
+                save = minv[j, icol]
+                minv[j, icol] = f32(0)
+                minv[j, :] = minv[j, :] - minv[icol, :] * save
+    for i in range(4):
+        j = 3 - i
+        if indxr[j] != indxc[j]:
+            minv[:, [indxr[j], indxc[j]]] = minv[:, [indxc[j], indxr[j]]]
+    return minv
+
+
+def _m4_mul(a, b):
+    r = np.zeros((4, 4), dtype=f32)
+    for i in range(4):
+        for j in range(4):
+            r[i, j] = a[i, 0] * b[0, j] + a[i, 1] * b[1, j] + a[i, 2] * b[2, j] + a[i, 3] * b[3, j]
+    return r
+
+
+class Transform:
+    def __init__(self, m=None, m_inv=None):
+        self.m = np.eye(4, dtype=f32) if m is None else np.array(m, dtype=f32)
+        self.m_inv = _m4_inverse(self.m) if m_inv is None else np.array(m_inv, dtype=f32)
+
+    def __mul__(self, o):  # transform.rs:647-656
+        return Transform(_m4_mul(self.m, o.m), _m4_mul(o.m_inv, self.m_inv))
+
+    def inverse(self):
+        return Transform(self.m_inv, self.m)
+
+    @staticmethod
+    def translate(d):  # transform.rs:255-271
+        m, mi = np.eye(4, dtype=f32), np.eye(4, dtype=f32)
+        m[:3, 3] = np.asarray(d, dtype=f32)
+        mi[:3, 3] = -np.asarray(d, dtype=f32)
+        return Transform(m, mi)
+
+    @staticmethod
+    def scale(x, y, z):  # transform.rs:273-289
+        m = np.diag(np.array([x, y, z, 1], dtype=f32))
+        mi = np.diag(np.array([f32(1) / f32(x), f32(1) / f32(y), f32(1) / f32(z), 1], dtype=f32))
+        return Transform(m, mi)
+
+    @staticmethod
+    def rotate(theta_deg, axis):  # transform.rs:333-355
+        a = np.asarray(axis, dtype=f32)
+        a = a / f32(np.sqrt(f32(a[0] * a[0] + a[1] * a[1] + a[2] * a[2])))
+        th = f32(math.pi / 180.0) * f32(theta_deg)
+        s, c = f32(np.sin(th)), f32(np.cos(th))
+        m = np.eye(4, dtype=f32)
+        m[0, 0] = a[0] * a[0] + (1 - a[0] * a[0]) * c
+        m[0, 1] = a[0] * a[1] * (1 - c) - a[2] * s
+        m[0, 2] = a[0] * a[2] * (1 - c) + a[1] * s
+        m[1, 0] = a[0] * a[1] * (1 - c) + a[2] * s
+        m[1, 1] = a[1] * a[1] + (1 - a[1] * a[1]) * c
+        m[1, 2] = a[1] * a[2] * (1 - c) - a[0] * s
+        m[2, 0] = a[0] * a[2] * (1 - c) - a[1] * s
+        m[2, 1] = a[1] * a[2] * (1 - c) + a[0] * s
+        m[2, 2] = a[2] * a[2] + (1 - a[2] * a[2]) * c
+        return Transform(m, m.T.copy())
+
+    @staticmethod
+    def look_at(pos, look, up):  # transform.rs:357-393 (returns world->camera; m_inv = camera->world)
+        pos, look, up = (np.asarray(v, dtype=f32) for v in (pos, look, up))
+
+        def nrm(v):
+            return v * (f32(1) / f32(np.sqrt(f32(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))))
+
+        def cross(a, b):
+            return np.cross(a.astype(np.float64), b.astype(np.float64)).astype(f32)
+
+        d = nrm(look - pos)
+        right = nrm(cross(nrm(up), d))
+        new_up = cross(d, right)
+        c2w = np.eye(4, dtype=f32)
+        c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, new_up, d, pos
+        return Transform(_m4_inverse(c2w), c2w)
+
+    @staticmethod
+    def perspective(fov, n, f):  # transform.rs:399-411
+        n, f = f32(n), f32(f)
+        persp = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, f / (f - n), -f * n / (f - n)], [0, 0, 1, 0]], dtype=f32)
+        inv_tan = f32(1) / f32(np.tan(f32(f32(math.pi / 180.0) * f32(fov)) / f32(2)))
+        return Transform.scale(inv_tan, inv_tan, 1) * Transform(persp)
+
+    def points(self, p):  # transform_point, transform.rs:413-431 (vectorised, f32, same op order)
+        p = np.asarray(p, dtype=f32).reshape(-1, 3)
+        m = self.m
+        x, y, z = p[:, 0], p[:, 1], p[:, 2]
+        xp = x * m[0, 0] + y * m[0, 1] + z * m[0, 2] + m[0, 3]
+        yp = x * m[1, 0] + y * m[1, 1] + z * m[1, 2] + m[1, 3]
+        zp = x * m[2, 0] + y * m[2, 1] + z * m[2, 2] + m[2, 3]
+        wp = x * m[3, 0] + y * m[3, 1] + z * m[3, 2] + m[3, 3]
+        out = np.stack([xp, yp, zp], axis=1).astype(f32)
+        div = wp != f32(1)
+        if div.any():
+            out[div] = out[div] * (f32(1) / wp[div])[:, None]
+        return out
+
+    def vectors(self, v):  # transform.rs:496-508
+        v = np.asarray(v, dtype=f32).reshape(-1, 3)
+        m = self.m
+        x, y, z = v[:, 0], v[:, 1], v[:, 2]
+        return np.stack([x * m[0, 0] + y * m[0, 1] + z * m[0, 2], x * m[1, 0] + y * m[1, 1] + z * m[1, 2],
+                         x * m[2, 0] + y * m[2, 1] + z * m[2, 2]], axis=1).astype(f32)
+
+    def normals(self, n):  # transform.rs:529-541
+        n = np.asarray(n, dtype=f32).reshape(-1, 3)
+        mi = self.m_inv
+        x, y, z = n[:, 0], n[:, 1], n[:, 2]
+        return np.stack([x * mi[0, 0] + y * mi[1, 0] + z * mi[2, 0], x * mi[0, 1] + y * mi[1, 1] + z * mi[2, 1],
+                         x * mi[0, 2] + y * mi[1, 2] + z * mi[2, 2]], axis=1).astype(f32)
+
+    def swaps_handedness(self):  # transform.rs:638-644
+        m = self.m
+        det = (m[0, 0] * (m[1, 1] * m[2, 2] - m[1, 2] * m[2, 1]) - m[0, 1] * (m[1, 0] * m[2, 2] - m[1, 2] * m[2, 0]) +
+               m[0, 2] * (m[1, 0] * m[2, 1] - m[1, 1] * m[2, 0]))
+        return bool(det < 0)
+
+
+# ---------------------------------------------------------------------------
+# BVHAccel (host build through the library) and the flattened scene
+# ---------------------------------------------------------------------------
+
+
+def bvh_build(prim_bounds, max_prims=4, split_method="sah"):
+    """BVHAccel::new (bvh.rs:145-198) via pbrt_b200_bvh_build -> (nodes, ordered)."""
+    lib = load_library()
+    pb = np.ascontiguousarray(prim_bounds, dtype=f32).reshape(-1, 6)
+    n = pb.shape[0]
+    nodes = np.zeros(max(2 * n - 1, 1), dtype=NODE_DTYPE)
+    ordered = np.zeros(max(n, 1), dtype=np.uint32)
+    nn = C.c_uint64(0)
+    _check(lib.pbrt_b200_bvh_build(_ptr(pb), n, int(max_prims), SPLIT[split_method], _ptr(nodes), _ptr(ordered), C.byref(nn)), "pbrt_b200_bvh_build")
+    return nodes[: nn.value].copy(), ordered[:n].copy()
+
+
+class FlatScene:
+    """The arrays behind `pbrt_b200_scene_desc` (owned here; the library copies them)."""
+
+    def __init__(self):
+        self.nodes = np.zeros(0, NODE_DTYPE)
+        self.prims = np.zeros(0, PRIM_DTYPE)
+        self.vertex_p = np.zeros((0, 3), f32)
+        self.vertex_n = None
+        self.vertex_s = None
+        self.vertex_uv = None
+        self.tri_indices = np.zeros((0, 3), np.uint32)
+        self.spheres = np.zeros(0, SPHERE_DTYPE)
+        self.materials = np.zeros(0, MATERIAL_DTYPE)
+        self.lights = np.zeros(0, LIGHT_DTYPE)
+
+    def desc(self):
+        d = SceneDesc()
+        d.abi_version = 1
+        d.nodes, d.n_nodes = _ptr(self.nodes), len(self.nodes)
+        d.prims, d.n_prims = _ptr(self.prims), len(self.prims)
+        d.vertex_p, d.n_vertices = _ptr(self.vertex_p), len(self.vertex_p)
+        d.vertex_n, d.vertex_s, d.vertex_uv = _ptr(self.vertex_n), _ptr(self.vertex_s), _ptr(self.vertex_uv)
+        d.tri_indices, d.n_triangles = _ptr(self.tri_indices), len(self.tri_indices)
+        d.spheres, d.n_spheres = _ptr(self.spheres), len(self.spheres)
+        d.materials, d.n_materials = _ptr(self.materials), len(self.materials)
+        d.lights, d.n_lights = _ptr(self.lights), len(self.lights)
+        return d
+
+    @property
+    def world_bound(self):
+        return self.nodes[0]["bounds"].copy() if len(self.nodes) else np.array([np.inf] * 3 + [-np.inf] * 3, f32)
+
+
+def _tri_area(p0, p1, p2):
+    """Triangle::area, triangle.rs:550-554: 0.5 * |(p1-p0) x (p2-p0)| with the f64 cross."""
+    c = np.cross((p1 - p0).astype(np.float64), (p2 - p0).astype(np.float64)).astype(f32)
+    return f32(0.5) * np.sqrt(c[..., 0] * c[..., 0] + c[..., 1] * c[..., 1] + c[..., 2] * c[..., 2]).astype(f32)
+
+
+# copper eta/k as RGB: Spectrum::from_sampled of metal.rs:13-53 evaluated by
+# tools/copper_rgb.py against the reference's CIE tables (src/core/cie.rs)
+COPPER_N = (0.19999069, 0.92208463, 1.09987593)
+COPPER_K = (3.90463543, 2.44763327, 2.13765264)
+
+
+class SceneBuilder:
+    """Graphics state + shape/light factories of pbrt-rust's API (api.rs:552-806,1493-1546)."""
+
+    def __init__(self):
+        self.ctm = Transform()
+        self._stack = []
+        self.reverse_orientation = False
+        self._material = self._mat_row("matte")  # api.rs default material: matte
+        self._materials = []
+        self._mat_index = {}
+        self._area_light = None
+        self._P, self._N, self._S, self._UV = [], [], [], []
+        self._nverts = 0
+        self._tris = []     # (indices[k,3] + base)
+        self._prims = []    # rows of PRIM_DTYPE before ordering
+        self._bounds = []
+        self._spheres = []
+        self._lights = []
+        self.any_n = self.any_s = self.any_uv = False
+
+    # --- graphics state ---------------------------------------------------
+    def attribute_begin(self):
+        self._stack.append((self.ctm, self._material, self._area_light, self.reverse_orientation))
+
+    def attribute_end(self):
+        self.ctm, self._material, self._area_light, self.reverse_orientation = self._stack.pop()
+
+    def identity(self):
+        self.ctm = Transform()
+
+    def translate(self, x, y, z):
+        self.ctm = self.ctm * Transform.translate((x, y, z))
+
+    def scale(self, x, y, z):
+        self.ctm = self.ctm * Transform.scale(x, y, z)
+
+    def rotate(self, deg, x, y, z):
+        self.ctm = self.ctm * Transform.rotate(deg, (x, y, z))
+
+    def transform(self, t):
+        self.ctm = self.ctm * t
+
+    # --- materials (src/materials/*.rs create_* defaults) -------------------
+    @staticmethod
+    def _mat_row(name, **kw):
+        r = np.zeros(1, MATERIAL_DTYPE)[0]
+        r["remap_roughness"] = 1 if kw.get("remaproughness", True) else 0
+
+        def rgb(key, default):
+            v = kw.get(key, default)
+            return np.full(3, v, f32) if np.isscalar(v) else np.asarray(v, f32)
+
+        if name == "matte":
+            r["type"], r["a"], r["f0"] = MAT_MATTE, rgb("Kd", 0.5), kw.get("sigma", 0.0)
+        elif name == "plastic":
+            r["type"], r["a"], r["b"], r["f0"] = MAT_PLASTIC, rgb("Kd", 0.25), rgb("Ks", 0.25), kw.get("roughness", 0.1)
+        elif name == "mirror":
+            r["type"], r["a"] = MAT_MIRROR, rgb("Kr", 0.9)
+        elif name == "glass":
+            r["type"], r["a"], r["b"] = MAT_GLASS, rgb("Kr", 1.0), rgb("Kt", 1.0)
+            r["f0"], r["f1"] = kw.get("uroughness", 0.0), kw.get("vroughness", 0.0)
+            r["f2"] = kw.get("eta", kw.get("index", 1.5))
+        elif name == "metal":
+            r["type"], r["a"], r["b"] = MAT_METAL, rgb("eta", COPPER_N), rgb("k", COPPER_K)
+            rough = kw.get("roughness", 0.01)
+            r["f0"], r["f1"] = kw.get("uroughness", rough), kw.get("vroughness", rough)
+        elif name in ("none", ""):
+            return None
+        else:
+            raise B200Error(f'Material "{name}" is outside the hot path (matte, plastic, mirror, glass, metal)')
+        return r
+
+    def material(self, name, **kw):
+        self._material = self._mat_row(name, **kw)
+
+    def _material_id(self):
+        if self._material is None:
+            return -1
+        key = self._material.tobytes()
+        if key not in self._mat_index:
+            self._mat_index[key] = len(self._materials)
+            self._materials.append(self._material.copy())
+        return self._mat_index[key]
+
+    # --- lights ------------------------------------------------------------
+    def area_light_source(self, name="diffuse", L=(1, 1, 1), scale=1.0, twosided=False):  # diffuse.rs:178-195
+        if name not in ("diffuse", "area"):
+            raise B200Error(f'AreaLightSource "{name}" unknown')
+        self._area_light = (np.asarray(L, f32) * f32(scale) if not np.isscalar(L) else np.full(3, L * scale, f32), bool(twosided))
+
+    def light_source(self, name, **kw):
+        r = np.zeros(1, LIGHT_DTYPE)[0]
+
+        def rgb(key, default):
+            v = kw.get(key, default)
+            return np.full(3, v, f32) if np.isscalar(v) else np.asarray(v, f32)
+
+        sc = rgb("scale", 1.0)
+        if name == "point":  # point.rs:99-106 (note the reference's translate(P.x, P.y, P.x) quirk)
+            P = np.asarray(kw.get("from", (0, 0, 0)), f32)
+            l2w = Transform.translate((P[0], P[1], P[0])) * self.ctm
+            r["type"], r["L"], r["pos"] = LIGHT_POINT, rgb("I", 1.0) * sc, l2w.points([[0, 0, 0]])[0]
+        elif name == "distant":  # distant.rs:124-132
+            frm, to = np.asarray(kw.get("from", (0, 0, 0)), f32), np.asarray(kw.get("to", (0, 0, 1)), f32)
+            w = self.ctm.vectors([frm - to])[0]
+            w = w * (f32(1) / np.sqrt(f32(w[0] * w[0] + w[1] * w[1] + w[2] * w[2])))
+            r["type"], r["L"], r["dir"] = LIGHT_DISTANT, rgb("L", 1.0) * sc, w
+        elif name == "infinite":  # infinite.rs, constant map only
+            if kw.get("mapname"):
+                raise B200Error("image-mapped infinite lights are outside the hot path")
+            r["type"], r["L"] = LIGHT_INFINITE, rgb("L", 1.0) * sc
+        else:
+            raise B200Error(f'LightSource "{name}" is outside the hot path (point, distant, infinite, diffuse area)')
+        self._lights.append(r)
+
+    # --- shapes --------------------------------------------------------------
+    def shape(self, name, **kw):
+        if name == "trianglemesh":
+            return self._trianglemesh(**kw)
+        if name == "sphere":
+            return self._sphere(**kw)
+        raise B200Error(f'Shape "{name}" is outside the hot path (trianglemesh, sphere)')
+
+    def _trianglemesh(self, P, indices, N=None, S=None, uv=None):  # triangle.rs:33-73,657-760
+        P = self.ctm.points(P)
+        idx = np.asarray(indices, np.uint32).reshape(-1, 3)
+        nv, nt = len(P), len(idx)
+        base = self._nverts
+        flags = (PRIM_REVERSE_ORIENTATION if self.reverse_orientation else 0) | (PRIM_SWAPS_HANDEDNESS if self.ctm.swaps_handedness() else 0)
+        self._P.append(P)
+        if N is not None:
+            flags |= PRIM_HAS_N
+            self.any_n = True
+        if S is not None:
+            flags |= PRIM_HAS_S
+            self.any_s = True
+        if uv is not None:
+            flags |= PRIM_HAS_UV
+            self.any_uv = True
+        self._N.append(self.ctm.normals(N) if N is not None else np.zeros((nv, 3), f32))
+        self._S.append(self.ctm.vectors(S) if S is not None else np.zeros((nv, 3), f32))
+        self._UV.append(np.asarray(uv, f32).reshape(-1, 2) if uv is not None else np.zeros((nv, 2), f32))
+        self._nverts += nv
+        tri_base = sum(len(t) for t in self._tris)
+        self._tris.append(idx + np.uint32(base))
+        p0, p1, p2 = P[idx[:, 0]], P[idx[:, 1]], P[idx[:, 2]]
+        lo = np.minimum(np.minimum(p0, p1), p2)
+        hi = np.maximum(np.maximum(p0, p1), p2)
+        self._bounds.append(np.concatenate([lo, hi], axis=1))
+        rows = np.zeros(nt, PRIM_DTYPE)
+        rows["shape_kind"] = SHAPE_TRIANGLE
+        rows["shape_index"] = np.arange(tri_base, tri_base + nt, dtype=np.uint32)
+        rows["material"] = self._material_id()
+        rows["area_light"] = -1
+        rows["flags"] = flags
+        if self._area_light is not None:  # api.rs:1531-1546: one DiffuseAreaLight per shape
+            L, two = self._area_light
+            lights = np.zeros(nt, LIGHT_DTYPE)
+            lights["type"], lights["two_sided"], lights["L"] = LIGHT_DIFFUSE, int(two), L
+            lights["shape_kind"], lights["shape_index"], lights["shape_flags"] = SHAPE_TRIANGLE, rows["shape_index"], flags
+            lights["area"] = _tri_area(p0, p1, p2)
+            first = len(self._lights)
+            self._lights.extend(list(lights))
+            rows["area_light"] = np.arange(first, first + nt, dtype=np.int32)
+        self._prims.append(rows)
+
+    def _sphere(self, radius=1.0):  # sphere.rs:397-432 (full sphere)
+        o2w = self.ctm
+        r = np.zeros(1, SPHERE_DTYPE)[0]
+        r["object_to_world"], r["world_to_object"], r["radius"] = o2w.m.reshape(-1), o2w.m_inv.reshape(-1), radius
+        flags = (PRIM_REVERSE_ORIENTATION if self.reverse_orientation else 0) | (PRIM_SWAPS_HANDEDNESS if o2w.swaps_handedness() else 0)
+        r["flags"] = flags
+        if self._area_light is not None:
+            raise B200Error("sphere area lights are outside the hot path")
+        # Transform::transform_bounds of the object bound (transform.rs:593-605)
+        rr = f32(radius)
+        corners = np.array([[x, y, z] for x in (-rr, rr) for y in (-rr, rr) for z in (-rr, rr)], f32)
+        wc = o2w.points(corners)
+        self._bounds.append(np.concatenate([wc.min(0), wc.max(0)])[None, :])
+        row = np.zeros(1, PRIM_DTYPE)
+        row["shape_kind"], row["shape_index"], row["material"], row["area_light"], row["flags"] = SHAPE_SPHERE, len(self._spheres), self._material_id(), -1, flags
+        self._spheres.append(r)
+        self._prims.append(row)
+
+    # --- WorldEnd: make_scene (api.rs:244-251) -------------------------------
+    def world_end(self, max_prims=4, split_method="sah", builder=None):
+        fs = FlatScene()
+        nprim = sum(len(p) for p in self._prims)
+        if self._P:
+            fs.vertex_p = np.ascontiguousarray(np.concatenate(self._P), f32)
+            fs.tri_indices = np.ascontiguousarray(np.concatenate(self._tris), np.uint32)
+            if self.any_n:
+                fs.vertex_n = np.ascontiguousarray(np.concatenate(self._N), f32)
+            if self.any_s:
+                fs.vertex_s = np.ascontiguousarray(np.concatenate(self._S), f32)
+            if self.any_uv:
+                fs.vertex_uv = np.ascontiguousarray(np.concatenate(self._UV), f32)
+        if self._spheres:
+            fs.spheres = np.array(self._spheres, SPHERE_DTYPE)
+        if self._materials:
+            fs.materials = np.array(self._materials, MATERIAL_DTYPE)
+        if self._lights:
+            fs.lights = np.array(self._lights, LIGHT_DTYPE)
+        if nprim:
+            prims = np.concatenate(self._prims)
+            prims["creation_index"] = np.arange(nprim, dtype=np.uint32)
+            bounds = np.ascontiguousarray(np.concatenate(self._bounds), f32)
+            nodes, ordered = (builder or bvh_build)(bounds, max_prims, split_method)
+            fs.nodes = nodes
+            fs.prims = np.ascontiguousarray(prims[ordered])
+            fs.prim_bounds = bounds
+        return fs
+
+
+# ---------------------------------------------------------------------------
+# Camera / Film / Sampler / Integrator descriptions
+# ---------------------------------------------------------------------------
+
+
+def _filter_eval(name, radius, x, y, **kw):
+    """Filters::evaluate (src/filters/*.rs) for the table build in Film::new."""
+    rx, ry = f32(radius[0]), f32(radius[1])
+    if name == "box":
+        return f32(1)
+    if name == "gaussian":  # gaussian.rs:16-33
+        alpha = f32(kw.get("alpha", 2.0))
+        ex, ey = f32(np.exp(-alpha * rx * rx)), f32(np.exp(-alpha * ry * ry))
+        gx = max(f32(0), f32(np.exp(-alpha * x * x)) - ex)
+        gy = max(f32(0), f32(np.exp(-alpha * y * y)) - ey)
+        return f32(gx * gy)
+    if name == "triangle":  # triangle.rs (filters)
+        return f32(max(f32(0), rx - abs(x)) * max(f32(0), ry - abs(y)))
+    raise B200Error(f'Filter "{name}" not mirrored on the host (box, gaussian, triangle); pass a 16x16 table instead')
+
+
+FILTER_DEFAULT_RADIUS = {"box": (0.5, 0.5), "gaussian": (2.0, 2.0), "triangle": (2.0, 2.0)}
+
+
+class Film:
+    """Film::new (film.rs:56-102): crop bounds, 16x16 filter table, sample bounds."""
+
+    def __init__(self, xres, yres, filter="box", radius=None, crop=(0.0, 1.0, 0.0, 1.0), scale=1.0, max_sample_luminance=float("inf"), **fkw):
+        self.full_resolution = (int(xres), int(yres))
+        self.filter = filter
+        self.radius = tuple(radius or FILTER_DEFAULT_RADIUS[filter])
+        x0, x1, y0, y1 = crop
+        self.cropped_pixel_bounds = (int(math.ceil(f32(xres) * f32(x0))), int(math.ceil(f32(yres) * f32(y0))),
+                                     int(math.ceil(f32(xres) * f32(x1))), int(math.ceil(f32(yres) * f32(y1))))
+        self.scale = scale
+        self.max_sample_luminance = max_sample_luminance
+        tab = np.zeros(256, f32)
+        for y in range(16):
+            for x in range(16):
+                px = (f32(x) + f32(0.5)) * f32(self.radius[0]) / f32(16)
+                py = (f32(y) + f32(0.5)) * f32(self.radius[1]) / f32(16)
+                tab[y * 16 + x] = _filter_eval(filter, self.radius, px, py, **fkw)
+        self.filter_table = tab
+
+    @property
+    def sample_bounds(self):  # film.rs:104-111
+        b = self.cropped_pixel_bounds
+        rx, ry = f32(self.radius[0]), f32(self.radius[1])
+        return (int(math.floor(f32(b[0]) + f32(0.5) - rx)), int(math.floor(f32(b[1]) + f32(0.5) - ry)),
+                int(math.ceil(f32(b[2]) - f32(0.5) + rx)), int(math.ceil(f32(b[3]) - f32(0.5) + ry)))
+
+    @property
+    def width(self):
+        return self.cropped_pixel_bounds[2] - self.cropped_pixel_bounds[0]
+
+    @property
+    def height(self):
+        return self.cropped_pixel_bounds[3] - self.cropped_pixel_bounds[1]
+
+    def desc(self):
+        d = FilmDesc()
+        d.full_resolution[:] = self.full_resolution
+        d.cropped_pixel_bounds[:] = self.cropped_pixel_bounds
+        d.filter_radius[:] = self.radius
+        d.filter_table[:] = self.filter_table.tolist()
+        d.scale, d.max_sample_luminance = self.scale, self.max_sample_luminance
+        return d
+
+
+class PerspectiveCamera:
+    """PerspectiveCamera::new + create_perspective_camera (perspective.rs:40-86,298-357)."""
+
+    def __init__(self, film, camera_to_world, fov=90.0, lensradius=0.0, focaldistance=1.0e30, shutteropen=0.0, shutterclose=1.0, screenwindow=None):
+        xr, yr = film.full_resolution
+        frame = f32(xr) / f32(yr)
+        if screenwindow is not None:
+            sx0, sx1, sy0, sy1 = (f32(v) for v in screenwindow)
+        elif frame > 1:
+            sx0, sx1, sy0, sy1 = -frame, frame, f32(-1), f32(1)
+        else:
+            sx0, sx1, sy0, sy1 = f32(-1), f32(1), f32(-1) / frame, f32(1) / frame
+        c2s = Transform.perspective(fov, 1e-2, 1000.0)
+        s2r = (Transform.scale(f32(xr), f32(yr), 1) * Transform.scale(f32(1) / (sx1 - sx0), f32(1) / (sy0 - sy1), 1) *
+               Transform.translate((-sx0, -sy1, 0)))
+        self.raster_to_camera = c2s.inverse() * s2r.inverse()
+        self.camera_to_world = camera_to_world
+        self.lens_radius, self.focal_distance = lensradius, focaldistance
+        self.shutter_open, self.shutter_close = shutteropen, shutterclose
+
+    def desc(self):
+        d = CameraDesc()
+        d.raster_to_camera[:] = self.raster_to_camera.m.reshape(-1).tolist()
+        d.camera_to_world[:] = self.camera_to_world.m.reshape(-1).tolist()
+        d.lens_radius, d.focal_distance = self.lens_radius, self.focal_distance
+        d.shutter_open, d.shutter_close = self.shutter_open, self.shutter_close
+        return d
+
+
+class Sampler:
+    KINDS = {"sobol": SAMPLER_SOBOL, "halton": SAMPLER_HALTON, "02sequence": SAMPLER_ZEROTWO, "lowdiscrepancy": SAMPLER_ZEROTWO}
+
+    def __init__(self, name="halton", pixelsamples=16, dimensions=4):
+        if name not in self.KINDS:
+            raise B200Error(f'Sampler "{name}" is outside the hot path (sobol, halton, 02sequence)')
+        self.kind, self.spp, self.dimensions = self.KINDS[name], int(pixelsamples), int(dimensions)
+
+    def desc(self, film):
+        t = sampler_tables()
+        d = SamplerDesc()
+        d.kind, d.samples_per_pixel, d.n_sampled_dimensions = self.kind, self.spp, self.dimensions
+        d.sample_bounds[:] = film.sample_bounds
+        d.sobol_matrices32, d.vdc_matrices, d.vdc_matrices_inv = _ptr(t["sobol32"]), _ptr(t["vdc"]), _ptr(t["vdc_inv"])
+        return d
+
+
+class PathIntegrator:
+    """PathIntegrator + create_path_integrator (src/integrators/path.rs:32-59,225-253)."""
+
+    STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER, "spatial": LIGHTS_SPATIAL}
+
+    def __init__(self, camera, film, sampler, maxdepth=5, rrthreshold=1.0, lightsamplestrategy="spatial", pixelbounds=None):
+        self.camera, self.film, self.sampler = camera, film, sampler
+        self.max_depth, self.rr_threshold = int(maxdepth), float(rrthreshold)
+        if lightsamplestrategy not in self.STRATEGY:
+            lightsamplestrategy = "spatial"  # path.rs -> lightdistrib.rs:27-30
+        self.light_sample_strategy = lightsamplestrategy
+        sb = film.sample_bounds
+        if pixelbounds is not None:  # path.rs:233-246: (x0, x1, y0, y1) intersected with the sample bounds
+            x0, x1, y0, y1 = pixelbounds
+            sb = (max(sb[0], x0), max(sb[1], y0), min(sb[2], x1), min(sb[3], y1))
+        self.pixel_bounds = sb
+
+    def desc(self, tile_range=None, sample_range=None, paths_in_flight=0, flags=0):
+        d = RenderDesc()
+        d.camera, d.film, d.sampler = self.camera.desc(), self.film.desc(), self.sampler.desc(self.film)
+        d.integrator.max_depth, d.integrator.rr_threshold = self.max_depth, self.rr_threshold
+        d.integrator.pixel_bounds[:] = self.pixel_bounds
+        d.integrator.light_sample_strategy = self.STRATEGY[self.light_sample_strategy]
+        if tile_range:
+            d.tile_begin, d.tile_end = tile_range
+        if sample_range:
+            d.sample_begin, d.sample_end = sample_range
+        d.paths_in_flight, d.flags = paths_in_flight, flags
+        return d
+
+    def n_tiles(self):  # integrator.rs:274-279
+        sb = self.film.sample_bounds
+        return ((sb[2] - sb[0] + 15) // 16) * ((sb[3] - sb[1] + 15) // 16)
+
+    def render(self, scene, **kw):
+        """Integrator::render (integrator.rs:249-252) -> linear RGB image [h, w, 3]."""
+        rgbw, stats = scene.render(self, **kw)
+        return scene.film_resolve(rgbw, self.film.scale).reshape(self.film.height, self.film.width, 3), stats
+
+
+class Scene:
+    """Device-resident Scene (scene.rs:23-29): owns the opaque `pbrt_b200_scene*`."""
+
+    def __init__(self, flat: FlatScene, device=0):
+        self.lib = load_library()
+        self.flat = flat
+        self.device = device
+        h = C.c_void_p()
+        d = flat.desc()
+        _check(self.lib.pbrt_b200_scene_create(C.byref(d), device, C.byref(h)), "pbrt_b200_scene_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pbrt_b200_scene_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def world_bound(self):
+        b = np.zeros(6, f32)
+        _check(self.lib.pbrt_b200_scene_world_bound(self.handle, _ptr(b)), "pbrt_b200_scene_world_bound")
+        return b
+
+    def intersect(self, rays):
+        """Scene::intersect over a batch of RAY_DTYPE rays -> HIT_DTYPE records (host buffers)."""
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        _check(self.lib.pbrt_b200_intersect(self.handle, _ptr(rays), len(rays), _ptr(hits)), "pbrt_b200_intersect")
+        return hits
+
+    def intersect_p(self, rays):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        occ = np.zeros(len(rays), np.uint8)
+        _check(self.lib.pbrt_b200_intersect_p(self.handle, _ptr(rays), len(rays), _ptr(occ)), "pbrt_b200_intersect_p")
+        return occ.astype(bool)
+
+    def intersect_dev(self, rays_ptr, n, hits_ptr, stream=None):
+        _check(self.lib.pbrt_b200_intersect_dev(self.handle, rays_ptr, n, hits_ptr, stream), "pbrt_b200_intersect_dev")
+
+    def intersect_p_dev(self, rays_ptr, n, occ_ptr, stream=None):
+        _check(self.lib.pbrt_b200_intersect_p_dev(self.handle, rays_ptr, n, occ_ptr, stream), "pbrt_b200_intersect_p_dev")
+
+    def render(self, integrator, rgbw=None, tile_range=None, sample_range=None, paths_in_flight=0, device_ptr=None):
+        film = integrator.film
+        stats = RenderStats()
+        if device_ptr is not None:
+            d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE)
+            _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), device_ptr, C.byref(stats)), "pbrt_b200_render")
+            return None, stats
+        if rgbw is None:
+            rgbw = np.zeros((film.height * film.width, 4), f32)
+        d = integrator.desc(tile_range, sample_range, paths_in_flight, 0)
+        _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), _ptr(rgbw), C.byref(stats)), "pbrt_b200_render")
+        return rgbw, stats
+
+    def film_resolve(self, rgbw, scale=1.0):
+        rgbw = np.ascontiguousarray(rgbw, f32).reshape(-1, 4)
+        out = np.zeros((len(rgbw), 3), f32)
+        _check(self.lib.pbrt_b200_film_resolve(_ptr(rgbw), len(rgbw), scale, _ptr(out)), "pbrt_b200_film_resolve")
+        return out
+
+
+def make_rays(o, d, t_max=np.inf, time=0.0):
+    o, d = np.asarray(o, f32).reshape(-1, 3), np.asarray(d, f32).reshape(-1, 3)
+    r = np.zeros(len(o), RAY_DTYPE)
+    r["o"], r["d"], r["t_max"], r["time"] = o, d, t_max, time
+    return r

@@ -1,0 +1,424 @@
+"""Deterministic synthetic scenes and ray batches (S1..S5, B-cam/B-diff/B-shadow).
+
+Each generator drives the SceneBuilder exactly as a .pbrt file would drive pbrt-rust's
+API, and returns (FlatScene, integrator factory).  All randomness is PCG32 (the
+reference's RNG, src/core/rng.rs) from the stated seeds.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import host as H
+
+f32 = np.float32
+ONE_MINUS_EPSILON = f32(float.fromhex("0x1.fffffep-1"))  # src/core/rng.rs:4
+
+
+# ---------------------------------------------------------------------------
+# PCG32 (src/core/rng.rs:25-76), vectorised over streams when needed
+# ---------------------------------------------------------------------------
+class PCG32:
+    MULT = 0x5851F42D4C957F2D
+
+    def __init__(self, seq=None):
+        self.state, self.inc = 0x853C49E6748FEA9B, 0xDA3E39CB94B95BDB
+        if seq is not None:
+            self.set_sequence(seq)
+
+    def set_sequence(self, seq):  # rng.rs:33-39
+        self.state = 0
+        self.inc = ((seq << 1) | 1) & 0xFFFFFFFFFFFFFFFF
+        self.uniform_u32()
+        self.state = (self.state + 0x853C49E6748FEA9B) & 0xFFFFFFFFFFFFFFFF
+        self.uniform_u32()
+
+    def uniform_u32(self):  # rng.rs:41-49
+        old = self.state
+        self.state = (old * self.MULT + self.inc) & 0xFFFFFFFFFFFFFFFF
+        xs = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
+        rot = old >> 59
+        return ((xs >> rot) | (xs << ((-rot) & 31))) & 0xFFFFFFFF
+
+    def uniform_float(self):  # rng.rs:66-68
+        return min(ONE_MINUS_EPSILON, f32(f32(self.uniform_u32()) * f32(2.3283064365386963e-10)))
+
+    def floats(self, n):
+        """n floats from this stream (vectorised LCG jump-free loop in numpy uint64)."""
+        out = np.empty(n, np.uint32)
+        st, inc, mult = np.uint64(self.state), np.uint64(self.inc), np.uint64(self.MULT)
+        with np.errstate(over="ignore"):
+            for i in range(n):
+                old = st
+                st = old * mult + inc
+                xs = np.uint32(((old >> np.uint64(18)) ^ old) >> np.uint64(27))
+                rot = np.uint32(old >> np.uint64(59))
+                out[i] = (xs >> rot) | (xs << ((np.uint32(32) - rot) & np.uint32(31)))
+        self.state = int(st)
+        return np.minimum(ONE_MINUS_EPSILON, out.astype(f32) * f32(2.3283064365386963e-10))
+
+
+def _hash_floats(n, seed):
+    """Counter-based PCG-style hash -> n floats in [0,1): one independent PCG32 stream
+    per element (sequence index = element index, seed folded into the state), first
+    output.  Used where millions of values are needed (vertex displacement, ray batches)."""
+    idx = np.arange(n, dtype=np.uint64)
+    mult = np.uint64(PCG32.MULT)
+    with np.errstate(over="ignore"):
+        inc = (idx << np.uint64(1)) | np.uint64(1)
+        st = np.zeros(n, np.uint64)
+        st = st * mult + inc
+        st = st + np.uint64(0x853C49E6748FEA9B) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        st = st * mult + inc
+        old = st
+        xs = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)).astype(np.uint32)
+        rot = (old >> np.uint64(59)).astype(np.uint32)
+        out = (xs >> rot) | (xs << ((np.uint32(32) - rot) & np.uint32(31)))
+    return np.minimum(ONE_MINUS_EPSILON, out.astype(f32) * f32(2.3283064365386963e-10))
+
+
+# ---------------------------------------------------------------------------
+# geometry helpers
+# ---------------------------------------------------------------------------
+def quad(p0, p1, p2, p3):
+    """Two triangles (0,1,2),(0,2,3) like the reference's scene files (spheres-differentials-texfilt.pbrt:26)."""
+    return np.array([p0, p1, p2, p3], f32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+
+
+def box_mesh(lo, hi):
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    P = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0], [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], f32)
+    I = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5], [0, 4, 7], [0, 7, 3]], np.uint32)
+    return P, I
+
+
+def _value_noise(p, seed):
+    """Trilinear value noise on the integer lattice, lattice values from _hash3."""
+    pi = np.floor(p).astype(np.int64)
+    pf = (p - pi).astype(f32)
+    w = pf * pf * (f32(3) - f32(2) * pf)
+
+    def lat(dx, dy, dz):
+        x, y, z = pi[:, 0] + dx, pi[:, 1] + dy, pi[:, 2] + dz
+        h = (x * 73856093) ^ (y * 19349663) ^ (z * 83492791) ^ (seed * 2654435761)
+        h = (h & 0xFFFFFFFF).astype(np.uint64)
+        h = (h ^ (h >> np.uint64(15))) * np.uint64(0x2C1B3C6D) & np.uint64(0xFFFFFFFF)
+        h = (h ^ (h >> np.uint64(12))) * np.uint64(0x297A2D39) & np.uint64(0xFFFFFFFF)
+        h = h ^ (h >> np.uint64(15))
+        return (h.astype(np.float64) / 4294967296.0).astype(f32)
+
+    c = [[[lat(i, j, k) for k in (0, 1)] for j in (0, 1)] for i in (0, 1)]
+    wx, wy, wz = w[:, 0], w[:, 1], w[:, 2]
+    x00 = c[0][0][0] * (1 - wx) + c[1][0][0] * wx
+    x10 = c[0][1][0] * (1 - wx) + c[1][1][0] * wx
+    x01 = c[0][0][1] * (1 - wx) + c[1][0][1] * wx
+    x11 = c[0][1][1] * (1 - wx) + c[1][1][1] * wx
+    y0 = x00 * (1 - wy) + x10 * wy
+    y1 = x01 * (1 - wy) + x11 * wy
+    return (y0 * (1 - wz) + y1 * wz).astype(f32)
+
+
+def fbm(p, seed=1234, octaves=5):
+    s = np.zeros(len(p), f32)
+    amp, freq = f32(0.5), f32(1.0)
+    for o in range(octaves):
+        s += amp * (_value_noise(p * freq, seed + o) * f32(2) - f32(1))
+        amp *= f32(0.5)
+        freq *= f32(2.0)
+    return s
+
+
+def displaced_sphere(nlong, nlat, radius=1.0, amplitude=0.1, seed=1234, freq=4.0):
+    """UV sphere with nlong x nlat quads (2 triangles each, shared vertices; the pole rows
+    are degenerate-free triangle fans), displaced along the normal by amplitude*fbm.
+    Returns P, indices, N (per-vertex normals of the displaced surface)."""
+    th = (np.arange(nlat + 1, dtype=np.float64) / nlat) * math.pi
+    ph = (np.arange(nlong, dtype=np.float64) / nlong) * 2.0 * math.pi
+    T, Ph = np.meshgrid(th, ph, indexing="ij")
+    d = np.stack([np.sin(T) * np.cos(Ph), np.sin(T) * np.sin(Ph), np.cos(T)], axis=-1).reshape(-1, 3)
+    disp = fbm((d * freq).astype(f32) + f32(17.0), seed=seed)
+    r = (radius + amplitude * disp.astype(np.float64))[:, None]
+    P = (d * r).astype(f32)
+    # collapse pole rows to single positions (keeps the mesh watertight)
+    P[:nlong] = P[0]
+    P[nlat * nlong:] = P[nlat * nlong]
+    i = np.arange(nlat)[:, None]
+    j = np.arange(nlong)[None, :]
+    a = (i * nlong + j).reshape(-1)
+    b = (i * nlong + (j + 1) % nlong).reshape(-1)
+    c = ((i + 1) * nlong + j).reshape(-1)
+    dd = ((i + 1) * nlong + (j + 1) % nlong).reshape(-1)
+    I = np.concatenate([np.stack([a, c, dd], 1), np.stack([a, dd, b], 1)]).astype(np.uint32)
+    # interleave so that the two triangles of a quad are adjacent
+    nq = nlat * nlong
+    I = np.stack([I[:nq], I[nq:]], axis=1).reshape(-1, 3)
+    # area-weighted vertex normals
+    p0, p1, p2 = (P[I[:, k]].astype(np.float64) for k in range(3))
+    fn = np.cross(p1 - p0, p2 - p0)
+    N = np.zeros((len(P), 3), np.float64)
+    for k in range(3):
+        np.add.at(N, I[:, k], fn)
+    ln = np.linalg.norm(N, axis=1, keepdims=True)
+    N = np.where(ln > 0, N / np.maximum(ln, 1e-30), d)
+    return P, I, N.astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# scenes
+# ---------------------------------------------------------------------------
+class SceneSetup:
+    def __init__(self, name, flat, make_integrator, description):
+        self.name, self.flat, self.make_integrator, self.description = name, flat, make_integrator, description
+
+
+def spheres_scene(xres=400, yres=400, spp=64, maxdepth=5, sampler="sobol"):
+    """S1 / config C1: the reference's spheres scene (src/scenes/spheres-differentials-texfilt.pbrt:1-37)
+    as a path-traced scene: mirror + glass sphere over a matte ground quad, distant light."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((2, 2, 5), (0, -0.4, 0), (0, 1, 0))
+    b.light_source("distant", **{"from": (0, 10, 0), "to": (0, 0, 0), "L": (3.141593, 3.141593, 3.141593)})
+    b.attribute_begin()
+    b.translate(0.25, 0, 0)
+    b.material("matte", Kd=0.5)
+    P, I = quad((-100, -1, -100), (400, -1, -100), (400, -1, 400), (-100, -1, 400))
+    b.shape("trianglemesh", P=P, indices=I)
+    b.attribute_end()
+    b.translate(-1.3, 0, 0)
+    b.material("mirror")
+    b.shape("sphere", radius=1.0)
+    b.translate(2.6, 0, 0)
+    b.material("glass")
+    b.shape("sphere", radius=1.0)
+    flat = b.world_end()
+
+    def make(spp_=spp, res=(xres, yres), maxdepth_=maxdepth, sampler_=sampler, strategy="spatial"):
+        film = H.Film(res[0], res[1], "box")
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=30.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    return SceneSetup("S1-spheres", flat, make, "two spheres (mirror, glass) + ground quad, distant light, path maxdepth 5")
+
+
+def cornell_scene(xres=1024, yres=1024, spp=256, maxdepth=8, sampler="sobol"):
+    """S2 / config C2: Cornell box, diffuse quad area light (2 triangles => 2 lights), matte walls,
+    two plastic boxes, lightsamplestrategy "power", gaussian 2x2 filter."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((278, 273, -800), (278, 273, 0), (0, 1, 0))
+    white, red, green = (0.73, 0.73, 0.73), (0.65, 0.05, 0.05), (0.12, 0.45, 0.15)
+    S = 555.0
+
+    def wall(col, *pts):
+        b.material("matte", Kd=col)
+        P, I = quad(*pts)
+        b.shape("trianglemesh", P=P, indices=I)
+
+    wall(white, (0, 0, 0), (S, 0, 0), (S, 0, S), (0, 0, S))       # floor
+    wall(white, (0, S, 0), (0, S, S), (S, S, S), (S, S, 0))       # ceiling
+    wall(white, (0, 0, S), (S, 0, S), (S, S, S), (0, S, S))       # back
+    wall(green, (0, 0, 0), (0, 0, S), (0, S, S), (0, S, 0))       # right (x=0)
+    wall(red, (S, 0, 0), (S, S, 0), (S, S, S), (S, 0, S))         # left (x=S)
+    b.attribute_begin()
+    b.area_light_source("diffuse", L=(17, 12, 4))
+    b.material("matte", Kd=0.0)
+    P, I = quad((213, S - 0.1, 227), (343, S - 0.1, 227), (343, S - 0.1, 332), (213, S - 0.1, 332))
+    b.shape("trianglemesh", P=P, indices=I)
+    b.attribute_end()
+    for (lo, hi, ang, tr) in (((0, 0, 0), (165, 165, 165), -18.0, (130, 0.05, 65)), ((0, 0, 0), (165, 330, 165), 15.0, (265, 0.05, 295))):
+        b.attribute_begin()
+        b.translate(*tr)
+        b.rotate(ang, 0, 1, 0)
+        b.material("plastic", Kd=(0.5, 0.5, 0.5), Ks=(0.25, 0.25, 0.25), roughness=0.1)
+        P, I = box_mesh(lo, hi)
+        b.shape("trianglemesh", P=P, indices=I)
+        b.attribute_end()
+    flat = b.world_end()
+
+    def make(spp_=spp, res=(xres, yres), maxdepth_=maxdepth, sampler_=sampler, strategy="power", filt="gaussian"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=40.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    return SceneSetup("S2-cornell", flat, make, "Cornell box, quad area light (2 triangle lights), matte + plastic, power light sampling")
+
+
+def displaced_sphere_scene(nlong=1024, nlat=512, xres=1920, yres=1080, spp=512, maxdepth=5, sampler="sobol"):
+    """S3 / config C3: nlong*nlat*2 triangles (1 048 576 at the defaults) on a displaced sphere with
+    per-vertex normals, half plastic / half copper metal by octant parity, ground quad, one quad
+    area light + one point light."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.0, -3.6, 1.4), (0, 0, 0.05), (0, 0, 1))
+    P, I, N = displaced_sphere(nlong, nlat, 1.0, 0.1, 1234)
+    cen = (P[I[:, 0]] + P[I[:, 1]] + P[I[:, 2]]) / f32(3)
+    octant_parity = ((cen[:, 0] > 0).astype(int) + (cen[:, 1] > 0).astype(int) + (cen[:, 2] > 0).astype(int)) % 2
+    for par, (mat, kw) in enumerate((("plastic", dict(Kd=(0.25, 0.25, 0.25), Ks=(0.25, 0.25, 0.25), roughness=0.1)), ("metal", dict(roughness=0.01)))):
+        b.material(mat, **kw)
+        b.shape("trianglemesh", P=P, indices=I[octant_parity == par], N=N)
+    b.material("matte", Kd=(0.4, 0.4, 0.4))
+    Pq, Iq = quad((-30, -30, -1.15), (30, -30, -1.15), (30, 30, -1.15), (-30, 30, -1.15))
+    b.shape("trianglemesh", P=Pq, indices=Iq)
+    b.attribute_begin()
+    b.area_light_source("diffuse", L=(30, 30, 30))
+    b.material("matte", Kd=0.0)
+    Pl, Il = quad((-1.5, -1.5, 4.0), (-1.5, 1.5, 4.0), (1.5, 1.5, 4.0), (1.5, -1.5, 4.0))
+    b.shape("trianglemesh", P=Pl, indices=Il)
+    b.attribute_end()
+    # positioned with the CTM: the reference's `from` handling has the (P.x, P.y, P.x) quirk (point.rs:103)
+    b.attribute_begin()
+    b.translate(3.0, -4.0, 3.0)
+    b.light_source("point", I=(20, 18, 15))
+    b.attribute_end()
+    flat = b.world_end()
+
+    def make(spp_=spp, res=(xres, yres), maxdepth_=maxdepth, sampler_=sampler, strategy="power", filt="box"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=35.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    ntri = len(I) + 4
+    return SceneSetup(f"S3-displaced-sphere-{ntri}", flat, make,
+                      f"{ntri}-triangle displaced sphere (plastic/metal) + ground + quad area light + point light")
+
+
+def glass_knot_scene(nu=2048, nv=512, xres=1024, yres=1024, spp=2048, maxdepth=32, sampler="sobol"):
+    """S5 / config C5 stand-in: glass (eta 1.5) torus knot tube of nu*nv*2 triangles on a matte ground
+    under a small bright quad light."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.0, -7.5, 4.5), (0, 0, 0.6), (0, 0, 1))
+    u = np.arange(nu, dtype=np.float64) / nu * 2 * math.pi
+    p, q = 2, 3
+    rr = 2.0 + np.cos(q * u)
+    c = np.stack([rr * np.cos(p * u), rr * np.sin(p * u), -np.sin(q * u) * 1.0 + 1.6], axis=1) * np.array([0.8, 0.8, 0.8])
+    t = np.roll(c, -1, axis=0) - np.roll(c, 1, axis=0)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    up = np.array([0.0, 0.0, 1.0])
+    n1 = np.cross(t, up)
+    n1 /= np.linalg.norm(n1, axis=1, keepdims=True)
+    n2 = np.cross(t, n1)
+    v = np.arange(nv, dtype=np.float64) / nv * 2 * math.pi
+    ring = np.cos(v)[None, :, None] * n1[:, None, :] + np.sin(v)[None, :, None] * n2[:, None, :]
+    base = (c[:, None, :] + 0.32 * ring).reshape(-1, 3)
+    disp = fbm((base * 3.0).astype(f32), seed=77).astype(np.float64)[:, None]
+    P = (base + 0.03 * disp * ring.reshape(-1, 3)).astype(f32)
+    i = np.arange(nu)[:, None]
+    j = np.arange(nv)[None, :]
+    a = (i * nv + j).reshape(-1)
+    bb = (((i + 1) % nu) * nv + j).reshape(-1)
+    cc = (i * nv + (j + 1) % nv).reshape(-1)
+    dd = (((i + 1) % nu) * nv + (j + 1) % nv).reshape(-1)
+    I = np.stack([np.stack([a, bb, dd], 1), np.stack([a, dd, cc], 1)], axis=1).reshape(-1, 3).astype(np.uint32)
+    b.material("glass", index=1.5)
+    b.shape("trianglemesh", P=P, indices=I)
+    b.material("matte", Kd=(0.5, 0.5, 0.5))
+    Pq, Iq = quad((-30, -30, 0), (30, -30, 0), (30, 30, 0), (-30, 30, 0))
+    b.shape("trianglemesh", P=Pq, indices=Iq)
+    b.attribute_begin()
+    b.area_light_source("diffuse", L=(400, 400, 400))
+    b.material("matte", Kd=0.0)
+    Pl, Il = quad((-0.4, -0.4, 9.0), (-0.4, 0.4, 9.0), (0.4, 0.4, 9.0), (0.4, -0.4, 9.0))
+    b.shape("trianglemesh", P=Pl, indices=Il)
+    b.attribute_end()
+    flat = b.world_end()
+
+    def make(spp_=spp, res=(xres, yres), maxdepth_=maxdepth, sampler_=sampler, strategy="power", filt="box"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=40.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, rrthreshold=1.0, lightsamplestrategy=strategy)
+
+    return SceneSetup(f"S5-glass-knot-{len(I) + 4}", flat, make, "glass torus knot, caustic light, maxdepth 32")
+
+
+def small_mixed_scene(n=24, seed=5):
+    """Test-sized scene touching every material/light/shape kind on the hot path."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.0, -5.0, 2.0), (0, 0, 0.3), (0, 0, 1))
+    P, I, N = displaced_sphere(n, n // 2, 0.8, 0.08, seed)
+    mats = [("matte", dict(Kd=(0.6, 0.3, 0.2), sigma=20.0)), ("plastic", dict(Kd=(0.2, 0.3, 0.6), Ks=0.3, roughness=0.05)),
+            ("metal", dict(roughness=0.05)), ("glass", dict(index=1.5)), ("mirror", dict(Kr=0.8)), ("glass", dict(uroughness=0.1, vroughness=0.1))]
+    for k, (m, kw) in enumerate(mats):
+        b.attribute_begin()
+        b.translate(-3.0 + 1.2 * k, 0.3 * (k % 2), 0.0)
+        b.material(m, **kw)
+        if k % 2 == 0:
+            b.shape("trianglemesh", P=P, indices=I, N=N)
+        else:
+            b.shape("trianglemesh", P=P, indices=I)
+        b.attribute_end()
+    b.attribute_begin()
+    b.translate(0, 1.8, 0.2)
+    b.material("glass")
+    b.shape("sphere", radius=0.7)
+    b.attribute_end()
+    b.material("matte", Kd=(0.5, 0.5, 0.5))
+    Pq, Iq = quad((-10, -10, -0.9), (10, -10, -0.9), (10, 10, -0.9), (-10, 10, -0.9))
+    b.shape("trianglemesh", P=Pq, indices=Iq)
+    b.attribute_begin()
+    b.area_light_source("diffuse", L=(25, 25, 22))
+    Pl, Il = quad((-1, -1, 4.0), (-1, 1, 4.0), (1, 1, 4.0), (1, -1, 4.0))
+    b.shape("trianglemesh", P=Pl, indices=Il)
+    b.attribute_end()
+    b.attribute_begin()
+    b.translate(-3.0, -3.0, 3.0)
+    b.light_source("point", I=(8, 8, 8))
+    b.attribute_end()
+    b.light_source("distant", **{"from": (1, -1, 2), "to": (0, 0, 0), "L": (0.6, 0.6, 0.7)})
+    b.light_source("infinite", L=(0.15, 0.18, 0.25))
+    flat = b.world_end()
+
+    def make(spp_=16, res=(96, 64), maxdepth_=5, sampler_="sobol", strategy="power", filt="gaussian"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=45.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    return SceneSetup("mixed-small", flat, make, "all hot-path materials/lights/shapes at test size")
+
+
+# ---------------------------------------------------------------------------
+# ray batches
+# ---------------------------------------------------------------------------
+def rays_diffuse(flat, n, seed=7):
+    """B-diff: origins uniform in the world bound, directions uniform on the sphere."""
+    wb = flat.world_bound
+    u = _hash_floats(5 * n, seed).reshape(5, n)
+    lo, hi = wb[:3], wb[3:]
+    o = lo[None, :] + (hi - lo)[None, :] * u[:3].T
+    z = f32(1) - f32(2) * u[3]
+    r = np.sqrt(np.maximum(f32(0), f32(1) - z * z)).astype(f32)
+    phi = f32(2 * math.pi) * u[4]
+    d = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1).astype(f32)
+    return H.make_rays(o.astype(f32), d)
+
+
+def rays_shadow(flat, n, seed=11):
+    """B-shadow: segments between random points on random triangles (t_max = 1 - 1e-4, like
+    Interaction::spawn_rayto_interaction, interaction.rs:46-52)."""
+    nt = len(flat.tri_indices)
+    u = _hash_floats(8 * n, seed).reshape(8, n)
+
+    def pts(ua, ub, uc):
+        t = np.minimum((ua * nt).astype(np.int64), nt - 1)
+        idx = flat.tri_indices[t]
+        su = np.sqrt(ub)
+        b0, b1 = 1 - su, uc * su
+        p = (flat.vertex_p[idx[:, 0]] * b0[:, None] + flat.vertex_p[idx[:, 1]] * b1[:, None] + flat.vertex_p[idx[:, 2]] * (1 - b0 - b1)[:, None])
+        return p.astype(f32)
+
+    a, bpt = pts(u[0], u[1], u[2]), pts(u[3], u[4], u[5])
+    d = bpt - a
+    keep = (d * d).sum(1) > 0
+    return H.make_rays(a[keep], d[keep], t_max=f32(1.0) - f32(1e-4))
+
+
+def rays_camera(integ, sample=0, max_rays=None):
+    """B-cam: pinhole camera rays through pixel centres (host-side, for batch tests only)."""
+    film, cam = integ.film, integ.camera
+    x0, y0, x1, y1 = film.cropped_pixel_bounds
+    xs, ys = np.meshgrid(np.arange(x0, x1, dtype=f32) + f32(0.5), np.arange(y0, y1, dtype=f32) + f32(0.5))
+    pf = np.stack([xs.reshape(-1), ys.reshape(-1), np.zeros(xs.size, f32)], axis=1)
+    if max_rays:
+        pf = pf[:: max(1, len(pf) // max_rays)]
+    pc = cam.raster_to_camera.points(pf)
+    d = pc * (f32(1) / np.sqrt((pc * pc).sum(1, dtype=f32)))[:, None]
+    o = cam.camera_to_world.points(np.zeros((len(d), 3), f32))
+    return H.make_rays(o, cam.camera_to_world.vectors(d))
