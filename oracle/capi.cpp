@@ -141,3 +141,107 @@ void orc_efloat_op(int op, float av, float aerr, float bv, float berr, float* ou
 }
 
 }  // extern "C"
+
+#ifdef ORC_HAVE_RENDER
+extern "C" {
+
+// SamplerIntegrator::render.  stats_out[12] = camera_rays, intersection_tests, shadow_tests, zero_radiance,
+// direct_den, closest{nodes,prims,rays}, any{nodes,prims,rays}, reserved
+int orc_render(const pbrt_b200_scene_desc* sdesc, const pbrt_b200_render_desc* rd, float* rgbw, int nthreads, uint64_t* stats_out) {
+    RenderJob job;
+    setup_job(job, *sdesc, *rd);
+    RenderCounters rc;
+    render(job, rgbw, nthreads <= 0 ? orc_hardware_threads() : nthreads, &rc);
+    if (stats_out) {
+        uint64_t v[12] = {rc.camera_rays, rc.intersection_tests, rc.shadow_tests, rc.zero_radiance, rc.direct_den,
+                          rc.trav_closest.nodes_tested, rc.trav_closest.tris_tested, rc.trav_closest.rays,
+                          rc.trav_any.nodes_tested, rc.trav_any.tris_tested, rc.trav_any.rays, 0};
+        std::memcpy(stats_out, v, sizeof v);
+    }
+    return 0;
+}
+
+// Film::write_image arithmetic (film.rs:217-264) on an {r,g,b,w} buffer
+void orc_film_resolve(const float* rgbw, uint64_t npix, float scale, float* rgb) {
+    for (uint64_t i = 0; i < npix; ++i) {
+        const float* p = rgbw + 4 * i;
+        float xyz[3] = {0.412453f * p[0] + 0.357580f * p[1] + 0.180423f * p[2], 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2],
+                        0.019334f * p[0] + 0.119193f * p[1] + 0.950227f * p[2]};
+        float c[3] = {3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2], -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2],
+                      0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2]};
+        if (p[3] != 0.0f) { float inv = 1.0f / p[3]; for (int k = 0; k < 3; ++k) c[k] = std::fmax(c[k] * inv, 0.0f); }
+        for (int k = 0; k < 3; ++k) rgb[3 * i + k] = c[k] * scale;
+    }
+}
+
+// Sampler stream for one pixel: for sample s in [0, nsamples): camera sample (5 values) followed by
+// `n1d2d` repetitions of get_1d + get_2d (3 values).  out has nsamples * (5 + 3*n1d2d) floats.
+// The tile's sampler is cloned with `seed` and start_pixel()ed on every pixel in `prefix_pixels`
+// (x fastest) before (px,py), as the tile loop would (integrator.rs:302-322).
+int orc_sampler_stream(const pbrt_b200_sampler* sd, int64_t seed, const int* prefix_pixels, int n_prefix, int px, int py, int nsamples, int n1d2d, float* out) {
+    SamplerTables t; t.sobol32 = sd->sobol_matrices32; t.vdc = sd->vdc_matrices; t.vdc_inv = sd->vdc_matrices_inv;
+    std::unique_ptr<Sampler> base = make_sampler(*sd, t);
+    std::unique_ptr<Sampler> s = base->clone(seed);
+    for (int i = 0; i < n_prefix; ++i) s->start_pixel(prefix_pixels[2 * i], prefix_pixels[2 * i + 1]);
+    s->start_pixel(px, py);
+    size_t k = 0;
+    for (int i = 0; i < nsamples; ++i) {
+        CameraSample cs = s->get_camera_sample(px, py);
+        out[k++] = cs.pfilm.x; out[k++] = cs.pfilm.y; out[k++] = cs.time; out[k++] = cs.plens.x; out[k++] = cs.plens.y;
+        for (int j = 0; j < n1d2d; ++j) { out[k++] = s->get_1d(); P2 p = s->get_2d(); out[k++] = p.x; out[k++] = p.y; }
+        if (!s->start_next_sample()) break;
+    }
+    return (int)k;
+}
+
+float orc_sobol_sample_float(const uint32_t* sobol32, uint64_t a, int dim, uint32_t scramble) { SamplerTables t; t.sobol32 = sobol32; return sobol_sample_float(t, a, dim, scramble); }
+uint64_t orc_sobol_interval_to_index(const uint64_t* vdc, const uint64_t* vdc_inv, uint32_t m, uint64_t frame, int px, int py) {
+    SamplerTables t; t.vdc = vdc; t.vdc_inv = vdc_inv; return sobol_interval_to_index(t, m, frame, px, py);
+}
+float orc_radical_inverse(int base_index, uint64_t n) { return radical_inverse(base_index, n); }
+float orc_scrambled_radical_inverse(int base_index, uint64_t n) { const HaltonTables& T = HaltonTables::get(); return scrambled_radical_inverse(base_index, n, &T.perms[T.prime_sums[base_index]]); }
+uint64_t orc_inverse_radical_inverse(uint64_t base, uint64_t inverse, uint64_t ndigits) { return inverse_radical_inverse(base, inverse, ndigits); }
+void orc_halton_tables(uint32_t* primes1000, uint32_t* sums1000, uint16_t* perms, uint64_t* nperms) {
+    const HaltonTables& T = HaltonTables::get();
+    if (primes1000) std::memcpy(primes1000, T.primes.data(), 4000);
+    if (sums1000) std::memcpy(sums1000, T.prime_sums.data(), 4000);
+    if (perms) std::memcpy(perms, T.perms.data(), T.perms.size() * 2);
+    if (nperms) *nperms = T.perms.size();
+}
+void orc_zerotwo_matrices(uint32_t* vdc32, uint32_t* sobol32) { std::memcpy(vdc32, ZeroTwoMatrices::get().vdc, 128); std::memcpy(sobol32, ZeroTwoMatrices::get().sobol1, 128); }
+uint32_t orc_rng_u32(uint64_t seq, int use_seq, int skip) { RNG r; if (use_seq) r.set_sequence(seq); uint32_t v = 0; for (int i = 0; i <= skip; ++i) v = r.uniform_int32(); return v; }
+
+// Distribution1D (tests/sampling.rs:202-281): mode 0 discrete -> out {index, pdf}; mode 1 continuous -> out {x, pdf, offset}
+void orc_distribution1d(const float* func, int n, float u, int mode, float* out3) {
+    Distribution1D d(std::vector<Float>(func, func + n));
+    if (mode == 0) { Float pdf; size_t i = d.sample_discrete(u, &pdf); out3[0] = (float)i; out3[1] = pdf; out3[2] = d.func_int; }
+    else { Float pdf; size_t off; Float x = d.sample_continuous(u, &pdf, &off); out3[0] = x; out3[1] = pdf; out3[2] = (float)off; }
+}
+
+// BSDF of material `m` on a canonical frame (n = +z, dpdu = +x): f, pdf and sample_f.
+// in: wo[3], wi[3], u[2].  out: f[3], pdf, sampled f[3], sampled wi[3], sampled pdf, sampled flags, ncomp(non-specular)
+void orc_bsdf_eval(const pbrt_b200_material* m, const float* wo, const float* wi, const float* u, int flags, float* out13) {
+    SurfaceInteraction si;
+    si.n = si.sh_n = V3(0, 0, 1); si.dpdu = si.sh_dpdu = V3(1, 0, 0); si.dpdv = si.sh_dpdv = V3(0, 1, 0);
+    BSDF b;
+    compute_scattering_functions(*m, si, &b);
+    for (int i = 0; i < 13; ++i) out13[i] = 0.0f;
+    if (!b.valid) { out13[12] = -1.0f; return; }
+    V3 WO(wo[0], wo[1], wo[2]), WI(wi[0], wi[1], wi[2]);
+    Spectrum f = b.f(WO, WI, flags);
+    out13[0] = f.c[0]; out13[1] = f.c[1]; out13[2] = f.c[2]; out13[3] = b.pdf(WO, WI, flags);
+    V3 swi; Float spdf = 0.0f; int st = 0;
+    Spectrum sf = b.sample_f(WO, &swi, P2(u[0], u[1]), &spdf, flags, &st);
+    out13[4] = sf.c[0]; out13[5] = sf.c[1]; out13[6] = sf.c[2]; out13[7] = swi.x; out13[8] = swi.y; out13[9] = swi.z; out13[10] = spdf; out13[11] = (float)st;
+    out13[12] = (float)b.num_components(BSDF_ALL & ~BSDF_SPECULAR);
+}
+
+// PerspectiveCamera::generate_ray for one camera sample -> o[3], d[3]
+void orc_generate_ray(const pbrt_b200_camera* c, const float* cs5, float* out6) {
+    CameraSample cs; cs.pfilm = P2(cs5[0], cs5[1]); cs.time = cs5[2]; cs.plens = P2(cs5[3], cs5[4]);
+    Ray r = generate_ray(*c, cs);
+    out6[0] = r.o.x; out6[1] = r.o.y; out6[2] = r.o.z; out6[3] = r.d.x; out6[4] = r.d.y; out6[5] = r.d.z;
+}
+
+}  // extern "C"
+#endif

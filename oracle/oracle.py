@@ -2,6 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this."""
 import ctypes as C
+import importlib
 import subprocess
 from pathlib import Path
 
@@ -12,10 +13,14 @@ LIB = HERE / "liboracle.so"
 _lib = None
 
 
+def _H():
+    return importlib.import_module("pbrt-rust_b200.host")
+
+
 def build(force=False):
     srcs = list(HERE.glob("*.hpp")) + [HERE / "capi.cpp", HERE.parent / "include" / "pbrt_b200.h"]
     if force or not LIB.exists() or LIB.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
-        subprocess.run(["make", "-C", str(HERE), "-B" if force else "-s"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", str(HERE)] + (["-B"] if force else []), check=True, capture_output=True)
     return LIB
 
 
@@ -23,12 +28,32 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        _lib = C.CDLL(str(LIB))
-        _lib.orc_next_float_up.restype = C.c_float
-        _lib.orc_next_float_up.argtypes = [C.c_float]
-        _lib.orc_next_float_down.restype = C.c_float
-        _lib.orc_next_float_down.argtypes = [C.c_float]
-        _lib.orc_gamma.restype = C.c_float
+        L = C.CDLL(str(LIB))
+        for name in ("orc_next_float_up", "orc_next_float_down"):
+            getattr(L, name).restype = C.c_float
+            getattr(L, name).argtypes = [C.c_float]
+        L.orc_gamma.restype = C.c_float
+        L.orc_sobol_sample_float.restype = C.c_float
+        L.orc_sobol_sample_float.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32]
+        L.orc_sobol_interval_to_index.restype = C.c_uint64
+        L.orc_sobol_interval_to_index.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int]
+        L.orc_radical_inverse.restype = C.c_float
+        L.orc_radical_inverse.argtypes = [C.c_int, C.c_uint64]
+        L.orc_scrambled_radical_inverse.restype = C.c_float
+        L.orc_scrambled_radical_inverse.argtypes = [C.c_int, C.c_uint64]
+        L.orc_inverse_radical_inverse.restype = C.c_uint64
+        L.orc_inverse_radical_inverse.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        L.orc_rng_u32.restype = C.c_uint32
+        L.orc_rng_u32.argtypes = [C.c_uint64, C.c_int, C.c_int]
+        L.orc_film_resolve.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
+        L.orc_film_resolve.restype = None
+        L.orc_distribution1d.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.orc_find_interval.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.orc_triangle_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+        L.orc_sphere_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        L.orc_efloat_op.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.orc_sampler_stream.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib = L
     return _lib
 
 
@@ -37,8 +62,7 @@ def ptr(a):
 
 
 def bvh_build(prim_bounds, max_prims=4, split_method="sah"):
-    import importlib
-    H = importlib.import_module("pbrt-rust_b200.host")
+    H = _H()
     pb = np.ascontiguousarray(prim_bounds, np.float32).reshape(-1, 6)
     n = len(pb)
     nodes = np.zeros(max(2 * n - 1, 1), H.NODE_DTYPE)
@@ -49,8 +73,7 @@ def bvh_build(prim_bounds, max_prims=4, split_method="sah"):
 
 
 def intersect(flat, rays, nthreads=0, per_ray=False):
-    import importlib
-    H = importlib.import_module("pbrt-rust_b200.host")
+    H = _H()
     rays = np.ascontiguousarray(rays, H.RAY_DTYPE)
     hits = np.zeros(len(rays), H.HIT_DTYPE)
     counters = np.zeros(3, np.uint64)
@@ -61,11 +84,61 @@ def intersect(flat, rays, nthreads=0, per_ray=False):
 
 
 def intersect_p(flat, rays, nthreads=0):
-    import importlib
-    H = importlib.import_module("pbrt-rust_b200.host")
+    H = _H()
     rays = np.ascontiguousarray(rays, H.RAY_DTYPE)
     occ = np.zeros(len(rays), np.uint8)
     counters = np.zeros(3, np.uint64)
     d = flat.desc()
     lib().orc_intersect_p(C.byref(d), ptr(rays), C.c_uint64(len(rays)), ptr(occ), int(nthreads), ptr(counters))
     return occ.astype(bool), counters
+
+
+STAT_NAMES = ["camera_rays", "intersection_tests", "shadow_tests", "zero_radiance", "direct_den", "closest_nodes", "closest_prims", "closest_rays",
+              "any_nodes", "any_prims", "any_rays", "reserved"]
+
+
+def render(flat, integrator, nthreads=0, tile_range=None, sample_range=None, rgbw=None):
+    """SamplerIntegrator::render on the CPU oracle -> ({r,g,b,w} sums [npix,4], stats dict)."""
+    film = integrator.film
+    if rgbw is None:
+        rgbw = np.zeros((film.height * film.width, 4), np.float32)
+    sd = flat.desc()
+    rd = integrator.desc(tile_range, sample_range)
+    stats = np.zeros(12, np.uint64)
+    lib().orc_render(C.byref(sd), C.byref(rd), ptr(rgbw), int(nthreads), ptr(stats))
+    return rgbw, dict(zip(STAT_NAMES, (int(v) for v in stats)))
+
+
+def film_resolve(rgbw, scale=1.0):
+    rgbw = np.ascontiguousarray(rgbw, np.float32).reshape(-1, 4)
+    out = np.zeros((len(rgbw), 3), np.float32)
+    lib().orc_film_resolve(ptr(rgbw), len(rgbw), scale, ptr(out))
+    return out
+
+
+def render_image(flat, integrator, **kw):
+    rgbw, stats = render(flat, integrator, **kw)
+    film = integrator.film
+    return film_resolve(rgbw, film.scale).reshape(film.height, film.width, 3), stats
+
+
+def sampler_stream(integrator, seed, px, py, nsamples, n1d2d, prefix_pixels=()):
+    sd = integrator.sampler.desc(integrator.film)
+    pre = np.ascontiguousarray(np.array(prefix_pixels, np.int32).reshape(-1, 2))
+    out = np.zeros(nsamples * (5 + 3 * n1d2d), np.float32)
+    k = lib().orc_sampler_stream(C.byref(sd), int(seed), ptr(pre) if len(pre) else None, len(pre), int(px), int(py), int(nsamples), int(n1d2d), ptr(out))
+    return out[:k].reshape(-1, 5 + 3 * n1d2d)
+
+
+def bsdf_eval(material_row, wo, wi, u, flags=31):
+    m = np.array([material_row], dtype=_H().MATERIAL_DTYPE)
+    wo, wi, u = (np.ascontiguousarray(v, np.float32) for v in (wo, wi, u))
+    out = np.zeros(13, np.float32)
+    lib().orc_bsdf_eval(ptr(m), ptr(wo), ptr(wi), ptr(u), int(flags), ptr(out))
+    return out
+
+
+def rel_mse(img, ref):
+    """relMSE of SURVEY.md s8(d): mean over pixels/channels of (a-b)^2 / (b^2 + 1e-2)."""
+    a, b = np.asarray(img, np.float64), np.asarray(ref, np.float64)
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))

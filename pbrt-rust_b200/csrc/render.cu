@@ -1,7 +1,1165 @@
-// placeholder until the wavefront lands
+// Wavefront path tracer: SamplerIntegrator::render driving PathIntegrator::li
+// (core/integrator.rs:81-403, integrators/path.rs:79-222) split into kernels:
+//
+//   raygen         get_camera_sample + generate_ray (samplers on device)             K1
+//   trace_closest  BVHAccel::intersect for path rays, classify hit by material       K2 + K4
+//   shade<mat>     emission, BSDF assembly, light pick + light sample (shadow ray),  K5 + K6
+//                  MIS BSDF sample (MIS ray), BSDF sample for the next bounce, RR
+//   trace_any      BVHAccel::intersect_p for shadow rays, adds the light-sample term K3
+//   trace_mis      closest hit for the BSDF-sampled MIS ray, adds the BSDF-sample term K7
+//   finish         radiance sanity rule + FilmTile::add_sample                       K8
+//
+// All queues live in HBM as index arrays; every kernel is a persistent grid-stride loop over
+// a queue whose length is read from device memory, so a whole wave runs without host syncs.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
 #include "scene.cuh"
+#include "shading.cuh"
+#include "trace.cuh"
 #include "util.cuh"
-namespace pb { void render_release_scene_state(pbrt_b200_scene*) {} }
-extern "C" int pbrt_b200_render(pbrt_b200_scene*, const pbrt_b200_render_desc*, float*, pbrt_b200_render_stats*) {
-    return fail(PBRT_B200_ERR_UNSUPPORTED, "render: not built yet");
+
+using namespace pb;
+
+namespace pb {
+
+enum { Q_MATTE = 0, Q_PLASTIC = 1, Q_MIRROR = 2, Q_GLASS = 3, Q_METAL = 4, Q_NOMAT = 5, Q_MISS = 6, Q_COUNT = 7 };
+
+struct Counters {
+    uint32_t n_path;          // rays to trace this iteration
+    uint32_t n_next;          // rays for the next iteration
+    uint32_t n_shadow, n_mis, n_dead;
+    uint32_t n_mat[Q_COUNT];
+    uint32_t pad[4];
+    unsigned long long camera_rays, closest_rays, shadow_rays, zero_radiance;
+};
+
+struct Tiny1D { float func[2], cdf[3], func_int; };  // Distribution1D with two entries
+struct InfDistrib { Tiny1D cond[2], marg; };         // Distribution2D of a constant 1x1 env map (2x2 image)
+
+struct SamplerDev {
+    uint32_t kind, spp;
+    int sb[4];
+    // Sobol (samplers/sobol.rs:34-87)
+    int resolution, log2_resolution;
+    const uint32_t* sobol32;
+    const unsigned long long* vdc;
+    const unsigned long long* vdc_inv;
+    // Halton (samplers/halton.rs:63-166)
+    long long base_scales[2], base_exponents[2], mult_inverse[2];
+    unsigned long long sample_stride;
+    const uint16_t* perms;
+    const uint32_t* primes;
+    const uint32_t* prime_sums;
+    uint32_t n_halton_dims;
+};
+
+struct RenderDev {
+    DevScene scene;
+    pbrt_b200_camera camera;
+    SamplerDev sampler;
+    // film (core/film.rs)
+    int crop[4];
+    float filter_radius[2], inv_filter_radius[2];
+    float max_sample_luminance;
+    const float* filter_table;  // 256 floats
+    float4* film;               // {r,g,b,w} per cropped pixel
+    // integrator
+    int max_depth;
+    float rr_threshold;
+    int pixel_bounds[4];
+    // light distribution (core/lightdistrib.rs:20-83): uniform or power
+    const float* ld_func;
+    const float* ld_cdf;
+    float ld_func_int;
+    uint32_t n_lights;
+    const InfDistrib* inf_distrib;     // indexed by light
+    const uint32_t* infinite_lights;   // Scene.infinite_lights
+    uint32_t n_infinite;
+    // work decomposition (integrator.rs:274-279)
+    int ntx, nty;
+    uint32_t tile_begin, n_tiles_sel, sample_begin, n_samples_sel;
+    // path state, SoA over `capacity` slots
+    uint32_t capacity;
+    float4* ray;         // 2 x float4 per slot: {o, t_max}, {d, time}
+    uint4* hit;          // {slot, t, b0, b1}
+    float* hit_b2;
+    float4* L_eta;       // {L.rgb, etascale}
+    float4* beta_st;     // {beta.rgb, bits: bounces | specular_bounce << 16}
+    float2* pfilm;
+    unsigned long long* s_index;  // sampler: global sample index (Sobol / Halton)
+    uint32_t* s_dim;              // sampler: next dimension
+    uint32_t* pixel;              // x | y << 16 relative to sample bounds min
+    float4* sh_ray;      // shadow ray (2 x float4)
+    float4* sh_contrib;  // {rgb to add when unoccluded, -}
+    float4* mis_ray;     // MIS ray (2 x float4)
+    float4* mis_contrib; // {rgb factor (beta * f * |cos| * w / (scattpdf * lightselpdf)), light index bits}
+    uint32_t* q_path[2];
+    uint32_t* q_shadow;
+    uint32_t* q_mis;
+    uint32_t* q_dead;
+    uint32_t* q_mat[Q_COUNT];
+    Counters* cnt;
+};
+
+// ---------------------------------------------------------------------------
+// queue helpers: warp-aggregated append (one atomic per warp per queue)
+// ---------------------------------------------------------------------------
+PB_D void queue_push(uint32_t* q, uint32_t* counter, uint32_t value, bool pred) {
+    unsigned mask = __ballot_sync(__activemask(), pred);
+    if (!pred) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    q[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
+
+// ---------------------------------------------------------------------------
+// samplers on device
+// ---------------------------------------------------------------------------
+// core/lowdiscrepancy.rs:512-543
+PB_D unsigned long long sobol_interval_to_index(const SamplerDev& S, uint32_t m, unsigned long long frame, int px, int py) {
+    if (m == 0) return 0;
+    uint32_t m2 = m << 1;
+    unsigned long long index = frame << m2, delta = 0;
+    const unsigned long long* V = S.vdc + (m - 1) * 52;
+    for (int c = 0; frame != 0; frame >>= 1, ++c)
+        if (frame & 1) delta ^= __ldg(V + c);
+    unsigned long long b = ((unsigned long long)((uint32_t)px << m) | (unsigned long long)(long long)py) ^ delta;
+    const unsigned long long* VI = S.vdc_inv + (m - 1) * 52;
+    for (int c = 0; b != 0; b >>= 1, ++c)
+        if (b & 1) index ^= __ldg(VI + c);
+    return index;
+}
+// core/lowdiscrepancy.rs:549-569 + SobolSampler::sample_dimension (samplers/sobol.rs:69-87)
+PB_D float sobol_dimension(const SamplerDev& S, unsigned long long a, uint32_t dim, int px, int py) {
+    uint32_t v = 0;
+    const uint32_t* M = S.sobol32 + dim * 52;
+    for (; a != 0; a >>= 1, ++M)
+        if (a & 1) v ^= __ldg(M);
+    float s = fminf((float)v * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
+    if (dim == 0 || dim == 1) {
+        s = s * (float)S.resolution + (float)S.sb[dim];
+        s = clampf(s - (float)(dim == 0 ? px : py), 0.0f, PB_ONE_MINUS_EPSILON);
+    }
+    return s;
+}
+PB_D uint32_t reverse_bits32(uint32_t n) { return __brev(n); }  // lowdiscrepancy.rs:381-389
+PB_D unsigned long long reverse_bits64(unsigned long long n) {
+    return ((unsigned long long)__brev((uint32_t)n) << 32) | (unsigned long long)__brev((uint32_t)(n >> 32));
+}
+// radical_inverse / scrambled_radical_inverse, lowdiscrepancy.rs:398-414, 468-484
+PB_D float radical_inverse(const SamplerDev& S, uint32_t base_index, unsigned long long n) {
+    if (base_index == 0) return (float)reverse_bits64(n) * 5.421010862427522e-20f;  // 2^-64, no clamp
+    unsigned long long base = __ldg(S.primes + base_index);
+    float inv_base = 1.0f / (float)base, inv_basen = 1.0f;
+    unsigned long long rev = 0;
+    while (n != 0) {
+        unsigned long long next = n / base, digit = n - next * base;
+        rev = rev * base + digit;
+        inv_basen *= inv_base;
+        n = next;
+    }
+    return fminf((float)rev * inv_basen, PB_ONE_MINUS_EPSILON);
+}
+PB_D float scrambled_radical_inverse(const SamplerDev& S, uint32_t base_index, unsigned long long a) {
+    unsigned long long base = __ldg(S.primes + base_index);
+    const uint16_t* perm = S.perms + __ldg(S.prime_sums + base_index);
+    float inv_base = 1.0f / (float)base, inv_basen = 1.0f;
+    unsigned long long rev = 0;
+    while (a != 0) {
+        unsigned long long next = a / base, digit = a - next * base;
+        rev = rev * base + (unsigned long long)__ldg(perm + digit);
+        inv_basen *= inv_base;
+        a = next;
+    }
+    float res = inv_basen * ((float)rev + inv_base * (float)__ldg(perm) / (1.0f - inv_base));
+    return fminf(res, PB_ONE_MINUS_EPSILON);
+}
+PB_D long long mod_ll(long long a, long long b) { long long r = a - (a / b) * b; return r < 0 ? r + b : r; }
+PB_D unsigned long long inverse_radical_inverse(unsigned long long base, unsigned long long inverse, unsigned long long nd) {
+    unsigned long long index = 0;
+    for (unsigned long long i = 0; i < nd; ++i) { unsigned long long digit = inverse % base; inverse /= base; index = index * base + digit; }
+    return index;
+}
+// HaltonSampler::get_index_for_sample, halton.rs:124-152 (px,py are absolute pixel coordinates)
+PB_D unsigned long long halton_index(const SamplerDev& S, unsigned long long sample, int px, int py) {
+    unsigned long long off = 0;
+    if (S.sample_stride > 1 && !(px == 0 && py == 0)) {  // pixel_for_offset starts at (0,0) in the reference
+        long long pm0 = mod_ll(px, 128), pm1 = mod_ll(py, 128);
+        off += inverse_radical_inverse(2, (unsigned long long)pm0, (unsigned long long)S.base_exponents[0]) *
+               (S.sample_stride / (unsigned long long)S.base_scales[0]) * (unsigned long long)S.mult_inverse[0];
+        off += inverse_radical_inverse(3, (unsigned long long)pm1, (unsigned long long)S.base_exponents[1]) *
+               (S.sample_stride / (unsigned long long)S.base_scales[1]) * (unsigned long long)S.mult_inverse[1];
+        off %= S.sample_stride;
+    }
+    return off + sample * S.sample_stride;
+}
+PB_D float halton_dimension(const SamplerDev& S, unsigned long long index, uint32_t dim) {
+    if (dim == 0) return radical_inverse(S, 0, index >> (unsigned long long)S.base_exponents[0]);
+    if (dim == 1) return radical_inverse(S, 1, index / (unsigned long long)S.base_scales[1]);
+    return scrambled_radical_inverse(S, dim, index);
+}
+
+struct SampleCursor { unsigned long long index; uint32_t dim; int px, py; };  // absolute pixel
+PB_D float sample_dimension(const SamplerDev& S, const SampleCursor& c, uint32_t dim) {
+    return S.kind == PBRT_B200_SAMPLER_SOBOL ? sobol_dimension(S, c.index, dim, c.px, c.py) : halton_dimension(S, c.index, dim);
+}
+// GlobalSampler::get_1d / get_2d, core/sampler.rs:322-353 (no sample arrays requested by the path integrator)
+PB_D float get_1d(const SamplerDev& S, SampleCursor& c) { float r = sample_dimension(S, c, c.dim); c.dim += 1; return r; }
+PB_D float2 get_2d(const SamplerDev& S, SampleCursor& c) {
+    float y = sample_dimension(S, c, c.dim + 1);
+    float x = sample_dimension(S, c, c.dim);
+    c.dim += 2;
+    return make_float2(x, y);
+}
+
+// ---------------------------------------------------------------------------
+// film: FilmTile::add_sample (core/film.rs:292-331) with warp-aggregated atomics
+// ---------------------------------------------------------------------------
+PB_D void film_atomic_add(float4* film, uint32_t pix, float4 v, bool active) {
+    // lanes that target the same pixel are summed in-warp; one vector atomic per distinct pixel
+    unsigned amask = __ballot_sync(__activemask(), active);
+    if (!active) return;
+    unsigned peers = __match_any_sync(amask, pix);
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(peers) - 1;
+    if (peers != (1u << lane)) {
+        // segmented reduction over the peer set (rare: only with filters wider than a pixel)
+        float4 acc = v;
+        unsigned rest = peers & ~(1u << leader);
+        // every peer publishes; leader gathers
+        for (unsigned m = rest; m; m &= m - 1) {
+            int src = __ffs(m) - 1;
+            float x = __shfl_sync(peers, v.x, src), y = __shfl_sync(peers, v.y, src), z = __shfl_sync(peers, v.z, src), w = __shfl_sync(peers, v.w, src);
+            if (lane == leader) { acc.x += x; acc.y += y; acc.z += z; acc.w += w; }
+        }
+        v = acc;
+    }
+    if (lane == leader) atomicAdd(film + pix, v);
+}
+
+PB_D void film_add_sample(const RenderDev& R, float2 pfilm, rgb L, bool active) {
+    // all lanes of the warp walk the same (maximal) footprint loop so the aggregation can use shuffles
+    float rx = R.filter_radius[0], ry = R.filter_radius[1];
+    int p0x = 0, p0y = 0, p1x = 0, p1y = 0;
+    float dx = 0.f, dy = 0.f;
+    if (active) {
+        float ly = lum(L);
+        if (ly > R.max_sample_luminance) L = L * rgb(R.max_sample_luminance / ly);
+        dx = pfilm.x - 0.5f; dy = pfilm.y - 0.5f;
+        p0x = max((int)ceilf(dx - rx), R.crop[0]); p0y = max((int)ceilf(dy - ry), R.crop[1]);
+        p1x = min((int)floorf(dx + rx) + 1, R.crop[2]); p1y = min((int)floorf(dy + ry) + 1, R.crop[3]);
+    }
+    int nx = max(p1x - p0x, 0), ny = max(p1y - p0y, 0);
+    unsigned amask = __activemask();
+    int mx = nx, my = ny;
+    for (int o = 16; o; o >>= 1) { mx = max(mx, __shfl_xor_sync(amask, mx, o)); my = max(my, __shfl_xor_sync(amask, my, o)); }
+    const int width = R.crop[2] - R.crop[0];
+    for (int j = 0; j < my; ++j)
+        for (int i = 0; i < mx; ++i) {
+            bool on = active && i < nx && j < ny;
+            int x = p0x + i, y = p0y + j;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t pix = 0;
+            if (on) {
+                float fx = fabsf(((float)x - dx) * R.inv_filter_radius[0] * 16.0f);
+                float fy = fabsf(((float)y - dy) * R.inv_filter_radius[1] * 16.0f);
+                int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
+                float fw = __ldg(R.filter_table + iy * 16 + ix);
+                rgb c = L * rgb(1.0f) * rgb(fw);  // sample_weight = 1 (perspective.rs:141)
+                v = make_float4(c.r, c.g, c.b, fw);
+                pix = (uint32_t)((y - R.crop[1]) * width + (x - R.crop[0]));
+            }
+            film_atomic_add(R.film, pix, v, on);
+        }
+}
+
+// ---------------------------------------------------------------------------
+// K1: raygen
+// ---------------------------------------------------------------------------
+// PerspectiveCamera::generate_ray_differential (cameras/perspective.rs:120-179), main ray;
+// Transform::transform_ray (core/transform.rs:543-577)
+PB_D void generate_ray(const pbrt_b200_camera& c, float2 pfilm, float time_u, float2 plens, f3* o_out, f3* d_out, float* time_out) {
+    f3 pc = xf_point(c.raster_to_camera, f3(pfilm.x, pfilm.y, 0.0f));
+    f3 o(0.f, 0.f, 0.f), d = normalize(pc);
+    if (c.lens_radius > 0.0f) {
+        float2 pl = concentric_disk(plens);
+        pl.x *= c.lens_radius; pl.y *= c.lens_radius;
+        float ft = c.focal_distance / d.z;
+        f3 pfocus = o + d * ft;
+        o = f3(pl.x, pl.y, 0.0f);
+        d = normalize(pfocus - o);
+    }
+    *time_out = c.shutter_open * (1.0f - time_u) + c.shutter_close * time_u;  // lerp, pbrt.rs:136-145
+    f3 oerr;
+    f3 ow = xf_point_err(c.camera_to_world, o, &oerr);
+    f3 dw = xf_vector(c.camera_to_world, d);
+    float l2 = len2(dw);
+    if (l2 > 0.0f) {
+        float dt = dot(vabs(dw), oerr) / l2;
+        ow = ow + dw * dt;
+    }
+    *o_out = ow; *d_out = dw;
+}
+
+__global__ void __launch_bounds__(256) k_raygen(RenderDev R, unsigned long long item_base, uint32_t count) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((count + 31u) & ~31u); i += gridDim.x * blockDim.x) {
+        bool valid = i < count;
+        int x = 0, y = 0;
+        uint32_t sample = 0;
+        if (valid) {
+            // item = (sample, tile, pixel-in-tile); pixels of a tile are contiguous (x fastest, bounds.rs:263-276)
+            unsigned long long item = item_base + i;
+            uint32_t p = (uint32_t)(item & 255u);
+            unsigned long long rest = item >> 8;
+            uint32_t t = (uint32_t)(rest % R.n_tiles_sel) + R.tile_begin;
+            sample = (uint32_t)(rest / R.n_tiles_sel) + R.sample_begin;
+            int tx = t % R.ntx, ty = t / R.ntx;
+            x = R.sampler.sb[0] + tx * 16 + (int)(p & 15u);
+            y = R.sampler.sb[1] + ty * 16 + (int)(p >> 4);
+            valid = x < R.sampler.sb[2] && y < R.sampler.sb[3] && x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] &&
+                    y < R.pixel_bounds[3];
+        }
+        if (valid) {
+            SampleCursor c;
+            c.px = x; c.py = y; c.dim = 0;
+            c.index = (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL)
+                          ? sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, sample, x - R.sampler.sb[0], y - R.sampler.sb[1])
+                          : halton_index(R.sampler, sample, x, y);
+            // get_camera_sample, sampler.rs:170-180
+            float2 u = get_2d(R.sampler, c);
+            float2 pfilm = make_float2((float)x + u.x, (float)y + u.y);
+            float tu = get_1d(R.sampler, c);
+            float2 plens = get_2d(R.sampler, c);
+            f3 o, d;
+            float time;
+            generate_ray(R.camera, pfilm, tu, plens, &o, &d, &time);
+            R.ray[2 * i] = make_float4(o.x, o.y, o.z, PB_INF);
+            R.ray[2 * i + 1] = make_float4(d.x, d.y, d.z, time);
+            R.L_eta[i] = make_float4(0.f, 0.f, 0.f, 1.0f);
+            R.beta_st[i] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
+            R.pfilm[i] = pfilm;
+            R.s_index[i] = c.index;
+            R.s_dim[i] = c.dim;
+            R.pixel[i] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, valid);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
+        queue_push(R.q_path[0], &R.cnt->n_path, i, valid);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2/K4: closest-hit for path rays + classification by material
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_closest(RenderDev R, int parity) {
+    const uint32_t n = R.cnt->n_path;
+    const uint32_t* q = R.q_path[parity];
+    const uint32_t nround = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        bool valid = i < n;
+        uint32_t id = 0;
+        int bin = Q_MISS;
+        if (valid) {
+            id = q[i];
+            float4 a = R.ray[2 * id], b = R.ray[2 * id + 1];
+            RayHit h;
+            bool found = traverse<false>(R.scene, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, &h);
+            R.hit[id] = make_uint4(h.slot, __float_as_uint(h.t), __float_as_uint(h.b0), __float_as_uint(h.b1));
+            R.hit_b2[id] = h.b2;
+            if (found) {
+                int m = R.scene.prims[h.slot].material;
+                bin = m < 0 ? Q_NOMAT : (int)R.scene.materials[m].type;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < Q_COUNT; ++k) queue_push(R.q_mat[k], &R.cnt->n_mat[k], id, valid && bin == k);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// lights
+// ---------------------------------------------------------------------------
+PB_D uint32_t find_interval_cdf(const float* cdf, int size, float u) {  // pbrt.rs:184-204 with pred = cdf[i] <= u
+    int first = 0, len_ = size;
+    while (len_ > 0) {
+        int half = len_ >> 1, middle = first + half;
+        if (__ldg(cdf + middle) <= u) { first = middle + 1; len_ -= half + 1; } else len_ = half;
+    }
+    int r = first - 1;
+    return (uint32_t)(r < 0 ? 0 : (r > size - 2 ? size - 2 : r));
+}
+PB_D float tiny_sample_continuous(const Tiny1D& d, float u, float* pdf, int* off) {  // sampling.rs:36-63
+    int first = 0, len_ = 3;
+    while (len_ > 0) {
+        int half = len_ >> 1, middle = first + half;
+        if (d.cdf[middle] <= u) { first = middle + 1; len_ -= half + 1; } else len_ = half;
+    }
+    int o = first - 1; o = o < 0 ? 0 : (o > 1 ? 1 : o);
+    *off = o;
+    float du = u - d.cdf[o];
+    float diff = d.cdf[o + 1] - d.cdf[o];
+    if (diff > 0.0f) du /= diff;
+    *pdf = d.func_int > 0.0f ? d.func[o] / d.func_int : 0.0f;
+    return ((float)o + du) / 2.0f;
+}
+
+struct LightSample { rgb Li; f3 wi; float pdf; f3 p1, p1_err, p1_n; };
+
+// Triangle::sample + Shape::sample_interaction (shapes/triangle.rs:556-584, core/shape.rs:40-58)
+PB_D void triangle_light_sample(const DevScene& s, const pbrt_b200_light& l, f3 ref_p, float2 u, LightSample& r) {
+    float su0 = sqrtf(u.x);
+    float b0 = 1.0f - su0, b1 = u.y * su0;  // uniform_sample_triangle, sampling.rs:244-248
+    const uint32_t* idx = s.tri_indices + 3ull * l.shape_index;
+    uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
+    const float* P = s.vertex_p;
+    f3 p0(P[3 * i0], P[3 * i0 + 1], P[3 * i0 + 2]), p1(P[3 * i1], P[3 * i1 + 1], P[3 * i1 + 2]), p2(P[3 * i2], P[3 * i2 + 1], P[3 * i2 + 2]);
+    float b2 = 1.0f - b0 - b1;
+    f3 p = p0 * b0 + p1 * b1 + p2 * b2;
+    f3 n = normalize(cross(p1 - p0, p2 - p0));
+    if ((l.shape_flags & PBRT_B200_PRIM_HAS_N) && s.vertex_n) {
+        const float* N = s.vertex_n;
+        f3 ns = f3(N[3 * i0], N[3 * i0 + 1], N[3 * i0 + 2]) * b0 + f3(N[3 * i1], N[3 * i1 + 1], N[3 * i1 + 2]) * b1 +
+                f3(N[3 * i2], N[3 * i2 + 1], N[3 * i2 + 2]) * b2;
+        n = face_forward(n, ns);
+    } else if (((l.shape_flags & PBRT_B200_PRIM_REVERSE_ORIENTATION) != 0) != ((l.shape_flags & PBRT_B200_PRIM_SWAPS_HANDEDNESS) != 0)) {
+        n = n * -1.0f;
+    }
+    f3 pabs = vabs(p0 * b0) + vabs(p1 * b1) + vabs(p2 * b2);
+    r.p1 = p; r.p1_n = n; r.p1_err = pabs * gamma_n(6);
+    float pdf = 1.0f / l.area;
+    f3 wi = p - ref_p;
+    if (len2(wi) == 0.0f) pdf = 0.0f;
+    else {
+        wi = normalize(wi);
+        f3 dd = ref_p - p;
+        pdf *= len2(dd) / absdot(n, -wi);
+        if (isinf(pdf)) pdf = 0.0f;
+    }
+    r.pdf = pdf;
+}
+
+// Light::sample_li for every light kind on the hot path
+PB_D void light_sample_li(const RenderDev& R, uint32_t li, f3 ref_p, float2 u, LightSample& r) {
+    const pbrt_b200_light& l = R.scene.lights[li];
+    rgb L = rgb3(l.L);
+    r.p1_err = f3(0.f, 0.f, 0.f); r.p1_n = f3(0.f, 0.f, 0.f);
+    switch (l.type) {
+        case PBRT_B200_LIGHT_POINT: {  // lights/point.rs:53-69
+            f3 pl(l.pos[0], l.pos[1], l.pos[2]);
+            r.wi = normalize(pl - ref_p); r.pdf = 1.0f; r.p1 = pl;
+            r.Li = L / len2(pl - ref_p);
+            break;
+        }
+        case PBRT_B200_LIGHT_SPOT: {  // lights/spot.rs:46-59,70-85
+            f3 pl(l.pos[0], l.pos[1], l.pos[2]);
+            r.wi = normalize(pl - ref_p); r.pdf = 1.0f; r.p1 = pl;
+            f3 wl = normalize(xf_vector(l.world_to_light, -r.wi));
+            float ct = wl.z, fall;
+            if (ct < l.cos_total_width) fall = 0.0f;
+            else if (ct >= l.cos_falloff_start) fall = 1.0f;
+            else { float dl = (ct - l.cos_total_width) / (l.cos_falloff_start - l.cos_total_width); fall = (dl * dl) * (dl * dl); }
+            r.Li = L * fall / len2(pl - ref_p);
+            break;
+        }
+        case PBRT_B200_LIGHT_DISTANT: {  // lights/distant.rs:66-83
+            f3 w(l.dir[0], l.dir[1], l.dir[2]);
+            r.wi = w; r.pdf = 1.0f;
+            r.p1 = ref_p + w * (2.0f * R.scene.world_radius);
+            r.Li = L;
+            break;
+        }
+        case PBRT_B200_LIGHT_DIFFUSE: {  // lights/diffuse.rs:91-106
+            triangle_light_sample(R.scene, l, ref_p, u, r);
+            f3 dlt = r.p1 - ref_p;
+            if (r.pdf == 0.0f || len2(dlt) == 0.0f) { r.pdf = 0.0f; r.Li = rgb(0.0f); r.wi = f3(0.f, 0.f, 0.f); return; }
+            r.wi = normalize(dlt);
+            r.Li = (l.two_sided || dot(r.p1_n, -r.wi) > 0.0f) ? L : rgb(0.0f);  // AreaLight::l, diffuse.rs:68-75
+            break;
+        }
+        default: {  // PBRT_B200_LIGHT_INFINITE, lights/infinite.rs:141-170 with a constant map
+            const InfDistrib& D = R.inf_distrib[li];
+            float pm, pc;
+            int v, dummy;
+            float d1 = tiny_sample_continuous(D.marg, u.y, &pm, &v);
+            float d0 = tiny_sample_continuous(D.cond[v], u.x, &pc, &dummy);
+            float map_pdf = pc * pm;
+            if (map_pdf == 0.0f) { r.Li = rgb(0.0f); r.pdf = 0.0f; r.wi = f3(0.f, 0.f, 0.f); return; }
+            float theta = d1 * PB_PI, phi = d0 * 2.0f * PB_PI;
+            float ct = cosf(theta), st = sinf(theta), sp = sinf(phi), cp = cosf(phi);
+            r.wi = f3(st * cp, st * sp, ct);
+            r.pdf = map_pdf / (2.0f * PB_PI * PB_PI * st);
+            if (st == 0.0f) r.pdf = 0.0f;
+            r.p1 = ref_p + r.wi * (2.0f * R.scene.world_radius);
+            r.Li = L;
+            break;
+        }
+    }
+}
+
+// Shape::pdf_wi for a triangle light (core/shape.rs:63-82): re-intersects that one shape
+// (Triangle::intersect with s = None) and converts to solid angle with the SIGNED cosine.
+PB_D float triangle_light_pdf_wi(const DevScene& s, const pbrt_b200_light& l, const Surf& ref, f3 wi) {
+    f3 o = offset_ray_origin(ref.p, ref.p_error, ref.n, wi);
+    const uint32_t* idx = s.tri_indices + 3ull * l.shape_index;
+    const float* P = s.vertex_p;
+    uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
+    f3 p0(P[3 * i0], P[3 * i0 + 1], P[3 * i0 + 2]), p1(P[3 * i1], P[3 * i1 + 1], P[3 * i1 + 2]), p2(P[3 * i2], P[3 * i2 + 1], P[3 * i2 + 2]);
+    f3 ad = vabs(wi);
+    int kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
+    int kx = (kz + 1 == 3) ? 0 : kz + 1, ky = (kx + 1 == 3) ? 0 : kx + 1;
+    float dz = comp(wi, kz);
+    float Sx = -comp(wi, kx) / dz, Sy = -comp(wi, ky) / dz, Sz = 1.0f / dz;
+    float t, b0, b1, b2;
+    if (!triangle_test<true>(o, wi, PB_INF, p0, p1, p2, kx, ky, kz, Sx, Sy, Sz, &t, &b0, &b1, &b2)) return 0.0f;
+    float2 uv0, uv1, uv2;
+    fetch_uv(s, l.shape_flags, l.shape_index, &uv0, &uv1, &uv2);
+    if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) return 0.0f;
+    Surf ls = triangle_surface(s, p0, p1, p2, l.shape_flags, l.shape_index, wi, b0, b1, b2, false);
+    f3 dd = ref.p - ls.p;
+    float pdf = len2(dd) / (dot(ls.n, -wi) * l.area);
+    if (isinf(pdf)) pdf = 0.0f;
+    return pdf;
+}
+PB_D float light_pdf_li(const RenderDev& R, uint32_t li, const Surf& ref, f3 wi) {
+    const pbrt_b200_light& l = R.scene.lights[li];
+    if (l.type == PBRT_B200_LIGHT_DIFFUSE) return triangle_light_pdf_wi(R.scene, l, ref, wi);
+    if (l.type == PBRT_B200_LIGHT_INFINITE) {  // lights/infinite.rs:131-139, Distribution2D::pdf sampling.rs:131-143
+        float theta = acosf(clampf(wi.z, -1.0f, 1.0f));
+        float phi = atan2f(wi.y, wi.x);
+        if (phi < 0.0f) phi += 2.0f * PB_PI;
+        float st = sinf(theta);
+        if (st == 0.0f) return 0.0f;
+        const InfDistrib& D = R.inf_distrib[li];
+        float pu = phi * 0.15915494309189533577f * 2.0f, pv = theta * PB_INV_PI * 2.0f;
+        int iu = (pu != pu || pu <= 0.0f) ? 0 : (int)fminf(pu, 1.0e9f), iv = (pv != pv || pv <= 0.0f) ? 0 : (int)fminf(pv, 1.0e9f);
+        iu = min(max(iu, 0), 1); iv = min(max(iv, 0), 1);
+        return (D.cond[iv].func[iu] / D.marg.func_int) / (2.0f * PB_PI * PB_PI * st);
+    }
+    return 0.0f;
+}
+PB_D bool is_delta_light(const pbrt_b200_light& l) { return l.type == PBRT_B200_LIGHT_POINT || l.type == PBRT_B200_LIGHT_DISTANT || l.type == PBRT_B200_LIGHT_SPOT; }
+
+// ---------------------------------------------------------------------------
+// K5/K6: shade
+// ---------------------------------------------------------------------------
+PB_D void store_ray(float4* rays, uint32_t id, f3 o, f3 d, float t_max, float time) {
+    rays[2 * id] = make_float4(o.x, o.y, o.z, t_max);
+    rays[2 * id + 1] = make_float4(d.x, d.y, d.z, time);
+}
+
+template <int BIN>
+__global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
+    const uint32_t n = R.cnt->n_mat[BIN];
+    const uint32_t* q = R.q_mat[BIN];
+    uint32_t* q_next = R.q_path[parity ^ 1];
+    const uint32_t nround = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        bool valid = i < n;
+        bool push_next = false, push_shadow = false, push_mis = false, push_dead = false, zero_rad = false;
+        uint32_t id = 0;
+        if (valid) {
+            id = q[i];
+            float4 ra = R.ray[2 * id], rb = R.ray[2 * id + 1];
+            f3 ro(ra.x, ra.y, ra.z), rd(rb.x, rb.y, rb.z);
+            float time = rb.w;
+            float4 Le = R.L_eta[id], bs = R.beta_st[id];
+            rgb L(Le.x, Le.y, Le.z), beta(bs.x, bs.y, bs.z);
+            float etascale = Le.w;
+            uint32_t st = __float_as_uint(bs.w);
+            uint32_t bounces = st & 0xffffu;
+            bool specular_bounce = (st >> 16) & 1u;
+            if (BIN == Q_MISS) {
+                // path.rs:106-120: escaped ray
+                if (bounces == 0 || specular_bounce)
+                    for (uint32_t k = 0; k < R.n_infinite; ++k) L = L + rgb3(R.scene.lights[R.infinite_lights[k]].L) * beta;
+                R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                push_dead = true;
+            } else {
+                uint4 h = R.hit[id];
+                uint32_t fl;
+                Surf si = surface_at(R.scene, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
+                const pbrt_b200_prim pr = R.scene.prims[h.x];
+                // SurfaceInteraction::le, interaction.rs:344-349 + AreaLight::l, diffuse.rs:68-75
+                if ((bounces == 0 || specular_bounce) && pr.area_light >= 0) {
+                    const pbrt_b200_light& al = R.scene.lights[pr.area_light];
+                    if (al.two_sided || dot(si.n, -rd) > 0.0f) L = L + rgb3(al.L) * beta;
+                }
+                if (bounces >= (uint32_t)R.max_depth) {
+                    R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                    push_dead = true;
+                } else {
+                    Bsdf bsdf;
+                    bsdf.valid = false;
+                    if (BIN != Q_NOMAT) material_bsdf(R.scene.materials[pr.material], si, bsdf);
+                    if (!bsdf.valid) {
+                        // path.rs:124-129: skip the surface, bounces NOT incremented
+                        f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
+                        store_ray(R.ray, id, o, rd, PB_INF, time);
+                        R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                        push_next = true;
+                    } else {
+                        SampleCursor c;
+                        c.index = R.s_index[id]; c.dim = R.s_dim[id];
+                        uint32_t pxy = R.pixel[id];
+                        c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
+                        const int NONSPEC = BX_ALL & ~BX_SPECULAR;
+                        // ---- uniform_sample_onelight + estimate_direct, integrator.rs:81-237
+                        if (bsdf_count(bsdf, NONSPEC) > 0 && R.n_lights > 0) {
+                            float u1 = get_1d(R.sampler, c);
+                            uint32_t ln = find_interval_cdf(R.ld_cdf, (int)R.n_lights + 1, u1);  // Distribution1D::sample_discrete
+                            float selpdf = R.ld_func_int > 0.0f ? __ldg(R.ld_func + ln) / (R.ld_func_int * (float)R.n_lights) : 0.0f;
+                            bool zero = true;
+                            if (selpdf != 0.0f) {
+                                float2 ulight = get_2d(R.sampler, c);
+                                float2 uscatt = get_2d(R.sampler, c);
+                                const pbrt_b200_light& light = R.scene.lights[ln];
+                                bool delta = is_delta_light(light);
+                                LightSample ls;
+                                light_sample_li(R, ln, si.p, ulight, ls);
+                                float scattpdf = 0.0f;
+                                if (ls.pdf > 0.0f && !is_black(ls.Li)) {
+                                    rgb f = bsdf_f(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
+                                    scattpdf = bsdf_pdf(bsdf, si.wo, ls.wi, NONSPEC);
+                                    if (!is_black(f)) {
+                                        // VisibilityTester::unoccluded -> spawn_rayto_interaction, interaction.rs:46-52
+                                        f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
+                                        f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
+                                        f3 d = tg - o;
+                                        rgb Ld = delta ? f * ls.Li / ls.pdf : f * ls.Li * power_heuristic(ls.pdf, scattpdf) / ls.pdf;
+                                        rgb add = beta * (Ld / selpdf);
+                                        store_ray(R.sh_ray, id, o, d, 1.0f - PB_SHADOW_EPSILON, time);
+                                        R.sh_contrib[id] = make_float4(add.r, add.g, add.b, 0.f);
+                                        push_shadow = true;
+                                        zero = false;
+                                    }
+                                }
+                                if (!delta) {
+                                    f3 wi(0.f, 0.f, 0.f);
+                                    int stype = 0;
+                                    rgb f = bsdf_sample(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
+                                    f = f * absdot(wi, si.sh_n);
+                                    if (!is_black(f) && scattpdf > 0.0f) {
+                                        float weight = 1.0f;
+                                        bool go = true;
+                                        if (!(stype & BX_SPECULAR)) {
+                                            float lpdf = light_pdf_li(R, ln, si, wi);
+                                            if (lpdf == 0.0f) go = false;
+                                            else weight = power_heuristic(scattpdf, lpdf);
+                                        }
+                                        if (go) {
+                                            f3 o = offset_ray_origin(si.p, si.p_error, si.n, wi);
+                                            rgb fac = beta * (f * weight / scattpdf / selpdf);
+                                            store_ray(R.mis_ray, id, o, wi, PB_INF, time);
+                                            R.mis_contrib[id] = make_float4(fac.r, fac.g, fac.b, __uint_as_float(ln));
+                                            push_mis = true;
+                                            zero = false;
+                                        }
+                                    }
+                                }
+                            }
+                            zero_rad = zero;
+                        }
+                        // ---- sample the BSDF for the next direction, path.rs:147-174
+                        f3 wo = -rd, wi(0.f, 0.f, 0.f);
+                        float pdf = 0.0f;
+                        int flags = 0;
+                        float2 ub = get_2d(R.sampler, c);
+                        rgb f = bsdf_sample(bsdf, wo, &wi, ub, &pdf, BX_ALL, &flags);
+                        bool alive = !(is_black(f) || pdf == 0.0f);
+                        if (alive) {
+                            beta = beta * (f * absdot(wi, si.sh_n) / pdf);
+                            specular_bounce = (flags & BX_SPECULAR) != 0;
+                            if ((flags & BX_SPECULAR) && (flags & BX_TRANSMISSION)) {
+                                float eta = bsdf.eta;
+                                etascale *= (dot(wo, si.n) > 0.0f) ? eta * eta : 1.0f / (eta * eta);
+                            }
+                            f3 o = offset_ray_origin(si.p, si.p_error, si.n, wi);
+                            // Russian roulette, path.rs:206-214
+                            rgb rrbeta = beta * etascale;
+                            float mc = max_comp(rrbeta);
+                            if (mc < R.rr_threshold && bounces > 3) {
+                                float qv = fmaxf(1.0f - mc, 0.05f);
+                                if (get_1d(R.sampler, c) < qv) alive = false;
+                                else beta = beta / (1.0f - qv);
+                            }
+                            if (alive) {
+                                store_ray(R.ray, id, o, wi, PB_INF, time);
+                                bounces += 1;
+                                R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(bounces | (specular_bounce ? 0x10000u : 0u)));
+                                push_next = true;
+                            }
+                        }
+                        if (!alive) push_dead = true;
+                        R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                        R.s_dim[id] = c.dim;
+                    }
+                }
+            }
+        }
+        {
+            unsigned zm = __ballot_sync(__activemask(), zero_rad);
+            if (zm && (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&R.cnt->zero_radiance, (unsigned long long)__popc(zm));
+        }
+        queue_push(q_next, &R.cnt->n_next, id, push_next);
+        queue_push(R.q_shadow, &R.cnt->n_shadow, id, push_shadow);
+        queue_push(R.q_mis, &R.cnt->n_mis, id, push_mis);
+        queue_push(R.q_dead, &R.cnt->n_dead, id, push_dead);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: shadow rays
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_shadow(RenderDev R) {
+    const uint32_t n = R.cnt->n_shadow;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t id = R.q_shadow[i];
+        float4 a = R.sh_ray[2 * id], b = R.sh_ray[2 * id + 1];
+        RayHit h;
+        if (!traverse<true>(R.scene, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, &h)) {
+            float4 c = R.sh_contrib[id];
+            float4 L = R.L_eta[id];
+            L.x += c.x; L.y += c.y; L.z += c.z;
+            R.L_eta[id] = L;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K7: MIS rays (estimate_direct's BSDF-sampled branch, integrator.rs:205-234)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_mis(RenderDev R) {
+    const uint32_t n = R.cnt->n_mis;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t id = R.q_mis[i];
+        float4 a = R.mis_ray[2 * id], b = R.mis_ray[2 * id + 1];
+        f3 o(a.x, a.y, a.z), d(b.x, b.y, b.z);
+        RayHit h;
+        bool found = traverse<false>(R.scene, o, d, a.w, &h);
+        float4 c = R.mis_contrib[id];
+        uint32_t ln = __float_as_uint(c.w);
+        rgb li(0.0f);
+        if (found) {
+            const pbrt_b200_prim pr = R.scene.prims[h.slot];
+            if (pr.area_light == (int)ln) {  // Arc::ptr_eq(light, hit primitive's area light)
+                uint32_t fl;
+                Surf ls = surface_at(R.scene, h.slot, o, d, h.t, h.b0, h.b1, h.b2, &fl);
+                const pbrt_b200_light& al = R.scene.lights[ln];
+                if (al.two_sided || dot(ls.n, -d) > 0.0f) li = rgb3(al.L);
+            }
+        } else {
+            const pbrt_b200_light& l = R.scene.lights[ln];
+            if (l.type == PBRT_B200_LIGHT_INFINITE) li = rgb3(l.L);  // light.le(ray)
+        }
+        if (!is_black(li)) {
+            float4 L = R.L_eta[id];
+            L.x += c.x * li.r; L.y += c.y * li.g; L.z += c.z * li.b;
+            R.L_eta[id] = L;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K8: finished paths -> film
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finish(RenderDev R) {
+    const uint32_t n = R.cnt->n_dead;
+    const uint32_t nround = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        bool valid = i < n;
+        rgb L(0.0f);
+        float2 pf = make_float2(0.f, 0.f);
+        if (valid) {
+            uint32_t id = R.q_dead[i];
+            float4 Le = R.L_eta[id];
+            L = rgb(Le.x, Le.y, Le.z);
+            pf = R.pfilm[id];
+            // integrator.rs:350-368: NaN / negative / infinite luminance => black
+            float y = lum(L);
+            if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
+            else if (y < -1.0e-5f) L = rgb(0.0f);
+            else if (isinf(y)) L = rgb(0.0f);
+        }
+        film_add_sample(R, pf, L, valid);
+    }
+}
+
+// single-thread bookkeeping between iterations: roll queue counters, accumulate stats
+__global__ void k_iter_end(Counters* c) {
+    c->closest_rays += (unsigned long long)c->n_path + c->n_mis;
+    c->shadow_rays += c->n_shadow;
+    c->n_path = c->n_next;
+    c->n_next = 0; c->n_shadow = 0; c->n_mis = 0; c->n_dead = 0;
+    for (int k = 0; k < Q_COUNT; ++k) c->n_mat[k] = 0;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct RenderBuffers {
+    std::vector<void*> allocs;
+    uint32_t capacity = 0;
+    RenderDev dev;
+    ~RenderBuffers() { for (void* p : allocs) cudaFree(p); }
+};
+
+struct SceneRenderState {  // cached per scene: light tables
+    float* ld_func = nullptr; float* ld_cdf = nullptr; float ld_func_int = 0;
+    InfDistrib* inf = nullptr; uint32_t* inf_list = nullptr; uint32_t n_inf = 0;
+    int strategy = -1;
+    // Halton tables (shared by all renders of the scene's device)
+    uint16_t* perms = nullptr; uint32_t* primes = nullptr; uint32_t* prime_sums = nullptr; uint32_t n_halton_dims = 0;
+    // Sobol tables copied to the device
+    uint32_t* sobol32 = nullptr; unsigned long long* vdc = nullptr; unsigned long long* vdc_inv = nullptr;
+    const void* sobol_src = nullptr;
+    float* filter_table = nullptr;
+    RenderBuffers* buffers = nullptr;
+};
+
+void render_release_scene_state(pbrt_b200_scene* sc) {
+    SceneRenderState* st = reinterpret_cast<SceneRenderState*>(sc->light_distrib);
+    if (!st) return;
+    cudaFree(st->ld_func); cudaFree(st->ld_cdf); cudaFree(st->inf); cudaFree(st->inf_list);
+    cudaFree(st->perms); cudaFree(st->primes); cudaFree(st->prime_sums);
+    cudaFree(st->sobol32); cudaFree(st->vdc); cudaFree(st->vdc_inv); cudaFree(st->filter_table);
+    delete st->buffers;
+    delete st;
+    sc->light_distrib = nullptr;
+}
+
+}  // namespace pb
+
+namespace {
+
+// Distribution1D::new, core/sampling.rs:13-33
+void make_distribution(const std::vector<float>& func, std::vector<float>& cdf, float* func_int) {
+    size_t n = func.size();
+    cdf.assign(n + 1, 0.0f);
+    for (size_t i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / (float)n;
+    *func_int = cdf[n];
+    if (*func_int == 0.0f) { for (size_t i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n; }
+    else { for (size_t i = 1; i < n + 1; ++i) cdf[i] /= *func_int; }
+}
+Tiny1D make_tiny(float f0, float f1) {
+    std::vector<float> cdf; float fi;
+    make_distribution({f0, f1}, cdf, &fi);
+    Tiny1D t; t.func[0] = f0; t.func[1] = f1; t.cdf[0] = cdf[0]; t.cdf[1] = cdf[1]; t.cdf[2] = cdf[2]; t.func_int = fi;
+    return t;
+}
+float lum_host(const float* c) { return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]; }
+
+// PCG32 + shuffle for compute_radical_inverse_permutations (core/rng.rs:25-76, sampling.rs:178-186,
+// lowdiscrepancy.rs:359-378)
+struct Pcg32 {
+    uint64_t state = 0x853c49e6748fea9bULL, inc = 0xda3e39cb94b95bdbULL;
+    uint32_t next() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27), rot = (uint32_t)(old >> 59);
+        return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+    }
+    uint32_t bounded(uint32_t b) { uint32_t th = (~b + 1u) % b; for (;;) { uint32_t r = next(); if (r >= th) return r % b; } }
+};
+
+template <typename T> int to_device(const std::vector<T>& h, T** d) {
+    *d = nullptr;
+    if (h.empty()) return PBRT_B200_OK;
+    PB_CUDA_TRY(cudaMalloc((void**)d, h.size() * sizeof(T)));
+    PB_CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return PBRT_B200_OK;
+}
+
+int prepare_scene_state(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, const std::vector<pbrt_b200_light>& lights, SceneRenderState** out) {
+    SceneRenderState* st = reinterpret_cast<SceneRenderState*>(sc->light_distrib);
+    if (!st) { st = new SceneRenderState(); sc->light_distrib = st; }
+    int rc;
+    const size_t nl = lights.size();
+    if (st->strategy != (int)rd->integrator.light_sample_strategy) {
+        cudaFree(st->ld_func); cudaFree(st->ld_cdf); cudaFree(st->inf); cudaFree(st->inf_list);
+        st->ld_func = st->ld_cdf = nullptr; st->inf = nullptr; st->inf_list = nullptr;
+        // create_light_sample_distribution, core/lightdistrib.rs:20-31 ("spatial" is not built yet: DESIGN.md)
+        std::vector<float> func(nl, 1.0f), cdf;
+        const float wr = sc->dev.world_radius, PI = 3.14159265358979323846f;
+        bool uniform = rd->integrator.light_sample_strategy == PBRT_B200_LIGHTS_UNIFORM || nl == 1;
+        std::vector<InfDistrib> inf(nl);
+        std::vector<uint32_t> inf_list;
+        for (size_t i = 0; i < nl; ++i) {
+            const pbrt_b200_light& l = lights[i];
+            float p[3];
+            for (int k = 0; k < 3; ++k) {
+                switch (l.type) {  // Light::power
+                    case PBRT_B200_LIGHT_POINT: p[k] = l.L[k] * 4.0f * PI; break;
+                    case PBRT_B200_LIGHT_DISTANT: p[k] = l.L[k] * PI * wr * wr; break;
+                    case PBRT_B200_LIGHT_SPOT: p[k] = l.L[k] * 2.0f * PI * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width)); break;
+                    case PBRT_B200_LIGHT_DIFFUSE: p[k] = l.L[k] * l.area * PI; break;
+                    default: p[k] = l.L[k] * wr * wr * PI; break;
+                }
+            }
+            if (!uniform) func[i] = lum_host(p);
+            if (l.type == PBRT_B200_LIGHT_INFINITE) {
+                inf_list.push_back((uint32_t)i);
+                float y = lum_host(l.L);
+                float s0 = sinf(PI * (0.0f + 0.5f) / 2.0f), s1 = sinf(PI * (1.0f + 0.5f) / 2.0f);
+                inf[i].cond[0] = make_tiny(y * s0, y * s0);
+                inf[i].cond[1] = make_tiny(y * s1, y * s1);
+                inf[i].marg = make_tiny(inf[i].cond[0].func_int, inf[i].cond[1].func_int);
+            }
+        }
+        make_distribution(func, cdf, &st->ld_func_int);
+        if ((rc = to_device(func, &st->ld_func))) return rc;
+        if ((rc = to_device(cdf, &st->ld_cdf))) return rc;
+        if ((rc = to_device(inf, &st->inf))) return rc;
+        if ((rc = to_device(inf_list, &st->inf_list))) return rc;
+        st->n_inf = (uint32_t)inf_list.size();
+        st->strategy = (int)rd->integrator.light_sample_strategy;
+    }
+    if (rd->sampler.kind == PBRT_B200_SAMPLER_SOBOL && st->sobol_src != rd->sampler.sobol_matrices32) {
+        if (!rd->sampler.sobol_matrices32 || !rd->sampler.vdc_matrices || !rd->sampler.vdc_matrices_inv)
+            return fail(PBRT_B200_ERR_INVALID, "render: the Sobol sampler needs sobol_matrices32, vdc_matrices and vdc_matrices_inv");
+        cudaFree(st->sobol32); cudaFree(st->vdc); cudaFree(st->vdc_inv);
+        PB_CUDA_TRY(cudaMalloc((void**)&st->sobol32, 1024 * 52 * 4));
+        PB_CUDA_TRY(cudaMalloc((void**)&st->vdc, 25 * 52 * 8));
+        PB_CUDA_TRY(cudaMalloc((void**)&st->vdc_inv, 26 * 52 * 8));
+        PB_CUDA_TRY(cudaMemcpy(st->sobol32, rd->sampler.sobol_matrices32, 1024 * 52 * 4, cudaMemcpyHostToDevice));
+        PB_CUDA_TRY(cudaMemcpy(st->vdc, rd->sampler.vdc_matrices, 25 * 52 * 8, cudaMemcpyHostToDevice));
+        PB_CUDA_TRY(cudaMemcpy(st->vdc_inv, rd->sampler.vdc_matrices_inv, 26 * 52 * 8, cudaMemcpyHostToDevice));
+        st->sobol_src = rd->sampler.sobol_matrices32;
+    }
+    if (rd->sampler.kind == PBRT_B200_SAMPLER_HALTON && !st->perms) {
+        const uint32_t N = 1000;  // PRIME_TABLE_SIZE, lowdiscrepancy.rs:9
+        std::vector<uint32_t> primes, sums;
+        for (uint32_t c = 2; primes.size() < N; ++c) {
+            bool ok = true;
+            for (uint32_t p : primes) { if (p * p > c) break; if (c % p == 0) { ok = false; break; } }
+            if (ok) primes.push_back(c);
+        }
+        uint32_t total = 0;
+        for (uint32_t p : primes) { sums.push_back(total); total += p; }
+        std::vector<uint16_t> perms(total);
+        Pcg32 rng;
+        size_t off = 0;
+        for (uint32_t i = 0; i < N; ++i) {
+            for (uint32_t j = 0; j < primes[i]; ++j) perms[off + j] = (uint16_t)j;
+            for (uint32_t k = 0; k < primes[i]; ++k) { uint32_t other = k + rng.bounded(primes[i] - k); std::swap(perms[off + k], perms[off + other]); }
+            off += primes[i];
+        }
+        if ((rc = to_device(perms, &st->perms))) return rc;
+        if ((rc = to_device(primes, &st->primes))) return rc;
+        if ((rc = to_device(sums, &st->prime_sums))) return rc;
+        st->n_halton_dims = N;
+    }
+    if (!st->filter_table) PB_CUDA_TRY(cudaMalloc((void**)&st->filter_table, 256 * sizeof(float)));
+    PB_CUDA_TRY(cudaMemcpy(st->filter_table, rd->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice));
+    *out = st;
+    return PBRT_B200_OK;
+}
+
+template <typename T> int dev_alloc(RenderBuffers* rb, T** p, size_t count) {
+    PB_CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+    rb->allocs.push_back(*p);
+    return PBRT_B200_OK;
+}
+
+int ensure_buffers(SceneRenderState* st, uint32_t capacity) {
+    if (st->buffers && st->buffers->capacity >= capacity) return PBRT_B200_OK;
+    delete st->buffers;
+    st->buffers = new RenderBuffers();
+    RenderBuffers* rb = st->buffers;
+    RenderDev& d = rb->dev;
+    std::memset(&d, 0, sizeof d);
+    int rc;
+#define A(ptr, n) if ((rc = dev_alloc(rb, &ptr, (size_t)(n)))) return rc
+    A(d.ray, 2 * (size_t)capacity); A(d.hit, capacity); A(d.hit_b2, capacity); A(d.L_eta, capacity); A(d.beta_st, capacity); A(d.pfilm, capacity);
+    A(d.s_index, capacity); A(d.s_dim, capacity); A(d.pixel, capacity);
+    A(d.sh_ray, 2 * (size_t)capacity); A(d.sh_contrib, capacity); A(d.mis_ray, 2 * (size_t)capacity); A(d.mis_contrib, capacity);
+    A(d.q_path[0], capacity); A(d.q_path[1], capacity); A(d.q_shadow, capacity); A(d.q_mis, capacity); A(d.q_dead, capacity);
+    for (int k = 0; k < Q_COUNT; ++k) A(d.q_mat[k], capacity);
+    A(d.cnt, 1);
+#undef A
+    rb->capacity = capacity;
+    return PBRT_B200_OK;
+}
+
+long long ext_gcd(long long a, long long b, long long* x, long long* y) {  // halton.rs:19-27
+    if (b == 0) { *x = 1; *y = 0; return a; }
+    long long d = a / b, r1, r2;
+    long long g = ext_gcd(b, a % b, &r1, &r2);
+    *x = r2; *y = r1 - d * r2;
+    return g;
+}
+long long mult_inverse(long long a, long long n) { long long x, y; ext_gcd(a, n, &x, &y); long long r = x - (x / n) * n; return r < 0 ? r + n : r; }
+
+}  // namespace
+
+extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, float* rgbw_out, pbrt_b200_render_stats* stats) {
+    if (!sc || !rd || !rgbw_out) return fail(PBRT_B200_ERR_INVALID, "render: null argument");
+    if (rd->sampler.kind > PBRT_B200_SAMPLER_HALTON)
+        return fail(PBRT_B200_ERR_UNSUPPORTED, "render: sampler not on the device path yet (sobol, halton)");
+    if (rd->sampler.samples_per_pixel == 0) return fail(PBRT_B200_ERR_INVALID, "render: samples_per_pixel is 0");
+    if (rd->integrator.light_sample_strategy == PBRT_B200_LIGHTS_SPATIAL && sc->dev.n_lights > 1)
+        return fail(PBRT_B200_ERR_UNSUPPORTED, "render: lightsamplestrategy \"spatial\" is not built yet (use \"power\" or \"uniform\")");
+    PB_CUDA_TRY(cudaSetDevice(sc->device));
+    int rc;
+    // lights live on the device; fetch them once for the host-side distribution build
+    std::vector<pbrt_b200_light> lights(sc->dev.n_lights);
+    if (!lights.empty()) PB_CUDA_TRY(cudaMemcpy(lights.data(), sc->dev.lights, lights.size() * sizeof(pbrt_b200_light), cudaMemcpyDeviceToHost));
+    SceneRenderState* st;
+    if ((rc = prepare_scene_state(sc, rd, lights, &st))) return rc;
+
+    const int* sb = rd->sampler.sample_bounds;
+    const int* crop = rd->film.cropped_pixel_bounds;
+    const int W = crop[2] - crop[0], Hh = crop[3] - crop[1];
+    if (W <= 0 || Hh <= 0) return fail(PBRT_B200_ERR_INVALID, "render: empty crop window");
+    int ntx = (sb[2] - sb[0] + 15) / 16, nty = (sb[3] - sb[1] + 15) / 16;
+    uint32_t tile_begin = rd->tile_begin, tile_end = rd->tile_end ? rd->tile_end : (uint32_t)(ntx * nty);
+    uint32_t s_begin = rd->sample_begin, s_end = rd->sample_end ? rd->sample_end : rd->sampler.samples_per_pixel;
+    if (tile_end > (uint32_t)(ntx * nty) || tile_begin > tile_end || s_begin > s_end || s_end > rd->sampler.samples_per_pixel)
+        return fail(PBRT_B200_ERR_INVALID, "render: tile/sample window out of range");
+    unsigned long long total_items = (unsigned long long)(tile_end - tile_begin) * 256ull * (s_end - s_begin);
+
+    uint32_t capacity = rd->paths_in_flight ? rd->paths_in_flight : (1u << 21);
+    capacity = (capacity + 255u) & ~255u;
+    if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
+    if (capacity == 0) capacity = 256;
+    if ((rc = ensure_buffers(st, capacity))) return rc;
+    RenderDev R = st->buffers->dev;
+    R.capacity = capacity;
+    R.scene = sc->dev;
+    R.camera = rd->camera;
+    // sampler
+    SamplerDev& S = R.sampler;
+    std::memset(&S, 0, sizeof S);
+    S.kind = rd->sampler.kind; S.spp = rd->sampler.samples_per_pixel;
+    for (int i = 0; i < 4; ++i) S.sb[i] = sb[i];
+    {
+        int v = std::max(sb[2] - sb[0], sb[3] - sb[1]);  // round_up_pow2_32 / log2_int, sobol.rs:43-46
+        v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v++;
+        S.resolution = v;
+        S.log2_resolution = 0; while ((1 << S.log2_resolution) < v) S.log2_resolution++;
+    }
+    S.sobol32 = st->sobol32; S.vdc = st->vdc; S.vdc_inv = st->vdc_inv;
+    {
+        long long res[2] = {sb[2] - sb[0], sb[3] - sb[1]};
+        for (int i = 0; i < 2; ++i) {
+            long long base = i == 0 ? 2 : 3, scale = 1, e = 0;
+            while (scale < std::min<long long>(res[i], 128)) { scale *= base; e += 1; }
+            S.base_scales[i] = scale; S.base_exponents[i] = e;
+        }
+        S.sample_stride = (unsigned long long)(S.base_scales[0] * S.base_scales[1]);
+        S.mult_inverse[0] = mult_inverse(S.base_scales[1], S.base_scales[0]);
+        S.mult_inverse[1] = mult_inverse(S.base_scales[0], S.base_scales[1]);
+    }
+    S.perms = st->perms; S.primes = st->primes; S.prime_sums = st->prime_sums; S.n_halton_dims = st->n_halton_dims;
+    // film
+    for (int i = 0; i < 4; ++i) R.crop[i] = crop[i];
+    R.filter_radius[0] = rd->film.filter_radius[0]; R.filter_radius[1] = rd->film.filter_radius[1];
+    R.inv_filter_radius[0] = 1.0f / rd->film.filter_radius[0]; R.inv_filter_radius[1] = 1.0f / rd->film.filter_radius[1];
+    R.max_sample_luminance = rd->film.max_sample_luminance;
+    R.filter_table = st->filter_table;
+    // integrator
+    R.max_depth = rd->integrator.max_depth; R.rr_threshold = rd->integrator.rr_threshold;
+    for (int i = 0; i < 4; ++i) R.pixel_bounds[i] = rd->integrator.pixel_bounds[i];
+    R.ld_func = st->ld_func; R.ld_cdf = st->ld_cdf; R.ld_func_int = st->ld_func_int; R.n_lights = sc->dev.n_lights;
+    R.inf_distrib = st->inf; R.infinite_lights = st->inf_list; R.n_infinite = st->n_inf;
+    R.ntx = ntx; R.nty = nty;
+    R.tile_begin = tile_begin; R.n_tiles_sel = tile_end - tile_begin; R.sample_begin = s_begin; R.n_samples_sel = s_end - s_begin;
+
+    // film buffer: device pointer supplied, or a scratch film that is added back to the host buffer
+    const size_t npix = (size_t)W * Hh;
+    float4* film_dev = nullptr;
+    bool own_film = !(rd->flags & PBRT_B200_RENDER_KEEP_ON_DEVICE);
+    if (own_film) {
+        PB_CUDA_TRY(cudaMalloc((void**)&film_dev, npix * sizeof(float4)));
+        PB_CUDA_TRY(cudaMemsetAsync(film_dev, 0, npix * sizeof(float4), 0));
+    } else film_dev = reinterpret_cast<float4*>(rgbw_out);
+    R.film = film_dev;
+
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
+    const int grid_trace = sm_count * 8, grid_shade = sm_count * 8, grid_small = sm_count * 4;
+
+    cudaStream_t stream = 0;
+    cudaEvent_t ev0, ev1;
+    PB_CUDA_TRY(cudaEventCreate(&ev0)); PB_CUDA_TRY(cudaEventCreate(&ev1));
+    std::vector<cudaEvent_t> tev;  // pairs around the trace kernels
+    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); tev.push_back(e); };
+    const bool timing = stats != nullptr;
+    uint64_t launches = 0;
+    PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
+    PB_CUDA_TRY(cudaEventRecord(ev0, stream));
+    if (total_items > 0) {
+        for (unsigned long long base = 0; base < total_items; base += capacity) {
+            uint32_t count = (uint32_t)std::min<unsigned long long>(capacity, total_items - base);
+            k_raygen<<<grid_small, 256, 0, stream>>>(R, base, count);
+            launches++;
+            int parity = 0;
+            int iter = 0;
+            for (;;) {
+                if (timing) mark();
+                k_trace_closest<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R, parity);
+                if (timing) mark();
+                k_shade<Q_MISS><<<grid_small, 128, 0, stream>>>(R, parity);
+                k_shade<Q_MATTE><<<grid_shade, 128, 0, stream>>>(R, parity);
+                k_shade<Q_PLASTIC><<<grid_shade, 128, 0, stream>>>(R, parity);
+                k_shade<Q_MIRROR><<<grid_shade, 128, 0, stream>>>(R, parity);
+                k_shade<Q_GLASS><<<grid_shade, 128, 0, stream>>>(R, parity);
+                k_shade<Q_METAL><<<grid_shade, 128, 0, stream>>>(R, parity);
+                k_shade<Q_NOMAT><<<grid_small, 128, 0, stream>>>(R, parity);
+                if (timing) mark();
+                k_trace_shadow<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                if (timing) mark();
+                k_trace_mis<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                if (timing) mark();
+                k_finish<<<grid_small, 256, 0, stream>>>(R);
+                k_iter_end<<<1, 1, 0, stream>>>(R.cnt);
+                launches += 12;
+                parity ^= 1;
+                iter++;
+                if (iter > R.max_depth) {
+                    // every path has had max_depth+1 intersections unless it crossed pass-through surfaces
+                    uint32_t left = 0;
+                    PB_CUDA_TRY(cudaMemcpyAsync(&left, &R.cnt->n_path, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                    PB_CUDA_TRY(cudaStreamSynchronize(stream));
+                    if (left == 0) break;
+                    if (iter > R.max_depth + 4096) return fail(PBRT_B200_ERR_CUDA, "render: path queue failed to drain");
+                }
+            }
+        }
+    }
+    PB_CUDA_TRY(cudaEventRecord(ev1, stream));
+    PB_CUDA_TRY(cudaGetLastError());
+    PB_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (stats) {
+        Counters c;
+        PB_CUDA_TRY(cudaMemcpy(&c, R.cnt, sizeof c, cudaMemcpyDeviceToHost));
+        std::memset(stats, 0, sizeof *stats);
+        stats->camera_rays = c.camera_rays; stats->intersection_tests = c.closest_rays; stats->shadow_tests = c.shadow_rays;
+        stats->zero_radiance_paths = c.zero_radiance; stats->kernel_launches = launches;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        stats->device_ms = ms;
+        for (size_t k = 0; k + 4 < tev.size(); k += 5) {
+            float a = 0.f, b = 0.f, m = 0.f;
+            cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
+            cudaEventElapsedTime(&b, tev[k + 2], tev[k + 3]);
+            cudaEventElapsedTime(&m, tev[k + 3], tev[k + 4]);
+            stats->trace_closest_ms += a + m; stats->trace_any_ms += b;
+        }
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (own_film) {
+        std::vector<float> tmp(npix * 4);
+        PB_CUDA_TRY(cudaMemcpy(tmp.data(), film_dev, npix * sizeof(float4), cudaMemcpyDeviceToHost));
+        cudaFree(film_dev);
+        for (size_t i = 0; i < npix * 4; ++i) rgbw_out[i] += tmp[i];
+    }
+    return PBRT_B200_OK;
 }

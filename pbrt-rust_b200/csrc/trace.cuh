@@ -69,7 +69,7 @@ PB_D bool triangle_test(f3 o, f3 dir, float t_max, f3 p0, f3 p1, f3 p2, int kx, 
 // triangle.rs:236-263: after the t tests a closest-hit candidate is still rejected when
 // both dpdu x dpdv and the geometric normal vanish.  uv = per-vertex (u,v) or the default
 // parameterisation (triangle.rs:109-115).
-__device__ __noinline__ bool triangle_bogus(f3 p0, f3 p1, f3 p2, float2 uv0, float2 uv1, float2 uv2) {
+static __device__ __noinline__ bool triangle_bogus(f3 p0, f3 p1, f3 p2, float2 uv0, float2 uv1, float2 uv2) {
     float2 duv02 = make_float2(uv0.x - uv2.x, uv0.y - uv2.y), duv12 = make_float2(uv1.x - uv2.x, uv1.y - uv2.y);
     f3 dp02 = p0 - p2, dp12 = p1 - p2;
     float determinant = duv02.x * duv12.y - duv02.y * duv12.x;
@@ -137,7 +137,7 @@ PB_D void sphere_object_ray(const pbrt_b200_sphere& sp, f3 o, f3 d, f3* oo, f3* 
 
 // Sphere::intersect / intersect_p up to the choice of t_shape_hit, sphere.rs:59-108
 // (full spheres; the partial-sphere clipping branch cannot trigger).
-__device__ __noinline__ bool sphere_test(const pbrt_b200_sphere* spp, f3 o, f3 d, float t_max, float* t_out) {
+static __device__ __noinline__ bool sphere_test(const pbrt_b200_sphere* spp, f3 o, f3 d, float t_max, float* t_out) {
     const pbrt_b200_sphere& sp = *spp;
     f3 oo, od, oe, de;
     sphere_object_ray(sp, o, d, &oo, &od, &oe, &de);
