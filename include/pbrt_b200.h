@@ -261,6 +261,11 @@ typedef struct pbrt_b200_render_desc {
     uint32_t sample_begin, sample_end;
     uint32_t paths_in_flight;   /* 0 => library default                          */
     uint32_t flags;             /* PBRT_B200_RENDER_*                            */
+    /* Interleaved ownership inside [tile_begin, tile_end) for static multi-GPU
+     * partitioning: tile t is rendered iff ((t - tile_begin) / tile_group) %
+     * tile_mod == tile_rem.  0,0,0 => every tile (group 1, mod 1, rem 0).       */
+    uint32_t tile_group, tile_mod, tile_rem;
+    uint32_t reserved;
 } pbrt_b200_render_desc;
 
 enum {

@@ -455,6 +455,10 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
         for (;;) {
             uint32_t tile = next.fetch_add(1);
             if (tile >= tile_end) break;
+            {   // interleaved tile ownership (pbrt_b200_render_desc.tile_group/mod/rem)
+                uint32_t g = rd.tile_group ? rd.tile_group : 1u, m = rd.tile_mod ? rd.tile_mod : 1u;
+                if (((tile - tile_begin) / g) % m != rd.tile_rem) continue;
+            }
             int tx = tile % ntx, ty = tile / ntx;
             std::unique_ptr<Sampler> ts = base->clone((int64_t)ty * ntx + tx);
             int x0 = sb[0] + tx * tilesize, x1 = std::min(x0 + tilesize, sb[2]);

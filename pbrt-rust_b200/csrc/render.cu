@@ -81,7 +81,8 @@ struct RenderDev {
     uint32_t n_infinite;
     // work decomposition (integrator.rs:274-279)
     int ntx, nty;
-    uint32_t tile_begin, n_tiles_sel, sample_begin, n_samples_sel;
+    uint32_t tile_begin, tile_end, n_tiles_sel, sample_begin, n_samples_sel;
+    uint32_t tile_group, tile_mod, tile_rem;
     // path state, SoA over `capacity` slots
     uint32_t capacity;
     float4* ray;         // 2 x float4 per slot: {o, t_max}, {d, time}
@@ -318,12 +319,14 @@ __global__ void __launch_bounds__(256) k_raygen(RenderDev R, unsigned long long 
             unsigned long long item = item_base + i;
             uint32_t p = (uint32_t)(item & 255u);
             unsigned long long rest = item >> 8;
-            uint32_t t = (uint32_t)(rest % R.n_tiles_sel) + R.tile_begin;
+            uint32_t j = (uint32_t)(rest % R.n_tiles_sel);  // ordinal among the tiles this call owns
+            uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
             sample = (uint32_t)(rest / R.n_tiles_sel) + R.sample_begin;
+            valid = t < R.tile_end;
             int tx = t % R.ntx, ty = t / R.ntx;
             x = R.sampler.sb[0] + tx * 16 + (int)(p & 15u);
             y = R.sampler.sb[1] + ty * 16 + (int)(p >> 4);
-            valid = x < R.sampler.sb[2] && y < R.sampler.sb[3] && x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] &&
+            valid = valid && x < R.sampler.sb[2] && y < R.sampler.sb[3] && x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] &&
                     y < R.pixel_bounds[3];
         }
         if (valid) {
@@ -1022,7 +1025,13 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     uint32_t s_begin = rd->sample_begin, s_end = rd->sample_end ? rd->sample_end : rd->sampler.samples_per_pixel;
     if (tile_end > (uint32_t)(ntx * nty) || tile_begin > tile_end || s_begin > s_end || s_end > rd->sampler.samples_per_pixel)
         return fail(PBRT_B200_ERR_INVALID, "render: tile/sample window out of range");
-    unsigned long long total_items = (unsigned long long)(tile_end - tile_begin) * 256ull * (s_end - s_begin);
+    uint32_t tile_group = rd->tile_group ? rd->tile_group : 1u, tile_mod = rd->tile_mod ? rd->tile_mod : 1u, tile_rem = rd->tile_rem;
+    if (tile_rem >= tile_mod) return fail(PBRT_B200_ERR_INVALID, "render: tile_rem must be < tile_mod");
+    // tiles owned by this call: whole groups g with g % tile_mod == tile_rem (the last one may be partial; raygen masks it)
+    uint32_t n_groups = (tile_end - tile_begin + tile_group - 1) / tile_group;
+    uint32_t n_owned_groups = n_groups > tile_rem ? (n_groups - tile_rem + tile_mod - 1) / tile_mod : 0;
+    uint32_t n_tiles_sel = n_owned_groups * tile_group;
+    unsigned long long total_items = (unsigned long long)n_tiles_sel * 256ull * (s_end - s_begin);
 
     uint32_t capacity = rd->paths_in_flight ? rd->paths_in_flight : (1u << 21);
     capacity = (capacity + 255u) & ~255u;
@@ -1069,7 +1078,8 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     R.ld_func = st->ld_func; R.ld_cdf = st->ld_cdf; R.ld_func_int = st->ld_func_int; R.n_lights = sc->dev.n_lights;
     R.inf_distrib = st->inf; R.infinite_lights = st->inf_list; R.n_infinite = st->n_inf;
     R.ntx = ntx; R.nty = nty;
-    R.tile_begin = tile_begin; R.n_tiles_sel = tile_end - tile_begin; R.sample_begin = s_begin; R.n_samples_sel = s_end - s_begin;
+    R.tile_begin = tile_begin; R.tile_end = tile_end; R.n_tiles_sel = n_tiles_sel; R.sample_begin = s_begin; R.n_samples_sel = s_end - s_begin;
+    R.tile_group = tile_group; R.tile_mod = tile_mod; R.tile_rem = tile_rem;
 
     // film buffer: device pointer supplied, or a scratch film that is added back to the host buffer
     const size_t npix = (size_t)W * Hh;

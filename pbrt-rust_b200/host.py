@@ -90,7 +90,8 @@ class IntegratorDesc(C.Structure):
 class RenderDesc(C.Structure):
     _fields_ = [("camera", CameraDesc), ("film", FilmDesc), ("sampler", SamplerDesc), ("integrator", IntegratorDesc),
                 ("tile_begin", C.c_uint32), ("tile_end", C.c_uint32), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
-                ("paths_in_flight", C.c_uint32), ("flags", C.c_uint32)]
+                ("paths_in_flight", C.c_uint32), ("flags", C.c_uint32),
+                ("tile_group", C.c_uint32), ("tile_mod", C.c_uint32), ("tile_rem", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class RenderStats(C.Structure):
@@ -713,7 +714,7 @@ class PathIntegrator:
             sb = (max(sb[0], x0), max(sb[1], y0), min(sb[2], x1), min(sb[3], y1))
         self.pixel_bounds = sb
 
-    def desc(self, tile_range=None, sample_range=None, paths_in_flight=0, flags=0):
+    def desc(self, tile_range=None, sample_range=None, paths_in_flight=0, flags=0, tile_interleave=None):
         d = RenderDesc()
         d.camera, d.film, d.sampler = self.camera.desc(), self.film.desc(), self.sampler.desc(self.film)
         d.integrator.max_depth, d.integrator.rr_threshold = self.max_depth, self.rr_threshold
@@ -724,6 +725,8 @@ class PathIntegrator:
         if sample_range:
             d.sample_begin, d.sample_end = sample_range
         d.paths_in_flight, d.flags = paths_in_flight, flags
+        if tile_interleave:  # (group, mod, rem): static multi-GPU ownership of tile groups
+            d.tile_group, d.tile_mod, d.tile_rem = tile_interleave
         return d
 
     def n_tiles(self):  # integrator.rs:274-279
@@ -779,16 +782,16 @@ class Scene:
     def intersect_p_dev(self, rays_ptr, n, occ_ptr, stream=None):
         _check(self.lib.pbrt_b200_intersect_p_dev(self.handle, rays_ptr, n, occ_ptr, stream), "pbrt_b200_intersect_p_dev")
 
-    def render(self, integrator, rgbw=None, tile_range=None, sample_range=None, paths_in_flight=0, device_ptr=None):
+    def render(self, integrator, rgbw=None, tile_range=None, sample_range=None, paths_in_flight=0, device_ptr=None, tile_interleave=None):
         film = integrator.film
         stats = RenderStats()
         if device_ptr is not None:
-            d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE)
+            d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE, tile_interleave)
             _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), device_ptr, C.byref(stats)), "pbrt_b200_render")
             return None, stats
         if rgbw is None:
             rgbw = np.zeros((film.height * film.width, 4), f32)
-        d = integrator.desc(tile_range, sample_range, paths_in_flight, 0)
+        d = integrator.desc(tile_range, sample_range, paths_in_flight, 0, tile_interleave)
         _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), _ptr(rgbw), C.byref(stats)), "pbrt_b200_render")
         return rgbw, stats
 
