@@ -19,29 +19,59 @@ void render_release_scene_state(pbrt_b200_scene* scene);  // render.cu
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-// One ray per thread; rays are 32-byte records read as two float4 (coalesced 128-bit).
-__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_batch(DevScene s, const float4* __restrict__ rays, uint64_t n, uint4* __restrict__ hits) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
-    RayHit h;
-    bool found = traverse<false>(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, &h);
-    uint4 out;
-    if (found) {
-        out.x = __float_as_uint(__ldg(s.tris + 3ull * h.slot).w);  // creation_index
-        out.y = __float_as_uint(h.t); out.z = __float_as_uint(h.b0); out.w = __float_as_uint(h.b1);
-    } else {
-        out.x = PBRT_B200_NO_HIT; out.y = __float_as_uint(a.w); out.z = 0u; out.w = 0u;
+// Persistent warps pull rays from the batch (trace.cuh: trace_queue); rays are 32-byte records
+// read as two float4 (128-bit loads), hits are written as one uint4.
+struct BatchClosestJob {
+    const float4* rays; uint4* hits; const float4* tris;
+    PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
+        float4 a = __ldg(rays + 2ull * i), b = __ldg(rays + 2ull * i + 1);
+        *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
+        return true;
     }
-    hits[i] = out;
+    PB_D void store(uint32_t i, const TravRay& r) const {
+        uint4 out;
+        if (r.found) {
+            out.x = __float_as_uint(__ldg(tris + 3ull * r.hit.slot).w);  // creation_index
+            out.y = __float_as_uint(r.hit.t); out.z = __float_as_uint(r.hit.b0); out.w = __float_as_uint(r.hit.b1);
+        } else {
+            out.x = PBRT_B200_NO_HIT; out.y = __float_as_uint(r.hit.t); out.z = 0u; out.w = 0u;
+        }
+        hits[i] = out;
+    }
+};
+struct BatchAnyJob {
+    const float4* rays; uint8_t* occluded;
+    PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
+        float4 a = __ldg(rays + 2ull * i), b = __ldg(rays + 2ull * i + 1);
+        *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
+        return true;
+    }
+    PB_D void store(uint32_t i, const TravRay& r) const { occluded[i] = r.found ? 1 : 0; }
+};
+
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_batch(DevScene s, const float4* __restrict__ rays, uint32_t n, uint4* __restrict__ hits,
+                                                                   uint32_t* fetch, TraceTune tune) {
+    BatchClosestJob job{rays, hits, s.tris};
+    trace_queue<false>(s, job, n, fetch, tune);
 }
 
-__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_p_batch(DevScene s, const float4* __restrict__ rays, uint64_t n, uint8_t* __restrict__ occluded) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// A/B variants for tuning (tools/trace_ab.py): one ray per thread, while-while or if-if
+template <int VARIANT>
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_batch_1rpt(DevScene s, const float4* __restrict__ rays, uint32_t n, uint4* __restrict__ hits) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
-    RayHit h;
-    occluded[i] = traverse<true>(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, &h) ? 1 : 0;
+    BatchClosestJob job{rays, hits, s.tris};
+    f3 o, d; float t_max;
+    job.load(i, &o, &d, &t_max);
+    TravRay r;
+    r.found = VARIANT == 0 ? traverse<false>(s, o, d, t_max, &r.hit) : traverse_ifif<false>(s, o, d, t_max, &r.hit);
+    job.store(i, r);
+}
+
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_p_batch(DevScene s, const float4* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occluded,
+                                                                     uint32_t* fetch) {
+    BatchAnyJob job{rays, occluded};
+    trace_queue<true>(s, job, n, fetch);
 }
 
 // ---------------------------------------------------------------------------
@@ -166,6 +196,7 @@ extern "C" void pbrt_b200_scene_destroy(pbrt_b200_scene* sc) {
     render_release_scene_state(sc);
     for (int i = 0; i < sc->n_allocs; ++i) cudaFree(sc->allocs[i]);
     if (sc->scratch) cudaFree(sc->scratch);
+    if (sc->fetch_counter) cudaFree(sc->fetch_counter);
     delete sc;
 }
 
@@ -253,14 +284,40 @@ extern "C" int pbrt_b200_scene_world_bound(const pbrt_b200_scene* sc, float* b) 
 // ---------------------------------------------------------------------------
 // batch intersect
 // ---------------------------------------------------------------------------
+// tunables for A/B measurement of the batch closest-hit kernel: [variant, refill_below, chunk, grid]
+static int g_tune[4] = {0, PB_REFILL_BELOW, PB_FETCH_CHUNK, 0};
+extern "C" void pbrt_b200_debug_tune(int key, int value) { if (key >= 0 && key < 4) g_tune[key] = value; }
+
+namespace {
+int ensure_fetch_counter(pbrt_b200_scene* sc) {
+    if (sc->fetch_counter) return PBRT_B200_OK;
+    PB_CUDA_TRY(cudaMalloc((void**)&sc->fetch_counter, 64));
+    int sm = 148, per_sm = 8;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, sc->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intersect_batch, PB_TRACE_BLOCK, 0);
+    sc->trace_grid = sm * (per_sm > 0 ? per_sm : 1);  // persistent: one resident wave of CTAs
+    return PBRT_B200_OK;
+}
+}  // namespace
+
 extern "C" int pbrt_b200_intersect_dev(pbrt_b200_scene* sc, const pbrt_b200_ray* rays, uint64_t n, pbrt_b200_hit* hits, void* stream) {
     if (!sc || (n && (!rays || !hits))) return fail(PBRT_B200_ERR_INVALID, "intersect_dev: null argument");
     if (n == 0) return PBRT_B200_OK;
     PB_CUDA_TRY(cudaSetDevice(sc->device));
-    uint64_t blocks = (n + PB_TRACE_BLOCK - 1) / PB_TRACE_BLOCK;
-    if (blocks > 0x7fffffffull) return fail(PBRT_B200_ERR_INVALID, "intersect_dev: batch too large");
-    k_intersect_batch<<<(unsigned)blocks, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), n,
-                                                                                    reinterpret_cast<uint4*>(hits));
+    if (n > 0xfffffff0ull) return fail(PBRT_B200_ERR_INVALID, "intersect_dev: batch too large (split it)");
+    int rc = ensure_fetch_counter(sc);
+    if (rc) return rc;
+    PB_CUDA_TRY(cudaMemsetAsync(sc->fetch_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    if (g_tune[0] == 1 || g_tune[0] == 2) {
+        unsigned blocks = (unsigned)((n + PB_TRACE_BLOCK - 1) / PB_TRACE_BLOCK);
+        if (g_tune[0] == 1) k_intersect_batch_1rpt<0><<<blocks, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, reinterpret_cast<uint4*>(hits));
+        else k_intersect_batch_1rpt<1><<<blocks, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, reinterpret_cast<uint4*>(hits));
+    } else {
+        TraceTune tune{g_tune[1], g_tune[2]};
+        int grid = g_tune[3] > 0 ? g_tune[3] : sc->trace_grid;
+        k_intersect_batch<<<grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n,
+                                                                             reinterpret_cast<uint4*>(hits), sc->fetch_counter, tune);
+    }
     PB_CUDA_TRY(cudaGetLastError());
     return PBRT_B200_OK;
 }
@@ -269,9 +326,12 @@ extern "C" int pbrt_b200_intersect_p_dev(pbrt_b200_scene* sc, const pbrt_b200_ra
     if (!sc || (n && (!rays || !occluded))) return fail(PBRT_B200_ERR_INVALID, "intersect_p_dev: null argument");
     if (n == 0) return PBRT_B200_OK;
     PB_CUDA_TRY(cudaSetDevice(sc->device));
-    uint64_t blocks = (n + PB_TRACE_BLOCK - 1) / PB_TRACE_BLOCK;
-    if (blocks > 0x7fffffffull) return fail(PBRT_B200_ERR_INVALID, "intersect_p_dev: batch too large");
-    k_intersect_p_batch<<<(unsigned)blocks, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), n, occluded);
+    if (n > 0xfffffff0ull) return fail(PBRT_B200_ERR_INVALID, "intersect_p_dev: batch too large (split it)");
+    int rc = ensure_fetch_counter(sc);
+    if (rc) return rc;
+    PB_CUDA_TRY(cudaMemsetAsync(sc->fetch_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    k_intersect_p_batch<<<sc->trace_grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, occluded,
+                                                                                    sc->fetch_counter);
     PB_CUDA_TRY(cudaGetLastError());
     return PBRT_B200_OK;
 }

@@ -33,7 +33,8 @@ struct Counters {
     uint32_t n_next;          // rays for the next iteration
     uint32_t n_shadow, n_mis, n_dead;
     uint32_t n_mat[Q_COUNT];
-    uint32_t pad[4];
+    uint32_t fetch_path, fetch_shadow, fetch_mis;  // persistent ray-queue cursors (trace.cuh: trace_queue)
+    uint32_t pad;
     unsigned long long camera_rays, closest_rays, shadow_rays, zero_radiance;
 };
 
@@ -46,6 +47,7 @@ struct SamplerDev {
     // Sobol (samplers/sobol.rs:34-87)
     int resolution, log2_resolution;
     const uint32_t* sobol32;
+    const uint32_t* sobol_t;  // transposed generator matrices [52 bits][1024 dims]: 8 consecutive dims of one bit are 32 contiguous bytes
     const unsigned long long* vdc;
     const unsigned long long* vdc_inv;
     // Halton (samplers/halton.rs:63-166)
@@ -88,6 +90,7 @@ struct RenderDev {
     float4* ray;         // 2 x float4 per slot: {o, t_max}, {d, time}
     uint4* hit;          // {slot, t, b0, b1}
     float* hit_b2;
+    uint8_t* hit_bin;    // material bin of the hit (Q_*), written by trace_closest, consumed by classify
     float4* L_eta;       // {L.rgb, etascale}
     float4* beta_st;     // {beta.rgb, bits: bounces | specular_bounce << 16}
     float2* pfilm;
@@ -218,6 +221,42 @@ PB_D float2 get_2d(const SamplerDev& S, SampleCursor& c) {
     float x = sample_dimension(S, c, c.dim);
     c.dim += 2;
     return make_float2(x, y);
+}
+
+// Eight consecutive dimensions of one sample at once.  For Sobol' this walks the set bits of the
+// index a single time and XORs 8 matrix columns per bit (sobol_sample_float, lowdiscrepancy.rs:549-569,
+// evaluated for dims dim0..dim0+7 together); the values are bit-identical to the per-dimension loop.
+struct SampleBlock { float u[8]; uint32_t used; };
+PB_D void sample_block(const SamplerDev& S, const SampleCursor& c, SampleBlock& b) {
+    b.used = 0;
+    if (S.kind == PBRT_B200_SAMPLER_SOBOL && c.dim >= 2 && c.dim + 8 <= 1024) {
+        uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        unsigned long long a = c.index;
+        while (a != 0) {
+            int bit = __ffsll((long long)a) - 1;
+            a &= a - 1;
+            const uint32_t* row = S.sobol_t + (uint32_t)bit * 1024u + c.dim;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] ^= __ldg(row + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b.u[k] = fminf((float)v[k] * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b.u[k] = (c.dim + k < 1024u) ? sample_dimension(S, c, c.dim + k) : 0.5f;
+    }
+}
+PB_D float block_pick(const SampleBlock& b, uint32_t k) {
+    float r = b.u[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = (k == (uint32_t)i) ? b.u[i] : r;
+    return r;
+}
+PB_D float get_1d(SampleBlock& b) { float r = block_pick(b, b.used); b.used += 1; return r; }
+PB_D float2 get_2d(SampleBlock& b) {  // x from the lower dimension (sampler.rs:341-352)
+    float2 r = make_float2(block_pick(b, b.used), block_pick(b, b.used + 1));
+    b.used += 2;
+    return r;
 }
 
 // ---------------------------------------------------------------------------
@@ -359,30 +398,45 @@ __global__ void __launch_bounds__(256) k_raygen(RenderDev R, unsigned long long 
 }
 
 // ---------------------------------------------------------------------------
-// K2/K4: closest-hit for path rays + classification by material
+// K2: closest-hit for path rays (persistent ray queue), K4: compaction by material
 // ---------------------------------------------------------------------------
+struct PathClosestJob {
+    RenderDev* R; const uint32_t* q;
+    PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
+        uint32_t id = q[i];
+        float4 a = R->ray[2 * id], b = R->ray[2 * id + 1];
+        *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
+        return true;
+    }
+    PB_D void store(uint32_t i, const TravRay& r) const {
+        uint32_t id = q[i];
+        R->hit[id] = make_uint4(r.hit.slot, __float_as_uint(r.hit.t), __float_as_uint(r.hit.b0), __float_as_uint(r.hit.b1));
+        R->hit_b2[id] = r.hit.b2;
+        int bin = Q_MISS;
+        if (r.found) {
+            int m = R->scene.prims[r.hit.slot].material;
+            bin = m < 0 ? Q_NOMAT : (int)R->scene.materials[m].type;
+        }
+        R->hit_bin[id] = (uint8_t)bin;
+    }
+};
+
 __global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_closest(RenderDev R, int parity) {
+    PathClosestJob job{&R, R.q_path[parity]};
+    trace_queue<false>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path);
+}
+
+// sort/compact-by-material: one warp-aggregated append per material queue
+__global__ void __launch_bounds__(256) k_classify(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_path;
     const uint32_t* q = R.q_path[parity];
     const uint32_t nround = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         bool valid = i < n;
-        uint32_t id = 0;
-        int bin = Q_MISS;
-        if (valid) {
-            id = q[i];
-            float4 a = R.ray[2 * id], b = R.ray[2 * id + 1];
-            RayHit h;
-            bool found = traverse<false>(R.scene, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, &h);
-            R.hit[id] = make_uint4(h.slot, __float_as_uint(h.t), __float_as_uint(h.b0), __float_as_uint(h.b1));
-            R.hit_b2[id] = h.b2;
-            if (found) {
-                int m = R.scene.prims[h.slot].material;
-                bin = m < 0 ? Q_NOMAT : (int)R.scene.materials[m].type;
-            }
-        }
+        uint32_t id = valid ? q[i] : 0u;
+        int bin = valid ? (int)R.hit_bin[id] : -1;
 #pragma unroll
-        for (int k = 0; k < Q_COUNT; ++k) queue_push(R.q_mat[k], &R.cnt->n_mat[k], id, valid && bin == k);
+        for (int k = 0; k < Q_COUNT; ++k) queue_push(R.q_mat[k], &R.cnt->n_mat[k], id, bin == k);
     }
 }
 
@@ -612,16 +666,18 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                         c.index = R.s_index[id]; c.dim = R.s_dim[id];
                         uint32_t pxy = R.pixel[id];
                         c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
+                        SampleBlock sb;
+                        sample_block(R.sampler, c, sb);
                         const int NONSPEC = BX_ALL & ~BX_SPECULAR;
                         // ---- uniform_sample_onelight + estimate_direct, integrator.rs:81-237
                         if (bsdf_count(bsdf, NONSPEC) > 0 && R.n_lights > 0) {
-                            float u1 = get_1d(R.sampler, c);
+                            float u1 = get_1d(sb);
                             uint32_t ln = find_interval_cdf(R.ld_cdf, (int)R.n_lights + 1, u1);  // Distribution1D::sample_discrete
                             float selpdf = R.ld_func_int > 0.0f ? __ldg(R.ld_func + ln) / (R.ld_func_int * (float)R.n_lights) : 0.0f;
                             bool zero = true;
                             if (selpdf != 0.0f) {
-                                float2 ulight = get_2d(R.sampler, c);
-                                float2 uscatt = get_2d(R.sampler, c);
+                                float2 ulight = get_2d(sb);
+                                float2 uscatt = get_2d(sb);
                                 const pbrt_b200_light& light = R.scene.lights[ln];
                                 bool delta = is_delta_light(light);
                                 LightSample ls;
@@ -673,7 +729,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                         f3 wo = -rd, wi(0.f, 0.f, 0.f);
                         float pdf = 0.0f;
                         int flags = 0;
-                        float2 ub = get_2d(R.sampler, c);
+                        float2 ub = get_2d(sb);
                         rgb f = bsdf_sample(bsdf, wo, &wi, ub, &pdf, BX_ALL, &flags);
                         bool alive = !(is_black(f) || pdf == 0.0f);
                         if (alive) {
@@ -689,7 +745,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                             float mc = max_comp(rrbeta);
                             if (mc < R.rr_threshold && bounces > 3) {
                                 float qv = fmaxf(1.0f - mc, 0.05f);
-                                if (get_1d(R.sampler, c) < qv) alive = false;
+                                if (get_1d(sb) < qv) alive = false;
                                 else beta = beta / (1.0f - qv);
                             }
                             if (alive) {
@@ -701,7 +757,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                         }
                         if (!alive) push_dead = true;
                         R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
-                        R.s_dim[id] = c.dim;
+                        R.s_dim[id] = c.dim + sb.used;
                     }
                 }
             }
@@ -718,55 +774,68 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
 }
 
 // ---------------------------------------------------------------------------
-// K3: shadow rays
+// K3: shadow rays (VisibilityTester::unoccluded, core/light.rs:120-123)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_shadow(RenderDev R) {
-    const uint32_t n = R.cnt->n_shadow;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t id = R.q_shadow[i];
-        float4 a = R.sh_ray[2 * id], b = R.sh_ray[2 * id + 1];
-        RayHit h;
-        if (!traverse<true>(R.scene, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, &h)) {
-            float4 c = R.sh_contrib[id];
-            float4 L = R.L_eta[id];
-            L.x += c.x; L.y += c.y; L.z += c.z;
-            R.L_eta[id] = L;
-        }
+struct ShadowJob {
+    RenderDev* R;
+    PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
+        uint32_t id = R->q_shadow[i];
+        float4 a = R->sh_ray[2 * id], b = R->sh_ray[2 * id + 1];
+        *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
+        return true;
     }
+    PB_D void store(uint32_t i, const TravRay& r) const {
+        if (r.found) return;
+        uint32_t id = R->q_shadow[i];
+        float4 c = R->sh_contrib[id];
+        float4 L = R->L_eta[id];
+        L.x += c.x; L.y += c.y; L.z += c.z;
+        R->L_eta[id] = L;
+    }
+};
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_shadow(RenderDev R) {
+    ShadowJob job{&R};
+    trace_queue<true>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
 }
 
 // ---------------------------------------------------------------------------
 // K7: MIS rays (estimate_direct's BSDF-sampled branch, integrator.rs:205-234)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_mis(RenderDev R) {
-    const uint32_t n = R.cnt->n_mis;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t id = R.q_mis[i];
-        float4 a = R.mis_ray[2 * id], b = R.mis_ray[2 * id + 1];
-        f3 o(a.x, a.y, a.z), d(b.x, b.y, b.z);
-        RayHit h;
-        bool found = traverse<false>(R.scene, o, d, a.w, &h);
-        float4 c = R.mis_contrib[id];
+struct MisJob {
+    RenderDev* R;
+    PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
+        uint32_t id = R->q_mis[i];
+        float4 a = R->mis_ray[2 * id], b = R->mis_ray[2 * id + 1];
+        *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
+        return true;
+    }
+    PB_D void store(uint32_t i, const TravRay& r) const {
+        uint32_t id = R->q_mis[i];
+        float4 c = R->mis_contrib[id];
         uint32_t ln = __float_as_uint(c.w);
         rgb li(0.0f);
-        if (found) {
-            const pbrt_b200_prim pr = R.scene.prims[h.slot];
+        if (r.found) {
+            const pbrt_b200_prim pr = R->scene.prims[r.hit.slot];
             if (pr.area_light == (int)ln) {  // Arc::ptr_eq(light, hit primitive's area light)
                 uint32_t fl;
-                Surf ls = surface_at(R.scene, h.slot, o, d, h.t, h.b0, h.b1, h.b2, &fl);
-                const pbrt_b200_light& al = R.scene.lights[ln];
-                if (al.two_sided || dot(ls.n, -d) > 0.0f) li = rgb3(al.L);
+                Surf ls = surface_at(R->scene, r.hit.slot, r.o, r.d, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
+                const pbrt_b200_light& al = R->scene.lights[ln];
+                if (al.two_sided || dot(ls.n, -r.d) > 0.0f) li = rgb3(al.L);
             }
         } else {
-            const pbrt_b200_light& l = R.scene.lights[ln];
+            const pbrt_b200_light& l = R->scene.lights[ln];
             if (l.type == PBRT_B200_LIGHT_INFINITE) li = rgb3(l.L);  // light.le(ray)
         }
         if (!is_black(li)) {
-            float4 L = R.L_eta[id];
+            float4 L = R->L_eta[id];
             L.x += c.x * li.r; L.y += c.y * li.g; L.z += c.z * li.b;
-            R.L_eta[id] = L;
+            R->L_eta[id] = L;
         }
     }
+};
+__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_mis(RenderDev R) {
+    MisJob job{&R};
+    trace_queue<false>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
 
 // ---------------------------------------------------------------------------
@@ -800,6 +869,7 @@ __global__ void k_iter_end(Counters* c) {
     c->shadow_rays += c->n_shadow;
     c->n_path = c->n_next;
     c->n_next = 0; c->n_shadow = 0; c->n_mis = 0; c->n_dead = 0;
+    c->fetch_path = 0; c->fetch_shadow = 0; c->fetch_mis = 0;
     for (int k = 0; k < Q_COUNT; ++k) c->n_mat[k] = 0;
 }
 
@@ -820,7 +890,7 @@ struct SceneRenderState {  // cached per scene: light tables
     // Halton tables (shared by all renders of the scene's device)
     uint16_t* perms = nullptr; uint32_t* primes = nullptr; uint32_t* prime_sums = nullptr; uint32_t n_halton_dims = 0;
     // Sobol tables copied to the device
-    uint32_t* sobol32 = nullptr; unsigned long long* vdc = nullptr; unsigned long long* vdc_inv = nullptr;
+    uint32_t* sobol32 = nullptr; uint32_t* sobol_t = nullptr; unsigned long long* vdc = nullptr; unsigned long long* vdc_inv = nullptr;
     const void* sobol_src = nullptr;
     float* filter_table = nullptr;
     RenderBuffers* buffers = nullptr;
@@ -831,7 +901,7 @@ void render_release_scene_state(pbrt_b200_scene* sc) {
     if (!st) return;
     cudaFree(st->ld_func); cudaFree(st->ld_cdf); cudaFree(st->inf); cudaFree(st->inf_list);
     cudaFree(st->perms); cudaFree(st->primes); cudaFree(st->prime_sums);
-    cudaFree(st->sobol32); cudaFree(st->vdc); cudaFree(st->vdc_inv); cudaFree(st->filter_table);
+    cudaFree(st->sobol32); cudaFree(st->sobol_t); cudaFree(st->vdc); cudaFree(st->vdc_inv); cudaFree(st->filter_table);
     delete st->buffers;
     delete st;
     sc->light_distrib = nullptr;
@@ -926,8 +996,15 @@ int prepare_scene_state(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, co
     if (rd->sampler.kind == PBRT_B200_SAMPLER_SOBOL && st->sobol_src != rd->sampler.sobol_matrices32) {
         if (!rd->sampler.sobol_matrices32 || !rd->sampler.vdc_matrices || !rd->sampler.vdc_matrices_inv)
             return fail(PBRT_B200_ERR_INVALID, "render: the Sobol sampler needs sobol_matrices32, vdc_matrices and vdc_matrices_inv");
-        cudaFree(st->sobol32); cudaFree(st->vdc); cudaFree(st->vdc_inv);
+        cudaFree(st->sobol32); cudaFree(st->sobol_t); cudaFree(st->vdc); cudaFree(st->vdc_inv);
         PB_CUDA_TRY(cudaMalloc((void**)&st->sobol32, 1024 * 52 * 4));
+        PB_CUDA_TRY(cudaMalloc((void**)&st->sobol_t, 1024 * 52 * 4));
+        {
+            std::vector<uint32_t> tr(1024 * 52);
+            for (int d = 0; d < 1024; ++d)
+                for (int b = 0; b < 52; ++b) tr[b * 1024 + d] = rd->sampler.sobol_matrices32[d * 52 + b];
+            PB_CUDA_TRY(cudaMemcpy(st->sobol_t, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+        }
         PB_CUDA_TRY(cudaMalloc((void**)&st->vdc, 25 * 52 * 8));
         PB_CUDA_TRY(cudaMalloc((void**)&st->vdc_inv, 26 * 52 * 8));
         PB_CUDA_TRY(cudaMemcpy(st->sobol32, rd->sampler.sobol_matrices32, 1024 * 52 * 4, cudaMemcpyHostToDevice));
@@ -979,7 +1056,7 @@ int ensure_buffers(SceneRenderState* st, uint32_t capacity) {
     std::memset(&d, 0, sizeof d);
     int rc;
 #define A(ptr, n) if ((rc = dev_alloc(rb, &ptr, (size_t)(n)))) return rc
-    A(d.ray, 2 * (size_t)capacity); A(d.hit, capacity); A(d.hit_b2, capacity); A(d.L_eta, capacity); A(d.beta_st, capacity); A(d.pfilm, capacity);
+    A(d.ray, 2 * (size_t)capacity); A(d.hit, capacity); A(d.hit_b2, capacity); A(d.hit_bin, capacity); A(d.L_eta, capacity); A(d.beta_st, capacity); A(d.pfilm, capacity);
     A(d.s_index, capacity); A(d.s_dim, capacity); A(d.pixel, capacity);
     A(d.sh_ray, 2 * (size_t)capacity); A(d.sh_contrib, capacity); A(d.mis_ray, 2 * (size_t)capacity); A(d.mis_contrib, capacity);
     A(d.q_path[0], capacity); A(d.q_path[1], capacity); A(d.q_shadow, capacity); A(d.q_mis, capacity); A(d.q_dead, capacity);
@@ -1053,7 +1130,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         S.resolution = v;
         S.log2_resolution = 0; while ((1 << S.log2_resolution) < v) S.log2_resolution++;
     }
-    S.sobol32 = st->sobol32; S.vdc = st->vdc; S.vdc_inv = st->vdc_inv;
+    S.sobol32 = st->sobol32; S.sobol_t = st->sobol_t; S.vdc = st->vdc; S.vdc_inv = st->vdc_inv;
     {
         long long res[2] = {sb[2] - sb[0], sb[3] - sb[1]};
         for (int i = 0; i < 2; ++i) {
@@ -1093,7 +1170,10 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
 
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
-    const int grid_trace = sm_count * 8, grid_shade = sm_count * 8, grid_small = sm_count * 4;
+    int trace_per_sm = 8;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, k_trace_closest, PB_TRACE_BLOCK, 0);
+    const int grid_trace = sm_count * (trace_per_sm > 0 ? trace_per_sm : 1);  // persistent: exactly one resident wave
+    const int grid_shade = sm_count * 8, grid_small = sm_count * 4;
 
     cudaStream_t stream = 0;
     cudaEvent_t ev0, ev1;
@@ -1115,6 +1195,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (timing) mark();
                 k_trace_closest<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R, parity);
                 if (timing) mark();
+                k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
                 k_shade<Q_MISS><<<grid_small, 128, 0, stream>>>(R, parity);
                 k_shade<Q_MATTE><<<grid_shade, 128, 0, stream>>>(R, parity);
                 k_shade<Q_PLASTIC><<<grid_shade, 128, 0, stream>>>(R, parity);
@@ -1129,7 +1210,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (timing) mark();
                 k_finish<<<grid_small, 256, 0, stream>>>(R);
                 k_iter_end<<<1, 1, 0, stream>>>(R.cnt);
-                launches += 12;
+                launches += 13;
                 parity ^= 1;
                 iter++;
                 if (iter > R.max_depth) {

@@ -62,4 +62,6 @@ struct pbrt_b200_scene {
     void* scratch = nullptr;     // reusable staging for the host-buffer batch API
     uint64_t scratch_bytes = 0;
     void* light_distrib = nullptr;  // owned by render.cu
+    uint32_t* fetch_counter = nullptr;  // device counter of the persistent ray queue (batch API)
+    int trace_grid = 0;
 };

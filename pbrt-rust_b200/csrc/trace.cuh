@@ -189,11 +189,171 @@ PB_D bool slab_test(float nx, float ny, float nz, float fx, float fy, float fz, 
     return ok && (tmax > 0.0f);
 }
 
-#define PB_STACK_DEPTH 64  /* bvh.rs:722 nodes_tovisit = vec![0; 64] */
+// Same predicate and the same tmin for rays whose direction has no zero component: then no
+// product (b - o) * inv can be NaN, the reference's compare-and-assign chain equals max/min,
+// and its pairwise early-outs equal `tmin <= tmax` (the i == j pairs it skips can only fail
+// when that axis' far plane is behind the ray, which `tmax > 0` rejects anyway).
+PB_D bool slab_fast(float nx, float ny, float nz, float fx, float fy, float fz, f3 o, f3 inv, float* tmin_out) {
+    const float widen = 1.0f + 2.0f * gamma_n(3);
+    float tx0 = (nx - o.x) * inv.x, ty0 = (ny - o.y) * inv.y, tz0 = (nz - o.z) * inv.z;
+    float tx1 = (fx - o.x) * inv.x, ty1 = (fy - o.y) * inv.y, tz1 = (fz - o.z) * inv.z;
+    tx1 *= widen; ty1 *= widen; tz1 *= widen;
+    float tmin = fmaxf(fmaxf(tx0, ty0), tz0);
+    float tmax = fminf(fminf(tx1, ty1), tz1);
+    *tmin_out = tmin;
+    return (tmin <= tmax) && (tmax > 0.0f);
+}
 
-// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray.
+#define PB_STACK_DEPTH 64  /* bvh.rs:722 nodes_tovisit = vec![0; 64] */
+#define PB_DONE 0xffffffffu /* traversal finished (has the leaf bit set so the interior loop exits) */
+
+// Per-ray traversal state.  The order of box and primitive tests is the reference's
+// (see the exactness contract above); the control flow is "while-while": an inner loop
+// that only walks interior nodes, then the leaf run, so that lanes of a warp reconverge
+// on the two hot bodies instead of interleaving them.
+struct TravRay {
+    f3 o, d, inv;
+    float t_max, Sx, Sy, Sz;
+    uint32_t cur;    // node / leaf reference being visited, or PB_DONE
+    int sp;
+    int kx, ky, kz;
+    bool ngx, ngy, ngz, found;
+    bool nan_possible;  // a zero direction component: 0 * inf can appear in the slab test
+    RayHit hit;
+};
+
+PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) {
+    r.o = o; r.d = d; r.t_max = t_max;
+    r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.b0 = r.hit.b1 = r.hit.b2 = 0.0f;
+    r.found = false; r.sp = 0; r.cur = PB_DONE;
+    r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.ngx = r.inv.x < 0.0f; r.ngy = r.inv.y < 0.0f; r.ngz = r.inv.z < 0.0f;
+    r.nan_possible = (d.x == 0.0f) || (d.y == 0.0f) || (d.z == 0.0f);
+    // ray-constant part of the watertight test (triangle.rs:151-165)
+    f3 ad = vabs(d);
+    r.kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
+    r.kx = (r.kz + 1 == 3) ? 0 : r.kz + 1;
+    r.ky = (r.kx + 1 == 3) ? 0 : r.kx + 1;
+    const float dpx = comp(d, r.kx), dpy = comp(d, r.ky), dpz = comp(d, r.kz);
+    r.Sx = -dpx / dpz; r.Sy = -dpy / dpz; r.Sz = 1.0f / dpz;
+    if (s.root_ref == PB_REF_NONE) return;
+    float tmin;
+    const float* rb = s.root_box;
+    bool ok = slab_test(r.ngx ? rb[3] : rb[0], r.ngy ? rb[4] : rb[1], r.ngz ? rb[5] : rb[2], r.ngx ? rb[0] : rb[3], r.ngy ? rb[1] : rb[4],
+                        r.ngz ? rb[2] : rb[5], o, r.inv, &tmin);
+    if (ok && tmin < t_max) r.cur = s.root_ref;
+}
+
+// pop: the reference tests the popped node's box against the *current* t_max
+#define PB_TRAV_POP(r, stack)                                           \
+    do {                                                                \
+        (r).cur = PB_DONE;                                              \
+        while ((r).sp > 0) {                                            \
+            --(r).sp;                                                   \
+            uint2 e__ = (stack)[(r).sp];                                \
+            if (__uint_as_float(e__.y) < (r).t_max) { (r).cur = e__.x; break; } \
+        }                                                               \
+    } while (0)
+
+// Runs the ray until it finishes, or (when `yield_below` > 0) until fewer than `yield_below`
+// lanes of the warp are still traversing, so that the caller can refill idle lanes.
+template <bool ANY, bool EXACT_NAN>
+PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_below) {
+    while (r.cur != PB_DONE) {
+        // ---- interior nodes
+        while (!(r.cur & PB_LEAF_BIT)) {
+            const float4* np = s.nodes + 4ull * r.cur;
+            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+            uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z);
+            float tmin0, tmin1;
+            bool ok0, ok1;
+            if (EXACT_NAN) {
+                ok0 = slab_test(r.ngx ? q0.w : q0.x, r.ngy ? q1.x : q0.y, r.ngz ? q1.y : q0.z, r.ngx ? q0.x : q0.w, r.ngy ? q0.y : q1.x,
+                                r.ngz ? q0.z : q1.y, r.o, r.inv, &tmin0);
+                ok1 = slab_test(r.ngx ? q2.y : q1.z, r.ngy ? q2.z : q1.w, r.ngz ? q2.w : q2.x, r.ngx ? q1.z : q2.y, r.ngy ? q1.w : q2.z,
+                                r.ngz ? q2.x : q2.w, r.o, r.inv, &tmin1);
+            } else {
+                ok0 = slab_fast(r.ngx ? q0.w : q0.x, r.ngy ? q1.x : q0.y, r.ngz ? q1.y : q0.z, r.ngx ? q0.x : q0.w, r.ngy ? q0.y : q1.x,
+                                r.ngz ? q0.z : q1.y, r.o, r.inv, &tmin0);
+                ok1 = slab_fast(r.ngx ? q2.y : q1.z, r.ngy ? q2.z : q1.w, r.ngz ? q2.w : q2.x, r.ngx ? q1.z : q2.y, r.ngy ? q1.w : q2.z,
+                                r.ngz ? q2.x : q2.w, r.o, r.inv, &tmin1);
+            }
+            // near child = second child when the ray is negative along the split axis (bvh.rs:743-751)
+            bool second_first = (axis == 0) ? r.ngx : ((axis == 1) ? r.ngy : r.ngz);
+            uint32_t nref = second_first ? ref1 : ref0, fref = second_first ? ref0 : ref1;
+            float ntmin = second_first ? tmin1 : tmin0, ftmin = second_first ? tmin0 : tmin1;
+            bool nok = second_first ? ok1 : ok0, fok = second_first ? ok0 : ok1;
+            bool nhit = nok && (ntmin < r.t_max);
+            // the far child's `tmin < t_max` is re-checked at pop time for closest-hit rays
+            // (t_max may have changed by then); for any-hit rays t_max is constant
+            bool fhit = fok && (ftmin < r.t_max);
+            if (nhit) {
+                if (ANY ? fhit : fok) { stack[r.sp] = make_uint2(fref, __float_as_uint(ftmin)); ++r.sp; }
+                r.cur = nref;
+            } else if (fhit) {
+                r.cur = fref;
+            } else {
+                PB_TRAV_POP(r, stack);
+            }
+        }
+        if (r.cur == PB_DONE) break;
+        // ---- leaf run (bvh.rs:730-736): every primitive of the leaf, in order
+        {
+            uint32_t slot = r.cur & ~PB_LEAF_BIT;
+            uint32_t fl;
+            do {
+                const float4* tp = s.tris + 3ull * slot;
+                float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                fl = __float_as_uint(v1.w);
+                float t, b0, b1, b2;
+                bool h;
+                if (fl & PB_TRI_SPHERE) {
+                    h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
+                    b0 = b1 = b2 = 0.0f;
+                } else {
+                    f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
+                    h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
+                    if (!ANY && h) {
+                        float2 uv0, uv1, uv2;
+                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2);
+                        if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) h = false;
+                    }
+                }
+                if (h) {
+                    r.found = true;
+                    r.hit.slot = slot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2;
+                    if (ANY) { r.cur = PB_DONE; r.sp = 0; break; }
+                    r.t_max = t;  // primitive.rs:137
+                }
+                ++slot;
+            } while (!(fl & PB_TRI_LAST));
+            if (ANY && r.found) break;
+            PB_TRAV_POP(r, stack);
+        }
+        if (yield_below > 0 && __popc(__activemask()) < yield_below) break;
+    }
+}
+
+template <bool ANY>
+PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below) {
+    if (r.nan_possible) trav_run_impl<ANY, true>(s, r, stack, yield_below);
+    else trav_run_impl<ANY, false>(s, r, stack, yield_below);
+}
+
+// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray, run to completion.
 template <bool ANY>
 PB_D bool traverse(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
+    uint2 stack[PB_STACK_DEPTH];
+    TravRay r;
+    trav_init(s, r, o, d, t_max);
+    trav_run<ANY>(s, r, stack, 0);
+    *hit = r.hit;
+    return r.found;
+}
+
+// Variant kept for A/B measurements: single loop with leaf / interior / pop branches ("if-if").
+template <bool ANY>
+PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
     hit->slot = PBRT_B200_NO_HIT;
     hit->t = t_max;
     if (s.root_ref == PB_REF_NONE) return false;
@@ -279,6 +439,57 @@ PB_D bool traverse(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
             uint2 e = stack[sp];
             if (__uint_as_float(e.y) < t_max) { cur = e.x; break; }
         }
+    }
+}
+
+
+// Persistent-thread ray queue: every warp pulls ray indices [0, n) from a global counter in
+// chunks and refills lanes whose ray has finished as soon as fewer than PB_REFILL_BELOW lanes
+// are still traversing.  Job provides
+//     bool load(uint32_t idx, f3* o, f3* d, float* t_max)
+//     void store(uint32_t idx, const TravRay& r)
+#define PB_FETCH_CHUNK 32   /* tools/trace_ab.py: larger chunks cost coherent rays 25-45% */
+#define PB_REFILL_BELOW 24
+struct TraceTune { int refill_below; int chunk; };
+template <bool ANY, typename Job>
+PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_counter, TraceTune tune = TraceTune{PB_REFILL_BELOW, PB_FETCH_CHUNK}) {
+    uint2 stack[PB_STACK_DEPTH];
+    TravRay r;
+    r.cur = PB_DONE; r.sp = 0; r.found = false;
+    uint32_t ray_idx = 0xffffffffu;
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
+    bool exhausted = false;                // warp-uniform
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (;;) {
+        __syncwarp();
+        if (r.cur == PB_DONE && ray_idx != 0xffffffffu) { job.store(ray_idx, r); ray_idx = 0xffffffffu; }
+        __syncwarp();
+        unsigned need = __ballot_sync(0xffffffffu, r.cur == PB_DONE);
+        while (need && !exhausted) {
+            if (pool_next == pool_end) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(fetch_counter, (uint32_t)tune.chunk);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= n) { exhausted = true; break; }
+                pool_next = b; pool_end = min(b + (uint32_t)tune.chunk, n);
+            }
+            uint32_t avail = pool_end - pool_next;
+            bool mine = (need >> lane) & 1u;
+            uint32_t rank = __popc(need & lt_mask);
+            bool take = mine && rank < avail;
+            if (take) {
+                ray_idx = pool_next + rank;
+                f3 o, d; float t_max = 0.0f;
+                if (job.load(ray_idx, &o, &d, &t_max)) trav_init(s, r, o, d, t_max);
+                else { r.cur = PB_DONE; r.sp = 0; r.found = false; r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; }
+            }
+            unsigned took = __ballot_sync(0xffffffffu, take);
+            pool_next += __popc(took);
+            need &= ~took;
+        }
+        if (__all_sync(0xffffffffu, ray_idx == 0xffffffffu)) break;
+        trav_run<ANY>(s, r, stack, exhausted ? 0 : tune.refill_below);
     }
 }
 

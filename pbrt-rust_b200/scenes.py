@@ -422,3 +422,29 @@ def rays_camera(integ, sample=0, max_rays=None):
     d = pc * (f32(1) / np.sqrt((pc * pc).sum(1, dtype=f32)))[:, None]
     o = cam.camera_to_world.points(np.zeros((len(d), 3), f32))
     return H.make_rays(o, cam.camera_to_world.vectors(d))
+
+
+def rays_surface(flat, n, seed=23, tri_lo=0, tri_hi=None):
+    """B-surf: incoherent secondary-like rays: origins on random triangles (offset along the face normal),
+    directions uniform in the hemisphere about that normal, t_max = inf.  Representative of bounce >= 1 path rays."""
+    idxs = flat.tri_indices[tri_lo:tri_hi]
+    nt = len(idxs)
+    u = _hash_floats(6 * n, seed).reshape(6, n)
+    t = np.minimum((u[0] * nt).astype(np.int64), nt - 1)
+    idx = idxs[t]
+    p0, p1, p2 = flat.vertex_p[idx[:, 0]], flat.vertex_p[idx[:, 1]], flat.vertex_p[idx[:, 2]]
+    su = np.sqrt(u[1])
+    b0, b1 = 1 - su, u[2] * su
+    p = p0 * b0[:, None] + p1 * b1[:, None] + p2 * (1 - b0 - b1)[:, None]
+    nrm = np.cross(p1 - p0, p2 - p0)
+    ln = np.linalg.norm(nrm, axis=1, keepdims=True)
+    keep = ln[:, 0] > 0
+    nrm = nrm / np.maximum(ln, 1e-30)
+    z = f32(1) - f32(2) * u[3]
+    r = np.sqrt(np.maximum(f32(0), f32(1) - z * z))
+    phi = f32(2 * math.pi) * u[4]
+    d = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1)
+    flip = (d * nrm).sum(1) < 0
+    d[flip] = -d[flip]
+    o = p + nrm * f32(1e-4)
+    return H.make_rays(o[keep].astype(f32), d[keep].astype(f32))
