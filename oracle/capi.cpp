@@ -245,3 +245,45 @@ void orc_generate_ray(const pbrt_b200_camera* c, const float* cs5, float* out6) 
 
 }  // extern "C"
 #endif
+
+// ---- the reference's own tests (tests/*.rs) re-run on the oracle: oracle/ref_tests.hpp ----
+#ifdef ORC_HAVE_RENDER
+#include <string>
+#include "ref_tests.hpp"
+extern "C" {
+// which: name of the reference #[test]; a,b: size parameters (0 = the reference's own counts); out2: optional info.
+// Returns the number of violated assertions, or (uint64_t)-1 for an unknown name.
+uint64_t orc_reftest(const char* which, uint64_t a, uint64_t b, int nthreads, const void* table, uint64_t* out2) {
+    using namespace orc::reftest;
+    std::string w(which);
+    int nt = nthreads <= 0 ? orc_hardware_threads() : nthreads;
+    uint64_t dummy[2] = {0, 0};
+    if (!out2) out2 = dummy;
+    if (w == "triangle_watertight") return triangle_watertight(a ? a : 100000, nt);
+    if (w == "triangle_reintersect") return triangle_reintersect(a ? a : 1000, b ? b : 10000, nt, out2);
+    if (w == "triangle_sampling") return triangle_sampling(a ? a : 512 * 1024, nt, out2);
+    if (w == "triangle_solid_angle") return triangle_solid_angle(nt, out2);
+    if (w == "triangle_badcases") return triangle_badcases();
+    if (w == "sphere_solid_angle") return sphere_solid_angle();
+    if (w == "full_sphere_reintersect") return full_sphere_reintersect(a ? a : 100, b ? b : 10000, nt, out2);
+    if (w == "radical_inverse_test") return radical_inverse_test();
+    if (w == "scrambled_radical_inverse_test") return scrambled_radical_inverse_test();
+    if (w == "generator_matrix") return generator_matrix();
+    if (w == "gray_code_sample_test") return gray_code_sample_test();
+    if (w == "sobol") return sobol_test((const uint32_t*)table);
+    if (w == "elementary_intervals") return elementary_intervals(a ? (int)a : 2);
+    if (w == "distribution1d_discrete") return distribution1d_discrete();
+    if (w == "distribution1d_continuous") return distribution1d_continuous();
+    if (w == "next_float_up_down") return next_float_up_down();
+    if (w == "float_bits") return float_bits();
+    if (w == "efloat_add") return efloat_arith(0, a ? a : 1000000, nt);
+    if (w == "efloat_sub") return efloat_arith(1, a ? a : 1000000, nt);
+    if (w == "efloat_mul") return efloat_arith(2, a ? a : 1000000, nt);
+    if (w == "efloat_div") return efloat_arith(3, a ? a : 1000000, nt);
+    if (w == "bounds3_union") return bounds3_union();
+    if (w == "bitops") return bitops();
+    if (w == "find_interval_test") return find_interval_test();
+    return (uint64_t)-1;
+}
+}
+#endif
