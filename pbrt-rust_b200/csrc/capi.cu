@@ -285,8 +285,8 @@ extern "C" int pbrt_b200_scene_world_bound(const pbrt_b200_scene* sc, float* b) 
 // batch intersect
 // ---------------------------------------------------------------------------
 // tunables for A/B measurement of the batch closest-hit kernel: [variant, refill_below, chunk, grid]
-static int g_tune[4] = {0, PB_REFILL_BELOW, PB_FETCH_CHUNK, 0};
-extern "C" void pbrt_b200_debug_tune(int key, int value) { if (key >= 0 && key < 4) g_tune[key] = value; }
+static int g_tune[8] = {0, PB_REFILL_BELOW, PB_FETCH_CHUNK, 0, PB_INTERIOR_MIN, 0, 0, 0};
+extern "C" void pbrt_b200_debug_tune(int key, int value) { if (key >= 0 && key < 8) g_tune[key] = value; }
 
 namespace {
 int ensure_fetch_counter(pbrt_b200_scene* sc) {
@@ -313,7 +313,7 @@ extern "C" int pbrt_b200_intersect_dev(pbrt_b200_scene* sc, const pbrt_b200_ray*
         if (g_tune[0] == 1) k_intersect_batch_1rpt<0><<<blocks, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, reinterpret_cast<uint4*>(hits));
         else k_intersect_batch_1rpt<1><<<blocks, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, reinterpret_cast<uint4*>(hits));
     } else {
-        TraceTune tune{g_tune[1], g_tune[2]};
+        TraceTune tune{g_tune[1], g_tune[2], g_tune[4]};
         int grid = g_tune[3] > 0 ? g_tune[3] : sc->trace_grid;
         k_intersect_batch<<<grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n,
                                                                              reinterpret_cast<uint4*>(hits), sc->fetch_counter, tune);

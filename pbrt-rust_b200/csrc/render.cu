@@ -31,11 +31,15 @@ enum { Q_MATTE = 0, Q_PLASTIC = 1, Q_MIRROR = 2, Q_GLASS = 3, Q_METAL = 4, Q_NOM
 struct Counters {
     uint32_t n_path;          // rays to trace this iteration
     uint32_t n_next;          // rays for the next iteration
-    uint32_t n_shadow, n_mis, n_dead;
+    uint32_t n_shadow, n_mis;
+    uint32_t n_dead;          // finished paths of this iteration (+ slots still waiting for a camera sample)
+    uint32_t n_dead_next;     // slots re-queued because their item was outside the pixel bounds
     uint32_t n_mat[Q_COUNT];
     uint32_t fetch_path, fetch_shadow, fetch_mis;  // persistent ray-queue cursors (trace.cuh: trace_queue)
     uint32_t pad;
     unsigned long long camera_rays, closest_rays, shadow_rays, zero_radiance;
+    unsigned long long item_cursor;  // next (sample, tile, pixel) item to hand to a free path slot
+    unsigned long long iterations;
 };
 
 struct Tiny1D { float func[2], cdf[3], func_int; };  // Distribution1D with two entries
@@ -104,7 +108,7 @@ struct RenderDev {
     uint32_t* q_path[2];
     uint32_t* q_shadow;
     uint32_t* q_mis;
-    uint32_t* q_dead;
+    uint32_t* q_dead[2];
     uint32_t* q_mat[Q_COUNT];
     Counters* cnt;
 };
@@ -348,53 +352,55 @@ PB_D void generate_ray(const pbrt_b200_camera& c, float2 pfilm, float time_u, fl
     *o_out = ow; *d_out = dw;
 }
 
-__global__ void __launch_bounds__(256) k_raygen(RenderDev R, unsigned long long item_base, uint32_t count) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((count + 31u) & ~31u); i += gridDim.x * blockDim.x) {
-        bool valid = i < count;
-        int x = 0, y = 0;
-        uint32_t sample = 0;
-        if (valid) {
-            // item = (sample, tile, pixel-in-tile); pixels of a tile are contiguous (x fastest, bounds.rs:263-276)
-            unsigned long long item = item_base + i;
-            uint32_t p = (uint32_t)(item & 255u);
-            unsigned long long rest = item >> 8;
-            uint32_t j = (uint32_t)(rest % R.n_tiles_sel);  // ordinal among the tiles this call owns
-            uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
-            sample = (uint32_t)(rest / R.n_tiles_sel) + R.sample_begin;
-            valid = t < R.tile_end;
-            int tx = t % R.ntx, ty = t / R.ntx;
-            x = R.sampler.sb[0] + tx * 16 + (int)(p & 15u);
-            y = R.sampler.sb[1] + ty * 16 + (int)(p >> 4);
-            valid = valid && x < R.sampler.sb[2] && y < R.sampler.sb[3] && x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] &&
-                    y < R.pixel_bounds[3];
-        }
-        if (valid) {
-            SampleCursor c;
-            c.px = x; c.py = y; c.dim = 0;
-            c.index = (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL)
-                          ? sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, sample, x - R.sampler.sb[0], y - R.sampler.sb[1])
-                          : halton_index(R.sampler, sample, x, y);
-            // get_camera_sample, sampler.rs:170-180
-            float2 u = get_2d(R.sampler, c);
-            float2 pfilm = make_float2((float)x + u.x, (float)y + u.y);
-            float tu = get_1d(R.sampler, c);
-            float2 plens = get_2d(R.sampler, c);
-            f3 o, d;
-            float time;
-            generate_ray(R.camera, pfilm, tu, plens, &o, &d, &time);
-            R.ray[2 * i] = make_float4(o.x, o.y, o.z, PB_INF);
-            R.ray[2 * i + 1] = make_float4(d.x, d.y, d.z, time);
-            R.L_eta[i] = make_float4(0.f, 0.f, 0.f, 1.0f);
-            R.beta_st[i] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
-            R.pfilm[i] = pfilm;
-            R.s_index[i] = c.index;
-            R.s_dim[i] = c.dim;
-            R.pixel[i] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
-        }
-        unsigned m = __ballot_sync(0xffffffffu, valid);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
-        queue_push(R.q_path[0], &R.cnt->n_path, i, valid);
+#define PB_NO_SAMPLE 0xffffffffu /* R.pixel[slot]: the slot carries no camera sample (nothing to add to the film) */
+
+// One camera sample into path slot `slot`: item = (sample, tile, pixel-in-tile), pixels of a tile contiguous
+// (x fastest, bounds.rs:263-276), tiles of the call in order, samples outermost.  Returns false when the item
+// falls outside the sample/pixel bounds (partial edge tiles) -- the slot then stays free.
+PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t slot) {
+    uint32_t p = (uint32_t)(item & 255u);
+    unsigned long long rest = item >> 8;
+    uint32_t j = (uint32_t)(rest % R.n_tiles_sel);  // ordinal among the tiles this call owns
+    uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
+    uint32_t sample = (uint32_t)(rest / R.n_tiles_sel) + R.sample_begin;
+    bool valid = t < R.tile_end;
+    int tx = t % R.ntx, ty = t / R.ntx;
+    int x = R.sampler.sb[0] + tx * 16 + (int)(p & 15u);
+    int y = R.sampler.sb[1] + ty * 16 + (int)(p >> 4);
+    valid = valid && x < R.sampler.sb[2] && y < R.sampler.sb[3] && x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] &&
+            y < R.pixel_bounds[3];
+    if (!valid) { R.pixel[slot] = PB_NO_SAMPLE; return false; }
+    SampleCursor c;
+    c.px = x; c.py = y; c.dim = 0;
+    c.index = (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL)
+                  ? sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, sample, x - R.sampler.sb[0], y - R.sampler.sb[1])
+                  : halton_index(R.sampler, sample, x, y);
+    // get_camera_sample, sampler.rs:170-180
+    float2 u = get_2d(R.sampler, c);
+    float2 pfilm = make_float2((float)x + u.x, (float)y + u.y);
+    float tu = get_1d(R.sampler, c);
+    float2 plens = get_2d(R.sampler, c);
+    f3 o, d;
+    float time;
+    generate_ray(R.camera, pfilm, tu, plens, &o, &d, &time);
+    R.ray[2 * slot] = make_float4(o.x, o.y, o.z, PB_INF);
+    R.ray[2 * slot + 1] = make_float4(d.x, d.y, d.z, time);
+    R.L_eta[slot] = make_float4(0.f, 0.f, 0.f, 1.0f);
+    R.beta_st[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
+    R.pfilm[slot] = pfilm;
+    R.s_index[slot] = c.index;
+    R.s_dim[slot] = c.dim;
+    R.pixel[slot] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
+    return true;
+}
+
+// Start of a render call: every path slot is free and carries no sample.
+__global__ void __launch_bounds__(256) k_init_slots(RenderDev R, uint32_t count) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        R.q_dead[1][i] = i;
+        R.pixel[i] = PB_NO_SAMPLE;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) R.cnt->n_dead = count;
 }
 
 // ---------------------------------------------------------------------------
@@ -769,7 +775,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
         queue_push(q_next, &R.cnt->n_next, id, push_next);
         queue_push(R.q_shadow, &R.cnt->n_shadow, id, push_shadow);
         queue_push(R.q_mis, &R.cnt->n_mis, id, push_mis);
-        queue_push(R.q_dead, &R.cnt->n_dead, id, push_dead);
+        queue_push(R.q_dead[parity], &R.cnt->n_dead, id, push_dead);
     }
 }
 
@@ -841,15 +847,24 @@ __global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_mis(RenderDev R) {
 // ---------------------------------------------------------------------------
 // K8: finished paths -> film
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_finish(RenderDev R) {
+// K8 + K1 fused ("path regeneration"): a finished path adds its sample to the film, then its slot is handed the next
+// camera sample of the call, so every iteration traces a full complement of rays instead of the dwindling tail of one wave.
+__global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, unsigned long long total_items) {
     const uint32_t n = R.cnt->n_dead;
     const uint32_t nround = (n + 31u) & ~31u;
+    const unsigned long long cursor = R.cnt->item_cursor;  // advanced by k_iter_end
+    const unsigned long long remaining = total_items > cursor ? total_items - cursor : 0ull;
+    const uint32_t* q = R.q_dead[parity];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
-        bool valid = i < n;
+        bool valid = i < n, has_sample = false;
         rgb L(0.0f);
         float2 pf = make_float2(0.f, 0.f);
+        uint32_t id = 0;
         if (valid) {
-            uint32_t id = R.q_dead[i];
+            id = q[i];
+            has_sample = R.pixel[id] != PB_NO_SAMPLE;
+        }
+        if (has_sample) {
             float4 Le = R.L_eta[id];
             L = rgb(Le.x, Le.y, Le.z);
             pf = R.pfilm[id];
@@ -859,18 +874,28 @@ __global__ void __launch_bounds__(256) k_finish(RenderDev R) {
             else if (y < -1.0e-5f) L = rgb(0.0f);
             else if (isinf(y)) L = rgb(0.0f);
         }
-        film_add_sample(R, pf, L, valid);
+        film_add_sample(R, pf, L, has_sample);
+        bool regen = valid && (unsigned long long)i < remaining, ok = false;
+        if (regen) ok = gen_camera_path(R, cursor + i, id);
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
+        queue_push(R.q_path[parity ^ 1], &R.cnt->n_next, id, ok);
+        queue_push(R.q_dead[parity ^ 1], &R.cnt->n_dead_next, id, regen && !ok);
     }
 }
 
 // single-thread bookkeeping between iterations: roll queue counters, accumulate stats
-__global__ void k_iter_end(Counters* c) {
+__global__ void k_iter_end(Counters* c, unsigned long long total_items) {
     c->closest_rays += (unsigned long long)c->n_path + c->n_mis;
     c->shadow_rays += c->n_shadow;
+    unsigned long long remaining = total_items > c->item_cursor ? total_items - c->item_cursor : 0ull;
+    c->item_cursor += remaining < (unsigned long long)c->n_dead ? remaining : (unsigned long long)c->n_dead;
     c->n_path = c->n_next;
-    c->n_next = 0; c->n_shadow = 0; c->n_mis = 0; c->n_dead = 0;
+    c->n_dead = c->n_dead_next;
+    c->n_next = 0; c->n_shadow = 0; c->n_mis = 0; c->n_dead_next = 0;
     c->fetch_path = 0; c->fetch_shadow = 0; c->fetch_mis = 0;
     for (int k = 0; k < Q_COUNT; ++k) c->n_mat[k] = 0;
+    c->iterations += 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -1059,7 +1084,7 @@ int ensure_buffers(SceneRenderState* st, uint32_t capacity) {
     A(d.ray, 2 * (size_t)capacity); A(d.hit, capacity); A(d.hit_b2, capacity); A(d.hit_bin, capacity); A(d.L_eta, capacity); A(d.beta_st, capacity); A(d.pfilm, capacity);
     A(d.s_index, capacity); A(d.s_dim, capacity); A(d.pixel, capacity);
     A(d.sh_ray, 2 * (size_t)capacity); A(d.sh_contrib, capacity); A(d.mis_ray, 2 * (size_t)capacity); A(d.mis_contrib, capacity);
-    A(d.q_path[0], capacity); A(d.q_path[1], capacity); A(d.q_shadow, capacity); A(d.q_mis, capacity); A(d.q_dead, capacity);
+    A(d.q_path[0], capacity); A(d.q_path[1], capacity); A(d.q_shadow, capacity); A(d.q_mis, capacity); A(d.q_dead[0], capacity); A(d.q_dead[1], capacity);
     for (int k = 0; k < Q_COUNT; ++k) A(d.q_mat[k], capacity);
     A(d.cnt, 1);
 #undef A
@@ -1185,13 +1210,22 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
     PB_CUDA_TRY(cudaEventRecord(ev0, stream));
     if (total_items > 0) {
-        for (unsigned long long base = 0; base < total_items; base += capacity) {
-            uint32_t count = (uint32_t)std::min<unsigned long long>(capacity, total_items - base);
-            k_raygen<<<grid_small, 256, 0, stream>>>(R, base, count);
-            launches++;
-            int parity = 0;
-            int iter = 0;
-            for (;;) {
+        // Persistent wavefront: all `capacity` slots start free; each iteration traces every live path one segment,
+        // shades, resolves shadow/MIS rays, then k_finish_regen retires finished paths and refills their slots.
+        struct Progress { unsigned long long cursor; uint32_t n_path; uint32_t pad; };
+        Progress* prog = nullptr;
+        PB_CUDA_TRY(cudaMallocHost((void**)&prog, sizeof(Progress)));
+        k_init_slots<<<grid_small, 256, 0, stream>>>(R, capacity);
+        k_finish_regen<<<grid_small, 256, 0, stream>>>(R, 1, total_items);
+        k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
+        launches += 3;
+        int parity = 0;
+        unsigned long long iter = 0;
+        const unsigned long long iter_cap = (total_items / capacity + 2) * (unsigned long long)(R.max_depth + 2) + 4096;
+        int poll = 4;
+        bool done = false;
+        while (!done) {
+            for (int b = 0; b < poll; ++b) {
                 if (timing) mark();
                 k_trace_closest<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R, parity);
                 if (timing) mark();
@@ -1208,21 +1242,24 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (timing) mark();
                 k_trace_mis<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 if (timing) mark();
-                k_finish<<<grid_small, 256, 0, stream>>>(R);
-                k_iter_end<<<1, 1, 0, stream>>>(R.cnt);
+                k_finish_regen<<<grid_small, 256, 0, stream>>>(R, parity, total_items);
+                k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
                 launches += 13;
                 parity ^= 1;
                 iter++;
-                if (iter > R.max_depth) {
-                    // every path has had max_depth+1 intersections unless it crossed pass-through surfaces
-                    uint32_t left = 0;
-                    PB_CUDA_TRY(cudaMemcpyAsync(&left, &R.cnt->n_path, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-                    PB_CUDA_TRY(cudaStreamSynchronize(stream));
-                    if (left == 0) break;
-                    if (iter > R.max_depth + 4096) return fail(PBRT_B200_ERR_CUDA, "render: path queue failed to drain");
-                }
             }
+            // progress check: {item_cursor, n_path} are adjacent in Counters? no -- two small copies
+            cudaMemcpyAsync(&prog->cursor, &R.cnt->item_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+            cudaMemcpyAsync(&prog->n_path, &R.cnt->n_path, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+            cudaError_t e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { cudaFreeHost(prog); PB_CUDA_TRY(e); }
+            if (prog->cursor >= total_items) {
+                if (prog->n_path == 0) done = true;
+                poll = 1;  // draining: at most max_depth more iterations, stop as soon as the queue is empty
+            }
+            if (iter > iter_cap) { cudaFreeHost(prog); return fail(PBRT_B200_ERR_CUDA, "render: path queue failed to drain"); }
         }
+        cudaFreeHost(prog);
     }
     PB_CUDA_TRY(cudaEventRecord(ev1, stream));
     PB_CUDA_TRY(cudaGetLastError());

@@ -13,6 +13,9 @@
 // (`tmin < ray.t_max`) is re-evaluated when the entry is popped -- which is when the
 // reference would have tested that node.
 #pragma once
+#ifndef PB_PACKED_SLAB
+#define PB_PACKED_SLAB 1  /* FADD2/FMUL2 two-child slab test: +2-3% on B200 (tools/trace_ab3.py), bit-identical */
+#endif
 #include "scene.cuh"
 #include "vecmath.cuh"
 
@@ -204,6 +207,24 @@ PB_D bool slab_fast(float nx, float ny, float nz, float fx, float fy, float fz, 
     return (tmin <= tmax) && (tmax > 0.0f);
 }
 
+// Both children of a fat node at once with Blackwell's packed f32x2 pipe (FADD2 / FMUL2: two IEEE-rounded f32
+// results per issue slot).  Lane .x = child 0, .y = child 1.  Every product and difference is rounded exactly as in
+// slab_fast (sub -> mul -> mul can never contract), so the results are bit-identical.
+struct SlabPair { float tmin0, tmin1; bool ok0, ok1; };
+PB_D SlabPair slab_fast2(float2 nx, float2 ny, float2 nz, float2 fx, float2 fy, float2 fz, float2 nox, float2 noy, float2 noz, float2 ix, float2 iy, float2 iz) {
+    const float w = 1.0f + 2.0f * gamma_n(3);
+    const float2 widen = make_float2(w, w);
+    float2 tx0 = __fmul2_rn(__fadd2_rn(nx, nox), ix), ty0 = __fmul2_rn(__fadd2_rn(ny, noy), iy), tz0 = __fmul2_rn(__fadd2_rn(nz, noz), iz);
+    float2 tx1 = __fmul2_rn(__fmul2_rn(__fadd2_rn(fx, nox), ix), widen), ty1 = __fmul2_rn(__fmul2_rn(__fadd2_rn(fy, noy), iy), widen),
+           tz1 = __fmul2_rn(__fmul2_rn(__fadd2_rn(fz, noz), iz), widen);
+    SlabPair r;
+    r.tmin0 = fmaxf(fmaxf(tx0.x, ty0.x), tz0.x); r.tmin1 = fmaxf(fmaxf(tx0.y, ty0.y), tz0.y);
+    float tmax0 = fminf(fminf(tx1.x, ty1.x), tz1.x), tmax1 = fminf(fminf(tx1.y, ty1.y), tz1.y);
+    r.ok0 = (r.tmin0 <= tmax0) && (tmax0 > 0.0f);
+    r.ok1 = (r.tmin1 <= tmax1) && (tmax1 > 0.0f);
+    return r;
+}
+
 #define PB_STACK_DEPTH 64  /* bvh.rs:722 nodes_tovisit = vec![0; 64] */
 #define PB_DONE 0xffffffffu /* traversal finished (has the leaf bit set so the interior loop exits) */
 
@@ -220,6 +241,9 @@ struct TravRay {
     bool ngx, ngy, ngz, found;
     bool nan_possible;  // a zero direction component: 0 * inf can appear in the slab test
     RayHit hit;
+#if PB_PACKED_SLAB
+    float2 nox, noy, noz, ivx, ivy, ivz;  // {-o, -o} and {1/d, 1/d} per axis for slab_fast2
+#endif
 };
 
 PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) {
@@ -229,6 +253,10 @@ PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) {
     r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     r.ngx = r.inv.x < 0.0f; r.ngy = r.inv.y < 0.0f; r.ngz = r.inv.z < 0.0f;
     r.nan_possible = (d.x == 0.0f) || (d.y == 0.0f) || (d.z == 0.0f);
+#if PB_PACKED_SLAB
+    r.nox = make_float2(-o.x, -o.x); r.noy = make_float2(-o.y, -o.y); r.noz = make_float2(-o.z, -o.z);
+    r.ivx = make_float2(r.inv.x, r.inv.x); r.ivy = make_float2(r.inv.y, r.inv.y); r.ivz = make_float2(r.inv.z, r.inv.z);
+#endif
     // ray-constant part of the watertight test (triangle.rs:151-165)
     f3 ad = vabs(d);
     r.kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
@@ -258,7 +286,7 @@ PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) {
 // Runs the ray until it finishes, or (when `yield_below` > 0) until fewer than `yield_below`
 // lanes of the warp are still traversing, so that the caller can refill idle lanes.
 template <bool ANY, bool EXACT_NAN>
-PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_below) {
+PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
     while (r.cur != PB_DONE) {
         // ---- interior nodes
         while (!(r.cur & PB_LEAF_BIT)) {
@@ -273,10 +301,18 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
                 ok1 = slab_test(r.ngx ? q2.y : q1.z, r.ngy ? q2.z : q1.w, r.ngz ? q2.w : q2.x, r.ngx ? q1.z : q2.y, r.ngy ? q1.w : q2.z,
                                 r.ngz ? q2.x : q2.w, r.o, r.inv, &tmin1);
             } else {
+#if PB_PACKED_SLAB
+                SlabPair sp2 = slab_fast2(make_float2(r.ngx ? q0.w : q0.x, r.ngx ? q2.y : q1.z), make_float2(r.ngy ? q1.x : q0.y, r.ngy ? q2.z : q1.w),
+                                          make_float2(r.ngz ? q1.y : q0.z, r.ngz ? q2.w : q2.x), make_float2(r.ngx ? q0.x : q0.w, r.ngx ? q1.z : q2.y),
+                                          make_float2(r.ngy ? q0.y : q1.x, r.ngy ? q1.w : q2.z), make_float2(r.ngz ? q0.z : q1.y, r.ngz ? q2.x : q2.w),
+                                          r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
+                ok0 = sp2.ok0; ok1 = sp2.ok1; tmin0 = sp2.tmin0; tmin1 = sp2.tmin1;
+#else
                 ok0 = slab_fast(r.ngx ? q0.w : q0.x, r.ngy ? q1.x : q0.y, r.ngz ? q1.y : q0.z, r.ngx ? q0.x : q0.w, r.ngy ? q0.y : q1.x,
                                 r.ngz ? q0.z : q1.y, r.o, r.inv, &tmin0);
                 ok1 = slab_fast(r.ngx ? q2.y : q1.z, r.ngy ? q2.z : q1.w, r.ngz ? q2.w : q2.x, r.ngx ? q1.z : q2.y, r.ngy ? q1.w : q2.z,
                                 r.ngz ? q2.x : q2.w, r.o, r.inv, &tmin1);
+#endif
             }
             // near child = second child when the ray is negative along the split axis (bvh.rs:743-751)
             bool second_first = (axis == 0) ? r.ngx : ((axis == 1) ? r.ngy : r.ngz);
@@ -295,10 +331,12 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
             } else {
                 PB_TRAV_POP(r, stack);
             }
+            // few lanes left descending while the rest of the warp waits at leaves: let the leaves run first
+            if (interior_min > 0 && __popc(__activemask()) < interior_min) break;
         }
         if (r.cur == PB_DONE) break;
         // ---- leaf run (bvh.rs:730-736): every primitive of the leaf, in order
-        {
+        if (r.cur & PB_LEAF_BIT) {
             uint32_t slot = r.cur & ~PB_LEAF_BIT;
             uint32_t fl;
             do {
@@ -335,9 +373,9 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
 }
 
 template <bool ANY>
-PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below) {
-    if (r.nan_possible) trav_run_impl<ANY, true>(s, r, stack, yield_below);
-    else trav_run_impl<ANY, false>(s, r, stack, yield_below);
+PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min = 0) {
+    if (r.nan_possible) trav_run_impl<ANY, true>(s, r, stack, yield_below, interior_min);
+    else trav_run_impl<ANY, false>(s, r, stack, yield_below, interior_min);
 }
 
 // Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray, run to completion.
@@ -450,9 +488,12 @@ PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit)
 //     void store(uint32_t idx, const TravRay& r)
 #define PB_FETCH_CHUNK 32   /* tools/trace_ab.py: larger chunks cost coherent rays 25-45% */
 #define PB_REFILL_BELOW 24
-struct TraceTune { int refill_below; int chunk; };
+#ifndef PB_INTERIOR_MIN
+#define PB_INTERIOR_MIN 16
+#endif
+struct TraceTune { int refill_below; int chunk; int interior_min; };
 template <bool ANY, typename Job>
-PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_counter, TraceTune tune = TraceTune{PB_REFILL_BELOW, PB_FETCH_CHUNK}) {
+PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_counter, TraceTune tune = TraceTune{PB_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN}) {
     uint2 stack[PB_STACK_DEPTH];
     TravRay r;
     r.cur = PB_DONE; r.sp = 0; r.found = false;
@@ -489,7 +530,7 @@ PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_c
             need &= ~took;
         }
         if (__all_sync(0xffffffffu, ray_idx == 0xffffffffu)) break;
-        trav_run<ANY>(s, r, stack, exhausted ? 0 : tune.refill_below);
+        trav_run<ANY>(s, r, stack, exhausted ? 0 : tune.refill_below, tune.interior_min);
     }
 }
 

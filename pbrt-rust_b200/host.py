@@ -118,9 +118,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise B200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
-    lib = C.CDLL(str(LIB_PATH))
+    import os
+    path = Path(os.environ.get("PBRT_B200_LIB", LIB_PATH))  # A/B builds (csrc/Makefile `variant`); still a CUDA library, never a fallback
+    if not path.exists():
+        raise B200Error(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    lib = C.CDLL(str(path))
     lib.pbrt_b200_last_error.restype = C.c_char_p
     lib.pbrt_b200_bvh_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     lib.pbrt_b200_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
