@@ -617,8 +617,16 @@ PB_D void store_ray(float4* rays, uint32_t id, f3 o, f3 d, float t_max, float ti
     rays[2 * id + 1] = make_float4(d.x, d.y, d.z, time);
 }
 
+template <int BIN> struct BinKinds { static constexpr int KM = KM_ALL, MAT = -1; };
+template <> struct BinKinds<Q_MATTE> { static constexpr int KM = KM_MATTE, MAT = PBRT_B200_MAT_MATTE; };
+template <> struct BinKinds<Q_PLASTIC> { static constexpr int KM = KM_PLASTIC, MAT = PBRT_B200_MAT_PLASTIC; };
+template <> struct BinKinds<Q_MIRROR> { static constexpr int KM = KM_MIRROR, MAT = PBRT_B200_MAT_MIRROR; };
+template <> struct BinKinds<Q_GLASS> { static constexpr int KM = KM_GLASS, MAT = PBRT_B200_MAT_GLASS; };
+template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT = PBRT_B200_MAT_METAL; };
+
 template <int BIN>
 __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
+    constexpr int KM = BinKinds<BIN>::KM;
     const uint32_t n = R.cnt->n_mat[BIN];
     const uint32_t* q = R.q_mat[BIN];
     uint32_t* q_next = R.q_path[parity ^ 1];
@@ -660,7 +668,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                 } else {
                     Bsdf bsdf;
                     bsdf.valid = false;
-                    if (BIN != Q_NOMAT) material_bsdf(R.scene.materials[pr.material], si, bsdf);
+                    if (BIN != Q_NOMAT && BIN != Q_MISS) material_bsdf<BinKinds<BIN>::MAT>(R.scene.materials[pr.material], si, bsdf);
                     if (!bsdf.valid) {
                         // path.rs:124-129: skip the surface, bounces NOT incremented
                         f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
@@ -690,8 +698,8 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                                 light_sample_li(R, ln, si.p, ulight, ls);
                                 float scattpdf = 0.0f;
                                 if (ls.pdf > 0.0f && !is_black(ls.Li)) {
-                                    rgb f = bsdf_f(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
-                                    scattpdf = bsdf_pdf(bsdf, si.wo, ls.wi, NONSPEC);
+                                    rgb f = bsdf_f<KM>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
+                                    scattpdf = bsdf_pdf<KM>(bsdf, si.wo, ls.wi, NONSPEC);
                                     if (!is_black(f)) {
                                         // VisibilityTester::unoccluded -> spawn_rayto_interaction, interaction.rs:46-52
                                         f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
@@ -708,7 +716,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                                 if (!delta) {
                                     f3 wi(0.f, 0.f, 0.f);
                                     int stype = 0;
-                                    rgb f = bsdf_sample(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
+                                    rgb f = bsdf_sample<KM>(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
                                     f = f * absdot(wi, si.sh_n);
                                     if (!is_black(f) && scattpdf > 0.0f) {
                                         float weight = 1.0f;
@@ -736,7 +744,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
                         float pdf = 0.0f;
                         int flags = 0;
                         float2 ub = get_2d(sb);
-                        rgb f = bsdf_sample(bsdf, wo, &wi, ub, &pdf, BX_ALL, &flags);
+                        rgb f = bsdf_sample<KM>(bsdf, wo, &wi, ub, &pdf, BX_ALL, &flags);
                         bool alive = !(is_black(f) || pdf == 0.0f);
                         if (alive) {
                             beta = beta * (f * absdot(wi, si.sh_n) / pdf);

@@ -288,10 +288,19 @@ struct Lobe {
 
 PB_D bool lobe_matches(const Lobe& l, int flags) { return (l.type & flags) == l.type; }
 
+// KM = compile-time mask of the lobe kinds a material can produce (1 << LobeKind): the shade kernel of one
+// material bin carries only that material's BxDF code (smaller kernels, fewer registers); KM_ALL = generic.
+#define KM_ALL 0x7f
+#define KM_HAS(k) ((KM & (1 << (k))) != 0)
+enum { KM_MATTE = (1 << LOBE_LAMBERT) | (1 << LOBE_OREN_NAYAR), KM_PLASTIC = (1 << LOBE_LAMBERT) | (1 << LOBE_MICRO_REFL_DIEL), KM_MIRROR = 1 << LOBE_MIRROR,
+       KM_GLASS = (1 << LOBE_FRESNEL_SPECULAR) | (1 << LOBE_MICRO_REFL_DIEL) | (1 << LOBE_MICRO_TRANS), KM_METAL = 1 << LOBE_MICRO_REFL_COND };
+
+template <int KM = KM_ALL>
 PB_D rgb lobe_f(const Lobe& l, f3 wo, f3 wi) {
     switch (l.kind) {
-        case LOBE_LAMBERT: return l.c0 * PB_INV_PI;  // reflection.rs:823-825
+        case LOBE_LAMBERT: if (!KM_HAS(LOBE_LAMBERT)) break; return l.c0 * PB_INV_PI;  // reflection.rs:823-825
         case LOBE_OREN_NAYAR: {                        // reflection.rs:925-952
+            if (!KM_HAS(LOBE_OREN_NAYAR)) break;
             float sti = sin_theta(wi), sto = sin_theta(wo);
             float max_cos = 0.0f;
             if (sti > 1e-4f && sto > 1e-4f) {
@@ -306,17 +315,20 @@ PB_D rgb lobe_f(const Lobe& l, f3 wo, f3 wi) {
         case LOBE_FRESNEL_SPECULAR: return rgb(1.0f);  // reflection.rs:745-747 (reference quirk)
         case LOBE_MICRO_REFL_DIEL:
         case LOBE_MICRO_REFL_COND: {  // reflection.rs:985-1003
+            if (!KM_HAS(LOBE_MICRO_REFL_DIEL) && !KM_HAS(LOBE_MICRO_REFL_COND)) break;
             float cto = fabsf(wo.z), cti = fabsf(wi.z);
             f3 wh = wi + wo;
             if (cti == 0.0f || cto == 0.0f) return rgb(0.0f);
             if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return rgb(0.0f);
             wh = normalize(wh);
             float cih = dot(wi, wh);
-            rgb F = (l.kind == LOBE_MICRO_REFL_DIEL) ? rgb(fr_dielectric(cih, l.p0, l.p1)) : fr_conductor(fabsf(cih), l.c1, l.c2);
+            const bool diel = !KM_HAS(LOBE_MICRO_REFL_COND) || (KM_HAS(LOBE_MICRO_REFL_DIEL) && l.kind == LOBE_MICRO_REFL_DIEL);
+            rgb F = diel ? rgb(fr_dielectric(cih, l.p0, l.p1)) : fr_conductor(fabsf(cih), l.c1, l.c2);
             float d = tr_d(l.tr, wh), g = tr_g(l.tr, wo, wi);
             return l.c0 * d * g * F / (4.0f * cti * cto);
         }
         case LOBE_MICRO_TRANS: {  // reflection.rs:1064-1095
+            if (!KM_HAS(LOBE_MICRO_TRANS)) break;
             if (same_hemi(wo, wi)) return rgb(0.0f);
             float cto = wo.z, cti = wi.z;
             if (cti == 0.0f || cto == 0.0f) return rgb(0.0f);
@@ -334,17 +346,20 @@ PB_D rgb lobe_f(const Lobe& l, f3 wo, f3 wi) {
     return rgb(0.0f);
 }
 
+template <int KM = KM_ALL>
 PB_D float lobe_pdf(const Lobe& l, f3 wo, f3 wi) {
     switch (l.kind) {
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR: case LOBE_FRESNEL_SPECULAR:
             return same_hemi(wo, wi) ? fabsf(wi.z) * PB_INV_PI : 0.0f;  // reflection.rs:438-445, 788-794
         case LOBE_MIRROR: return 0.0f;
         case LOBE_MICRO_REFL_DIEL: case LOBE_MICRO_REFL_COND: {  // reflection.rs:1021-1027
+            if (!KM_HAS(LOBE_MICRO_REFL_DIEL) && !KM_HAS(LOBE_MICRO_REFL_COND)) break;
             if (!same_hemi(wo, wi)) return 0.0f;
             f3 wh = normalize(wo + wi);
             return tr_pdf(l.tr, wo, wh) / (4.0f * dot(wo, wh));
         }
         case LOBE_MICRO_TRANS: {  // reflection.rs:1115-1129
+            if (!KM_HAS(LOBE_MICRO_TRANS)) break;
             if (same_hemi(wo, wi)) return 0.0f;
             float eta = wo.z > 0.0f ? l.p0 / l.p1 : l.p1 / l.p0;
             f3 wh = normalize(wo + wi * eta);
@@ -359,20 +374,24 @@ PB_D float lobe_pdf(const Lobe& l, f3 wo, f3 wi) {
 
 // BxDF::sample_f; *pdf and *stype keep their incoming values on early returns, like the
 // reference's &mut parameters.
+template <int KM = KM_ALL>
 PB_D rgb lobe_sample(const Lobe& l, f3 wo, f3* wi, float2 u, float* pdf, int* stype) {
     switch (l.kind) {
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR: {  // reflection.rs:392-405
+            if (!KM_HAS(LOBE_LAMBERT) && !KM_HAS(LOBE_OREN_NAYAR)) break;
             *wi = cosine_hemisphere(u);
             if (wo.z < 0.0f) wi->z *= -1.0f;
-            *pdf = lobe_pdf(l, wo, *wi);
-            return lobe_f(l, wo, *wi);
+            *pdf = lobe_pdf<KM>(l, wo, *wi);
+            return lobe_f<KM>(l, wo, *wi);
         }
         case LOBE_MIRROR: {  // reflection.rs:634-640, FresnelNoOp
+            if (!KM_HAS(LOBE_MIRROR)) break;
             *wi = f3(-wo.x, -wo.y, wo.z);
             *pdf = 1.0f;
             return rgb(1.0f) * l.c0 / fabsf(wi->z);
         }
         case LOBE_FRESNEL_SPECULAR: {  // reflection.rs:749-786
+            if (!KM_HAS(LOBE_FRESNEL_SPECULAR)) break;
             float F = fr_dielectric(wo.z, l.p0, l.p1);
             if (u.x < F) {
                 *wi = f3(-wo.x, -wo.y, wo.z);
@@ -390,22 +409,24 @@ PB_D rgb lobe_sample(const Lobe& l, f3 wo, f3* wi, float2 u, float* pdf, int* st
             return ft / fabsf(wi->z);
         }
         case LOBE_MICRO_REFL_DIEL: case LOBE_MICRO_REFL_COND: {  // reflection.rs:1005-1019
+            if (!KM_HAS(LOBE_MICRO_REFL_DIEL) && !KM_HAS(LOBE_MICRO_REFL_COND)) break;
             if (wo.z == 0.0f) return rgb(0.0f);
             f3 wh = tr_sample_wh(l.tr, wo, u);
             if (dot(wo, wh) < 0.0f) return rgb(0.0f);
             *wi = reflect_about(wo, wh);
             if (!same_hemi(wo, *wi)) return rgb(0.0f);
             *pdf = tr_pdf(l.tr, wo, wh) / (4.0f * dot(wo, wh));
-            return lobe_f(l, wo, *wi);
+            return lobe_f<KM>(l, wo, *wi);
         }
         case LOBE_MICRO_TRANS: {  // reflection.rs:1097-1113
+            if (!KM_HAS(LOBE_MICRO_TRANS)) break;
             if (wo.z == 0.0f) return rgb(0.0f);
             f3 wh = tr_sample_wh(l.tr, wo, u);
             if (dot(wo, wh) < 0.0f) return rgb(0.0f);
             float eta = wo.z > 0.0f ? l.p0 / l.p1 : l.p1 / l.p0;
             if (!refract_dir(wo, wh, eta, wi)) return rgb(0.0f);
-            *pdf = lobe_pdf(l, wo, *wi);
-            return lobe_f(l, wo, *wi);
+            *pdf = lobe_pdf<KM>(l, wo, *wi);
+            return lobe_f<KM>(l, wo, *wi);
         }
     }
     return rgb(0.0f);
@@ -427,6 +448,7 @@ PB_D f3 to_world(const Bsdf& b, f3 v) {
     return f3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z, b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
 PB_D int bsdf_count(const Bsdf& b, int flags) { int c = 0; for (int i = 0; i < b.n; ++i) c += lobe_matches(b.lobe[i], flags) ? 1 : 0; return c; }
+template <int KM = KM_ALL>
 PB_D rgb bsdf_f(const Bsdf& b, f3 wow, f3 wiw, int flags) {
     f3 wi = to_local(b, wiw), wo = to_local(b, wow);
     if (wo.z == 0.0f) return rgb(0.0f);
@@ -434,10 +456,11 @@ PB_D rgb bsdf_f(const Bsdf& b, f3 wow, f3 wiw, int flags) {
     rgb res(0.0f);
     for (int i = 0; i < b.n; ++i) {
         const Lobe& l = b.lobe[i];
-        if (lobe_matches(l, flags) && ((refl && (l.type & BX_REFLECTION)) || (!refl && (l.type & BX_TRANSMISSION)))) res = res + lobe_f(l, wo, wi);
+        if (lobe_matches(l, flags) && ((refl && (l.type & BX_REFLECTION)) || (!refl && (l.type & BX_TRANSMISSION)))) res = res + lobe_f<KM>(l, wo, wi);
     }
     return res;
 }
+template <int KM = KM_ALL>
 PB_D float bsdf_pdf(const Bsdf& b, f3 wow, f3 wiw, int flags) {
     if (b.n == 0) return 0.0f;
     f3 wo = to_local(b, wow), wi = to_local(b, wiw);
@@ -445,10 +468,11 @@ PB_D float bsdf_pdf(const Bsdf& b, f3 wow, f3 wiw, int flags) {
     float p = 0.0f;
     int m = 0;
     for (int i = 0; i < b.n; ++i)
-        if (lobe_matches(b.lobe[i], flags)) { m += 1; p += lobe_pdf(b.lobe[i], wo, wi); }
+        if (lobe_matches(b.lobe[i], flags)) { m += 1; p += lobe_pdf<KM>(b.lobe[i], wo, wi); }
     return m > 0 ? p / (float)m : 0.0f;
 }
 // *pdf / *stype in-out as in the reference (path.rs initialises pdf = 0, flags = 0).
+template <int KM = KM_ALL>
 PB_D rgb bsdf_sample(const Bsdf& b, f3 wow, f3* wiw, float2 u, float* pdf, int flags, int* stype) {
     int m = bsdf_count(b, flags);
     if (m == 0) { *pdf = 0.0f; *stype = 0; return rgb(0.0f); }
@@ -468,19 +492,19 @@ PB_D rgb bsdf_sample(const Bsdf& b, f3 wow, f3* wiw, float2 u, float* pdf, int f
     if (wo.z == 0.0f) return rgb(0.0f);
     *pdf = 0.0f;
     *stype = l.type;
-    rgb f = lobe_sample(l, wo, &wi, ur, pdf, stype);
+    rgb f = lobe_sample<KM>(l, wo, &wi, ur, pdf, stype);
     if (*pdf == 0.0f) { *stype = 0; return rgb(0.0f); }
     *wiw = to_world(b, wi);
     if ((l.type & BX_SPECULAR) == 0 && m > 1)
         for (int i = 0; i < b.n; ++i)
-            if (i != idx && lobe_matches(b.lobe[i], flags)) *pdf += lobe_pdf(b.lobe[i], wo, wi);
+            if (i != idx && lobe_matches(b.lobe[i], flags)) *pdf += lobe_pdf<KM>(b.lobe[i], wo, wi);
     if (m > 1) *pdf /= fm;
     if ((l.type & BX_SPECULAR) == 0) {
         bool refl = dot(*wiw, b.ng) * dot(wow, b.ng) > 0.0f;
         f = rgb(0.0f);
         for (int i = 0; i < b.n; ++i) {
             const Lobe& q = b.lobe[i];
-            if (lobe_matches(q, flags) && ((refl && (q.type & BX_REFLECTION)) || (!refl && (q.type & BX_TRANSMISSION)))) f = f + lobe_f(q, wo, wi);
+            if (lobe_matches(q, flags) && ((refl && (q.type & BX_REFLECTION)) || (!refl && (q.type & BX_TRANSMISSION)))) f = f + lobe_f<KM>(q, wo, wi);
         }
     }
     return f;
@@ -488,10 +512,12 @@ PB_D rgb bsdf_sample(const Bsdf& b, f3 wow, f3* wiw, float2 u, float* pdf, int f
 
 // Material::compute_scattering_functions for the five hot materials (constant textures, no
 // bump, allow_multiple_lobes = true, mode = Radiance).
+// MAT >= 0: the material type is known at compile time (the shade kernel of that bin).
+template <int MAT = -1>
 PB_D void material_bsdf(const pbrt_b200_material& m, const Surf& si, Bsdf& b) {
     b.valid = false; b.n = 0;
     rgb A = rgb_clamp0(rgb3(m.a)), B = rgb_clamp0(rgb3(m.b));
-    switch (m.type) {
+    switch (MAT >= 0 ? (uint32_t)MAT : m.type) {
         case PBRT_B200_MAT_MATTE: {  // materials/matte.rs:28-52
             bsdf_init(b, si, 1.0f);
             float sig = clampf(m.f0, 0.0f, 90.0f);
