@@ -283,6 +283,9 @@ typedef struct pbrt_b200_render_stats {
     double   device_ms;            /* CUDA-event time of the wavefront loop          */
     double   trace_closest_ms;     /* of which: closest-hit traversal kernel         */
     double   trace_any_ms;         /* of which: any-hit traversal kernel             */
+    double   shade_ms;             /* of which: classify + shade<material> kernels   */
+    double   finish_ms;            /* of which: film accumulation + path regeneration */
+    uint64_t iterations;           /* wavefront iterations (one path segment each)   */
 } pbrt_b200_render_stats;
 
 /* SamplerIntegrator::render (src/core/integrator.rs:263-403) minus file output:

@@ -161,6 +161,25 @@ int orc_render(const pbrt_b200_scene_desc* sdesc, const pbrt_b200_render_desc* r
     return 0;
 }
 
+// SpatialLightDistribution::lookup (lightdistrib.rs:231-340) at n points: voxel[3*n] (integer voxel coordinates) and
+// func[n * n_lights] (the per-voxel light_contrib the Distribution1D is built from).  nvoxels_out[3] = grid resolution.
+int orc_spatial_lookup(const pbrt_b200_scene_desc* sdesc, const float* points, uint64_t n, int32_t* voxel, float* func, int32_t* nvoxels_out) {
+    RenderScene scene;
+    scene.init_render(*sdesc);
+    SpatialLightDistribution sp(&scene, 64);
+    const size_t nl = sdesc->n_lights;
+    for (int k = 0; k < 3; ++k) nvoxels_out[k] = (int32_t)sp.nvoxels[k];
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 p(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+        int64_t pi[3];
+        sp.voxel_of(p, pi);
+        for (int k = 0; k < 3; ++k) voxel[3 * i + k] = (int32_t)pi[k];
+        const Distribution1D& d = sp.lookup(p);
+        for (size_t j = 0; j < nl; ++j) func[i * nl + j] = d.func[j];
+    }
+    return 0;
+}
+
 // Film::write_image arithmetic (film.rs:217-264) on an {r,g,b,w} buffer
 void orc_film_resolve(const float* rgbw, uint64_t npix, float scale, float* rgb) {
     for (uint64_t i = 0; i < npix; ++i) {

@@ -142,3 +142,15 @@ def rel_mse(img, ref):
     """relMSE of SURVEY.md s8(d): mean over pixels/channels of (a-b)^2 / (b^2 + 1e-2)."""
     a, b = np.asarray(img, np.float64), np.asarray(ref, np.float64)
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
+
+def spatial_lookup(flat, points):
+    """SpatialLightDistribution::lookup at `points` -> (voxel [n,3] int32, func [n,n_lights] f32, nvoxels [3])."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    d = flat.desc()
+    nl = int(d.n_lights)
+    voxel = np.zeros((len(pts), 3), np.int32)
+    func = np.zeros((len(pts), max(nl, 1)), np.float32)
+    nv = np.zeros(3, np.int32)
+    lib().orc_spatial_lookup(C.byref(d), ptr(pts), C.c_uint64(len(pts)), ptr(voxel), ptr(func), ptr(nv))
+    return voxel, func[:, :nl], nv

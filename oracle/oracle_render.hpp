@@ -285,11 +285,81 @@ inline Spectrum estimate_direct(const RenderScene& s, const SurfaceInteraction& 
     return Ld;
 }
 
+// SpatialLightDistribution, src/core/lightdistrib.rs:105-340.  The reference keeps the per-voxel distributions in a
+// lock-free hash table filled on first touch; a voxel's distribution is a pure function of (scene, voxel), so a dense
+// lazily-filled table gives the same answers.
+struct SpatialLightDistribution {
+    const RenderScene* scene = nullptr;
+    size_t nvoxels[3] = {1, 1, 1};
+    mutable std::vector<std::atomic<const Distribution1D*>> table;
+    mutable std::atomic<uint64_t> ncreated{0};
+    SpatialLightDistribution(const RenderScene* s, size_t max_voxels) : scene(s) {  // lightdistrib.rs:113-150
+        const Bounds3& b = s->wb;
+        V3 diag = b.p_max - b.p_min;
+        int me = (diag.x > diag.y && diag.x > diag.z) ? 0 : (diag.y > diag.z ? 1 : 2);  // bounds.rs:346-360
+        Float bmax = diag[me];
+        for (int i = 0; i < 3; ++i) nvoxels[i] = std::max<size_t>(1, (size_t)f2u_sat(std::round(diag[i] / bmax * (Float)max_voxels)));
+        table = std::vector<std::atomic<const Distribution1D*>>(nvoxels[0] * nvoxels[1] * nvoxels[2]);
+        for (auto& e : table) e.store(nullptr);
+    }
+    ~SpatialLightDistribution() { for (auto& e : table) delete e.load(); }
+    // compute_dsitribution, lightdistrib.rs:152-228
+    Distribution1D compute(const int64_t pi[3]) const {
+        const Bounds3& wb = scene->wb;
+        V3 p0((Float)pi[0] / (Float)nvoxels[0], (Float)pi[1] / (Float)nvoxels[1], (Float)pi[2] / (Float)nvoxels[2]);
+        V3 p1((Float)(pi[0] + 1) / (Float)nvoxels[0], (Float)(pi[1] + 1) / (Float)nvoxels[1], (Float)(pi[2] + 1) / (Float)nvoxels[2]);
+        auto blerp = [](const Bounds3& b, V3 t) { return V3(lerp(t.x, b.p_min.x, b.p_max.x), lerp(t.y, b.p_min.y, b.p_max.y), lerp(t.z, b.p_min.z, b.p_max.z)); };
+        V3 a = blerp(wb, p0), c = blerp(wb, p1);
+        Bounds3 vb(V3(std::fmin(a.x, c.x), std::fmin(a.y, c.y), std::fmin(a.z, c.z)), V3(std::fmax(a.x, c.x), std::fmax(a.y, c.y), std::fmax(a.z, c.z)));
+        const size_t nl = scene->d.n_lights;
+        const int nsamples = 128;
+        std::vector<Float> contrib(nl, 0.0f);
+        for (int i = 0; i < nsamples; ++i) {
+            V3 po = blerp(vb, V3(radical_inverse(0, (uint64_t)i), radical_inverse(1, (uint64_t)i), radical_inverse(2, (uint64_t)i)));
+            InteractionData intr; intr.p = po; intr.p_error = V3(0, 0, 0); intr.n = V3(0, 0, 0); intr.time = 0.0f;
+            P2 u(radical_inverse(3, (uint64_t)i), radical_inverse(4, (uint64_t)i));
+            for (size_t j = 0; j < nl; ++j) {
+                LightSample ls = light_sample_li(*scene, (int)j, intr, u);
+                if (ls.pdf > 0.0f) contrib[j] += ls.Li.y() / ls.pdf;
+            }
+        }
+        Float sum = 0.0f;
+        for (Float v : contrib) sum += v;
+        Float avg = sum / ((Float)nsamples * (Float)nl);
+        Float min_contrib = avg > 0.0f ? 0.001f * avg : 1.0f;
+        for (Float& v : contrib) v = std::fmax(v, min_contrib);
+        return Distribution1D(contrib);
+    }
+    void voxel_of(V3 p, int64_t pi[3]) const {  // lightdistrib.rs:236-246
+        const Bounds3& wb = scene->wb;
+        V3 o = p - wb.p_min;  // Bounds3::offset, bounds.rs:372-390
+        if (wb.p_max.x > wb.p_min.x) o.x /= wb.p_max.x - wb.p_min.x;
+        if (wb.p_max.y > wb.p_min.y) o.y /= wb.p_max.y - wb.p_min.y;
+        if (wb.p_max.z > wb.p_min.z) o.z /= wb.p_max.z - wb.p_min.z;
+        for (int i = 0; i < 3; ++i) pi[i] = clamp<int64_t>(f2i_sat(o[i] * (Float)nvoxels[i]), 0, (int64_t)nvoxels[i] - 1);
+    }
+    const Distribution1D& lookup(V3 p) const {
+        int64_t pi[3];
+        voxel_of(p, pi);
+        size_t idx = ((size_t)pi[2] * nvoxels[1] + (size_t)pi[1]) * nvoxels[0] + (size_t)pi[0];
+        const Distribution1D* d = table[idx].load(std::memory_order_acquire);
+        if (!d) {
+            Distribution1D* fresh = new Distribution1D(compute(pi));
+            const Distribution1D* expected = nullptr;
+            if (table[idx].compare_exchange_strong(expected, fresh, std::memory_order_acq_rel)) { d = fresh; ncreated++; }
+            else { delete fresh; d = expected; }
+        }
+        return *d;
+    }
+};
+
 struct IntegratorParams {
     int max_depth = 5;
     Float rr_threshold = 1.0f;
     int pixel_bounds[4];
-    Distribution1D light_distrib;  // uniform or power (spatial: DESIGN.md "next")
+    Distribution1D light_distrib;                       // uniform or power
+    std::shared_ptr<SpatialLightDistribution> spatial;  // "spatial" with more than one light
+    const Distribution1D& lookup(V3 p) const { return spatial ? spatial->lookup(p) : light_distrib; }  // LightDistribution::lookup
 };
 
 // uniform_sample_onelight, src/core/integrator.rs:81-106
@@ -330,9 +400,10 @@ inline Spectrum path_li(const RenderScene& s, const IntegratorParams& ip, Ray ra
             ray = spawn_ray(isect.p, isect.p_error, isect.n, ray.d, isect.time);
             continue;
         }
+        const Distribution1D& distrib = ip.lookup(isect.p);  // path.rs:132
         if (bsdf.num_components(BSDF_ALL & ~BSDF_SPECULAR) > 0) {
             rc.direct_den++;
-            Spectrum Ld = beta * uniform_sample_onelight(s, isect, bsdf, sampler, ip.light_distrib, rc);
+            Spectrum Ld = beta * uniform_sample_onelight(s, isect, bsdf, sampler, distrib, rc);
             if (Ld.is_black()) rc.zero_radiance++;
             L += Ld;
         }
@@ -431,9 +502,13 @@ inline void setup_job(RenderJob& job, const pbrt_b200_scene_desc& sdesc, const p
     // create_light_sample_distribution, lightdistrib.rs:20-31
     size_t nl = sdesc.n_lights;
     std::vector<Float> f(nl, 1.0f);
-    if (!(rd.integrator.light_sample_strategy == PBRT_B200_LIGHTS_UNIFORM || nl == 1))
+    const bool uniform = rd.integrator.light_sample_strategy == PBRT_B200_LIGHTS_UNIFORM || nl == 1;
+    if (!uniform && rd.integrator.light_sample_strategy == PBRT_B200_LIGHTS_POWER)
         for (size_t i = 0; i < nl; ++i) f[i] = light_power(job.scene, sdesc.lights[i]).y();
     job.ip.light_distrib = Distribution1D(f);
+    job.ip.spatial.reset();
+    if (!uniform && rd.integrator.light_sample_strategy != PBRT_B200_LIGHTS_POWER && nl > 0)
+        job.ip.spatial = std::make_shared<SpatialLightDistribution>(&job.scene, 64);
 }
 
 // SamplerIntegrator::render, src/core/integrator.rs:263-403.  rgbw is ADDED to.

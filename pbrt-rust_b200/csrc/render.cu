@@ -927,7 +927,15 @@ struct SceneRenderState {  // cached per scene: light tables
     const void* sobol_src = nullptr;
     float* filter_table = nullptr;
     RenderBuffers* buffers = nullptr;
+    // host-side resources reused by every render call of the scene (cudaMallocHost / cudaEventCreate per call stall the
+    // submitting thread for milliseconds on a busy host while the GPU idles)
+    struct Progress { unsigned long long cursor; uint32_t n_path; uint32_t pad; };
+    Progress* prog = nullptr;            // pinned, PB_PROG_RING entries
+    std::vector<cudaEvent_t> events;     // pool, grown on demand
+    std::vector<pbrt_b200_light> lights_host;
+    bool lights_cached = false;
 };
+#define PB_PROG_RING 4
 
 void render_release_scene_state(pbrt_b200_scene* sc) {
     SceneRenderState* st = reinterpret_cast<SceneRenderState*>(sc->light_distrib);
@@ -935,6 +943,8 @@ void render_release_scene_state(pbrt_b200_scene* sc) {
     cudaFree(st->ld_func); cudaFree(st->ld_cdf); cudaFree(st->inf); cudaFree(st->inf_list);
     cudaFree(st->perms); cudaFree(st->primes); cudaFree(st->prime_sums);
     cudaFree(st->sobol32); cudaFree(st->sobol_t); cudaFree(st->vdc); cudaFree(st->vdc_inv); cudaFree(st->filter_table);
+    if (st->prog) cudaFreeHost(st->prog);
+    for (cudaEvent_t e : st->events) cudaEventDestroy(e);
     delete st->buffers;
     delete st;
     sc->light_distrib = nullptr;
@@ -1069,7 +1079,8 @@ int prepare_scene_state(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, co
         st->n_halton_dims = N;
     }
     if (!st->filter_table) PB_CUDA_TRY(cudaMalloc((void**)&st->filter_table, 256 * sizeof(float)));
-    PB_CUDA_TRY(cudaMemcpy(st->filter_table, rd->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice));
+    PB_CUDA_TRY(cudaMemcpyAsync(st->filter_table, rd->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (!st->prog) PB_CUDA_TRY(cudaMallocHost((void**)&st->prog, PB_PROG_RING * sizeof(SceneRenderState::Progress)));
     *out = st;
     return PBRT_B200_OK;
 }
@@ -1120,11 +1131,16 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         return fail(PBRT_B200_ERR_UNSUPPORTED, "render: lightsamplestrategy \"spatial\" is not built yet (use \"power\" or \"uniform\")");
     PB_CUDA_TRY(cudaSetDevice(sc->device));
     int rc;
-    // lights live on the device; fetch them once for the host-side distribution build
-    std::vector<pbrt_b200_light> lights(sc->dev.n_lights);
-    if (!lights.empty()) PB_CUDA_TRY(cudaMemcpy(lights.data(), sc->dev.lights, lights.size() * sizeof(pbrt_b200_light), cudaMemcpyDeviceToHost));
-    SceneRenderState* st;
-    if ((rc = prepare_scene_state(sc, rd, lights, &st))) return rc;
+    // lights live on the device; fetch them once per scene for the host-side distribution build
+    SceneRenderState* st = reinterpret_cast<SceneRenderState*>(sc->light_distrib);
+    if (!st) { st = new SceneRenderState(); sc->light_distrib = st; }
+    if (!st->lights_cached) {
+        st->lights_host.resize(sc->dev.n_lights);
+        if (!st->lights_host.empty())
+            PB_CUDA_TRY(cudaMemcpy(st->lights_host.data(), sc->dev.lights, st->lights_host.size() * sizeof(pbrt_b200_light), cudaMemcpyDeviceToHost));
+        st->lights_cached = true;
+    }
+    if ((rc = prepare_scene_state(sc, rd, st->lights_host, &st))) return rc;
 
     const int* sb = rd->sampler.sample_bounds;
     const int* crop = rd->film.cropped_pixel_bounds;
@@ -1209,10 +1225,15 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     const int grid_shade = sm_count * 8, grid_small = sm_count * 4;
 
     cudaStream_t stream = 0;
-    cudaEvent_t ev0, ev1;
-    PB_CUDA_TRY(cudaEventCreate(&ev0)); PB_CUDA_TRY(cudaEventCreate(&ev1));
-    std::vector<cudaEvent_t> tev;  // pairs around the trace kernels
-    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); tev.push_back(e); };
+    // events come from the scene's pool: [0] start, [1] end, [2..2+PB_PROG_RING) progress copies, then timing marks
+    size_t ev_used = 2 + PB_PROG_RING;
+    auto pool_event = [&](size_t i) -> cudaEvent_t {
+        while (st->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); st->events.push_back(e); }
+        return st->events[i];
+    };
+    cudaEvent_t ev0 = pool_event(0), ev1 = pool_event(1);
+    const size_t tev_base = ev_used;
+    auto mark = [&]() { cudaEventRecord(pool_event(ev_used++), stream); };  // pairs around the trace kernels
     const bool timing = stats != nullptr;
     uint64_t launches = 0;
     PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
@@ -1220,17 +1241,18 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (total_items > 0) {
         // Persistent wavefront: all `capacity` slots start free; each iteration traces every live path one segment,
         // shades, resolves shadow/MIS rays, then k_finish_regen retires finished paths and refills their slots.
-        struct Progress { unsigned long long cursor; uint32_t n_path; uint32_t pad; };
-        Progress* prog = nullptr;
-        PB_CUDA_TRY(cudaMallocHost((void**)&prog, sizeof(Progress)));
+        // The host never waits on the batch it has just submitted: after every batch of `poll` iterations the queue
+        // state is copied to a pinned ring entry, and the host looks at the copy of the batch BEFORE the one in flight,
+        // so the GPU always has work queued behind the running iteration (over-submitted iterations find empty queues).
+        SceneRenderState::Progress* prog = st->prog;
         k_init_slots<<<grid_small, 256, 0, stream>>>(R, capacity);
         k_finish_regen<<<grid_small, 256, 0, stream>>>(R, 1, total_items);
         k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
         launches += 3;
         int parity = 0;
-        unsigned long long iter = 0;
+        unsigned long long iter = 0, batch = 0;
         const unsigned long long iter_cap = (total_items / capacity + 2) * (unsigned long long)(R.max_depth + 2) + 4096;
-        int poll = 4;
+        const int poll = 4;
         bool done = false;
         while (!done) {
             for (int b = 0; b < poll; ++b) {
@@ -1252,22 +1274,26 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (timing) mark();
                 k_finish_regen<<<grid_small, 256, 0, stream>>>(R, parity, total_items);
                 k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
+                if (timing) mark();
                 launches += 13;
                 parity ^= 1;
                 iter++;
             }
-            // progress check: {item_cursor, n_path} are adjacent in Counters? no -- two small copies
-            cudaMemcpyAsync(&prog->cursor, &R.cnt->item_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
-            cudaMemcpyAsync(&prog->n_path, &R.cnt->n_path, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
-            cudaError_t e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) { cudaFreeHost(prog); PB_CUDA_TRY(e); }
-            if (prog->cursor >= total_items) {
-                if (prog->n_path == 0) done = true;
-                poll = 1;  // draining: at most max_depth more iterations, stop as soon as the queue is empty
+            // {item_cursor, n_path} of this batch -> ring entry, event marks the copy
+            SceneRenderState::Progress* pe = prog + (batch % PB_PROG_RING);
+            cudaMemcpyAsync(&pe->cursor, &R.cnt->item_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+            cudaMemcpyAsync(&pe->n_path, &R.cnt->n_path, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+            cudaEventRecord(pool_event(2 + batch % PB_PROG_RING), stream);
+            if (batch >= 1) {  // wait for the PREVIOUS batch only
+                unsigned long long pb = batch - 1;
+                cudaError_t e = cudaEventSynchronize(pool_event(2 + pb % PB_PROG_RING));
+                if (e != cudaSuccess) PB_CUDA_TRY(e);
+                const SceneRenderState::Progress* pp = prog + (pb % PB_PROG_RING);
+                if (pp->cursor >= total_items && pp->n_path == 0) done = true;
             }
-            if (iter > iter_cap) { cudaFreeHost(prog); return fail(PBRT_B200_ERR_CUDA, "render: path queue failed to drain"); }
+            batch++;
+            if (iter > iter_cap) return fail(PBRT_B200_ERR_CUDA, "render: path queue failed to drain");
         }
-        cudaFreeHost(prog);
     }
     PB_CUDA_TRY(cudaEventRecord(ev1, stream));
     PB_CUDA_TRY(cudaGetLastError());
@@ -1281,16 +1307,17 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
         stats->device_ms = ms;
-        for (size_t k = 0; k + 4 < tev.size(); k += 5) {
-            float a = 0.f, b = 0.f, m = 0.f;
-            cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
-            cudaEventElapsedTime(&b, tev[k + 2], tev[k + 3]);
-            cudaEventElapsedTime(&m, tev[k + 3], tev[k + 4]);
-            stats->trace_closest_ms += a + m; stats->trace_any_ms += b;
+        for (size_t k = tev_base; k + 5 < ev_used; k += 6) {
+            float a = 0.f, b = 0.f, m = 0.f, sh = 0.f, fin = 0.f;
+            cudaEventElapsedTime(&a, st->events[k], st->events[k + 1]);
+            cudaEventElapsedTime(&sh, st->events[k + 1], st->events[k + 2]);
+            cudaEventElapsedTime(&b, st->events[k + 2], st->events[k + 3]);
+            cudaEventElapsedTime(&m, st->events[k + 3], st->events[k + 4]);
+            cudaEventElapsedTime(&fin, st->events[k + 4], st->events[k + 5]);
+            stats->trace_closest_ms += a + m; stats->trace_any_ms += b; stats->shade_ms += sh; stats->finish_ms += fin;
         }
+        stats->iterations = c.iterations;
     }
-    for (cudaEvent_t e : tev) cudaEventDestroy(e);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (own_film) {
         std::vector<float> tmp(npix * 4);
         PB_CUDA_TRY(cudaMemcpy(tmp.data(), film_dev, npix * sizeof(float4), cudaMemcpyDeviceToHost));

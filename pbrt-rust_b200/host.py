@@ -96,7 +96,8 @@ class RenderDesc(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("camera_rays", C.c_uint64), ("intersection_tests", C.c_uint64), ("shadow_tests", C.c_uint64), ("zero_radiance_paths", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("trace_closest_ms", C.c_double), ("trace_any_ms", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("trace_closest_ms", C.c_double), ("trace_any_ms", C.c_double),
+                ("shade_ms", C.c_double), ("finish_ms", C.c_double), ("iterations", C.c_uint64)]
 
 
 RENDER_KEEP_ON_DEVICE = 1
