@@ -269,7 +269,10 @@ typedef struct pbrt_b200_render_desc {
 } pbrt_b200_render_desc;
 
 enum {
-    PBRT_B200_RENDER_KEEP_ON_DEVICE = 1u << 0 /* rgbw_out is a device pointer      */
+    PBRT_B200_RENDER_KEEP_ON_DEVICE = 1u << 0, /* rgbw_out is a device pointer      */
+    PBRT_B200_RENDER_LAZY_SPATIAL = 1u << 1    /* "spatial" light distribution: build voxels on first touch even when
+                                                * the whole grid would fit (the mode used automatically for voxels x
+                                                * lights > 2^25; results are identical, lightdistrib.rs:231-340)    */
 };
 
 /* Counters mirroring the reference's stats (integrator.rs:36, scene.rs:14-15,
@@ -295,6 +298,13 @@ typedef struct pbrt_b200_render_stats {
  * may split a render into several calls (or GPUs) and sum.  `stats` may be NULL. */
 int pbrt_b200_render(pbrt_b200_scene *scene, const pbrt_b200_render_desc *desc,
                      float *rgbw_out, pbrt_b200_render_stats *stats);
+
+/* LightDistribution::lookup (src/core/lightdistrib.rs:33-36; Uniform :44-61, Power :63-83, Spatial :231-340) for a
+ * batch of world-space points: voxel_out[3*n] = SpatialLightDistribution's integer voxel of each point (-1,-1,-1 for
+ * the uniform/power strategies), func_out[n * n_lights] = the Distribution1D::func the integrator samples a light from
+ * at that point.  Host buffers.  `flags`: PBRT_B200_RENDER_LAZY_SPATIAL or 0.                                        */
+int pbrt_b200_light_distribution_lookup(pbrt_b200_scene *scene, uint32_t strategy, uint32_t flags,
+                                        const float *points, uint64_t n, int32_t *voxel_out, float *func_out);
 
 /* Film::write_image arithmetic (src/core/film.rs:217-264): RGB->XYZ->RGB,
  * divide by weight, clamp at 0, scale.  rgb_out[3*npixels].  Host buffers.      */

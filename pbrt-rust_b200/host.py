@@ -101,10 +101,11 @@ class RenderStats(C.Structure):
 
 
 RENDER_KEEP_ON_DEVICE = 1
+RENDER_LAZY_SPATIAL = 2
 
 EXPORTS = ["pbrt_b200_last_error", "pbrt_b200_abi_version", "pbrt_b200_device_count", "pbrt_b200_bvh_build", "pbrt_b200_scene_create",
            "pbrt_b200_scene_destroy", "pbrt_b200_scene_world_bound", "pbrt_b200_intersect", "pbrt_b200_intersect_p", "pbrt_b200_intersect_dev",
-           "pbrt_b200_intersect_p_dev", "pbrt_b200_render", "pbrt_b200_film_resolve"]
+           "pbrt_b200_intersect_p_dev", "pbrt_b200_render", "pbrt_b200_film_resolve", "pbrt_b200_light_distribution_lookup"]
 
 
 class B200Error(RuntimeError):
@@ -136,6 +137,7 @@ def load_library():
     lib.pbrt_b200_intersect_p_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.pbrt_b200_render.argtypes = [C.c_void_p, C.POINTER(RenderDesc), C.c_void_p, C.POINTER(RenderStats)]
     lib.pbrt_b200_film_resolve.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
+    lib.pbrt_b200_light_distribution_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -478,12 +480,30 @@ class SceneBuilder:
             w = self.ctm.vectors([frm - to])[0]
             w = w * (f32(1) / np.sqrt(f32(w[0] * w[0] + w[1] * w[1] + w[2] * w[2])))
             r["type"], r["L"], r["dir"] = LIGHT_DISTANT, rgb("L", 1.0) * sc, w
+        elif name == "spot":  # spot.rs:119-146 (+ SpotLight::new :31-45)
+            frm, to = np.asarray(kw.get("from", (0, 0, 0)), f32), np.asarray(kw.get("to", (0, 0, 1)), f32)
+            d = to - frm
+            d = d * (f32(1) / np.sqrt(f32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])))
+            if abs(d[0]) > abs(d[1]):  # vec3_coordinate_system, vector.rs:551-560 (division = multiply by the reciprocal)
+                du = np.array([-d[2], 0, d[0]], f32) * (f32(1) / np.sqrt(f32(d[0] * d[0] + d[2] * d[2])))
+            else:
+                du = np.array([0, d[2], -d[1]], f32) * (f32(1) / np.sqrt(f32(d[1] * d[1] + d[2] * d[2])))
+            d64, u64 = d.astype(np.float64), du.astype(np.float64)  # Vector3::cross is evaluated in f64 (vector.rs:339-353)
+            dv = np.array([d64[1] * u64[2] - d64[2] * u64[1], d64[2] * u64[0] - d64[0] * u64[2], d64[0] * u64[1] - d64[1] * u64[0]]).astype(f32)
+            m = np.array([[du[0], du[1], du[2], 0], [dv[0], dv[1], dv[2], 0], [d[0], d[1], d[2], 0], [0, 0, 0, 1]], f32)
+            dirtoz = Transform(m)
+            l2w = self.ctm * Transform.translate((frm[0], frm[1], frm[2])) * dirtoz.inverse()
+            cone, delta = f32(kw.get("coneangle", 30.0)), f32(kw.get("conedeltaangle", 5.0))
+            rad = lambda deg: f32(f32(np.pi) / f32(180.0)) * f32(deg)  # pbrt.rs:167-169
+            r["type"], r["L"], r["pos"] = LIGHT_SPOT, rgb("I", 1.0) * sc, l2w.points([[0, 0, 0]])[0]
+            r["cos_total_width"], r["cos_falloff_start"] = np.cos(rad(cone)), np.cos(rad(f32(cone - delta)))
+            r["world_to_light"] = l2w.m_inv.reshape(-1)
         elif name == "infinite":  # infinite.rs, constant map only
             if kw.get("mapname"):
                 raise B200Error("image-mapped infinite lights are outside the hot path")
             r["type"], r["L"] = LIGHT_INFINITE, rgb("L", 1.0) * sc
         else:
-            raise B200Error(f'LightSource "{name}" is outside the hot path (point, distant, infinite, diffuse area)')
+            raise B200Error(f'LightSource "{name}" is outside the hot path (point, spot, distant, infinite, diffuse area)')
         self._lights.append(r)
 
     # --- shapes --------------------------------------------------------------
@@ -785,16 +805,26 @@ class Scene:
     def intersect_p_dev(self, rays_ptr, n, occ_ptr, stream=None):
         _check(self.lib.pbrt_b200_intersect_p_dev(self.handle, rays_ptr, n, occ_ptr, stream), "pbrt_b200_intersect_p_dev")
 
-    def render(self, integrator, rgbw=None, tile_range=None, sample_range=None, paths_in_flight=0, device_ptr=None, tile_interleave=None):
+    def light_distribution_lookup(self, points, strategy="spatial", lazy=False):
+        """LightDistribution::lookup at `points` -> (voxel [n,3] int32, func [n,n_lights] f32)."""
+        pts = np.ascontiguousarray(points, f32).reshape(-1, 3)
+        nl = len(self.flat.lights) if self.flat.lights is not None else 0
+        voxel = np.zeros((len(pts), 3), np.int32)
+        func = np.zeros((len(pts), max(nl, 1)), f32)
+        _check(self.lib.pbrt_b200_light_distribution_lookup(self.handle, PathIntegrator.STRATEGY[strategy], RENDER_LAZY_SPATIAL if lazy else 0, _ptr(pts),
+                                                           C.c_uint64(len(pts)), _ptr(voxel), _ptr(func)), "pbrt_b200_light_distribution_lookup")
+        return voxel, func[:, :nl]
+
+    def render(self, integrator, rgbw=None, tile_range=None, sample_range=None, paths_in_flight=0, device_ptr=None, tile_interleave=None, flags=0):
         film = integrator.film
         stats = RenderStats()
         if device_ptr is not None:
-            d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE, tile_interleave)
+            d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE | flags, tile_interleave)
             _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), device_ptr, C.byref(stats)), "pbrt_b200_render")
             return None, stats
         if rgbw is None:
             rgbw = np.zeros((film.height * film.width, 4), f32)
-        d = integrator.desc(tile_range, sample_range, paths_in_flight, 0, tile_interleave)
+        d = integrator.desc(tile_range, sample_range, paths_in_flight, flags, tile_interleave)
         _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), _ptr(rgbw), C.byref(stats)), "pbrt_b200_render")
         return rgbw, stats
 

@@ -374,6 +374,57 @@ def small_mixed_scene(n=24, seed=5):
     return SceneSetup("mixed-small", flat, make, "all hot-path materials/lights/shapes at test size")
 
 
+def many_lights_scene(grid=6, n_quads=6, seed=99):
+    """Room lit by many small lights (a test-sized stand-in for config C4's light population): grid x grid point lights
+    under the ceiling, a few spot lights and small quad area lights (2 triangle lights each).  With this many lights of
+    very different reach the three `lightsamplestrategy` choices give visibly different sampling distributions."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.0, -9.5, 3.0), (0, 0, 1.5), (0, 0, 1))
+    rng = PCG32(seed)
+    u = rng.floats(8 * (grid * grid + n_quads + 8))
+    k = 0
+    b.material("matte", Kd=(0.55, 0.55, 0.5))
+    for pts in (((-10, -10, 0), (10, -10, 0), (10, 10, 0), (-10, 10, 0)), ((-10, 10, 0), (10, 10, 0), (10, 10, 6), (-10, 10, 6)),
+                ((-10, -10, 0), (-10, 10, 0), (-10, 10, 6), (-10, -10, 6)), ((10, -10, 0), (10, -10, 6), (10, 10, 6), (10, 10, 0))):
+        Pq, Iq = quad(*pts)
+        b.shape("trianglemesh", P=Pq, indices=Iq)
+    P, I, N = displaced_sphere(24, 12, 0.9, 0.08, 3)
+    for j, (m, kw) in enumerate((("plastic", dict(Kd=(0.6, 0.2, 0.2), Ks=0.3, roughness=0.1)), ("metal", dict(roughness=0.08)), ("matte", dict(Kd=(0.2, 0.5, 0.7))))):
+        b.attribute_begin()
+        b.translate(-4.0 + 4.0 * j, 1.0 - 1.5 * (j % 2), 0.95)
+        b.material(m, **kw)
+        b.shape("trianglemesh", P=P, indices=I, N=N)
+        b.attribute_end()
+    for gy in range(grid):
+        for gx in range(grid):
+            b.attribute_begin()
+            b.translate(-8.5 + 17.0 * (gx + float(u[k])) / grid, -8.5 + 17.0 * (gy + float(u[k + 1])) / grid, 4.0 + 1.5 * float(u[k + 2]))
+            c = 0.3 + 2.5 * float(u[k + 3]) ** 3
+            b.light_source("point", I=(c * (0.6 + 0.4 * float(u[k + 4])), c * (0.6 + 0.4 * float(u[k + 5])), c * (0.6 + 0.4 * float(u[k + 6]))))
+            b.attribute_end()
+            k += 8
+    for j in range(4):
+        x, y = -6.0 + 4.0 * j, -6.0 + 3.0 * (j % 2)
+        b.light_source("spot", **{"from": (x, y, 5.5), "to": (x + 1.0, y + 2.0, 0.0), "I": (30, 28, 22), "coneangle": 25.0, "conedeltaangle": 8.0})
+    for j in range(n_quads):
+        cx, cy, cz = -8.0 + 16.0 * float(u[k]), -8.0 + 16.0 * float(u[k + 1]), 5.0 + 0.8 * float(u[k + 2])
+        hs = 0.15 + 0.2 * float(u[k + 3])
+        b.attribute_begin()
+        b.area_light_source("diffuse", L=(20 + 40 * float(u[k + 4]), 20 + 30 * float(u[k + 5]), 15 + 30 * float(u[k + 6])))
+        Pl, Il = quad((cx - hs, cy - hs, cz), (cx - hs, cy + hs, cz), (cx + hs, cy + hs, cz), (cx + hs, cy - hs, cz))
+        b.shape("trianglemesh", P=Pl, indices=Il)
+        b.attribute_end()
+        k += 8
+    flat = b.world_end()
+
+    def make(spp_=16, res=(128, 72), maxdepth_=5, sampler_="sobol", strategy="spatial", filt="box"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=55.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    return SceneSetup("many-lights", flat, make, f"{grid * grid} point + 4 spot + {2 * n_quads} triangle area lights in a room")
+
+
 # ---------------------------------------------------------------------------
 # ray batches (SURVEY.md s8(d))
 # ---------------------------------------------------------------------------
