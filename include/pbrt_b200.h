@@ -299,6 +299,11 @@ typedef struct pbrt_b200_render_stats {
 int pbrt_b200_render(pbrt_b200_scene *scene, const pbrt_b200_render_desc *desc,
                      float *rgbw_out, pbrt_b200_render_stats *stats);
 
+/* Device and pinned-host blocks released by pbrt_b200_scene_destroy are kept in a per-process pool and handed to the
+ * next scene (the reference drops its Scene after every WorldEnd, src/core/api.rs:1750-1755; re-allocating ~6 GB of
+ * path state per render would dominate short renders).  This returns every cached block to the driver.             */
+void pbrt_b200_release_cached_memory(void);
+
 /* LightDistribution::lookup (src/core/lightdistrib.rs:33-36; Uniform :44-61, Power :63-83, Spatial :231-340) for a
  * batch of world-space points: voxel_out[3*n] = SpatialLightDistribution's integer voxel of each point (-1,-1,-1 for
  * the uniform/power strategies), func_out[n * n_lights] = the Distribution1D::func the integrator samples a light from

@@ -5,7 +5,13 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <type_traits>
+
 #include "error.h"
+#include "pool.h"
 #include "scene.cuh"
 #include "trace.cuh"
 #include "util.cuh"
@@ -77,20 +83,104 @@ __global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_p_batch(DevScene s
 // ---------------------------------------------------------------------------
 // scene
 // ---------------------------------------------------------------------------
-namespace {
-
-template <typename T>
-int upload(pbrt_b200_scene* sc, const T* host, uint64_t count, const T** dev_out) {
-    *dev_out = nullptr;
-    if (count == 0 || host == nullptr) return PBRT_B200_OK;
-    void* d = nullptr;
-    PB_CUDA_TRY(cudaMalloc(&d, count * sizeof(T)));
-    sc->allocs[sc->n_allocs++] = d;
-    sc->device_bytes += count * sizeof(T);
-    PB_CUDA_TRY(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
-    *dev_out = reinterpret_cast<const T*>(d);
-    return PBRT_B200_OK;
+// Device-side construction of the traversal layout from the reference's own tables (scene.cuh).
+//   k_leaf_records : GeometricPrimitive rows + TriangleMesh SoA -> 48-byte leaf records in BVH slot order
+//   k_interior_*   : exclusive scan of "node is interior" -> index of each interior node in the fat-node array
+//   k_fat_nodes    : LinearBVHNode[] -> fat nodes (both child boxes in the parent), LAST flags on leaf records
+__global__ void __launch_bounds__(256) k_leaf_records(const pbrt_b200_prim* __restrict__ prims, uint32_t n, const uint32_t* __restrict__ tri_indices,
+                                                      const float* __restrict__ vertex_p, float4* __restrict__ tris) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const pbrt_b200_prim p = prims[s];
+        uint32_t fl = p.flags & PB_TRI_FLAGS_MASK;
+        float4 v[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+        if (p.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
+            const uint32_t* ix = tri_indices + 3ull * p.shape_index;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float* vp = vertex_p + 3ull * ix[k];
+                v[k].x = vp[0]; v[k].y = vp[1]; v[k].z = vp[2];
+            }
+        } else {
+            fl |= PB_TRI_SPHERE;
+        }
+        v[0].w = __uint_as_float(p.creation_index);
+        v[1].w = __uint_as_float(fl);
+        v[2].w = __uint_as_float(p.shape_index);
+        tris[3ull * s] = v[0]; tris[3ull * s + 1] = v[1]; tris[3ull * s + 2] = v[2];
+    }
 }
+
+#define PB_SCAN_BLOCK 1024
+PB_D uint32_t node_is_interior(const pbrt_b200_bvh_node* nodes, uint32_t i, uint32_t n) { return (i < n && nodes[i].n_prims == 0) ? 1u : 0u; }
+// block-wide exclusive scan of one flag per thread; returns the exclusive prefix, *total = block sum
+PB_D uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += t; }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= (unsigned)o) winc += t; }
+        warp_sums[lane] = winc - w;  // exclusive
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    uint32_t r = inc - v + warp_sums[warp];
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(PB_SCAN_BLOCK) k_interior_count(const pbrt_b200_bvh_node* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t total;
+    block_exclusive_scan(node_is_interior(nodes, blockIdx.x * PB_SCAN_BLOCK + threadIdx.x, n), &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(PB_SCAN_BLOCK) k_interior_scan_blocks(uint32_t* __restrict__ block_sums, uint32_t nb) {
+    __shared__ uint32_t total, carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += PB_SCAN_BLOCK) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nb ? block_sums[i] : 0u;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < nb) block_sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(PB_SCAN_BLOCK) k_interior_index(const pbrt_b200_bvh_node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ block_sums,
+                                                                 uint32_t* __restrict__ fat_index) {
+    __shared__ uint32_t total;
+    uint32_t i = blockIdx.x * PB_SCAN_BLOCK + threadIdx.x;
+    uint32_t ex = block_exclusive_scan(node_is_interior(nodes, i, n), &total);
+    if (i < n) fat_index[i] = ex + block_sums[blockIdx.x];
+}
+__global__ void __launch_bounds__(256) k_fat_nodes(const pbrt_b200_bvh_node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ fat_index,
+                                                   float4* __restrict__ fat, float4* __restrict__ tris) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const pbrt_b200_bvh_node nd = nodes[i];
+        if (nd.n_prims != 0) {  // leaf: the last primitive of the run carries PB_TRI_LAST
+            float4* rec = tris + 3ull * (nd.offset + nd.n_prims - 1) + 1;
+            rec->w = __uint_as_float(__float_as_uint(rec->w) | PB_TRI_LAST);
+            continue;
+        }
+        const uint32_t c0 = i + 1, c1 = nd.offset;
+        const pbrt_b200_bvh_node a = nodes[c0], b = nodes[c1];
+        const uint32_t r0 = a.n_prims ? (PB_LEAF_BIT | a.offset) : fat_index[c0];
+        const uint32_t r1 = b.n_prims ? (PB_LEAF_BIT | b.offset) : fat_index[c1];
+        float4* q = fat + 4ull * fat_index[i];
+        q[0] = make_float4(a.bounds[0], a.bounds[1], a.bounds[2], a.bounds[3]);
+        q[1] = make_float4(a.bounds[4], a.bounds[5], b.bounds[0], b.bounds[1]);
+        q[2] = make_float4(b.bounds[2], b.bounds[3], b.bounds[4], b.bounds[5]);
+        q[3] = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float((uint32_t)nd.axis), 0.0f);
+    }
+}
+
+namespace {
 
 int validate(const pbrt_b200_scene_desc* d) {
     if (d->abi_version != PBRT_B200_ABI_VERSION) return fail(PBRT_B200_ERR_INVALID, "scene_create: abi_version mismatch");
@@ -98,6 +188,7 @@ int validate(const pbrt_b200_scene_desc* d) {
     if (d->n_nodes && !d->nodes) return fail(PBRT_B200_ERR_INVALID, "scene_create: nodes is null");
     if (d->n_prims && !d->n_nodes) return fail(PBRT_B200_ERR_INVALID, "scene_create: primitives without a BVH (Accelerator \"bvh\" is required)");
     if (d->n_prims > 0x7ffffff0ull) return fail(PBRT_B200_ERR_INVALID, "scene_create: too many primitives");
+    if (d->n_nodes > 0x7ffffff0ull) return fail(PBRT_B200_ERR_INVALID, "scene_create: too many BVH nodes");
     for (uint64_t i = 0; i < d->n_prims; ++i) {
         const pbrt_b200_prim& p = d->prims[i];
         if (p.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
@@ -120,65 +211,38 @@ int validate(const pbrt_b200_scene_desc* d) {
         if (l.type > PBRT_B200_LIGHT_INFINITE) return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: light type outside the hot path");
         if (l.type == PBRT_B200_LIGHT_DIFFUSE && l.shape_kind != PBRT_B200_SHAPE_TRIANGLE)
             return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: only triangle area lights are on the hot path");
+        if (l.type == PBRT_B200_LIGHT_DIFFUSE && l.shape_index >= d->n_triangles) return fail(PBRT_B200_ERR_INVALID, "scene_create: area light shape out of range");
     }
     return PBRT_B200_OK;
 }
 
-// LinearBVHNode[] -> fat nodes (see scene.cuh).  Also checks what the reference would
-// panic on (stack deeper than 64, bvh.rs:722).
-int build_fat_nodes(const pbrt_b200_scene_desc* d, std::vector<float4>& fat, std::vector<uint8_t>& last_flag, uint32_t* root_ref) {
+// One pass over LinearBVHNode[] in array order (parents precede their children: first child at i+1, second at
+// `offset` > i, bvh.rs:662-693): structural checks, interior count, and the depth of every node -- the reference
+// would panic on a traversal stack deeper than 64 entries (bvh.rs:722).
+int check_nodes(const pbrt_b200_scene_desc* d, uint32_t* n_interior, uint32_t* root_ref) {
     const uint64_t nn = d->n_nodes;
-    *root_ref = PB_REF_NONE;
+    *n_interior = 0; *root_ref = PB_REF_NONE;
     if (nn == 0) return PBRT_B200_OK;
-    std::vector<uint32_t> fat_index(nn, 0xffffffffu);
-    uint32_t nfat = 0;
-    for (uint64_t i = 0; i < nn; ++i)
-        if (d->nodes[i].n_prims == 0) fat_index[i] = nfat++;
-    fat.assign(4ull * nfat, make_float4(0, 0, 0, 0));
-    auto ref_of = [&](uint64_t c, uint32_t* out) -> bool {
-        if (c >= nn) return false;
-        const pbrt_b200_bvh_node& n = d->nodes[c];
-        if (n.n_prims > 0) {
-            if ((uint64_t)n.offset + n.n_prims > d->n_prims) return false;
-            last_flag[n.offset + n.n_prims - 1] = 1;
-            *out = PB_LEAF_BIT | n.offset;
-        } else {
-            *out = fat_index[c];
-        }
-        return true;
-    };
-    if (!ref_of(0, root_ref)) return fail(PBRT_B200_ERR_INVALID, "scene_create: root node refers past the primitive table");
+    std::vector<uint8_t> depth(nn, 0);
+    uint32_t ni = 0;
+    int maxd = 0;
     for (uint64_t i = 0; i < nn; ++i) {
         const pbrt_b200_bvh_node& n = d->nodes[i];
-        if (n.n_prims != 0) continue;
-        uint64_t c0 = i + 1, c1 = n.offset;
-        uint32_t r0, r1;
-        if (n.axis > 2 || c1 <= i || !ref_of(c0, &r0) || !ref_of(c1, &r1))
-            return fail(PBRT_B200_ERR_INVALID, "scene_create: malformed LinearBVHNode array");
-        const float* a = d->nodes[c0].bounds;
-        const float* b = d->nodes[c1].bounds;
-        float4* q = &fat[4ull * fat_index[i]];
-        q[0] = make_float4(a[0], a[1], a[2], a[3]);
-        q[1] = make_float4(a[4], a[5], b[0], b[1]);
-        q[2] = make_float4(b[2], b[3], b[4], b[5]);
-        uint32_t ax = n.axis, z = 0;
-        float4 m;
-        std::memcpy(&m.x, &r0, 4); std::memcpy(&m.y, &r1, 4); std::memcpy(&m.z, &ax, 4); std::memcpy(&m.w, &z, 4);
-        q[3] = m;
-    }
-    // depth check (explicit stack; the pending-entry count equals the tree depth)
-    {
-        std::vector<std::pair<uint64_t, int>> st;
-        st.push_back({0, 0});
-        int maxd = 0;
-        while (!st.empty()) {
-            auto e = st.back(); st.pop_back();
-            maxd = e.second > maxd ? e.second : maxd;
-            const pbrt_b200_bvh_node& n = d->nodes[e.first];
-            if (n.n_prims == 0) { st.push_back({e.first + 1, e.second + 1}); st.push_back({n.offset, e.second + 1}); }
+        if (n.n_prims != 0) {
+            if ((uint64_t)n.offset + n.n_prims > d->n_prims)
+                return fail(PBRT_B200_ERR_INVALID, i == 0 ? "scene_create: root node refers past the primitive table" : "scene_create: malformed LinearBVHNode array");
+            continue;
         }
-        if (maxd >= PB_STACK_DEPTH) return fail(PBRT_B200_ERR_INVALID, "scene_create: BVH deeper than the reference's 64-entry traversal stack");
+        const uint64_t c0 = i + 1, c1 = n.offset;
+        if (n.axis > 2 || c1 <= c0 || c1 >= nn) return fail(PBRT_B200_ERR_INVALID, "scene_create: malformed LinearBVHNode array");
+        const int dd = depth[i] + 1;
+        if (dd >= PB_STACK_DEPTH) return fail(PBRT_B200_ERR_INVALID, "scene_create: BVH deeper than the reference's 64-entry traversal stack");
+        depth[c0] = depth[c1] = (uint8_t)dd;
+        maxd = dd > maxd ? dd : maxd;
+        ++ni;
     }
+    *n_interior = ni;
+    *root_ref = d->nodes[0].n_prims ? (PB_LEAF_BIT | d->nodes[0].offset) : 0u;
     return PBRT_B200_OK;
 }
 
@@ -193,61 +257,64 @@ extern "C" int pbrt_b200_device_count(void) {
 extern "C" void pbrt_b200_scene_destroy(pbrt_b200_scene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
+    cudaDeviceSynchronize();  // blocks go back to the pool: nothing may still be reading them
     render_release_scene_state(sc);
-    for (int i = 0; i < sc->n_allocs; ++i) cudaFree(sc->allocs[i]);
-    if (sc->scratch) cudaFree(sc->scratch);
-    if (sc->fetch_counter) cudaFree(sc->fetch_counter);
+    pool_free(sc->arena, sc->arena_bytes);
+    pool_free(sc->scratch, sc->scratch_bytes);
+    if (sc->fetch_counter) pool_free(sc->fetch_counter, 256);
     delete sc;
 }
 
 extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device, pbrt_b200_scene** out) {
     if (!d || !out) return fail(PBRT_B200_ERR_INVALID, "scene_create: null argument");
     *out = nullptr;
+    const bool prof = getenv("PBRT_B200_PROFILE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!prof) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pbrt_b200] scene_create %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     int rc = validate(d);
     if (rc) return rc;
+    lap("validate");
+    uint32_t n_interior = 0, root_ref = PB_REF_NONE;
+    if ((rc = check_nodes(d, &n_interior, &root_ref))) return rc;
+    lap("check_nodes");
     int ndev = pbrt_b200_device_count();
     if (ndev <= 0) return fail(PBRT_B200_ERR_NO_DEVICE, "scene_create: no CUDA device visible; this library has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(PBRT_B200_ERR_INVALID, "scene_create: device ordinal out of range");
     PB_CUDA_TRY(cudaSetDevice(device));
 
-    std::vector<float4> fat;
-    std::vector<uint8_t> last(d->n_prims, 0);
-    uint32_t root_ref;
-    rc = build_fat_nodes(d, fat, last, &root_ref);
-    if (rc) return rc;
-
-    // leaf records: vertices gathered into BVH slot order
-    std::vector<float4> tris(3ull * d->n_prims);
-    for (uint64_t s = 0; s < d->n_prims; ++s) {
-        const pbrt_b200_prim& p = d->prims[s];
-        uint32_t fl = (p.flags & PB_TRI_FLAGS_MASK) | (last[s] ? PB_TRI_LAST : 0u);
-        float4 v[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
-        if (p.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
-            const uint32_t* ix = d->tri_indices + 3ull * p.shape_index;
-            for (int k = 0; k < 3; ++k) {
-                const float* vp = d->vertex_p + 3ull * ix[k];
-                v[k].x = vp[0]; v[k].y = vp[1]; v[k].z = vp[2];
-            }
-        } else {
-            fl |= PB_TRI_SPHERE;
-        }
-        std::memcpy(&v[0].w, &p.creation_index, 4);
-        std::memcpy(&v[1].w, &fl, 4);
-        std::memcpy(&v[2].w, &p.shape_index, 4);
-        tris[3 * s] = v[0]; tris[3 * s + 1] = v[1]; tris[3 * s + 2] = v[2];
-    }
+    const uint64_t nn = d->n_nodes, np = d->n_prims, nv = d->n_vertices, nt = d->n_triangles;
+    const uint32_t nb = (uint32_t)((nn + PB_SCAN_BLOCK - 1) / PB_SCAN_BLOCK);
+    // resident tables, then build-only temporaries (reference node array, scan scratch) at the tail of the same block
+    size_t need = 0;
+    auto add = [&](size_t bytes) { need += Arena::padded(bytes); };
+    add(64ull * n_interior); add(48ull * np); add(sizeof(pbrt_b200_prim) * np);
+    add(12ull * nv); add(d->vertex_n ? 12ull * nv : 0); add(d->vertex_s ? 12ull * nv : 0); add(d->vertex_uv ? 8ull * nv : 0);
+    add(12ull * nt); add(sizeof(pbrt_b200_sphere) * d->n_spheres); add(sizeof(pbrt_b200_material) * d->n_materials); add(sizeof(pbrt_b200_light) * d->n_lights);
+    const size_t resident = need;
+    add(sizeof(pbrt_b200_bvh_node) * nn); add(4ull * nn); add(4ull * nb);
+    need += 4096;
 
     pbrt_b200_scene* sc = new pbrt_b200_scene();
     sc->device = device;
-    sc->n_prims = d->n_prims; sc->n_nodes = d->n_nodes;
+    sc->n_prims = np; sc->n_nodes = nn;
     std::memset(&sc->dev, 0, sizeof sc->dev);
+    sc->arena = pool_alloc(need, &sc->arena_bytes);
+    if (!sc->arena) { delete sc; return fail(PBRT_B200_ERR_CUDA, "scene_create: out of device memory"); }
+    lap("arena");
+    sc->device_bytes = resident;
+    Arena A; A.base = reinterpret_cast<char*>(sc->arena); A.size = sc->arena_bytes;
     DevScene& ds = sc->dev;
     ds.root_ref = root_ref;
-    ds.n_fat = (uint32_t)(fat.size() / 4);
-    ds.n_slots = (uint32_t)d->n_prims;
+    ds.n_fat = n_interior;
+    ds.n_slots = (uint32_t)np;
     ds.n_lights = (uint32_t)d->n_lights;
     ds.n_materials = (uint32_t)d->n_materials;
-    if (d->n_nodes) {
+    if (nn) {
         std::memcpy(ds.root_box, d->nodes[0].bounds, sizeof ds.root_box);
         // Bounds3f::bounding_sphere (bounds.rs:515-523) on Scene.wb, used by DistantLight::preprocess
         float c[3];
@@ -258,19 +325,47 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
         ds.world_center[0] = c[0]; ds.world_center[1] = c[1]; ds.world_center[2] = c[2];
         ds.world_radius = inside ? sqrtf(dx * dx + dy * dy + dz * dz) : 0.0f;
     }
-#define PB_UP(expr) do { rc = (expr); if (rc) { pbrt_b200_scene_destroy(sc); return rc; } } while (0)
-    PB_UP(upload(sc, fat.data(), fat.size(), &ds.nodes));
-    PB_UP(upload(sc, tris.data(), tris.size(), &ds.tris));
-    PB_UP(upload(sc, d->prims, d->n_prims, &ds.prims));
-    PB_UP(upload(sc, d->vertex_p, 3 * d->n_vertices, &ds.vertex_p));
-    PB_UP(upload(sc, d->vertex_n, d->vertex_n ? 3 * d->n_vertices : 0, &ds.vertex_n));
-    PB_UP(upload(sc, d->vertex_s, d->vertex_s ? 3 * d->n_vertices : 0, &ds.vertex_s));
-    PB_UP(upload(sc, d->vertex_uv, d->vertex_uv ? 2 * d->n_vertices : 0, &ds.vertex_uv));
-    PB_UP(upload(sc, d->tri_indices, 3 * d->n_triangles, &ds.tri_indices));
-    PB_UP(upload(sc, d->spheres, d->n_spheres, &ds.spheres));
-    PB_UP(upload(sc, d->materials, d->n_materials, &ds.materials));
-    PB_UP(upload(sc, d->lights, d->n_lights, &ds.lights));
-#undef PB_UP
+    cudaStream_t stream = 0;
+    cudaError_t err = cudaSuccess;
+    // host table -> arena (pageable source: the runtime stages it, the call returns once the source has been read)
+    auto up = [&](const void* host, size_t bytes, auto** dev_out) {
+        using T = std::remove_pointer_t<std::remove_reference_t<decltype(*dev_out)>>;
+        *dev_out = nullptr;
+        if (!host || bytes == 0) return;
+        char* p = A.take<char>(bytes);
+        *dev_out = reinterpret_cast<T*>(p);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, stream);
+    };
+    float4* fat = A.take<float4>(4ull * n_interior);
+    float4* tris = A.take<float4>(3ull * np);
+    ds.nodes = fat; ds.tris = tris;
+    up(d->prims, sizeof(pbrt_b200_prim) * np, &ds.prims);
+    up(d->vertex_p, 12ull * nv, &ds.vertex_p);
+    up(d->tri_indices, 12ull * nt, &ds.tri_indices);
+    if (np && err == cudaSuccess) k_leaf_records<<<(unsigned)std::min<uint64_t>((np + 255) / 256, 148 * 16), 256, 0, stream>>>(ds.prims, (uint32_t)np, ds.tri_indices, ds.vertex_p, tris);
+    up(d->vertex_n, d->vertex_n ? 12ull * nv : 0, &ds.vertex_n);
+    up(d->vertex_s, d->vertex_s ? 12ull * nv : 0, &ds.vertex_s);
+    up(d->vertex_uv, d->vertex_uv ? 8ull * nv : 0, &ds.vertex_uv);
+    up(d->spheres, sizeof(pbrt_b200_sphere) * d->n_spheres, &ds.spheres);
+    up(d->materials, sizeof(pbrt_b200_material) * d->n_materials, &ds.materials);
+    up(d->lights, sizeof(pbrt_b200_light) * d->n_lights, &ds.lights);
+    if (nn) {
+        const pbrt_b200_bvh_node* nodes_dev = nullptr;
+        up(d->nodes, sizeof(pbrt_b200_bvh_node) * nn, &nodes_dev);
+        uint32_t* fat_index = A.take<uint32_t>(nn);
+        uint32_t* block_sums = A.take<uint32_t>(nb);
+        if (err == cudaSuccess) {
+            k_interior_count<<<nb, PB_SCAN_BLOCK, 0, stream>>>(nodes_dev, (uint32_t)nn, block_sums);
+            k_interior_scan_blocks<<<1, PB_SCAN_BLOCK, 0, stream>>>(block_sums, nb);
+            k_interior_index<<<nb, PB_SCAN_BLOCK, 0, stream>>>(nodes_dev, (uint32_t)nn, block_sums, fat_index);
+            k_fat_nodes<<<(unsigned)std::min<uint64_t>((nn + 255) / 256, 148 * 16), 256, 0, stream>>>(nodes_dev, (uint32_t)nn, fat_index, fat, tris);
+        }
+    }
+    lap("enqueue h2d+build");
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+    if (err != cudaSuccess) { pbrt_b200_scene_destroy(sc); PB_CUDA_TRY(err); }
+    lap("sync");
     *out = sc;
     return PBRT_B200_OK;
 }
@@ -291,7 +386,9 @@ extern "C" void pbrt_b200_debug_tune(int key, int value) { if (key >= 0 && key <
 namespace {
 int ensure_fetch_counter(pbrt_b200_scene* sc) {
     if (sc->fetch_counter) return PBRT_B200_OK;
-    PB_CUDA_TRY(cudaMalloc((void**)&sc->fetch_counter, 64));
+    size_t got = 0;
+    sc->fetch_counter = reinterpret_cast<uint32_t*>(pool_alloc(256, &got));
+    if (!sc->fetch_counter) return fail(PBRT_B200_ERR_CUDA, "out of device memory");
     int sm = 148, per_sm = 8;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, sc->device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intersect_batch, PB_TRACE_BLOCK, 0);
@@ -339,10 +436,9 @@ extern "C" int pbrt_b200_intersect_p_dev(pbrt_b200_scene* sc, const pbrt_b200_ra
 namespace {
 int ensure_scratch(pbrt_b200_scene* sc, uint64_t bytes) {
     if (sc->scratch_bytes >= bytes) return PBRT_B200_OK;
-    if (sc->scratch) cudaFree(sc->scratch);
-    sc->scratch = nullptr; sc->scratch_bytes = 0;
-    PB_CUDA_TRY(cudaMalloc(&sc->scratch, bytes));
-    sc->scratch_bytes = bytes;
+    if (sc->scratch) { cudaDeviceSynchronize(); pool_free(sc->scratch, sc->scratch_bytes); }
+    sc->scratch = pool_alloc(bytes, &sc->scratch_bytes);
+    if (!sc->scratch) { sc->scratch_bytes = 0; return fail(PBRT_B200_ERR_CUDA, "out of device memory"); }
     return PBRT_B200_OK;
 }
 }  // namespace

@@ -12,11 +12,16 @@
 // All queues live in HBM as index arrays; every kernel is a persistent grid-stride loop over
 // a queue whose length is read from device memory, so a whole wave runs without host syncs.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <utility>
 #include <vector>
 
+#include "pool.h"
 #include "scene.cuh"
 #include "shading.cuh"
 #include "trace.cuh"
@@ -1065,47 +1070,63 @@ __global__ void k_iter_end(Counters* c, unsigned long long total_items) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-struct RenderBuffers {
-    std::vector<void*> allocs;
+struct RenderBuffers {  // all path-state arrays and queues sub-allocated from ONE pooled block (pool.h)
+    void* block = nullptr;
+    size_t block_bytes = 0;
     uint32_t capacity = 0;
     RenderDev dev;
-    ~RenderBuffers() { for (void* p : allocs) cudaFree(p); }
+    ~RenderBuffers() { pool_free(block, block_bytes); }
 };
 
-struct SceneRenderState {  // cached per scene: light tables
-    float* ld_func = nullptr; float* ld_cdf = nullptr; float ld_func_int = 0;
-    InfDistrib* inf = nullptr; uint32_t* inf_list = nullptr; uint32_t n_inf = 0;
-    int strategy = -1;
-    // Halton tables (shared by all renders of the scene's device)
+// Resources that depend only on the DEVICE, shared by every scene rendered on it and kept for the life of the process:
+// sampler tables (the reference's compile-time constants), pinned progress ring, CUDA events.  Render calls on one device
+// are serialised by `mu` (the reference calls Integrator::render from one thread, api.rs:1740-1747).
+struct DeviceShared {
+    std::mutex mu;
+    // Halton tables (lowdiscrepancy.rs:359-378: permutations from the default-seeded RNG => a constant)
     uint16_t* perms = nullptr; uint32_t* primes = nullptr; uint32_t* prime_sums = nullptr; uint32_t n_halton_dims = 0;
-    // Sobol tables copied to the device
+    // Sobol tables copied to the device, keyed by a hash of the caller's arrays
     uint32_t* sobol32 = nullptr; uint32_t* sobol_t = nullptr; unsigned long long* vdc = nullptr; unsigned long long* vdc_inv = nullptr;
-    const void* sobol_src = nullptr;
+    unsigned long long sobol_hash = 0;
     float* filter_table = nullptr;
-    RenderBuffers* buffers = nullptr;
-    // host-side resources reused by every render call of the scene (cudaMallocHost / cudaEventCreate per call stall the
-    // submitting thread for milliseconds on a busy host while the GPU idles)
     struct Progress { unsigned long long cursor; uint32_t n_path; uint32_t pad; };
     Progress* prog = nullptr;            // pinned, PB_PROG_RING entries
     std::vector<cudaEvent_t> events;     // pool, grown on demand
+};
+#define PB_PROG_RING 4
+static DeviceShared* device_shared(int device) {
+    static std::mutex m;
+    static DeviceShared* tab[64] = {nullptr};
+    std::lock_guard<std::mutex> g(m);
+    if (device < 0 || device >= 64) device = 0;
+    if (!tab[device]) tab[device] = new DeviceShared();  // never freed: outlives every scene; CUDA may be gone at exit
+    return tab[device];
+}
+
+struct SceneRenderState {  // cached per scene: light tables + path-state buffers (pooled blocks)
+    float* ld_func = nullptr; float* ld_cdf = nullptr; float ld_func_int = 0;
+    InfDistrib* inf = nullptr; uint32_t* inf_list = nullptr; uint32_t n_inf = 0;
+    int strategy = -1;
+    std::vector<std::pair<void*, size_t>> light_blocks;  // pooled
+    RenderBuffers* buffers = nullptr;
     std::vector<pbrt_b200_light> lights_host;
     bool lights_cached = false;
     // SpatialLightDistribution tables (persist across render calls of the scene: lazily built voxels stay built)
     SpatialDev sp = {};
     bool sp_eager_pending = false;
-    void* sp_allocs[8] = {nullptr};
+    DeviceShared* shared = nullptr;
+    void release_light_blocks() {
+        for (auto& b : light_blocks) pool_free(b.first, b.second);
+        light_blocks.clear();
+        ld_func = ld_cdf = nullptr; inf = nullptr; inf_list = nullptr;
+        sp = SpatialDev{}; sp_eager_pending = false;
+    }
 };
-#define PB_PROG_RING 4
 
-void render_release_scene_state(pbrt_b200_scene* sc) {
+void render_release_scene_state(pbrt_b200_scene* sc) {  // caller has synchronised the device
     SceneRenderState* st = reinterpret_cast<SceneRenderState*>(sc->light_distrib);
     if (!st) return;
-    cudaFree(st->ld_func); cudaFree(st->ld_cdf); cudaFree(st->inf); cudaFree(st->inf_list);
-    cudaFree(st->perms); cudaFree(st->primes); cudaFree(st->prime_sums);
-    cudaFree(st->sobol32); cudaFree(st->sobol_t); cudaFree(st->vdc); cudaFree(st->vdc_inv); cudaFree(st->filter_table);
-    if (st->prog) cudaFreeHost(st->prog);
-    for (cudaEvent_t e : st->events) cudaEventDestroy(e);
-    for (void* a : st->sp_allocs) cudaFree(a);
+    st->release_light_blocks();
     delete st->buffers;
     delete st;
     sc->light_distrib = nullptr;
@@ -1145,9 +1166,22 @@ struct Pcg32 {
     uint32_t bounded(uint32_t b) { uint32_t th = (~b + 1u) % b; for (;;) { uint32_t r = next(); if (r >= th) return r % b; } }
 };
 
-template <typename T> int to_device(const std::vector<T>& h, T** d) {
+template <typename T> int pooled_alloc(std::vector<std::pair<void*, size_t>>& owner, T** d, size_t count) {
+    size_t got = 0;
+    *d = reinterpret_cast<T*>(pool_alloc(count * sizeof(T), &got));
+    if (!*d) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory");
+    owner.push_back({*d, got});
+    return PBRT_B200_OK;
+}
+template <typename T> int to_device(std::vector<std::pair<void*, size_t>>& owner, const std::vector<T>& h, T** d) {
     *d = nullptr;
     if (h.empty()) return PBRT_B200_OK;
+    int rc = pooled_alloc(owner, d, h.size());
+    if (rc) return rc;
+    PB_CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return PBRT_B200_OK;
+}
+template <typename T> int to_device_once(const std::vector<T>& h, T** d) {  // device-shared tables: plain cudaMalloc, never freed
     PB_CUDA_TRY(cudaMalloc((void**)d, h.size() * sizeof(T)));
     PB_CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return PBRT_B200_OK;
@@ -1169,8 +1203,8 @@ int prepare_light_state(pbrt_b200_scene* sc, uint32_t strategy, uint32_t flags, 
     const size_t nl = lights.size();
     const int key = (int)strategy | ((flags & PBRT_B200_RENDER_LAZY_SPATIAL) ? 0x100 : 0);
     if (st->strategy != key) {
-        cudaFree(st->ld_func); cudaFree(st->ld_cdf); cudaFree(st->inf); cudaFree(st->inf_list);
-        st->ld_func = st->ld_cdf = nullptr; st->inf = nullptr; st->inf_list = nullptr;
+        if (st->strategy != -1) cudaDeviceSynchronize();
+        st->release_light_blocks();
         // create_light_sample_distribution, core/lightdistrib.rs:20-31 ("spatial" is not built yet: DESIGN.md)
         std::vector<float> func(nl, 1.0f), cdf;
         const float wr = sc->dev.world_radius, PI = 3.14159265358979323846f;
@@ -1200,9 +1234,6 @@ int prepare_light_state(pbrt_b200_scene* sc, uint32_t strategy, uint32_t flags, 
             }
         }
         // SpatialLightDistribution::new, lightdistrib.rs:113-150 (max_voxels = 64, lightdistrib.rs:26)
-        for (void*& a : st->sp_allocs) { cudaFree(a); a = nullptr; }
-        st->sp = SpatialDev{};
-        st->sp_eager_pending = false;
         if (!uniform && strategy == PBRT_B200_LIGHTS_SPATIAL && sc->n_nodes > 0) {
             SpatialDev& sp = st->sp;
             const float* wb = sc->dev.root_box;
@@ -1237,16 +1268,14 @@ int prepare_light_state(pbrt_b200_scene* sc, uint32_t strategy, uint32_t flags, 
                         hal[5 * i + b] = std::fmin((float)rev * inv_basen, 0.99999994f);
                     }
                 }
-            int na = 0;
-            auto alloc = [&](void** ptr, size_t bytes) -> int { PB_CUDA_TRY(cudaMalloc(ptr, bytes)); st->sp_allocs[na++] = *ptr; return PBRT_B200_OK; };
-            if ((rc = alloc((void**)&sp.slot, total * sizeof(int)))) return rc;
-            if ((rc = alloc((void**)&sp.func, cap * nl * sizeof(float)))) return rc;
-            if ((rc = alloc((void**)&sp.cdf, cap * (nl + 1) * sizeof(float)))) return rc;
-            if ((rc = alloc((void**)&sp.func_int, cap * sizeof(float)))) return rc;
-            if ((rc = alloc((void**)&sp.build_list, cap * sizeof(uint2)))) return rc;
-            if ((rc = alloc((void**)&sp.counters, 4 * sizeof(uint32_t)))) return rc;
+            if ((rc = pooled_alloc(st->light_blocks, &sp.slot, total))) return rc;
+            if ((rc = pooled_alloc(st->light_blocks, &sp.func, cap * nl))) return rc;
+            if ((rc = pooled_alloc(st->light_blocks, &sp.cdf, cap * (nl + 1)))) return rc;
+            if ((rc = pooled_alloc(st->light_blocks, &sp.func_int, cap))) return rc;
+            if ((rc = pooled_alloc(st->light_blocks, &sp.build_list, cap))) return rc;
+            if ((rc = pooled_alloc(st->light_blocks, &sp.counters, 4))) return rc;
             float* hal_dev = nullptr;
-            if ((rc = alloc((void**)&hal_dev, hal.size() * sizeof(float)))) return rc;
+            if ((rc = pooled_alloc(st->light_blocks, &hal_dev, hal.size()))) return rc;
             PB_CUDA_TRY(cudaMemcpy(hal_dev, hal.data(), hal.size() * sizeof(float), cudaMemcpyHostToDevice));
             sp.halton = hal_dev;
             PB_CUDA_TRY(cudaMemset(sp.slot, 0xff, total * sizeof(int)));
@@ -1254,10 +1283,10 @@ int prepare_light_state(pbrt_b200_scene* sc, uint32_t strategy, uint32_t flags, 
             st->sp_eager_pending = !sp.lazy;
         }
         make_distribution(func, cdf, &st->ld_func_int);
-        if ((rc = to_device(func, &st->ld_func))) return rc;
-        if ((rc = to_device(cdf, &st->ld_cdf))) return rc;
-        if ((rc = to_device(inf, &st->inf))) return rc;
-        if ((rc = to_device(inf_list, &st->inf_list))) return rc;
+        if ((rc = to_device(st->light_blocks, func, &st->ld_func))) return rc;
+        if ((rc = to_device(st->light_blocks, cdf, &st->ld_cdf))) return rc;
+        if ((rc = to_device(st->light_blocks, inf, &st->inf))) return rc;
+        if ((rc = to_device(st->light_blocks, inf_list, &st->inf_list))) return rc;
         st->n_inf = (uint32_t)inf_list.size();
         st->strategy = key;
     }
@@ -1268,26 +1297,38 @@ int prepare_scene_state(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, Sc
     SceneRenderState* st = nullptr;
     int rc = prepare_light_state(sc, rd->integrator.light_sample_strategy, rd->flags, &st);
     if (rc) return rc;
-    if (rd->sampler.kind == PBRT_B200_SAMPLER_SOBOL && st->sobol_src != rd->sampler.sobol_matrices32) {
+    DeviceShared* sh = device_shared(sc->device);
+    st->shared = sh;
+    if (rd->sampler.kind == PBRT_B200_SAMPLER_SOBOL) {
         if (!rd->sampler.sobol_matrices32 || !rd->sampler.vdc_matrices || !rd->sampler.vdc_matrices_inv)
             return fail(PBRT_B200_ERR_INVALID, "render: the Sobol sampler needs sobol_matrices32, vdc_matrices and vdc_matrices_inv");
-        cudaFree(st->sobol32); cudaFree(st->sobol_t); cudaFree(st->vdc); cudaFree(st->vdc_inv);
-        PB_CUDA_TRY(cudaMalloc((void**)&st->sobol32, 1024 * 52 * 4));
-        PB_CUDA_TRY(cudaMalloc((void**)&st->sobol_t, 1024 * 52 * 4));
-        {
+        // FNV-1a over the caller's tables (~230 KB): the device copy is reused while the contents are the same
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&](const void* p, size_t bytes) {
+            const unsigned long long* w = reinterpret_cast<const unsigned long long*>(p);
+            for (size_t i = 0; i < bytes / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+        };
+        mix(rd->sampler.sobol_matrices32, 1024 * 52 * 4); mix(rd->sampler.vdc_matrices, 25 * 52 * 8); mix(rd->sampler.vdc_matrices_inv, 26 * 52 * 8);
+        if (h == 0) h = 1;
+        if (sh->sobol_hash != h) {
+            if (!sh->sobol32) {
+                PB_CUDA_TRY(cudaMalloc((void**)&sh->sobol32, 1024 * 52 * 4));
+                PB_CUDA_TRY(cudaMalloc((void**)&sh->sobol_t, 1024 * 52 * 4));
+                PB_CUDA_TRY(cudaMalloc((void**)&sh->vdc, 25 * 52 * 8));
+                PB_CUDA_TRY(cudaMalloc((void**)&sh->vdc_inv, 26 * 52 * 8));
+            }
+            PB_CUDA_TRY(cudaDeviceSynchronize());
             std::vector<uint32_t> tr(1024 * 52);
             for (int d = 0; d < 1024; ++d)
                 for (int b = 0; b < 52; ++b) tr[b * 1024 + d] = rd->sampler.sobol_matrices32[d * 52 + b];
-            PB_CUDA_TRY(cudaMemcpy(st->sobol_t, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+            PB_CUDA_TRY(cudaMemcpy(sh->sobol_t, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+            PB_CUDA_TRY(cudaMemcpy(sh->sobol32, rd->sampler.sobol_matrices32, 1024 * 52 * 4, cudaMemcpyHostToDevice));
+            PB_CUDA_TRY(cudaMemcpy(sh->vdc, rd->sampler.vdc_matrices, 25 * 52 * 8, cudaMemcpyHostToDevice));
+            PB_CUDA_TRY(cudaMemcpy(sh->vdc_inv, rd->sampler.vdc_matrices_inv, 26 * 52 * 8, cudaMemcpyHostToDevice));
+            sh->sobol_hash = h;
         }
-        PB_CUDA_TRY(cudaMalloc((void**)&st->vdc, 25 * 52 * 8));
-        PB_CUDA_TRY(cudaMalloc((void**)&st->vdc_inv, 26 * 52 * 8));
-        PB_CUDA_TRY(cudaMemcpy(st->sobol32, rd->sampler.sobol_matrices32, 1024 * 52 * 4, cudaMemcpyHostToDevice));
-        PB_CUDA_TRY(cudaMemcpy(st->vdc, rd->sampler.vdc_matrices, 25 * 52 * 8, cudaMemcpyHostToDevice));
-        PB_CUDA_TRY(cudaMemcpy(st->vdc_inv, rd->sampler.vdc_matrices_inv, 26 * 52 * 8, cudaMemcpyHostToDevice));
-        st->sobol_src = rd->sampler.sobol_matrices32;
     }
-    if (rd->sampler.kind == PBRT_B200_SAMPLER_HALTON && !st->perms) {
+    if (rd->sampler.kind == PBRT_B200_SAMPLER_HALTON && !sh->perms) {
         const uint32_t N = 1000;  // PRIME_TABLE_SIZE, lowdiscrepancy.rs:9
         std::vector<uint32_t> primes, sums;
         for (uint32_t c = 2; primes.size() < N; ++c) {
@@ -1305,40 +1346,43 @@ int prepare_scene_state(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, Sc
             for (uint32_t k = 0; k < primes[i]; ++k) { uint32_t other = k + rng.bounded(primes[i] - k); std::swap(perms[off + k], perms[off + other]); }
             off += primes[i];
         }
-        if ((rc = to_device(perms, &st->perms))) return rc;
-        if ((rc = to_device(primes, &st->primes))) return rc;
-        if ((rc = to_device(sums, &st->prime_sums))) return rc;
-        st->n_halton_dims = N;
+        if ((rc = to_device_once(perms, &sh->perms))) return rc;
+        if ((rc = to_device_once(primes, &sh->primes))) return rc;
+        if ((rc = to_device_once(sums, &sh->prime_sums))) return rc;
+        sh->n_halton_dims = N;
     }
-    if (!st->filter_table) PB_CUDA_TRY(cudaMalloc((void**)&st->filter_table, 256 * sizeof(float)));
-    PB_CUDA_TRY(cudaMemcpyAsync(st->filter_table, rd->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice, 0));
-    if (!st->prog) PB_CUDA_TRY(cudaMallocHost((void**)&st->prog, PB_PROG_RING * sizeof(SceneRenderState::Progress)));
+    if (!sh->filter_table) PB_CUDA_TRY(cudaMalloc((void**)&sh->filter_table, 256 * sizeof(float)));
+    PB_CUDA_TRY(cudaMemcpyAsync(sh->filter_table, rd->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (!sh->prog) PB_CUDA_TRY(cudaMallocHost((void**)&sh->prog, PB_PROG_RING * sizeof(DeviceShared::Progress)));
     *out = st;
-    return PBRT_B200_OK;
-}
-
-template <typename T> int dev_alloc(RenderBuffers* rb, T** p, size_t count) {
-    PB_CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
-    rb->allocs.push_back(*p);
     return PBRT_B200_OK;
 }
 
 int ensure_buffers(SceneRenderState* st, uint32_t capacity) {
     if (st->buffers && st->buffers->capacity >= capacity) return PBRT_B200_OK;
+    if (st->buffers) cudaDeviceSynchronize();
     delete st->buffers;
     st->buffers = new RenderBuffers();
     RenderBuffers* rb = st->buffers;
     RenderDev& d = rb->dev;
     std::memset(&d, 0, sizeof d);
-    int rc;
-#define A(ptr, n) if ((rc = dev_alloc(rb, &ptr, (size_t)(n)))) return rc
-    A(d.ray, 2 * (size_t)capacity); A(d.hit, capacity); A(d.hit_b2, capacity); A(d.hit_bin, capacity); A(d.L_eta, capacity); A(d.beta_st, capacity); A(d.pfilm, capacity);
-    A(d.s_index, capacity); A(d.s_dim, capacity); A(d.pixel, capacity);
-    A(d.sh_ray, 2 * (size_t)capacity); A(d.sh_contrib, capacity); A(d.mis_ray, 2 * (size_t)capacity); A(d.mis_contrib, capacity);
-    A(d.q_path[0], capacity); A(d.q_path[1], capacity); A(d.q_shadow, capacity); A(d.q_mis, capacity); A(d.q_dead[0], capacity); A(d.q_dead[1], capacity);
-    for (int k = 0; k < Q_COUNT; ++k) A(d.q_mat[k], capacity);
-    A(d.cnt, 1);
-#undef A
+    const size_t c = capacity;
+    // bytes per slot: ray 32, hit 16+4+1, L_eta 16, beta_st 16, pfilm 8, s_index 8, s_dim 4, pixel 4, sh_ray 32, sh_contrib 16, mis_ray 32,
+    // mis_contrib 16, 6 + Q_COUNT index queues x 4
+    const size_t per_slot = 32 + 16 + 4 + 1 + 16 + 16 + 8 + 8 + 4 + 4 + 32 + 16 + 32 + 16 + 4 * (6 + Q_COUNT);
+    const size_t need = per_slot * c + 256 * 40 + sizeof(Counters);
+    rb->block = pool_alloc(need, &rb->block_bytes);
+    if (!rb->block) { delete st->buffers; st->buffers = nullptr; return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the path state"); }
+    Arena A; A.base = reinterpret_cast<char*>(rb->block); A.size = rb->block_bytes;
+    d.ray = A.take<float4>(2 * c); d.hit = A.take<uint4>(c); d.hit_b2 = A.take<float>(c); d.hit_bin = A.take<uint8_t>(c);
+    d.L_eta = A.take<float4>(c); d.beta_st = A.take<float4>(c); d.pfilm = A.take<float2>(c);
+    d.s_index = A.take<unsigned long long>(c); d.s_dim = A.take<uint32_t>(c); d.pixel = A.take<uint32_t>(c);
+    d.sh_ray = A.take<float4>(2 * c); d.sh_contrib = A.take<float4>(c); d.mis_ray = A.take<float4>(2 * c); d.mis_contrib = A.take<float4>(c);
+    d.q_path[0] = A.take<uint32_t>(c); d.q_path[1] = A.take<uint32_t>(c); d.q_shadow = A.take<uint32_t>(c); d.q_mis = A.take<uint32_t>(c);
+    d.q_dead[0] = A.take<uint32_t>(c); d.q_dead[1] = A.take<uint32_t>(c);
+    for (int k = 0; k < Q_COUNT; ++k) d.q_mat[k] = A.take<uint32_t>(c);
+    d.cnt = A.take<Counters>(1);
+    if (!d.cnt) { delete st->buffers; st->buffers = nullptr; return fail(PBRT_B200_ERR_CUDA, "render: path-state arena too small (internal error)"); }
     rb->capacity = capacity;
     return PBRT_B200_OK;
 }
@@ -1404,8 +1448,19 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (rd->integrator.light_sample_strategy > PBRT_B200_LIGHTS_SPATIAL) return fail(PBRT_B200_ERR_INVALID, "render: unknown light_sample_strategy");
     PB_CUDA_TRY(cudaSetDevice(sc->device));
     int rc;
+    DeviceShared* sh = device_shared(sc->device);
+    std::lock_guard<std::mutex> render_lock(sh->mu);
+    const bool prof = getenv("PBRT_B200_PROFILE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!prof) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pbrt_b200] render %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     SceneRenderState* st = nullptr;
     if ((rc = prepare_scene_state(sc, rd, &st))) return rc;
+    lap("prepare");
 
     const int* sb = rd->sampler.sample_bounds;
     const int* crop = rd->film.cropped_pixel_bounds;
@@ -1430,6 +1485,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
     if (capacity == 0) capacity = 256;
     if ((rc = ensure_buffers(st, capacity))) return rc;
+    lap("buffers");
     RenderDev R = st->buffers->dev;
     R.capacity = capacity;
     R.scene = sc->dev;
@@ -1445,7 +1501,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         S.resolution = v;
         S.log2_resolution = 0; while ((1 << S.log2_resolution) < v) S.log2_resolution++;
     }
-    S.sobol32 = st->sobol32; S.sobol_t = st->sobol_t; S.vdc = st->vdc; S.vdc_inv = st->vdc_inv;
+    S.sobol32 = sh->sobol32; S.sobol_t = sh->sobol_t; S.vdc = sh->vdc; S.vdc_inv = sh->vdc_inv;
     {
         long long res[2] = {sb[2] - sb[0], sb[3] - sb[1]};
         for (int i = 0; i < 2; ++i) {
@@ -1457,13 +1513,13 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         S.mult_inverse[0] = mult_inverse(S.base_scales[1], S.base_scales[0]);
         S.mult_inverse[1] = mult_inverse(S.base_scales[0], S.base_scales[1]);
     }
-    S.perms = st->perms; S.primes = st->primes; S.prime_sums = st->prime_sums; S.n_halton_dims = st->n_halton_dims;
+    S.perms = sh->perms; S.primes = sh->primes; S.prime_sums = sh->prime_sums; S.n_halton_dims = sh->n_halton_dims;
     // film
     for (int i = 0; i < 4; ++i) R.crop[i] = crop[i];
     R.filter_radius[0] = rd->film.filter_radius[0]; R.filter_radius[1] = rd->film.filter_radius[1];
     R.inv_filter_radius[0] = 1.0f / rd->film.filter_radius[0]; R.inv_filter_radius[1] = 1.0f / rd->film.filter_radius[1];
     R.max_sample_luminance = rd->film.max_sample_luminance;
-    R.filter_table = st->filter_table;
+    R.filter_table = sh->filter_table;
     // integrator
     R.max_depth = rd->integrator.max_depth; R.rr_threshold = rd->integrator.rr_threshold;
     for (int i = 0; i < 4; ++i) R.pixel_bounds[i] = rd->integrator.pixel_bounds[i];
@@ -1478,8 +1534,10 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     const size_t npix = (size_t)W * Hh;
     float4* film_dev = nullptr;
     bool own_film = !(rd->flags & PBRT_B200_RENDER_KEEP_ON_DEVICE);
+    size_t film_block = 0;
     if (own_film) {
-        PB_CUDA_TRY(cudaMalloc((void**)&film_dev, npix * sizeof(float4)));
+        film_dev = reinterpret_cast<float4*>(pool_alloc(npix * sizeof(float4), &film_block));
+        if (!film_dev) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the film");
         PB_CUDA_TRY(cudaMemsetAsync(film_dev, 0, npix * sizeof(float4), 0));
     } else film_dev = reinterpret_cast<float4*>(rgbw_out);
     R.film = film_dev;
@@ -1495,8 +1553,8 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     // events come from the scene's pool: [0] start, [1] end, [2..2+PB_PROG_RING) progress copies, then timing marks
     size_t ev_used = 2 + PB_PROG_RING;
     auto pool_event = [&](size_t i) -> cudaEvent_t {
-        while (st->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); st->events.push_back(e); }
-        return st->events[i];
+        while (sh->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sh->events.push_back(e); }
+        return sh->events[i];
     };
     cudaEvent_t ev0 = pool_event(0), ev1 = pool_event(1);
     const size_t tev_base = ev_used;
@@ -1517,7 +1575,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         // The host never waits on the batch it has just submitted: after every batch of `poll` iterations the queue
         // state is copied to a pinned ring entry, and the host looks at the copy of the batch BEFORE the one in flight,
         // so the GPU always has work queued behind the running iteration (over-submitted iterations find empty queues).
-        SceneRenderState::Progress* prog = st->prog;
+        DeviceShared::Progress* prog = sh->prog;
         k_init_slots<<<grid_small, 256, 0, stream>>>(R, capacity);
         k_finish_regen<<<grid_small, 256, 0, stream>>>(R, 1, total_items);
         k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
@@ -1559,7 +1617,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 iter++;
             }
             // {item_cursor, n_path} of this batch -> ring entry, event marks the copy
-            SceneRenderState::Progress* pe = prog + (batch % PB_PROG_RING);
+            DeviceShared::Progress* pe = prog + (batch % PB_PROG_RING);
             cudaMemcpyAsync(&pe->cursor, &R.cnt->item_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
             cudaMemcpyAsync(&pe->n_path, &R.cnt->n_path, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
             cudaEventRecord(pool_event(2 + batch % PB_PROG_RING), stream);
@@ -1567,7 +1625,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 unsigned long long pb = batch - 1;
                 cudaError_t e = cudaEventSynchronize(pool_event(2 + pb % PB_PROG_RING));
                 if (e != cudaSuccess) PB_CUDA_TRY(e);
-                const SceneRenderState::Progress* pp = prog + (pb % PB_PROG_RING);
+                const DeviceShared::Progress* pp = prog + (pb % PB_PROG_RING);
                 if (pp->cursor >= total_items && pp->n_path == 0) done = true;
             }
             batch++;
@@ -1577,6 +1635,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     PB_CUDA_TRY(cudaEventRecord(ev1, stream));
     PB_CUDA_TRY(cudaGetLastError());
     PB_CUDA_TRY(cudaStreamSynchronize(stream));
+    lap("wavefront loop");
     if (R.sp.enabled) {
         uint32_t spc[4];
         PB_CUDA_TRY(cudaMemcpy(spc, R.sp.counters, sizeof spc, cudaMemcpyDeviceToHost));
@@ -1592,21 +1651,45 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         cudaEventElapsedTime(&ms, ev0, ev1);
         stats->device_ms = ms;
         for (size_t k = tev_base; k + 5 < ev_used; k += 6) {
-            float a = 0.f, b = 0.f, m = 0.f, sh = 0.f, fin = 0.f;
-            cudaEventElapsedTime(&a, st->events[k], st->events[k + 1]);
-            cudaEventElapsedTime(&sh, st->events[k + 1], st->events[k + 2]);
-            cudaEventElapsedTime(&b, st->events[k + 2], st->events[k + 3]);
-            cudaEventElapsedTime(&m, st->events[k + 3], st->events[k + 4]);
-            cudaEventElapsedTime(&fin, st->events[k + 4], st->events[k + 5]);
-            stats->trace_closest_ms += a + m; stats->trace_any_ms += b; stats->shade_ms += sh; stats->finish_ms += fin;
+            float a = 0.f, b = 0.f, m = 0.f, shd = 0.f, fin = 0.f;
+            cudaEventElapsedTime(&a, sh->events[k], sh->events[k + 1]);
+            cudaEventElapsedTime(&shd, sh->events[k + 1], sh->events[k + 2]);
+            cudaEventElapsedTime(&b, sh->events[k + 2], sh->events[k + 3]);
+            cudaEventElapsedTime(&m, sh->events[k + 3], sh->events[k + 4]);
+            cudaEventElapsedTime(&fin, sh->events[k + 4], sh->events[k + 5]);
+            stats->trace_closest_ms += a + m; stats->trace_any_ms += b; stats->shade_ms += shd; stats->finish_ms += fin;
         }
         stats->iterations = c.iterations;
     }
     if (own_film) {
-        std::vector<float> tmp(npix * 4);
-        PB_CUDA_TRY(cudaMemcpy(tmp.data(), film_dev, npix * sizeof(float4), cudaMemcpyDeviceToHost));
-        cudaFree(film_dev);
-        for (size_t i = 0; i < npix * 4; ++i) rgbw_out[i] += tmp[i];
+        // film tile merge (merge_film_tile, film.rs:142-161): device film -> pinned staging in chunks, each chunk added into
+        // the caller's buffer while the next one is in flight
+        size_t stage_bytes = 0;
+        const size_t nfl = npix * 4, chunk = (size_t)1 << 20;  // floats per chunk (4 MB)
+        float* stage = reinterpret_cast<float*>(pool_alloc_host(std::min(nfl, 2 * chunk) * sizeof(float), &stage_bytes));
+        if (!stage) { pool_free(film_dev, film_block); return fail(PBRT_B200_ERR_CUDA, "render: out of pinned host memory"); }
+        const float* src = reinterpret_cast<const float*>(film_dev);
+        cudaEvent_t done[2] = {pool_event(0), pool_event(1)};
+        const size_t nchunks = (nfl + chunk - 1) / chunk;
+        cudaError_t e = cudaSuccess;
+        for (size_t k = 0; k <= nchunks && e == cudaSuccess; ++k) {
+            if (k < nchunks) {
+                size_t o = k * chunk, m = std::min(chunk, nfl - o);
+                e = cudaMemcpyAsync(stage + (k & 1) * chunk, src + o, m * sizeof(float), cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaEventRecord(done[k & 1], stream);
+            }
+            if (k >= 1 && e == cudaSuccess) {
+                size_t o = (k - 1) * chunk, m = std::min(chunk, nfl - o);
+                e = cudaEventSynchronize(done[(k - 1) & 1]);
+                const float* t = stage + ((k - 1) & 1) * chunk;
+                float* dst = rgbw_out + o;
+                for (size_t i = 0; i < m; ++i) dst[i] += t[i];
+            }
+        }
+        pool_free_host(stage, stage_bytes);
+        pool_free(film_dev, film_block);
+        PB_CUDA_TRY(e);
+        lap("film d2h + merge");
     }
     return PBRT_B200_OK;
 }

@@ -55,12 +55,12 @@ struct DevScene {
 struct pbrt_b200_scene {
     int device = 0;
     pb::DevScene dev;            // pointers are device pointers
-    void* allocs[16] = {nullptr};
-    int n_allocs = 0;
+    void* arena = nullptr;       // ONE pooled device block (pool.h) holding every scene table
+    size_t arena_bytes = 0;
     uint64_t n_prims = 0, n_nodes = 0;
     uint64_t device_bytes = 0;
-    void* scratch = nullptr;     // reusable staging for the host-buffer batch API
-    uint64_t scratch_bytes = 0;
+    void* scratch = nullptr;     // reusable staging for the host-buffer batch API (pooled)
+    size_t scratch_bytes = 0;
     void* light_distrib = nullptr;  // owned by render.cu
     uint32_t* fetch_counter = nullptr;  // device counter of the persistent ray queue (batch API)
     int trace_grid = 0;
