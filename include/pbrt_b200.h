@@ -270,6 +270,8 @@ typedef struct pbrt_b200_render_desc {
 
 enum {
     PBRT_B200_RENDER_KEEP_ON_DEVICE = 1u << 0, /* rgbw_out is a device pointer      */
+    PBRT_B200_RENDER_OVERWRITE = 1u << 2,      /* host rgbw_out is overwritten, not added to (Film::set_image, film.rs:172-184,
+                                                * instead of merge_film_tile): saves zeroing and re-reading the buffer   */
     PBRT_B200_RENDER_LAZY_SPATIAL = 1u << 1    /* "spatial" light distribution: build voxels on first touch even when
                                                 * the whole grid would fit (the mode used automatically for voxels x
                                                 * lights > 2^25; results are identical, lightdistrib.rs:231-340)    */

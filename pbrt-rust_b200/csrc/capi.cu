@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <algorithm>
@@ -276,23 +277,38 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
         fprintf(stderr, "[pbrt_b200] scene_create %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     };
-    int rc = validate(d);
-    if (rc) return rc;
-    lap("validate");
+    if (d->abi_version != PBRT_B200_ABI_VERSION) return fail(PBRT_B200_ERR_INVALID, "scene_create: abi_version mismatch");
+    if (d->n_prims && !d->prims) return fail(PBRT_B200_ERR_INVALID, "scene_create: prims is null");
+    if (d->n_nodes && !d->nodes) return fail(PBRT_B200_ERR_INVALID, "scene_create: nodes is null");
+    // The table checks (index ranges, BVH structure and depth: ~10 ms for 10^6 primitives) run on two worker threads
+    // while this thread stages the tables into HBM; nothing on the device dereferences an index before they have passed.
+    int rc = PBRT_B200_OK, rc_v = PBRT_B200_OK, rc_n = PBRT_B200_OK;
+    std::string err_v, err_n;
     uint32_t n_interior = 0, root_ref = PB_REF_NONE;
-    if ((rc = check_nodes(d, &n_interior, &root_ref))) return rc;
-    lap("check_nodes");
+    std::thread th_v([&] { rc_v = validate(d); if (rc_v) err_v = pbrt_b200::last_error_cstr(); });
+    std::thread th_n([&] { rc_n = check_nodes(d, &n_interior, &root_ref); if (rc_n) err_n = pbrt_b200::last_error_cstr(); });
+    struct Joiner { std::thread &a, &b; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); } } joiner{th_v, th_n};
+    auto join_checks = [&]() -> int {
+        th_v.join(); th_n.join();
+        if (rc_v) return fail(rc_v, err_v);
+        if (rc_n) return fail(rc_n, err_n);
+        return PBRT_B200_OK;
+    };
     int ndev = pbrt_b200_device_count();
-    if (ndev <= 0) return fail(PBRT_B200_ERR_NO_DEVICE, "scene_create: no CUDA device visible; this library has no CPU fallback");
+    if (ndev <= 0) {
+        if ((rc = join_checks())) return rc;  // malformed tables are reported as such even without a device
+        return fail(PBRT_B200_ERR_NO_DEVICE, "scene_create: no CUDA device visible; this library has no CPU fallback");
+    }
     if (device < 0 || device >= ndev) return fail(PBRT_B200_ERR_INVALID, "scene_create: device ordinal out of range");
     PB_CUDA_TRY(cudaSetDevice(device));
 
     const uint64_t nn = d->n_nodes, np = d->n_prims, nv = d->n_vertices, nt = d->n_triangles;
     const uint32_t nb = (uint32_t)((nn + PB_SCAN_BLOCK - 1) / PB_SCAN_BLOCK);
     // resident tables, then build-only temporaries (reference node array, scan scratch) at the tail of the same block
+    const uint64_t max_interior = nn / 2 + 1;  // a binary tree has one interior node less than leaves
     size_t need = 0;
     auto add = [&](size_t bytes) { need += Arena::padded(bytes); };
-    add(64ull * n_interior); add(48ull * np); add(sizeof(pbrt_b200_prim) * np);
+    add(64ull * max_interior); add(48ull * np); add(sizeof(pbrt_b200_prim) * np);
     add(12ull * nv); add(d->vertex_n ? 12ull * nv : 0); add(d->vertex_s ? 12ull * nv : 0); add(d->vertex_uv ? 8ull * nv : 0);
     add(12ull * nt); add(sizeof(pbrt_b200_sphere) * d->n_spheres); add(sizeof(pbrt_b200_material) * d->n_materials); add(sizeof(pbrt_b200_light) * d->n_lights);
     const size_t resident = need;
@@ -309,8 +325,6 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     sc->device_bytes = resident;
     Arena A; A.base = reinterpret_cast<char*>(sc->arena); A.size = sc->arena_bytes;
     DevScene& ds = sc->dev;
-    ds.root_ref = root_ref;
-    ds.n_fat = n_interior;
     ds.n_slots = (uint32_t)np;
     ds.n_lights = (uint32_t)d->n_lights;
     ds.n_materials = (uint32_t)d->n_materials;
@@ -336,22 +350,27 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
         *dev_out = reinterpret_cast<T*>(p);
         if (err == cudaSuccess) err = cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, stream);
     };
-    float4* fat = A.take<float4>(4ull * n_interior);
+    float4* fat = A.take<float4>(4ull * max_interior);
     float4* tris = A.take<float4>(3ull * np);
     ds.nodes = fat; ds.tris = tris;
+    const pbrt_b200_bvh_node* nodes_dev = nullptr;
     up(d->prims, sizeof(pbrt_b200_prim) * np, &ds.prims);
     up(d->vertex_p, 12ull * nv, &ds.vertex_p);
     up(d->tri_indices, 12ull * nt, &ds.tri_indices);
-    if (np && err == cudaSuccess) k_leaf_records<<<(unsigned)std::min<uint64_t>((np + 255) / 256, 148 * 16), 256, 0, stream>>>(ds.prims, (uint32_t)np, ds.tri_indices, ds.vertex_p, tris);
+    up(d->nodes, sizeof(pbrt_b200_bvh_node) * nn, &nodes_dev);
     up(d->vertex_n, d->vertex_n ? 12ull * nv : 0, &ds.vertex_n);
     up(d->vertex_s, d->vertex_s ? 12ull * nv : 0, &ds.vertex_s);
     up(d->vertex_uv, d->vertex_uv ? 8ull * nv : 0, &ds.vertex_uv);
     up(d->spheres, sizeof(pbrt_b200_sphere) * d->n_spheres, &ds.spheres);
     up(d->materials, sizeof(pbrt_b200_material) * d->n_materials, &ds.materials);
     up(d->lights, sizeof(pbrt_b200_light) * d->n_lights, &ds.lights);
+    lap("h2d staged");
+    if ((rc = join_checks())) { pbrt_b200_scene_destroy(sc); return rc; }
+    lap("checks joined");
+    ds.root_ref = root_ref;
+    ds.n_fat = n_interior;
+    if (np && err == cudaSuccess) k_leaf_records<<<(unsigned)std::min<uint64_t>((np + 255) / 256, 148 * 16), 256, 0, stream>>>(ds.prims, (uint32_t)np, ds.tri_indices, ds.vertex_p, tris);
     if (nn) {
-        const pbrt_b200_bvh_node* nodes_dev = nullptr;
-        up(d->nodes, sizeof(pbrt_b200_bvh_node) * nn, &nodes_dev);
         uint32_t* fat_index = A.take<uint32_t>(nn);
         uint32_t* block_sums = A.take<uint32_t>(nb);
         if (err == cudaSuccess) {

@@ -27,6 +27,19 @@
 #include "trace.cuh"
 #include "util.cuh"
 
+// occupancy knobs (min resident CTAs per SM in __launch_bounds__), A/B-measured with tools/step_diag.py on S3: shade 5/6/8 CTAs
+// (96/80/64 registers) and trace 6/8/10 CTAs are all within +-1% or slower than the compiler's default choice
+#ifdef PB_SHADE_MINB
+#define PB_SHADE_BOUNDS __launch_bounds__(128, PB_SHADE_MINB)
+#else
+#define PB_SHADE_BOUNDS __launch_bounds__(128)
+#endif
+#ifdef PB_TRACE_MINB
+#define PB_TRACE_BOUNDS __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB)
+#else
+#define PB_TRACE_BOUNDS __launch_bounds__(PB_TRACE_BLOCK)
+#endif
+
 using namespace pb;
 
 namespace pb {
@@ -398,11 +411,35 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     c.index = (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL)
                   ? sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, sample, x - R.sampler.sb[0], y - R.sampler.sb[1])
                   : halton_index(R.sampler, sample, x, y);
-    // get_camera_sample, sampler.rs:170-180
-    float2 u = get_2d(R.sampler, c);
+    // get_camera_sample, sampler.rs:170-180: dimensions 0..4
+    float2 u, plens;
+    float tu;
+    if (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL) {
+        // sobol_sample_float (lowdiscrepancy.rs:549-569) for the five dimensions in ONE walk over the set bits of the index,
+        // reading 5 adjacent columns of the bit-transposed matrices; dims 0/1 then get SobolSampler::sample_dimension's
+        // pixel remap (sobol.rs:69-87).  Same XOR sums as the per-dimension loops => identical values.
+        uint32_t v[5] = {0u, 0u, 0u, 0u, 0u};
+        unsigned long long a = c.index;
+        while (a != 0) {
+            int bit = __ffsll((long long)a) - 1;
+            a &= a - 1;
+            const uint32_t* row = R.sampler.sobol_t + (uint32_t)bit * 1024u;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) v[k] ^= __ldg(row + k);
+        }
+        float f[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) f[k] = fminf((float)v[k] * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
+        f[0] = clampf(f[0] * (float)R.sampler.resolution + (float)R.sampler.sb[0] - (float)x, 0.0f, PB_ONE_MINUS_EPSILON);
+        f[1] = clampf(f[1] * (float)R.sampler.resolution + (float)R.sampler.sb[1] - (float)y, 0.0f, PB_ONE_MINUS_EPSILON);
+        u = make_float2(f[0], f[1]); tu = f[2]; plens = make_float2(f[3], f[4]);
+        c.dim = 5;
+    } else {
+        u = get_2d(R.sampler, c);
+        tu = get_1d(R.sampler, c);
+        plens = get_2d(R.sampler, c);
+    }
     float2 pfilm = make_float2((float)x + u.x, (float)y + u.y);
-    float tu = get_1d(R.sampler, c);
-    float2 plens = get_2d(R.sampler, c);
     f3 o, d;
     float time;
     generate_ray(R.camera, pfilm, tu, plens, &o, &d, &time);
@@ -450,7 +487,7 @@ struct PathClosestJob {
     }
 };
 
-__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_closest(RenderDev R, int parity) {
+__global__ void PB_TRACE_BOUNDS k_trace_closest(RenderDev R, int parity) {
     PathClosestJob job{&R, R.q_path[parity]};
     trace_queue<false>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path);
 }
@@ -779,7 +816,7 @@ template <> struct BinKinds<Q_GLASS> { static constexpr int KM = KM_GLASS, MAT =
 template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT = PBRT_B200_MAT_METAL; };
 
 template <int BIN>
-__global__ void __launch_bounds__(128) k_shade(RenderDev R, int parity) {
+__global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     constexpr int KM = BinKinds<BIN>::KM;
     const uint32_t n = R.cnt->n_mat[BIN];
     const uint32_t* q = R.q_mat[BIN];
@@ -968,7 +1005,7 @@ struct ShadowJob {
         R->L_eta[id] = L;
     }
 };
-__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_shadow(RenderDev R) {
+__global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
     ShadowJob job{&R};
     trace_queue<true>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
 }
@@ -1008,7 +1045,7 @@ struct MisJob {
         }
     }
 };
-__global__ void __launch_bounds__(PB_TRACE_BLOCK) k_trace_mis(RenderDev R) {
+__global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
     MisJob job{&R};
     trace_queue<false>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
@@ -1683,7 +1720,8 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 e = cudaEventSynchronize(done[(k - 1) & 1]);
                 const float* t = stage + ((k - 1) & 1) * chunk;
                 float* dst = rgbw_out + o;
-                for (size_t i = 0; i < m; ++i) dst[i] += t[i];
+                if (rd->flags & PBRT_B200_RENDER_OVERWRITE) std::memcpy(dst, t, m * sizeof(float));
+                else for (size_t i = 0; i < m; ++i) dst[i] += t[i];
             }
         }
         pool_free_host(stage, stage_bytes);

@@ -102,6 +102,7 @@ class RenderStats(C.Structure):
 
 RENDER_KEEP_ON_DEVICE = 1
 RENDER_LAZY_SPATIAL = 2
+RENDER_OVERWRITE = 4
 
 EXPORTS = ["pbrt_b200_last_error", "pbrt_b200_abi_version", "pbrt_b200_device_count", "pbrt_b200_bvh_build", "pbrt_b200_scene_create",
            "pbrt_b200_scene_destroy", "pbrt_b200_scene_world_bound", "pbrt_b200_intersect", "pbrt_b200_intersect_p", "pbrt_b200_intersect_dev",
@@ -823,8 +824,9 @@ class Scene:
             d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE | flags, tile_interleave)
             _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), device_ptr, C.byref(stats)), "pbrt_b200_render")
             return None, stats
-        if rgbw is None:
-            rgbw = np.zeros((film.height * film.width, 4), f32)
+        if rgbw is None:  # fresh image: the library overwrites it (no zero fill, no read-modify-write on the host)
+            rgbw = np.empty((film.height * film.width, 4), f32)
+            flags |= RENDER_OVERWRITE
         d = integrator.desc(tile_range, sample_range, paths_in_flight, flags, tile_interleave)
         _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), _ptr(rgbw), C.byref(stats)), "pbrt_b200_render")
         return rgbw, stats
