@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PBRT_B200_ABI_VERSION 1
+#define PBRT_B200_ABI_VERSION 2
 
 enum {
     PBRT_B200_OK = 0,
@@ -62,7 +62,12 @@ int pbrt_b200_bvh_build(const float *prim_bounds, uint64_t n, int max_prims_in_n
 
 /* ---- scene tables ------------------------------------------------------ */
 
-enum { PBRT_B200_SHAPE_TRIANGLE = 0, PBRT_B200_SHAPE_SPHERE = 1 };
+enum {
+    PBRT_B200_SHAPE_TRIANGLE = 0,
+    PBRT_B200_SHAPE_SPHERE = 1,
+    PBRT_B200_SHAPE_INSTANCE = 2 /* the row is a TransformedPrimitive (primitive.rs:41-103): shape_index = instance number,
+                                  * material = area_light = -1 (get_material / get_area_light return None, :91-97)   */
+};
 enum {
     PBRT_B200_PRIM_REVERSE_ORIENTATION = 1u << 0, /* Shape::reverse_orientation          */
     PBRT_B200_PRIM_SWAPS_HANDEDNESS    = 1u << 1, /* Shape::transform_swapshandedness    */
@@ -81,6 +86,26 @@ typedef struct pbrt_b200_prim {
     uint32_t flags;          /* PBRT_B200_PRIM_*                                     */
     uint32_t creation_index; /* index before BVH reordering (what hit records carry) */
 } pbrt_b200_prim;
+
+/* = what an ObjectInstance refers to (src/core/api.rs:1663-1713): the primitives collected between ObjectBegin and
+ * ObjectEnd, wrapped in their own BVHAccel when there is more than one (api.rs:1691-1699).  An object's BVH nodes and
+ * primitive rows live in the scene's nodes[] / prims[] arrays AFTER the top-level ones; inside an object, node
+ * `offset`s (second child / first primitive) are relative to node_offset / prim_offset.  Objects are stored back to
+ * back in objects[] order: object 0 starts at n_top_nodes / n_top_prims, object k+1 where object k ends.            */
+typedef struct pbrt_b200_object {
+    uint64_t node_offset, n_nodes;   /* n_nodes == 0: a single primitive, referenced directly (no accelerator)       */
+    uint64_t prim_offset, n_prims;
+} pbrt_b200_object;
+
+/* = TransformedPrimitive (src/core/primitive.rs:41-103) with a static AnimatedTransform (start == end,
+ * transform.rs:1493-1497).  Per ray: Transform::inverse (m/m_inv swap) + transform_ray (:543-577, origin-error
+ * nudge and t_max -= dt), the object's own intersect, r.t_max = ray.t_max, transform_surface_interaction (:607-636). */
+typedef struct pbrt_b200_instance {
+    float prim_to_world[16];  /* row-major m                                                                          */
+    float world_to_prim[16];  /* m_inv                                                                                */
+    uint32_t object;          /* index into objects[]                                                                 */
+    uint32_t pad[3];
+} pbrt_b200_instance; /* 144 bytes */
 
 /* = Sphere (src/shapes/sphere.rs:19-57); full spheres only on the hot path.   */
 typedef struct pbrt_b200_sphere {
@@ -194,6 +219,11 @@ typedef struct pbrt_b200_scene_desc {
     const pbrt_b200_sphere *spheres; uint64_t n_spheres;
     const pbrt_b200_material *materials; uint64_t n_materials;
     const pbrt_b200_light *lights;   uint64_t n_lights;  /* Scene.lights order        */
+    /* Object instancing.  With n_objects == 0 every node and primitive row belongs to the top-level BVH and
+     * n_top_nodes / n_top_prims may be 0 (= n_nodes / n_prims).                                                  */
+    const pbrt_b200_object *objects;     uint64_t n_objects;
+    const pbrt_b200_instance *instances; uint64_t n_instances;
+    uint64_t n_top_nodes, n_top_prims;   /* Scene.aggregate: nodes[0, n_top_nodes), prims[0, n_top_prims)          */
 } pbrt_b200_scene_desc;
 
 typedef struct pbrt_b200_scene pbrt_b200_scene; /* opaque; owns device memory */

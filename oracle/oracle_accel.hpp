@@ -204,8 +204,9 @@ struct Counters {
 };
 
 struct Hit {
-    uint32_t slot = PBRT_B200_NO_HIT;  // index into prims[] (BVH order)
+    uint32_t slot = PBRT_B200_NO_HIT;  // index into prims[] (BVH order); for an instanced hit the row of the object's primitive
     Float t = 0, b0 = 0, b1 = 0, b2 = 0;
+    uint32_t inst = PBRT_B200_NO_HIT;  // instances[] index when the hit went through a TransformedPrimitive
 };
 
 struct SceneView {
@@ -215,6 +216,7 @@ struct SceneView {
     V3 N(uint32_t vi) const { return V3(d.vertex_n[3 * vi], d.vertex_n[3 * vi + 1], d.vertex_n[3 * vi + 2]); }
     V3 S(uint32_t vi) const { return V3(d.vertex_s[3 * vi], d.vertex_s[3 * vi + 1], d.vertex_s[3 * vi + 2]); }
     P2 UV(uint32_t vi) const { return P2(d.vertex_uv[2 * vi], d.vertex_uv[2 * vi + 1]); }
+    uint64_t top_nodes() const { return d.n_objects ? d.n_top_nodes : d.n_nodes; }
     void init(const pbrt_b200_scene_desc& desc) {
         d = desc;
         if (d.n_nodes) {
@@ -375,8 +377,28 @@ inline bool sphere_test(const pbrt_b200_sphere& sp, const Ray& r, Float* t_out, 
 // BVHAccel::intersect / intersect_p: src/accelerators/bvh.rs:705-814
 // GeometricPrimitive::intersect: src/core/primitive.rs:126-147
 // ------------------------------------------------------------------------
+template <bool ANY> inline bool bvh_traverse_range(const SceneView& s, uint64_t node_base, uint64_t n_nodes, uint64_t prim_base, Ray& r, Hit* hit, Counters* cnt);
+inline bool prim_intersect(const SceneView& s, uint32_t slot, Ray& r, Hit* hit, Counters* cnt);
+inline bool prim_intersect_p(const SceneView& s, uint32_t slot, const Ray& r, Counters* cnt);
+
+// TransformedPrimitive::intersect / intersect_p, src/core/primitive.rs:58-89 (static transform: interpolate returns the start
+// transform, transform.rs:1493-1497; Transform::inverse swaps m and m_inv, :240-242)
+template <bool ANY>
+inline bool instance_intersect(const SceneView& s, uint32_t inst, Ray& r, Hit* hit, Counters* cnt) {
+    const pbrt_b200_instance& in = s.d.instances[inst];
+    const pbrt_b200_object& ob = s.d.objects[in.object];
+    Ray ray = m4_ray(m4_from(in.world_to_prim), r);
+    bool found;
+    if (ob.n_nodes) found = bvh_traverse_range<ANY>(s, ob.node_offset, ob.n_nodes, ob.prim_offset, ray, hit, cnt);
+    else found = ANY ? prim_intersect_p(s, (uint32_t)ob.prim_offset, ray, cnt) : prim_intersect(s, (uint32_t)ob.prim_offset, ray, hit, cnt);
+    if (!found) return false;
+    if (!ANY) { r.t_max = ray.t_max; hit->inst = inst; }  // primitive.rs:72
+    return true;
+}
+
 inline bool prim_intersect(const SceneView& s, uint32_t slot, Ray& r, Hit* hit, Counters* cnt) {
     const pbrt_b200_prim& pr = s.d.prims[slot];
+    if (pr.shape_kind == PBRT_B200_SHAPE_INSTANCE) return instance_intersect<false>(s, pr.shape_index, r, hit, cnt);
     if (cnt) cnt->tris_tested++;
     if (pr.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
         uint32_t vi[3]; V3 p[3]; P2 uv[3];
@@ -384,18 +406,19 @@ inline bool prim_intersect(const SceneView& s, uint32_t slot, Ray& r, Hit* hit, 
         Float t, b0, b1, b2;
         if (!triangle_test(r, p[0], p[1], p[2], uv, true, &t, &b0, &b1, &b2)) return false;
         r.t_max = t;  // primitive.rs:137
-        hit->slot = slot; hit->t = t; hit->b0 = b0; hit->b1 = b1; hit->b2 = b2;
+        hit->slot = slot; hit->t = t; hit->b0 = b0; hit->b1 = b1; hit->b2 = b2; hit->inst = PBRT_B200_NO_HIT;
         return true;
     } else {
         Float t;
         if (!sphere_test(s.d.spheres[pr.shape_index], r, &t, nullptr)) return false;
         r.t_max = t;
-        hit->slot = slot; hit->t = t; hit->b0 = hit->b1 = hit->b2 = 0.0f;
+        hit->slot = slot; hit->t = t; hit->b0 = hit->b1 = hit->b2 = 0.0f; hit->inst = PBRT_B200_NO_HIT;
         return true;
     }
 }
 inline bool prim_intersect_p(const SceneView& s, uint32_t slot, const Ray& r, Counters* cnt) {
     const pbrt_b200_prim& pr = s.d.prims[slot];
+    if (pr.shape_kind == PBRT_B200_SHAPE_INSTANCE) { Ray rr = r; Hit h; return instance_intersect<true>(s, pr.shape_index, rr, &h, cnt); }
     if (cnt) cnt->tris_tested++;
     if (pr.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
         uint32_t vi[3]; V3 p[3]; P2 uv[3];
@@ -410,23 +433,26 @@ inline bool prim_intersect_p(const SceneView& s, uint32_t slot, const Ray& r, Co
 
 inline Bounds3 node_bounds(const pbrt_b200_bvh_node& n) { return Bounds3(V3(n.bounds[0], n.bounds[1], n.bounds[2]), V3(n.bounds[3], n.bounds[4], n.bounds[5])); }
 
+// node_base / prim_base: where this accelerator's nodes and primitive rows start in the flat arrays (0 for Scene.aggregate;
+// an object's BVH stores offsets relative to its own base, include/pbrt_b200.h pbrt_b200_object)
 template <bool ANY>
-inline bool bvh_traverse(const SceneView& s, Ray& r, Hit* hit, Counters* cnt) {
-    if (s.d.n_nodes == 0) return false;
-    if (cnt) cnt->rays++;
+inline bool bvh_traverse_range(const SceneView& s, uint64_t node_base, uint64_t n_nodes, uint64_t prim_base, Ray& r, Hit* hit, Counters* cnt) {
+    if (n_nodes == 0) return false;
+    const pbrt_b200_bvh_node* nodes = s.d.nodes + node_base;
     bool found = false;
     V3 inv_dir(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     int dir_isneg[3] = {inv_dir.x < 0.0f, inv_dir.y < 0.0f, inv_dir.z < 0.0f};
     size_t to_visit = 0, current = 0;
     size_t stack[64];
     for (;;) {
-        const pbrt_b200_bvh_node& node = s.d.nodes[current];
+        const pbrt_b200_bvh_node& node = nodes[current];
         if (cnt) cnt->nodes_tested++;
         if (bounds_intersect_p2(node_bounds(node), r, inv_dir, dir_isneg)) {
             if (node.n_prims > 0) {
                 for (uint32_t i = 0; i < node.n_prims; ++i) {
-                    if (ANY) { if (prim_intersect_p(s, node.offset + i, r, cnt)) return true; }
-                    else if (prim_intersect(s, node.offset + i, r, hit, cnt)) found = true;
+                    const uint32_t slot = (uint32_t)(prim_base + node.offset + i);
+                    if (ANY) { if (prim_intersect_p(s, slot, r, cnt)) return true; }
+                    else if (prim_intersect(s, slot, r, hit, cnt)) found = true;
                 }
                 if (to_visit == 0) break;
                 current = stack[--to_visit];
@@ -440,6 +466,12 @@ inline bool bvh_traverse(const SceneView& s, Ray& r, Hit* hit, Counters* cnt) {
         }
     }
     return found;
+}
+template <bool ANY>
+inline bool bvh_traverse(const SceneView& s, Ray& r, Hit* hit, Counters* cnt) {
+    if (s.d.n_nodes == 0) return false;
+    if (cnt) cnt->rays++;
+    return bvh_traverse_range<ANY>(s, 0, s.top_nodes(), 0, r, hit, cnt);
 }
 // Scene::intersect / intersect_p, src/core/scene.rs:54-66
 inline bool scene_intersect(const SceneView& s, Ray& r, Hit* hit, Counters* cnt) { return bvh_traverse<false>(s, r, hit, cnt); }
@@ -564,8 +596,37 @@ inline SurfaceInteraction sphere_interaction(const pbrt_b200_sphere& sp, const R
     return ret;
 }
 
+// Transform::transform_surface_interaction, transform.rs:607-636 (the fields the path integrator reads)
+inline SurfaceInteraction m4_surface_interaction(const M4& m, const M4& m_inv, const SurfaceInteraction& s) {
+    SurfaceInteraction ret;
+    ret.p = m4_point_abs_error(m, s.p, s.p_error, &ret.p_error);
+    ret.n = normalize(m4_normal(m_inv, s.n));
+    ret.wo = normalize(m4_vector(m, s.wo));
+    ret.time = s.time; ret.uv = s.uv;
+    ret.dpdu = m4_vector(m, s.dpdu); ret.dpdv = m4_vector(m, s.dpdv);
+    ret.sh_n = normalize(m4_normal(m_inv, s.sh_n));
+    ret.sh_dpdu = m4_vector(m, s.sh_dpdu); ret.sh_dpdv = m4_vector(m, s.sh_dpdv);
+    ret.sh_n = face_forward(ret.sh_n, ret.n);
+    ret.slot = s.slot;
+    return ret;
+}
+inline bool m4_is_identity(const M4& m) {  // transform.rs:229-238
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (m.m[i][j] != (i == j ? 1.0f : 0.0f)) return false;
+    return true;
+}
+
 inline SurfaceInteraction make_interaction(const SceneView& s, const Ray& r, const Hit& h) {
     const pbrt_b200_prim& pr = s.d.prims[h.slot];
+    if (h.inst != PBRT_B200_NO_HIT) {  // TransformedPrimitive::intersect, primitive.rs:58-80
+        const pbrt_b200_instance& in = s.d.instances[h.inst];
+        M4 p2w = m4_from(in.prim_to_world), w2p = m4_from(in.world_to_prim);
+        Ray ray = m4_ray(w2p, r);
+        SurfaceInteraction si = (pr.shape_kind == PBRT_B200_SHAPE_TRIANGLE) ? triangle_interaction(s, pr, ray, h.b0, h.b1, h.b2, true)
+                                                                            : sphere_interaction(s.d.spheres[pr.shape_index], ray, h.t);
+        si.slot = h.slot;
+        if (!m4_is_identity(p2w)) si = m4_surface_interaction(p2w, w2p, si);
+        return si;
+    }
     SurfaceInteraction si = (pr.shape_kind == PBRT_B200_SHAPE_TRIANGLE) ? triangle_interaction(s, pr, r, h.b0, h.b1, h.b2, true)
                                                                         : sphere_interaction(s.d.spheres[pr.shape_index], r, h.t);
     si.slot = h.slot;

@@ -56,10 +56,11 @@ struct BatchAnyJob {
     PB_D void store(uint32_t i, const TravRay& r) const { occluded[i] = r.found ? 1 : 0; }
 };
 
+template <bool INST>
 __global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_batch(DevScene s, const float4* __restrict__ rays, uint32_t n, uint4* __restrict__ hits,
                                                                    uint32_t* fetch, TraceTune tune) {
     BatchClosestJob job{rays, hits, s.tris};
-    trace_queue<false>(s, job, n, fetch, tune);
+    trace_queue<false, INST>(s, job, n, fetch, tune);
 }
 
 // A/B variants for tuning (tools/trace_ab.py): one ray per thread, while-while or if-if
@@ -75,10 +76,11 @@ __global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_batch_1rpt(DevScen
     job.store(i, r);
 }
 
+template <bool INST>
 __global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_p_batch(DevScene s, const float4* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occluded,
                                                                      uint32_t* fetch) {
     BatchAnyJob job{rays, occluded};
-    trace_queue<true>(s, job, n, fetch);
+    trace_queue<true, INST>(s, job, n, fetch);
 }
 
 // ---------------------------------------------------------------------------
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(256) k_leaf_records(const pbrt_b200_prim* __re
                 const float* vp = vertex_p + 3ull * ix[k];
                 v[k].x = vp[0]; v[k].y = vp[1]; v[k].z = vp[2];
             }
+        } else if (p.shape_kind == PBRT_B200_SHAPE_INSTANCE) {
+            fl |= PB_TRI_INSTANCE;
         } else {
             fl |= PB_TRI_SPHERE;
         }
@@ -160,24 +164,34 @@ __global__ void __launch_bounds__(PB_SCAN_BLOCK) k_interior_index(const pbrt_b20
     uint32_t ex = block_exclusive_scan(node_is_interior(nodes, i, n), &total);
     if (i < n) fat_index[i] = ex + block_sums[blockIdx.x];
 }
-__global__ void __launch_bounds__(256) k_fat_nodes(const pbrt_b200_bvh_node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ fat_index,
-                                                   float4* __restrict__ fat, float4* __restrict__ tris) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// One accelerator (the scene's aggregate or one instanced object): nodes [node_base, node_base + n), whose `offset`s are
+// relative to node_base (second child) / prim_base (first primitive).  Child refs written to the fat nodes are global.
+__global__ void __launch_bounds__(256) k_fat_nodes(const pbrt_b200_bvh_node* __restrict__ nodes, uint32_t node_base, uint32_t n, uint32_t prim_base,
+                                                   const uint32_t* __restrict__ fat_index, float4* __restrict__ fat, float4* __restrict__ tris) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t i = node_base + k;
         const pbrt_b200_bvh_node nd = nodes[i];
         if (nd.n_prims != 0) {  // leaf: the last primitive of the run carries PB_TRI_LAST
-            float4* rec = tris + 3ull * (nd.offset + nd.n_prims - 1) + 1;
+            float4* rec = tris + 3ull * (prim_base + nd.offset + nd.n_prims - 1) + 1;
             rec->w = __uint_as_float(__float_as_uint(rec->w) | PB_TRI_LAST);
             continue;
         }
-        const uint32_t c0 = i + 1, c1 = nd.offset;
+        const uint32_t c0 = i + 1, c1 = node_base + nd.offset;
         const pbrt_b200_bvh_node a = nodes[c0], b = nodes[c1];
-        const uint32_t r0 = a.n_prims ? (PB_LEAF_BIT | a.offset) : fat_index[c0];
-        const uint32_t r1 = b.n_prims ? (PB_LEAF_BIT | b.offset) : fat_index[c1];
+        const uint32_t r0 = a.n_prims ? (PB_LEAF_BIT | (prim_base + a.offset)) : fat_index[c0];
+        const uint32_t r1 = b.n_prims ? (PB_LEAF_BIT | (prim_base + b.offset)) : fat_index[c1];
         float4* q = fat + 4ull * fat_index[i];
         q[0] = make_float4(a.bounds[0], a.bounds[1], a.bounds[2], a.bounds[3]);
         q[1] = make_float4(a.bounds[4], a.bounds[5], b.bounds[0], b.bounds[1]);
         q[2] = make_float4(b.bounds[2], b.bounds[3], b.bounds[4], b.bounds[5]);
         q[3] = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float((uint32_t)nd.axis), 0.0f);
+    }
+}
+
+__global__ void k_single_prim_last(const uint32_t* __restrict__ slots, uint32_t n, float4* __restrict__ tris) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        float4* rec = tris + 3ull * slots[k] + 1;
+        rec->w = __uint_as_float(__float_as_uint(rec->w) | PB_TRI_LAST);
     }
 }
 
@@ -199,11 +213,32 @@ int validate(const pbrt_b200_scene_desc* d) {
                 return fail(PBRT_B200_ERR_INVALID, "scene_create: vertex index out of range");
         } else if (p.shape_kind == PBRT_B200_SHAPE_SPHERE) {
             if (p.shape_index >= d->n_spheres) return fail(PBRT_B200_ERR_INVALID, "scene_create: sphere index out of range");
+        } else if (p.shape_kind == PBRT_B200_SHAPE_INSTANCE) {
+            if (p.shape_index >= d->n_instances) return fail(PBRT_B200_ERR_INVALID, "scene_create: instance index out of range");
+            if (d->n_objects == 0 || i >= d->n_top_prims) return fail(PBRT_B200_ERR_INVALID, "scene_create: an instance inside an object (ObjectInstance can't be nested, api.rs:1674-1677)");
         } else {
             return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: shape kind outside the hot path (triangle, sphere)");
         }
         if (p.material >= (int64_t)d->n_materials) return fail(PBRT_B200_ERR_INVALID, "scene_create: material index out of range");
         if (p.area_light >= (int64_t)d->n_lights) return fail(PBRT_B200_ERR_INVALID, "scene_create: area light index out of range");
+    }
+    if (d->n_objects) {
+        if (!d->objects || (d->n_instances && !d->instances)) return fail(PBRT_B200_ERR_INVALID, "scene_create: objects / instances is null");
+        if (d->n_top_nodes > d->n_nodes || d->n_top_prims > d->n_prims) return fail(PBRT_B200_ERR_INVALID, "scene_create: n_top_nodes / n_top_prims out of range");
+        uint64_t next_node = d->n_top_nodes, next_prim = d->n_top_prims;
+        for (uint64_t k = 0; k < d->n_objects; ++k) {
+            const pbrt_b200_object& o = d->objects[k];
+            if (o.node_offset != next_node || o.prim_offset != next_prim)
+                return fail(PBRT_B200_ERR_INVALID, "scene_create: objects must follow the top-level tables back to back, in order");
+            next_node += o.n_nodes; next_prim += o.n_prims;
+            if (o.node_offset < d->n_top_nodes || o.node_offset + o.n_nodes > d->n_nodes || o.prim_offset < d->n_top_prims || o.n_prims == 0 ||
+                o.prim_offset + o.n_prims > d->n_prims || (o.n_nodes == 0 && o.n_prims != 1))
+                return fail(PBRT_B200_ERR_INVALID, "scene_create: object table out of range");
+        }
+        for (uint64_t k = 0; k < d->n_instances; ++k)
+            if (d->instances[k].object >= d->n_objects) return fail(PBRT_B200_ERR_INVALID, "scene_create: instance refers to a missing object");
+    } else if (d->n_instances) {
+        return fail(PBRT_B200_ERR_INVALID, "scene_create: instances without objects");
     }
     for (uint64_t i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type > PBRT_B200_MAT_METAL) return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: material outside the hot path");
@@ -220,17 +255,15 @@ int validate(const pbrt_b200_scene_desc* d) {
 // One pass over LinearBVHNode[] in array order (parents precede their children: first child at i+1, second at
 // `offset` > i, bvh.rs:662-693): structural checks, interior count, and the depth of every node -- the reference
 // would panic on a traversal stack deeper than 64 entries (bvh.rs:722).
-int check_nodes(const pbrt_b200_scene_desc* d, uint32_t* n_interior, uint32_t* root_ref) {
-    const uint64_t nn = d->n_nodes;
-    *n_interior = 0; *root_ref = PB_REF_NONE;
+int check_node_range(const pbrt_b200_bvh_node* nodes, uint64_t nn, uint64_t n_prims, uint32_t* n_interior) {
+    *n_interior = 0;
     if (nn == 0) return PBRT_B200_OK;
     std::vector<uint8_t> depth(nn, 0);
     uint32_t ni = 0;
-    int maxd = 0;
     for (uint64_t i = 0; i < nn; ++i) {
-        const pbrt_b200_bvh_node& n = d->nodes[i];
+        const pbrt_b200_bvh_node& n = nodes[i];
         if (n.n_prims != 0) {
-            if ((uint64_t)n.offset + n.n_prims > d->n_prims)
+            if ((uint64_t)n.offset + n.n_prims > n_prims)
                 return fail(PBRT_B200_ERR_INVALID, i == 0 ? "scene_create: root node refers past the primitive table" : "scene_create: malformed LinearBVHNode array");
             continue;
         }
@@ -239,11 +272,30 @@ int check_nodes(const pbrt_b200_scene_desc* d, uint32_t* n_interior, uint32_t* r
         const int dd = depth[i] + 1;
         if (dd >= PB_STACK_DEPTH) return fail(PBRT_B200_ERR_INVALID, "scene_create: BVH deeper than the reference's 64-entry traversal stack");
         depth[c0] = depth[c1] = (uint8_t)dd;
-        maxd = dd > maxd ? dd : maxd;
         ++ni;
     }
     *n_interior = ni;
-    *root_ref = d->nodes[0].n_prims ? (PB_LEAF_BIT | d->nodes[0].offset) : 0u;
+    return PBRT_B200_OK;
+}
+// the scene's aggregate, then every instanced object's accelerator
+int check_nodes(const pbrt_b200_scene_desc* d, uint32_t* n_interior, uint32_t* root_ref, std::vector<uint32_t>* obj_fat_base) {
+    *n_interior = 0; *root_ref = PB_REF_NONE;
+    obj_fat_base->assign(d->n_objects, 0u);
+    const uint64_t top_nodes = d->n_objects ? d->n_top_nodes : d->n_nodes, top_prims = d->n_objects ? d->n_top_prims : d->n_prims;
+    if (top_nodes == 0) return PBRT_B200_OK;
+    uint32_t ni = 0;
+    int rc = check_node_range(d->nodes, top_nodes, top_prims, &ni);
+    if (rc) return rc;
+    *root_ref = d->nodes[0].n_prims ? (PB_LEAF_BIT | d->nodes[0].offset) : 0u;  // fat index of node 0 is 0 when it is interior
+    for (uint64_t k = 0; k < d->n_objects; ++k) {
+        const pbrt_b200_object& o = d->objects[k];
+        if (o.n_nodes > d->n_nodes || o.node_offset > d->n_nodes - o.n_nodes || o.n_prims > d->n_prims || o.prim_offset > d->n_prims - o.n_prims) continue;  // validate() reports it
+        uint32_t no = 0;
+        if ((rc = check_node_range(d->nodes + o.node_offset, o.n_nodes, o.n_prims, &no))) return rc;
+        (*obj_fat_base)[k] = ni;  // interior nodes are numbered in array order across all accelerators
+        ni += no;
+    }
+    *n_interior = ni;
     return PBRT_B200_OK;
 }
 
@@ -286,7 +338,8 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     std::string err_v, err_n;
     uint32_t n_interior = 0, root_ref = PB_REF_NONE;
     std::thread th_v([&] { rc_v = validate(d); if (rc_v) err_v = pbrt_b200::last_error_cstr(); });
-    std::thread th_n([&] { rc_n = check_nodes(d, &n_interior, &root_ref); if (rc_n) err_n = pbrt_b200::last_error_cstr(); });
+    std::vector<uint32_t> obj_fat_base;
+    std::thread th_n([&] { rc_n = check_nodes(d, &n_interior, &root_ref, &obj_fat_base); if (rc_n) err_n = pbrt_b200::last_error_cstr(); });
     struct Joiner { std::thread &a, &b; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); } } joiner{th_v, th_n};
     auto join_checks = [&]() -> int {
         th_v.join(); th_n.join();
@@ -311,6 +364,7 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     add(64ull * max_interior); add(48ull * np); add(sizeof(pbrt_b200_prim) * np);
     add(12ull * nv); add(d->vertex_n ? 12ull * nv : 0); add(d->vertex_s ? 12ull * nv : 0); add(d->vertex_uv ? 8ull * nv : 0);
     add(12ull * nt); add(sizeof(pbrt_b200_sphere) * d->n_spheres); add(sizeof(pbrt_b200_material) * d->n_materials); add(sizeof(pbrt_b200_light) * d->n_lights);
+    add(sizeof(DevInstance) * d->n_instances); add(4ull * d->n_objects); add(sizeof(DevScene));
     const size_t resident = need;
     add(sizeof(pbrt_b200_bvh_node) * nn); add(4ull * nn); add(4ull * nb);
     need += 4096;
@@ -377,8 +431,51 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
             k_interior_count<<<nb, PB_SCAN_BLOCK, 0, stream>>>(nodes_dev, (uint32_t)nn, block_sums);
             k_interior_scan_blocks<<<1, PB_SCAN_BLOCK, 0, stream>>>(block_sums, nb);
             k_interior_index<<<nb, PB_SCAN_BLOCK, 0, stream>>>(nodes_dev, (uint32_t)nn, block_sums, fat_index);
-            k_fat_nodes<<<(unsigned)std::min<uint64_t>((nn + 255) / 256, 148 * 16), 256, 0, stream>>>(nodes_dev, (uint32_t)nn, fat_index, fat, tris);
+            auto fat_launch = [&](uint64_t node_base, uint64_t count, uint64_t prim_base) {
+                if (count) k_fat_nodes<<<(unsigned)std::min<uint64_t>((count + 255) / 256, 148 * 16), 256, 0, stream>>>(nodes_dev, (uint32_t)node_base, (uint32_t)count,
+                                                                                                                      (uint32_t)prim_base, fat_index, fat, tris);
+            };
+            fat_launch(0, d->n_objects ? d->n_top_nodes : nn, 0);
+            for (uint64_t k = 0; k < d->n_objects; ++k) fat_launch(d->objects[k].node_offset, d->objects[k].n_nodes, d->objects[k].prim_offset);
         }
+    }
+    if (d->n_instances && err == cudaSuccess) {
+        // TransformedPrimitive table + the LAST flag of one-primitive objects (they have no leaf node to set it)
+        std::vector<DevInstance> inst(d->n_instances);
+        std::vector<uint32_t> singles;
+        for (uint64_t k = 0; k < d->n_objects; ++k)
+            if (d->objects[k].n_nodes == 0) singles.push_back((uint32_t)d->objects[k].prim_offset);
+        for (uint64_t k = 0; k < d->n_instances; ++k) {
+            const pbrt_b200_instance& in = d->instances[k];
+            const pbrt_b200_object& o = d->objects[in.object];
+            DevInstance& di = inst[k];
+            std::memcpy(di.world_to_prim, in.world_to_prim, 64); std::memcpy(di.prim_to_world, in.prim_to_world, 64);
+            bool ident = true;
+            for (int a = 0; a < 16; ++a) ident = ident && in.prim_to_world[a] == ((a % 5 == 0) ? 1.0f : 0.0f);  // transform.rs:229-238
+            di.flags = ident ? PB_INST_IDENTITY : 0u;
+            if (o.n_nodes == 0) {
+                di.root_ref = PB_LEAF_BIT | (uint32_t)o.prim_offset;
+                for (int a = 0; a < 6; ++a) di.root_box[a] = 0.0f;
+            } else {
+                const pbrt_b200_bvh_node& rn = d->nodes[o.node_offset];
+                di.root_ref = rn.n_prims ? (PB_LEAF_BIT | (uint32_t)(o.prim_offset + rn.offset)) : obj_fat_base[in.object];
+                di.flags |= PB_INST_HAS_BOX;
+                std::memcpy(di.root_box, rn.bounds, sizeof di.root_box);
+            }
+        }
+        up(inst.data(), sizeof(DevInstance) * inst.size(), &ds.instances);
+        ds.n_instances = (uint32_t)d->n_instances;
+        if (!singles.empty()) {
+            const uint32_t* singles_dev = nullptr;
+            up(singles.data(), 4ull * singles.size(), &singles_dev);
+            if (err == cudaSuccess) k_single_prim_last<<<(unsigned)((singles.size() + 255) / 256), 256, 0, stream>>>(singles_dev, (uint32_t)singles.size(), tris);
+        }
+        if (err == cudaSuccess) err = cudaStreamSynchronize(stream);  // `inst` / `singles` are stack-owned staging sources
+    }
+    {
+        DevScene* self = A.take<DevScene>(1);
+        ds.self_dev = self;
+        if (self && err == cudaSuccess) err = cudaMemcpyAsync(self, &ds, sizeof(DevScene), cudaMemcpyHostToDevice, stream);
     }
     lap("enqueue h2d+build");
     if (err == cudaSuccess) err = cudaGetLastError();
@@ -410,7 +507,7 @@ int ensure_fetch_counter(pbrt_b200_scene* sc) {
     if (!sc->fetch_counter) return fail(PBRT_B200_ERR_CUDA, "out of device memory");
     int sm = 148, per_sm = 8;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, sc->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intersect_batch, PB_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc->dev.n_instances ? k_intersect_batch<true> : k_intersect_batch<false>, PB_TRACE_BLOCK, 0);
     sc->trace_grid = sm * (per_sm > 0 ? per_sm : 1);  // persistent: one resident wave of CTAs
     return PBRT_B200_OK;
 }
@@ -431,8 +528,12 @@ extern "C" int pbrt_b200_intersect_dev(pbrt_b200_scene* sc, const pbrt_b200_ray*
     } else {
         TraceTune tune{g_tune[1], g_tune[2], g_tune[4]};
         int grid = g_tune[3] > 0 ? g_tune[3] : sc->trace_grid;
-        k_intersect_batch<<<grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n,
-                                                                             reinterpret_cast<uint4*>(hits), sc->fetch_counter, tune);
+        if (sc->dev.n_instances)
+            k_intersect_batch<true><<<grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n,
+                                                                                       reinterpret_cast<uint4*>(hits), sc->fetch_counter, tune);
+        else
+            k_intersect_batch<false><<<grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n,
+                                                                                        reinterpret_cast<uint4*>(hits), sc->fetch_counter, tune);
     }
     PB_CUDA_TRY(cudaGetLastError());
     return PBRT_B200_OK;
@@ -446,8 +547,12 @@ extern "C" int pbrt_b200_intersect_p_dev(pbrt_b200_scene* sc, const pbrt_b200_ra
     int rc = ensure_fetch_counter(sc);
     if (rc) return rc;
     PB_CUDA_TRY(cudaMemsetAsync(sc->fetch_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
-    k_intersect_p_batch<<<sc->trace_grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, occluded,
-                                                                                    sc->fetch_counter);
+    if (sc->dev.n_instances)
+        k_intersect_p_batch<true><<<sc->trace_grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, occluded,
+                                                                                              sc->fetch_counter);
+    else
+        k_intersect_p_batch<false><<<sc->trace_grid, PB_TRACE_BLOCK, 0, (cudaStream_t)stream>>>(sc->dev, reinterpret_cast<const float4*>(rays), (uint32_t)n, occluded,
+                                                                                               sc->fetch_counter);
     PB_CUDA_TRY(cudaGetLastError());
     return PBRT_B200_OK;
 }

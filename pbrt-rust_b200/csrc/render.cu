@@ -130,6 +130,7 @@ struct RenderDev {
     float4* ray;         // 2 x float4 per slot: {o, t_max}, {d, time}
     uint4* hit;          // {slot, t, b0, b1}
     float* hit_b2;
+    uint32_t* hit_inst;  // instance of the hit (TransformedPrimitive) or PBRT_B200_NO_HIT; only touched when the scene has instances
     uint8_t* hit_bin;    // material bin of the hit (Q_*), written by trace_closest, consumed by classify
     float4* L_eta;       // {L.rgb, etascale}
     float4* beta_st;     // {beta.rgb, bits: bounces | specular_bounce << 16}
@@ -478,6 +479,7 @@ struct PathClosestJob {
         uint32_t id = q[i];
         R->hit[id] = make_uint4(r.hit.slot, __float_as_uint(r.hit.t), __float_as_uint(r.hit.b0), __float_as_uint(r.hit.b1));
         R->hit_b2[id] = r.hit.b2;
+        if (R->scene.n_instances) R->hit_inst[id] = r.hit.inst;
         int bin = Q_MISS;
         if (r.found) {
             int m = R->scene.prims[r.hit.slot].material;
@@ -487,9 +489,10 @@ struct PathClosestJob {
     }
 };
 
+template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_closest(RenderDev R, int parity) {
     PathClosestJob job{&R, R.q_path[parity]};
-    trace_queue<false>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path);
+    trace_queue<false, INST>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path);
 }
 
 // sort/compact-by-material: one warp-aggregated append per material queue
@@ -761,7 +764,9 @@ __global__ void __launch_bounds__(256) k_spatial_mark(RenderDev R, int parity) {
         float4 ra = R.ray[2 * id], rb = R.ray[2 * id + 1];
         uint4 h = R.hit[id];
         uint32_t fl;
-        Surf si = surface_at(R.scene, h.x, f3(ra.x, ra.y, ra.z), f3(rb.x, rb.y, rb.z), __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
+        const uint32_t hinst = R.scene.n_instances ? R.hit_inst[id] : PBRT_B200_NO_HIT;
+        Surf si = surface_at_hit<true>(R.scene, hinst, h.x, f3(ra.x, ra.y, ra.z), f3(rb.x, rb.y, rb.z), __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w),
+                                 R.hit_b2[id], &fl);
         int v = spatial_voxel(R, si.p);
         if (R.sp.slot[v] != -1) continue;
         if (atomicCAS(R.sp.slot + v, -1, -2) == -1) {
@@ -815,7 +820,7 @@ template <> struct BinKinds<Q_MIRROR> { static constexpr int KM = KM_MIRROR, MAT
 template <> struct BinKinds<Q_GLASS> { static constexpr int KM = KM_GLASS, MAT = PBRT_B200_MAT_GLASS; };
 template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT = PBRT_B200_MAT_METAL; };
 
-template <int BIN>
+template <int BIN, bool INST>
 __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     constexpr int KM = BinKinds<BIN>::KM;
     const uint32_t n = R.cnt->n_mat[BIN];
@@ -846,7 +851,8 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
             } else {
                 uint4 h = R.hit[id];
                 uint32_t fl;
-                Surf si = surface_at(R.scene, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
+                const uint32_t hinst = INST ? R.hit_inst[id] : PBRT_B200_NO_HIT;
+                Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
                 const pbrt_b200_prim pr = R.scene.prims[h.x];
                 // SurfaceInteraction::le, interaction.rs:344-349 + AreaLight::l, diffuse.rs:68-75
                 if ((bounces == 0 || specular_bounce) && pr.area_light >= 0) {
@@ -1005,14 +1011,16 @@ struct ShadowJob {
         R->L_eta[id] = L;
     }
 };
+template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
     ShadowJob job{&R};
-    trace_queue<true>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
+    trace_queue<true, INST>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
 }
 
 // ---------------------------------------------------------------------------
 // K7: MIS rays (estimate_direct's BSDF-sampled branch, integrator.rs:205-234)
 // ---------------------------------------------------------------------------
+template <bool INST>
 struct MisJob {
     RenderDev* R;
     PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
@@ -1030,7 +1038,7 @@ struct MisJob {
             const pbrt_b200_prim pr = R->scene.prims[r.hit.slot];
             if (pr.area_light == (int)ln) {  // Arc::ptr_eq(light, hit primitive's area light)
                 uint32_t fl;
-                Surf ls = surface_at(R->scene, r.hit.slot, r.o, r.d, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
+                Surf ls = surface_at_hit<INST>(R->scene, r.hit.inst, r.hit.slot, r.o, r.d, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
                 const pbrt_b200_light& al = R->scene.lights[ln];
                 if (al.two_sided || dot(ls.n, -r.d) > 0.0f) li = rgb3(al.L);
             }
@@ -1045,9 +1053,10 @@ struct MisJob {
         }
     }
 };
+template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
-    MisJob job{&R};
-    trace_queue<false>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
+    MisJob<INST> job{&R};
+    trace_queue<false, INST>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
 
 // ---------------------------------------------------------------------------
@@ -1404,14 +1413,14 @@ int ensure_buffers(SceneRenderState* st, uint32_t capacity) {
     RenderDev& d = rb->dev;
     std::memset(&d, 0, sizeof d);
     const size_t c = capacity;
-    // bytes per slot: ray 32, hit 16+4+1, L_eta 16, beta_st 16, pfilm 8, s_index 8, s_dim 4, pixel 4, sh_ray 32, sh_contrib 16, mis_ray 32,
+    // bytes per slot: ray 32, hit 16+4+4+1, L_eta 16, beta_st 16, pfilm 8, s_index 8, s_dim 4, pixel 4, sh_ray 32, sh_contrib 16, mis_ray 32,
     // mis_contrib 16, 6 + Q_COUNT index queues x 4
-    const size_t per_slot = 32 + 16 + 4 + 1 + 16 + 16 + 8 + 8 + 4 + 4 + 32 + 16 + 32 + 16 + 4 * (6 + Q_COUNT);
+    const size_t per_slot = 32 + 16 + 4 + 4 + 1 + 16 + 16 + 8 + 8 + 4 + 4 + 32 + 16 + 32 + 16 + 4 * (6 + Q_COUNT);
     const size_t need = per_slot * c + 256 * 40 + sizeof(Counters);
     rb->block = pool_alloc(need, &rb->block_bytes);
     if (!rb->block) { delete st->buffers; st->buffers = nullptr; return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the path state"); }
     Arena A; A.base = reinterpret_cast<char*>(rb->block); A.size = rb->block_bytes;
-    d.ray = A.take<float4>(2 * c); d.hit = A.take<uint4>(c); d.hit_b2 = A.take<float>(c); d.hit_bin = A.take<uint8_t>(c);
+    d.ray = A.take<float4>(2 * c); d.hit = A.take<uint4>(c); d.hit_b2 = A.take<float>(c); d.hit_inst = A.take<uint32_t>(c); d.hit_bin = A.take<uint8_t>(c);
     d.L_eta = A.take<float4>(c); d.beta_st = A.take<float4>(c); d.pfilm = A.take<float2>(c);
     d.s_index = A.take<unsigned long long>(c); d.s_dim = A.take<uint32_t>(c); d.pixel = A.take<uint32_t>(c);
     d.sh_ray = A.take<float4>(2 * c); d.sh_contrib = A.take<float4>(c); d.mis_ray = A.take<float4>(2 * c); d.mis_contrib = A.take<float4>(c);
@@ -1582,7 +1591,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
     int trace_per_sm = 8;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, k_trace_closest, PB_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, sc->dev.n_instances ? k_trace_closest<true> : k_trace_closest<false>, PB_TRACE_BLOCK, 0);
     const int grid_trace = sm_count * (trace_per_sm > 0 ? trace_per_sm : 1);  // persistent: exactly one resident wave
     const int grid_shade = sm_count * 8, grid_small = sm_count * 4;
 
@@ -1621,11 +1630,13 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         unsigned long long iter = 0, batch = 0;
         const unsigned long long iter_cap = (total_items / capacity + 2) * (unsigned long long)(R.max_depth + 2) + 4096;
         const int poll = 4;
+        const bool inst = sc->dev.n_instances != 0;
         bool done = false;
         while (!done) {
             for (int b = 0; b < poll; ++b) {
                 if (timing) mark();
-                k_trace_closest<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R, parity);
+                if (inst) k_trace_closest<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R, parity);
+                else k_trace_closest<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R, parity);
                 if (timing) mark();
                 if (R.sp.enabled && R.sp.lazy) {
                     k_spatial_mark<<<grid_small, 256, 0, stream>>>(R, parity);
@@ -1634,17 +1645,29 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                     launches += 3;
                 }
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
-                k_shade<Q_MISS><<<grid_small, 128, 0, stream>>>(R, parity);
-                k_shade<Q_MATTE><<<grid_shade, 128, 0, stream>>>(R, parity);
-                k_shade<Q_PLASTIC><<<grid_shade, 128, 0, stream>>>(R, parity);
-                k_shade<Q_MIRROR><<<grid_shade, 128, 0, stream>>>(R, parity);
-                k_shade<Q_GLASS><<<grid_shade, 128, 0, stream>>>(R, parity);
-                k_shade<Q_METAL><<<grid_shade, 128, 0, stream>>>(R, parity);
-                k_shade<Q_NOMAT><<<grid_small, 128, 0, stream>>>(R, parity);
+                if (inst) {
+                    k_shade<Q_MISS, true><<<grid_small, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_MATTE, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_PLASTIC, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_MIRROR, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_GLASS, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_METAL, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_NOMAT, true><<<grid_small, 128, 0, stream>>>(R, parity);
+                } else {
+                    k_shade<Q_MISS, false><<<grid_small, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_MATTE, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_PLASTIC, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_MIRROR, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_GLASS, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_METAL, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    k_shade<Q_NOMAT, false><<<grid_small, 128, 0, stream>>>(R, parity);
+                }
                 if (timing) mark();
-                k_trace_shadow<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                if (inst) k_trace_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                else k_trace_shadow<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 if (timing) mark();
-                k_trace_mis<<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                if (inst) k_trace_mis<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                else k_trace_mis<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 if (timing) mark();
                 k_finish_regen<<<grid_small, 256, 0, stream>>>(R, parity, total_items);
                 k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);

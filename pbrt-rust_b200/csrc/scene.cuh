@@ -15,7 +15,20 @@ namespace pb {
 // flags in TriRec.v1.w (as uint)
 #define PB_TRI_LAST 0x80000000u     /* last primitive of its leaf            */
 #define PB_TRI_SPHERE 0x40000000u   /* slot is a sphere, v2.w = sphere index */
+#define PB_TRI_INSTANCE 0x20000000u /* slot is a TransformedPrimitive, v2.w = instance index */
 #define PB_TRI_FLAGS_MASK 0x000000ffu /* PBRT_B200_PRIM_* of the primitive     */
+
+// TransformedPrimitive (primitive.rs:41-103) as the traversal sees it: both matrices, and where the instanced object's
+// accelerator starts in the shared fat-node / leaf-record arrays (child refs are global).
+#define PB_INST_IDENTITY 1u /* prim_to_world.is_identity(): the interaction is not transformed back (primitive.rs:75-77) */
+#define PB_INST_HAS_BOX 2u
+struct DevInstance {
+    float world_to_prim[16];
+    float prim_to_world[16];
+    uint32_t root_ref;     // fat-node index or PB_LEAF_BIT | slot (a BVH whose root is a leaf, or a one-primitive object)
+    uint32_t flags;        // PB_INST_IDENTITY | PB_INST_HAS_BOX
+    float root_box[6];     // object BVH root bounds; a one-primitive object has no accelerator (api.rs:1691) and no box test
+};
 
 struct DevScene {
     // Fat BVH2: per INTERIOR node of the reference's LinearBVHNode array, the exact f32
@@ -42,6 +55,12 @@ struct DevScene {
     const pbrt_b200_sphere* spheres;
     const pbrt_b200_material* materials;
     const pbrt_b200_light* lights;
+    const DevInstance* instances;
+    uint32_t n_instances;
+    // This struct again, resident in HBM.  Kernels get DevScene by value (constant bank); the out-of-line instance code
+    // takes this pointer instead, because the address of a kernel parameter would force a local-memory copy of the whole
+    // struct into every kernel that might call it.
+    const DevScene* self_dev;
     uint32_t n_lights;
     uint32_t n_materials;
     // Scene::new preprocessing (scene.rs:32-52, distant.rs:53-60)

@@ -146,6 +146,33 @@ PB_D Surf surface_at(const DevScene& s, uint32_t slot, f3 ray_o, f3 ray_d, float
     return triangle_surface(s, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), fl, __float_as_uint(v2.w), ray_d, b0, b1, b2, true);
 }
 
+// Hit inside an instanced object: TransformedPrimitive::intersect (primitive.rs:58-80) -- the object's interaction is
+// computed with the ray in object space, then Transform::transform_surface_interaction (transform.rs:607-636) takes it
+// to world space unless prim_to_world is the identity.
+static __device__ __noinline__ Surf surface_at_instance(const DevScene* sp, uint32_t inst, uint32_t slot, f3 ray_o, f3 ray_d, float t, float b0, float b1, float b2,
+                                                        uint32_t* flags_out) {
+    const DevScene& s = *sp;
+    const DevInstance& in = s.instances[inst];
+    f3 o2, d2;
+    float tm2;
+    xf_ray(in.world_to_prim, ray_o, ray_d, PB_INF, &o2, &d2, &tm2);
+    Surf si = surface_at(s, slot, o2, d2, t, b0, b1, b2, flags_out);
+    if (in.flags & PB_INST_IDENTITY) return si;
+    Surf r;
+    r.p = xf_point_abs_err(in.prim_to_world, si.p, si.p_error, &r.p_error);
+    r.n = normalize(xf_normal(in.world_to_prim, si.n));
+    r.wo = normalize(xf_vector(in.prim_to_world, si.wo));
+    r.sh_n = normalize(xf_normal(in.world_to_prim, si.sh_n));
+    r.sh_dpdu = xf_vector(in.prim_to_world, si.sh_dpdu);
+    r.sh_n = face_forward(r.sh_n, r.n);
+    return r;
+}
+template <bool INST>
+PB_D Surf surface_at_hit(const DevScene& s, uint32_t inst, uint32_t slot, f3 ray_o, f3 ray_d, float t, float b0, float b1, float b2, uint32_t* flags_out) {
+    if (INST && inst != PBRT_B200_NO_HIT) return surface_at_instance(s.self_dev, inst, slot, ray_o, ray_d, t, b0, b1, b2, flags_out);
+    return surface_at(s, slot, ray_o, ray_d, t, b0, b1, b2, flags_out);
+}
+
 // ---- BxDF local-frame helpers, core/reflection.rs:78-176
 PB_D float cos2_theta(f3 w) { return w.z * w.z; }
 PB_D float sin2_theta(f3 w) { return fmaxf(1.0f - cos2_theta(w), 0.0f); }
@@ -202,7 +229,9 @@ PB_D float2 concentric_disk(float2 u) {  // :154-176
     float th, r;
     if (fabsf(ox) > fabsf(oy)) { r = ox; th = PB_PI_OVER4 * (oy / ox); }
     else { r = oy; th = PB_PI_OVER2 - PB_PI_OVER4 * (ox / oy); }
-    return make_float2(cosf(th) * r, sinf(th) * r);
+    float sn, cs;
+    sincosf(th, &sn, &cs);  // one argument reduction for both (th is in [-pi/4, 3pi/4])
+    return make_float2(cs * r, sn * r);
 }
 PB_D f3 cosine_hemisphere(float2 u) {  // :188-193
     float2 d = concentric_disk(u);

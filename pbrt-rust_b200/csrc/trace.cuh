@@ -24,6 +24,7 @@ namespace pb {
 struct RayHit {
     uint32_t slot;  // BVH slot of the hit primitive or PBRT_B200_NO_HIT
     float t, b0, b1, b2;
+    uint32_t inst;  // instance the hit went through (TransformedPrimitive) or PBRT_B200_NO_HIT
 };
 
 // --- Triangle::intersect, triangle.rs:136-233 (+ :236-263 rejection for closest hits)
@@ -246,9 +247,11 @@ struct TravRay {
 #endif
 };
 
-PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) {
+// root_ref / root_box: the accelerator to walk (the scene's aggregate or an instanced object's BVH); root_box == nullptr
+// for a one-primitive object, which the reference intersects directly (no accelerator, no bounds test)
+PB_D void trav_init_at(TravRay& r, f3 o, f3 d, float t_max, uint32_t root_ref, const float* rb) {
     r.o = o; r.d = d; r.t_max = t_max;
-    r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.b0 = r.hit.b1 = r.hit.b2 = 0.0f;
+    r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.b0 = r.hit.b1 = r.hit.b2 = 0.0f; r.hit.inst = PBRT_B200_NO_HIT;
     r.found = false; r.sp = 0; r.cur = PB_DONE;
     r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     r.ngx = r.inv.x < 0.0f; r.ngy = r.inv.y < 0.0f; r.ngz = r.inv.z < 0.0f;
@@ -264,13 +267,30 @@ PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) {
     r.ky = (r.kx + 1 == 3) ? 0 : r.kx + 1;
     const float dpx = comp(d, r.kx), dpy = comp(d, r.ky), dpz = comp(d, r.kz);
     r.Sx = -dpx / dpz; r.Sy = -dpy / dpz; r.Sz = 1.0f / dpz;
-    if (s.root_ref == PB_REF_NONE) return;
+    if (root_ref == PB_REF_NONE) return;
+    if (rb == nullptr) { r.cur = root_ref; return; }
     float tmin;
-    const float* rb = s.root_box;
     bool ok = slab_test(r.ngx ? rb[3] : rb[0], r.ngy ? rb[4] : rb[1], r.ngz ? rb[5] : rb[2], r.ngx ? rb[0] : rb[3], r.ngy ? rb[1] : rb[4],
                         r.ngz ? rb[2] : rb[5], o, r.inv, &tmin);
-    if (ok && tmin < t_max) r.cur = s.root_ref;
+    if (ok && tmin < t_max) r.cur = root_ref;
 }
+PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) { trav_init_at(r, o, d, t_max, s.root_ref, s.root_box); }
+
+// Transform::transform_ray, core/transform.rs:543-577: origin nudged along d by its transform error, t_max -= dt
+PB_D void xf_ray(const float* M, f3 o, f3 d, float t_max, f3* o_out, f3* d_out, float* t_max_out) {
+    f3 oerr;
+    f3 o2 = xf_point_err(M, o, &oerr);
+    f3 d2 = xf_vector(M, d);
+    float l2 = len2(d2);
+    if (l2 > 0.0f) {
+        float dt = dot(vabs(d2), oerr) / l2;
+        o2 = o2 + d2 * dt;
+        t_max -= dt;
+    }
+    *o_out = o2; *d_out = d2; *t_max_out = t_max;
+}
+
+template <bool ANY> static __device__ __noinline__ bool instance_test(const DevScene* sp, uint32_t inst, f3 o, f3 d, float t_max, RayHit* hit);
 
 // pop: the reference tests the popped node's box against the *current* t_max
 #define PB_TRAV_POP(r, stack)                                           \
@@ -285,7 +305,9 @@ PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) {
 
 // Runs the ray until it finishes, or (when `yield_below` > 0) until fewer than `yield_below`
 // lanes of the warp are still traversing, so that the caller can refill idle lanes.
-template <bool ANY, bool EXACT_NAN>
+// TOP: walking the scene's aggregate (leaf slots may be TransformedPrimitives); false inside an instanced object, where
+// ObjectInstance cannot appear (api.rs:1674-1677) -- which also keeps instance_test from recursing.
+template <bool ANY, bool EXACT_NAN, bool TOP>
 PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
     while (r.cur != PB_DONE) {
         // ---- interior nodes
@@ -345,9 +367,17 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
                 fl = __float_as_uint(v1.w);
                 float t, b0, b1, b2;
                 bool h;
-                if (fl & PB_TRI_SPHERE) {
-                    h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
-                    b0 = b1 = b2 = 0.0f;
+                uint32_t hslot = slot, hinst = PBRT_B200_NO_HIT;
+                if (fl & (PB_TRI_SPHERE | PB_TRI_INSTANCE)) {
+                    if (TOP && (fl & PB_TRI_INSTANCE)) {  // TransformedPrimitive::intersect / intersect_p, primitive.rs:58-89
+                        RayHit ih;
+                        hinst = __float_as_uint(v2.w);
+                        h = instance_test<ANY>(s.self_dev, hinst, r.o, r.d, r.t_max, &ih);
+                        t = ih.t; b0 = ih.b0; b1 = ih.b1; b2 = ih.b2; hslot = ih.slot;
+                    } else {
+                        h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
+                        b0 = b1 = b2 = 0.0f;
+                    }
                 } else {
                     f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
                     h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
@@ -359,9 +389,9 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
                 }
                 if (h) {
                     r.found = true;
-                    r.hit.slot = slot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2;
+                    r.hit.slot = hslot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2; r.hit.inst = hinst;
                     if (ANY) { r.cur = PB_DONE; r.sp = 0; break; }
-                    r.t_max = t;  // primitive.rs:137
+                    r.t_max = t;  // primitive.rs:137 (for an instance: r.t_max = ray.t_max, primitive.rs:72)
                 }
                 ++slot;
             } while (!(fl & PB_TRI_LAST));
@@ -372,19 +402,39 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
     }
 }
 
-template <bool ANY>
+// INST: the scene contains TransformedPrimitives.  Scenes without instancing run kernels compiled with INST = false, which
+// contain no trace of the instance path (measured on S3: the mere presence of the out-of-line call in the leaf loop costs 20%).
+template <bool ANY, bool INST>
 PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min = 0) {
-    if (r.nan_possible) trav_run_impl<ANY, true>(s, r, stack, yield_below, interior_min);
-    else trav_run_impl<ANY, false>(s, r, stack, yield_below, interior_min);
+    if (r.nan_possible) trav_run_impl<ANY, true, INST>(s, r, stack, yield_below, interior_min);
+    else trav_run_impl<ANY, false, INST>(s, r, stack, yield_below, interior_min);
+}
+
+// The instanced object's own accelerator, walked to completion with the ray taken into the object's space.  Out of line
+// (own traversal stack in its frame): scenes without instancing only pay the flag test above.
+template <bool ANY>
+static __device__ __noinline__ bool instance_test(const DevScene* sp, uint32_t inst, f3 o, f3 d, float t_max, RayHit* hit) {
+    const DevScene& s = *sp;
+    const DevInstance& in = s.instances[inst];
+    f3 o2, d2;
+    float tm2;
+    xf_ray(in.world_to_prim, o, d, t_max, &o2, &d2, &tm2);
+    uint2 stack[PB_STACK_DEPTH];
+    TravRay r;
+    trav_init_at(r, o2, d2, tm2, in.root_ref, (in.flags & PB_INST_HAS_BOX) ? in.root_box : nullptr);
+    if (r.nan_possible) trav_run_impl<ANY, true, false>(s, r, stack, 0, 0);
+    else trav_run_impl<ANY, false, false>(s, r, stack, 0, 0);
+    *hit = r.hit;
+    return r.found;
 }
 
 // Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray, run to completion.
-template <bool ANY>
+template <bool ANY, bool INST = false>
 PB_D bool traverse(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
     uint2 stack[PB_STACK_DEPTH];
     TravRay r;
     trav_init(s, r, o, d, t_max);
-    trav_run<ANY>(s, r, stack, 0);
+    trav_run<ANY, INST>(s, r, stack, 0);
     *hit = r.hit;
     return r.found;
 }
@@ -392,7 +442,7 @@ PB_D bool traverse(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
 // Variant kept for A/B measurements: single loop with leaf / interior / pop branches ("if-if").
 template <bool ANY>
 PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
-    hit->slot = PBRT_B200_NO_HIT;
+    hit->slot = PBRT_B200_NO_HIT; hit->inst = PBRT_B200_NO_HIT;
     hit->t = t_max;
     if (s.root_ref == PB_REF_NONE) return false;
     const f3 inv(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -492,7 +542,7 @@ PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit)
 #define PB_INTERIOR_MIN 16
 #endif
 struct TraceTune { int refill_below; int chunk; int interior_min; };
-template <bool ANY, typename Job>
+template <bool ANY, bool INST, typename Job>
 PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_counter, TraceTune tune = TraceTune{PB_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN}) {
     uint2 stack[PB_STACK_DEPTH];
     TravRay r;
@@ -523,14 +573,14 @@ PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_c
                 ray_idx = pool_next + rank;
                 f3 o, d; float t_max = 0.0f;
                 if (job.load(ray_idx, &o, &d, &t_max)) trav_init(s, r, o, d, t_max);
-                else { r.cur = PB_DONE; r.sp = 0; r.found = false; r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; }
+                else { r.cur = PB_DONE; r.sp = 0; r.found = false; r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.inst = PBRT_B200_NO_HIT; }
             }
             unsigned took = __ballot_sync(0xffffffffu, take);
             pool_next += __popc(took);
             need &= ~took;
         }
         if (__all_sync(0xffffffffu, ray_idx == 0xffffffffu)) break;
-        trav_run<ANY>(s, r, stack, exhausted ? 0 : tune.refill_below, tune.interior_min);
+        trav_run<ANY, INST>(s, r, stack, exhausted ? 0 : tune.refill_below, tune.interior_min);
     }
 }
 

@@ -47,7 +47,10 @@ HIT_DTYPE = np.dtype([("prim", "<u4"), ("t", "<f4"), ("b0", "<f4"), ("b1", "<f4"
 assert NODE_DTYPE.itemsize == 32 and PRIM_DTYPE.itemsize == 24 and SPHERE_DTYPE.itemsize == 144
 assert MATERIAL_DTYPE.itemsize == 48 and LIGHT_DTYPE.itemsize == 132 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16
 
-SHAPE_TRIANGLE, SHAPE_SPHERE = 0, 1
+SHAPE_TRIANGLE, SHAPE_SPHERE, SHAPE_INSTANCE = 0, 1, 2
+OBJECT_DTYPE = np.dtype([("node_offset", "<u8"), ("n_nodes", "<u8"), ("prim_offset", "<u8"), ("n_prims", "<u8")])
+INSTANCE_DTYPE = np.dtype([("prim_to_world", "<f4", 16), ("world_to_prim", "<f4", 16), ("object", "<u4"), ("pad", "<u4", 3)])
+assert OBJECT_DTYPE.itemsize == 32 and INSTANCE_DTYPE.itemsize == 144
 PRIM_REVERSE_ORIENTATION, PRIM_SWAPS_HANDEDNESS, PRIM_HAS_N, PRIM_HAS_S, PRIM_HAS_UV = 1, 2, 4, 8, 16
 MAT_MATTE, MAT_PLASTIC, MAT_MIRROR, MAT_GLASS, MAT_METAL = range(5)
 LIGHT_POINT, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_DIFFUSE, LIGHT_INFINITE = range(5)
@@ -64,7 +67,10 @@ class SceneDesc(C.Structure):
                 ("tri_indices", C.c_void_p), ("n_triangles", C.c_uint64),
                 ("spheres", C.c_void_p), ("n_spheres", C.c_uint64),
                 ("materials", C.c_void_p), ("n_materials", C.c_uint64),
-                ("lights", C.c_void_p), ("n_lights", C.c_uint64)]
+                ("lights", C.c_void_p), ("n_lights", C.c_uint64),
+                ("objects", C.c_void_p), ("n_objects", C.c_uint64),
+                ("instances", C.c_void_p), ("n_instances", C.c_uint64),
+                ("n_top_nodes", C.c_uint64), ("n_top_prims", C.c_uint64)]
 
 
 class CameraDesc(C.Structure):
@@ -306,6 +312,15 @@ class Transform:
         return np.stack([x * mi[0, 0] + y * mi[1, 0] + z * mi[2, 0], x * mi[0, 1] + y * mi[1, 1] + z * mi[2, 1],
                          x * mi[0, 2] + y * mi[1, 2] + z * mi[2, 2]], axis=1).astype(f32)
 
+    def bounds(self, b):  # transform_bounds, transform.rs:593-605: union of the 8 transformed corners
+        b = np.asarray(b, f32)
+        corners = np.array([[b[0 if i & 1 == 0 else 3], b[1 if i & 2 == 0 else 4], b[2 if i & 4 == 0 else 5]] for i in range(8)], f32)
+        w = self.points(corners)
+        return np.concatenate([w.min(0), w.max(0)]).astype(f32)
+
+    def is_identity(self):  # transform.rs:229-238
+        return bool(np.array_equal(self.m, np.eye(4, dtype=f32)))
+
     def swaps_handedness(self):  # transform.rs:638-644
         m = self.m
         det = (m[0, 0] * (m[1, 1] * m[2, 2] - m[1, 2] * m[2, 1]) - m[0, 1] * (m[1, 0] * m[2, 2] - m[1, 2] * m[2, 0]) +
@@ -344,10 +359,13 @@ class FlatScene:
         self.spheres = np.zeros(0, SPHERE_DTYPE)
         self.materials = np.zeros(0, MATERIAL_DTYPE)
         self.lights = np.zeros(0, LIGHT_DTYPE)
+        self.objects = np.zeros(0, OBJECT_DTYPE)
+        self.instances = np.zeros(0, INSTANCE_DTYPE)
+        self.n_top_nodes = self.n_top_prims = 0  # 0 = all of nodes / prims (no object instancing)
 
     def desc(self):
         d = SceneDesc()
-        d.abi_version = 1
+        d.abi_version = 2
         d.nodes, d.n_nodes = _ptr(self.nodes), len(self.nodes)
         d.prims, d.n_prims = _ptr(self.prims), len(self.prims)
         d.vertex_p, d.n_vertices = _ptr(self.vertex_p), len(self.vertex_p)
@@ -356,6 +374,9 @@ class FlatScene:
         d.spheres, d.n_spheres = _ptr(self.spheres), len(self.spheres)
         d.materials, d.n_materials = _ptr(self.materials), len(self.materials)
         d.lights, d.n_lights = _ptr(self.lights), len(self.lights)
+        d.objects, d.n_objects = _ptr(self.objects), len(self.objects)
+        d.instances, d.n_instances = _ptr(self.instances), len(self.instances)
+        d.n_top_nodes, d.n_top_prims = self.n_top_nodes, self.n_top_prims
         return d
 
     @property
@@ -394,6 +415,37 @@ class SceneBuilder:
         self._spheres = []
         self._lights = []
         self.any_n = self.any_s = self.any_uv = False
+        self._objects, self._instances, self._cur_object = {}, [], None
+
+    # --- object instancing (api.rs:1593-1713) ---------------------------------
+    def object_begin(self, name):
+        self.attribute_begin()
+        if self._cur_object is not None:
+            raise B200Error("ObjectBegin called inside of instance definition")
+        self._objects[name] = {"prims": [], "bounds": []}
+        self._cur_object = name
+        self._top = (self._prims, self._bounds)
+        self._prims, self._bounds = self._objects[name]["prims"], self._objects[name]["bounds"]
+
+    def object_end(self):
+        if self._cur_object is None:
+            raise B200Error("ObjectEnd called outside of instance definition")
+        self._prims, self._bounds = self._top
+        self._cur_object = None
+        self.attribute_end()
+
+    def object_instance(self, name):
+        if self._cur_object is not None:
+            raise B200Error("ObjectInstance can't be called inside instance definition")
+        if name not in self._objects:
+            raise B200Error(f'Unable to find instance named "{name}"')
+        if not self._objects[name]["prims"]:
+            return  # api.rs:1684-1686: empty instance
+        row = np.zeros(1, PRIM_DTYPE)
+        row["shape_kind"], row["shape_index"], row["material"], row["area_light"] = SHAPE_INSTANCE, len(self._instances), -1, -1
+        self._instances.append((name, self.ctm))
+        self._prims.append(row)
+        self._bounds.append(None)  # TransformedPrimitive::world_bound needs the object's BVH: filled in by world_end
 
     # --- graphics state ---------------------------------------------------
     def attribute_begin(self):
@@ -548,6 +600,8 @@ class SceneBuilder:
         rows["material"] = self._material_id()
         rows["area_light"] = -1
         rows["flags"] = flags
+        if self._area_light is not None and self._cur_object is not None:
+            raise B200Error("Area lights not supported with object instancing (api.rs:1573-1575)")
         if self._area_light is not None:  # api.rs:1531-1546: one DiffuseAreaLight per shape
             L, two = self._area_light
             lights = np.zeros(nt, LIGHT_DTYPE)
@@ -596,14 +650,57 @@ class SceneBuilder:
             fs.materials = np.array(self._materials, MATERIAL_DTYPE)
         if self._lights:
             fs.lights = np.array(self._lights, LIGHT_DTYPE)
+        if self._cur_object is not None:
+            raise B200Error("WorldEnd inside an object definition")
+        build = builder or bvh_build
+        # ObjectInstance (api.rs:1663-1713): an object with more than one primitive gets its own accelerator, built with the
+        # scene's accelerator parameters; TransformedPrimitive::world_bound = prim_to_world.motion_bounds(object bound)
+        used, obj_tables, next_ci = {}, [], nprim
+        for name, _ in self._instances:
+            if name in used:
+                continue
+            o = self._objects[name]
+            oprims = np.concatenate(o["prims"])
+            obounds = np.ascontiguousarray(np.concatenate(o["bounds"]), f32)
+            oprims["creation_index"] = np.arange(next_ci, next_ci + len(oprims), dtype=np.uint32)
+            next_ci += len(oprims)
+            if len(oprims) > 1:
+                onodes, oorder = build(obounds, max_prims, split_method)
+                oprims = oprims[oorder]
+                wb = onodes[0]["bounds"].copy()
+            else:
+                onodes, wb = np.zeros(0, NODE_DTYPE), obounds[0].copy()
+            used[name] = len(obj_tables)
+            obj_tables.append((onodes, np.ascontiguousarray(oprims), wb))
         if nprim:
+            for k, bnd in enumerate(self._bounds):
+                if bnd is None:
+                    inst = int(self._prims[k]["shape_index"][0])
+                    name, ctm = self._instances[inst]
+                    self._bounds[k] = ctm.bounds(obj_tables[used[name]][2])[None, :]
             prims = np.concatenate(self._prims)
             prims["creation_index"] = np.arange(nprim, dtype=np.uint32)
             bounds = np.ascontiguousarray(np.concatenate(self._bounds), f32)
-            nodes, ordered = (builder or bvh_build)(bounds, max_prims, split_method)
+            nodes, ordered = build(bounds, max_prims, split_method)
             fs.nodes = nodes
             fs.prims = np.ascontiguousarray(prims[ordered])
             fs.prim_bounds = bounds
+        if obj_tables:
+            fs.n_top_nodes, fs.n_top_prims = len(fs.nodes), len(fs.prims)
+            objs = np.zeros(len(obj_tables), OBJECT_DTYPE)
+            all_nodes, all_prims = [fs.nodes], [fs.prims]
+            noff, poff = len(fs.nodes), len(fs.prims)
+            for k, (onodes, oprims, _) in enumerate(obj_tables):
+                objs[k] = (noff, len(onodes), poff, len(oprims))
+                all_nodes.append(onodes); all_prims.append(oprims)
+                noff += len(onodes); poff += len(oprims)
+            fs.nodes = np.ascontiguousarray(np.concatenate(all_nodes))
+            fs.prims = np.ascontiguousarray(np.concatenate(all_prims))
+            fs.objects = objs
+            inst = np.zeros(len(self._instances), INSTANCE_DTYPE)
+            for k, (name, ctm) in enumerate(self._instances):
+                inst[k]["prim_to_world"], inst[k]["world_to_prim"], inst[k]["object"] = ctm.m.reshape(-1), ctm.m_inv.reshape(-1), used[name]
+            fs.instances = inst
         return fs
 
 

@@ -374,6 +374,96 @@ def small_mixed_scene(n=24, seed=5):
     return SceneSetup("mixed-small", flat, make, "all hot-path materials/lights/shapes at test size")
 
 
+def _plant_mesh(n_blades=10, seg=6, seed=17):
+    """A small procedural 'plant': n_blades curved two-sided blades of 2*seg triangles each, fanned around the z axis."""
+    rng = PCG32(seed)
+    u = rng.floats(4 * n_blades)
+    P, I = [], []
+    for b in range(n_blades):
+        ang = 2 * math.pi * (b + 0.5 * float(u[4 * b])) / n_blades
+        lean, height, width = 0.3 + 0.5 * float(u[4 * b + 1]), 0.7 + 0.6 * float(u[4 * b + 2]), 0.05 + 0.05 * float(u[4 * b + 3])
+        ca, sa = math.cos(ang), math.sin(ang)
+        base = len(P)
+        for k in range(seg + 1):
+            t = k / seg
+            r, z, w = lean * t * t, height * t, width * (1 - 0.9 * t)
+            cx, cy = r * ca, r * sa
+            P.append((cx - w * sa, cy + w * ca, z)); P.append((cx + w * sa, cy - w * ca, z))
+        for k in range(seg):
+            a = base + 2 * k
+            I.append((a, a + 1, a + 3)); I.append((a, a + 3, a + 2))
+    return np.array(P, f32), np.array(I, np.uint32)
+
+
+def instanced_scene(n_side=6, baked=False, seed=99):
+    """Object instancing at test size (config C4's structure): a 'plant' object (its own BVH), a one-sphere object (a
+    single primitive: no accelerator, api.rs:1691) and a one-triangle object, instanced n_side^2 times with translations,
+    rotations, non-uniform and mirroring scales over a ground quad.  `baked=True` builds the SAME geometry as ordinary
+    world-space meshes instead of instances (for cross-checking the instancing code against the plain path)."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.0, -7.5, 4.0), (0, 0, 0.4), (0, 0, 1))
+    Pp, Ip = _plant_mesh()
+    Ptri, Itri = np.array([(-0.3, 0, 0), (0.3, 0, 0), (0, 0.1, 0.8)], f32), np.array([(0, 1, 2)], np.uint32)
+    mats = {"plant": ("plastic", dict(Kd=(0.15, 0.45, 0.12), Ks=0.2, roughness=0.2)), "ball": ("metal", dict(roughness=0.05)),
+            "shard": ("matte", dict(Kd=(0.7, 0.3, 0.2)))}
+
+    def define(name):
+        m, kw = mats[name]
+        b.material(m, **kw)
+        if name == "plant":
+            b.shape("trianglemesh", P=Pp, indices=Ip)
+        elif name == "ball":
+            b.translate(0, 0, 0.35)
+            b.shape("sphere", radius=0.35)
+        else:
+            b.shape("trianglemesh", P=Ptri, indices=Itri)
+
+    if not baked:
+        for name in mats:
+            b.object_begin(name)
+            define(name)
+            b.object_end()
+    b.material("matte", Kd=(0.5, 0.5, 0.45))
+    Pq, Iq = quad((-12, -12, 0), (12, -12, 0), (12, 12, 0), (-12, 12, 0))
+    b.shape("trianglemesh", P=Pq, indices=Iq)
+    rng = PCG32(seed)
+    u = rng.floats(6 * n_side * n_side)
+    names = list(mats)
+    for j in range(n_side):
+        for i in range(n_side):
+            k = 6 * (j * n_side + i)
+            b.attribute_begin()
+            b.translate(-4.5 + 9.0 * (i + 0.5 + 0.6 * (float(u[k]) - 0.5)) / n_side, -3.0 + 9.0 * (j + 0.5 + 0.6 * (float(u[k + 1]) - 0.5)) / n_side, 0.0)
+            b.rotate(360.0 * float(u[k + 2]), 0, 0, 1)
+            sx = 0.6 + 0.9 * float(u[k + 3])
+            b.scale(sx, sx * (1.0 if (i + j) % 3 else 1.4), (0.7 + 0.8 * float(u[k + 4])) * (-1.0 if (i * 7 + j) % 5 == 0 else 1.0))
+            if (i * 7 + j) % 5 == 0:
+                b.translate(0, 0, -1.2)  # mirrored in z: lift it back above the ground
+            name = names[(i + 2 * j) % 3] if (i + j) % 4 else "plant"
+            if baked:
+                define(name)
+            else:
+                b.object_instance(name)
+            b.attribute_end()
+    b.attribute_begin()
+    b.area_light_source("diffuse", L=(30, 30, 27))
+    Pl, Il = quad((-1.5, -1.5, 6.0), (-1.5, 1.5, 6.0), (1.5, 1.5, 6.0), (1.5, -1.5, 6.0))
+    b.shape("trianglemesh", P=Pl, indices=Il)
+    b.attribute_end()
+    b.attribute_begin()
+    b.translate(4.0, -4.0, 3.0)
+    b.light_source("point", I=(10, 10, 12))
+    b.attribute_end()
+    flat = b.world_end()
+
+    def make(spp_=16, res=(128, 96), maxdepth_=5, sampler_="sobol", strategy="power", filt="box"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=50.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    return SceneSetup("instanced-small", flat, make, f"{n_side * n_side} object instances (plant BVH / single sphere / single triangle) on a ground quad")
+
+
 def many_lights_scene(grid=6, n_quads=6, seed=99):
     """Room lit by many small lights (a test-sized stand-in for config C4's light population): grid x grid point lights
     under the ceiling, a few spot lights and small quad area lights (2 triangle lights each).  With this many lights of
