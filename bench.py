@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=16, help="camera samples per pixel per step and per GPU")
-    ap.add_argument("--scene", default="s3", choices=["s3", "cornell", "spheres", "s3small"])
+    ap.add_argument("--scene", default="s3", choices=["s3", "cornell", "spheres", "s3small", "s4", "s5"])
     ap.add_argument("--paths-in-flight", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -54,6 +54,10 @@ def make_setup(pkg, name):
         return S.displaced_sphere_scene(), dict(), "S3: 1,048,580-triangle displaced sphere, SAH BVH (maxnodeprims 4), plastic+metal, quad area light + point light, 1920x1080, Sobol, maxdepth 5, power light sampling"
     if name == "s3small":
         return S.displaced_sphere_scene(256, 128), dict(res=(480, 270)), "S3-small (65k triangles, 480x270) -- smoke/profiling only"
+    if name == "s4":
+        return S.foliage_field_scene(), dict(), "S4: 2000 instances x 10,000-triangle plant (20M instanced triangles), 9800 point + 200 triangle area lights, power light sampling, 3840x2160, Sobol, maxdepth 5"
+    if name == "s5":
+        return S.glass_knot_scene(nu=4096, nv=640), dict(), "S5: 5,242,884-triangle glass torus-knot mesh, maxdepth 32, Russian roulette, 1024x1024, Sobol"
     if name == "cornell":
         return S.cornell_scene(), dict(), "S2: Cornell box 1024x1024, maxdepth 8, gaussian filter"
     return S.spheres_scene(), dict(), "S1: two spheres 400x400, maxdepth 5"

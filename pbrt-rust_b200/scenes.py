@@ -464,6 +464,68 @@ def instanced_scene(n_side=6, baked=False, seed=99):
     return SceneSetup("instanced-small", flat, make, f"{n_side * n_side} object instances (plant BVH / single sphere / single triangle) on a ground quad")
 
 
+def foliage_field_scene(n_instances=2000, n_blades=250, seg=20, n_point=9800, n_quads=100, field=100.0, xres=3840, yres=2160, spp=64, maxdepth=5, sampler="sobol",
+                        seed=99):
+    """S4 / config C4: `n_instances` instances (PCG32 placement on a field x field area, random yaw and
+    scale) of ONE procedural plant of 2 * n_blades * seg triangles (default 10 000 => 20 M instanced triangles), lit by
+    `n_point` point lights on a jittered grid plus `n_quads` small quad area lights (2 triangle lights each), power light
+    sampling.  Instanced geometry is stored once (~1 MB); the top-level BVH holds the instances, the ground and the lights."""
+    b = H.SceneBuilder()
+    half = 0.5 * field
+    cam_w2c = H.Transform.look_at((0.0, -0.62 * field, 0.16 * field), (0, -0.1 * field, 0.0), (0, 0, 1))
+    Pp, Ip = _plant_mesh(n_blades=n_blades, seg=seg, seed=17)
+    b.object_begin("plant")
+    b.material("plastic", Kd=(0.12, 0.4, 0.1), Ks=(0.15, 0.15, 0.15), roughness=0.2)
+    b.shape("trianglemesh", P=Pp, indices=Ip)
+    b.object_end()
+    b.material("matte", Kd=(0.35, 0.3, 0.22))
+    Pq, Iq = quad((-half * 1.5, -half * 1.5, 0), (half * 1.5, -half * 1.5, 0), (half * 1.5, half * 1.5, 0), (-half * 1.5, half * 1.5, 0))
+    b.shape("trianglemesh", P=Pq, indices=Iq)
+    rng = PCG32(seed)
+    u = rng.floats(4 * n_instances + 7 * n_point + 8 * n_quads)
+    k = 0
+    side = max(1, int(math.ceil(math.sqrt(n_instances))))
+    for i in range(n_instances):
+        gx, gy = i % side, i // side
+        b.attribute_begin()
+        b.translate(-half + field * (gx + float(u[k])) / side, -half + field * (gy + float(u[k + 1])) / side, 0.0)
+        b.rotate(360.0 * float(u[k + 2]), 0, 0, 1)
+        sc = (0.8 + 1.2 * float(u[k + 3])) * field / side * 0.9
+        b.scale(sc, sc, sc)
+        b.object_instance("plant")
+        b.attribute_end()
+        k += 4
+    lside = max(1, int(math.ceil(math.sqrt(max(n_point, 1)))))
+    for i in range(n_point):
+        gx, gy = i % lside, i // lside
+        b.attribute_begin()
+        b.translate(-half + field * (gx + float(u[k])) / lside, -half + field * (gy + float(u[k + 1])) / lside, field * (0.05 + 0.05 * float(u[k + 2])))
+        c = field * field / max(n_point, 1) * (0.05 + 0.4 * float(u[k + 3]) ** 2)
+        b.light_source("point", I=(c * (0.7 + 0.3 * float(u[k + 4])), c * (0.7 + 0.3 * float(u[k + 5])), c * (0.6 + 0.4 * float(u[k + 6]))))
+        b.attribute_end()
+        k += 7
+    for i in range(n_quads):
+        cx, cy, cz = -half + field * float(u[k]), -half + field * float(u[k + 1]), field * (0.06 + 0.04 * float(u[k + 2]))
+        hs = field * (0.004 + 0.006 * float(u[k + 3]))
+        b.attribute_begin()
+        e = field * field / max(n_quads, 1) * 0.02 / (hs * hs)
+        b.area_light_source("diffuse", L=(e * (0.7 + 0.3 * float(u[k + 4])), e * (0.7 + 0.3 * float(u[k + 5])), e * (0.6 + 0.4 * float(u[k + 6]))))
+        Pl, Il = quad((cx - hs, cy - hs, cz), (cx - hs, cy + hs, cz), (cx + hs, cy + hs, cz), (cx + hs, cy - hs, cz))
+        b.shape("trianglemesh", P=Pl, indices=Il)
+        b.attribute_end()
+        k += 8
+    flat = b.world_end()
+
+    def make(spp_=spp, res=(xres, yres), maxdepth_=maxdepth, sampler_=sampler, strategy="power", filt="box"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=45.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    ntri = 2 * n_blades * seg
+    return SceneSetup("S4-foliage", flat, make, f"{n_instances} instances x {ntri} triangles = {n_instances * ntri} instanced triangles, "
+                      f"{n_point} point + {2 * n_quads} triangle area lights, power light sampling")
+
+
 def many_lights_scene(grid=6, n_quads=6, seed=99):
     """Room lit by many small lights (a test-sized stand-in for config C4's light population): grid x grid point lights
     under the ceiling, a few spot lights and small quad area lights (2 triangle lights each).  With this many lights of

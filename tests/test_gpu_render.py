@@ -26,6 +26,9 @@ CASES = {
     "mixed-depth1": (lambda S: S.small_mixed_scene(), dict(spp_=4, res=(96, 64), maxdepth_=1)),
     "mixed-depth0": (lambda S: S.small_mixed_scene(), dict(spp_=4, res=(96, 64), maxdepth_=0)),
     "sphere16k-normals": (lambda S: S.displaced_sphere_scene(128, 64), dict(spp_=8, res=(160, 90))),
+    # reduced-size versions of BASELINE.json configs[3] and configs[4]
+    "s4-foliage-small": (lambda S: S.foliage_field_scene(n_instances=100, n_blades=24, seg=6, n_point=180, n_quads=10, field=24.0), dict(spp_=8, res=(160, 90))),
+    "s5-glass-knot-small-depth32": (lambda S: S.glass_knot_scene(nu=96, nv=24), dict(spp_=16, res=(96, 96))),
 }
 
 
