@@ -98,6 +98,28 @@ struct SpatialDev {
     const float* halton;    // [128][5] radical_inverse(0..4, i)
 };
 
+// ZeroTwoSequenceSampler (src/samplers/zerotwosequence.rs:32-105 on the PixelSampler machinery, src/core/sampler.rs:185-253).
+// The reference clones ONE sampler per 16x16 tile (seed = tile number, integrator.rs:302-303) and threads its PCG32 through
+// every start_pixel() and every get_1d()/get_2d() beyond the precomputed dimensions of every path of the tile, in pixel /
+// sample / bounce order: the random numbers a path sees depend on how many draws every earlier path of its tile made.  That
+// stream cannot be reproduced with two paths of a tile in flight, so this sampler runs the wavefront "tile-serial": one
+// path slot per tile, all tiles in parallel (8160 tiles at 1080p), each slot walking its tile's pixels and samples in
+// the reference's order with the tile's generator state and sample tables in HBM.
+struct ZtTile {
+    unsigned long long state, inc;    // RNG (core/rng.rs:12-22)
+    uint32_t pixel_idx, sample_idx;   // position in the tile's pixel loop (x fastest); current_pixel_sample_index
+    uint32_t cur1d, cur2d;            // current_1d_dimension / current_2d_dimension
+    int x0, y0;                       // tile bounds clipped to the sample bounds (integrator.rs:305-310)
+    uint32_t w, npix;
+};
+struct ZtDev {
+    ZtTile* tiles;
+    float* s1d;      // [tile][dim][spp]   samples_1d
+    float2* s2d;     // [tile][dim][spp]   samples_2d
+    uint32_t spp;    // rounded up to a power of two (zerotwosequence.rs:36-40)
+    uint32_t ndims;  // n_sampled_dimensions
+};
+
 struct RenderDev {
     DevScene scene;
     pbrt_b200_camera camera;
@@ -118,6 +140,7 @@ struct RenderDev {
     float ld_func_int;
     uint32_t n_lights;
     SpatialDev sp;
+    ZtDev zt;
     const InfDistrib* inf_distrib;     // indexed by light
     const uint32_t* infinite_lights;   // Scene.infinite_lights
     uint32_t n_infinite;
@@ -299,6 +322,107 @@ PB_D float2 get_2d(SampleBlock& b) {  // x from the lower dimension (sampler.rs:
     b.used += 2;
     return r;
 }
+
+// ---- (0,2)-sequence sampler, tile-serial (see ZtTile)
+PB_D uint32_t zt_u32(ZtTile& t) {  // RNG::uniform_int32, rng.rs:31-48
+    unsigned long long old = t.state;
+    t.state = old * 0x5851f42d4c957f2dULL + t.inc;
+    uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27), rot = (uint32_t)(old >> 59);
+    return (xs >> rot) | (xs << ((~rot + 1u) & 31u));
+}
+PB_D uint32_t zt_bounded(ZtTile& t, uint32_t b) {  // uniform_int32_2, rng.rs:50-60
+    uint32_t threshold = (~b + 1u) % b;
+    for (;;) { uint32_t r = zt_u32(t); if (r >= threshold) return r % b; }
+}
+PB_D float zt_float(ZtTile& t) { return fminf(PB_ONE_MINUS_EPSILON, (float)zt_u32(t) * 2.3283064365386963e-10f); }  // rng.rs:62-64
+PB_D void zt_set_sequence(ZtTile& t, unsigned long long seq) {  // rng.rs:66-74
+    t.state = 0; t.inc = (seq << 1) | 1ull;
+    zt_u32(t);
+    t.state += 0x853c49e6748fea9bULL;
+    zt_u32(t);
+}
+// ZeroTwoSequenceSampler::start_pixel (zerotwosequence.rs:54-66): van_der_corput / sobol_2d (lowdiscrepancy.rs:486-510) with
+// one sample per pixel sample => gray-code points, one shuffle() of every 1-element block (a draw each), one shuffle of the lot
+static __device__ __noinline__ void zt_start_pixel(ZtTile* tp, float* s1d, float2* s2d, uint32_t spp, uint32_t ndims) {
+    ZtTile t = *tp;
+    for (uint32_t d = 0; d < ndims; ++d) {
+        float* sm = s1d + (size_t)d * spp;
+        uint32_t v = zt_u32(t);  // scramble
+        for (uint32_t i = 0; i < spp; ++i) {  // gray_code_sample1d with CVAN_DER_CORPUT (identity, MSB first)
+            sm[i] = fminf((float)v * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
+            v ^= 0x80000000u >> __ffs((int)(i + 1)) - 1;
+        }
+        for (uint32_t i = 0; i < spp; ++i) zt_bounded(t, 1u);  // shuffle(&samples[i..], 1, 1): other = i + 0
+        for (uint32_t i = 0; i < spp; ++i) {                   // shuffle(samples, spp, 1), sampling.rs:178-186
+            uint32_t other = i + zt_bounded(t, spp - i);
+            float a = sm[i]; sm[i] = sm[other]; sm[other] = a;
+        }
+    }
+    for (uint32_t d = 0; d < ndims; ++d) {
+        float2* sm = s2d + (size_t)d * spp;
+        uint32_t v0 = zt_u32(t), v1 = zt_u32(t);
+        for (uint32_t i = 0; i < spp; ++i) {  // gray_code_sample2d with CSOBOL[0], CSOBOL[1] (lowdiscrepancy.rs:203-217)
+            sm[i] = make_float2(fminf((float)v0 * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON), fminf((float)v1 * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON));
+            int k = __ffs((int)(i + 1)) - 1;
+            v0 ^= 0x80000000u >> k;
+            uint32_t c1 = 0x80000000u;  // CSOBOL[1][k]: c[0] = 2^31, c[j] = c[j-1] ^ (c[j-1] >> 1)
+            for (int j = 0; j < k; ++j) c1 ^= c1 >> 1;
+            v1 ^= c1;
+        }
+        for (uint32_t i = 0; i < spp; ++i) zt_bounded(t, 1u);
+        for (uint32_t i = 0; i < spp; ++i) {
+            uint32_t other = i + zt_bounded(t, spp - i);
+            float2 a = sm[i]; sm[i] = sm[other]; sm[other] = a;
+        }
+    }
+    t.sample_idx = 0; t.cur1d = 0; t.cur2d = 0;
+    *tp = t;
+}
+// PixelSampler get_1d / get_2d, sampler.rs:228-253 (beyond the precomputed dimensions: raw draws, y before x)
+struct ZtCursor { ZtTile* t; const float* s1d; const float2* s2d; uint32_t spp, ndims; };
+PB_D ZtCursor zt_cursor(const RenderDev& R, uint32_t tile_ordinal) {
+    ZtCursor c;
+    c.t = R.zt.tiles + tile_ordinal;
+    c.s1d = R.zt.s1d + (size_t)tile_ordinal * R.zt.ndims * R.zt.spp;
+    c.s2d = R.zt.s2d + (size_t)tile_ordinal * R.zt.ndims * R.zt.spp;
+    c.spp = R.zt.spp; c.ndims = R.zt.ndims;
+    return c;
+}
+PB_D float get_1d(ZtCursor& c) {
+    ZtTile& t = *c.t;
+    if (t.cur1d < c.ndims) { float v = c.s1d[(size_t)t.cur1d * c.spp + t.sample_idx]; t.cur1d += 1; return v; }
+    return zt_float(t);
+}
+PB_D float2 get_2d(ZtCursor& c) {
+    ZtTile& t = *c.t;
+    if (t.cur2d < c.ndims) { float2 v = c.s2d[(size_t)t.cur2d * c.spp + t.sample_idx]; t.cur2d += 1; return v; }
+    float y = zt_float(t);
+    float x = zt_float(t);
+    return make_float2(x, y);
+}
+
+// The sampler interface the shade kernels are written against.  ZT = false: Sobol' / Halton, a pure function of
+// (sample index, dimension) evaluated eight dimensions at a time; ZT = true: the tile's (0,2)-sequence state.
+template <bool ZT> struct PathSampler;
+template <> struct PathSampler<false> {
+    SampleCursor c; SampleBlock sb;
+    PB_D void begin(const RenderDev& R, uint32_t id) {
+        c.index = R.s_index[id]; c.dim = R.s_dim[id];
+        uint32_t pxy = R.pixel[id];
+        c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
+        sample_block(R.sampler, c, sb);
+    }
+    PB_D float get_1d() { return pb::get_1d(sb); }
+    PB_D float2 get_2d() { return pb::get_2d(sb); }
+    PB_D void end(const RenderDev& R, uint32_t id) { R.s_dim[id] = c.dim + sb.used; }
+};
+template <> struct PathSampler<true> {
+    ZtCursor z;
+    PB_D void begin(const RenderDev& R, uint32_t id) { z = zt_cursor(R, id); }  // slot == tile ordinal
+    PB_D float get_1d() { return pb::get_1d(z); }
+    PB_D float2 get_2d() { return pb::get_2d(z); }
+    PB_D void end(const RenderDev&, uint32_t) {}
+};
 
 // ---------------------------------------------------------------------------
 // film: FilmTile::add_sample (core/film.rs:292-331) with warp-aggregated atomics
@@ -820,7 +944,7 @@ template <> struct BinKinds<Q_MIRROR> { static constexpr int KM = KM_MIRROR, MAT
 template <> struct BinKinds<Q_GLASS> { static constexpr int KM = KM_GLASS, MAT = PBRT_B200_MAT_GLASS; };
 template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT = PBRT_B200_MAT_METAL; };
 
-template <int BIN, bool INST>
+template <int BIN, bool INST, bool ZT>
 __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     constexpr int KM = BinKinds<BIN>::KM;
     const uint32_t n = R.cnt->n_mat[BIN];
@@ -851,7 +975,7 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
             } else {
                 uint4 h = R.hit[id];
                 uint32_t fl;
-                const uint32_t hinst = INST ? R.hit_inst[id] : PBRT_B200_NO_HIT;
+                const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
                 Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
                 const pbrt_b200_prim pr = R.scene.prims[h.x];
                 // SurfaceInteraction::le, interaction.rs:344-349 + AreaLight::l, diffuse.rs:68-75
@@ -873,16 +997,12 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
                         R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
                         push_next = true;
                     } else {
-                        SampleCursor c;
-                        c.index = R.s_index[id]; c.dim = R.s_dim[id];
-                        uint32_t pxy = R.pixel[id];
-                        c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
-                        SampleBlock sb;
-                        sample_block(R.sampler, c, sb);
+                        PathSampler<ZT> smp;
+                        smp.begin(R, id);
                         const int NONSPEC = BX_ALL & ~BX_SPECULAR;
                         // ---- uniform_sample_onelight + estimate_direct, integrator.rs:81-237
                         if (bsdf_count(bsdf, NONSPEC) > 0 && R.n_lights > 0) {
-                            float u1 = get_1d(sb);
+                            float u1 = smp.get_1d();
                             // light_distrib.lookup(isect.p), path.rs:132
                             const float* ld_cdf = R.ld_cdf; const float* ld_func = R.ld_func; float ld_func_int = R.ld_func_int;
                             if (R.sp.enabled) {
@@ -894,8 +1014,8 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
                             float selpdf = ld_func_int > 0.0f ? ld_func[ln] / (ld_func_int * (float)R.n_lights) : 0.0f;
                             bool zero = true;
                             if (selpdf != 0.0f) {
-                                float2 ulight = get_2d(sb);
-                                float2 uscatt = get_2d(sb);
+                                float2 ulight = smp.get_2d();
+                                float2 uscatt = smp.get_2d();
                                 const pbrt_b200_light& light = R.scene.lights[ln];
                                 bool delta = is_delta_light(light);
                                 LightSample ls;
@@ -947,7 +1067,7 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
                         f3 wo = -rd, wi(0.f, 0.f, 0.f);
                         float pdf = 0.0f;
                         int flags = 0;
-                        float2 ub = get_2d(sb);
+                        float2 ub = smp.get_2d();
                         rgb f = bsdf_sample<KM>(bsdf, wo, &wi, ub, &pdf, BX_ALL, &flags);
                         bool alive = !(is_black(f) || pdf == 0.0f);
                         if (alive) {
@@ -963,7 +1083,7 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
                             float mc = max_comp(rrbeta);
                             if (mc < R.rr_threshold && bounces > 3) {
                                 float qv = fmaxf(1.0f - mc, 0.05f);
-                                if (get_1d(sb) < qv) alive = false;
+                                if (smp.get_1d() < qv) alive = false;
                                 else beta = beta / (1.0f - qv);
                             }
                             if (alive) {
@@ -975,7 +1095,7 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
                         }
                         if (!alive) push_dead = true;
                         R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
-                        R.s_dim[id] = c.dim + sb.used;
+                        smp.end(R, id);
                     }
                 }
             }
@@ -1096,6 +1216,99 @@ __global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, u
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
         queue_push(R.q_path[parity ^ 1], &R.cnt->n_next, id, ok);
         queue_push(R.q_dead[parity ^ 1], &R.cnt->n_dead_next, id, regen && !ok);
+    }
+}
+
+// ---- (0,2)-sequence: tile-serial sample generation (the pixel / sample loops of integrator.rs:320-380 per tile)
+// Advances tile `j` (slot == tile ordinal) to its next camera sample and writes the path into the slot.  `first`: the tile
+// has not started (start_pixel of its first pixel is due).  Returns false when the tile is finished.
+PB_D bool zt_next_path(const RenderDev& R, uint32_t j, bool first) {
+    ZtTile* tp = R.zt.tiles + j;
+    float* s1d = R.zt.s1d + (size_t)j * R.zt.ndims * R.zt.spp;
+    float2* s2d = R.zt.s2d + (size_t)j * R.zt.ndims * R.zt.spp;
+    const uint32_t s_begin = R.sample_begin, s_end = R.sample_begin + R.n_samples_sel;
+    bool have = false;
+    if (!first) {  // start_next_sample(), sampler.rs:206-216
+        tp->cur1d = 0; tp->cur2d = 0;
+        tp->sample_idx += 1;
+        have = tp->sample_idx < R.zt.spp && tp->sample_idx < s_end;
+        if (!have) tp->pixel_idx += 1;
+    }
+    while (!have) {
+        if (tp->pixel_idx >= tp->npix) return false;
+        zt_start_pixel(tp, s1d, s2d, R.zt.spp, R.zt.ndims);  // every pixel of the tile, inside the pixel bounds or not (integrator.rs:322-330)
+        int x = tp->x0 + (int)(tp->pixel_idx % tp->w), y = tp->y0 + (int)(tp->pixel_idx / tp->w);
+        bool inside = x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] && y < R.pixel_bounds[3];
+        if (inside && s_begin < R.zt.spp && s_begin < s_end) { tp->sample_idx = s_begin; have = true; }  // set_sample_number
+        else tp->pixel_idx += 1;
+    }
+    const int x = tp->x0 + (int)(tp->pixel_idx % tp->w), y = tp->y0 + (int)(tp->pixel_idx / tp->w);
+    ZtCursor c = zt_cursor(R, j);
+    // get_camera_sample, sampler.rs:170-180
+    float2 u = get_2d(c);
+    float2 pfilm = make_float2((float)x + u.x, (float)y + u.y);
+    float tu = get_1d(c);
+    float2 plens = get_2d(c);
+    f3 o, d;
+    float time;
+    generate_ray(R.camera, pfilm, tu, plens, &o, &d, &time);
+    R.ray[2 * j] = make_float4(o.x, o.y, o.z, PB_INF);
+    R.ray[2 * j + 1] = make_float4(d.x, d.y, d.z, time);
+    R.L_eta[j] = make_float4(0.f, 0.f, 0.f, 1.0f);
+    R.beta_st[j] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
+    R.pfilm[j] = pfilm;
+    R.pixel[j] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
+    return true;
+}
+// tile j of the call -> tile number, clipped bounds, generator (sampler.clone(seed = tile.y * ntiles.x + tile.x), integrator.rs:302-303)
+__global__ void __launch_bounds__(128) k_zt_init(RenderDev R) {
+    const uint32_t n = R.n_tiles_sel;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < ((n + 31u) & ~31u); j += gridDim.x * blockDim.x) {
+        bool ok = false;
+        if (j < n) {
+            uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
+            ZtTile* tp = R.zt.tiles + j;
+            R.pixel[j] = PB_NO_SAMPLE;
+            if (t < R.tile_end) {
+                int tx = t % R.ntx, ty = t / R.ntx;
+                int x0 = R.sampler.sb[0] + tx * 16, y0 = R.sampler.sb[1] + ty * 16;
+                int x1 = min(x0 + 16, R.sampler.sb[2]), y1 = min(y0 + 16, R.sampler.sb[3]);
+                tp->x0 = x0; tp->y0 = y0; tp->w = (uint32_t)max(x1 - x0, 0); tp->npix = tp->w * (uint32_t)max(y1 - y0, 0);
+                tp->pixel_idx = 0; tp->sample_idx = 0; tp->cur1d = 0; tp->cur2d = 0;
+                zt_set_sequence(*tp, (unsigned long long)((long long)ty * R.ntx + tx));
+                ok = zt_next_path(R, j, true);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
+        queue_push(R.q_path[0], &R.cnt->n_next, j, ok);
+    }
+}
+// finished paths -> film; their tile moves on to its next sample
+__global__ void __launch_bounds__(128) k_finish_zt(RenderDev R, int parity) {
+    const uint32_t n = R.cnt->n_dead;
+    const uint32_t nround = (n + 31u) & ~31u;
+    const uint32_t* q = R.q_dead[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        bool valid = i < n;
+        rgb L(0.0f);
+        float2 pf = make_float2(0.f, 0.f);
+        uint32_t id = 0;
+        if (valid) {
+            id = q[i];
+            float4 Le = R.L_eta[id];
+            L = rgb(Le.x, Le.y, Le.z);
+            pf = R.pfilm[id];
+            float y = lum(L);  // integrator.rs:350-368
+            if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
+            else if (y < -1.0e-5f) L = rgb(0.0f);
+            else if (isinf(y)) L = rgb(0.0f);
+        }
+        film_add_sample(R, pf, L, valid);
+        bool ok = valid && zt_next_path(R, id, false);
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
+        queue_push(R.q_path[parity ^ 1], &R.cnt->n_next, id, ok);
     }
 }
 
@@ -1444,6 +1657,20 @@ long long mult_inverse(long long a, long long n) { long long x, y; ext_gcd(a, n,
 
 }  // namespace
 
+namespace {
+// one launch per material queue (sort/compact-by-material); INST / ZT select the kernel family (trace.cuh, PathSampler)
+template <bool INST, bool ZT>
+void launch_shade(const RenderDev& R, int parity, int grid_small, int grid_shade, cudaStream_t stream) {
+    k_shade<Q_MISS, INST, ZT><<<grid_small, 128, 0, stream>>>(R, parity);
+    k_shade<Q_MATTE, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_PLASTIC, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_MIRROR, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_GLASS, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_METAL, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_NOMAT, INST, ZT><<<grid_small, 128, 0, stream>>>(R, parity);
+}
+}  // namespace
+
 extern "C" int pbrt_b200_light_distribution_lookup(pbrt_b200_scene* sc, uint32_t strategy, uint32_t flags, const float* points, uint64_t n, int32_t* voxel_out,
                                                     float* func_out) {
     if (!sc || (n && (!points || !voxel_out || !func_out))) return fail(PBRT_B200_ERR_INVALID, "light_distribution_lookup: null argument");
@@ -1488,9 +1715,15 @@ extern "C" int pbrt_b200_light_distribution_lookup(pbrt_b200_scene* sc, uint32_t
 
 extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, float* rgbw_out, pbrt_b200_render_stats* stats) {
     if (!sc || !rd || !rgbw_out) return fail(PBRT_B200_ERR_INVALID, "render: null argument");
-    if (rd->sampler.kind > PBRT_B200_SAMPLER_HALTON)
-        return fail(PBRT_B200_ERR_UNSUPPORTED, "render: sampler not on the device path yet (sobol, halton)");
+    if (rd->sampler.kind > PBRT_B200_SAMPLER_ZEROTWO) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: sampler outside the hot path (sobol, halton, 02sequence)");
     if (rd->sampler.samples_per_pixel == 0) return fail(PBRT_B200_ERR_INVALID, "render: samples_per_pixel is 0");
+    const bool zt = rd->sampler.kind == PBRT_B200_SAMPLER_ZEROTWO;
+    uint32_t spp_eff = rd->sampler.samples_per_pixel;
+    if (zt) {  // ZeroTwoSequenceSampler::new rounds up to a power of two (zerotwosequence.rs:36-40)
+        if (spp_eff > (1u << 20)) return fail(PBRT_B200_ERR_INVALID, "render: 02sequence pixelsamples too large");
+        uint32_t v = 1; while (v < spp_eff) v <<= 1; spp_eff = v;
+        if (rd->sampler.n_sampled_dimensions > 64) return fail(PBRT_B200_ERR_INVALID, "render: 02sequence dimensions too large");
+    }
     if (rd->integrator.light_sample_strategy > PBRT_B200_LIGHTS_SPATIAL) return fail(PBRT_B200_ERR_INVALID, "render: unknown light_sample_strategy");
     PB_CUDA_TRY(cudaSetDevice(sc->device));
     int rc;
@@ -1514,8 +1747,8 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (W <= 0 || Hh <= 0) return fail(PBRT_B200_ERR_INVALID, "render: empty crop window");
     int ntx = (sb[2] - sb[0] + 15) / 16, nty = (sb[3] - sb[1] + 15) / 16;
     uint32_t tile_begin = rd->tile_begin, tile_end = rd->tile_end ? rd->tile_end : (uint32_t)(ntx * nty);
-    uint32_t s_begin = rd->sample_begin, s_end = rd->sample_end ? rd->sample_end : rd->sampler.samples_per_pixel;
-    if (tile_end > (uint32_t)(ntx * nty) || tile_begin > tile_end || s_begin > s_end || s_end > rd->sampler.samples_per_pixel)
+    uint32_t s_begin = rd->sample_begin, s_end = rd->sample_end ? rd->sample_end : spp_eff;
+    if (tile_end > (uint32_t)(ntx * nty) || tile_begin > tile_end || s_begin > s_end || s_end > spp_eff)
         return fail(PBRT_B200_ERR_INVALID, "render: tile/sample window out of range");
     uint32_t tile_group = rd->tile_group ? rd->tile_group : 1u, tile_mod = rd->tile_mod ? rd->tile_mod : 1u, tile_rem = rd->tile_rem;
     if (tile_rem >= tile_mod) return fail(PBRT_B200_ERR_INVALID, "render: tile_rem must be < tile_mod");
@@ -1529,6 +1762,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     uint32_t capacity = rd->paths_in_flight ? rd->paths_in_flight : (1u << 24);
     capacity = (capacity + 255u) & ~255u;
     if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
+    if (zt) capacity = (n_tiles_sel + 255u) & ~255u;  // tile-serial: one path slot per tile (see ZtTile)
     if (capacity == 0) capacity = 256;
     if ((rc = ensure_buffers(st, capacity))) return rc;
     lap("buffers");
@@ -1576,6 +1810,17 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     R.tile_begin = tile_begin; R.tile_end = tile_end; R.n_tiles_sel = n_tiles_sel; R.sample_begin = s_begin; R.n_samples_sel = s_end - s_begin;
     R.tile_group = tile_group; R.tile_mod = tile_mod; R.tile_rem = tile_rem;
 
+    void* zt_block = nullptr; size_t zt_bytes = 0;
+    if (zt && n_tiles_sel > 0) {
+        const size_t nd = rd->sampler.n_sampled_dimensions, per_tile = nd * spp_eff;
+        const size_t need = Arena::padded(sizeof(ZtTile) * n_tiles_sel) + Arena::padded(4 * per_tile * n_tiles_sel) + Arena::padded(8 * per_tile * n_tiles_sel) + 1024;
+        zt_block = pool_alloc(need, &zt_bytes);
+        if (!zt_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the 02sequence sample tables");
+        Arena A; A.base = reinterpret_cast<char*>(zt_block); A.size = zt_bytes;
+        R.zt.tiles = A.take<ZtTile>(n_tiles_sel); R.zt.s1d = A.take<float>(std::max<size_t>(per_tile * n_tiles_sel, 1)); R.zt.s2d = A.take<float2>(std::max<size_t>(per_tile * n_tiles_sel, 1));
+        R.zt.spp = spp_eff; R.zt.ndims = (uint32_t)nd;
+    }
+    struct ZtRelease { void* p; size_t n; ~ZtRelease() { if (p) { cudaDeviceSynchronize(); pool_free(p, n); } } } zt_release{zt_block, zt_bytes};
     // film buffer: device pointer supplied, or a scratch film that is added back to the host buffer
     const size_t npix = (size_t)W * Hh;
     float4* film_dev = nullptr;
@@ -1605,7 +1850,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     cudaEvent_t ev0 = pool_event(0), ev1 = pool_event(1);
     const size_t tev_base = ev_used;
     auto mark = [&]() { cudaEventRecord(pool_event(ev_used++), stream); };  // pairs around the trace kernels
-    const bool timing = stats != nullptr;
+    const bool timing = stats != nullptr && !zt;  // tile-serial mode runs ~10^5 tiny iterations: no per-phase events
     uint64_t launches = 0;
     PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
     if (st->sp_eager_pending) {  // every voxel's distribution, once per scene
@@ -1615,21 +1860,29 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         st->sp_eager_pending = false;
     }
     PB_CUDA_TRY(cudaEventRecord(ev0, stream));
-    if (total_items > 0) {
+    const unsigned long long loop_items = zt ? 0ull : total_items;  // tile-serial mode: the queues themselves say when the tiles are done
+    if (zt ? n_tiles_sel > 0 : total_items > 0) {
         // Persistent wavefront: all `capacity` slots start free; each iteration traces every live path one segment,
         // shades, resolves shadow/MIS rays, then k_finish_regen retires finished paths and refills their slots.
         // The host never waits on the batch it has just submitted: after every batch of `poll` iterations the queue
         // state is copied to a pinned ring entry, and the host looks at the copy of the batch BEFORE the one in flight,
         // so the GPU always has work queued behind the running iteration (over-submitted iterations find empty queues).
         DeviceShared::Progress* prog = sh->prog;
-        k_init_slots<<<grid_small, 256, 0, stream>>>(R, capacity);
-        k_finish_regen<<<grid_small, 256, 0, stream>>>(R, 1, total_items);
-        k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
-        launches += 3;
+        if (zt) {
+            k_zt_init<<<grid_small, 128, 0, stream>>>(R);
+            k_iter_end<<<1, 1, 0, stream>>>(R.cnt, 0ull);
+            launches += 2;
+        } else {
+            k_init_slots<<<grid_small, 256, 0, stream>>>(R, capacity);
+            k_finish_regen<<<grid_small, 256, 0, stream>>>(R, 1, total_items);
+            k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
+            launches += 3;
+        }
         int parity = 0;
         unsigned long long iter = 0, batch = 0;
-        const unsigned long long iter_cap = (total_items / capacity + 2) * (unsigned long long)(R.max_depth + 2) + 4096;
-        const int poll = 4;
+        const unsigned long long iter_cap = zt ? 256ull * spp_eff * (unsigned long long)(R.max_depth + 3) * 2ull + 4096
+                                               : (total_items / capacity + 2) * (unsigned long long)(R.max_depth + 2) + 4096;
+        const int poll = zt ? 32 : 4;  // tile-serial iterations are a few microseconds of work each
         const bool inst = sc->dev.n_instances != 0;
         bool done = false;
         while (!done) {
@@ -1645,23 +1898,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                     launches += 3;
                 }
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
-                if (inst) {
-                    k_shade<Q_MISS, true><<<grid_small, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_MATTE, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_PLASTIC, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_MIRROR, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_GLASS, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_METAL, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_NOMAT, true><<<grid_small, 128, 0, stream>>>(R, parity);
-                } else {
-                    k_shade<Q_MISS, false><<<grid_small, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_MATTE, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_PLASTIC, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_MIRROR, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_GLASS, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_METAL, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    k_shade<Q_NOMAT, false><<<grid_small, 128, 0, stream>>>(R, parity);
-                }
+                if (zt) launch_shade<true, true>(R, parity, grid_small, grid_shade, stream);
+                else if (inst) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
+                else launch_shade<false, false>(R, parity, grid_small, grid_shade, stream);
                 if (timing) mark();
                 if (inst) k_trace_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 else k_trace_shadow<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
@@ -1669,8 +1908,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (inst) k_trace_mis<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 else k_trace_mis<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 if (timing) mark();
-                k_finish_regen<<<grid_small, 256, 0, stream>>>(R, parity, total_items);
-                k_iter_end<<<1, 1, 0, stream>>>(R.cnt, total_items);
+                if (zt) k_finish_zt<<<grid_small, 128, 0, stream>>>(R, parity);
+                else k_finish_regen<<<grid_small, 256, 0, stream>>>(R, parity, total_items);
+                k_iter_end<<<1, 1, 0, stream>>>(R.cnt, loop_items);
                 if (timing) mark();
                 launches += 13;
                 parity ^= 1;
@@ -1686,7 +1926,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 cudaError_t e = cudaEventSynchronize(pool_event(2 + pb % PB_PROG_RING));
                 if (e != cudaSuccess) PB_CUDA_TRY(e);
                 const DeviceShared::Progress* pp = prog + (pb % PB_PROG_RING);
-                if (pp->cursor >= total_items && pp->n_path == 0) done = true;
+                if (pp->cursor >= loop_items && pp->n_path == 0) done = true;
             }
             batch++;
             if (iter > iter_cap) return fail(PBRT_B200_ERR_CUDA, "render: path queue failed to drain");

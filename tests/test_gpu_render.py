@@ -26,6 +26,10 @@ CASES = {
     "mixed-depth1": (lambda S: S.small_mixed_scene(), dict(spp_=4, res=(96, 64), maxdepth_=1)),
     "mixed-depth0": (lambda S: S.small_mixed_scene(), dict(spp_=4, res=(96, 64), maxdepth_=0)),
     "sphere16k-normals": (lambda S: S.displaced_sphere_scene(128, 64), dict(spp_=8, res=(160, 90))),
+    # ZeroTwoSequenceSampler: tile-serial on the device, so the per-tile PCG32 stream is the reference's
+    "mixed-02sequence": (lambda S: S.small_mixed_scene(), dict(spp_=8, res=(80, 56), sampler_="02sequence")),
+    "cornell-02sequence-spp-not-pow2": (lambda S: S.cornell_scene(), dict(spp_=6, res=(48, 40), sampler_="02sequence", filt="box")),
+    "spheres-02sequence-partial-tiles": (lambda S: S.spheres_scene(), dict(spp_=4, res=(70, 50), sampler_="02sequence")),
     # reduced-size versions of BASELINE.json configs[3] and configs[4]
     "s4-foliage-small": (lambda S: S.foliage_field_scene(n_instances=100, n_blades=24, seg=6, n_point=180, n_quads=10, field=24.0), dict(spp_=8, res=(160, 90))),
     "s5-glass-knot-small-depth32": (lambda S: S.glass_knot_scene(nu=96, nv=24), dict(spp_=16, res=(96, 96))),
