@@ -268,6 +268,28 @@ def main():
                "note": f"{n_e2e} steps after 1 warm-up; each = pbrt_b200_scene_create (host scene tables -> HBM, pageable host memory as handed over by the scene API) + render"
                        + (" + NCCL film reduce to rank 0" if world > 1 else "") + " + film download to host + scene destroy; host wall clock"}
 
+    # ---- Mrays/s on fixed ray batches through the batch C ABI (BASELINE.json metric (i); SURVEY.md s8(d) B-diff / B-shadow)
+    ray_batches = None
+    if rank == 0 and world == 1 and args.scene in ("s3", "s3small"):
+        S = pkg.scenes
+        ray_batches = {}
+        for bname, rays, anyhit in (("B-diff closest-hit", S.rays_diffuse(setup.flat, 4_000_000, seed=7), False),
+                                    ("B-surf closest-hit", S.rays_surface(setup.flat, 4_000_000, seed=23), False),
+                                    ("B-shadow any-hit", S.rays_shadow(setup.flat, 4_000_000, seed=11), True)):
+            m = len(rays)
+            dr = torch.from_numpy(np.ascontiguousarray(rays).view(np.float32).reshape(-1, 8)).cuda()
+            dh = torch.empty(m, dtype=torch.uint8, device="cuda") if anyhit else torch.empty((m, 4), dtype=torch.int32, device="cuda")
+            f = scene.intersect_p_dev if anyhit else scene.intersect_dev
+            for _ in range(3):
+                f(dr.data_ptr(), m, dh.data_ptr())
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(10):
+                f(dr.data_ptr(), m, dh.data_ptr())
+            b1.record(); torch.cuda.synchronize()
+            ray_batches[bname] = {"rays": m, "mrays_per_s": m / (b0.elapsed_time(b1) / 10) / 1e3}
+
     if rank == 0:
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
@@ -300,7 +322,7 @@ def main():
                           "l2": "no explicit flush: per-step working set (2^24 path slots x ~300 B state + 110 MB scene + 33 MB film) exceeds the 126 MB L2",
                           "paths_in_flight": args.paths_in_flight or 1 << 24, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"},
                "mrays_per_s": (closest + shadow) / (ms * 1e-3) / 1e6, "rays_per_sample": (closest + shadow) / max(camera, 1),
-               "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+               "ray_batches": ray_batches, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "kernel_ms": {"trace_closest": tot["trace_closest_ms"], "trace_shadow": tot["trace_any_ms"], "wavefront_total": tot["device_ms"]}}
         print(json.dumps(out))
     scene.close()
