@@ -227,6 +227,9 @@ PB_D SlabPair slab_fast2(float2 nx, float2 ny, float2 nz, float2 fx, float2 fy, 
 }
 
 #define PB_STACK_DEPTH 64  /* bvh.rs:722 nodes_tovisit = vec![0; 64] */
+/* the reference keeps one 64-entry stack per BVHAccel; the unified two-level walk stacks the object's entries on top of the
+ * world's, plus the sentinel and the rest-of-leaf entry */
+#define PB_STACK_SIZE(INST) ((INST) ? 2 * PB_STACK_DEPTH + 2 : PB_STACK_DEPTH)
 #define PB_DONE 0xffffffffu /* traversal finished (has the leaf bit set so the interior loop exits) */
 
 // Per-ray traversal state.  The order of box and primitive tests is the reference's
@@ -242,6 +245,12 @@ struct TravRay {
     bool ngx, ngy, ngz, found;
     bool nan_possible;  // a zero direction component: 0 * inf can appear in the slab test
     RayHit hit;
+    // Inside an instanced object (INST kernels only): the instance being walked, whether it produced a hit, and the world
+    // ray to restore when the object's sub-tree has been exhausted (the traversal stack holds a sentinel at that point).
+    uint32_t cur_inst;
+    bool inst_found;
+    float world_t_max;
+    f3 wo, wd;
 #if PB_PACKED_SLAB
     float2 nox, noy, noz, ivx, ivy, ivz;  // {-o, -o} and {1/d, 1/d} per axis for slab_fast2
 #endif
@@ -249,10 +258,9 @@ struct TravRay {
 
 // root_ref / root_box: the accelerator to walk (the scene's aggregate or an instanced object's BVH); root_box == nullptr
 // for a one-primitive object, which the reference intersects directly (no accelerator, no bounds test)
-PB_D void trav_init_at(TravRay& r, f3 o, f3 d, float t_max, uint32_t root_ref, const float* rb) {
-    r.o = o; r.d = d; r.t_max = t_max;
-    r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.b0 = r.hit.b1 = r.hit.b2 = 0.0f; r.hit.inst = PBRT_B200_NO_HIT;
-    r.found = false; r.sp = 0; r.cur = PB_DONE;
+// everything the box and triangle tests derive from (o, d) alone
+PB_D void trav_set_ray(TravRay& r, f3 o, f3 d) {
+    r.o = o; r.d = d;
     r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     r.ngx = r.inv.x < 0.0f; r.ngy = r.inv.y < 0.0f; r.ngz = r.inv.z < 0.0f;
     r.nan_possible = (d.x == 0.0f) || (d.y == 0.0f) || (d.z == 0.0f);
@@ -267,12 +275,24 @@ PB_D void trav_init_at(TravRay& r, f3 o, f3 d, float t_max, uint32_t root_ref, c
     r.ky = (r.kx + 1 == 3) ? 0 : r.kx + 1;
     const float dpx = comp(d, r.kx), dpy = comp(d, r.ky), dpz = comp(d, r.kz);
     r.Sx = -dpx / dpz; r.Sy = -dpy / dpz; r.Sz = 1.0f / dpz;
-    if (root_ref == PB_REF_NONE) return;
-    if (rb == nullptr) { r.cur = root_ref; return; }
+}
+// BVHAccel::intersect's first step: the root node's own bounds test (bvh.rs:724-727).  rb == nullptr: a one-primitive
+// object, which the reference intersects directly.
+PB_D uint32_t trav_enter_root(const TravRay& r, uint32_t root_ref, const float* rb) {
+    if (root_ref == PB_REF_NONE) return PB_DONE;
+    if (rb == nullptr) return root_ref;
     float tmin;
     bool ok = slab_test(r.ngx ? rb[3] : rb[0], r.ngy ? rb[4] : rb[1], r.ngz ? rb[5] : rb[2], r.ngx ? rb[0] : rb[3], r.ngy ? rb[1] : rb[4],
-                        r.ngz ? rb[2] : rb[5], o, r.inv, &tmin);
-    if (ok && tmin < t_max) r.cur = root_ref;
+                        r.ngz ? rb[2] : rb[5], r.o, r.inv, &tmin);
+    return (ok && tmin < r.t_max) ? root_ref : PB_DONE;
+}
+PB_D void trav_init_at(TravRay& r, f3 o, f3 d, float t_max, uint32_t root_ref, const float* rb) {
+    r.t_max = t_max;
+    r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.b0 = r.hit.b1 = r.hit.b2 = 0.0f; r.hit.inst = PBRT_B200_NO_HIT;
+    r.found = false; r.sp = 0;
+    r.cur_inst = PBRT_B200_NO_HIT; r.inst_found = false;
+    trav_set_ray(r, o, d);
+    r.cur = trav_enter_root(r, root_ref, rb);
 }
 PB_D void trav_init(const DevScene& s, TravRay& r, f3 o, f3 d, float t_max) { trav_init_at(r, o, d, t_max, s.root_ref, s.root_box); }
 
@@ -290,7 +310,7 @@ PB_D void xf_ray(const float* M, f3 o, f3 d, float t_max, f3* o_out, f3* d_out, 
     *o_out = o2; *d_out = d2; *t_max_out = t_max;
 }
 
-template <bool ANY> static __device__ __noinline__ bool instance_test(const DevScene* sp, uint32_t inst, f3 o, f3 d, float t_max, RayHit* hit);
+#define PB_INST_EXIT 0xfffffffeu /* stack sentinel (leaf bit set): the instanced object's sub-tree is exhausted */
 
 // pop: the reference tests the popped node's box against the *current* t_max
 #define PB_TRAV_POP(r, stack)                                           \
@@ -306,7 +326,7 @@ template <bool ANY> static __device__ __noinline__ bool instance_test(const DevS
 // Runs the ray until it finishes, or (when `yield_below` > 0) until fewer than `yield_below`
 // lanes of the warp are still traversing, so that the caller can refill idle lanes.
 // TOP: walking the scene's aggregate (leaf slots may be TransformedPrimitives); false inside an instanced object, where
-// ObjectInstance cannot appear (api.rs:1674-1677) -- which also keeps instance_test from recursing.
+// ObjectInstance cannot appear (api.rs:1674-1677): one level of instancing, one sentinel on the stack at most.
 template <bool ANY, bool EXACT_NAN, bool TOP>
 PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
     while (r.cur != PB_DONE) {
@@ -358,26 +378,46 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
         }
         if (r.cur == PB_DONE) break;
         // ---- leaf run (bvh.rs:730-736): every primitive of the leaf, in order
+        if (TOP && r.cur == PB_INST_EXIT) {
+            // back in world space: r.t_max = ray.t_max when the object was hit (primitive.rs:72), the world value otherwise
+            if (!r.inst_found) r.t_max = r.world_t_max;
+            trav_set_ray(r, r.wo, r.wd);
+            r.cur_inst = PBRT_B200_NO_HIT; r.inst_found = false;
+            PB_TRAV_POP(r, stack);
+            continue;
+        }
         if (r.cur & PB_LEAF_BIT) {
             uint32_t slot = r.cur & ~PB_LEAF_BIT;
             uint32_t fl;
+            bool entered = false;
             do {
                 const float4* tp = s.tris + 3ull * slot;
                 float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
                 fl = __float_as_uint(v1.w);
                 float t, b0, b1, b2;
                 bool h;
-                uint32_t hslot = slot, hinst = PBRT_B200_NO_HIT;
                 if (fl & (PB_TRI_SPHERE | PB_TRI_INSTANCE)) {
-                    if (TOP && (fl & PB_TRI_INSTANCE)) {  // TransformedPrimitive::intersect / intersect_p, primitive.rs:58-89
-                        RayHit ih;
-                        hinst = __float_as_uint(v2.w);
-                        h = instance_test<ANY>(s.self_dev, hinst, r.o, r.d, r.t_max, &ih);
-                        t = ih.t; b0 = ih.b0; b1 = ih.b1; b2 = ih.b2; hslot = ih.slot;
-                    } else {
-                        h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
-                        b0 = b1 = b2 = 0.0f;
+                    if (TOP && (fl & PB_TRI_INSTANCE)) {
+                        // TransformedPrimitive::intersect / intersect_p, primitive.rs:58-89: continue the SAME loop inside the
+                        // object's accelerator with the ray taken to object space (Transform::transform_ray: origin-error
+                        // nudge, t_max -= dt).  Left on the stack, in pop order: the object's nodes, the sentinel that
+                        // restores the world ray, then the rest of this leaf.
+                        const DevInstance* in = s.instances + __float_as_uint(v2.w);
+                        if (!(fl & PB_TRI_LAST)) { stack[r.sp] = make_uint2(PB_LEAF_BIT | (slot + 1), 0xff800000u); ++r.sp; }  // tmin = -inf: always resumed
+                        stack[r.sp] = make_uint2(PB_INST_EXIT, 0xff800000u); ++r.sp;
+                        r.wo = r.o; r.wd = r.d; r.world_t_max = r.t_max;
+                        r.cur_inst = __float_as_uint(v2.w); r.inst_found = false;
+                        f3 o2, d2;
+                        float tm2;
+                        xf_ray(in->world_to_prim, r.o, r.d, r.t_max, &o2, &d2, &tm2);
+                        r.t_max = tm2;
+                        trav_set_ray(r, o2, d2);
+                        r.cur = trav_enter_root(r, in->root_ref, (in->flags & PB_INST_HAS_BOX) ? in->root_box : nullptr);
+                        entered = true;
+                        break;
                     }
+                    h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
+                    b0 = b1 = b2 = 0.0f;
                 } else {
                     f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
                     h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
@@ -389,14 +429,19 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
                 }
                 if (h) {
                     r.found = true;
-                    r.hit.slot = hslot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2; r.hit.inst = hinst;
+                    r.hit.slot = slot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2;
+                    if (TOP) { r.hit.inst = r.cur_inst; r.inst_found = r.cur_inst != PBRT_B200_NO_HIT; }
                     if (ANY) { r.cur = PB_DONE; r.sp = 0; break; }
-                    r.t_max = t;  // primitive.rs:137 (for an instance: r.t_max = ray.t_max, primitive.rs:72)
+                    r.t_max = t;  // primitive.rs:137
                 }
                 ++slot;
             } while (!(fl & PB_TRI_LAST));
             if (ANY && r.found) break;
-            PB_TRAV_POP(r, stack);
+            if (TOP && entered) {
+                if (r.cur == PB_DONE) PB_TRAV_POP(r, stack);  // the object's root box was missed: straight to the sentinel
+            } else {
+                PB_TRAV_POP(r, stack);
+            }
         }
         if (yield_below > 0 && __popc(__activemask()) < yield_below) break;
     }
@@ -406,32 +451,16 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
 // contain no trace of the instance path (measured on S3: the mere presence of the out-of-line call in the leaf loop costs 20%).
 template <bool ANY, bool INST>
 PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min = 0) {
-    if (r.nan_possible) trav_run_impl<ANY, true, INST>(s, r, stack, yield_below, interior_min);
+    // with instances the ray changes along the way, so the NaN-free slab shortcut cannot be chosen once per ray: INST
+    // kernels always evaluate the literal reference chain
+    if (INST || r.nan_possible) trav_run_impl<ANY, true, INST>(s, r, stack, yield_below, interior_min);
     else trav_run_impl<ANY, false, INST>(s, r, stack, yield_below, interior_min);
-}
-
-// The instanced object's own accelerator, walked to completion with the ray taken into the object's space.  Out of line
-// (own traversal stack in its frame): scenes without instancing only pay the flag test above.
-template <bool ANY>
-static __device__ __noinline__ bool instance_test(const DevScene* sp, uint32_t inst, f3 o, f3 d, float t_max, RayHit* hit) {
-    const DevScene& s = *sp;
-    const DevInstance& in = s.instances[inst];
-    f3 o2, d2;
-    float tm2;
-    xf_ray(in.world_to_prim, o, d, t_max, &o2, &d2, &tm2);
-    uint2 stack[PB_STACK_DEPTH];
-    TravRay r;
-    trav_init_at(r, o2, d2, tm2, in.root_ref, (in.flags & PB_INST_HAS_BOX) ? in.root_box : nullptr);
-    if (r.nan_possible) trav_run_impl<ANY, true, false>(s, r, stack, 0, 0);
-    else trav_run_impl<ANY, false, false>(s, r, stack, 0, 0);
-    *hit = r.hit;
-    return r.found;
 }
 
 // Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray, run to completion.
 template <bool ANY, bool INST = false>
 PB_D bool traverse(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
-    uint2 stack[PB_STACK_DEPTH];
+    uint2 stack[PB_STACK_SIZE(INST)];
     TravRay r;
     trav_init(s, r, o, d, t_max);
     trav_run<ANY, INST>(s, r, stack, 0);
@@ -544,7 +573,7 @@ PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit)
 struct TraceTune { int refill_below; int chunk; int interior_min; };
 template <bool ANY, bool INST, typename Job>
 PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_counter, TraceTune tune = TraceTune{PB_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN}) {
-    uint2 stack[PB_STACK_DEPTH];
+    uint2 stack[PB_STACK_SIZE(INST)];
     TravRay r;
     r.cur = PB_DONE; r.sp = 0; r.found = false;
     uint32_t ray_idx = 0xffffffffu;
