@@ -352,7 +352,7 @@ static __device__ __noinline__ void zt_start_pixel(ZtTile* tp, float* s1d, float
             sm[i] = fminf((float)v * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
             v ^= 0x80000000u >> __ffs((int)(i + 1)) - 1;
         }
-        for (uint32_t i = 0; i < spp; ++i) zt_bounded(t, 1u);  // shuffle(&samples[i..], 1, 1): other = i + 0
+        for (uint32_t i = 0; i < spp; ++i) zt_u32(t);          // shuffle(&samples[i..], 1, 1): uniform_int32_2(1) = one draw (threshold 0), result 0
         for (uint32_t i = 0; i < spp; ++i) {                   // shuffle(samples, spp, 1), sampling.rs:178-186
             uint32_t other = i + zt_bounded(t, spp - i);
             float a = sm[i]; sm[i] = sm[other]; sm[other] = a;
@@ -369,7 +369,7 @@ static __device__ __noinline__ void zt_start_pixel(ZtTile* tp, float* s1d, float
             for (int j = 0; j < k; ++j) c1 ^= c1 >> 1;
             v1 ^= c1;
         }
-        for (uint32_t i = 0; i < spp; ++i) zt_bounded(t, 1u);
+        for (uint32_t i = 0; i < spp; ++i) zt_u32(t);
         for (uint32_t i = 0; i < spp; ++i) {
             uint32_t other = i + zt_bounded(t, spp - i);
             float2 a = sm[i]; sm[i] = sm[other]; sm[other] = a;
@@ -1837,8 +1837,12 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
     int trace_per_sm = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, sc->dev.n_instances ? k_trace_closest<true> : k_trace_closest<false>, PB_TRACE_BLOCK, 0);
-    const int grid_trace = sm_count * (trace_per_sm > 0 ? trace_per_sm : 1);  // persistent: exactly one resident wave
-    const int grid_shade = sm_count * 8, grid_small = sm_count * 4;
+    int grid_trace = sm_count * (trace_per_sm > 0 ? trace_per_sm : 1);  // persistent: exactly one resident wave
+    int grid_shade = sm_count * 8, grid_small = sm_count * 4;
+    if (zt) {  // tile-serial: at most one path per tile in flight -- a few CTAs cover the queues
+        const int need = (int)((capacity + 127u) / 128u);
+        grid_trace = std::min(grid_trace, need); grid_shade = std::min(grid_shade, need); grid_small = std::min(grid_small, need);
+    }
 
     cudaStream_t stream = 0;
     // events come from the scene's pool: [0] start, [1] end, [2..2+PB_PROG_RING) progress copies, then timing marks

@@ -5,8 +5,12 @@ sys.path.insert(0, '.')
 import numpy as np
 import torch
 P = importlib.import_module("pbrt-rust_b200")
-setup = P.scenes.displaced_sphere_scene()
-integ = setup.make_integrator(spp_=16 * 16)
+import os
+SCENE = os.environ.get("DIAG_SCENE", "s3")
+SPP = int(os.environ.get("DIAG_SPP", "16"))
+setup = {"s3": P.scenes.displaced_sphere_scene, "s4": P.scenes.foliage_field_scene, "cornell": P.scenes.cornell_scene,
+         "s5": lambda: P.scenes.glass_knot_scene(nu=4096, nv=640)}[SCENE]()
+integ = setup.make_integrator(spp_=SPP * 16)
 film = integ.film
 sc = P.Scene(setup.flat)
 film_t = torch.zeros((film.width * film.height, 4), dtype=torch.float32, device="cuda")
@@ -20,7 +24,7 @@ def run(tag, n=4, k0=0):
     agg = None
     for k in range(n):
         film_t.zero_()
-        _, st = sc.render(integ, sample_range=((k0 + k) * 16, (k0 + k + 1) * 16), device_ptr=film_t.data_ptr(), paths_in_flight=pif)
+        _, st = sc.render(integ, sample_range=((k0 + k) * SPP, (k0 + k + 1) * SPP), device_ptr=film_t.data_ptr(), paths_in_flight=pif)
         agg = st
     e1.record(); torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / n * 1e3
