@@ -137,8 +137,18 @@ def cpu_baseline(pkg, setup, integ_kw, seconds, threads=0):
             "rays_per_sample": rays / max(samples, 1)}
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout when
+    NCCL_DEBUG=VERSION is set on the box), so fd 1 is pointed at stderr for the run and the JSON line goes to the saved fd."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
     args = parse()
+    out_stream = _claim_stdout()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     pkg = importlib.import_module("pbrt-rust_b200")
@@ -165,7 +175,7 @@ def main():
                           "config": {"workload": desc, "step": "1 spp over the full frame (bounded sample of the workload)"},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nth, "kind": "port",
                                            "sample": f"{args.steps} steps x 1 spp x {film.width}x{film.height} on {nth} threads (CPU oracle: the Rust reference cannot be built here)"},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out_stream, flush=True)
         return 0
 
     import torch
@@ -324,7 +334,7 @@ def main():
                "mrays_per_s": (closest + shadow) / (ms * 1e-3) / 1e6, "rays_per_sample": (closest + shadow) / max(camera, 1),
                "ray_batches": ray_batches, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "kernel_ms": {"trace_closest": tot["trace_closest_ms"], "trace_shadow": tot["trace_any_ms"], "wavefront_total": tot["device_ms"]}}
-        print(json.dumps(out))
+        print(json.dumps(out), file=out_stream, flush=True)
     scene.close()
     if world > 1:
         dist.destroy_process_group()
