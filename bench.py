@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--spp", type=int, default=16, help="camera samples per pixel per step and per GPU")
+    ap.add_argument("--spp", type=int, default=64, help="camera samples per pixel per step and per GPU")
     ap.add_argument("--scene", default="s3", choices=["s3", "cornell", "spheres", "s3small", "s4", "s5"])
     ap.add_argument("--paths-in-flight", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
