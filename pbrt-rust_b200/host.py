@@ -227,7 +227,9 @@ class Transform:
         return Transform(_m4_mul(self.m, o.m), _m4_mul(o.m_inv, self.m_inv))
 
     def inverse(self):
-        return Transform(self.m_inv, self.m)
+        r = Transform(self.m_inv, self.m)
+        r.inverse_of = self  # provenance only (scenefile.py writes `LookAt` for a camera built from look_at().inverse())
+        return r
 
     @staticmethod
     def translate(d):  # transform.rs:255-271
@@ -275,7 +277,9 @@ class Transform:
         new_up = cross(d, right)
         c2w = np.eye(4, dtype=f32)
         c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, new_up, d, pos
-        return Transform(_m4_inverse(c2w), c2w)
+        r = Transform(_m4_inverse(c2w), c2w)
+        r.lookat_args = (pos, look, up)
+        return r
 
     @staticmethod
     def perspective(fov, n, f):  # transform.rs:399-411
@@ -416,10 +420,12 @@ class SceneBuilder:
         self._lights = []
         self.any_n = self.any_s = self.any_uv = False
         self._objects, self._instances, self._cur_object = {}, [], None
+        self.log = []  # every directive in call order (scenefile.py turns it back into a .pbrt file)
 
     # --- object instancing (api.rs:1593-1713) ---------------------------------
     def object_begin(self, name):
-        self.attribute_begin()
+        self.log.append(("ObjectBegin", name))
+        self._push()
         if self._cur_object is not None:
             raise B200Error("ObjectBegin called inside of instance definition")
         self._objects[name] = {"prims": [], "bounds": []}
@@ -432,13 +438,15 @@ class SceneBuilder:
             raise B200Error("ObjectEnd called outside of instance definition")
         self._prims, self._bounds = self._top
         self._cur_object = None
-        self.attribute_end()
+        self._pop()
+        self.log.append(("ObjectEnd",))
 
     def object_instance(self, name):
         if self._cur_object is not None:
             raise B200Error("ObjectInstance can't be called inside instance definition")
         if name not in self._objects:
             raise B200Error(f'Unable to find instance named "{name}"')
+        self.log.append(("ObjectInstance", name))
         if not self._objects[name]["prims"]:
             return  # api.rs:1684-1686: empty instance
         row = np.zeros(1, PRIM_DTYPE)
@@ -448,25 +456,38 @@ class SceneBuilder:
         self._bounds.append(None)  # TransformedPrimitive::world_bound needs the object's BVH: filled in by world_end
 
     # --- graphics state ---------------------------------------------------
-    def attribute_begin(self):
+    def _push(self):
         self._stack.append((self.ctm, self._material, self._area_light, self.reverse_orientation))
 
-    def attribute_end(self):
+    def _pop(self):
         self.ctm, self._material, self._area_light, self.reverse_orientation = self._stack.pop()
 
+    def attribute_begin(self):
+        self.log.append(("AttributeBegin",))
+        self._push()
+
+    def attribute_end(self):
+        self._pop()
+        self.log.append(("AttributeEnd",))
+
     def identity(self):
+        self.log.append(("Identity",))
         self.ctm = Transform()
 
     def translate(self, x, y, z):
+        self.log.append(("Translate", x, y, z))
         self.ctm = self.ctm * Transform.translate((x, y, z))
 
     def scale(self, x, y, z):
+        self.log.append(("Scale", x, y, z))
         self.ctm = self.ctm * Transform.scale(x, y, z)
 
     def rotate(self, deg, x, y, z):
+        self.log.append(("Rotate", deg, x, y, z))
         self.ctm = self.ctm * Transform.rotate(deg, (x, y, z))
 
     def transform(self, t):
+        self.log.append(("ConcatTransform", t))
         self.ctm = self.ctm * t
 
     # --- materials (src/materials/*.rs create_* defaults) -------------------
@@ -500,6 +521,7 @@ class SceneBuilder:
         return r
 
     def material(self, name, **kw):
+        self.log.append(("Material", name, kw))
         self._material = self._mat_row(name, **kw)
 
     def _material_id(self):
@@ -515,9 +537,11 @@ class SceneBuilder:
     def area_light_source(self, name="diffuse", L=(1, 1, 1), scale=1.0, twosided=False):  # diffuse.rs:178-195
         if name not in ("diffuse", "area"):
             raise B200Error(f'AreaLightSource "{name}" unknown')
+        self.log.append(("AreaLightSource", name, {"L": L, "scale": scale, "twosided": twosided}))
         self._area_light = (np.asarray(L, f32) * f32(scale) if not np.isscalar(L) else np.full(3, L * scale, f32), bool(twosided))
 
     def light_source(self, name, **kw):
+        self.log.append(("LightSource", name, kw))
         r = np.zeros(1, LIGHT_DTYPE)[0]
 
         def rgb(key, default):
@@ -562,6 +586,7 @@ class SceneBuilder:
 
     # --- shapes --------------------------------------------------------------
     def shape(self, name, **kw):
+        self.log.append(("Shape", name, kw))
         if name == "trianglemesh":
             return self._trianglemesh(**kw)
         if name == "sphere":
@@ -634,6 +659,7 @@ class SceneBuilder:
     # --- WorldEnd: make_scene (api.rs:244-251) -------------------------------
     def world_end(self, max_prims=4, split_method="sah", builder=None):
         fs = FlatScene()
+        fs.source_log, fs.accelerator = self.log, (split_method, max_prims)
         nprim = sum(len(p) for p in self._prims)
         if self._P:
             fs.vertex_p = np.ascontiguousarray(np.concatenate(self._P), f32)
@@ -722,10 +748,39 @@ def _filter_eval(name, radius, x, y, **kw):
         return f32(gx * gy)
     if name == "triangle":  # triangle.rs (filters)
         return f32(max(f32(0), rx - abs(x)) * max(f32(0), ry - abs(y)))
-    raise B200Error(f'Filter "{name}" not mirrored on the host (box, gaussian, triangle); pass a 16x16 table instead')
+    if name == "mitchell":  # mitchell.rs:26-45, including its two slips (`6B * 30C`, `x * x` in the inner branch)
+        B, Cc = f32(kw.get("B", 1.0 / 3.0)), f32(kw.get("C", 1.0 / 3.0))
+
+        def m1d(v):
+            v = f32(v)
+            a = abs(f32(2) * v)
+            if a > 1:
+                return f32(((-B - f32(6) * Cc) * a * a * a + (f32(6) * B * f32(30) * Cc) * a * a + (f32(-12) * B - f32(48) * Cc) * a +
+                            (f32(8) * B + f32(24) * Cc)) * f32(1.0 / 6.0))
+            return f32(((f32(12) - f32(9) * B - f32(6) * Cc) * a * a * a + (f32(-18) + f32(12) * B + f32(6) * Cc) * v * v + (f32(6) - f32(2) * B)) *
+                       f32(1.0 / 6.0))
+
+        return f32(m1d(f32(x) * (f32(1) / rx)) * m1d(f32(y) * (f32(1) / ry)))
+    if name == "sinc":  # sinc.rs:18-45: the window test is `y < radius -> 0`, so the table is zero inside the support (kept as is)
+        tau = f32(kw.get("tau", 3.0))
+
+        def sinc(v):
+            v = abs(f32(v))
+            if v < f32(1e-5):
+                return f32(1)
+            return f32(np.sin(f32(np.pi) * v)) / (f32(np.pi) * v)
+
+        def wsinc(v, r):
+            v = abs(f32(v))
+            if v < r:
+                return f32(0)
+            return f32(sinc(v) * sinc(v / tau))
+
+        return f32(wsinc(x, rx) * wsinc(y, ry))
+    raise B200Error(f'Filter "{name}" unknown')  # api.rs:868-881 panics
 
 
-FILTER_DEFAULT_RADIUS = {"box": (0.5, 0.5), "gaussian": (2.0, 2.0), "triangle": (2.0, 2.0)}
+FILTER_DEFAULT_RADIUS = {"box": (0.5, 0.5), "gaussian": (2.0, 2.0), "triangle": (2.0, 2.0), "mitchell": (2.0, 2.0), "sinc": (4.0, 4.0)}
 
 
 class Film:
@@ -736,6 +791,7 @@ class Film:
         self.filter = filter
         self.radius = tuple(radius or FILTER_DEFAULT_RADIUS[filter])
         x0, x1, y0, y1 = crop
+        self.crop, self.filter_params = tuple(float(v) for v in crop), dict(fkw)
         self.cropped_pixel_bounds = (int(math.ceil(f32(xres) * f32(x0))), int(math.ceil(f32(yres) * f32(y0))),
                                      int(math.ceil(f32(xres) * f32(x1))), int(math.ceil(f32(yres) * f32(y1))))
         self.scale = scale
@@ -791,6 +847,7 @@ class PerspectiveCamera:
         self.raster_to_camera = c2s.inverse() * s2r.inverse()
         self.camera_to_world = camera_to_world
         self.lens_radius, self.focal_distance = lensradius, focaldistance
+        self.fov, self.screenwindow = fov, (None if screenwindow is None else tuple(float(v) for v in screenwindow))
         self.shutter_open, self.shutter_close = shutteropen, shutterclose
 
     def desc(self):
@@ -809,6 +866,8 @@ class Sampler:
         if name not in self.KINDS:
             raise B200Error(f'Sampler "{name}" is outside the hot path (sobol, halton, 02sequence)')
         self.kind, self.spp, self.dimensions = self.KINDS[name], int(pixelsamples), int(dimensions)
+        if self.kind == SAMPLER_ZEROTWO and self.spp > 0:  # zerotwosequence.rs:33-36 rounds up; SobolSampler::new only warns (sobol.rs:35-40)
+            self.spp = 1 << (self.spp - 1).bit_length()
 
     def desc(self, film):
         t = sampler_tables()
@@ -831,6 +890,7 @@ class PathIntegrator:
             lightsamplestrategy = "spatial"  # path.rs -> lightdistrib.rs:27-30
         self.light_sample_strategy = lightsamplestrategy
         sb = film.sample_bounds
+        self.pixelbounds_param = pixelbounds
         if pixelbounds is not None:  # path.rs:233-246: (x0, x1, y0, y1) intersected with the sample bounds
             x0, x1, y0, y1 = pixelbounds
             sb = (max(sb[0], x0), max(sb[1], y0), min(sb[2], x1), min(sb[3], y1))
