@@ -1839,7 +1839,11 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     int trace_per_sm = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, sc->dev.n_instances ? k_trace_closest<true> : k_trace_closest<false>, PB_TRACE_BLOCK, 0);
     int grid_trace = sm_count * (trace_per_sm > 0 ? trace_per_sm : 1);  // persistent: exactly one resident wave
-    int grid_shade = sm_count * 8, grid_small = sm_count * 4;
+    // shade kernels keep 5 CTAs of 128 threads resident per SM (96-104 registers): 10 per SM = two full waves (8 left a
+    // 3-CTA tail wave: -1.5 % on S3, gpurun_out/ab4.log)
+    int grid_shade = sm_count * 10, grid_small = sm_count * 4;
+    if (const char* e = getenv("PBRT_B200_GRID_SMALL")) grid_small = sm_count * std::max(1, atoi(e));  // A/B knobs (tools/ab_variants.sh)
+    if (const char* e = getenv("PBRT_B200_GRID_SHADE")) grid_shade = sm_count * std::max(1, atoi(e));
     if (zt) {  // tile-serial: at most one path per tile in flight -- a few CTAs cover the queues
         const int need = (int)((capacity + 127u) / 128u);
         grid_trace = std::min(grid_trace, need); grid_shade = std::min(grid_shade, need); grid_small = std::min(grid_small, need);

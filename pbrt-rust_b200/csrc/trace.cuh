@@ -16,6 +16,12 @@
 #ifndef PB_PACKED_SLAB
 #define PB_PACKED_SLAB 1  /* FADD2/FMUL2 two-child slab test: +2-3% on B200 (tools/trace_ab3.py), bit-identical */
 #endif
+#ifndef PB_LEAN_SELECT
+#define PB_LEAN_SELECT 1  /* failed slab test folded into tmin = +inf, near child by (negmask >> axis): +3-4% on B200, bit-identical (gpurun_out/ab1.log) */
+#endif
+#ifndef PB_PREFETCH_FAR
+#define PB_PREFETCH_FAR 0
+#endif
 #include "scene.cuh"
 #include "vecmath.cuh"
 
@@ -243,6 +249,7 @@ struct TravRay {
     int sp;
     int kx, ky, kz;
     bool ngx, ngy, ngz, found;
+    uint32_t negmask;   // bit a set: the direction is negative along axis a
     bool nan_possible;  // a zero direction component: 0 * inf can appear in the slab test
     RayHit hit;
     // Inside an instanced object (INST kernels only): the instance being walked, whether it produced a hit, and the world
@@ -263,6 +270,7 @@ PB_D void trav_set_ray(TravRay& r, f3 o, f3 d) {
     r.o = o; r.d = d;
     r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     r.ngx = r.inv.x < 0.0f; r.ngy = r.inv.y < 0.0f; r.ngz = r.inv.z < 0.0f;
+    r.negmask = (r.ngx ? 1u : 0u) | (r.ngy ? 2u : 0u) | (r.ngz ? 4u : 0u);
     r.nan_possible = (d.x == 0.0f) || (d.y == 0.0f) || (d.z == 0.0f);
 #if PB_PACKED_SLAB
     r.nox = make_float2(-o.x, -o.x); r.noy = make_float2(-o.y, -o.y); r.noz = make_float2(-o.z, -o.z);
@@ -357,6 +365,17 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
 #endif
             }
             // near child = second child when the ray is negative along the split axis (bvh.rs:743-751)
+#if PB_LEAN_SELECT
+            // a failed slab test becomes tmin = +inf: `tmin < t_max` is then false at the visit and at every later pop, which is
+            // all the reference ever asks of that box (an entry whose true tmin is +inf can never pass either)
+            tmin0 = ok0 ? tmin0 : PB_INF; tmin1 = ok1 ? tmin1 : PB_INF;
+            bool second_first = (r.negmask >> axis) & 1u;
+            uint32_t nref = second_first ? ref1 : ref0, fref = second_first ? ref0 : ref1;
+            float ntmin = second_first ? tmin1 : tmin0, ftmin = second_first ? tmin0 : tmin1;
+            bool nhit = ntmin < r.t_max;
+            bool fhit = ftmin < r.t_max;
+            bool fok = ANY ? fhit : (ftmin < PB_INF);
+#else
             bool second_first = (axis == 0) ? r.ngx : ((axis == 1) ? r.ngy : r.ngz);
             uint32_t nref = second_first ? ref1 : ref0, fref = second_first ? ref0 : ref1;
             float ntmin = second_first ? tmin1 : tmin0, ftmin = second_first ? tmin0 : tmin1;
@@ -365,8 +384,17 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
             // the far child's `tmin < t_max` is re-checked at pop time for closest-hit rays
             // (t_max may have changed by then); for any-hit rays t_max is constant
             bool fhit = fok && (ftmin < r.t_max);
+#endif
             if (nhit) {
-                if (ANY ? fhit : fok) { stack[r.sp] = make_uint2(fref, __float_as_uint(ftmin)); ++r.sp; }
+                if (ANY ? fhit : fok) {
+                    stack[r.sp] = make_uint2(fref, __float_as_uint(ftmin)); ++r.sp;
+#if PB_PREFETCH_FAR
+                    {
+                        const void* pf = (fref & PB_LEAF_BIT) ? (const void*)(s.tris + 3ull * (fref & ~PB_LEAF_BIT)) : (const void*)(s.nodes + 4ull * fref);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    }
+#endif
+                }
                 r.cur = nref;
             } else if (fhit) {
                 r.cur = fref;

@@ -61,6 +61,8 @@ def run(rays, anyhit, reps=10):
 
 configs = [(f"refill<{rb} interior_min {im}", {1: rb, 4: im}) for rb in (24,) for im in (0, 4, 8, 12, 16, 20, 24)]
 configs += [(f"refill<{rb} interior_min {im}", {1: rb, 4: im}) for rb in (16, 28) for im in (0, 12)]
+if os.environ.get("AB_QUICK"):
+    configs = [("default (refill<24 interior_min 16)", {1: 24, 4: 16})] * int(os.environ["AB_QUICK"])
 for name, tune in configs:
     for k, v in {0: 0, 1: 24, 2: 32, 3: 0, 4: 0, **tune}.items(): lib.pbrt_b200_debug_tune(k, v)
     out = []
