@@ -193,13 +193,21 @@ typedef struct pbrt_b200_sampler {
 
 enum { PBRT_B200_LIGHTS_UNIFORM = 0, PBRT_B200_LIGHTS_POWER = 1, PBRT_B200_LIGHTS_SPATIAL = 2 };
 
-/* = PathIntegrator (src/integrators/path.rs:32-40,228-249).                  */
+/* Which SamplerIntegrator drives the kernels (api.rs:276-289): `Integrator "path"` (src/integrators/path.rs),
+ * `"directlighting"` (src/integrators/directlighting.rs, strategy "one" or "all") or `"whitted"`
+ * (src/integrators/whitted.rs).  0 = path keeps descriptors written before the field existed valid.         */
+enum { PBRT_B200_INTEGRATOR_PATH = 0, PBRT_B200_INTEGRATOR_DIRECT_ONE = 1, PBRT_B200_INTEGRATOR_DIRECT_ALL = 2,
+       PBRT_B200_INTEGRATOR_WHITTED = 3 };
+
+/* = PathIntegrator (src/integrators/path.rs:32-40,228-249); max_depth and pixel_bounds mean the same for
+ * DirectLightingIntegrator (directlighting.rs:27-39,122-157) and WhittedIntegrator (whitted.rs), which ignore
+ * rr_threshold and light_sample_strategy.                                                                  */
 typedef struct pbrt_b200_integrator {
     int32_t  max_depth;
     float    rr_threshold;
     int32_t  pixel_bounds[4];
     uint32_t light_sample_strategy;
-    uint32_t pad;
+    uint32_t kind;                   /* PBRT_B200_INTEGRATOR_*                        */
 } pbrt_b200_integrator;
 
 /* Flattened Scene (src/core/scene.rs:23-29 + what hangs off it).              */

@@ -155,7 +155,7 @@ struct TrowbridgeReitz {
 };
 
 // ---- BxDFs (closed set reachable from the five hot materials)
-enum BxKind { BX_LAMBERT, BX_OREN_NAYAR, BX_SPEC_REFL_NOOP, BX_FRESNEL_SPECULAR, BX_MICRO_REFL, BX_MICRO_TRANS };
+enum BxKind { BX_LAMBERT, BX_OREN_NAYAR, BX_SPEC_REFL_NOOP, BX_FRESNEL_SPECULAR, BX_MICRO_REFL, BX_MICRO_TRANS, BX_SPEC_REFL, BX_SPEC_TRANS };
 enum FresnelKind { FR_DIELECTRIC, FR_CONDUCTOR };
 
 struct BxDF {
@@ -190,7 +190,7 @@ struct BxDF {
                 else { sin_alpha = sin_thetai; tan_beta = sin_thetao / abs_cos_theta(wo); }
                 return r * INV_PI * (A + B * max_cos * sin_alpha * tan_beta);
             }
-            case BX_SPEC_REFL_NOOP: return Spectrum(0.0f);     // reflection.rs:630-632
+            case BX_SPEC_REFL_NOOP: case BX_SPEC_REFL: case BX_SPEC_TRANS: return Spectrum(0.0f);  // reflection.rs:630-632, 682-684
             case BX_FRESNEL_SPECULAR: return Spectrum(1.0f);   // reflection.rs:745-747 (quirk a-Q3)
             case BX_MICRO_REFL: {                               // reflection.rs:985-1003
                 Float cos_thetao = abs_cos_theta(wo), cos_thetai = abs_cos_theta(wi);
@@ -225,7 +225,7 @@ struct BxDF {
         switch (kind) {
             case BX_LAMBERT: case BX_OREN_NAYAR: case BX_FRESNEL_SPECULAR:  // reflection.rs:438-445, 788-794
                 return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI : 0.0f;
-            case BX_SPEC_REFL_NOOP: return 0.0f;
+            case BX_SPEC_REFL_NOOP: case BX_SPEC_REFL: case BX_SPEC_TRANS: return 0.0f;  // reflection.rs:642-644, 710-712
             case BX_MICRO_REFL: {  // reflection.rs:1021-1027
                 if (!same_hemisphere(wo, wi)) return 0.0f;
                 V3 wh = normalize(wo + wi);
@@ -258,6 +258,20 @@ struct BxDF {
                 *wi = V3(-wo.x, -wo.y, wo.z);
                 *pdf_ = 1.0f;
                 return Spectrum(1.0f) * r / abs_cos_theta(*wi);
+            }
+            case BX_SPEC_REFL: {  // reflection.rs:634-640 with FresnelDielectric (glass without allow_multiple_lobes)
+                *wi = V3(-wo.x, -wo.y, wo.z);
+                *pdf_ = 1.0f;
+                return fresnel_eval(cos_theta(*wi)) * r / abs_cos_theta(*wi);
+            }
+            case BX_SPEC_TRANS: {  // reflection.rs:686-708, mode = Radiance
+                Float etai, etat;
+                if (cos_theta(wo) > 0.0f) { etai = etaa; etat = etab; } else { etai = etab; etat = etaa; }
+                if (!refract(wo, face_forward(V3(0, 0, 1), wo), etai / etat, wi)) return Spectrum(0.0f);
+                *pdf_ = 1.0f;
+                Spectrum ft = t * (Spectrum(1.0f) - Spectrum(fr_dielectric(cos_theta(*wi), etaa, etab)));
+                ft = ft * ((etai * etai) / (etat * etat));
+                return ft / abs_cos_theta(*wi);
             }
             case BX_FRESNEL_SPECULAR: {  // reflection.rs:749-786
                 Float F = fr_dielectric(cos_theta(wo), etaa, etab);
@@ -372,8 +386,9 @@ struct BSDF {
 };
 
 // ---- Material::compute_scattering_functions for the five hot materials (constant textures,
-// no bump map, mode = Radiance, allow_multiple_lobes = true as passed by path.rs:123).
-inline void compute_scattering_functions(const pbrt_b200_material& m, const SurfaceInteraction& si, BSDF* bsdf) {
+// no bump map, mode = Radiance; allow_multiple_lobes = true as passed by path.rs:123, false from whitted.rs:75 and
+// directlighting.rs:90 -- only glass looks at it).
+inline void compute_scattering_functions(const pbrt_b200_material& m, const SurfaceInteraction& si, BSDF* bsdf, bool allow_multiple_lobes = true) {
     bsdf->valid = false;
     switch (m.type) {
         case PBRT_B200_MAT_MATTE: {  // matte.rs:28-52
@@ -421,7 +436,7 @@ inline void compute_scattering_functions(const pbrt_b200_material& m, const Surf
             if (R.is_black() && T.is_black()) return;  // si.bsdf stays None (quirk a-Q4)
             bsdf->init(si, eta);
             bool is_specular = urough == 0.0f && vrough == 0.0f;
-            if (is_specular) {
+            if (is_specular && allow_multiple_lobes) {
                 BxDF b; b.kind = BX_FRESNEL_SPECULAR; b.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
                 b.r = R; b.t = T; b.etaa = 1.0f; b.etab = eta;
                 bsdf->add(b);
@@ -431,10 +446,12 @@ inline void compute_scattering_functions(const pbrt_b200_material& m, const Surf
                 if (!R.is_black()) {
                     BxDF b; b.kind = BX_MICRO_REFL; b.type = BSDF_REFLECTION | BSDF_GLOSSY; b.r = R; b.distrib = distrib;
                     b.fresnel = FR_DIELECTRIC; b.fr_etai = 1.0f; b.fr_etat = eta;
+                    if (is_specular) { b.kind = BX_SPEC_REFL; b.type = BSDF_REFLECTION | BSDF_SPECULAR; }  // glass.rs:69-74
                     bsdf->add(b);
                 }
                 if (!T.is_black()) {
                     BxDF b; b.kind = BX_MICRO_TRANS; b.type = BSDF_TRANSMISSION | BSDF_GLOSSY; b.t = T; b.distrib = distrib; b.etaa = 1.0f; b.etab = eta;
+                    if (is_specular) { b.kind = BX_SPEC_TRANS; b.type = BSDF_TRANSMISSION | BSDF_SPECULAR; }  // glass.rs:79-84
                     bsdf->add(b);
                 }
             }

@@ -354,6 +354,8 @@ struct SpatialLightDistribution {
 };
 
 struct IntegratorParams {
+    int kind = PBRT_B200_INTEGRATOR_PATH;
+    std::vector<int> nlight_samples;  // DirectLightingIntegrator::preprocess, directlighting.rs:61-76
     int max_depth = 5;
     Float rr_threshold = 1.0f;
     int pixel_bounds[4];
@@ -484,6 +486,90 @@ inline void film_add_sample(const pbrt_b200_film& film, P2 pfilm, Spectrum L, Fl
     }
 }
 
+// uniform_sample_all_lights, src/core/integrator.rs:40-79 (handle_media = false).  Every light of the reference's
+// flattened scene reports nsamples() == 1 across this ABI (pbrt_b200_light carries no sample count; host.py rejects
+// "samples" != 1), so nlight_samples[j] = round_count(1) = 1.
+inline Spectrum uniform_sample_all_lights(const RenderScene& s, const SurfaceInteraction& it, const BSDF& bsdf, Sampler& sampler,
+                                          const std::vector<int>& nlight_samples, RenderCounters& rc) {
+    Spectrum L(0.0f);
+    std::vector<P2> larray, sarray;
+    for (size_t j = 0; j < s.d.n_lights; ++j) {
+        int nsamples = nlight_samples[j];
+        bool have_l = sampler.get_2d_array(nsamples, &larray);
+        bool have_s = sampler.get_2d_array(nsamples, &sarray);
+        if (!have_l || !have_s) {
+            P2 ulight = sampler.get_2d();
+            P2 uscattering = sampler.get_2d();
+            L += estimate_direct(s, it, bsdf, uscattering, (int)j, ulight, rc);
+        } else {
+            Spectrum Ld(0.0f);
+            for (int k = 0; k < nsamples; ++k) Ld += estimate_direct(s, it, bsdf, sarray[k], (int)j, larray[k], rc);
+            L += Ld / (Float)nsamples;
+        }
+    }
+    return L;
+}
+
+// DirectLightingIntegrator::li (directlighting.rs:78-119) and WhittedIntegrator::li (whitted.rs:52-105) with
+// SamplerIntegrator::specular_reflect / specular_transmit (integrator.rs:409-520; the ray differentials they build only
+// feed texture filtering, which this path does not have).
+inline Spectrum recursive_li(const RenderScene& s, const IntegratorParams& ip, Ray ray, Sampler& sampler, RenderCounters& rc, int depth) {
+    Spectrum L(0.0f);
+    Hit h;
+    Ray r0 = ray;
+    rc.intersection_tests++;
+    if (!scene_intersect(s, ray, &h, &rc.trav_closest)) {
+        for (size_t li = 0; li < s.d.n_lights; ++li) L += light_le(s, (int)li);  // every light's le(): non-zero for infinite lights only
+        return L;
+    }
+    SurfaceInteraction isect = make_interaction(s, r0, h);
+    BSDF bsdf;
+    int mat = s.d.prims[h.slot].material;
+    if (mat >= 0) compute_scattering_functions(s.d.materials[mat], isect, &bsdf, false);
+    if (!bsdf.valid) return recursive_li(s, ip, spawn_ray(isect.p, isect.p_error, isect.n, ray.d, isect.time), sampler, rc, depth);
+    V3 wo = isect.wo;
+    L += surface_le(s, isect, wo);
+    if (ip.kind == PBRT_B200_INTEGRATOR_WHITTED) {
+        InteractionData ref; ref.p = isect.p; ref.p_error = isect.p_error; ref.n = isect.n; ref.time = isect.time;
+        for (size_t li = 0; li < s.d.n_lights; ++li) {  // whitted.rs:85-97
+            LightSample ls = light_sample_li(s, (int)li, ref, sampler.get_2d());
+            if (ls.Li.is_black() || ls.pdf == 0.0f) continue;
+            Spectrum f = bsdf.f(wo, ls.wi, BSDF_ALL);
+            if (!f.is_black()) {
+                rc.shadow_tests++;
+                Ray sh = spawn_ray_to(ref, ls.p1);
+                if (!scene_intersect_p(s, sh, &rc.trav_any)) L += f * ls.Li * abs_dot(ls.wi, isect.n) / ls.pdf;
+            }
+        }
+    } else if (s.d.n_lights > 0) {
+        if (ip.kind == PBRT_B200_INTEGRATOR_DIRECT_ALL) L += uniform_sample_all_lights(s, isect, bsdf, sampler, ip.nlight_samples, rc);
+        else {  // uniform_sample_onelight with no distribution: light_num = min(u * n, n - 1), pdf 1/n (integrator.rs:88-97)
+            size_t nl = s.d.n_lights;
+            Float u = sampler.get_1d();
+            size_t ln = std::min((size_t)f2u_sat(u * (Float)nl), nl - 1);
+            Float lightpdf = 1.0f / (Float)nl;
+            P2 ulight = sampler.get_2d();
+            P2 uscattering = sampler.get_2d();
+            L += estimate_direct(s, isect, bsdf, uscattering, (int)ln, ulight, rc) / lightpdf;
+        }
+    }
+    if (depth + 1 < ip.max_depth) {
+        for (int pass = 0; pass < 2; ++pass) {  // specular_reflect, then specular_transmit
+            V3 wi;
+            Float pdf = 0.0f;
+            int st = 0;
+            Spectrum f = bsdf.sample_f(wo, &wi, sampler.get_2d(), &pdf, (pass == 0 ? BSDF_REFLECTION : BSDF_TRANSMISSION) | BSDF_SPECULAR, &st);
+            if (pdf > 0.0f && !f.is_black() && abs_dot(wi, isect.sh_n) != 0.0f) {
+                Ray rd = spawn_ray(isect.p, isect.p_error, isect.n, wi, isect.time);
+                Spectrum Li = recursive_li(s, ip, rd, sampler, rc, depth + 1);
+                if (pass == 0) L += f * Li * abs_dot(wi, isect.sh_n) / pdf;
+                else L += f * Li * (abs_dot(wi, isect.sh_n) / pdf);
+            }
+        }
+    }
+    return L;
+}
+
 struct RenderJob {
     RenderScene scene;
     pbrt_b200_render_desc rd;
@@ -498,6 +584,7 @@ inline void setup_job(RenderJob& job, const pbrt_b200_scene_desc& sdesc, const p
     job.rd = rd;
     job.tables.sobol32 = rd.sampler.sobol_matrices32; job.tables.vdc = rd.sampler.vdc_matrices; job.tables.vdc_inv = rd.sampler.vdc_matrices_inv;
     job.ip.max_depth = rd.integrator.max_depth; job.ip.rr_threshold = rd.integrator.rr_threshold;
+    job.ip.kind = (int)rd.integrator.kind;
     for (int i = 0; i < 4; ++i) job.ip.pixel_bounds[i] = rd.integrator.pixel_bounds[i];
     // create_light_sample_distribution, lightdistrib.rs:20-31
     size_t nl = sdesc.n_lights;
@@ -526,6 +613,12 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
     auto worker = [&](int tid) {
         RenderCounters& rc = rcs[tid];
         std::unique_ptr<Sampler> base = make_sampler(rd.sampler, job.tables);
+        IntegratorParams ipl = job.ip;
+        if (ipl.kind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {  // DirectLightingIntegrator::preprocess, directlighting.rs:61-76
+            for (size_t j = 0; j < job.scene.d.n_lights; ++j) ipl.nlight_samples.push_back(base->round_count(1));
+            for (int i = 0; i < ipl.max_depth; ++i)
+                for (size_t j = 0; j < job.scene.d.n_lights; ++j) { base->request_2d_array(ipl.nlight_samples[j]); base->request_2d_array(ipl.nlight_samples[j]); }
+        }
         std::vector<double> local;
         for (;;) {
             uint32_t tile = next.fetch_add(1);
@@ -552,7 +645,7 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
                         CameraSample cs = ts->get_camera_sample(x, y);
                         Ray ray = generate_ray(rd.camera, cs);
                         rc.camera_rays++;
-                        Spectrum L = path_li(job.scene, job.ip, ray, *ts, rc);
+                        Spectrum L = ipl.kind == PBRT_B200_INTEGRATOR_PATH ? path_li(job.scene, ipl, ray, *ts, rc) : recursive_li(job.scene, ipl, ray, *ts, rc, 0);
                         if (L.has_nans()) L = Spectrum(0.0f);                 // integrator.rs:350-368
                         else if (L.y() < -1.0e-5f) L = Spectrum(0.0f);
                         else if (std::isinf(L.y())) L = Spectrum(0.0f);

@@ -3,6 +3,7 @@
 #pragma once
 #include <vector>
 #include <memory>
+#include <stdexcept>
 #include "oracle_math.hpp"
 #include "../include/pbrt_b200.h"
 
@@ -103,12 +104,15 @@ struct SamplerTables {
     const uint64_t* vdc_inv = nullptr;
 };
 
-// ---- Sampler trait, src/core/sampler.rs:24-42 (array requests unused by PathIntegrator)
+// ---- Sampler trait, src/core/sampler.rs:24-42 (2D sample arrays: DirectLightingIntegrator "all", directlighting.rs:61-76)
 struct Sampler {
     uint64_t samples_per_pixel = 1;
     int px = 0, py = 0;  // current_pixel
     uint64_t current_pixel_sample_index = 0;
     virtual ~Sampler() {}
+    virtual int round_count(int n) const { return n; }                                   // sampler.rs:34
+    virtual void request_2d_array(int) { throw std::runtime_error("oracle: sample arrays are only restated for the global samplers (sobol, halton)"); }
+    virtual bool get_2d_array(int, std::vector<P2>*) { return false; }                  // None: no arrays were requested
     virtual void start_pixel(int x, int y) = 0;
     virtual Float get_1d() = 0;
     virtual P2 get_2d() = 0;
@@ -132,23 +136,46 @@ struct GlobalSampler : Sampler {
     uint64_t interval_sample_index = 0;
     static const size_t ARRAY_START_DIM = 5;
     size_t array_end_dim = 5;
+    std::vector<int> samples_2d_array_sizes;  // request_2d_array, sampler.rs:116-124
+    size_t array_2d_offset = 0;
     virtual uint64_t get_index_for_sample(uint64_t sample_num) = 0;
     virtual Float sample_dimension(uint64_t index, size_t dim) const = 0;
+    void request_2d_array(int n) override { samples_2d_array_sizes.push_back(n); }
+    // get_2d_array, sampler.rs:149-166.  global_start_pixel! (sampler.rs:268-303) fills every array for every sample of the
+    // pixel up front: element j of array i is sample_dimension(get_index_for_sample(j), 5 + 2i [+1]) -- a pure function of
+    // (pixel, j, i), so it is evaluated here when it is asked for; the values are the same.
+    bool get_2d_array(int n, std::vector<P2>* out) override {
+        if (array_2d_offset == samples_2d_array_sizes.size()) return false;
+        if (samples_2d_array_sizes[array_2d_offset] != n) throw std::runtime_error("oracle: get_2d_array size mismatch (the reference asserts)");
+        size_t dim = ARRAY_START_DIM + 2 * array_2d_offset;
+        out->resize(n);
+        for (int k = 0; k < n; ++k) {
+            uint64_t idx = get_index_for_sample(current_pixel_sample_index * (uint64_t)n + (uint64_t)k);
+            Float y = sample_dimension(idx, dim + 1);
+            Float x = sample_dimension(idx, dim);
+            (*out)[k] = P2(x, y);
+        }
+        array_2d_offset += 1;
+        return true;
+    }
     void start_pixel(int x, int y) override {
         px = x; py = y; current_pixel_sample_index = 0;
+        array_2d_offset = 0;
         dimension = 0;
         interval_sample_index = get_index_for_sample(0);
-        array_end_dim = ARRAY_START_DIM;
+        array_end_dim = ARRAY_START_DIM + 2 * samples_2d_array_sizes.size();
     }
     bool start_next_sample() override {
         dimension = 0;
         interval_sample_index = get_index_for_sample(current_pixel_sample_index + 1);
+        array_2d_offset = 0;
         current_pixel_sample_index += 1;
         return current_pixel_sample_index < samples_per_pixel;
     }
     bool set_sample_number(uint64_t n) override {
         dimension = 0;
         interval_sample_index = get_index_for_sample(n);
+        array_2d_offset = 0;
         current_pixel_sample_index = n;
         return current_pixel_sample_index < samples_per_pixel;
     }

@@ -92,6 +92,7 @@ class API:
         ro["accelerator"], ro["integrator"], ro["camera"] = ("bvh", PS.ParamSet()), ("path", PS.ParamSet()), ("perspective", PS.ParamSet())
         ro["camera_to_world"] = Transform()
         self.have_scattering_media = False
+        self._max_light_samples = 1
 
     def _error(self, msg):  # the reference logs with `error!` and carries on
         self.errors.append(msg)
@@ -351,7 +352,7 @@ class API:
         elif name in ("infinite", "exinfinite"):  # infinite.rs:243-262
             if params.find_one_filename("mapname", ""):
                 raise B200Error("image-mapped infinite lights are outside the hot path (SURVEY.md §8 f3)")
-            params.find_one_int("nsamples", 1), params.find_one_int("samples", 1)
+            self._max_light_samples = max(self._max_light_samples, params.find_one_int("samples", params.find_one_int("nsamples", 1)))
             b.light_source("infinite", L=params.find_one_spectrum("L", one), scale=params.find_one_spectrum("scale", one))
         elif name in ("goniometric", "projection"):
             raise B200Error(f'LightSource "{name}" is outside the hot path (point, spot, distant, infinite, diffuse area)')
@@ -383,7 +384,7 @@ class API:
             ap = self.gs.area_light_params
             if self.gs.area_light in ("area", "diffuse"):  # diffuse.rs:178-196
                 L = (ap.find_one_spectrum("L", f32(1.0)) * ap.find_one_spectrum("scale", f32(1.0))).astype(f32)
-                ap.find_one_int("nsamples", 1), ap.find_one_int("samples", 1)
+                self._max_light_samples = max(self._max_light_samples, ap.find_one_int("samples", ap.find_one_int("nsamples", 1)))
                 two = ap.find_one_bool("twosided", False)
                 if b._cur_object is not None:
                     warnings.warn("Area lights not supported with object instancing")  # api.rs:1604-1606: the light is dropped
@@ -581,11 +582,11 @@ class API:
         camera = self._make_camera(film)
         sampler = self._make_sampler()
         name, p = self.ro["integrator"]
-        if name != "path":
+        if name not in ("path", "directlighting", "whitted"):
             if name in KNOWN_INTEGRATORS:
-                raise B200Error(f'Integrator "{name}" is outside the hot path ("path"; SURVEY.md §8 f4 lists directlighting / whitted / volpath next)')
+                raise B200Error(f'Integrator "{name}" is outside the device path ("path", "directlighting", "whitted"; SURVEY.md §8 f4 lists volpath next)')
             raise B200Error(f'Integrator "{name}" unknown.')
-        maxdepth = p.find_one_int("maxdepth", 5)  # path.rs:225-253
+        maxdepth = p.find_one_int("maxdepth", 5)  # path.rs:225-253, directlighting.rs:125, whitted.rs:111
         pb = p.find_int("pixelbounds")
         pixelbounds = None
         if pb is not None:
@@ -593,10 +594,22 @@ class API:
                 self._error(f'Expected four values for "pixelbounds" parameter. Got {len(pb)}.')
             else:
                 pixelbounds = tuple(int(v) for v in pb)
-        rr = float(p.find_one_float("rrthreshold", 1.0))
-        strategy = p.find_one_string("lightsamplestrategy", "spatial")
+        if name == "path":
+            rr = float(p.find_one_float("rrthreshold", 1.0))
+            strategy = p.find_one_string("lightsamplestrategy", "spatial")
+            integ = H.PathIntegrator(camera, film, sampler, maxdepth=maxdepth, rrthreshold=rr, lightsamplestrategy=strategy, pixelbounds=pixelbounds)
+        elif name == "directlighting":  # directlighting.rs:146-156
+            st = p.find_one_string("strategy", "all")
+            if st not in ("one", "all"):
+                warnings.warn(f'Strategy "{st}" for direct lighting unknown. Using "all".')
+                st = "all"
+            if st == "all" and self._max_light_samples != 1:
+                raise B200Error('directlighting "all" with area / infinite lights asking for more than one sample ("samples" / "nsamples") is not '
+                                "carried across the C ABI (pbrt_b200_light has no sample count)")
+            integ = H.DirectLightingIntegrator(camera, film, sampler, maxdepth=maxdepth, strategy=st, pixelbounds=pixelbounds)
+        else:
+            integ = H.WhittedIntegrator(camera, film, sampler, maxdepth=maxdepth, pixelbounds=pixelbounds)
         p.report_unused()
-        integ = H.PathIntegrator(camera, film, sampler, maxdepth=maxdepth, rrthreshold=rr, lightsamplestrategy=strategy, pixelbounds=pixelbounds)
         if pixelbounds is not None and (integ.pixel_bounds[2] <= integ.pixel_bounds[0] or integ.pixel_bounds[3] <= integ.pixel_bounds[1]):
             self._error('Degenerate "pixelbounds" specified.')
         aname, ap = self.ro["accelerator"]  # make_accelerator, api.rs:807-819 + bvh.rs:913-930

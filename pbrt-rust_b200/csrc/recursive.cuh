@@ -1,0 +1,314 @@
+// WhittedIntegrator::li (src/integrators/whitted.rs:52-105) and DirectLightingIntegrator::li
+// (src/integrators/directlighting.rs:78-119) as wavefront kernels on the PathIntegrator's queues.
+// Included by render.cu after the path kernels; everything it calls (surface_at_hit, material_bsdf, light_sample_li,
+// trace_queue, film, k_finish_regen) is the path integrator's.
+//
+// Both integrators recurse: `li` calls `specular_reflect` and then `specular_transmit` (integrator.rs:409-520), each of
+// which draws a 2D sample and may call `li` again one level deeper.  A Sobol' / Halton sampler hands out dimensions in
+// call order, so the numbers a radiance evaluation sees depend on everything evaluated before it for the same camera
+// sample.  The recursion is therefore run depth-first per camera sample, one ray at a time: a path slot owns a small
+// stack of pending `specular_transmit` calls (ray and weight are fixed when the parent surface is shaded -- a specular
+// lobe ignores its 2D sample -- but the sample's two dimensions are only consumed when the frame is popped, which is
+// when the reference draws them).  Radiance is linear in the recursion, so each frame carries the product of the
+// f * |cos| / pdf factors above it and adds straight into the camera sample's L.
+//
+// Direct lighting produces up to `entries_per_slot` shadow rays (and MIS rays) per shaded surface; they go to global
+// entry arrays {ray, weight, slot} appended with one atomic each, are traced by the any-hit / closest-hit queue
+// kernels, and add into L with float atomics (several entries of one slot can finish at the same time).
+#pragma once
+
+namespace pb {
+
+PB_D void rec_atomic_add(float4* L, uint32_t slot, rgb v) {
+    float* p = reinterpret_cast<float*>(L + slot);
+    if (v.r != 0.0f) atomicAdd(p, v.r);
+    if (v.g != 0.0f) atomicAdd(p + 1, v.g);
+    if (v.b != 0.0f) atomicAdd(p + 2, v.b);
+}
+
+// GlobalSampler::get_1d / get_2d with the sample-array dimensions skipped (sampler.rs:322-353)
+PB_D float rec_get_1d(const RenderDev& R, SampleCursor& c) {
+    const uint32_t end = 5u + 2u * R.rec.n_arrays;
+    if (c.dim >= 5u && c.dim < end) c.dim = end;
+    float r = c.dim < 1024u || R.sampler.kind != PBRT_B200_SAMPLER_SOBOL ? sample_dimension(R.sampler, c, c.dim) : 0.5f;
+    c.dim += 1;
+    return r;
+}
+PB_D void rec_skip_2d(const RenderDev& R, SampleCursor& c) {
+    const uint32_t end = 5u + 2u * R.rec.n_arrays;
+    if (c.dim + 1u >= 5u && c.dim < end) c.dim = end;
+}
+PB_D float2 rec_get_2d(const RenderDev& R, SampleCursor& c) {
+    rec_skip_2d(R, c);
+    const bool ok = c.dim + 1u < 1024u || R.sampler.kind != PBRT_B200_SAMPLER_SOBOL;
+    float y = ok ? sample_dimension(R.sampler, c, c.dim + 1) : 0.5f;
+    float x = ok ? sample_dimension(R.sampler, c, c.dim) : 0.5f;
+    c.dim += 2;
+    return make_float2(x, y);
+}
+// Sampler::get_2d_array(1) (sampler.rs:149-166): array `arr` of a global sampler lives in dimensions 5+2*arr, 5+2*arr+1
+// and its element for pixel sample s is that sample's own index (one element per sample).
+PB_D bool rec_get_2d_array(const RenderDev& R, const SampleCursor& c, uint32_t& arr, float2* out) {
+    if (arr == R.rec.n_arrays) return false;
+    const uint32_t dim = 5u + 2u * arr;
+    float y = sample_dimension(R.sampler, c, dim + 1);
+    float x = sample_dimension(R.sampler, c, dim);
+    *out = make_float2(x, y);
+    arr += 1;
+    return true;
+}
+
+// estimate_direct (integrator.rs:109-237, handle_media = false, specular = false): the light-sampled half becomes a
+// shadow entry, the BSDF-sampled half a MIS entry; `scale` = 1 / (light selection pdf).
+template <bool INST>
+PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, const Bsdf& bsdf, uint32_t ln, float2 ulight, float2 uscatt, rgb beta,
+                              float inv_selpdf, float time) {
+    const int NONSPEC = BX_ALL & ~BX_SPECULAR;
+    const pbrt_b200_light& light = R.scene.lights[ln];
+    const bool delta = is_delta_light(light);
+    LightSample ls;
+    light_sample_li(R, ln, si.p, ulight, ls);
+    float scattpdf = 0.0f;
+    if (ls.pdf > 0.0f && !is_black(ls.Li)) {
+        rgb f = bsdf_f<KM_ALL>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
+        scattpdf = bsdf_pdf<KM_ALL>(bsdf, si.wo, ls.wi, NONSPEC);
+        if (!is_black(f)) {
+            f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
+            f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
+            rgb Ld = delta ? f * ls.Li / ls.pdf : f * ls.Li * power_heuristic(ls.pdf, scattpdf) / ls.pdf;
+            rgb add = beta * (Ld * inv_selpdf);
+            uint32_t e = atomicAdd(&R.cnt->n_shadow, 1u);
+            store_ray(R.rec.e_sh_ray, e, o, tg - o, 1.0f - PB_SHADOW_EPSILON, time);
+            R.rec.e_sh_contrib[e] = make_float4(add.r, add.g, add.b, __uint_as_float(id));
+        }
+    }
+    if (!delta) {
+        f3 wi(0.f, 0.f, 0.f);
+        int stype = 0;
+        rgb f = bsdf_sample<KM_ALL>(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
+        f = f * absdot(wi, si.sh_n);
+        if (!is_black(f) && scattpdf > 0.0f) {
+            float weight = 1.0f;
+            bool go = true;
+            if (!(stype & BX_SPECULAR)) {
+                float lpdf = light_pdf_li(R, ln, si, wi);
+                if (lpdf == 0.0f) go = false;
+                else weight = power_heuristic(scattpdf, lpdf);
+            }
+            if (go) {
+                f3 o = offset_ray_origin(si.p, si.p_error, si.n, wi);
+                rgb fac = beta * (f * weight / scattpdf * inv_selpdf);
+                uint32_t e = atomicAdd(&R.cnt->n_mis, 1u);
+                store_ray(R.rec.e_mis_ray, e, o, wi, PB_INF, time);
+                R.rec.e_mis_contrib[e] = make_float4(fac.r, fac.g, fac.b, __uint_as_float(ln));
+                R.rec.e_mis_slot[e] = id;
+            }
+        }
+    }
+}
+
+// One step of the depth-first recursion for every live camera sample: shade the hit of its current ray.
+template <bool INST>
+__global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
+    const uint32_t n = R.cnt->n_path;
+    const uint32_t* q = R.q_path[parity];
+    uint32_t* q_next = R.q_path[parity ^ 1];
+    const uint32_t nround = (n + 31u) & ~31u;
+    const uint32_t D = R.rec.stack_depth;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        bool push_next = false, push_dead = false;
+        uint32_t id = 0;
+        if (i < n) {
+            id = q[i];
+            float4 ra = R.ray[2 * id], rb = R.ray[2 * id + 1];
+            f3 ro(ra.x, ra.y, ra.z), rd(rb.x, rb.y, rb.z);
+            const float time = rb.w;
+            float4 bs = R.beta_st[id];
+            rgb beta(bs.x, bs.y, bs.z), Ladd(0.0f);
+            uint32_t depth = __float_as_uint(bs.w) & 0xffffu;
+            SampleCursor c;
+            c.index = R.s_index[id]; c.dim = R.s_dim[id];
+            const uint32_t pxy = R.pixel[id];
+            c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
+            uint32_t arr = R.rec.arr[id], sp = R.rec.sp[id];
+            const int bin = (int)R.hit_bin[id];
+            bool pop = false;
+            if (bin == Q_MISS) {
+                // every light's le(ray): non-zero for infinite lights only (whitted.rs:60-65, directlighting.rs:83-86)
+                for (uint32_t k = 0; k < R.n_infinite; ++k) Ladd = Ladd + rgb3(R.scene.lights[R.infinite_lights[k]].L) * beta;
+                pop = true;
+            } else {
+                uint4 h = R.hit[id];
+                uint32_t fl;
+                const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
+                Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
+                const pbrt_b200_prim pr = R.scene.prims[h.x];
+                Bsdf bsdf;
+                bsdf.valid = false;
+                if (pr.material >= 0) material_bsdf<-1, false>(R.scene.materials[pr.material], si, bsdf);
+                if (!bsdf.valid) {  // same depth, nothing drawn from the sampler (whitted.rs:76-80, directlighting.rs:91-94)
+                    f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
+                    store_ray(R.ray, id, o, rd, PB_INF, time);
+                    push_next = true;
+                } else {
+                    if (pr.area_light >= 0) {  // isect.le(wo)
+                        const pbrt_b200_light& al = R.scene.lights[pr.area_light];
+                        if (al.two_sided || dot(si.n, si.wo) > 0.0f) Ladd = Ladd + rgb3(al.L) * beta;
+                    }
+                    const uint32_t nl = R.n_lights;
+                    if (R.rec.kind == PBRT_B200_INTEGRATOR_WHITTED) {  // whitted.rs:85-97
+                        for (uint32_t li = 0; li < nl; ++li) {
+                            float2 u = rec_get_2d(R, c);
+                            LightSample ls;
+                            light_sample_li(R, li, si.p, u, ls);
+                            if (is_black(ls.Li) || ls.pdf == 0.0f) continue;
+                            rgb f = bsdf_f<KM_ALL>(bsdf, si.wo, ls.wi, BX_ALL);
+                            if (is_black(f)) continue;
+                            f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
+                            f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
+                            rgb add = beta * (f * ls.Li * absdot(ls.wi, si.n) / ls.pdf);
+                            uint32_t e = atomicAdd(&R.cnt->n_shadow, 1u);
+                            store_ray(R.rec.e_sh_ray, e, o, tg - o, 1.0f - PB_SHADOW_EPSILON, time);
+                            R.rec.e_sh_contrib[e] = make_float4(add.r, add.g, add.b, __uint_as_float(id));
+                        }
+                    } else if (nl > 0) {
+                        if (R.rec.kind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {  // uniform_sample_all_lights, integrator.rs:40-79
+                            for (uint32_t li = 0; li < nl; ++li) {
+                                float2 ulight, uscatt;
+                                bool hl = rec_get_2d_array(R, c, arr, &ulight);
+                                bool hs = rec_get_2d_array(R, c, arr, &uscatt);
+                                if (!hl || !hs) { ulight = rec_get_2d(R, c); uscatt = rec_get_2d(R, c); }
+                                rec_estimate_direct<INST>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f, time);
+                            }
+                        } else {  // uniform_sample_onelight without a distribution, integrator.rs:81-106
+                            float u1 = rec_get_1d(R, c);
+                            float fl1 = u1 * (float)nl;
+                            uint32_t ln = (fl1 != fl1 || fl1 <= 0.0f) ? 0u : (fl1 >= 4294967040.0f ? 0xffffffffu : (uint32_t)fl1);  // `as usize`
+                            ln = min(ln, nl - 1u);
+                            float lightpdf = 1.0f / (float)nl;
+                            float2 ulight = rec_get_2d(R, c);
+                            float2 uscatt = rec_get_2d(R, c);
+                            rec_estimate_direct<INST>(R, id, si, bsdf, ln, ulight, uscatt, beta, 1.0f / lightpdf, time);
+                        }
+                    }
+                    pop = true;
+                    if ((int)depth + 1 < R.max_depth) {
+                        // specular_reflect (integrator.rs:413-455): the 2D sample is drawn whatever the BSDF holds
+                        float2 ur = rec_get_2d(R, c);
+                        f3 wir(0.f, 0.f, 0.f), wit(0.f, 0.f, 0.f);
+                        float pdfr = 0.0f, pdft = 0.0f;
+                        int st = 0;
+                        rgb fr = bsdf_sample<KM_ALL>(bsdf, si.wo, &wir, ur, &pdfr, BX_REFLECTION | BX_SPECULAR, &st);
+                        const bool okr = pdfr > 0.0f && !is_black(fr) && absdot(wir, si.sh_n) != 0.0f;
+                        // specular_transmit (integrator.rs:457-520): a specular lobe ignores its sample, so the direction and
+                        // weight are known now; the two dimensions are drawn when the reference draws them (after the
+                        // reflection sub-tree)
+                        rgb ft = bsdf_sample<KM_ALL>(bsdf, si.wo, &wit, make_float2(0.0f, 0.0f), &pdft, BX_TRANSMISSION | BX_SPECULAR, &st);
+                        const bool okt = pdft > 0.0f && !is_black(ft) && absdot(wit, si.sh_n) != 0.0f;
+                        rgb beta_t = okt ? beta * (ft * (absdot(wit, si.sh_n) / pdft)) : rgb(0.0f);
+                        f3 ot = okt ? offset_ray_origin(si.p, si.p_error, si.n, wit) : f3(0.f, 0.f, 0.f);
+                        if (okr) {
+                            if (sp < D) {
+                                const size_t fi = (size_t)id * D + sp;
+                                R.rec.st_ray[2 * fi] = make_float4(ot.x, ot.y, ot.z, okt ? 1.0f : 0.0f);
+                                R.rec.st_ray[2 * fi + 1] = make_float4(wit.x, wit.y, wit.z, time);
+                                R.rec.st_beta[fi] = make_float4(beta_t.r, beta_t.g, beta_t.b, __uint_as_float(depth + 1u));
+                                sp += 1;
+                            }
+                            beta = beta * (fr * absdot(wir, si.sh_n) / pdfr);
+                            f3 o = offset_ray_origin(si.p, si.p_error, si.n, wir);
+                            store_ray(R.ray, id, o, wir, PB_INF, time);
+                            depth += 1;
+                            push_next = true; pop = false;
+                        } else {
+                            rec_skip_2d(R, c); c.dim += 2;  // specular_transmit's get_2d
+                            if (okt) {
+                                beta = beta_t;
+                                store_ray(R.ray, id, ot, wit, PB_INF, time);
+                                depth += 1;
+                                push_next = true; pop = false;
+                            }
+                        }
+                    }
+                }
+            }
+            if (pop) {
+                // this `li` has returned: resume the innermost pending specular_transmit
+                while (sp > 0 && !push_next) {
+                    sp -= 1;
+                    const size_t fi = (size_t)id * D + sp;
+                    float4 a = R.rec.st_ray[2 * fi], b = R.rec.st_ray[2 * fi + 1], w = R.rec.st_beta[fi];
+                    rec_skip_2d(R, c); c.dim += 2;
+                    if (a.w != 0.0f) {
+                        R.ray[2 * id] = make_float4(a.x, a.y, a.z, PB_INF);
+                        R.ray[2 * id + 1] = b;
+                        beta = rgb(w.x, w.y, w.z);
+                        depth = __float_as_uint(w.w);
+                        push_next = true;
+                    }
+                }
+                if (!push_next) push_dead = true;
+            }
+            if (!is_black(Ladd)) rec_atomic_add(R.L_eta, id, Ladd);
+            R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(depth));
+            R.s_dim[id] = c.dim;
+            R.rec.arr[id] = arr; R.rec.sp[id] = sp;
+        }
+        queue_push(q_next, &R.cnt->n_next, id, push_next);
+        queue_push(R.q_dead[parity], &R.cnt->n_dead, id, push_dead);
+    }
+}
+
+struct RecShadowJob {
+    RenderDev* R;
+    PB_D bool load(uint32_t e, f3* o, f3* d, float* t_max) const {
+        float4 a = R->rec.e_sh_ray[2 * e], b = R->rec.e_sh_ray[2 * e + 1];
+        *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
+        return true;
+    }
+    PB_D void store(uint32_t e, const TravRay& r) const {
+        if (r.found) return;
+        float4 c = R->rec.e_sh_contrib[e];
+        rec_atomic_add(R->L_eta, __float_as_uint(c.w), rgb(c.x, c.y, c.z));
+    }
+};
+template <bool INST>
+__global__ void PB_TRACE_BOUNDS k_rec_shadow(RenderDev R) {
+    RecShadowJob job{&R};
+    trace_queue<true, INST>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
+}
+
+template <bool INST>
+struct RecMisJob {
+    RenderDev* R;
+    PB_D bool load(uint32_t e, f3* o, f3* d, float* t_max) const {
+        float4 a = R->rec.e_mis_ray[2 * e], b = R->rec.e_mis_ray[2 * e + 1];
+        *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
+        return true;
+    }
+    PB_D void store(uint32_t e, const TravRay& r) const {  // integrator.rs:205-234, as MisJob::store
+        float4 c = R->rec.e_mis_contrib[e];
+        uint32_t ln = __float_as_uint(c.w);
+        rgb li(0.0f);
+        if (r.found) {
+            const pbrt_b200_prim pr = R->scene.prims[r.hit.slot];
+            if (pr.area_light == (int)ln) {
+                uint32_t fl;
+                Surf ls = surface_at_hit<INST>(R->scene, r.hit.inst, r.hit.slot, r.o, r.d, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
+                const pbrt_b200_light& al = R->scene.lights[ln];
+                if (al.two_sided || dot(ls.n, -r.d) > 0.0f) li = rgb3(al.L);
+            }
+        } else {
+            const pbrt_b200_light& l = R->scene.lights[ln];
+            if (l.type == PBRT_B200_LIGHT_INFINITE) li = rgb3(l.L);
+        }
+        if (!is_black(li)) rec_atomic_add(R->L_eta, R->rec.e_mis_slot[e], rgb(c.x * li.r, c.y * li.g, c.z * li.b));
+    }
+};
+template <bool INST>
+__global__ void PB_TRACE_BOUNDS k_rec_mis(RenderDev R) {
+    RecMisJob<INST> job{&R};
+    trace_queue<false, INST>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
+}
+
+}  // namespace pb

@@ -120,6 +120,24 @@ struct ZtDev {
     uint32_t ndims;  // n_sampled_dimensions
 };
 
+// State of the recursive integrators (recursive.cuh): per-slot stack of pending specular_transmit calls, sample-array
+// cursor, and the per-iteration shadow / MIS entry arrays.  kind == 0 (path): nothing allocated.
+struct RecDev {
+    uint32_t kind;              // PBRT_B200_INTEGRATOR_*
+    uint32_t stack_depth;       // frames per slot (= max_depth)
+    uint32_t n_arrays;          // 2D sample arrays requested by DirectLightingIntegrator::preprocess ("all"): max_depth * n_lights * 2
+    uint32_t entries_per_slot;  // shadow (and MIS) rays one shaded surface can emit
+    uint32_t* sp;               // [capacity] frames on the stack
+    uint32_t* arr;              // [capacity] Sampler::array_2d_offset
+    float4* st_ray;             // [capacity * stack_depth * 2] {o, valid}, {d, time}
+    float4* st_beta;            // [capacity * stack_depth] {weight rgb, depth bits}
+    float4* e_sh_ray;           // [capacity * entries_per_slot * 2]
+    float4* e_sh_contrib;       // {rgb, slot bits}
+    float4* e_mis_ray;
+    float4* e_mis_contrib;      // {rgb factor, light index bits}
+    uint32_t* e_mis_slot;
+};
+
 struct RenderDev {
     DevScene scene;
     pbrt_b200_camera camera;
@@ -141,6 +159,7 @@ struct RenderDev {
     uint32_t n_lights;
     SpatialDev sp;
     ZtDev zt;
+    RecDev rec;
     const InfDistrib* inf_distrib;     // indexed by light
     const uint32_t* infinite_lights;   // Scene.infinite_lights
     uint32_t n_infinite;
@@ -576,6 +595,7 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     R.s_index[slot] = c.index;
     R.s_dim[slot] = c.dim;
     R.pixel[slot] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
+    if (R.rec.kind) { R.rec.sp[slot] = 0; R.rec.arr[slot] = 0; }  // start_next_sample resets the array offsets (sampler.rs:85-92)
     return true;
 }
 
@@ -1179,6 +1199,10 @@ __global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
     trace_queue<false, INST>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
 
+}  // namespace pb
+#include "recursive.cuh"
+namespace pb {
+
 // ---------------------------------------------------------------------------
 // K8: finished paths -> film
 // ---------------------------------------------------------------------------
@@ -1725,6 +1749,12 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         if (rd->sampler.n_sampled_dimensions > 64) return fail(PBRT_B200_ERR_INVALID, "render: 02sequence dimensions too large");
     }
     if (rd->integrator.light_sample_strategy > PBRT_B200_LIGHTS_SPATIAL) return fail(PBRT_B200_ERR_INVALID, "render: unknown light_sample_strategy");
+    const uint32_t ikind = rd->integrator.kind;
+    if (ikind > PBRT_B200_INTEGRATOR_WHITTED) return fail(PBRT_B200_ERR_INVALID, "render: unknown integrator kind");
+    if (ikind != PBRT_B200_INTEGRATOR_PATH && zt)
+        return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting / whitted run with the sobol and halton samplers (the 02sequence sampler's tile-serial stream is wired to the path integrator only)");
+    if (ikind != PBRT_B200_INTEGRATOR_PATH && (rd->integrator.max_depth < 1 || rd->integrator.max_depth > 64))
+        return fail(PBRT_B200_ERR_INVALID, "render: directlighting / whitted need 1 <= maxdepth <= 64");
     PB_CUDA_TRY(cudaSetDevice(sc->device));
     int rc;
     DeviceShared* sh = device_shared(sc->device);
@@ -1764,6 +1794,14 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     capacity = (capacity + 255u) & ~255u;
     if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
     if (zt) capacity = (n_tiles_sel + 255u) & ~255u;  // tile-serial: one path slot per tile (see ZtTile)
+    // recursive integrators: per slot a stack of max_depth frames and up to `eps` shadow + MIS entries; keep that state <= 6 GB
+    const uint32_t rec_eps = ikind == PBRT_B200_INTEGRATOR_PATH ? 0u : (ikind == PBRT_B200_INTEGRATOR_DIRECT_ONE ? 1u : std::max<uint32_t>(sc->dev.n_lights, 1u));
+    const size_t rec_per_slot = ikind == PBRT_B200_INTEGRATOR_PATH ? 0 : 8 + (size_t)rd->integrator.max_depth * 48 + (size_t)rec_eps * (48 + 52);
+    if (rec_per_slot) {
+        const unsigned long long fit = (6ull << 30) / rec_per_slot;
+        if (fit < 256) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: too many lights for one whitted / directlighting \"all\" surface evaluation");
+        if (capacity > fit) capacity = (uint32_t)(fit & ~255ull);
+    }
     if (capacity == 0) capacity = 256;
     if ((rc = ensure_buffers(st, capacity))) return rc;
     lap("buffers");
@@ -1822,6 +1860,30 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         R.zt.spp = spp_eff; R.zt.ndims = (uint32_t)nd;
     }
     struct ZtRelease { void* p; size_t n; ~ZtRelease() { if (p) { cudaDeviceSynchronize(); pool_free(p, n); } } } zt_release{zt_block, zt_bytes};
+    std::memset(&R.rec, 0, sizeof R.rec);
+    void* rec_block = nullptr; size_t rec_bytes = 0;
+    if (ikind != PBRT_B200_INTEGRATOR_PATH) {
+        RecDev& rec = R.rec;
+        rec.kind = ikind; rec.stack_depth = (uint32_t)R.max_depth; rec.entries_per_slot = rec_eps;
+        if (ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {
+            // DirectLightingIntegrator::preprocess (directlighting.rs:61-76) with nsamples() == 1 for every light
+            rec.n_arrays = (uint32_t)R.max_depth * R.n_lights * 2u;
+            if (rd->sampler.kind == PBRT_B200_SAMPLER_SOBOL && 5ull + 2ull * rec.n_arrays + 8ull > 1024ull)
+                return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting \"all\" needs more Sobol' dimensions than the 1024 the tables hold (the reference panics)");
+        }
+        const size_t c = capacity, e = c * rec_eps;
+        const size_t need = Arena::padded(4 * c) * 2 + Arena::padded(32 * c * rec.stack_depth) + Arena::padded(16 * c * rec.stack_depth) + Arena::padded(32 * e) * 2 +
+                            Arena::padded(16 * e) * 2 + Arena::padded(4 * e) + 4096;
+        rec_block = pool_alloc(need, &rec_bytes);
+        if (!rec_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the recursion state");
+        Arena A; A.base = reinterpret_cast<char*>(rec_block); A.size = rec_bytes;
+        rec.sp = A.take<uint32_t>(c); rec.arr = A.take<uint32_t>(c);
+        rec.st_ray = A.take<float4>(2 * c * rec.stack_depth); rec.st_beta = A.take<float4>(c * rec.stack_depth);
+        rec.e_sh_ray = A.take<float4>(2 * e); rec.e_sh_contrib = A.take<float4>(e);
+        rec.e_mis_ray = A.take<float4>(2 * e); rec.e_mis_contrib = A.take<float4>(e); rec.e_mis_slot = A.take<uint32_t>(e);
+        if (!rec.e_mis_slot) { pool_free(rec_block, rec_bytes); return fail(PBRT_B200_ERR_CUDA, "render: recursion arena too small (internal error)"); }
+    }
+    ZtRelease rec_release{rec_block, rec_bytes};
     // film buffer: device pointer supplied, or a scratch film that is added back to the host buffer
     const size_t npix = (size_t)W * Hh;
     float4* film_dev = nullptr;
@@ -1899,7 +1961,8 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         }
         int parity = 0;
         const unsigned long long iter_cap = zt ? 256ull * spp_eff * (unsigned long long)(R.max_depth + 3) * 2ull + 4096
-                                               : (total_items / capacity + 2) * (unsigned long long)(R.max_depth + 2 + 8) * 4ull + 4096;
+                                               : (total_items / capacity + 2) * (unsigned long long)(R.max_depth + 2 + 8) * 4ull *
+                                                         (R.rec.kind ? 1ull << std::min(R.max_depth, 16) : 1ull) + 4096;  // recursive: a binary tree of rays
         const int poll = zt ? 32 : 4;  // tile-serial iterations are a few microseconds of work each
         bool done = false;
         while (!done) {
@@ -1914,6 +1977,17 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                     k_spatial_reset<<<1, 1, 0, stream>>>(R.sp);
                     launches += 3;
                 }
+                if (R.rec.kind) {  // whitted / directlighting: one generic shade kernel, entry-indexed shadow and MIS rays
+                    if (inst) k_rec_shade<true><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    else k_rec_shade<false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    if (timing) mark();
+                    if (inst) k_rec_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                    else k_rec_shadow<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                    if (timing) mark();
+                    if (inst) k_rec_mis<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                    else k_rec_mis<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                    if (timing) mark();
+                } else {
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
                 if (zt) launch_shade<true, true>(R, parity, grid_small, grid_shade, stream);
                 else if (inst) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
@@ -1925,6 +1999,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (inst) k_trace_mis<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 else k_trace_mis<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 if (timing) mark();
+                }
                 if (zt) k_finish_zt<<<grid_small, 128, 0, stream>>>(R, parity);
                 else k_finish_regen<<<grid_small, 256, 0, stream>>>(R, parity, wave_end);
                 k_iter_end<<<1, 1, 0, stream>>>(R.cnt, loop_items);

@@ -306,7 +306,8 @@ PB_D f3 tr_sample_wh(TRDist t, f3 wo, float2 u) {
 
 // ---- lobes (closed set; BxDFType bits as in reflection.rs:181-190)
 enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16, BX_ALL = 31 };
-enum LobeKind { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR = 1, LOBE_MIRROR = 2, LOBE_FRESNEL_SPECULAR = 3, LOBE_MICRO_REFL_DIEL = 4, LOBE_MICRO_REFL_COND = 5, LOBE_MICRO_TRANS = 6 };
+enum LobeKind { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR = 1, LOBE_MIRROR = 2, LOBE_FRESNEL_SPECULAR = 3, LOBE_MICRO_REFL_DIEL = 4, LOBE_MICRO_REFL_COND = 5, LOBE_MICRO_TRANS = 6,
+                LOBE_SPEC_REFL_DIEL = 7, LOBE_SPEC_TRANS = 8 };  // glass without allow_multiple_lobes (whitted / directlighting), glass.rs:69-84
 
 struct Lobe {
     int kind, type;
@@ -319,7 +320,7 @@ PB_D bool lobe_matches(const Lobe& l, int flags) { return (l.type & flags) == l.
 
 // KM = compile-time mask of the lobe kinds a material can produce (1 << LobeKind): the shade kernel of one
 // material bin carries only that material's BxDF code (smaller kernels, fewer registers); KM_ALL = generic.
-#define KM_ALL 0x7f
+#define KM_ALL 0x1ff
 #define KM_HAS(k) ((KM & (1 << (k))) != 0)
 enum { KM_MATTE = (1 << LOBE_LAMBERT) | (1 << LOBE_OREN_NAYAR), KM_PLASTIC = (1 << LOBE_LAMBERT) | (1 << LOBE_MICRO_REFL_DIEL), KM_MIRROR = 1 << LOBE_MIRROR,
        KM_GLASS = (1 << LOBE_FRESNEL_SPECULAR) | (1 << LOBE_MICRO_REFL_DIEL) | (1 << LOBE_MICRO_TRANS), KM_METAL = 1 << LOBE_MICRO_REFL_COND };
@@ -340,7 +341,7 @@ PB_D rgb lobe_f(const Lobe& l, f3 wo, f3 wi) {
             if (fabsf(wi.z) > fabsf(wo.z)) { sa = sto; tb = sti / fabsf(wi.z); } else { sa = sti; tb = sto / fabsf(wo.z); }
             return l.c0 * PB_INV_PI * (l.p0 + l.p1 * max_cos * sa * tb);
         }
-        case LOBE_MIRROR: return rgb(0.0f);
+        case LOBE_MIRROR: case LOBE_SPEC_REFL_DIEL: case LOBE_SPEC_TRANS: return rgb(0.0f);  // reflection.rs:630-632, 682-684
         case LOBE_FRESNEL_SPECULAR: return rgb(1.0f);  // reflection.rs:745-747 (reference quirk)
         case LOBE_MICRO_REFL_DIEL:
         case LOBE_MICRO_REFL_COND: {  // reflection.rs:985-1003
@@ -380,7 +381,7 @@ PB_D float lobe_pdf(const Lobe& l, f3 wo, f3 wi) {
     switch (l.kind) {
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR: case LOBE_FRESNEL_SPECULAR:
             return same_hemi(wo, wi) ? fabsf(wi.z) * PB_INV_PI : 0.0f;  // reflection.rs:438-445, 788-794
-        case LOBE_MIRROR: return 0.0f;
+        case LOBE_MIRROR: case LOBE_SPEC_REFL_DIEL: case LOBE_SPEC_TRANS: return 0.0f;
         case LOBE_MICRO_REFL_DIEL: case LOBE_MICRO_REFL_COND: {  // reflection.rs:1021-1027
             if (!KM_HAS(LOBE_MICRO_REFL_DIEL) && !KM_HAS(LOBE_MICRO_REFL_COND)) break;
             if (!same_hemi(wo, wi)) return 0.0f;
@@ -418,6 +419,22 @@ PB_D rgb lobe_sample(const Lobe& l, f3 wo, f3* wi, float2 u, float* pdf, int* st
             *wi = f3(-wo.x, -wo.y, wo.z);
             *pdf = 1.0f;
             return rgb(1.0f) * l.c0 / fabsf(wi->z);
+        }
+        case LOBE_SPEC_REFL_DIEL: {  // reflection.rs:634-640 with FresnelDielectric(1, eta)
+            if (!KM_HAS(LOBE_SPEC_REFL_DIEL)) break;
+            *wi = f3(-wo.x, -wo.y, wo.z);
+            *pdf = 1.0f;
+            return rgb(fr_dielectric(wi->z, l.p0, l.p1)) * l.c0 / fabsf(wi->z);
+        }
+        case LOBE_SPEC_TRANS: {  // reflection.rs:686-708, TransportMode::Radiance
+            if (!KM_HAS(LOBE_SPEC_TRANS)) break;
+            float etai = wo.z > 0.0f ? l.p0 : l.p1, etat = wo.z > 0.0f ? l.p1 : l.p0;
+            f3 nf = (wo.z < 0.0f) ? f3(-0.0f, -0.0f, -1.0f) : f3(0.0f, 0.0f, 1.0f);  // face_foward_vec
+            if (!refract_dir(wo, nf, etai / etat, wi)) return rgb(0.0f);
+            *pdf = 1.0f;
+            rgb ft = l.c0 * (rgb(1.0f) - rgb(fr_dielectric(wi->z, l.p0, l.p1)));
+            ft = ft * ((etai * etai) / (etat * etat));
+            return ft / fabsf(wi->z);
         }
         case LOBE_FRESNEL_SPECULAR: {  // reflection.rs:749-786
             if (!KM_HAS(LOBE_FRESNEL_SPECULAR)) break;
@@ -540,9 +557,10 @@ PB_D rgb bsdf_sample(const Bsdf& b, f3 wow, f3* wiw, float2 u, float* pdf, int f
 }
 
 // Material::compute_scattering_functions for the five hot materials (constant textures, no
-// bump, allow_multiple_lobes = true, mode = Radiance).
+// bump, mode = Radiance).  MULTI = allow_multiple_lobes: true from path.rs:123, false from whitted.rs:75 and
+// directlighting.rs:90 (only glass looks at it).
 // MAT >= 0: the material type is known at compile time (the shade kernel of that bin).
-template <int MAT = -1>
+template <int MAT = -1, bool MULTI = true>
 PB_D void material_bsdf(const pbrt_b200_material& m, const Surf& si, Bsdf& b) {
     b.valid = false; b.n = 0;
     rgb A = rgb_clamp0(rgb3(m.a)), B = rgb_clamp0(rgb3(m.b));
@@ -584,7 +602,10 @@ PB_D void material_bsdf(const pbrt_b200_material& m, const Surf& si, Bsdf& b) {
             float eta = m.f2, ur = m.f0, vr = m.f1;
             if (is_black(A) && is_black(B)) return;  // si.bsdf stays None: pass-through surface
             bsdf_init(b, si, eta);
-            if (ur == 0.0f && vr == 0.0f) {
+            if (!MULTI && ur == 0.0f && vr == 0.0f) {
+                if (!is_black(A)) { Lobe& l = b.lobe[b.n++]; l.kind = LOBE_SPEC_REFL_DIEL; l.type = BX_REFLECTION | BX_SPECULAR; l.c0 = A; l.p0 = 1.0f; l.p1 = eta; }
+                if (!is_black(B)) { Lobe& l = b.lobe[b.n++]; l.kind = LOBE_SPEC_TRANS; l.type = BX_TRANSMISSION | BX_SPECULAR; l.c0 = B; l.p0 = 1.0f; l.p1 = eta; }
+            } else if (ur == 0.0f && vr == 0.0f) {
                 Lobe& l = b.lobe[b.n++];
                 l.kind = LOBE_FRESNEL_SPECULAR; l.type = BX_REFLECTION | BX_TRANSMISSION | BX_SPECULAR; l.c0 = A; l.c1 = B; l.p0 = 1.0f; l.p1 = eta;
             } else {

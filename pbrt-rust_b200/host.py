@@ -56,6 +56,7 @@ MAT_MATTE, MAT_PLASTIC, MAT_MIRROR, MAT_GLASS, MAT_METAL = range(5)
 LIGHT_POINT, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_DIFFUSE, LIGHT_INFINITE = range(5)
 SAMPLER_SOBOL, SAMPLER_HALTON, SAMPLER_ZEROTWO = range(3)
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = range(3)
+INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED = range(4)
 SPLIT = {"sah": 0, "middle": 2, "equal": 3}
 
 
@@ -90,7 +91,7 @@ class SamplerDesc(C.Structure):
 
 class IntegratorDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4), ("light_sample_strategy", C.c_uint32),
-                ("pad", C.c_uint32)]
+                ("kind", C.c_uint32)]
 
 
 class RenderDesc(C.Structure):
@@ -882,6 +883,8 @@ class PathIntegrator:
     """PathIntegrator + create_path_integrator (src/integrators/path.rs:32-59,225-253)."""
 
     STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER, "spatial": LIGHTS_SPATIAL}
+    kind = INTEGRATOR_PATH
+    name = "path"
 
     def __init__(self, camera, film, sampler, maxdepth=5, rrthreshold=1.0, lightsamplestrategy="spatial", pixelbounds=None):
         self.camera, self.film, self.sampler = camera, film, sampler
@@ -902,6 +905,7 @@ class PathIntegrator:
         d.integrator.max_depth, d.integrator.rr_threshold = self.max_depth, self.rr_threshold
         d.integrator.pixel_bounds[:] = self.pixel_bounds
         d.integrator.light_sample_strategy = self.STRATEGY[self.light_sample_strategy]
+        d.integrator.kind = self.kind
         if tile_range:
             d.tile_begin, d.tile_end = tile_range
         if sample_range:
@@ -919,6 +923,27 @@ class PathIntegrator:
         """Integrator::render (integrator.rs:249-252) -> linear RGB image [h, w, 3]."""
         rgbw, stats = scene.render(self, **kw)
         return scene.film_resolve(rgbw, self.film.scale).reshape(self.film.height, self.film.width, 3), stats
+
+
+class DirectLightingIntegrator(PathIntegrator):
+    """DirectLightingIntegrator + create_directlighting_integrator (src/integrators/directlighting.rs:27-39,122-157)."""
+    name = "directlighting"
+
+    def __init__(self, camera, film, sampler, maxdepth=5, strategy="all", pixelbounds=None):
+        super().__init__(camera, film, sampler, maxdepth=maxdepth, lightsamplestrategy="uniform", pixelbounds=pixelbounds)
+        if strategy not in ("one", "all"):
+            strategy = "all"  # directlighting.rs:149-152: unknown strategies fall back to "all" with a warning
+        self.strategy = strategy
+        self.kind = INTEGRATOR_DIRECT_ALL if strategy == "all" else INTEGRATOR_DIRECT_ONE
+
+
+class WhittedIntegrator(PathIntegrator):
+    """WhittedIntegrator + create_whitted_integrator (src/integrators/whitted.rs:25-50,108-131)."""
+    name = "whitted"
+    kind = INTEGRATOR_WHITTED
+
+    def __init__(self, camera, film, sampler, maxdepth=5, pixelbounds=None):
+        super().__init__(camera, film, sampler, maxdepth=maxdepth, lightsamplestrategy="uniform", pixelbounds=pixelbounds)
 
 
 class Scene:

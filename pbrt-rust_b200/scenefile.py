@@ -93,11 +93,14 @@ def write_pbrt(path, flat, integrator, ply_min_vertices=64):
     if samp.kind == H.SAMPLER_ZEROTWO:
         sp += f' "integer dimensions" [{samp.dimensions}]'
     L.append(f'Sampler "{_SAMPLER_NAMES[samp.kind]}" {sp}')
-    ip = [f'"integer maxdepth" [{integrator.max_depth}]', f'"float rrthreshold" [{_num(integrator.rr_threshold)}]',
-          f'"string lightsamplestrategy" "{integrator.light_sample_strategy}"']
+    ip = [f'"integer maxdepth" [{integrator.max_depth}]']
+    if integrator.name == "path":
+        ip += [f'"float rrthreshold" [{_num(integrator.rr_threshold)}]', f'"string lightsamplestrategy" "{integrator.light_sample_strategy}"']
+    elif integrator.name == "directlighting":
+        ip.append(f'"string strategy" "{integrator.strategy}"')
     if integrator.pixelbounds_param is not None:
         ip.append('"integer pixelbounds" [%d %d %d %d]' % tuple(integrator.pixelbounds_param))
-    L.append('Integrator "path" ' + " ".join(ip))
+    L.append(f'Integrator "{integrator.name}" ' + " ".join(ip))
     split, max_prims = getattr(flat, "accelerator", ("sah", 4))
     L.append(f'Accelerator "bvh" "string splitmethod" "{split}" "integer maxnodeprims" [{max_prims}]')
     L.append("WorldBegin")

@@ -164,6 +164,23 @@ def test_written_scene_files_parse_back_bit_identically(gen, tmp_path):
     assert bytes(api.jobs[0].integrator.desc()) == bytes(integ.desc())
 
 
+def test_directlighting_and_whitted_scene_files(tmp_path):
+    setup = pkg.scenes.small_mixed_scene()
+    base = setup.make_integrator()
+    for integ in (pkg.host.WhittedIntegrator(base.camera, base.film, base.sampler, maxdepth=7),
+                  pkg.host.DirectLightingIntegrator(base.camera, base.film, base.sampler, maxdepth=3, strategy="one"),
+                  pkg.host.DirectLightingIntegrator(base.camera, base.film, base.sampler)):
+        job = pkg.pbrt_parse(SF.write_pbrt(tmp_path / (integ.name + ".pbrt"), setup.flat, integ)[0]).jobs[0]
+        assert type(job.integrator) is type(integ) and bytes(job.integrator.desc()) == bytes(integ.desc())
+        assert same_flat(job.flat, setup.flat) is None
+    # directlighting.rs:146-152: strategy defaults to "all"; area lights asking for several samples cannot cross the C ABI
+    job = pkg.pbrt_parse_string('Integrator "directlighting"\nWorldBegin\nShape "sphere"\nWorldEnd').jobs[0]
+    assert job.integrator.kind == pkg.host.INTEGRATOR_DIRECT_ALL and job.integrator.max_depth == 5
+    with pytest.raises(pkg.B200Error):
+        pkg.pbrt_parse_string('Integrator "directlighting"\nWorldBegin\nAreaLightSource "diffuse" "integer samples" [4]\n'
+                              'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd')
+
+
 def test_inline_meshes_and_ply_meshes_agree(tmp_path):
     setup = pkg.scenes.small_mixed_scene()
     integ = setup.make_integrator(sampler_="02sequence", filt="gaussian")
