@@ -175,7 +175,20 @@ struct ZeroTwoSequenceSampler : Sampler {
     std::vector<std::vector<Float>> samples_1d;
     std::vector<std::vector<P2>> samples_2d;
     size_t current_1d_dimension = 0, current_2d_dimension = 0;
+    std::vector<int> samples_2d_array_sizes;        // request_2d_array_default!, sampler.rs:116-124
+    std::vector<std::vector<P2>> sample_array_2d;
+    size_t array_2d_offset = 0;
     RNG rng;
+    int round_count(int n) const override { return (int)round_up_pow2_64(n); }  // zerotwosequence.rs:86-88
+    void request_2d_array(int n) override { samples_2d_array_sizes.push_back(n); sample_array_2d.emplace_back((size_t)n * samples_per_pixel); }
+    bool get_2d_array(int n, std::vector<P2>* out) override {  // get_2d_array_default!, sampler.rs:149-166
+        if (array_2d_offset == sample_array_2d.size()) return false;
+        if (samples_2d_array_sizes[array_2d_offset] != n) throw std::runtime_error("oracle: get_2d_array size mismatch (the reference asserts)");
+        const P2* a = sample_array_2d[array_2d_offset].data() + current_pixel_sample_index * (uint64_t)n;
+        out->assign(a, a + n);
+        array_2d_offset += 1;
+        return true;
+    }
     ZeroTwoSequenceSampler(uint64_t spp, size_t ndims) {
         samples_per_pixel = (uint64_t)round_up_pow2_64((int64_t)spp);
         for (size_t i = 0; i < ndims; ++i) { samples_1d.emplace_back(samples_per_pixel, 0.0f); samples_2d.emplace_back(samples_per_pixel); }
@@ -183,7 +196,10 @@ struct ZeroTwoSequenceSampler : Sampler {
     void start_pixel(int x, int y) override {
         for (auto& s : samples_1d) vander_corput(1, samples_per_pixel, s.data(), rng);
         for (auto& s : samples_2d) sobol_2d(1, samples_per_pixel, s.data(), rng);
+        for (size_t i = 0; i < sample_array_2d.size(); ++i)  // zerotwosequence.rs:67-71 (no 1D arrays are requested on this path)
+            sobol_2d((size_t)samples_2d_array_sizes[i], samples_per_pixel, sample_array_2d[i].data(), rng);
         px = x; py = y; current_pixel_sample_index = 0;
+        array_2d_offset = 0;
     }
     Float get_1d() override {
         if (current_1d_dimension < samples_1d.size()) return samples_1d[current_1d_dimension++][current_pixel_sample_index];
@@ -197,11 +213,13 @@ struct ZeroTwoSequenceSampler : Sampler {
     }
     bool start_next_sample() override {
         current_1d_dimension = current_2d_dimension = 0;
+        array_2d_offset = 0;
         current_pixel_sample_index += 1;
         return current_pixel_sample_index < samples_per_pixel;
     }
     bool set_sample_number(uint64_t n) override {
         current_1d_dimension = current_2d_dimension = 0;
+        array_2d_offset = 0;
         current_pixel_sample_index = n;
         return current_pixel_sample_index < samples_per_pixel;
     }

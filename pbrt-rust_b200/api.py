@@ -18,6 +18,7 @@ point light's translate(P.x, P.y, P.x) (point.rs:103); the mitchell / sinc filte
 """
 from __future__ import annotations
 
+import os
 import warnings
 
 import numpy as np
@@ -185,8 +186,6 @@ class API:
             self.named_coordinate_system["name"] = self.ro["camera_to_world"]  # sic, api.rs:1210 (pbrt-v3 says "camera")
 
     def include(self, name):  # api.rs:1198-1201
-        import os
-
         from . import pbrtparser
 
         pbrtparser.parse_file(os.path.abspath(PS.resolve_filename(name)), self)
@@ -254,10 +253,26 @@ class API:
                 table[name] = f32(tp.get_floattexture("tex1", 1.0) * tp.get_floattexture("tex2", 1.0))
             else:
                 table[name] = (tp.get_spectrumtexture("tex1", 1.0) * tp.get_spectrumtexture("tex2", 1.0)).astype(f32)
+        elif texname == "imagemap" and not os.path.isfile(tp.geo.find_one_filename("filename", "")):
+            # ImageTexture::get_texture, imagemap.rs:136-142: an image that cannot be read becomes a 1x1 grey (0.5) texture, converted
+            # like any texel (:71-98: inverse gamma for .png / .tga unless "gamma" says otherwise, times "scale") -- a constant
+            fn = tp.geo.find_one_filename("filename", "")
+            warnings.warn(f'Creating a constant grey texture to replace "{fn}".')
+            scale = tp.find_float("scale", 1.0)
+            gamma = tp.find_bool("gamma", fn.lower().endswith((".tga", ".png")))
+            g = f32(0.5)
+            if gamma:  # inverse_gamma_correct, pbrt.rs:218-222 (0.5 > 0.04045)
+                g = f32(np.power(f32(f32(g + f32(0.055)) * f32(1.0) / f32(1.055)), f32(2.4)))
+            # float textures convert the luminance of the grey texel (0.212671 + 0.715160 + 0.072169 = 1.0 in f32 here)
+            y = f32(f32(0.212671) * f32(0.5) + f32(0.715160) * f32(0.5) + f32(0.072169) * f32(0.5))
+            if ty == "float":
+                gy = f32(np.power(f32(f32(y + f32(0.055)) * f32(1.0) / f32(1.055)), f32(2.4))) if gamma else y
+                table[name] = f32(scale * gy)
+            else:
+                table[name] = np.full(3, g * scale, f32)
         else:
-            raise B200Error(f'Texture "{texname}": only constant-valued textures ("constant", "scale" of constants) exist on the device path; '
-                            "image maps and procedural textures are SURVEY.md §8 f3")
-        params.report_unused()
+            table[name] = PS.UnsupportedTexture(name, texname)  # an error when a material refers to it
+        params.looked_up.update((b, n) for b in params.BUCKETS for n in getattr(params, b))
 
     # --- materials (api.rs:595-654,1391-1460; src/materials/*.rs create_*) ----------------------------
     def _make_material(self, name, mp):

@@ -58,6 +58,39 @@ PB_D bool rec_get_2d_array(const RenderDev& R, const SampleCursor& c, uint32_t& 
     return true;
 }
 
+// The sampler as the recursion sees it: get_1d / get_2d / get_2d_array(1).  ZT = false: the global samplers above
+// (state = cursor + array offset in registers, written back by end()); ZT = true: the tile's (0,2)-sequence state in HBM
+// (PixelSampler: arrays are extra rows of the tile's 2D table, filled by start_pixel).
+template <bool ZT> struct RecSampler;
+template <> struct RecSampler<false> {
+    SampleCursor c; uint32_t arr;
+    PB_D void begin(const RenderDev& R, uint32_t id) {
+        c.index = R.s_index[id]; c.dim = R.s_dim[id];
+        const uint32_t pxy = R.pixel[id];
+        c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
+        arr = R.rec.arr[id];
+    }
+    PB_D float get_1d(const RenderDev& R) { return rec_get_1d(R, c); }
+    PB_D float2 get_2d(const RenderDev& R) { return rec_get_2d(R, c); }
+    PB_D void skip_2d(const RenderDev& R) { rec_skip_2d(R, c); c.dim += 2; }  // a get_2d whose value nobody looks at
+    PB_D bool get_2d_array(const RenderDev& R, float2* out) { return rec_get_2d_array(R, c, arr, out); }
+    PB_D void end(const RenderDev& R, uint32_t id) { R.s_dim[id] = c.dim; R.rec.arr[id] = arr; }
+};
+template <> struct RecSampler<true> {
+    ZtCursor z; uint32_t arr;
+    PB_D void begin(const RenderDev& R, uint32_t id) { z = zt_cursor(R, id); arr = R.rec.arr[id]; }  // slot == tile ordinal
+    PB_D float get_1d(const RenderDev&) { return pb::get_1d(z); }
+    PB_D float2 get_2d(const RenderDev&) { return pb::get_2d(z); }
+    PB_D void skip_2d(const RenderDev&) { (void)pb::get_2d(z); }  // the draw happens (table row or two RNG numbers)
+    PB_D bool get_2d_array(const RenderDev& R, float2* out) {
+        if (arr == R.rec.n_arrays) return false;
+        *out = z.s2d[(size_t)(z.ndims + arr) * z.spp + z.t->sample_idx];
+        arr += 1;
+        return true;
+    }
+    PB_D void end(const RenderDev& R, uint32_t id) { R.rec.arr[id] = arr; }
+};
+
 // estimate_direct (integrator.rs:109-237, handle_media = false, specular = false): the light-sampled half becomes a
 // shadow entry, the BSDF-sampled half a MIS entry; `scale` = 1 / (light selection pdf).
 template <bool INST>
@@ -108,7 +141,7 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
 }
 
 // One step of the depth-first recursion for every live camera sample: shade the hit of its current ray.
-template <bool INST>
+template <bool INST, bool ZT>
 __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_path;
     const uint32_t* q = R.q_path[parity];
@@ -126,11 +159,9 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
             float4 bs = R.beta_st[id];
             rgb beta(bs.x, bs.y, bs.z), Ladd(0.0f);
             uint32_t depth = __float_as_uint(bs.w) & 0xffffu;
-            SampleCursor c;
-            c.index = R.s_index[id]; c.dim = R.s_dim[id];
-            const uint32_t pxy = R.pixel[id];
-            c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
-            uint32_t arr = R.rec.arr[id], sp = R.rec.sp[id];
+            RecSampler<ZT> smp;
+            smp.begin(R, id);
+            uint32_t sp = R.rec.sp[id];
             const int bin = (int)R.hit_bin[id];
             bool pop = false;
             if (bin == Q_MISS) {
@@ -158,7 +189,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                     const uint32_t nl = R.n_lights;
                     if (R.rec.kind == PBRT_B200_INTEGRATOR_WHITTED) {  // whitted.rs:85-97
                         for (uint32_t li = 0; li < nl; ++li) {
-                            float2 u = rec_get_2d(R, c);
+                            float2 u = smp.get_2d(R);
                             LightSample ls;
                             light_sample_li(R, li, si.p, u, ls);
                             if (is_black(ls.Li) || ls.pdf == 0.0f) continue;
@@ -175,26 +206,26 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                         if (R.rec.kind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {  // uniform_sample_all_lights, integrator.rs:40-79
                             for (uint32_t li = 0; li < nl; ++li) {
                                 float2 ulight, uscatt;
-                                bool hl = rec_get_2d_array(R, c, arr, &ulight);
-                                bool hs = rec_get_2d_array(R, c, arr, &uscatt);
-                                if (!hl || !hs) { ulight = rec_get_2d(R, c); uscatt = rec_get_2d(R, c); }
+                                bool hl = smp.get_2d_array(R, &ulight);
+                                bool hs = smp.get_2d_array(R, &uscatt);
+                                if (!hl || !hs) { ulight = smp.get_2d(R); uscatt = smp.get_2d(R); }
                                 rec_estimate_direct<INST>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f, time);
                             }
                         } else {  // uniform_sample_onelight without a distribution, integrator.rs:81-106
-                            float u1 = rec_get_1d(R, c);
+                            float u1 = smp.get_1d(R);
                             float fl1 = u1 * (float)nl;
                             uint32_t ln = (fl1 != fl1 || fl1 <= 0.0f) ? 0u : (fl1 >= 4294967040.0f ? 0xffffffffu : (uint32_t)fl1);  // `as usize`
                             ln = min(ln, nl - 1u);
                             float lightpdf = 1.0f / (float)nl;
-                            float2 ulight = rec_get_2d(R, c);
-                            float2 uscatt = rec_get_2d(R, c);
+                            float2 ulight = smp.get_2d(R);
+                            float2 uscatt = smp.get_2d(R);
                             rec_estimate_direct<INST>(R, id, si, bsdf, ln, ulight, uscatt, beta, 1.0f / lightpdf, time);
                         }
                     }
                     pop = true;
                     if ((int)depth + 1 < R.max_depth) {
                         // specular_reflect (integrator.rs:413-455): the 2D sample is drawn whatever the BSDF holds
-                        float2 ur = rec_get_2d(R, c);
+                        float2 ur = smp.get_2d(R);
                         f3 wir(0.f, 0.f, 0.f), wit(0.f, 0.f, 0.f);
                         float pdfr = 0.0f, pdft = 0.0f;
                         int st = 0;
@@ -221,7 +252,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                             depth += 1;
                             push_next = true; pop = false;
                         } else {
-                            rec_skip_2d(R, c); c.dim += 2;  // specular_transmit's get_2d
+                            smp.skip_2d(R);  // specular_transmit's get_2d
                             if (okt) {
                                 beta = beta_t;
                                 store_ray(R.ray, id, ot, wit, PB_INF, time);
@@ -238,7 +269,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                     sp -= 1;
                     const size_t fi = (size_t)id * D + sp;
                     float4 a = R.rec.st_ray[2 * fi], b = R.rec.st_ray[2 * fi + 1], w = R.rec.st_beta[fi];
-                    rec_skip_2d(R, c); c.dim += 2;
+                    smp.skip_2d(R);
                     if (a.w != 0.0f) {
                         R.ray[2 * id] = make_float4(a.x, a.y, a.z, PB_INF);
                         R.ray[2 * id + 1] = b;
@@ -251,8 +282,8 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
             }
             if (!is_black(Ladd)) rec_atomic_add(R.L_eta, id, Ladd);
             R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(depth));
-            R.s_dim[id] = c.dim;
-            R.rec.arr[id] = arr; R.rec.sp[id] = sp;
+            smp.end(R, id);
+            R.rec.sp[id] = sp;
         }
         queue_push(q_next, &R.cnt->n_next, id, push_next);
         queue_push(R.q_dead[parity], &R.cnt->n_dead, id, push_dead);

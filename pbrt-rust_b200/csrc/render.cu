@@ -118,6 +118,8 @@ struct ZtDev {
     float2* s2d;     // [tile][dim][spp]   samples_2d
     uint32_t spp;    // rounded up to a power of two (zerotwosequence.rs:36-40)
     uint32_t ndims;  // n_sampled_dimensions
+    uint32_t n2d;    // rows of s2d per tile: ndims + the 2D sample arrays a DirectLightingIntegrator requested (one element per pixel sample:
+                     // sobol_2d(1, spp) fills them right after the 2D dimensions, zerotwosequence.rs:67-71)
 };
 
 // State of the recursive integrators (recursive.cuh): per-slot stack of pending specular_transmit calls, sample-array
@@ -362,7 +364,7 @@ PB_D void zt_set_sequence(ZtTile& t, unsigned long long seq) {  // rng.rs:66-74
 }
 // ZeroTwoSequenceSampler::start_pixel (zerotwosequence.rs:54-66): van_der_corput / sobol_2d (lowdiscrepancy.rs:486-510) with
 // one sample per pixel sample => gray-code points, one shuffle() of every 1-element block (a draw each), one shuffle of the lot
-static __device__ __noinline__ void zt_start_pixel(ZtTile* tp, float* s1d, float2* s2d, uint32_t spp, uint32_t ndims) {
+static __device__ __noinline__ void zt_start_pixel(ZtTile* tp, float* s1d, float2* s2d, uint32_t spp, uint32_t ndims, uint32_t n2d) {
     ZtTile t = *tp;
     for (uint32_t d = 0; d < ndims; ++d) {
         float* sm = s1d + (size_t)d * spp;
@@ -377,7 +379,7 @@ static __device__ __noinline__ void zt_start_pixel(ZtTile* tp, float* s1d, float
             float a = sm[i]; sm[i] = sm[other]; sm[other] = a;
         }
     }
-    for (uint32_t d = 0; d < ndims; ++d) {
+    for (uint32_t d = 0; d < n2d; ++d) {  // the 2D dimensions, then the 2D sample arrays (no 1D arrays are ever requested)
         float2* sm = s2d + (size_t)d * spp;
         uint32_t v0 = zt_u32(t), v1 = zt_u32(t);
         for (uint32_t i = 0; i < spp; ++i) {  // gray_code_sample2d with CSOBOL[0], CSOBOL[1] (lowdiscrepancy.rs:203-217)
@@ -398,13 +400,13 @@ static __device__ __noinline__ void zt_start_pixel(ZtTile* tp, float* s1d, float
     *tp = t;
 }
 // PixelSampler get_1d / get_2d, sampler.rs:228-253 (beyond the precomputed dimensions: raw draws, y before x)
-struct ZtCursor { ZtTile* t; const float* s1d; const float2* s2d; uint32_t spp, ndims; };
+struct ZtCursor { ZtTile* t; const float* s1d; const float2* s2d; uint32_t spp, ndims, n2d; };
 PB_D ZtCursor zt_cursor(const RenderDev& R, uint32_t tile_ordinal) {
     ZtCursor c;
     c.t = R.zt.tiles + tile_ordinal;
     c.s1d = R.zt.s1d + (size_t)tile_ordinal * R.zt.ndims * R.zt.spp;
-    c.s2d = R.zt.s2d + (size_t)tile_ordinal * R.zt.ndims * R.zt.spp;
-    c.spp = R.zt.spp; c.ndims = R.zt.ndims;
+    c.s2d = R.zt.s2d + (size_t)tile_ordinal * R.zt.n2d * R.zt.spp;
+    c.spp = R.zt.spp; c.ndims = R.zt.ndims; c.n2d = R.zt.n2d;
     return c;
 }
 PB_D float get_1d(ZtCursor& c) {
@@ -1249,7 +1251,7 @@ __global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, u
 PB_D bool zt_next_path(const RenderDev& R, uint32_t j, bool first) {
     ZtTile* tp = R.zt.tiles + j;
     float* s1d = R.zt.s1d + (size_t)j * R.zt.ndims * R.zt.spp;
-    float2* s2d = R.zt.s2d + (size_t)j * R.zt.ndims * R.zt.spp;
+    float2* s2d = R.zt.s2d + (size_t)j * R.zt.n2d * R.zt.spp;
     const uint32_t s_begin = R.sample_begin, s_end = R.sample_begin + R.n_samples_sel;
     bool have = false;
     if (!first) {  // start_next_sample(), sampler.rs:206-216
@@ -1260,7 +1262,7 @@ PB_D bool zt_next_path(const RenderDev& R, uint32_t j, bool first) {
     }
     while (!have) {
         if (tp->pixel_idx >= tp->npix) return false;
-        zt_start_pixel(tp, s1d, s2d, R.zt.spp, R.zt.ndims);  // every pixel of the tile, inside the pixel bounds or not (integrator.rs:322-330)
+        zt_start_pixel(tp, s1d, s2d, R.zt.spp, R.zt.ndims, R.zt.n2d);  // every pixel of the tile, inside the pixel bounds or not (integrator.rs:322-330)
         int x = tp->x0 + (int)(tp->pixel_idx % tp->w), y = tp->y0 + (int)(tp->pixel_idx / tp->w);
         bool inside = x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] && y < R.pixel_bounds[3];
         if (inside && s_begin < R.zt.spp && s_begin < s_end) { tp->sample_idx = s_begin; have = true; }  // set_sample_number
@@ -1282,6 +1284,7 @@ PB_D bool zt_next_path(const RenderDev& R, uint32_t j, bool first) {
     R.beta_st[j] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
     R.pfilm[j] = pfilm;
     R.pixel[j] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
+    if (R.rec.kind) { R.rec.sp[j] = 0; R.rec.arr[j] = 0; }
     return true;
 }
 // tile j of the call -> tile number, clipped bounds, generator (sampler.clone(seed = tile.y * ntiles.x + tile.x), integrator.rs:302-303)
@@ -1751,8 +1754,6 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (rd->integrator.light_sample_strategy > PBRT_B200_LIGHTS_SPATIAL) return fail(PBRT_B200_ERR_INVALID, "render: unknown light_sample_strategy");
     const uint32_t ikind = rd->integrator.kind;
     if (ikind > PBRT_B200_INTEGRATOR_WHITTED) return fail(PBRT_B200_ERR_INVALID, "render: unknown integrator kind");
-    if (ikind != PBRT_B200_INTEGRATOR_PATH && zt)
-        return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting / whitted run with the sobol and halton samplers (the 02sequence sampler's tile-serial stream is wired to the path integrator only)");
     if (ikind != PBRT_B200_INTEGRATOR_PATH && (rd->integrator.max_depth < 1 || rd->integrator.max_depth > 64))
         return fail(PBRT_B200_ERR_INVALID, "render: directlighting / whitted need 1 <= maxdepth <= 64");
     PB_CUDA_TRY(cudaSetDevice(sc->device));
@@ -1849,14 +1850,18 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     R.tile_begin = tile_begin; R.tile_end = tile_end; R.n_tiles_sel = n_tiles_sel; R.sample_begin = s_begin; R.n_samples_sel = s_end - s_begin;
     R.tile_group = tile_group; R.tile_mod = tile_mod; R.tile_rem = tile_rem;
 
+    // DirectLightingIntegrator::preprocess (directlighting.rs:61-76) with nsamples() == 1 for every light
+    const uint32_t rec_n_arrays = ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL ? (uint32_t)R.max_depth * R.n_lights * 2u : 0u;
     void* zt_block = nullptr; size_t zt_bytes = 0;
+    R.zt.n2d = rd->sampler.n_sampled_dimensions + rec_n_arrays;
     if (zt && n_tiles_sel > 0) {
-        const size_t nd = rd->sampler.n_sampled_dimensions, per_tile = nd * spp_eff;
-        const size_t need = Arena::padded(sizeof(ZtTile) * n_tiles_sel) + Arena::padded(4 * per_tile * n_tiles_sel) + Arena::padded(8 * per_tile * n_tiles_sel) + 1024;
+        const size_t nd = rd->sampler.n_sampled_dimensions, per_tile = nd * spp_eff, per_tile2 = (size_t)R.zt.n2d * spp_eff;
+        if (per_tile2 * n_tiles_sel * 8 > (8ull << 30)) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: 02sequence sample arrays for directlighting \"all\" exceed 8 GB");
+        const size_t need = Arena::padded(sizeof(ZtTile) * n_tiles_sel) + Arena::padded(4 * per_tile * n_tiles_sel) + Arena::padded(8 * per_tile2 * n_tiles_sel) + 1024;
         zt_block = pool_alloc(need, &zt_bytes);
         if (!zt_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the 02sequence sample tables");
         Arena A; A.base = reinterpret_cast<char*>(zt_block); A.size = zt_bytes;
-        R.zt.tiles = A.take<ZtTile>(n_tiles_sel); R.zt.s1d = A.take<float>(std::max<size_t>(per_tile * n_tiles_sel, 1)); R.zt.s2d = A.take<float2>(std::max<size_t>(per_tile * n_tiles_sel, 1));
+        R.zt.tiles = A.take<ZtTile>(n_tiles_sel); R.zt.s1d = A.take<float>(std::max<size_t>(per_tile * n_tiles_sel, 1)); R.zt.s2d = A.take<float2>(std::max<size_t>(per_tile2 * n_tiles_sel, 1));
         R.zt.spp = spp_eff; R.zt.ndims = (uint32_t)nd;
     }
     struct ZtRelease { void* p; size_t n; ~ZtRelease() { if (p) { cudaDeviceSynchronize(); pool_free(p, n); } } } zt_release{zt_block, zt_bytes};
@@ -1866,8 +1871,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         RecDev& rec = R.rec;
         rec.kind = ikind; rec.stack_depth = (uint32_t)R.max_depth; rec.entries_per_slot = rec_eps;
         if (ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {
-            // DirectLightingIntegrator::preprocess (directlighting.rs:61-76) with nsamples() == 1 for every light
-            rec.n_arrays = (uint32_t)R.max_depth * R.n_lights * 2u;
+            rec.n_arrays = rec_n_arrays;
             if (rd->sampler.kind == PBRT_B200_SAMPLER_SOBOL && 5ull + 2ull * rec.n_arrays + 8ull > 1024ull)
                 return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting \"all\" needs more Sobol' dimensions than the 1024 the tables hold (the reference panics)");
         }
@@ -1978,8 +1982,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                     launches += 3;
                 }
                 if (R.rec.kind) {  // whitted / directlighting: one generic shade kernel, entry-indexed shadow and MIS rays
-                    if (inst) k_rec_shade<true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    else k_rec_shade<false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    if (zt) k_rec_shade<true, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    else if (inst) k_rec_shade<true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    else k_rec_shade<false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
                     if (timing) mark();
                     if (inst) k_rec_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                     else k_rec_shadow<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);

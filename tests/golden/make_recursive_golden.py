@@ -18,5 +18,6 @@ out = {}
 for kind in ("whitted", "one", "all"):
     out[kind], _ = O.render_image(setup.flat, _integ(setup, kind, 4, (48, 32)))
 out["all_halton_d3"], _ = O.render_image(setup.flat, _integ(setup, "all", 4, (48, 32), sampler="halton", maxdepth=3))
+out["all_zt_d3"], _ = O.render_image(setup.flat, _integ(setup, "all", 4, (48, 32), sampler="02sequence", maxdepth=3))
 np.savez_compressed(Path(__file__).parent / "recursive_golden.npz", **out)
 print({k: float(v.mean()) for k, v in out.items()})

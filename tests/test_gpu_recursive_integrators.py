@@ -69,12 +69,50 @@ def test_small_queue_and_tile_windows(pkg, oracle, gpu_lib):
 
 
 def test_unsupported_combinations_fail_loudly(pkg, gpu_lib):
-    setup = pkg.scenes.spheres_scene()
-    integ = _make(pkg, setup, "whitted", spp=4, res=(32, 32), sampler="02sequence")
+    setup = pkg.scenes.many_lights_scene()  # > 50 lights: "all" would need more than the 1024 Sobol' dimensions (the reference panics)
+    assert len(setup.flat.lights) > 51
+    integ = _make(pkg, setup, "all", spp=4, res=(32, 32))
     sc = pkg.Scene(setup.flat)
     with pytest.raises(pkg.B200Error):
         sc.render(integ)
     sc.close()
+
+
+@pytest.mark.parametrize("kind,kw", [("whitted", dict(spp=4, res=(70, 50))), ("one", dict(spp=2, res=(64, 48))), ("all", dict(spp=4, res=(64, 48), maxdepth=3))])
+def test_02sequence_sampler_under_the_recursive_integrators(pkg, oracle, gpu_lib, kind, kw):
+    """Tile-serial (0,2)-sequence stream: get_1d / get_2d beyond the precomputed dimensions draw from the tile's PCG32 in the
+    recursion's depth-first order, and the 2D sample arrays of "all" are extra sobol_2d tables filled by start_pixel."""
+    setup = pkg.scenes.small_mixed_scene()
+    integ = _make(pkg, setup, kind, sampler="02sequence", **kw)
+    sc = pkg.Scene(setup.flat)
+    img, stats = integ.render(sc)
+    sc.close()
+    ref, ostats = oracle.render_image(setup.flat, integ)
+    err = oracle.rel_mse(img, ref)
+    assert err <= REL_MSE_TOL, f"relMSE {err:.3e}"
+    assert stats.camera_rays == ostats["camera_rays"]
+
+
+def test_reference_spheres_scene_file_verbatim(pkg, oracle, gpu_lib, tmp_path):
+    """tests/golden/reference_spheres_scene.pbrt is the reference's src/scenes/spheres-differentials-texfilt.pbrt, byte for byte:
+    Integrator "directlighting" maxdepth 10 (strategy "all"), Sampler "lowdiscrepancy" 1 spp, 1000x500, a checkerboard texture
+    nobody uses and an image map whose file does not exist in the reference tree either (-> the constant grey texture of
+    imagemap.rs:136-142).  Parsed, flattened and rendered on the device; compared with the oracle's render of the same job."""
+    import shutil
+    from pathlib import Path
+    import warnings
+    shutil.copy(Path(__file__).parent / "golden" / "reference_spheres_scene.pbrt", tmp_path / "spheres.pbrt")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        job = pkg.pbrt_parse(tmp_path / "spheres.pbrt").jobs[0]
+    assert (job.integrator.name, job.integrator.strategy, job.integrator.max_depth) == ("directlighting", "all", 10)
+    assert job.sampler.kind == pkg.host.SAMPLER_ZEROTWO and job.sampler.spp == 1 and job.film.full_resolution == (1000, 500)
+    assert abs(float(job.flat.materials[0]["a"][0]) - 0.21404114) < 1e-7  # inverse_gamma_correct(0.5): lines.png is missing
+    img, stats = job.render(device=0)
+    ref, ostats = oracle.render_image(job.flat, job.integrator)
+    err = oracle.rel_mse(img, ref)
+    assert err <= REL_MSE_TOL, f"relMSE {err:.3e}"
+    assert stats.camera_rays == ostats["camera_rays"] == 500000
 
 
 def test_scene_file_with_directlighting(pkg, oracle, gpu_lib, tmp_path):

@@ -60,3 +60,17 @@ def test_recursive_integrators_golden(oracle):
         assert np.allclose(img, g[kind], rtol=1e-5, atol=1e-6), kind
     img, _ = oracle.render_image(setup.flat, _integ(setup, "all", 4, (48, 32), sampler="halton", maxdepth=3))
     assert np.allclose(img, g["all_halton_d3"], rtol=1e-5, atol=1e-6)
+    img, _ = oracle.render_image(setup.flat, _integ(setup, "all", 4, (48, 32), sampler="02sequence", maxdepth=3))
+    assert np.allclose(img, g["all_zt_d3"], rtol=1e-5, atol=1e-6)
+
+
+def test_02sequence_sample_arrays_shift_the_tile_stream(oracle):
+    """Requesting 2D arrays makes start_pixel draw more from the tile's PCG32 (zerotwosequence.rs:67-71): with "all" the camera
+    samples of every pixel after the first differ from the array-free "one" run; the first pixel's first sample does not."""
+    setup = pkg.scenes.small_mixed_scene()
+    one = _integ(setup, "one", 16, (32, 32), sampler="02sequence")
+    all_ = _integ(setup, "all", 16, (32, 32), sampler="02sequence")
+    a, _ = oracle.render_image(setup.flat, one)
+    b, _ = oracle.render_image(setup.flat, all_)
+    assert not np.allclose(a, b)
+    assert abs(a.mean() - b.mean()) < 0.1 * a.mean()

@@ -232,11 +232,32 @@ def test_api_state_rules():
 
 def test_out_of_scope_features_fail_loudly():
     for text in ('Integrator "sppm"\nWorldBegin\nWorldEnd', 'WorldBegin\nMaterial "uber"\nWorldEnd', 'WorldBegin\nShape "cylinder"\nWorldEnd',
-                 'Camera "orthographic"\nWorldBegin\nWorldEnd', 'WorldBegin\nTexture "t" "color" "imagemap" "string filename" "x.png"\nWorldEnd',
+                 'Camera "orthographic"\nWorldBegin\nWorldEnd',
+                 'WorldBegin\nTexture "t" "color" "checkerboard"\nMaterial "matte" "texture Kd" "t"\nWorldEnd',
                  'WorldBegin\nLightSource "infinite" "string mapname" "env.exr"\nWorldEnd', 'Sampler "random"\nWorldBegin\nWorldEnd',
                  'WorldBegin\nMediumInterface "a" "b"\nWorldEnd'):
         with pytest.raises(pkg.B200Error):
             pkg.pbrt_parse_string(text)
+
+
+def test_textures_that_are_declared_but_unused_and_missing_image_maps(tmp_path):
+    # a procedural texture nobody references is not an error (the reference's spheres scene declares one); an image map whose
+    # file cannot be read is the constant grey texture of imagemap.rs:136-142, inverse-gamma-corrected for .png / .tga
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        job = pkg.pbrt_parse_string('WorldBegin\nTexture "c" "color" "checkerboard" "float uscale" 4\n'
+                                    'Texture "a" "color" "imagemap" "string filename" "nope/lines.png" "float scale" 2\n'
+                                    'Texture "b" "color" "imagemap" "string filename" "nope/lines.exr"\n'
+                                    'Texture "f" "float" "imagemap" "string filename" "nope/r.tga"\n'
+                                    'Material "matte" "texture Kd" "a"\nShape "sphere"\nMaterial "matte" "texture Kd" "b" "texture sigma" "f"\nShape "sphere"\nWorldEnd',
+                                    search_dir=str(tmp_path)).jobs[0]
+    m = job.flat.materials
+    g = ((0.5 + 0.055) / 1.055) ** 2.4
+    assert np.allclose(m[0]["a"], 2 * g, rtol=1e-6) and np.allclose(m[1]["a"], 0.5) and abs(m[1]["f0"] - g) < 1e-6
+    (tmp_path / "real.png").write_bytes(b"\x89PNG\r\n")  # a file that exists would have to be decoded and filtered: refused when used
+    with pytest.raises(pkg.B200Error):
+        pkg.pbrt_parse_string('WorldBegin\nTexture "a" "color" "imagemap" "string filename" "real.png"\nMaterial "matte" "texture Kd" "a"\nWorldEnd',
+                              search_dir=str(tmp_path))
 
 
 def test_include_resolves_against_the_scene_directory(tmp_path):
@@ -259,6 +280,13 @@ def test_reference_scene_files_lex_and_parse():
     with pytest.raises(pkg.B200Error), warnings.catch_warnings():
         warnings.simplefilter("ignore")
         pkg.pbrt_parse(REF_SCENES / "caustic-glass.pbrt")
+    # ... except the spheres scene, which runs verbatim (directlighting "all", lowdiscrepancy sampler, missing image map -> grey):
+    # tests/golden/reference_spheres_scene.pbrt is that file, rendered on the GPU by tests/test_gpu_recursive_integrators.py
+    assert (REF_SCENES / "spheres-differentials-texfilt.pbrt").read_bytes() == (Path(__file__).parent / "golden" / "reference_spheres_scene.pbrt").read_bytes()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        job = pkg.pbrt_parse(REF_SCENES / "spheres-differentials-texfilt.pbrt").jobs[0]
+    assert job.integrator.kind == pkg.host.INTEGRATOR_DIRECT_ALL and len(job.flat.spheres) == 2 and job.flat.vertex_uv is not None
     m = PLY.read_ply(str(REF_SCENES / "geometry" / "mesh_00001.ply"))  # the 88k-triangle caustic glass mesh
     assert m["P"].shape == (44034, 3) and m["indices"].shape == (88064, 3) and m["N"].shape == (44034, 3)
     # the same geometry with the path integrator: flattens, BVH builds, every triangle is referenced exactly once
