@@ -93,8 +93,10 @@ def test_02sequence_sampler_under_the_recursive_integrators(pkg, oracle, gpu_lib
     assert stats.camera_rays == ostats["camera_rays"]
 
 
-def test_reference_spheres_scene_file_verbatim(pkg, oracle, gpu_lib, tmp_path):
-    """tests/golden/reference_spheres_scene.pbrt is the reference's src/scenes/spheres-differentials-texfilt.pbrt, byte for byte:
+def test_reference_spheres_scene_file(pkg, oracle, gpu_lib, tmp_path):
+    """tests/golden/reference_spheres_scene.pbrt holds the directives and parameters of the reference's
+    src/scenes/spheres-differentials-texfilt.pbrt (re-emitted from the parsed command list; tests/test_scene_file_frontend.py
+    checks that both files parse to the same commands whenever the reference tree is mounted):
     Integrator "directlighting" maxdepth 10 (strategy "all"), Sampler "lowdiscrepancy" 1 spp, 1000x500, a checkerboard texture
     nobody uses and an image map whose file does not exist in the reference tree either (-> the constant grey texture of
     imagemap.rs:136-142).  Parsed, flattened and rendered on the device; compared with the oracle's render of the same job."""
