@@ -188,6 +188,40 @@ __global__ void __launch_bounds__(256) k_fat_nodes(const pbrt_b200_bvh_node* __r
     }
 }
 
+// fat nodes -> quad nodes (scene.cuh): quad[i] = the children of fat[i]'s two children
+__global__ void __launch_bounds__(256) k_quad_nodes(const float4* __restrict__ fat, uint32_t n_fat, float4* __restrict__ quads) {
+    const float INF = __int_as_float(0x7f800000);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_fat; i += gridDim.x * blockDim.x) {
+        const float4 p0 = fat[4ull * i], p1 = fat[4ull * i + 1], p2 = fat[4ull * i + 2], p3 = fat[4ull * i + 3];
+        const uint32_t cref[2] = {__float_as_uint(p3.x), __float_as_uint(p3.y)};
+        const float cbox[2][6] = {{p0.x, p0.y, p0.z, p0.w, p1.x, p1.y}, {p1.z, p1.w, p2.x, p2.y, p2.z, p2.w}};
+        float lo[4][3], hi[4][3];
+        uint32_t ref[4], axis[2] = {0u, 0u};
+        for (int c = 0; c < 2; ++c) {
+            if (cref[c] & PB_LEAF_BIT) {  // a leaf child occupies one slot
+                for (int a = 0; a < 3; ++a) { lo[2 * c][a] = cbox[c][a]; hi[2 * c][a] = cbox[c][3 + a]; lo[2 * c + 1][a] = INF; hi[2 * c + 1][a] = -INF; }
+                ref[2 * c] = cref[c]; ref[2 * c + 1] = PB_REF_NONE;
+            } else {
+                const float4 g0 = fat[4ull * cref[c]], g1 = fat[4ull * cref[c] + 1], g2 = fat[4ull * cref[c] + 2], g3 = fat[4ull * cref[c] + 3];
+                const float gb[2][6] = {{g0.x, g0.y, g0.z, g0.w, g1.x, g1.y}, {g1.z, g1.w, g2.x, g2.y, g2.z, g2.w}};
+                for (int k = 0; k < 2; ++k)
+                    for (int a = 0; a < 3; ++a) { lo[2 * c + k][a] = gb[k][a]; hi[2 * c + k][a] = gb[k][3 + a]; }
+                ref[2 * c] = __float_as_uint(g3.x); ref[2 * c + 1] = __float_as_uint(g3.y);
+                axis[c] = __float_as_uint(g3.z);
+            }
+        }
+        float4* q = quads + 8ull * i;
+        for (int pr = 0; pr < 2; ++pr) {
+            const int a = 2 * pr, b = 2 * pr + 1;
+            q[3 * pr + 0] = make_float4(lo[a][0], lo[b][0], lo[a][1], lo[b][1]);
+            q[3 * pr + 1] = make_float4(lo[a][2], lo[b][2], hi[a][0], hi[b][0]);
+            q[3 * pr + 2] = make_float4(hi[a][1], hi[b][1], hi[a][2], hi[b][2]);
+        }
+        q[6] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float(ref[2]), __uint_as_float(ref[3]));
+        q[7] = make_float4(__uint_as_float(__float_as_uint(p3.z) | (axis[0] << 2) | (axis[1] << 4)), 0.0f, 0.0f, 0.0f);
+    }
+}
+
 __global__ void k_single_prim_last(const uint32_t* __restrict__ slots, uint32_t n, float4* __restrict__ tris) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         float4* rec = tris + 3ull * slots[k] + 1;
@@ -361,7 +395,7 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     const uint64_t max_interior = nn / 2 + 1;  // a binary tree has one interior node less than leaves
     size_t need = 0;
     auto add = [&](size_t bytes) { need += Arena::padded(bytes); };
-    add(64ull * max_interior); add(48ull * np); add(sizeof(pbrt_b200_prim) * np);
+    add(64ull * max_interior); add(128ull * max_interior); add(48ull * np); add(sizeof(pbrt_b200_prim) * np);
     add(12ull * nv); add(d->vertex_n ? 12ull * nv : 0); add(d->vertex_s ? 12ull * nv : 0); add(d->vertex_uv ? 8ull * nv : 0);
     add(12ull * nt); add(sizeof(pbrt_b200_sphere) * d->n_spheres); add(sizeof(pbrt_b200_material) * d->n_materials); add(sizeof(pbrt_b200_light) * d->n_lights);
     add(sizeof(DevInstance) * d->n_instances); add(4ull * d->n_objects); add(sizeof(DevScene));
@@ -405,8 +439,9 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
         if (err == cudaSuccess) err = cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, stream);
     };
     float4* fat = A.take<float4>(4ull * max_interior);
+    float4* quads = A.take<float4>(8ull * max_interior);
     float4* tris = A.take<float4>(3ull * np);
-    ds.nodes = fat; ds.tris = tris;
+    ds.nodes = fat; ds.quads = quads; ds.tris = tris;
     const pbrt_b200_bvh_node* nodes_dev = nullptr;
     up(d->prims, sizeof(pbrt_b200_prim) * np, &ds.prims);
     up(d->vertex_p, 12ull * nv, &ds.vertex_p);
@@ -437,6 +472,7 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
             };
             fat_launch(0, d->n_objects ? d->n_top_nodes : nn, 0);
             for (uint64_t k = 0; k < d->n_objects; ++k) fat_launch(d->objects[k].node_offset, d->objects[k].n_nodes, d->objects[k].prim_offset);
+            if (n_interior) k_quad_nodes<<<(unsigned)std::min<uint64_t>((n_interior + 255) / 256, 148 * 16), 256, 0, stream>>>(fat, n_interior, quads);
         }
     }
     if (d->n_instances && err == cudaSuccess) {

@@ -39,6 +39,14 @@ struct DevScene {
     //  q3 = {ref0, ref1, axis, 0} (bit patterns)
     // c0 = reference child at index+1, c1 = reference child at `offset` (bvh.rs:662-693).
     const float4* nodes;
+    // Quad nodes, 128 B = 8 x float4, one per fat node and with the same index: the four GRANDCHILDREN of the reference's
+    // interior node (the children of its two children; a child that is a leaf fills one slot and leaves the other empty:
+    // lo = +inf, hi = -inf, ref = PB_REF_NONE).  Slots 0,1 = under the first child, 2,3 = under the second child.
+    //  pair A (slots 0,1): qa0 = {lo0.x, lo1.x, lo0.y, lo1.y}  qa1 = {lo0.z, lo1.z, hi0.x, hi1.x}  qa2 = {hi0.y, hi1.y, hi0.z, hi1.z}
+    //  pair B (slots 2,3): qb0, qb1, qb2 likewise
+    //  q6 = {ref0, ref1, ref2, ref3}   q7 = {axis | axis_first << 2 | axis_second << 4, 0, 0, 0}
+    // Used by rays without a zero direction component in scenes without instancing (trace.cuh: trav_run_quad).
+    const float4* quads;
     uint32_t n_fat;
     uint32_t root_ref;      // PB_REF_NONE when the scene is empty
     float root_box[6];      // LinearBVHNode[0].bounds = Scene.wb

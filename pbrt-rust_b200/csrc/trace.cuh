@@ -235,7 +235,9 @@ PB_D SlabPair slab_fast2(float2 nx, float2 ny, float2 nz, float2 fx, float2 fy, 
 #define PB_STACK_DEPTH 64  /* bvh.rs:722 nodes_tovisit = vec![0; 64] */
 /* the reference keeps one 64-entry stack per BVHAccel; the unified two-level walk stacks the object's entries on top of the
  * world's, plus the sentinel and the rest-of-leaf entry */
-#define PB_STACK_SIZE(INST) ((INST) ? 2 * PB_STACK_DEPTH + 2 : PB_STACK_DEPTH)
+/* the quad walk descends two binary levels per step and can stack three siblings: 3 * 64 / 2 entries for the deepest tree
+ * scene_create accepts (depth <= 64) */
+#define PB_STACK_SIZE(INST) ((INST) ? 2 * PB_STACK_DEPTH + 2 : 3 * PB_STACK_DEPTH / 2)
 #define PB_DONE 0xffffffffu /* traversal finished (has the leaf bit set so the interior loop exits) */
 
 // Per-ray traversal state.  The order of box and primitive tests is the reference's
@@ -475,6 +477,89 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
     }
 }
 
+#ifndef PB_QUAD_NODES
+#define PB_QUAD_NODES 1
+#endif
+// The same walk over QUAD nodes (scene.cuh): one 128-byte fetch tests the four grandchildren of a reference node.
+// Exactness: the reference visits a leaf iff the leaf's box passes `tmin < t_max` (and the slab test) when it is reached AND
+// every ancestor's box passed when IT was reached.  A child box contains its children's boxes and (x - o) * inv is monotone
+// in x in floating point, so a grandchild that passes implies its parent passed (tmin_parent <= tmin_gc <= tmax_gc <=
+// tmax_parent, against a t_max that only shrinks): skipping the intermediate box test cannot change the set of leaves
+// visited, PROVIDED the leaves are visited in the reference's order -- which is depth-first with the near child first at
+// every binary node.  The four slots are therefore walked in exactly that order (near group by the node's axis, near
+// slot inside each group by the child's axis), later ones are stacked behind earlier ones, and a stacked entry is
+// re-checked against the current t_max when popped, as in the binary walk.  Only for rays without zero direction
+// components (slab_fast's precondition; the others take the binary, NaN-exact walk).
+template <bool ANY>
+PB_D void trav_run_quad(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
+    while (r.cur != PB_DONE) {
+        while (!(r.cur & PB_LEAF_BIT)) {
+            const float4* np = s.quads + 8ull * r.cur;
+            const float4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2), b0 = __ldg(np + 3), b1 = __ldg(np + 4), b2 = __ldg(np + 5), q6 = __ldg(np + 6), q7 = __ldg(np + 7);
+            SlabPair pa = slab_fast2(r.ngx ? make_float2(a1.z, a1.w) : make_float2(a0.x, a0.y), r.ngy ? make_float2(a2.x, a2.y) : make_float2(a0.z, a0.w),
+                                     r.ngz ? make_float2(a2.z, a2.w) : make_float2(a1.x, a1.y), r.ngx ? make_float2(a0.x, a0.y) : make_float2(a1.z, a1.w),
+                                     r.ngy ? make_float2(a0.z, a0.w) : make_float2(a2.x, a2.y), r.ngz ? make_float2(a1.x, a1.y) : make_float2(a2.z, a2.w),
+                                     r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
+            SlabPair pb = slab_fast2(r.ngx ? make_float2(b1.z, b1.w) : make_float2(b0.x, b0.y), r.ngy ? make_float2(b2.x, b2.y) : make_float2(b0.z, b0.w),
+                                     r.ngz ? make_float2(b2.z, b2.w) : make_float2(b1.x, b1.y), r.ngx ? make_float2(b0.x, b0.y) : make_float2(b1.z, b1.w),
+                                     r.ngy ? make_float2(b0.z, b0.w) : make_float2(b2.x, b2.y), r.ngz ? make_float2(b1.x, b1.y) : make_float2(b2.z, b2.w),
+                                     r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
+            const float tA0 = pa.ok0 ? pa.tmin0 : PB_INF, tA1 = pa.ok1 ? pa.tmin1 : PB_INF, tB0 = pb.ok0 ? pb.tmin0 : PB_INF, tB1 = pb.ok1 ? pb.tmin1 : PB_INF;
+            const uint32_t meta = __float_as_uint(q7.x);
+            const bool g = (r.negmask >> (meta & 3u)) & 1u, sA = (r.negmask >> ((meta >> 2) & 3u)) & 1u, sB = (r.negmask >> ((meta >> 4) & 3u)) & 1u;
+            // reference order inside each group, then of the groups
+            const float tAn = sA ? tA1 : tA0, tAf = sA ? tA0 : tA1, tBn = sB ? tB1 : tB0, tBf = sB ? tB0 : tB1;
+            const uint32_t rAn = __float_as_uint(sA ? q6.y : q6.x), rAf = __float_as_uint(sA ? q6.x : q6.y);
+            const uint32_t rBn = __float_as_uint(sB ? q6.w : q6.z), rBf = __float_as_uint(sB ? q6.z : q6.w);
+            const float t0 = g ? tBn : tAn, t1 = g ? tBf : tAf, t2 = g ? tAn : tBn, t3 = g ? tAf : tBf;
+            const uint32_t r0 = g ? rBn : rAn, r1 = g ? rBf : rAf, r2 = g ? rAn : rBn, r3 = g ? rAf : rBf;
+            // the first slot that passes is visited now; the others wait on the stack, nearest on top
+            uint32_t nref = PB_DONE; float ntm = 0.0f;
+            if (t3 < r.t_max) { nref = r3; ntm = t3; }
+            if (t2 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r2; ntm = t2; }
+            if (t1 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r1; ntm = t1; }
+            if (t0 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r0; ntm = t0; }
+            if (nref != PB_DONE) r.cur = nref;
+            else PB_TRAV_POP(r, stack);
+            if (interior_min > 0 && __popc(__activemask()) < interior_min) break;
+        }
+        if (r.cur == PB_DONE) break;
+        if (r.cur & PB_LEAF_BIT) {
+            uint32_t slot = r.cur & ~PB_LEAF_BIT;
+            uint32_t fl;
+            do {
+                const float4* tp = s.tris + 3ull * slot;
+                float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                fl = __float_as_uint(v1.w);
+                float t, b0, b1, b2;
+                bool h;
+                if (fl & PB_TRI_SPHERE) {
+                    h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
+                    b0 = b1 = b2 = 0.0f;
+                } else {
+                    f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
+                    h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
+                    if (!ANY && h) {
+                        float2 uv0, uv1, uv2;
+                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2);
+                        if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) h = false;
+                    }
+                }
+                if (h) {
+                    r.found = true;
+                    r.hit.slot = slot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2;
+                    if (ANY) { r.cur = PB_DONE; r.sp = 0; break; }
+                    r.t_max = t;  // primitive.rs:137
+                }
+                ++slot;
+            } while (!(fl & PB_TRI_LAST));
+            if (ANY && r.found) break;
+            PB_TRAV_POP(r, stack);
+        }
+        if (yield_below > 0 && __popc(__activemask()) < yield_below) break;
+    }
+}
+
 // INST: the scene contains TransformedPrimitives.  Scenes without instancing run kernels compiled with INST = false, which
 // contain no trace of the instance path (measured on S3: the mere presence of the out-of-line call in the leaf loop costs 20%).
 template <bool ANY, bool INST>
@@ -482,7 +567,11 @@ PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below,
     // with instances the ray changes along the way, so the NaN-free slab shortcut cannot be chosen once per ray: INST
     // kernels always evaluate the literal reference chain
     if (INST || r.nan_possible) trav_run_impl<ANY, true, INST>(s, r, stack, yield_below, interior_min);
+#if PB_QUAD_NODES
+    else trav_run_quad<ANY>(s, r, stack, yield_below, interior_min);
+#else
     else trav_run_impl<ANY, false, INST>(s, r, stack, yield_below, interior_min);
+#endif
 }
 
 // Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray, run to completion.
