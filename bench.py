@@ -323,6 +323,9 @@ def main():
             ach = tot["closest"] * bytes_per_ray / (tot["trace_closest_ms"] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": "k_trace_closest (+k_trace_mis): closest-hit BVH traversal", "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "peak_source": peak_src, "traffic": prof.get("traffic_bytes_per_launch"),
+                        "traffic_launch": {"rays": prof.get("traffic_launch_rays"), "ms": prof.get("traffic_launch_ms"),
+                                           "algorithmic_bytes": None if prof.get("traffic_launch_rays") is None else prof["traffic_launch_rays"] * bytes_per_ray,
+                                           "source": "profiles/roofline_inputs.json (one ncu --set full capture of the first k_trace_closest launch of a step)"},
                         "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": npr, "prims_per_ray": ppr,
                         "closest_rays_rank0": tot["closest"], "kernel_ms_rank0": tot["trace_closest_ms"],
                         "share_of_step": tot["trace_closest_ms"] / max(tot["device_ms"], 1e-9)}
