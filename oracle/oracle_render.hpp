@@ -141,6 +141,85 @@ struct LightSample {
     InteractionData p1;  // VisibilityTester.p1
 };
 
+// ---- Sphere as an area-light shape: Sphere::sample / sample_interaction / pdf_wi (sphere.rs:295-395, full spheres)
+inline V3 uniform_sample_sphere_(P2 u) {  // sampling.rs:212-218
+    Float z = 1.0f - 2.0f * u.x;
+    Float r = std::sqrt(std::fmax(1.0f - z * z, 0.0f));
+    Float phi = 2.0f * PI * u.y;
+    return V3(r * std::cos(phi), r * std::sin(phi), z);
+}
+inline InteractionData sphere_sample(const pbrt_b200_sphere& sp, const pbrt_b200_light& l, P2 u, Float* pdf) {  // sphere.rs:295-311
+    M4 o2w = m4_from(sp.object_to_world), w2o = m4_from(sp.world_to_object);
+    V3 pobj = V3(0, 0, 0) + uniform_sample_sphere_(u) * sp.radius;
+    InteractionData it;
+    it.n = normalize(m4_normal(w2o, pobj));
+    if (l.shape_flags & PBRT_B200_PRIM_REVERSE_ORIENTATION) it.n = it.n * -1.0f;
+    pobj = pobj * (sp.radius / distance(pobj, V3(0, 0, 0)));
+    V3 pobj_error = vabs(pobj) * gamma(5);
+    it.p = m4_point_abs_error(o2w, pobj, pobj_error, &it.p_error);
+    *pdf = 1.0f / l.area;
+    return it;
+}
+inline InteractionData sphere_sample_interaction(const RenderScene& s, const pbrt_b200_light& l, const InteractionData& ref, P2 u, Float* pdf) {  // sphere.rs:313-380
+    const pbrt_b200_sphere& sp = s.d.spheres[l.shape_index];
+    V3 pcenter = m4_point(m4_from(sp.object_to_world), V3(0, 0, 0));
+    V3 porigin = offset_ray_origin(ref.p, ref.p_error, ref.n, pcenter - ref.p);
+    if (distance_squared(porigin, pcenter) <= sp.radius * sp.radius) {  // inside: uniform over the sphere, converted to solid angle
+        InteractionData intr = sphere_sample(sp, l, u, pdf);
+        V3 wi = intr.p - ref.p;
+        if (length_squared(wi) == 0.0f) *pdf = 0.0f;
+        else {
+            wi = normalize(wi);
+            *pdf *= distance_squared(ref.p, intr.p) / abs_dot(intr.n, -wi);
+        }
+        if (std::isinf(*pdf)) *pdf = 0.0f;
+        return intr;
+    }
+    // uniform in the subtended cone
+    Float dc = distance(ref.p, pcenter);
+    Float invdc = 1.0f / dc;
+    V3 wc = (pcenter - ref.p) * invdc, wcx, wcy;
+    coordinate_system(wc, &wcx, &wcy);
+    Float sin_thetamax = sp.radius * invdc;
+    Float sin_thetamax2 = sin_thetamax * sin_thetamax;
+    Float inv_sin_thetamax = 1.0f / sin_thetamax;
+    Float cos_thetamax = std::sqrt(std::fmax(1.0f - sin_thetamax2, 0.0f));
+    Float cos_theta = (cos_thetamax - 1.0f) * u.x + 1.0f;
+    Float sin_theta2 = 1.0f - cos_theta * cos_theta;
+    if (sin_thetamax2 < 0.00068523f) {  // Taylor expansion for small angles
+        sin_theta2 = sin_thetamax2 * u.x;
+        cos_theta = std::sqrt(1.0f - sin_theta2);
+    }
+    Float cos_alpha = sin_theta2 * inv_sin_thetamax + cos_theta * std::sqrt(std::fmax(1.0f - sin_theta2 * inv_sin_thetamax * inv_sin_thetamax, 0.0f));
+    Float sin_alpha = std::sqrt(std::fmax(1.0f - cos_alpha * cos_alpha, 0.0f));
+    Float phi = u.y * 2.0f * PI;
+    // spherical_direction_basis(sin_alpha, cos_alpha, phi, -wcx, -wcy, -wc), geometry.rs:36-38
+    V3 nworld = (wcx * -1.0f) * sin_alpha * std::cos(phi) + (wcy * -1.0f) * sin_alpha * std::sin(phi) + (wc * -1.0f) * cos_alpha;
+    V3 pworld = pcenter + nworld * sp.radius;
+    InteractionData it;  // it.n stays (0,0,0): sphere.rs:371-374 never sets it (quirk a-Q8) => only two-sided sphere lights emit through light sampling
+    it.p = pworld;
+    it.p_error = vabs(pworld) * gamma(5);
+    *pdf = 1.0f / (2.0f * PI * (1.0f - cos_thetamax));
+    return it;
+}
+inline Float sphere_pdf_wi(const RenderScene& s, const pbrt_b200_light& l, const InteractionData& ref, V3 wi) {  // sphere.rs:382-395
+    const pbrt_b200_sphere& sp = s.d.spheres[l.shape_index];
+    V3 pcenter = m4_point(m4_from(sp.object_to_world), V3(0, 0, 0));
+    V3 porigin = offset_ray_origin(ref.p, ref.p_error, ref.n, pcenter - ref.p);
+    if (distance_squared(porigin, pcenter) <= sp.radius * sp.radius) {  // shape_pdfwi, shape.rs:63-82
+        Ray ray = spawn_ray(ref.p, ref.p_error, ref.n, wi, ref.time);
+        Float t;
+        if (!sphere_test(sp, ray, &t, nullptr)) return 0.0f;
+        SurfaceInteraction isect = sphere_interaction(sp, ray, t);
+        Float pdf = distance_squared(ref.p, isect.p) / (dot(isect.n, -wi) * l.area);  // signed dot (quirk a-Q2)
+        if (std::isinf(pdf)) pdf = 0.0f;
+        return pdf;
+    }
+    Float sin_thetamax2 = sp.radius * sp.radius / distance_squared(ref.p, pcenter);
+    Float cos_thetamax = std::sqrt(std::fmax(1.0f - sin_thetamax2, 0.0f));
+    return 1.0f / (2.0f * PI * (1.0f - cos_thetamax));  // uniform_cone_pdf
+}
+
 // Light::sample_li
 inline LightSample light_sample_li(const RenderScene& s, int li, const InteractionData& ref, P2 u) {
     const pbrt_b200_light& l = s.d.lights[li];
@@ -175,7 +254,7 @@ inline LightSample light_sample_li(const RenderScene& s, int li, const Interacti
         }
         case PBRT_B200_LIGHT_DIFFUSE: {  // diffuse.rs:91-106
             Float pdf;
-            InteractionData ps = triangle_sample_interaction(s, l, ref, u, &pdf);
+            InteractionData ps = l.shape_kind == PBRT_B200_SHAPE_SPHERE ? sphere_sample_interaction(s, l, ref, u, &pdf) : triangle_sample_interaction(s, l, ref, u, &pdf);
             if (pdf == 0.0f || length_squared(ps.p - ref.p) == 0.0f) { r.pdf = 0.0f; r.Li = Spectrum(0.0f); return r; }
             r.pdf = pdf;
             r.wi = normalize(ps.p - ref.p);
@@ -203,7 +282,7 @@ inline LightSample light_sample_li(const RenderScene& s, int li, const Interacti
 // Light::pdf_li
 inline Float light_pdf_li(const RenderScene& s, int li, const InteractionData& ref, V3 wi) {
     const pbrt_b200_light& l = s.d.lights[li];
-    if (l.type == PBRT_B200_LIGHT_DIFFUSE) return triangle_pdf_wi(s, l, ref, wi);
+    if (l.type == PBRT_B200_LIGHT_DIFFUSE) return l.shape_kind == PBRT_B200_SHAPE_SPHERE ? sphere_pdf_wi(s, l, ref, wi) : triangle_pdf_wi(s, l, ref, wi);
     if (l.type == PBRT_B200_LIGHT_INFINITE) {  // infinite.rs:131-139
         Float theta = spherical_theta(wi), phi = spherical_phi(wi);
         Float sin_theta = std::sin(theta);

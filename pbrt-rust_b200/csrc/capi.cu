@@ -279,9 +279,10 @@ int validate(const pbrt_b200_scene_desc* d) {
     for (uint64_t i = 0; i < d->n_lights; ++i) {
         const pbrt_b200_light& l = d->lights[i];
         if (l.type > PBRT_B200_LIGHT_INFINITE) return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: light type outside the hot path");
-        if (l.type == PBRT_B200_LIGHT_DIFFUSE && l.shape_kind != PBRT_B200_SHAPE_TRIANGLE)
-            return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: only triangle area lights are on the hot path");
-        if (l.type == PBRT_B200_LIGHT_DIFFUSE && l.shape_index >= d->n_triangles) return fail(PBRT_B200_ERR_INVALID, "scene_create: area light shape out of range");
+        if (l.type == PBRT_B200_LIGHT_DIFFUSE && l.shape_kind != PBRT_B200_SHAPE_TRIANGLE && l.shape_kind != PBRT_B200_SHAPE_SPHERE)
+            return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: area lights are triangles or spheres");
+        if (l.type == PBRT_B200_LIGHT_DIFFUSE && l.shape_index >= (l.shape_kind == PBRT_B200_SHAPE_SPHERE ? d->n_spheres : d->n_triangles))
+            return fail(PBRT_B200_ERR_INVALID, "scene_create: area light shape out of range");
     }
     return PBRT_B200_OK;
 }
@@ -415,6 +416,9 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     DevScene& ds = sc->dev;
     ds.n_slots = (uint32_t)np;
     ds.n_lights = (uint32_t)d->n_lights;
+    ds.n_sphere_lights = 0;
+    for (uint64_t i = 0; i < d->n_lights; ++i)
+        if (d->lights[i].type == PBRT_B200_LIGHT_DIFFUSE && d->lights[i].shape_kind == PBRT_B200_SHAPE_SPHERE) ds.n_sphere_lights += 1;
     ds.n_materials = (uint32_t)d->n_materials;
     if (nn) {
         std::memcpy(ds.root_box, d->nodes[0].bounds, sizeof ds.root_box);

@@ -100,7 +100,7 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
     const pbrt_b200_light& light = R.scene.lights[ln];
     const bool delta = is_delta_light(light);
     LightSample ls;
-    light_sample_li(R, ln, si.p, ulight, ls);
+    light_sample_li<INST>(R, ln, si.p, ulight, ls, si.p_error, si.n);
     float scattpdf = 0.0f;
     if (ls.pdf > 0.0f && !is_black(ls.Li)) {
         rgb f = bsdf_f<KM_ALL>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
@@ -124,7 +124,7 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
             float weight = 1.0f;
             bool go = true;
             if (!(stype & BX_SPECULAR)) {
-                float lpdf = light_pdf_li(R, ln, si, wi);
+                float lpdf = light_pdf_li<INST>(R, ln, si, wi);
                 if (lpdf == 0.0f) go = false;
                 else weight = power_heuristic(scattpdf, lpdf);
             }
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                         for (uint32_t li = 0; li < nl; ++li) {
                             float2 u = smp.get_2d(R);
                             LightSample ls;
-                            light_sample_li(R, li, si.p, u, ls);
+                            light_sample_li<INST>(R, li, si.p, u, ls, si.p_error, si.n);
                             if (is_black(ls.Li) || ls.pdf == 0.0f) continue;
                             rgb f = bsdf_f<KM_ALL>(bsdf, si.wo, ls.wi, BX_ALL);
                             if (is_black(f)) continue;

@@ -717,8 +717,92 @@ PB_D void triangle_light_sample(const DevScene& s, const pbrt_b200_light& l, f3 
     r.pdf = pdf;
 }
 
-// Light::sample_li for every light kind on the hot path
-PB_D void light_sample_li(const RenderDev& R, uint32_t li, f3 ref_p, float2 u, LightSample& r) {
+// ---- Sphere as an area-light shape: Sphere::sample / sample_interaction / pdf_wi (shapes/sphere.rs:295-395, full spheres).
+// Out of line and fed through the HBM copy of the scene (DevScene::self_dev): scenes without sphere lights pay one
+// predicated call, and the shade kernels' register allocation does not move.
+struct SphereLightSample { f3 p, p_err, n; float pdf; };
+static __device__ __noinline__ void sphere_light_sample(const DevScene* sp, uint32_t li, f3 ref_p, f3 ref_perr, f3 ref_n, float ux, float uy, SphereLightSample* out) {
+    const DevScene& s = *sp;
+    const pbrt_b200_light& l = s.lights[li];
+    const pbrt_b200_sphere& sph = s.spheres[l.shape_index];
+    f3 pcenter = xf_point(sph.object_to_world, f3(0.f, 0.f, 0.f));
+    f3 porigin = offset_ray_origin(ref_p, ref_perr, ref_n, pcenter - ref_p);
+    f3 dco = porigin - pcenter;
+    if (len2(dco) <= sph.radius * sph.radius) {  // inside: Sphere::sample (uniform over the surface), converted to solid angle
+        float z = 1.0f - 2.0f * ux;
+        float rr = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+        float phi = 2.0f * PB_PI * uy;
+        f3 pobj = f3(rr * cosf(phi), rr * sinf(phi), z) * sph.radius;
+        f3 n = normalize(xf_normal(sph.world_to_object, pobj));
+        if (l.shape_flags & PBRT_B200_PRIM_REVERSE_ORIENTATION) n = n * -1.0f;
+        pobj = pobj * (sph.radius / len(pobj));
+        f3 pe = vabs(pobj) * gamma_n(5);
+        out->p = xf_point_abs_err(sph.object_to_world, pobj, pe, &out->p_err);
+        out->n = n;
+        float pdf = 1.0f / l.area;
+        f3 wi = out->p - ref_p;
+        if (len2(wi) == 0.0f) pdf = 0.0f;
+        else {
+            wi = normalize(wi);
+            f3 dd = ref_p - out->p;
+            pdf *= len2(dd) / absdot(n, -wi);
+        }
+        if (isinf(pdf)) pdf = 0.0f;
+        out->pdf = pdf;
+        return;
+    }
+    // uniform inside the subtended cone (sphere.rs:335-378)
+    f3 dcv = ref_p - pcenter;
+    float dc = len(dcv);
+    float invdc = 1.0f / dc;
+    f3 wc = (pcenter - ref_p) * invdc, wcx, wcy;
+    coordinate_system(wc, &wcx, &wcy);
+    float stm = sph.radius * invdc;
+    float stm2 = stm * stm;
+    float istm = 1.0f / stm;
+    float ctm = sqrtf(fmaxf(1.0f - stm2, 0.0f));
+    float ct = (ctm - 1.0f) * ux + 1.0f;
+    float st2 = 1.0f - ct * ct;
+    if (stm2 < 0.00068523f) { st2 = stm2 * ux; ct = sqrtf(1.0f - st2); }
+    float ca = st2 * istm + ct * sqrtf(fmaxf(1.0f - st2 * istm * istm, 0.0f));
+    float sa = sqrtf(fmaxf(1.0f - ca * ca, 0.0f));
+    float phi = uy * 2.0f * PB_PI;
+    f3 nworld = (wcx * -1.0f) * sa * cosf(phi) + (wcy * -1.0f) * sa * sinf(phi) + (wc * -1.0f) * ca;  // spherical_direction_basis, geometry.rs:36-38
+    f3 pworld = pcenter + nworld * sph.radius;
+    out->p = pworld;
+    out->p_err = vabs(pworld) * gamma_n(5);
+    out->n = f3(0.f, 0.f, 0.f);  // sphere.rs:371-374 never sets it.n: only two-sided sphere lights emit through light sampling
+    out->pdf = 1.0f / (2.0f * PB_PI * (1.0f - ctm));
+}
+static __device__ __noinline__ float sphere_light_pdf_wi(const DevScene* sp, uint32_t li, f3 ref_p, f3 ref_perr, f3 ref_n, f3 wi) {
+    const DevScene& s = *sp;
+    const pbrt_b200_light& l = s.lights[li];
+    const pbrt_b200_sphere& sph = s.spheres[l.shape_index];
+    f3 pcenter = xf_point(sph.object_to_world, f3(0.f, 0.f, 0.f));
+    f3 porigin = offset_ray_origin(ref_p, ref_perr, ref_n, pcenter - ref_p);
+    f3 dco = porigin - pcenter;
+    if (len2(dco) <= sph.radius * sph.radius) {  // shape_pdfwi, core/shape.rs:117-136: re-intersect the shape, signed cosine
+        f3 o = offset_ray_origin(ref_p, ref_perr, ref_n, wi);
+        float t;
+        if (!sphere_test(&sph, o, wi, PB_INF, &t)) return 0.0f;
+        Surf ls = sphere_surface(&sph, o, wi, t);
+        f3 dd = ref_p - ls.p;
+        float pdf = len2(dd) / (dot(ls.n, -wi) * l.area);
+        if (isinf(pdf)) pdf = 0.0f;
+        return pdf;
+    }
+    f3 dcv = ref_p - pcenter;
+    float stm2 = sph.radius * sph.radius / len2(dcv);
+    float ctm = sqrtf(fmaxf(1.0f - stm2, 0.0f));
+    return 1.0f / (2.0f * PB_PI * (1.0f - ctm));  // uniform_cone_pdf
+}
+
+// Light::sample_li for every light kind on the hot path.  ref_perr / ref_n: the reference point's error bounds and normal
+// (only a sphere light's inside test looks at them, through offset_ray_origin).  SPH: sphere area lights are compiled in
+// (the kernels of the full-featured family, selected when the scene has object instances or sphere lights; the lean family
+// keeps the code -- and the register allocation -- it had without them).
+template <bool SPH = false>
+PB_D void light_sample_li(const RenderDev& R, uint32_t li, f3 ref_p, float2 u, LightSample& r, f3 ref_perr = f3(0.f, 0.f, 0.f), f3 ref_n = f3(0.f, 0.f, 0.f)) {
     const pbrt_b200_light& l = R.scene.lights[li];
     rgb L = rgb3(l.L);
     r.p1_err = f3(0.f, 0.f, 0.f); r.p1_n = f3(0.f, 0.f, 0.f);
@@ -748,7 +832,11 @@ PB_D void light_sample_li(const RenderDev& R, uint32_t li, f3 ref_p, float2 u, L
             break;
         }
         case PBRT_B200_LIGHT_DIFFUSE: {  // lights/diffuse.rs:91-106
-            triangle_light_sample(R.scene, l, ref_p, u, r);
+            if (SPH && l.shape_kind == PBRT_B200_SHAPE_SPHERE) {
+                SphereLightSample so;
+                sphere_light_sample(R.scene.self_dev, li, ref_p, ref_perr, ref_n, u.x, u.y, &so);
+                r.p1 = so.p; r.p1_err = so.p_err; r.p1_n = so.n; r.pdf = so.pdf;
+            } else triangle_light_sample(R.scene, l, ref_p, u, r);
             f3 dlt = r.p1 - ref_p;
             if (r.pdf == 0.0f || len2(dlt) == 0.0f) { r.pdf = 0.0f; r.Li = rgb(0.0f); r.wi = f3(0.f, 0.f, 0.f); return; }
             r.wi = normalize(dlt);
@@ -799,9 +887,11 @@ PB_D float triangle_light_pdf_wi(const DevScene& s, const pbrt_b200_light& l, co
     if (isinf(pdf)) pdf = 0.0f;
     return pdf;
 }
+template <bool SPH = false>
 PB_D float light_pdf_li(const RenderDev& R, uint32_t li, const Surf& ref, f3 wi) {
     const pbrt_b200_light& l = R.scene.lights[li];
-    if (l.type == PBRT_B200_LIGHT_DIFFUSE) return triangle_light_pdf_wi(R.scene, l, ref, wi);
+    if (l.type == PBRT_B200_LIGHT_DIFFUSE)
+        return (SPH && l.shape_kind == PBRT_B200_SHAPE_SPHERE) ? sphere_light_pdf_wi(R.scene.self_dev, li, ref.p, ref.p_error, ref.n, wi) : triangle_light_pdf_wi(R.scene, l, ref, wi);
     if (l.type == PBRT_B200_LIGHT_INFINITE) {  // lights/infinite.rs:131-139, Distribution2D::pdf sampling.rs:131-143
         float theta = acosf(clampf(wi.z, -1.0f, 1.0f));
         float phi = atan2f(wi.y, wi.x);
@@ -842,6 +932,7 @@ PB_D int spatial_voxel(const RenderDev& R, f3 p) {
 // compute_dsitribution, lightdistrib.rs:152-228: one CTA per voxel; thread j owns lights j, j+blockDim, ... and walks the
 // 128 Halton points in order (same accumulation order as the reference); the sum / floor / cdf passes that the reference
 // does sequentially are done by one thread so the f32 roundings match.
+template <bool SPH>
 __global__ void __launch_bounds__(128) k_spatial_build(RenderDev R, int eager, uint32_t n_eager) {
     const SpatialDev& S = R.sp;
     const uint32_t n = eager ? n_eager : S.counters[0];
@@ -869,7 +960,7 @@ __global__ void __launch_bounds__(128) k_spatial_build(RenderDev R, int eager, u
                 f3 po(lo[0] * (1.0f - h[0]) + hi[0] * h[0], lo[1] * (1.0f - h[1]) + hi[1] * h[1], lo[2] * (1.0f - h[2]) + hi[2] * h[2]);
                 LightSample ls;
                 ls.pdf = 0.0f; ls.Li = rgb(0.0f);
-                light_sample_li(R, j, po, make_float2(h[3], h[4]), ls);
+                light_sample_li<SPH>(R, j, po, make_float2(h[3], h[4]), ls);
                 if (ls.pdf > 0.0f) contrib += lum(ls.Li) / ls.pdf;
             }
             func[j] = contrib;
@@ -1041,7 +1132,7 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
                                 const pbrt_b200_light& light = R.scene.lights[ln];
                                 bool delta = is_delta_light(light);
                                 LightSample ls;
-                                light_sample_li(R, ln, si.p, ulight, ls);
+                                light_sample_li<INST>(R, ln, si.p, ulight, ls, si.p_error, si.n);
                                 float scattpdf = 0.0f;
                                 if (ls.pdf > 0.0f && !is_black(ls.Li)) {
                                     rgb f = bsdf_f<KM>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
@@ -1068,7 +1159,7 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
                                         float weight = 1.0f;
                                         bool go = true;
                                         if (!(stype & BX_SPECULAR)) {
-                                            float lpdf = light_pdf_li(R, ln, si, wi);
+                                            float lpdf = light_pdf_li<INST>(R, ln, si, wi);
                                             if (lpdf == 0.0f) go = false;
                                             else weight = power_heuristic(scattpdf, lpdf);
                                         }
@@ -1685,6 +1776,10 @@ long long mult_inverse(long long a, long long n) { long long x, y; ext_gcd(a, n,
 }  // namespace
 
 namespace {
+void launch_spatial_build(const RenderDev& R, uint32_t grid, cudaStream_t stream, int eager, uint32_t n_eager) {
+    if (R.scene.n_sphere_lights) k_spatial_build<true><<<grid, 128, 0, stream>>>(R, eager, n_eager);
+    else k_spatial_build<false><<<grid, 128, 0, stream>>>(R, eager, n_eager);
+}
 // one launch per material queue (sort/compact-by-material); INST / ZT select the kernel family (trace.cuh, PathSampler)
 template <bool INST, bool ZT>
 void launch_shade(const RenderDev& R, int parity, int grid_small, int grid_shade, cudaStream_t stream) {
@@ -1723,11 +1818,11 @@ extern "C" int pbrt_b200_light_distribution_lookup(pbrt_b200_scene* sc, uint32_t
     if (R.sp.enabled) {
         if (st->sp_eager_pending) {
             const uint32_t nv = (uint32_t)R.sp.nvox[0] * (uint32_t)R.sp.nvox[1] * (uint32_t)R.sp.nvox[2];
-            k_spatial_build<<<std::min<uint32_t>(nv, 148u * 16u), 128>>>(R, 1, nv);
+            launch_spatial_build(R, std::min<uint32_t>(nv, 148u * 16u), 0, 1, nv);
             st->sp_eager_pending = false;
         } else if (R.sp.lazy) {
             k_spatial_mark_points<<<592, 256>>>(R, d_pts, (uint32_t)n);
-            k_spatial_build<<<148 * 8, 128>>>(R, 0, 0);
+            launch_spatial_build(R, 148 * 8, 0, 0, 0);
             k_spatial_reset<<<1, 1>>>(R.sp);
         }
     }
@@ -1930,7 +2025,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
     if (st->sp_eager_pending) {  // every voxel's distribution, once per scene
         const uint32_t nv = (uint32_t)R.sp.nvox[0] * (uint32_t)R.sp.nvox[1] * (uint32_t)R.sp.nvox[2];
-        k_spatial_build<<<std::min<uint32_t>(nv, (uint32_t)sm_count * 16u), 128, 0, stream>>>(R, 1, nv);
+        launch_spatial_build(R, std::min<uint32_t>(nv, (uint32_t)sm_count * 16u), stream, 1, nv);
         PB_CUDA_TRY(cudaGetLastError());
         st->sp_eager_pending = false;
     }
@@ -1949,7 +2044,8 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         // against 619 M for drained waves: k_finish_regen's writes and the shade gathers lose their coalescing.)
         const bool drained_waves = !zt && capacity >= (1u << 22);
         unsigned long long iter = 0, batch = 0;
-        const bool inst = sc->dev.n_instances != 0;
+        const bool inst = sc->dev.n_instances != 0;                 // trace kernels: two-level walk
+        const bool full = inst || sc->dev.n_sphere_lights != 0;     // shade kernels: + instanced surfaces, sphere area lights
         for (unsigned long long wave_begin = 0; wave_begin < (zt ? 1ull : total_items);) {
         const unsigned long long wave_end = drained_waves ? std::min<unsigned long long>(wave_begin + capacity, total_items) : total_items;
         const unsigned long long loop_items = zt ? 0ull : wave_end;  // tile-serial mode: the queues themselves say when the tiles are done
@@ -1977,13 +2073,13 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (timing) mark();
                 if (R.sp.enabled && R.sp.lazy) {
                     k_spatial_mark<<<grid_small, 256, 0, stream>>>(R, parity);
-                    k_spatial_build<<<sm_count * 8, 128, 0, stream>>>(R, 0, 0);
+                    launch_spatial_build(R, (uint32_t)sm_count * 8u, stream, 0, 0);
                     k_spatial_reset<<<1, 1, 0, stream>>>(R.sp);
                     launches += 3;
                 }
                 if (R.rec.kind) {  // whitted / directlighting: one generic shade kernel, entry-indexed shadow and MIS rays
                     if (zt) k_rec_shade<true, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    else if (inst) k_rec_shade<true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    else if (full) k_rec_shade<true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
                     else k_rec_shade<false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
                     if (timing) mark();
                     if (inst) k_rec_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
@@ -1995,7 +2091,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 } else {
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
                 if (zt) launch_shade<true, true>(R, parity, grid_small, grid_shade, stream);
-                else if (inst) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
+                else if (full) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
                 else launch_shade<false, false>(R, parity, grid_small, grid_shade, stream);
                 if (timing) mark();
                 if (inst) k_trace_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);

@@ -70,6 +70,7 @@ struct DevScene {
     // struct into every kernel that might call it.
     const DevScene* self_dev;
     uint32_t n_lights;
+    uint32_t n_sphere_lights;  // diffuse area lights whose shape is a sphere: render.cu picks the kernel family that samples them
     uint32_t n_materials;
     // Scene::new preprocessing (scene.rs:32-52, distant.rs:53-60)
     float world_center[3];

@@ -645,8 +645,8 @@ class SceneBuilder:
         r["object_to_world"], r["world_to_object"], r["radius"] = o2w.m.reshape(-1), o2w.m_inv.reshape(-1), radius
         flags = (PRIM_REVERSE_ORIENTATION if self.reverse_orientation else 0) | (PRIM_SWAPS_HANDEDNESS if o2w.swaps_handedness() else 0)
         r["flags"] = flags
-        if self._area_light is not None:
-            raise B200Error("sphere area lights are outside the hot path")
+        if self._area_light is not None and self._cur_object is not None:
+            raise B200Error("Area lights not supported with object instancing (api.rs:1573-1575)")
         # Transform::transform_bounds of the object bound (transform.rs:593-605)
         rr = f32(radius)
         corners = np.array([[x, y, z] for x in (-rr, rr) for y in (-rr, rr) for z in (-rr, rr)], f32)
@@ -654,6 +654,15 @@ class SceneBuilder:
         self._bounds.append(np.concatenate([wc.min(0), wc.max(0)])[None, :])
         row = np.zeros(1, PRIM_DTYPE)
         row["shape_kind"], row["shape_index"], row["material"], row["area_light"], row["flags"] = SHAPE_SPHERE, len(self._spheres), self._material_id(), -1, flags
+        if self._area_light is not None:  # api.rs:1531-1546 + DiffuseAreaLight::new (diffuse.rs:33-66): area = Sphere::area (sphere.rs:291-293)
+            L, two = self._area_light
+            light = np.zeros(1, LIGHT_DTYPE)[0]
+            light["type"], light["two_sided"], light["L"] = LIGHT_DIFFUSE, int(two), L
+            light["shape_kind"], light["shape_index"], light["shape_flags"] = SHAPE_SPHERE, len(self._spheres), flags
+            phi_max = f32(f32(np.pi) / f32(180.0)) * f32(360.0)  # radians(clamp(phimax, 0, 360)), sphere.rs:36
+            light["area"] = phi_max * rr * (rr - (-rr))
+            row["area_light"] = len(self._lights)
+            self._lights.append(light)
         self._spheres.append(r)
         self._prims.append(row)
 

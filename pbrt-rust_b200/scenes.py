@@ -374,6 +374,60 @@ def small_mixed_scene(n=24, seed=5):
     return SceneSetup("mixed-small", flat, make, "all hot-path materials/lights/shapes at test size")
 
 
+def sphere_lights_scene(enclosing=True, tessellated=False):
+    """Sphere area lights (Sphere::sample_interaction / pdf_wi, sphere.rs:313-395): a small two-sided sphere light seen from
+    outside (cone sampling), a one-sided one (the reference's cone branch leaves the sampled normal at zero, so it only emits
+    through BSDF-sampled rays and camera hits), and -- `enclosing` -- a large two-sided sphere light around the whole scene
+    (every shading point is inside it: uniform-area branch).  `tessellated`: the small two-sided light as a 64x32 triangle
+    mesh with the same emission instead (cross-check: same image in expectation)."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.0, -6.0, 2.5), (0, 0, 0.6), (0, 0, 1))
+    b.material("matte", Kd=(0.5, 0.5, 0.5))
+    Pq, Iq = quad((-8, -8, 0), (8, -8, 0), (8, 8, 0), (-8, 8, 0))
+    b.shape("trianglemesh", P=Pq, indices=Iq)
+    b.attribute_begin()
+    b.translate(-1.2, 0.5, 0.7)
+    b.material("plastic", Kd=(0.2, 0.4, 0.7), Ks=0.3, roughness=0.1)
+    b.shape("sphere", radius=0.7)
+    b.attribute_end()
+    b.attribute_begin()
+    b.translate(1.3, 0.2, 0.6)
+    b.material("metal", roughness=0.08)
+    P, I, N = displaced_sphere(24, 12, 0.6, 0.05, 3)
+    b.shape("trianglemesh", P=P, indices=I, N=N)
+    b.attribute_end()
+    b.attribute_begin()  # two-sided sphere light, outside case
+    b.translate(0.0, 0.5, 2.6)
+    b.area_light_source("diffuse", L=(14, 13, 11), twosided=True)
+    b.material("matte", Kd=0.0)
+    if tessellated:
+        Pt, It, _ = displaced_sphere(64, 32, 0.35, 0.0, 1)
+        b.shape("trianglemesh", P=Pt, indices=It)
+    else:
+        b.shape("sphere", radius=0.35)
+    b.attribute_end()
+    b.attribute_begin()  # one-sided sphere light
+    b.translate(-2.5, -1.0, 1.6)
+    b.area_light_source("diffuse", L=(3, 6, 9))
+    b.material("matte", Kd=0.0)
+    b.shape("sphere", radius=0.3)
+    b.attribute_end()
+    if enclosing:
+        b.attribute_begin()
+        b.area_light_source("diffuse", L=(0.12, 0.14, 0.2), twosided=True)
+        b.material("matte", Kd=0.0)
+        b.shape("sphere", radius=30.0)
+        b.attribute_end()
+    flat = b.world_end()
+
+    def make(spp_=16, res=(96, 64), maxdepth_=5, sampler_="sobol", strategy="power", filt="box"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=42.0)
+        return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy)
+
+    return SceneSetup("sphere-lights", flat, make, "sphere area lights: cone-sampled, one-sided, enclosing")
+
+
 def _plant_mesh(n_blades=10, seg=6, seed=17):
     """A small procedural 'plant': n_blades curved two-sided blades of 2*seg triangles each, fanned around the z axis."""
     rng = PCG32(seed)

@@ -78,3 +78,67 @@ def test_small_paths_in_flight(pkg, oracle, gpu_lib):
     b, _ = sc.render(integ)
     sc.close()
     assert np.allclose(a, b, rtol=2e-5, atol=2e-5)
+
+
+# sphere area lights (Sphere::sample_interaction / pdf_wi): cone-sampled from outside, uniform-area from inside
+# (the enclosing light), one-sided (emits only when hit); under the path integrator's three light strategies, the recursive
+# integrators, and from a scene file
+SPHERE_LIGHT_CASES = {
+    "path-power": dict(spp_=16, res=(96, 64)),
+    "path-spatial-halton": dict(spp_=8, res=(96, 64), strategy="spatial", sampler_="halton"),
+    "path-uniform-02sequence": dict(spp_=4, res=(64, 48), strategy="uniform", sampler_="02sequence"),
+}
+
+
+@pytest.mark.parametrize("name", list(SPHERE_LIGHT_CASES))
+def test_sphere_area_lights_match_oracle(pkg, oracle, gpu_lib, name):
+    setup = pkg.scenes.sphere_lights_scene()
+    img, stats, ref, ostats = _render_both(pkg, oracle, setup, **SPHERE_LIGHT_CASES[name])
+    assert np.isfinite(img).all()
+    err = oracle.rel_mse(img, ref)
+    assert err <= REL_MSE_TOL, f"relMSE {err:.3e}"
+    assert stats.camera_rays == ostats["camera_rays"]
+    assert abs(int(stats.shadow_tests) - ostats["shadow_tests"]) <= 0.002 * ostats["shadow_tests"] + 8
+
+
+@pytest.mark.parametrize("kind", ["whitted", "all", "one"])
+def test_sphere_area_lights_recursive_integrators(pkg, oracle, gpu_lib, kind):
+    setup = pkg.scenes.sphere_lights_scene()
+    base = setup.make_integrator(spp_=8, res=(80, 56))
+    H = pkg.host
+    integ = H.WhittedIntegrator(base.camera, base.film, base.sampler) if kind == "whitted" else H.DirectLightingIntegrator(base.camera, base.film, base.sampler, strategy=kind)
+    sc = pkg.Scene(setup.flat)
+    img, stats = integ.render(sc)
+    sc.close()
+    ref, ostats = oracle.render_image(setup.flat, integ)
+    err = oracle.rel_mse(img, ref)
+    assert err <= REL_MSE_TOL, f"relMSE {err:.3e}"
+    assert stats.camera_rays == ostats["camera_rays"]
+
+
+def test_sphere_area_light_from_a_scene_file(pkg, oracle, gpu_lib):
+    text = '''LookAt 0 -6 2.5  0 0 .8  0 0 1
+Camera "perspective" "float fov" 45
+Film "image" "integer xresolution" [72] "integer yresolution" [48]
+Sampler "sobol" "integer pixelsamples" 8
+Integrator "path" "integer maxdepth" 4
+WorldBegin
+Material "matte" "rgb Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-8 -8 0 8 -8 0 8 8 0 -8 8 0]
+AttributeBegin
+  Translate 0 0 2.2
+  AreaLightSource "diffuse" "rgb L" [9 8 7] "bool twosided" "true"
+  Shape "sphere" "float radius" .4
+AttributeEnd
+AttributeBegin
+  Translate -1.5 .5 .6
+  Material "glass"
+  Shape "sphere" "float radius" .6
+AttributeEnd
+WorldEnd
+'''
+    job = pkg.pbrt_parse_string(text).jobs[0]
+    assert len(job.flat.lights) == 1 and job.flat.lights[0]["shape_kind"] == pkg.host.SHAPE_SPHERE and job.flat.lights[0]["two_sided"] == 1
+    img, stats = job.render(device=0)
+    ref, ostats = oracle.render_image(job.flat, job.integrator)
+    assert oracle.rel_mse(img, ref) <= REL_MSE_TOL and stats.camera_rays == ostats["camera_rays"]
