@@ -47,7 +47,7 @@ def test_one_sided_sphere_light_emits_only_when_hit(oracle):
     assert 20 < lit.sum() < 200 and img[lit].max() <= 5.0 + 1e-4 and np.isclose(img.max(), 5.0, atol=1e-4)
     path = H.PathIntegrator(cam, film, H.Sampler("sobol", 16), maxdepth=2, lightsamplestrategy="uniform")
     img2, _ = oracle.render_image(flat, path)
-    assert (img2.sum(axis=2) > 0).sum() > 600  # BSDF-sampled rays that hit the light do see its emission
+    assert (img2.sum(axis=2) > 0).sum() > 3 * lit.sum()  # BSDF-sampled rays that hit the light do see its emission
 
 
 def test_sphere_lights_golden(oracle):
