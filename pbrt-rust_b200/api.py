@@ -53,6 +53,25 @@ class RenderJob:
         finally:
             scene.close()
 
+    @staticmethod
+    def write_image(path, image):
+        """Film::write_image hands the resolved linear RGB image to an encoder chosen by extension (film.rs:217-264,
+        imageio.rs:42-66).  Image encoders are outside this repo's scope: `.pfm` (the reference writes it too,
+        imageio.rs) and `.npy` are written here; any other extension is replaced by `.pfm` and the path actually written is
+        returned."""
+        path = str(path)
+        img = np.ascontiguousarray(image, np.float32)
+        if path.lower().endswith(".npy"):
+            np.save(path, img)
+            return path
+        if not path.lower().endswith(".pfm"):
+            path = os.path.splitext(path)[0] + ".pfm"
+        h, w = img.shape[:2]
+        with open(path, "wb") as f:  # PFM: bottom-to-top scanlines, negative scale = little endian
+            f.write(b"PF\n%d %d\n-1.0\n" % (w, h))
+            f.write(img[::-1].astype("<f4").tobytes())
+        return path
+
 
 class _GraphicsState:
     def __init__(self):
