@@ -81,3 +81,21 @@ def test_written_s3_scene_file_renders_like_the_generator(pkg, oracle, gpu_lib, 
     b, _ = integ.render(sc)
     sc.close()
     assert np.array_equal(a, b) or np.allclose(a, b, rtol=2e-5, atol=2e-5)  # same tables, same descriptor; only atomics order differs
+
+
+def test_command_line_renderer(pkg, gpu_lib, tmp_path):
+    """tools/render_file.py = the reference's `pbrt-rust scene.pbrt --outfile ...` for this path: scene file in, PFM out."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    scene = root / "tests" / "golden" / "reference_spheres_scene.pbrt"
+    out = tmp_path / "spheres.pfm"
+    r = subprocess.run([sys.executable, str(root / "tools" / "render_file.py"), str(scene), "--outfile", str(out), "--cropwindow", "0.25", "0.75", "0.2", "0.8"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = out.read_bytes()
+    hdr, body = raw.split(b"-1.0\n", 1)
+    assert hdr == b"PF\n500 300\n"
+    img = np.frombuffer(body, "<f4").reshape(300, 500, 3)
+    assert np.isfinite(img).all() and 0.05 < img.mean() < 1.0
