@@ -237,7 +237,7 @@ PB_D SlabPair slab_fast2(float2 nx, float2 ny, float2 nz, float2 fx, float2 fy, 
  * world's, plus the sentinel and the rest-of-leaf entry */
 /* the quad walk descends two binary levels per step and can stack three siblings: 3 * 64 / 2 entries for the deepest tree
  * scene_create accepts (depth <= 64) */
-#define PB_STACK_SIZE(INST) ((INST) ? 2 * PB_STACK_DEPTH + 2 : 3 * PB_STACK_DEPTH / 2)
+#define PB_STACK_SIZE(INST) ((INST) ? 3 * PB_STACK_DEPTH + 2 : 3 * PB_STACK_DEPTH / 2)
 #define PB_DONE 0xffffffffu /* traversal finished (has the leaf bit set so the interior loop exits) */
 
 // Per-ray traversal state.  The order of box and primitive tests is the reference's
@@ -333,6 +333,8 @@ PB_D void xf_ray(const float* M, f3 o, f3 d, float t_max, f3* o_out, f3* d_out, 
         }                                                               \
     } while (0)
 
+template <bool ANY> PB_D void quad_step(const DevScene& s, TravRay& r, uint2* stack);  // defined below (quad nodes)
+
 // Runs the ray until it finishes, or (when `yield_below` > 0) until fewer than `yield_below`
 // lanes of the warp are still traversing, so that the caller can refill idle lanes.
 // TOP: walking the scene's aggregate (leaf slots may be TransformedPrimitives); false inside an instanced object, where
@@ -342,6 +344,14 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
     while (r.cur != PB_DONE) {
         // ---- interior nodes
         while (!(r.cur & PB_LEAF_BIT)) {
+#if PB_QUAD_NODES
+            // two-level walk: the ray changes at instance boundaries, so the NaN-free test is chosen per node visit
+            if (EXACT_NAN && TOP && !r.nan_possible) {
+                quad_step<ANY>(s, r, stack);
+                if (interior_min > 0 && __popc(__activemask()) < interior_min) break;
+                continue;
+            }
+#endif
             const float4* np = s.nodes + 4ull * r.cur;
             float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
             uint32_t ref0 = __float_as_uint(q3.x), ref1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z);
@@ -491,36 +501,40 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
 // re-checked against the current t_max when popped, as in the binary walk.  Only for rays without zero direction
 // components (slab_fast's precondition; the others take the binary, NaN-exact walk).
 template <bool ANY>
+PB_D void quad_step(const DevScene& s, TravRay& r, uint2* stack) {
+    const float4* np = s.quads + 8ull * r.cur;
+    const float4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2), b0 = __ldg(np + 3), b1 = __ldg(np + 4), b2 = __ldg(np + 5), q6 = __ldg(np + 6), q7 = __ldg(np + 7);
+    SlabPair pa = slab_fast2(r.ngx ? make_float2(a1.z, a1.w) : make_float2(a0.x, a0.y), r.ngy ? make_float2(a2.x, a2.y) : make_float2(a0.z, a0.w),
+                             r.ngz ? make_float2(a2.z, a2.w) : make_float2(a1.x, a1.y), r.ngx ? make_float2(a0.x, a0.y) : make_float2(a1.z, a1.w),
+                             r.ngy ? make_float2(a0.z, a0.w) : make_float2(a2.x, a2.y), r.ngz ? make_float2(a1.x, a1.y) : make_float2(a2.z, a2.w),
+                             r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
+    SlabPair pb = slab_fast2(r.ngx ? make_float2(b1.z, b1.w) : make_float2(b0.x, b0.y), r.ngy ? make_float2(b2.x, b2.y) : make_float2(b0.z, b0.w),
+                             r.ngz ? make_float2(b2.z, b2.w) : make_float2(b1.x, b1.y), r.ngx ? make_float2(b0.x, b0.y) : make_float2(b1.z, b1.w),
+                             r.ngy ? make_float2(b0.z, b0.w) : make_float2(b2.x, b2.y), r.ngz ? make_float2(b1.x, b1.y) : make_float2(b2.z, b2.w),
+                             r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
+    const float tA0 = pa.ok0 ? pa.tmin0 : PB_INF, tA1 = pa.ok1 ? pa.tmin1 : PB_INF, tB0 = pb.ok0 ? pb.tmin0 : PB_INF, tB1 = pb.ok1 ? pb.tmin1 : PB_INF;
+    const uint32_t meta = __float_as_uint(q7.x);
+    const bool g = (r.negmask >> (meta & 3u)) & 1u, sA = (r.negmask >> ((meta >> 2) & 3u)) & 1u, sB = (r.negmask >> ((meta >> 4) & 3u)) & 1u;
+    // reference order inside each group, then of the groups
+    const float tAn = sA ? tA1 : tA0, tAf = sA ? tA0 : tA1, tBn = sB ? tB1 : tB0, tBf = sB ? tB0 : tB1;
+    const uint32_t rAn = __float_as_uint(sA ? q6.y : q6.x), rAf = __float_as_uint(sA ? q6.x : q6.y);
+    const uint32_t rBn = __float_as_uint(sB ? q6.w : q6.z), rBf = __float_as_uint(sB ? q6.z : q6.w);
+    const float t0 = g ? tBn : tAn, t1 = g ? tBf : tAf, t2 = g ? tAn : tBn, t3 = g ? tAf : tBf;
+    const uint32_t r0 = g ? rBn : rAn, r1 = g ? rBf : rAf, r2 = g ? rAn : rBn, r3 = g ? rAf : rBf;
+    // the first slot that passes is visited now; the others wait on the stack, nearest on top
+    uint32_t nref = PB_DONE; float ntm = 0.0f;
+    if (t3 < r.t_max) { nref = r3; ntm = t3; }
+    if (t2 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r2; ntm = t2; }
+    if (t1 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r1; ntm = t1; }
+    if (t0 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r0; ntm = t0; }
+    if (nref != PB_DONE) r.cur = nref;
+    else PB_TRAV_POP(r, stack);
+}
+template <bool ANY>
 PB_D void trav_run_quad(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
     while (r.cur != PB_DONE) {
         while (!(r.cur & PB_LEAF_BIT)) {
-            const float4* np = s.quads + 8ull * r.cur;
-            const float4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2), b0 = __ldg(np + 3), b1 = __ldg(np + 4), b2 = __ldg(np + 5), q6 = __ldg(np + 6), q7 = __ldg(np + 7);
-            SlabPair pa = slab_fast2(r.ngx ? make_float2(a1.z, a1.w) : make_float2(a0.x, a0.y), r.ngy ? make_float2(a2.x, a2.y) : make_float2(a0.z, a0.w),
-                                     r.ngz ? make_float2(a2.z, a2.w) : make_float2(a1.x, a1.y), r.ngx ? make_float2(a0.x, a0.y) : make_float2(a1.z, a1.w),
-                                     r.ngy ? make_float2(a0.z, a0.w) : make_float2(a2.x, a2.y), r.ngz ? make_float2(a1.x, a1.y) : make_float2(a2.z, a2.w),
-                                     r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
-            SlabPair pb = slab_fast2(r.ngx ? make_float2(b1.z, b1.w) : make_float2(b0.x, b0.y), r.ngy ? make_float2(b2.x, b2.y) : make_float2(b0.z, b0.w),
-                                     r.ngz ? make_float2(b2.z, b2.w) : make_float2(b1.x, b1.y), r.ngx ? make_float2(b0.x, b0.y) : make_float2(b1.z, b1.w),
-                                     r.ngy ? make_float2(b0.z, b0.w) : make_float2(b2.x, b2.y), r.ngz ? make_float2(b1.x, b1.y) : make_float2(b2.z, b2.w),
-                                     r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
-            const float tA0 = pa.ok0 ? pa.tmin0 : PB_INF, tA1 = pa.ok1 ? pa.tmin1 : PB_INF, tB0 = pb.ok0 ? pb.tmin0 : PB_INF, tB1 = pb.ok1 ? pb.tmin1 : PB_INF;
-            const uint32_t meta = __float_as_uint(q7.x);
-            const bool g = (r.negmask >> (meta & 3u)) & 1u, sA = (r.negmask >> ((meta >> 2) & 3u)) & 1u, sB = (r.negmask >> ((meta >> 4) & 3u)) & 1u;
-            // reference order inside each group, then of the groups
-            const float tAn = sA ? tA1 : tA0, tAf = sA ? tA0 : tA1, tBn = sB ? tB1 : tB0, tBf = sB ? tB0 : tB1;
-            const uint32_t rAn = __float_as_uint(sA ? q6.y : q6.x), rAf = __float_as_uint(sA ? q6.x : q6.y);
-            const uint32_t rBn = __float_as_uint(sB ? q6.w : q6.z), rBf = __float_as_uint(sB ? q6.z : q6.w);
-            const float t0 = g ? tBn : tAn, t1 = g ? tBf : tAf, t2 = g ? tAn : tBn, t3 = g ? tAf : tBf;
-            const uint32_t r0 = g ? rBn : rAn, r1 = g ? rBf : rAf, r2 = g ? rAn : rBn, r3 = g ? rAf : rBf;
-            // the first slot that passes is visited now; the others wait on the stack, nearest on top
-            uint32_t nref = PB_DONE; float ntm = 0.0f;
-            if (t3 < r.t_max) { nref = r3; ntm = t3; }
-            if (t2 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r2; ntm = t2; }
-            if (t1 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r1; ntm = t1; }
-            if (t0 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r0; ntm = t0; }
-            if (nref != PB_DONE) r.cur = nref;
-            else PB_TRAV_POP(r, stack);
+            quad_step<ANY>(s, r, stack);
             if (interior_min > 0 && __popc(__activemask()) < interior_min) break;
         }
         if (r.cur == PB_DONE) break;
