@@ -613,6 +613,19 @@ __global__ void __launch_bounds__(256) k_init_slots(RenderDev R, uint32_t count)
 // ---------------------------------------------------------------------------
 // K2: closest-hit for path rays (persistent ray queue), K4: compaction by material
 // ---------------------------------------------------------------------------
+// hit record + material bin of a path's closest-hit ray
+PB_D int store_closest_hit(const RenderDev& R, uint32_t id, const TravRay& r) {
+    R.hit[id] = make_uint4(r.hit.slot, __float_as_uint(r.hit.t), __float_as_uint(r.hit.b0), __float_as_uint(r.hit.b1));
+    R.hit_b2[id] = r.hit.b2;
+    if (R.scene.n_instances) R.hit_inst[id] = r.hit.inst;
+    int bin = Q_MISS;
+    if (r.found) {
+        int m = R.scene.prims[r.hit.slot].material;
+        bin = m < 0 ? Q_NOMAT : (int)R.scene.materials[m].type;
+    }
+    R.hit_bin[id] = (uint8_t)bin;
+    return bin;
+}
 struct PathClosestJob {
     RenderDev* R; const uint32_t* q;
     PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
@@ -621,18 +634,7 @@ struct PathClosestJob {
         *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
         return true;
     }
-    PB_D void store(uint32_t i, const TravRay& r) const {
-        uint32_t id = q[i];
-        R->hit[id] = make_uint4(r.hit.slot, __float_as_uint(r.hit.t), __float_as_uint(r.hit.b0), __float_as_uint(r.hit.b1));
-        R->hit_b2[id] = r.hit.b2;
-        if (R->scene.n_instances) R->hit_inst[id] = r.hit.inst;
-        int bin = Q_MISS;
-        if (r.found) {
-            int m = R->scene.prims[r.hit.slot].material;
-            bin = m < 0 ? Q_NOMAT : (int)R->scene.materials[m].type;
-        }
-        R->hit_bin[id] = (uint8_t)bin;
-    }
+    PB_D void store(uint32_t i, const TravRay& r) const { store_closest_hit(*R, q[i], r); }
 };
 
 template <bool INST>
@@ -1057,176 +1059,194 @@ template <> struct BinKinds<Q_MIRROR> { static constexpr int KM = KM_MIRROR, MAT
 template <> struct BinKinds<Q_GLASS> { static constexpr int KM = KM_GLASS, MAT = PBRT_B200_MAT_GLASS; };
 template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT = PBRT_B200_MAT_METAL; };
 
+// One path of a material queue: PathIntegrator::li from the hit to the next ray (path.rs:104-214).  Shared by the wavefront
+// kernel k_shade and the tile-serial megakernel k_zt_mega.
+struct ShadeOut { bool push_next, push_shadow, push_mis, push_dead, zero_rad; };
+template <int BIN, bool INST, bool ZT>
+PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
+    constexpr int KM = BinKinds<BIN>::KM;
+    (void)KM;
+    bool push_next = false, push_shadow = false, push_mis = false, push_dead = false, zero_rad = false;
+    {
+    float4 ra = R.ray[2 * id], rb = R.ray[2 * id + 1];
+    f3 ro(ra.x, ra.y, ra.z), rd(rb.x, rb.y, rb.z);
+    float time = rb.w;
+    float4 Le = R.L_eta[id], bs = R.beta_st[id];
+    rgb L(Le.x, Le.y, Le.z), beta(bs.x, bs.y, bs.z);
+    float etascale = Le.w;
+    uint32_t st = __float_as_uint(bs.w);
+    uint32_t bounces = st & 0xffffu;
+    bool specular_bounce = (st >> 16) & 1u;
+    if (BIN == Q_MISS) {
+        // path.rs:106-120: escaped ray
+        if (bounces == 0 || specular_bounce)
+            for (uint32_t k = 0; k < R.n_infinite; ++k) L = L + rgb3(R.scene.lights[R.infinite_lights[k]].L) * beta;
+        R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+        push_dead = true;
+    } else {
+        uint4 h = R.hit[id];
+        uint32_t fl;
+        const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
+        Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
+        const pbrt_b200_prim pr = R.scene.prims[h.x];
+        // SurfaceInteraction::le, interaction.rs:344-349 + AreaLight::l, diffuse.rs:68-75
+        if ((bounces == 0 || specular_bounce) && pr.area_light >= 0) {
+            const pbrt_b200_light& al = R.scene.lights[pr.area_light];
+            if (al.two_sided || dot(si.n, -rd) > 0.0f) L = L + rgb3(al.L) * beta;
+        }
+        if (bounces >= (uint32_t)R.max_depth) {
+            R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+            push_dead = true;
+        } else {
+            Bsdf bsdf;
+            bsdf.valid = false;
+            if (BIN != Q_NOMAT && BIN != Q_MISS) material_bsdf<BinKinds<BIN>::MAT>(R.scene.materials[pr.material], si, bsdf);
+            if (!bsdf.valid) {
+                // path.rs:124-129: skip the surface, bounces NOT incremented
+                f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
+                store_ray(R.ray, id, o, rd, PB_INF, time);
+                R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                push_next = true;
+            } else {
+                PathSampler<ZT> smp;
+                smp.begin(R, id);
+                const int NONSPEC = BX_ALL & ~BX_SPECULAR;
+                // ---- uniform_sample_onelight + estimate_direct, integrator.rs:81-237
+                if (bsdf_count(bsdf, NONSPEC) > 0 && R.n_lights > 0) {
+                    float u1 = smp.get_1d();
+                    // light_distrib.lookup(isect.p), path.rs:132
+                    const float* ld_cdf = R.ld_cdf; const float* ld_func = R.ld_func; float ld_func_int = R.ld_func_int;
+                    if (R.sp.enabled) {
+                        int sl = R.sp.slot[spatial_voxel(R, si.p)];
+                        if (sl >= 0) { ld_cdf = R.sp.cdf + (size_t)sl * (R.n_lights + 1); ld_func = R.sp.func + (size_t)sl * R.n_lights; ld_func_int = R.sp.func_int[sl]; }
+                        else atomicExch(R.sp.counters + 2, 1u);  // cannot happen unless the slot table overflowed: the host fails the call
+                    }
+                    uint32_t ln = find_interval_cdf(ld_cdf, (int)R.n_lights + 1, u1);  // Distribution1D::sample_discrete
+                    float selpdf = ld_func_int > 0.0f ? ld_func[ln] / (ld_func_int * (float)R.n_lights) : 0.0f;
+                    bool zero = true;
+                    if (selpdf != 0.0f) {
+                        float2 ulight = smp.get_2d();
+                        float2 uscatt = smp.get_2d();
+                        const pbrt_b200_light& light = R.scene.lights[ln];
+                        bool delta = is_delta_light(light);
+                        LightSample ls;
+                        light_sample_li<INST>(R, ln, si.p, ulight, ls, si.p_error, si.n);
+                        float scattpdf = 0.0f;
+                        if (ls.pdf > 0.0f && !is_black(ls.Li)) {
+                            rgb f = bsdf_f<KM>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
+                            scattpdf = bsdf_pdf<KM>(bsdf, si.wo, ls.wi, NONSPEC);
+                            if (!is_black(f)) {
+                                // VisibilityTester::unoccluded -> spawn_rayto_interaction, interaction.rs:46-52
+                                f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
+                                f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
+                                f3 d = tg - o;
+                                rgb Ld = delta ? f * ls.Li / ls.pdf : f * ls.Li * power_heuristic(ls.pdf, scattpdf) / ls.pdf;
+                                rgb add = beta * (Ld / selpdf);
+                                store_ray(R.sh_ray, id, o, d, 1.0f - PB_SHADOW_EPSILON, time);
+                                R.sh_contrib[id] = make_float4(add.r, add.g, add.b, 0.f);
+                                push_shadow = true;
+                                zero = false;
+                            }
+                        }
+                        if (!delta) {
+                            f3 wi(0.f, 0.f, 0.f);
+                            int stype = 0;
+                            rgb f = bsdf_sample<KM>(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
+                            f = f * absdot(wi, si.sh_n);
+                            if (!is_black(f) && scattpdf > 0.0f) {
+                                float weight = 1.0f;
+                                bool go = true;
+                                if (!(stype & BX_SPECULAR)) {
+                                    float lpdf = light_pdf_li<INST>(R, ln, si, wi);
+                                    if (lpdf == 0.0f) go = false;
+                                    else weight = power_heuristic(scattpdf, lpdf);
+                                }
+                                if (go) {
+                                    f3 o = offset_ray_origin(si.p, si.p_error, si.n, wi);
+                                    rgb fac = beta * (f * weight / scattpdf / selpdf);
+                                    store_ray(R.mis_ray, id, o, wi, PB_INF, time);
+                                    R.mis_contrib[id] = make_float4(fac.r, fac.g, fac.b, __uint_as_float(ln));
+                                    push_mis = true;
+                                    zero = false;
+                                }
+                            }
+                        }
+                    }
+                    zero_rad = zero;
+                }
+                // ---- sample the BSDF for the next direction, path.rs:147-174
+                f3 wo = -rd, wi(0.f, 0.f, 0.f);
+                float pdf = 0.0f;
+                int flags = 0;
+                float2 ub = smp.get_2d();
+                rgb f = bsdf_sample<KM>(bsdf, wo, &wi, ub, &pdf, BX_ALL, &flags);
+                bool alive = !(is_black(f) || pdf == 0.0f);
+                if (alive) {
+                    beta = beta * (f * absdot(wi, si.sh_n) / pdf);
+                    specular_bounce = (flags & BX_SPECULAR) != 0;
+                    if ((flags & BX_SPECULAR) && (flags & BX_TRANSMISSION)) {
+                        float eta = bsdf.eta;
+                        etascale *= (dot(wo, si.n) > 0.0f) ? eta * eta : 1.0f / (eta * eta);
+                    }
+                    f3 o = offset_ray_origin(si.p, si.p_error, si.n, wi);
+                    // Russian roulette, path.rs:206-214
+                    rgb rrbeta = beta * etascale;
+                    float mc = max_comp(rrbeta);
+                    if (mc < R.rr_threshold && bounces > 3) {
+                        float qv = fmaxf(1.0f - mc, 0.05f);
+                        if (smp.get_1d() < qv) alive = false;
+                        else beta = beta / (1.0f - qv);
+                    }
+                    if (alive) {
+                        store_ray(R.ray, id, o, wi, PB_INF, time);
+                        bounces += 1;
+                        R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(bounces | (specular_bounce ? 0x10000u : 0u)));
+                        push_next = true;
+                    }
+                }
+                if (!alive) push_dead = true;
+                R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                smp.end(R, id);
+            }
+        }
+    }
+    }
+    return ShadeOut{push_next, push_shadow, push_mis, push_dead, zero_rad};
+}
+
 template <int BIN, bool INST, bool ZT>
 __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
-    constexpr int KM = BinKinds<BIN>::KM;
     const uint32_t n = R.cnt->n_mat[BIN];
     const uint32_t* q = R.q_mat[BIN];
     uint32_t* q_next = R.q_path[parity ^ 1];
     const uint32_t nround = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
-        bool valid = i < n;
-        bool push_next = false, push_shadow = false, push_mis = false, push_dead = false, zero_rad = false;
+        ShadeOut o = {false, false, false, false, false};
         uint32_t id = 0;
-        if (valid) {
+        if (i < n) {
             id = q[i];
-            float4 ra = R.ray[2 * id], rb = R.ray[2 * id + 1];
-            f3 ro(ra.x, ra.y, ra.z), rd(rb.x, rb.y, rb.z);
-            float time = rb.w;
-            float4 Le = R.L_eta[id], bs = R.beta_st[id];
-            rgb L(Le.x, Le.y, Le.z), beta(bs.x, bs.y, bs.z);
-            float etascale = Le.w;
-            uint32_t st = __float_as_uint(bs.w);
-            uint32_t bounces = st & 0xffffu;
-            bool specular_bounce = (st >> 16) & 1u;
-            if (BIN == Q_MISS) {
-                // path.rs:106-120: escaped ray
-                if (bounces == 0 || specular_bounce)
-                    for (uint32_t k = 0; k < R.n_infinite; ++k) L = L + rgb3(R.scene.lights[R.infinite_lights[k]].L) * beta;
-                R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
-                push_dead = true;
-            } else {
-                uint4 h = R.hit[id];
-                uint32_t fl;
-                const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
-                Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
-                const pbrt_b200_prim pr = R.scene.prims[h.x];
-                // SurfaceInteraction::le, interaction.rs:344-349 + AreaLight::l, diffuse.rs:68-75
-                if ((bounces == 0 || specular_bounce) && pr.area_light >= 0) {
-                    const pbrt_b200_light& al = R.scene.lights[pr.area_light];
-                    if (al.two_sided || dot(si.n, -rd) > 0.0f) L = L + rgb3(al.L) * beta;
-                }
-                if (bounces >= (uint32_t)R.max_depth) {
-                    R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
-                    push_dead = true;
-                } else {
-                    Bsdf bsdf;
-                    bsdf.valid = false;
-                    if (BIN != Q_NOMAT && BIN != Q_MISS) material_bsdf<BinKinds<BIN>::MAT>(R.scene.materials[pr.material], si, bsdf);
-                    if (!bsdf.valid) {
-                        // path.rs:124-129: skip the surface, bounces NOT incremented
-                        f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
-                        store_ray(R.ray, id, o, rd, PB_INF, time);
-                        R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
-                        push_next = true;
-                    } else {
-                        PathSampler<ZT> smp;
-                        smp.begin(R, id);
-                        const int NONSPEC = BX_ALL & ~BX_SPECULAR;
-                        // ---- uniform_sample_onelight + estimate_direct, integrator.rs:81-237
-                        if (bsdf_count(bsdf, NONSPEC) > 0 && R.n_lights > 0) {
-                            float u1 = smp.get_1d();
-                            // light_distrib.lookup(isect.p), path.rs:132
-                            const float* ld_cdf = R.ld_cdf; const float* ld_func = R.ld_func; float ld_func_int = R.ld_func_int;
-                            if (R.sp.enabled) {
-                                int sl = R.sp.slot[spatial_voxel(R, si.p)];
-                                if (sl >= 0) { ld_cdf = R.sp.cdf + (size_t)sl * (R.n_lights + 1); ld_func = R.sp.func + (size_t)sl * R.n_lights; ld_func_int = R.sp.func_int[sl]; }
-                                else atomicExch(R.sp.counters + 2, 1u);  // cannot happen unless the slot table overflowed: the host fails the call
-                            }
-                            uint32_t ln = find_interval_cdf(ld_cdf, (int)R.n_lights + 1, u1);  // Distribution1D::sample_discrete
-                            float selpdf = ld_func_int > 0.0f ? ld_func[ln] / (ld_func_int * (float)R.n_lights) : 0.0f;
-                            bool zero = true;
-                            if (selpdf != 0.0f) {
-                                float2 ulight = smp.get_2d();
-                                float2 uscatt = smp.get_2d();
-                                const pbrt_b200_light& light = R.scene.lights[ln];
-                                bool delta = is_delta_light(light);
-                                LightSample ls;
-                                light_sample_li<INST>(R, ln, si.p, ulight, ls, si.p_error, si.n);
-                                float scattpdf = 0.0f;
-                                if (ls.pdf > 0.0f && !is_black(ls.Li)) {
-                                    rgb f = bsdf_f<KM>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
-                                    scattpdf = bsdf_pdf<KM>(bsdf, si.wo, ls.wi, NONSPEC);
-                                    if (!is_black(f)) {
-                                        // VisibilityTester::unoccluded -> spawn_rayto_interaction, interaction.rs:46-52
-                                        f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
-                                        f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
-                                        f3 d = tg - o;
-                                        rgb Ld = delta ? f * ls.Li / ls.pdf : f * ls.Li * power_heuristic(ls.pdf, scattpdf) / ls.pdf;
-                                        rgb add = beta * (Ld / selpdf);
-                                        store_ray(R.sh_ray, id, o, d, 1.0f - PB_SHADOW_EPSILON, time);
-                                        R.sh_contrib[id] = make_float4(add.r, add.g, add.b, 0.f);
-                                        push_shadow = true;
-                                        zero = false;
-                                    }
-                                }
-                                if (!delta) {
-                                    f3 wi(0.f, 0.f, 0.f);
-                                    int stype = 0;
-                                    rgb f = bsdf_sample<KM>(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
-                                    f = f * absdot(wi, si.sh_n);
-                                    if (!is_black(f) && scattpdf > 0.0f) {
-                                        float weight = 1.0f;
-                                        bool go = true;
-                                        if (!(stype & BX_SPECULAR)) {
-                                            float lpdf = light_pdf_li<INST>(R, ln, si, wi);
-                                            if (lpdf == 0.0f) go = false;
-                                            else weight = power_heuristic(scattpdf, lpdf);
-                                        }
-                                        if (go) {
-                                            f3 o = offset_ray_origin(si.p, si.p_error, si.n, wi);
-                                            rgb fac = beta * (f * weight / scattpdf / selpdf);
-                                            store_ray(R.mis_ray, id, o, wi, PB_INF, time);
-                                            R.mis_contrib[id] = make_float4(fac.r, fac.g, fac.b, __uint_as_float(ln));
-                                            push_mis = true;
-                                            zero = false;
-                                        }
-                                    }
-                                }
-                            }
-                            zero_rad = zero;
-                        }
-                        // ---- sample the BSDF for the next direction, path.rs:147-174
-                        f3 wo = -rd, wi(0.f, 0.f, 0.f);
-                        float pdf = 0.0f;
-                        int flags = 0;
-                        float2 ub = smp.get_2d();
-                        rgb f = bsdf_sample<KM>(bsdf, wo, &wi, ub, &pdf, BX_ALL, &flags);
-                        bool alive = !(is_black(f) || pdf == 0.0f);
-                        if (alive) {
-                            beta = beta * (f * absdot(wi, si.sh_n) / pdf);
-                            specular_bounce = (flags & BX_SPECULAR) != 0;
-                            if ((flags & BX_SPECULAR) && (flags & BX_TRANSMISSION)) {
-                                float eta = bsdf.eta;
-                                etascale *= (dot(wo, si.n) > 0.0f) ? eta * eta : 1.0f / (eta * eta);
-                            }
-                            f3 o = offset_ray_origin(si.p, si.p_error, si.n, wi);
-                            // Russian roulette, path.rs:206-214
-                            rgb rrbeta = beta * etascale;
-                            float mc = max_comp(rrbeta);
-                            if (mc < R.rr_threshold && bounces > 3) {
-                                float qv = fmaxf(1.0f - mc, 0.05f);
-                                if (smp.get_1d() < qv) alive = false;
-                                else beta = beta / (1.0f - qv);
-                            }
-                            if (alive) {
-                                store_ray(R.ray, id, o, wi, PB_INF, time);
-                                bounces += 1;
-                                R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(bounces | (specular_bounce ? 0x10000u : 0u)));
-                                push_next = true;
-                            }
-                        }
-                        if (!alive) push_dead = true;
-                        R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
-                        smp.end(R, id);
-                    }
-                }
-            }
+            o = shade_path<BIN, INST, ZT>(R, id);
         }
         {
-            unsigned zm = __ballot_sync(__activemask(), zero_rad);
+            unsigned zm = __ballot_sync(__activemask(), o.zero_rad);
             if (zm && (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&R.cnt->zero_radiance, (unsigned long long)__popc(zm));
         }
-        queue_push(q_next, &R.cnt->n_next, id, push_next);
-        queue_push(R.q_shadow, &R.cnt->n_shadow, id, push_shadow);
-        queue_push(R.q_mis, &R.cnt->n_mis, id, push_mis);
-        queue_push(R.q_dead[parity], &R.cnt->n_dead, id, push_dead);
+        queue_push(q_next, &R.cnt->n_next, id, o.push_next);
+        queue_push(R.q_shadow, &R.cnt->n_shadow, id, o.push_shadow);
+        queue_push(R.q_mis, &R.cnt->n_mis, id, o.push_mis);
+        queue_push(R.q_dead[parity], &R.cnt->n_dead, id, o.push_dead);
     }
 }
 
 // ---------------------------------------------------------------------------
 // K3: shadow rays (VisibilityTester::unoccluded, core/light.rs:120-123)
 // ---------------------------------------------------------------------------
+PB_D void shadow_unoccluded(const RenderDev& R, uint32_t id) {  // the light sample's contribution reaches the path
+    float4 c = R.sh_contrib[id];
+    float4 L = R.L_eta[id];
+    L.x += c.x; L.y += c.y; L.z += c.z;
+    R.L_eta[id] = L;
+}
 struct ShadowJob {
     RenderDev* R;
     PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
@@ -1237,11 +1257,7 @@ struct ShadowJob {
     }
     PB_D void store(uint32_t i, const TravRay& r) const {
         if (r.found) return;
-        uint32_t id = R->q_shadow[i];
-        float4 c = R->sh_contrib[id];
-        float4 L = R->L_eta[id];
-        L.x += c.x; L.y += c.y; L.z += c.z;
-        R->L_eta[id] = L;
+        shadow_unoccluded(*R, R->q_shadow[i]);
     }
 };
 template <bool INST>
@@ -1253,6 +1269,30 @@ __global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
 // ---------------------------------------------------------------------------
 // K7: MIS rays (estimate_direct's BSDF-sampled branch, integrator.rs:205-234)
 // ---------------------------------------------------------------------------
+// estimate_direct's BSDF-sampled ray came back (integrator.rs:205-234): emission of the sampled light if the ray found it
+template <bool INST>
+PB_D void mis_resolve(const RenderDev& R, uint32_t id, const TravRay& r) {
+    float4 c = R.mis_contrib[id];
+    uint32_t ln = __float_as_uint(c.w);
+    rgb li(0.0f);
+    if (r.found) {
+        const pbrt_b200_prim pr = R.scene.prims[r.hit.slot];
+        if (pr.area_light == (int)ln) {  // Arc::ptr_eq(light, hit primitive's area light)
+            uint32_t fl;
+            Surf ls = surface_at_hit<INST>(R.scene, r.hit.inst, r.hit.slot, r.o, r.d, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
+            const pbrt_b200_light& al = R.scene.lights[ln];
+            if (al.two_sided || dot(ls.n, -r.d) > 0.0f) li = rgb3(al.L);
+        }
+    } else {
+        const pbrt_b200_light& l = R.scene.lights[ln];
+        if (l.type == PBRT_B200_LIGHT_INFINITE) li = rgb3(l.L);  // light.le(ray)
+    }
+    if (!is_black(li)) {
+        float4 L = R.L_eta[id];
+        L.x += c.x * li.r; L.y += c.y * li.g; L.z += c.z * li.b;
+        R.L_eta[id] = L;
+    }
+}
 template <bool INST>
 struct MisJob {
     RenderDev* R;
@@ -1262,29 +1302,7 @@ struct MisJob {
         *o = f3(a.x, a.y, a.z); *d = f3(b.x, b.y, b.z); *t_max = a.w;
         return true;
     }
-    PB_D void store(uint32_t i, const TravRay& r) const {
-        uint32_t id = R->q_mis[i];
-        float4 c = R->mis_contrib[id];
-        uint32_t ln = __float_as_uint(c.w);
-        rgb li(0.0f);
-        if (r.found) {
-            const pbrt_b200_prim pr = R->scene.prims[r.hit.slot];
-            if (pr.area_light == (int)ln) {  // Arc::ptr_eq(light, hit primitive's area light)
-                uint32_t fl;
-                Surf ls = surface_at_hit<INST>(R->scene, r.hit.inst, r.hit.slot, r.o, r.d, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
-                const pbrt_b200_light& al = R->scene.lights[ln];
-                if (al.two_sided || dot(ls.n, -r.d) > 0.0f) li = rgb3(al.L);
-            }
-        } else {
-            const pbrt_b200_light& l = R->scene.lights[ln];
-            if (l.type == PBRT_B200_LIGHT_INFINITE) li = rgb3(l.L);  // light.le(ray)
-        }
-        if (!is_black(li)) {
-            float4 L = R->L_eta[id];
-            L.x += c.x * li.r; L.y += c.y * li.g; L.z += c.z * li.b;
-            R->L_eta[id] = L;
-        }
-    }
+    PB_D void store(uint32_t i, const TravRay& r) const { mis_resolve<INST>(*R, R->q_mis[i], r); }
 };
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
@@ -1428,6 +1446,88 @@ __global__ void __launch_bounds__(128) k_finish_zt(RenderDev R, int parity) {
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
         queue_push(R.q_path[parity ^ 1], &R.cnt->n_next, id, ok);
     }
+}
+
+// The (0,2)-sequence sampler under the PathIntegrator, one kernel: a tile's paths are inherently serial (every draw of
+// every path advances the tile's PCG32), so the wavefront form spends its time launching 13 kernels per path segment for a
+// few hundred threads.  Here ONE thread per tile (one warp per CTA, lane 0 working) walks its tile's pixels, samples and
+// bounces start to finish -- camera sample, closest hit, shade, shadow ray, MIS ray, film -- with the same device
+// functions, in the same order per tile, hence the same random stream and the same image as the wavefront form.
+template <int BIN, bool INST>
+static __device__ __noinline__ ShadeOut zt_shade(const RenderDev* Rp, uint32_t id) { return shade_path<BIN, INST, true>(*Rp, id); }
+template <bool INST>
+__global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rdev, uint32_t lanes) {
+    // `lanes` tiles per warp: 1 when there are few tiles (pure latency), more when one-lane warps would fill the issue slots
+    if (threadIdx.x >= lanes) return;
+    const uint32_t j = blockIdx.x * lanes + threadIdx.x;
+    if (j >= R.n_tiles_sel) return;
+    uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
+    ZtTile* tp = R.zt.tiles + j;
+    R.pixel[j] = PB_NO_SAMPLE;
+    if (t >= R.tile_end) return;
+    {
+        int tx = t % R.ntx, ty = t / R.ntx;
+        int x0 = R.sampler.sb[0] + tx * 16, y0 = R.sampler.sb[1] + ty * 16;
+        int x1 = min(x0 + 16, R.sampler.sb[2]), y1 = min(y0 + 16, R.sampler.sb[3]);
+        tp->x0 = x0; tp->y0 = y0; tp->w = (uint32_t)max(x1 - x0, 0); tp->npix = tp->w * (uint32_t)max(y1 - y0, 0);
+        tp->pixel_idx = 0; tp->sample_idx = 0; tp->cur1d = 0; tp->cur2d = 0;
+        zt_set_sequence(*tp, (unsigned long long)((long long)ty * R.ntx + tx));
+    }
+    unsigned long long n_camera = 0, n_closest = 0, n_shadow = 0, n_zero = 0, n_iter = 0;
+    bool ok = zt_next_path(R, j, true);
+    uint2 stack[PB_STACK_SIZE(INST)];
+    while (ok) {
+        n_camera += 1;
+        bool alive = true;
+        while (alive) {
+            n_iter += 1;
+            TravRay r;
+            {
+                float4 a = R.ray[2 * j], b = R.ray[2 * j + 1];
+                trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+                trav_run<false, INST>(R.scene, r, stack, 0);
+                n_closest += 1;
+            }
+            const int bin = store_closest_hit(R, j, r);
+            ShadeOut o;
+            switch (bin) {
+                case Q_MATTE: o = zt_shade<Q_MATTE, INST>(Rdev, j); break;
+                case Q_PLASTIC: o = zt_shade<Q_PLASTIC, INST>(Rdev, j); break;
+                case Q_MIRROR: o = zt_shade<Q_MIRROR, INST>(Rdev, j); break;
+                case Q_GLASS: o = zt_shade<Q_GLASS, INST>(Rdev, j); break;
+                case Q_METAL: o = zt_shade<Q_METAL, INST>(Rdev, j); break;
+                case Q_NOMAT: o = zt_shade<Q_NOMAT, INST>(Rdev, j); break;
+                default: o = zt_shade<Q_MISS, INST>(Rdev, j); break;
+            }
+            if (o.zero_rad) n_zero += 1;
+            if (o.push_shadow) {
+                float4 a = R.sh_ray[2 * j], b = R.sh_ray[2 * j + 1];
+                trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+                trav_run<true, INST>(R.scene, r, stack, 0);
+                n_shadow += 1;
+                if (!r.found) shadow_unoccluded(R, j);
+            }
+            if (o.push_mis) {
+                float4 a = R.mis_ray[2 * j], b = R.mis_ray[2 * j + 1];
+                trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+                trav_run<false, INST>(R.scene, r, stack, 0);
+                n_closest += 1;
+                mis_resolve<INST>(R, j, r);
+            }
+            alive = o.push_next;
+        }
+        // finished path -> film (integrator.rs:350-368 sanity rule), then the tile's next sample
+        float4 Le = R.L_eta[j];
+        rgb L(Le.x, Le.y, Le.z);
+        float y = lum(L);
+        if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
+        else if (y < -1.0e-5f) L = rgb(0.0f);
+        else if (isinf(y)) L = rgb(0.0f);
+        film_add_sample(R, R.pfilm[j], L, true);
+        ok = zt_next_path(R, j, false);
+    }
+    atomicAdd(&R.cnt->camera_rays, n_camera); atomicAdd(&R.cnt->closest_rays, n_closest); atomicAdd(&R.cnt->shadow_rays, n_shadow);
+    atomicAdd(&R.cnt->zero_radiance, n_zero); atomicMax(&R.cnt->iterations, n_iter);
 }
 
 // single-thread bookkeeping between iterations: roll queue counters, accumulate stats
@@ -1948,15 +2048,17 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     // DirectLightingIntegrator::preprocess (directlighting.rs:61-76) with nsamples() == 1 for every light
     const uint32_t rec_n_arrays = ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL ? (uint32_t)R.max_depth * R.n_lights * 2u : 0u;
     void* zt_block = nullptr; size_t zt_bytes = 0;
+    RenderDev* zt_rdev = nullptr;  // R in device memory, for the out-of-line shade calls of k_zt_mega
     R.zt.n2d = rd->sampler.n_sampled_dimensions + rec_n_arrays;
     if (zt && n_tiles_sel > 0) {
         const size_t nd = rd->sampler.n_sampled_dimensions, per_tile = nd * spp_eff, per_tile2 = (size_t)R.zt.n2d * spp_eff;
         if (per_tile2 * n_tiles_sel * 8 > (8ull << 30)) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: 02sequence sample arrays for directlighting \"all\" exceed 8 GB");
-        const size_t need = Arena::padded(sizeof(ZtTile) * n_tiles_sel) + Arena::padded(4 * per_tile * n_tiles_sel) + Arena::padded(8 * per_tile2 * n_tiles_sel) + 1024;
+        const size_t need = Arena::padded(sizeof(ZtTile) * n_tiles_sel) + Arena::padded(4 * per_tile * n_tiles_sel) + Arena::padded(8 * per_tile2 * n_tiles_sel) + Arena::padded(sizeof(RenderDev)) + 1024;
         zt_block = pool_alloc(need, &zt_bytes);
         if (!zt_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the 02sequence sample tables");
         Arena A; A.base = reinterpret_cast<char*>(zt_block); A.size = zt_bytes;
         R.zt.tiles = A.take<ZtTile>(n_tiles_sel); R.zt.s1d = A.take<float>(std::max<size_t>(per_tile * n_tiles_sel, 1)); R.zt.s2d = A.take<float2>(std::max<size_t>(per_tile2 * n_tiles_sel, 1));
+        zt_rdev = A.take<RenderDev>(1);
         R.zt.spp = spp_eff; R.zt.ndims = (uint32_t)nd;
     }
     struct ZtRelease { void* p; size_t n; ~ZtRelease() { if (p) { cudaDeviceSynchronize(); pool_free(p, n); } } } zt_release{zt_block, zt_bytes};
@@ -2046,7 +2148,21 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         unsigned long long iter = 0, batch = 0;
         const bool inst = sc->dev.n_instances != 0;                 // trace kernels: two-level walk
         const bool full = inst || sc->dev.n_sphere_lights != 0;     // shade kernels: + instanced surfaces, sphere area lights
-        for (unsigned long long wave_begin = 0; wave_begin < (zt ? 1ull : total_items);) {
+        // (0,2)-sequence + PathIntegrator: the whole call is one kernel, a thread per tile (k_zt_mega); PBRT_B200_ZT_WAVEFRONT=1
+        // keeps the wavefront form (the two must give the same image: tests/test_gpu_render.py)
+        const bool zt_mega = zt && !R.rec.kind && getenv("PBRT_B200_ZT_WAVEFRONT") == nullptr;
+        if (zt_mega) {
+            PB_CUDA_TRY(cudaMemcpyAsync(zt_rdev, &R, sizeof(RenderDev), cudaMemcpyHostToDevice, stream));
+            // tiles per warp, measured on B200 (gpurun_out/ab14.log): 625 tiles -> 2 lanes 7.1 M samples/s (1: 6.1, 4: 5.7); 8160 tiles ->
+            // 8-16 lanes 11.2 M (1: 6.1, 32: 10.8); 32640 tiles -> 32 lanes 23.8 M (1: 6.5)
+            uint32_t lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (n_tiles_sel + (uint32_t)sm_count * 4u - 1u) / ((uint32_t)sm_count * 4u)));
+            if (const char* e = getenv("PBRT_B200_ZT_LANES")) lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (uint32_t)atoi(e)));
+            const uint32_t nblk = (n_tiles_sel + lanes - 1) / lanes;
+            if (full) k_zt_mega<true><<<nblk, 32, 0, stream>>>(R, zt_rdev, lanes);
+            else k_zt_mega<false><<<nblk, 32, 0, stream>>>(R, zt_rdev, lanes);
+            launches += 1;
+        }
+        for (unsigned long long wave_begin = 0; !zt_mega && wave_begin < (zt ? 1ull : total_items);) {
         const unsigned long long wave_end = drained_waves ? std::min<unsigned long long>(wave_begin + capacity, total_items) : total_items;
         const unsigned long long loop_items = zt ? 0ull : wave_end;  // tile-serial mode: the queues themselves say when the tiles are done
         if (zt) {
