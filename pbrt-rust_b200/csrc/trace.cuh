@@ -19,6 +19,9 @@
 #ifndef PB_LEAN_SELECT
 #define PB_LEAN_SELECT 1  /* failed slab test folded into tmin = +inf, near child by (negmask >> axis): +3-4% on B200, bit-identical (gpurun_out/ab1.log) */
 #endif
+#ifndef PB_QUAD_NODES
+#define PB_QUAD_NODES 1  /* 128-byte quad nodes (four grandchildren per fetch) for rays without a zero direction component */
+#endif
 #ifndef PB_PREFETCH_FAR
 #define PB_PREFETCH_FAR 0
 #endif
@@ -487,9 +490,6 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
     }
 }
 
-#ifndef PB_QUAD_NODES
-#define PB_QUAD_NODES 1
-#endif
 // The same walk over QUAD nodes (scene.cuh): one 128-byte fetch tests the four grandchildren of a reference node.
 // Exactness: the reference visits a leaf iff the leaf's box passes `tmin < t_max` (and the slab test) when it is reached AND
 // every ancestor's box passed when IT was reached.  A child box contains its children's boxes and (x - o) * inv is monotone
