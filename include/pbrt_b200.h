@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PBRT_B200_ABI_VERSION 2
+#define PBRT_B200_ABI_VERSION 3
 
 enum {
     PBRT_B200_OK = 0,
@@ -154,7 +154,9 @@ typedef struct pbrt_b200_light {
     float cos_total_width;     /* spot                                               */
     float cos_falloff_start;   /* spot                                               */
     float world_to_light[16];  /* spot                                               */
-} pbrt_b200_light; /* 132 bytes */
+    uint32_t n_samples;        /* Light::nsamples() (diffuse / infinite "samples", 1 otherwise; 0 reads as 1): only
+                                  DirectLightingIntegrator "all" looks at it (directlighting.rs:61-76)  */
+} pbrt_b200_light; /* 136 bytes */
 
 /* = PerspectiveCamera (src/cameras/perspective.rs:22-37); matrices row-major. */
 typedef struct pbrt_b200_camera {

@@ -565,9 +565,8 @@ inline void film_add_sample(const pbrt_b200_film& film, P2 pfilm, Spectrum L, Fl
     }
 }
 
-// uniform_sample_all_lights, src/core/integrator.rs:40-79 (handle_media = false).  Every light of the reference's
-// flattened scene reports nsamples() == 1 across this ABI (pbrt_b200_light carries no sample count; host.py rejects
-// "samples" != 1), so nlight_samples[j] = round_count(1) = 1.
+// uniform_sample_all_lights, src/core/integrator.rs:40-79 (handle_media = false); nlight_samples[j] =
+// round_count(light.nsamples()) with nsamples() = pbrt_b200_light.n_samples.
 inline Spectrum uniform_sample_all_lights(const RenderScene& s, const SurfaceInteraction& it, const BSDF& bsdf, Sampler& sampler,
                                           const std::vector<int>& nlight_samples, RenderCounters& rc) {
     Spectrum L(0.0f);
@@ -694,7 +693,7 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
         std::unique_ptr<Sampler> base = make_sampler(rd.sampler, job.tables);
         IntegratorParams ipl = job.ip;
         if (ipl.kind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {  // DirectLightingIntegrator::preprocess, directlighting.rs:61-76
-            for (size_t j = 0; j < job.scene.d.n_lights; ++j) ipl.nlight_samples.push_back(base->round_count(1));
+            for (size_t j = 0; j < job.scene.d.n_lights; ++j) ipl.nlight_samples.push_back(base->round_count((int)std::max<uint32_t>(job.scene.d.lights[j].n_samples, 1u)));
             for (int i = 0; i < ipl.max_depth; ++i)
                 for (size_t j = 0; j < job.scene.d.n_lights; ++j) { base->request_2d_array(ipl.nlight_samples[j]); base->request_2d_array(ipl.nlight_samples[j]); }
         }

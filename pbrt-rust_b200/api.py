@@ -386,8 +386,11 @@ class API:
         elif name in ("infinite", "exinfinite"):  # infinite.rs:243-262
             if params.find_one_filename("mapname", ""):
                 raise B200Error("image-mapped infinite lights are outside the hot path (SURVEY.md §8 f3)")
-            self._max_light_samples = max(self._max_light_samples, params.find_one_int("samples", params.find_one_int("nsamples", 1)))
-            b.light_source("infinite", L=params.find_one_spectrum("L", one), scale=params.find_one_spectrum("scale", one))
+            ns = params.find_one_int("samples", params.find_one_int("nsamples", 1))  # infinite.rs:249-250
+            if self.opts["quick_render"]:
+                ns = max(1, ns // 4)
+            self._max_light_samples = max(self._max_light_samples, ns)
+            b.light_source("infinite", L=params.find_one_spectrum("L", one), scale=params.find_one_spectrum("scale", one), samples=ns)
         elif name in ("goniometric", "projection"):
             raise B200Error(f'LightSource "{name}" is outside the hot path (point, spot, distant, infinite, diffuse area)')
         else:
@@ -418,12 +421,15 @@ class API:
             ap = self.gs.area_light_params
             if self.gs.area_light in ("area", "diffuse"):  # diffuse.rs:178-196
                 L = (ap.find_one_spectrum("L", f32(1.0)) * ap.find_one_spectrum("scale", f32(1.0))).astype(f32)
-                self._max_light_samples = max(self._max_light_samples, ap.find_one_int("samples", ap.find_one_int("nsamples", 1)))
+                ns = ap.find_one_int("samples", ap.find_one_int("nsamples", 1))  # diffuse.rs:184-190
+                if self.opts["quick_render"]:
+                    ns = max(1, ns // 4)
+                self._max_light_samples = max(self._max_light_samples, ns)
                 two = ap.find_one_bool("twosided", False)
                 if b._cur_object is not None:
                     warnings.warn("Area lights not supported with object instancing")  # api.rs:1604-1606: the light is dropped
                 else:
-                    b._area_light = (L, two)
+                    b._area_light = (L, two, max(ns, 1))
             else:
                 warnings.warn(f'Area light "{self.gs.area_light}" unknown.')
         b.shape("trianglemesh" if name == "plymesh" else name, **kw)
@@ -637,9 +643,9 @@ class API:
             if st not in ("one", "all"):
                 warnings.warn(f'Strategy "{st}" for direct lighting unknown. Using "all".')
                 st = "all"
-            if st == "all" and self._max_light_samples != 1:
-                raise B200Error('directlighting "all" with area / infinite lights asking for more than one sample ("samples" / "nsamples") is not '
-                                "carried across the C ABI (pbrt_b200_light has no sample count)")
+            if st == "all" and self._max_light_samples != 1 and sampler.kind == H.SAMPLER_ZEROTWO:
+                raise B200Error('directlighting "all" with lights asking for more than one sample needs the sobol or halton sampler on the device path '
+                                "(the 02sequence sample arrays are built for one element per pixel sample)")
             integ = H.DirectLightingIntegrator(camera, film, sampler, maxdepth=maxdepth, strategy=st, pixelbounds=pixelbounds)
         else:
             integ = H.WhittedIntegrator(camera, film, sampler, maxdepth=maxdepth, pixelbounds=pixelbounds)

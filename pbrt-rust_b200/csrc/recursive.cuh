@@ -57,6 +57,19 @@ PB_D bool rec_get_2d_array(const RenderDev& R, const SampleCursor& c, uint32_t& 
     arr += 1;
     return true;
 }
+// element k of an n-element array (a light asking for n samples): the array holds n * spp points, point j is evaluated at
+// get_index_for_sample(j) (global_start_pixel!, sampler.rs:268-303), and pixel sample s reads j = s * n + k
+PB_D float2 rec_array_element(const RenderDev& R, const SampleCursor& c, uint32_t arr_index, uint32_t sample_num, uint32_t n, uint32_t k) {
+    SampleCursor e = c;
+    const unsigned long long j = (unsigned long long)sample_num * n + k;
+    e.index = R.sampler.kind == PBRT_B200_SAMPLER_SOBOL
+                  ? sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, j, c.px - R.sampler.sb[0], c.py - R.sampler.sb[1])
+                  : halton_index(R.sampler, j, c.px, c.py);
+    const uint32_t dim = 5u + 2u * arr_index;
+    float y = sample_dimension(R.sampler, e, dim + 1);
+    float x = sample_dimension(R.sampler, e, dim);
+    return make_float2(x, y);
+}
 
 // The sampler as the recursion sees it: get_1d / get_2d / get_2d_array(1).  ZT = false: the global samplers above
 // (state = cursor + array offset in registers, written back by end()); ZT = true: the tile's (0,2)-sequence state in HBM
@@ -74,6 +87,7 @@ template <> struct RecSampler<false> {
     PB_D float2 get_2d(const RenderDev& R) { return rec_get_2d(R, c); }
     PB_D void skip_2d(const RenderDev& R) { rec_skip_2d(R, c); c.dim += 2; }  // a get_2d whose value nobody looks at
     PB_D bool get_2d_array(const RenderDev& R, float2* out) { return rec_get_2d_array(R, c, arr, out); }
+    PB_D float2 array_element(const RenderDev& R, uint32_t a, uint32_t sn, uint32_t n, uint32_t k) { return rec_array_element(R, c, a, sn, n, k); }
     PB_D void end(const RenderDev& R, uint32_t id) { R.s_dim[id] = c.dim; R.rec.arr[id] = arr; }
 };
 template <> struct RecSampler<true> {
@@ -82,6 +96,7 @@ template <> struct RecSampler<true> {
     PB_D float get_1d(const RenderDev&) { return pb::get_1d(z); }
     PB_D float2 get_2d(const RenderDev&) { return pb::get_2d(z); }
     PB_D void skip_2d(const RenderDev&) { (void)pb::get_2d(z); }  // the draw happens (table row or two RNG numbers)
+    PB_D float2 array_element(const RenderDev&, uint32_t, uint32_t, uint32_t, uint32_t) { return make_float2(0.5f, 0.5f); }  // multi-sample arrays: global samplers only
     PB_D bool get_2d_array(const RenderDev& R, float2* out) {
         if (arr == R.rec.n_arrays) return false;
         *out = z.s2d[(size_t)(z.ndims + arr) * z.spp + z.t->sample_idx];
@@ -206,6 +221,23 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                         if (R.rec.kind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {  // uniform_sample_all_lights, integrator.rs:40-79
                             for (uint32_t li = 0; li < nl; ++li) {
                                 float2 ulight, uscatt;
+                                const uint32_t ns = R.rec.multi ? max(R.scene.lights[li].n_samples, 1u) : 1u;
+                                if (!ZT && ns > 1u) {  // Ld = sum_k estimate_direct(array element k) / nsamples, integrator.rs:63-74
+                                    if (smp.arr + 2u <= R.rec.n_arrays) {
+                                        const uint32_t a0 = smp.arr, sn = R.rec.sample_num[id];
+                                        smp.arr += 2u;
+                                        for (uint32_t k = 0; k < ns; ++k) {
+                                            ulight = smp.array_element(R, a0, sn, ns, k);
+                                            uscatt = smp.array_element(R, a0 + 1u, sn, ns, k);
+                                            rec_estimate_direct<INST>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f / (float)ns, time);
+                                        }
+                                        continue;
+                                    }
+                                    smp.arr = R.rec.n_arrays;  // requests exhausted: get_2d_array returns None from here on
+                                    ulight = smp.get_2d(R); uscatt = smp.get_2d(R);
+                                    rec_estimate_direct<INST>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f, time);
+                                    continue;
+                                }
                                 bool hl = smp.get_2d_array(R, &ulight);
                                 bool hs = smp.get_2d_array(R, &uscatt);
                                 if (!hl || !hs) { ulight = smp.get_2d(R); uscatt = smp.get_2d(R); }

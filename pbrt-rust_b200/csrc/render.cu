@@ -128,6 +128,8 @@ struct RecDev {
     uint32_t kind;              // PBRT_B200_INTEGRATOR_*
     uint32_t stack_depth;       // frames per slot (= max_depth)
     uint32_t n_arrays;          // 2D sample arrays requested by DirectLightingIntegrator::preprocess ("all"): max_depth * n_lights * 2
+    uint32_t multi;             // some light asks for more than one sample: array i then has lights[(i / 2) % n_lights].n_samples elements
+    uint32_t* sample_num;       // [capacity] current_pixel_sample_index of the slot's camera sample (array element j = sample * n + k)
     uint32_t entries_per_slot;  // shadow (and MIS) rays one shaded surface can emit
     uint32_t* sp;               // [capacity] frames on the stack
     uint32_t* arr;              // [capacity] Sampler::array_2d_offset
@@ -597,7 +599,10 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     R.s_index[slot] = c.index;
     R.s_dim[slot] = c.dim;
     R.pixel[slot] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
-    if (R.rec.kind) { R.rec.sp[slot] = 0; R.rec.arr[slot] = 0; }  // start_next_sample resets the array offsets (sampler.rs:85-92)
+    if (R.rec.kind) {  // start_next_sample resets the array offsets (sampler.rs:85-92)
+        R.rec.sp[slot] = 0; R.rec.arr[slot] = 0;
+        if (R.rec.multi) R.rec.sample_num[slot] = sample;
+    }
     return true;
 }
 
@@ -1991,7 +1996,15 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
     if (zt) capacity = (n_tiles_sel + 255u) & ~255u;  // tile-serial: one path slot per tile (see ZtTile)
     // recursive integrators: per slot a stack of max_depth frames and up to `eps` shadow + MIS entries; keep that state <= 6 GB
-    const uint32_t rec_eps = ikind == PBRT_B200_INTEGRATOR_PATH ? 0u : (ikind == PBRT_B200_INTEGRATOR_DIRECT_ONE ? 1u : std::max<uint32_t>(sc->dev.n_lights, 1u));
+    uint32_t rec_eps = ikind == PBRT_B200_INTEGRATOR_PATH ? 0u : (ikind == PBRT_B200_INTEGRATOR_DIRECT_ONE ? 1u : std::max<uint32_t>(sc->dev.n_lights, 1u));
+    uint32_t rec_multi = 0;
+    if (ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {  // one shadow + one MIS entry per light SAMPLE (uniform_sample_all_lights, integrator.rs:63-74)
+        unsigned long long tot = 0;
+        for (const pbrt_b200_light& l : st->lights_host) { tot += std::max<uint32_t>(l.n_samples, 1u); if (l.n_samples > 1) rec_multi = 1; }
+        if (tot > (1ull << 20)) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: too many light samples per surface for directlighting \"all\"");
+        rec_eps = (uint32_t)std::max<unsigned long long>(tot, 1ull);
+        if (rec_multi && zt) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting \"all\" with multi-sample lights needs the sobol or halton sampler");
+    }
     const size_t rec_per_slot = ikind == PBRT_B200_INTEGRATOR_PATH ? 0 : 8 + (size_t)rd->integrator.max_depth * 48 + (size_t)rec_eps * (48 + 52);
     if (rec_per_slot) {
         const unsigned long long fit = (6ull << 30) / rec_per_slot;
@@ -2066,19 +2079,19 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     void* rec_block = nullptr; size_t rec_bytes = 0;
     if (ikind != PBRT_B200_INTEGRATOR_PATH) {
         RecDev& rec = R.rec;
-        rec.kind = ikind; rec.stack_depth = (uint32_t)R.max_depth; rec.entries_per_slot = rec_eps;
+        rec.kind = ikind; rec.stack_depth = (uint32_t)R.max_depth; rec.entries_per_slot = rec_eps; rec.multi = rec_multi;
         if (ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {
             rec.n_arrays = rec_n_arrays;
             if (rd->sampler.kind == PBRT_B200_SAMPLER_SOBOL && 5ull + 2ull * rec.n_arrays + 8ull > 1024ull)
                 return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting \"all\" needs more Sobol' dimensions than the 1024 the tables hold (the reference panics)");
         }
         const size_t c = capacity, e = c * rec_eps;
-        const size_t need = Arena::padded(4 * c) * 2 + Arena::padded(32 * c * rec.stack_depth) + Arena::padded(16 * c * rec.stack_depth) + Arena::padded(32 * e) * 2 +
+        const size_t need = Arena::padded(4 * c) * 3 + Arena::padded(32 * c * rec.stack_depth) + Arena::padded(16 * c * rec.stack_depth) + Arena::padded(32 * e) * 2 +
                             Arena::padded(16 * e) * 2 + Arena::padded(4 * e) + 4096;
         rec_block = pool_alloc(need, &rec_bytes);
         if (!rec_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the recursion state");
         Arena A; A.base = reinterpret_cast<char*>(rec_block); A.size = rec_bytes;
-        rec.sp = A.take<uint32_t>(c); rec.arr = A.take<uint32_t>(c);
+        rec.sp = A.take<uint32_t>(c); rec.arr = A.take<uint32_t>(c); rec.sample_num = A.take<uint32_t>(c);
         rec.st_ray = A.take<float4>(2 * c * rec.stack_depth); rec.st_beta = A.take<float4>(c * rec.stack_depth);
         rec.e_sh_ray = A.take<float4>(2 * e); rec.e_sh_contrib = A.take<float4>(e);
         rec.e_mis_ray = A.take<float4>(2 * e); rec.e_mis_contrib = A.take<float4>(e); rec.e_mis_slot = A.take<uint32_t>(e);

@@ -41,11 +41,11 @@ SPHERE_DTYPE = np.dtype([("object_to_world", "<f4", 16), ("world_to_object", "<f
 MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("remap_roughness", "<u4"), ("a", "<f4", 3), ("b", "<f4", 3), ("f0", "<f4"), ("f1", "<f4"), ("f2", "<f4"), ("pad", "<f4")])
 LIGHT_DTYPE = np.dtype([("type", "<u4"), ("two_sided", "<u4"), ("L", "<f4", 3), ("pos", "<f4", 3), ("dir", "<f4", 3), ("shape_kind", "<u4"),
                         ("shape_index", "<u4"), ("shape_flags", "<u4"), ("area", "<f4"), ("cos_total_width", "<f4"), ("cos_falloff_start", "<f4"),
-                        ("world_to_light", "<f4", 16)])
+                        ("world_to_light", "<f4", 16), ("n_samples", "<u4")])
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("t_max", "<f4"), ("d", "<f4", 3), ("time", "<f4")])
 HIT_DTYPE = np.dtype([("prim", "<u4"), ("t", "<f4"), ("b0", "<f4"), ("b1", "<f4")])
 assert NODE_DTYPE.itemsize == 32 and PRIM_DTYPE.itemsize == 24 and SPHERE_DTYPE.itemsize == 144
-assert MATERIAL_DTYPE.itemsize == 48 and LIGHT_DTYPE.itemsize == 132 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16
+assert MATERIAL_DTYPE.itemsize == 48 and LIGHT_DTYPE.itemsize == 136 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16
 
 SHAPE_TRIANGLE, SHAPE_SPHERE, SHAPE_INSTANCE = 0, 1, 2
 OBJECT_DTYPE = np.dtype([("node_offset", "<u8"), ("n_nodes", "<u8"), ("prim_offset", "<u8"), ("n_prims", "<u8")])
@@ -370,7 +370,7 @@ class FlatScene:
 
     def desc(self):
         d = SceneDesc()
-        d.abi_version = 2
+        d.abi_version = 3
         d.nodes, d.n_nodes = _ptr(self.nodes), len(self.nodes)
         d.prims, d.n_prims = _ptr(self.prims), len(self.prims)
         d.vertex_p, d.n_vertices = _ptr(self.vertex_p), len(self.vertex_p)
@@ -535,15 +535,16 @@ class SceneBuilder:
         return self._mat_index[key]
 
     # --- lights ------------------------------------------------------------
-    def area_light_source(self, name="diffuse", L=(1, 1, 1), scale=1.0, twosided=False):  # diffuse.rs:178-195
+    def area_light_source(self, name="diffuse", L=(1, 1, 1), scale=1.0, twosided=False, samples=1):  # diffuse.rs:178-195
         if name not in ("diffuse", "area"):
             raise B200Error(f'AreaLightSource "{name}" unknown')
-        self.log.append(("AreaLightSource", name, {"L": L, "scale": scale, "twosided": twosided}))
-        self._area_light = (np.asarray(L, f32) * f32(scale) if not np.isscalar(L) else np.full(3, L * scale, f32), bool(twosided))
+        self.log.append(("AreaLightSource", name, {"L": L, "scale": scale, "twosided": twosided, **({"samples": int(samples)} if samples != 1 else {})}))
+        self._area_light = (np.asarray(L, f32) * f32(scale) if not np.isscalar(L) else np.full(3, L * scale, f32), bool(twosided), max(int(samples), 1))
 
     def light_source(self, name, **kw):
         self.log.append(("LightSource", name, kw))
         r = np.zeros(1, LIGHT_DTYPE)[0]
+        r["n_samples"] = 1
 
         def rgb(key, default):
             v = kw.get(key, default)
@@ -580,7 +581,7 @@ class SceneBuilder:
         elif name == "infinite":  # infinite.rs, constant map only
             if kw.get("mapname"):
                 raise B200Error("image-mapped infinite lights are outside the hot path")
-            r["type"], r["L"] = LIGHT_INFINITE, rgb("L", 1.0) * sc
+            r["type"], r["L"], r["n_samples"] = LIGHT_INFINITE, rgb("L", 1.0) * sc, max(int(kw.get("samples", 1)), 1)
         else:
             raise B200Error(f'LightSource "{name}" is outside the hot path (point, spot, distant, infinite, diffuse area)')
         self._lights.append(r)
@@ -629,11 +630,12 @@ class SceneBuilder:
         if self._area_light is not None and self._cur_object is not None:
             raise B200Error("Area lights not supported with object instancing (api.rs:1573-1575)")
         if self._area_light is not None:  # api.rs:1531-1546: one DiffuseAreaLight per shape
-            L, two = self._area_light
+            L, two, nsamp = self._area_light
             lights = np.zeros(nt, LIGHT_DTYPE)
             lights["type"], lights["two_sided"], lights["L"] = LIGHT_DIFFUSE, int(two), L
             lights["shape_kind"], lights["shape_index"], lights["shape_flags"] = SHAPE_TRIANGLE, rows["shape_index"], flags
             lights["area"] = _tri_area(p0, p1, p2)
+            lights["n_samples"] = nsamp
             first = len(self._lights)
             self._lights.extend(list(lights))
             rows["area_light"] = np.arange(first, first + nt, dtype=np.int32)
@@ -655,12 +657,13 @@ class SceneBuilder:
         row = np.zeros(1, PRIM_DTYPE)
         row["shape_kind"], row["shape_index"], row["material"], row["area_light"], row["flags"] = SHAPE_SPHERE, len(self._spheres), self._material_id(), -1, flags
         if self._area_light is not None:  # api.rs:1531-1546 + DiffuseAreaLight::new (diffuse.rs:33-66): area = Sphere::area (sphere.rs:291-293)
-            L, two = self._area_light
+            L, two, nsamp = self._area_light
             light = np.zeros(1, LIGHT_DTYPE)[0]
             light["type"], light["two_sided"], light["L"] = LIGHT_DIFFUSE, int(two), L
             light["shape_kind"], light["shape_index"], light["shape_flags"] = SHAPE_SPHERE, len(self._spheres), flags
             phi_max = f32(f32(np.pi) / f32(180.0)) * f32(360.0)  # radians(clamp(phimax, 0, 360)), sphere.rs:36
             light["area"] = phi_max * rr * (rr - (-rr))
+            light["n_samples"] = nsamp
             row["area_light"] = len(self._lights)
             self._lights.append(light)
         self._spheres.append(r)

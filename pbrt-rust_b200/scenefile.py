@@ -51,6 +51,8 @@ def _params(kind, name, kw):
             out.append(f'"point {k}" [{_nums(v)}]')
         elif k in _RGB_KEYS or (k == "eta" and name == "metal"):
             out.append(f'"rgb {k}" [{_rgb(v)}]')
+        elif k == "samples":
+            out.append(f'"integer samples" [{int(v)}]')
         elif isinstance(v, str):
             out.append(f'"string {k}" "{v}"')
         else:

@@ -27,14 +27,14 @@ def test_library_exports_every_declared_symbol(pkg):
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, f"libpbrt_b200.so lacks {missing}"
     assert sorted(pkg.host.EXPORTS) == declared_symbols(), "host.EXPORTS and the header disagree"
-    assert lib.pbrt_b200_abi_version() == 2  # v2: object instancing tables in pbrt_b200_scene_desc
+    assert lib.pbrt_b200_abi_version() == 3  # v2: object instancing tables in pbrt_b200_scene_desc; v3: pbrt_b200_light.n_samples
 
 
 def test_struct_layouts_match_the_header(pkg):
     H = pkg.host
     # sizes stated in include/pbrt_b200.h
     assert H.NODE_DTYPE.itemsize == 32 and H.PRIM_DTYPE.itemsize == 24 and H.MATERIAL_DTYPE.itemsize == 48
-    assert H.LIGHT_DTYPE.itemsize == 132 and H.RAY_DTYPE.itemsize == 32 and H.HIT_DTYPE.itemsize == 16 and H.SPHERE_DTYPE.itemsize == 144
+    assert H.LIGHT_DTYPE.itemsize == 136 and H.RAY_DTYPE.itemsize == 32 and H.HIT_DTYPE.itemsize == 16 and H.SPHERE_DTYPE.itemsize == 144
     lib = pkg.load_library()
     if hasattr(lib, "pbrt_b200_struct_size"):
         for name, py in (("scene_desc", C.sizeof(H.SceneDesc)), ("render_desc", C.sizeof(H.RenderDesc)), ("render_stats", C.sizeof(H.RenderStats))):

@@ -146,3 +146,49 @@ WorldEnd
     img, stats = job.render(device=0)
     ref, ostats = oracle.render_image(job.flat, job.integrator)
     assert oracle.rel_mse(img, ref) <= REL_MSE_TOL and stats.camera_rays == ostats["camera_rays"]
+
+
+@pytest.mark.parametrize("sampler", ["sobol", "halton"])
+def test_directlighting_all_with_multi_sample_lights(pkg, oracle, gpu_lib, sampler):
+    """Lights asking for several samples ("integer samples" n): uniform_sample_all_lights averages n estimate_direct calls fed
+    from n-element sample arrays (integrator.rs:63-74); element j of an array is evaluated at get_index_for_sample(j)."""
+    H = pkg.host
+    b = H.SceneBuilder()
+    b.material("matte", Kd=(0.5, 0.5, 0.5))
+    P, I = pkg.scenes.quad((-6, -6, 0), (6, -6, 0), (6, 6, 0), (-6, 6, 0))
+    b.shape("trianglemesh", P=P, indices=I)
+    b.attribute_begin()
+    b.translate(-1.0, 0.3, 0.8)
+    b.material("plastic", Kd=(0.3, 0.5, 0.2), Ks=0.4, roughness=0.05)
+    b.shape("sphere", radius=0.8)
+    b.attribute_end()
+    b.attribute_begin()
+    b.translate(1.2, 0.0, 0.6)
+    b.material("glass")
+    b.shape("sphere", radius=0.6)
+    b.attribute_end()
+    b.attribute_begin()
+    b.area_light_source("diffuse", L=(12, 11, 9), samples=4)
+    Pl, Il = pkg.scenes.quad((-1, -1, 3.5), (-1, 1, 3.5), (1, 1, 3.5), (1, -1, 3.5))
+    b.shape("trianglemesh", P=Pl, indices=Il)
+    b.attribute_end()
+    b.attribute_begin()
+    b.translate(2.5, -2.0, 2.0)
+    b.area_light_source("diffuse", L=(4, 6, 9), twosided=True, samples=3)
+    b.shape("sphere", radius=0.3)
+    b.attribute_end()
+    b.light_source("infinite", L=(0.1, 0.1, 0.15), samples=2)
+    b.light_source("point", I=(3, 3, 3), **{"from": (-3, -3, 3)})
+    flat = b.world_end()
+    assert sorted(set(flat.lights["n_samples"].tolist())) == [1, 2, 3, 4]
+    film = H.Film(80, 56, "box")
+    cam = H.PerspectiveCamera(film, H.Transform.look_at((0, -6, 2.5), (0, 0, 0.7), (0, 0, 1)).inverse(), fov=42.0)
+    integ = H.DirectLightingIntegrator(cam, film, H.Sampler(sampler, 4), maxdepth=4, strategy="all")
+    sc = pkg.Scene(flat)
+    img, stats = integ.render(sc)
+    sc.close()
+    ref, ostats = oracle.render_image(flat, integ)
+    err = oracle.rel_mse(img, ref)
+    assert err <= REL_MSE_TOL, f"relMSE {err:.3e}"
+    assert stats.camera_rays == ostats["camera_rays"]
+    assert abs(int(stats.shadow_tests) - ostats["shadow_tests"]) <= 0.002 * ostats["shadow_tests"] + 8

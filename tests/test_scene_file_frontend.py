@@ -176,9 +176,12 @@ def test_directlighting_and_whitted_scene_files(tmp_path):
     # directlighting.rs:146-152: strategy defaults to "all"; area lights asking for several samples cannot cross the C ABI
     job = pkg.pbrt_parse_string('Integrator "directlighting"\nWorldBegin\nShape "sphere"\nWorldEnd').jobs[0]
     assert job.integrator.kind == pkg.host.INTEGRATOR_DIRECT_ALL and job.integrator.max_depth == 5
+    # a light's "samples" travels in pbrt_b200_light.n_samples (diffuse.rs:184-185); multi-sample arrays need a global sampler
+    tri = 'AreaLightSource "diffuse" "integer samples" [4]\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd'
+    job = pkg.pbrt_parse_string('Integrator "directlighting"\nWorldBegin\nLightSource "infinite" "integer nsamples" 2\n' + tri).jobs[0]
+    assert job.flat.lights["n_samples"].tolist() == [2, 4]
     with pytest.raises(pkg.B200Error):
-        pkg.pbrt_parse_string('Integrator "directlighting"\nWorldBegin\nAreaLightSource "diffuse" "integer samples" [4]\n'
-                              'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd')
+        pkg.pbrt_parse_string('Integrator "directlighting"\nSampler "02sequence"\nWorldBegin\n' + tri)
 
 
 def test_inline_meshes_and_ply_meshes_agree(tmp_path):
