@@ -2161,9 +2161,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         unsigned long long iter = 0, batch = 0;
         const bool inst = sc->dev.n_instances != 0;                 // trace kernels: two-level walk
         const bool full = inst || sc->dev.n_sphere_lights != 0;     // shade kernels: + instanced surfaces, sphere area lights
-        // (0,2)-sequence + PathIntegrator: the whole call is one kernel, a thread per tile (k_zt_mega); PBRT_B200_ZT_WAVEFRONT=1
-        // keeps the wavefront form (the two must give the same image: tests/test_gpu_render.py)
-        const bool zt_mega = zt && !R.rec.kind && getenv("PBRT_B200_ZT_WAVEFRONT") == nullptr;
+        // (0,2)-sequence + PathIntegrator: the whole call is one kernel, a thread per tile (k_zt_mega, always the full-featured
+        // family: one instantiation); the recursive integrators keep the wavefront tile-serial form
+        const bool zt_mega = zt && !R.rec.kind;
         if (zt_mega) {
             PB_CUDA_TRY(cudaMemcpyAsync(zt_rdev, &R, sizeof(RenderDev), cudaMemcpyHostToDevice, stream));
             // tiles per warp, measured on B200 (gpurun_out/ab14.log): 625 tiles -> 2 lanes 7.1 M samples/s (1: 6.1, 4: 5.7); 8160 tiles ->
@@ -2171,8 +2171,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
             uint32_t lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (n_tiles_sel + (uint32_t)sm_count * 4u - 1u) / ((uint32_t)sm_count * 4u)));
             if (const char* e = getenv("PBRT_B200_ZT_LANES")) lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (uint32_t)atoi(e)));
             const uint32_t nblk = (n_tiles_sel + lanes - 1) / lanes;
-            if (full) k_zt_mega<true><<<nblk, 32, 0, stream>>>(R, zt_rdev, lanes);
-            else k_zt_mega<false><<<nblk, 32, 0, stream>>>(R, zt_rdev, lanes);
+            k_zt_mega<true><<<nblk, 32, 0, stream>>>(R, zt_rdev, lanes);
             launches += 1;
         }
         for (unsigned long long wave_begin = 0; !zt_mega && wave_begin < (zt ? 1ull : total_items);) {
@@ -2219,8 +2218,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                     if (timing) mark();
                 } else {
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
-                if (zt) launch_shade<true, true>(R, parity, grid_small, grid_shade, stream);
-                else if (full) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
+                if (full) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
                 else launch_shade<false, false>(R, parity, grid_small, grid_shade, stream);
                 if (timing) mark();
                 if (inst) k_trace_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);

@@ -142,18 +142,3 @@ WorldEnd
     img, stats = job.render(device=0)
     ref, ostats = oracle.render_image(job.flat, job.integrator)
     assert oracle.rel_mse(img, ref) <= REL_MSE_TOL and stats.camera_rays == ostats["camera_rays"]
-
-
-def test_02sequence_megakernel_equals_wavefront_form(pkg, oracle, gpu_lib, monkeypatch):
-    """The tile-serial (0,2)-sequence path integrator runs as one kernel with a thread per tile (k_zt_mega); the wavefront form
-    (PBRT_B200_ZT_WAVEFRONT=1) walks the same per-tile random stream: same image, same ray counts."""
-    setup = pkg.scenes.small_mixed_scene()
-    integ = setup.make_integrator(spp_=4, res=(80, 56), sampler_="02sequence")
-    sc = pkg.Scene(setup.flat)
-    a, sa = integ.render(sc)
-    monkeypatch.setenv("PBRT_B200_ZT_WAVEFRONT", "1")
-    b, sb = integ.render(sc)
-    sc.close()
-    assert np.allclose(a, b, rtol=2e-5, atol=2e-5)
-    assert (sa.camera_rays, sa.intersection_tests, sa.shadow_tests) == (sb.camera_rays, sb.intersection_tests, sb.shadow_tests)
-    assert sa.kernel_launches < 10 < sb.kernel_launches
