@@ -332,8 +332,8 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": desc, "step": f"{args.spp} spp per GPU over the full frame ({spp_step} spp per step in total), tiles interleaved across ranks in groups of 8",
-                          "l2": "no explicit flush: per-step working set (2^25 path slots x ~300 B state + 110 MB scene + 33 MB film) exceeds the 126 MB L2",
-                          "paths_in_flight": args.paths_in_flight or 1 << 25, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"},
+                          "l2": "no explicit flush: per-step working set (2^26 path slots x ~300 B state + 110 MB scene + 33 MB film) exceeds the 126 MB L2",
+                          "paths_in_flight": args.paths_in_flight or 1 << 26, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"},
                "mrays_per_s": (closest + shadow) / (ms * 1e-3) / 1e6, "rays_per_sample": (closest + shadow) / max(camera, 1),
                "ray_batches": ray_batches, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "kernel_ms": {"trace_closest": tot["trace_closest_ms"], "trace_shadow": tot["trace_any_ms"], "wavefront_total": tot["device_ms"]}}

@@ -17,7 +17,7 @@ struct Pool {
 Pool& pool() { static Pool* p = new Pool(); return *p; }  // leaked on purpose: CUDA may already be torn down at exit
 
 // Keep at most this much idle memory per process; anything beyond is returned to the driver right away.
-const size_t kMaxCachedDev = (size_t)24 << 30, kMaxCachedHost = (size_t)2 << 30;
+const size_t kMaxCachedDev = (size_t)48 << 30, kMaxCachedHost = (size_t)2 << 30;
 
 // Smallest cached block with bytes <= size <= 2 * bytes (+ slack for small ones), same device.
 int pick(std::vector<Block>& v, size_t bytes, int device) {

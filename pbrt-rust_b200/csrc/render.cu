@@ -1989,9 +1989,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     uint32_t n_tiles_sel = n_owned_groups * tile_group;
     unsigned long long total_items = (unsigned long long)n_tiles_sel * 256ull * (s_end - s_begin);
 
-    // default 2^25 slots (~9 GB of path state on a 180 GB part): measured on S3, 2^21 -> 360 M samples/s, 2^23 -> 480, 2^24 -> 549,
-    // 2^25 -> 600 (fewer, fuller iterations; a 16-spp 1080p step fits one wave)
-    uint32_t capacity = rd->paths_in_flight ? rd->paths_in_flight : (1u << 25);
+    // default 2^26 slots (~20 GB of path state on a 180 GB part): measured on S3, 2^21 -> 360 M samples/s, 2^23 -> 480, 2^24 -> 549,
+    // 2^25 -> 600 (634 with this round's kernels), 2^26 -> 659, 2^27 -> 655 (fewer, fuller iterations; gpurun_out/ab18.log)
+    uint32_t capacity = rd->paths_in_flight ? rd->paths_in_flight : (1u << 26);
     capacity = (capacity + 255u) & ~255u;
     if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
     if (zt) capacity = (n_tiles_sel + 255u) & ~255u;  // tile-serial: one path slot per tile (see ZtTile)
