@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-spp", type=int, default=8, help="--impl reference: samples per pixel per step (bounded sample of the GPU arm's step)")
     return ap.parse_args()
 
 
@@ -61,6 +62,14 @@ def make_setup(pkg, name):
     if name == "cornell":
         return S.cornell_scene(), dict(), "S2: Cornell box 1024x1024, maxdepth 8, gaussian filter"
     return S.spheres_scene(), dict(), "S1: two spheres 400x400, maxdepth 5"
+
+
+def bench_config(desc, spp, world, pif):
+    """`config` of the JSON line.  Both arms print the SAME dict (the reference arm runs on the GPU arm's config; what its bounded
+    per-step sample is goes into its `cpu_baseline.sample`)."""
+    return {"workload": desc, "step": f"{spp} spp per GPU over the full frame ({spp * world} spp per step in total), tiles interleaved across ranks in groups of 8",
+            "l2": "no explicit flush: per-step working set (2^26 path slots x ~300 B state + 110 MB scene + 33 MB film) exceeds the 126 MB L2",
+            "paths_in_flight": pif or 1 << 26, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"}
 
 
 class ClockSampler:
@@ -154,27 +163,37 @@ def main():
     pkg = importlib.import_module("pbrt-rust_b200")
 
     if args.impl == "reference":
+        # The reference's own CPU implementation of the path on all host threads.  pbrt-rust cannot be built here (nightly Rust +
+        # LALRPOP + ~40 crates, no network), so this is the oracle port.  The scene is built WITHOUT the product library (the
+        # accelerator comes from the oracle's BVH builder), and nothing below touches CUDA.
         if rank != 0:
             return 0
-        setup, kw, desc = make_setup(pkg, args.scene)
         from oracle import oracle as O
+        pkg.host.DEFAULT_BVH_BUILDER = O.bvh_build
+        setup, kw, desc = make_setup(pkg, args.scene)
         nth = os.cpu_count() or 1
-        integ = setup.make_integrator(spp_=max(64, args.steps + args.warmup), **kw)
+        # each step = a bounded sample of the GPU arm's step: the same full frame, `ref_spp` of its sample indices in ONE oracle
+        # call (one call per spp cost ~25 % in per-call set-up in round 1 and made the two CPU legs disagree)
+        ref_spp = max(1, args.ref_spp)
+        nst = args.steps + args.warmup
+        integ = setup.make_integrator(spp_=max(64, ref_spp * nst), **kw)
         film = integ.film
         for w in range(args.warmup):
-            O.render(setup.flat, integ, nthreads=nth, sample_range=(w, w + 1))
+            O.render(setup.flat, integ, nthreads=nth, sample_range=(w * ref_spp, (w + 1) * ref_spp))
         t0 = time.time()
         samples = 0
         for k in range(args.steps):
-            _, st = O.render(setup.flat, integ, nthreads=nth, sample_range=(args.warmup + k, args.warmup + k + 1))
+            b = (args.warmup + k) * ref_spp
+            _, st = O.render(setup.flat, integ, nthreads=nth, sample_range=(b, b + ref_spp))
             samples += st["camera_rays"]
         dt = time.time() - t0
         v = samples / dt
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": desc, "step": "1 spp over the full frame (bounded sample of the workload)"},
+                          "config": bench_config(desc, args.spp, args.gpus, args.paths_in_flight),
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nth, "kind": "port",
-                                           "sample": f"{args.steps} steps x 1 spp x {film.width}x{film.height} on {nth} threads (CPU oracle: the Rust reference cannot be built here)"},
+                                           "sample": f"{args.steps} steps, each {ref_spp} of the step's {args.spp} spp over the full {film.width}x{film.height} frame in one "
+                                                     f"call = {samples} camera samples in {dt:.1f} s on {nth} threads (CPU oracle: the Rust reference cannot be built here)"},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out_stream, flush=True)
         return 0
 
@@ -331,9 +350,7 @@ def main():
                         "share_of_step": tot["trace_closest_ms"] / max(tot["device_ms"], 1e-9)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": desc, "step": f"{args.spp} spp per GPU over the full frame ({spp_step} spp per step in total), tiles interleaved across ranks in groups of 8",
-                          "l2": "no explicit flush: per-step working set (2^26 path slots x ~300 B state + 110 MB scene + 33 MB film) exceeds the 126 MB L2",
-                          "paths_in_flight": args.paths_in_flight or 1 << 26, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"},
+               "config": bench_config(desc, args.spp, world, args.paths_in_flight),
                "mrays_per_s": (closest + shadow) / (ms * 1e-3) / 1e6, "rays_per_sample": (closest + shadow) / max(camera, 1),
                "ray_batches": ray_batches, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "kernel_ms": {"trace_closest": tot["trace_closest_ms"], "trace_shadow": tot["trace_any_ms"], "wavefront_total": tot["device_ms"]}}

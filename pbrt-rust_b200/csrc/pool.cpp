@@ -1,6 +1,8 @@
 #include "pool.h"
 
+#include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/pbrt_b200.h"
@@ -13,11 +15,23 @@ struct Pool {
     std::mutex mu;
     std::vector<Block> free_dev, free_host;
     size_t cached_dev = 0, cached_host = 0;
+    std::unordered_map<void*, int> live_dev;  // device of every block handed out: pool_free must not trust cudaGetDevice()
 };
 Pool& pool() { static Pool* p = new Pool(); return *p; }  // leaked on purpose: CUDA may already be torn down at exit
 
-// Keep at most this much idle memory per process; anything beyond is returned to the driver right away.
-const size_t kMaxCachedDev = (size_t)48 << 30, kMaxCachedHost = (size_t)2 << 30;
+// Keep at most this much idle memory per process; anything beyond is returned to the driver right away.  The device cap
+// (default 48 GB, PBRT_B200_POOL_CACHE_GB overrides; 0 = cache nothing) matters to whoever shares the process: torch / NCCL
+// allocate outside this pool and cannot reclaim what sits idle here -- pbrt_b200_release_cached_memory() hands it back.
+const size_t kMaxCachedHost = (size_t)2 << 30;
+size_t max_cached_dev() {
+    static const size_t v = [] {
+        const char* e = getenv("PBRT_B200_POOL_CACHE_GB");
+        double gb = e ? atof(e) : 48.0;
+        if (!(gb >= 0.0)) gb = 48.0;
+        return (size_t)(gb * (double)((size_t)1 << 30));
+    }();
+    return v;
+}
 
 // Smallest cached block with bytes <= size <= 2 * bytes (+ slack for small ones), same device.
 int pick(std::vector<Block>& v, size_t bytes, int device) {
@@ -45,6 +59,7 @@ void* pool_alloc(size_t bytes, size_t* got) {
             Block b = P.free_dev[i];
             P.free_dev.erase(P.free_dev.begin() + i);
             P.cached_dev -= b.bytes;
+            P.live_dev[b.p] = dev;
             *got = b.bytes;
             return b.p;
         }
@@ -55,24 +70,29 @@ void* pool_alloc(size_t bytes, size_t* got) {
         pool_trim();  // give cached blocks back and retry once
         if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
     }
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        P.live_dev[p] = dev;
+    }
     *got = bytes;
     return p;
 }
 
 void pool_free(void* p, size_t bytes) {
     if (!p) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
     Pool& P = pool();
     {
         std::lock_guard<std::mutex> g(P.mu);
-        if (P.cached_dev + bytes <= kMaxCachedDev) {
+        int dev = -1;
+        auto it = P.live_dev.find(p);
+        if (it != P.live_dev.end()) { dev = it->second; P.live_dev.erase(it); }
+        if (dev >= 0 && P.cached_dev + bytes <= max_cached_dev()) {  // a block this pool did not hand out is never cached
             P.free_dev.push_back(Block{p, bytes, dev});
             P.cached_dev += bytes;
             return;
         }
     }
-    cudaFree(p);
+    cudaFree(p);  // valid from any current device (unified addressing)
 }
 
 void* pool_alloc_host(size_t bytes, size_t* got) {

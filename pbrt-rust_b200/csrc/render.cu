@@ -79,6 +79,13 @@ struct SamplerDev {
     const uint32_t* primes;
     const uint32_t* prime_sums;
     uint32_t n_halton_dims;
+    // Sobol' sample tables (see sobol_tab_block): value bits of dimension d for pixel p / sample number s, XORed at use
+    const uint32_t* vp;     // [sample-bounds pixels][vstride]
+    const uint32_t* vs;     // [samples of the call][vstride]
+    uint32_t vdims;         // dimensions the tables cover; 0 = no tables (Halton, recursive integrators, 1x1 sample bounds)
+    uint32_t vstride;       // row stride in words (multiple of 4: rows are 16-byte aligned)
+    uint32_t sbw;           // sample-bounds width in pixels
+    uint32_t vs_begin;      // sample number of row 0 of vs
 };
 
 // SpatialLightDistribution (core/lightdistrib.rs:105-340) on the device.  The reference fills a lock-free hash table of
@@ -188,6 +195,8 @@ struct RenderDev {
     float4* sh_contrib;  // {rgb to add when unoccluded, -}
     float4* mis_ray;     // MIS ray (2 x float4)
     float4* mis_contrib; // {rgb factor (beta * f * |cos| * w / (scattpdf * lightselpdf)), light index bits}
+    float4* u8;          // 2 x float4 per slot: the next eight sample dimensions, written by k_sample_block when the Sobol' tables
+                         // do not serve the path (Halton; dimensions beyond the tables); nullptr when that cannot happen
     uint32_t* q_path[2];
     uint32_t* q_shadow;
     uint32_t* q_mis;
@@ -346,6 +355,25 @@ PB_D float2 get_2d(SampleBlock& b) {  // x from the lower dimension (sampler.rs:
     return r;
 }
 
+// Sobol' through tables.  sobol_interval_to_index and sobol_sample_float (lowdiscrepancy.rs:512-569) are linear over GF(2):
+//   index(p, s) = Ip(p) ^ Is(s),  Ip = XOR of VdCInv columns over the bits of (p.x << m | p.y),
+//                                 Is = (s << 2m) ^ XOR of VdCInv columns over the bits of delta(s)
+//   bits_d(index) = XOR of generator-matrix columns of dimension d over the bits of index = bits_d(Ip) ^ bits_d(Is)
+// so the 32 value bits of (pixel, sample, dimension) are vp[pixel][d] ^ vs[s][d]: two table rows replace the index
+// computation and the ~15-step walk over the set bits of the index with 8 loads each (27 % of the shade kernels' stall
+// samples, profiles/r01_ncu_full_s10.md).  XOR is associative and commutative: the bits, hence the floats, are identical.
+// In table mode R.s_index[slot] holds the SAMPLE NUMBER, not the Sobol' index.
+PB_D bool sobol_tab_covers(const SamplerDev& S, uint32_t dim) { return dim + 8u <= S.vdims; }
+PB_D void sobol_tab_block(const SamplerDev& S, uint32_t pxy, uint32_t sample, uint32_t dim, float* u) {
+    const uint32_t* a = S.vp + ((size_t)(pxy >> 16) * S.sbw + (pxy & 0xffffu)) * S.vstride + dim;
+    const uint32_t* b = S.vs + (size_t)(sample - S.vs_begin) * S.vstride + dim;
+    uint32_t va[8], vb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { va[k] = __ldg(a + k); vb[k] = __ldg(b + k); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = fminf((float)(va[k] ^ vb[k]) * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
+}
+
 // ---- (0,2)-sequence sampler, tile-serial (see ZtTile)
 PB_D uint32_t zt_u32(ZtTile& t) {  // RNG::uniform_int32, rng.rs:31-48
     unsigned long long old = t.state;
@@ -429,11 +457,16 @@ PB_D float2 get_2d(ZtCursor& c) {
 template <bool ZT> struct PathSampler;
 template <> struct PathSampler<false> {
     SampleCursor c; SampleBlock sb;
+    // The shade kernels carry no sampler arithmetic: either the Sobol' tables cover the block (two row reads), or the
+    // pre-pass k_sample_block has left the eight values in R.u8 (Halton, Sobol' dimensions beyond the tables).
     PB_D void begin(const RenderDev& R, uint32_t id) {
         c.index = R.s_index[id]; c.dim = R.s_dim[id];
-        uint32_t pxy = R.pixel[id];
-        c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
-        sample_block(R.sampler, c, sb);
+        sb.used = 0;
+        if (sobol_tab_covers(R.sampler, c.dim)) sobol_tab_block(R.sampler, R.pixel[id], (uint32_t)c.index, c.dim, sb.u);
+        else {
+            const float4 lo = R.u8[2 * id], hi = R.u8[2 * id + 1];
+            sb.u[0] = lo.x; sb.u[1] = lo.y; sb.u[2] = lo.z; sb.u[3] = lo.w; sb.u[4] = hi.x; sb.u[5] = hi.y; sb.u[6] = hi.z; sb.u[7] = hi.w;
+        }
     }
     PB_D float get_1d() { return pb::get_1d(sb); }
     PB_D float2 get_2d() { return pb::get_2d(sb); }
@@ -556,13 +589,24 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     if (!valid) { R.pixel[slot] = PB_NO_SAMPLE; return false; }
     SampleCursor c;
     c.px = x; c.py = y; c.dim = 0;
-    c.index = (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL)
-                  ? sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, sample, x - R.sampler.sb[0], y - R.sampler.sb[1])
-                  : halton_index(R.sampler, sample, x, y);
     // get_camera_sample, sampler.rs:170-180: dimensions 0..4
     float2 u, plens;
     float tu;
-    if (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL) {
+    if (R.sampler.vdims) {
+        // Sobol' tables (sobol_tab_block): no index, no bit walk; the slot remembers the sample number
+        const uint32_t* a = R.sampler.vp + ((size_t)(y - R.sampler.sb[1]) * R.sampler.sbw + (uint32_t)(x - R.sampler.sb[0])) * R.sampler.vstride;
+        const uint32_t* b = R.sampler.vs + (size_t)(sample - R.sampler.vs_begin) * R.sampler.vstride;
+        const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(a)), b4 = __ldg(reinterpret_cast<const uint4*>(b));
+        const uint32_t v[5] = {a4.x ^ b4.x, a4.y ^ b4.y, a4.z ^ b4.z, a4.w ^ b4.w, __ldg(a + 4) ^ __ldg(b + 4)};
+        float f[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) f[k] = fminf((float)v[k] * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
+        f[0] = clampf(f[0] * (float)R.sampler.resolution + (float)R.sampler.sb[0] - (float)x, 0.0f, PB_ONE_MINUS_EPSILON);
+        f[1] = clampf(f[1] * (float)R.sampler.resolution + (float)R.sampler.sb[1] - (float)y, 0.0f, PB_ONE_MINUS_EPSILON);
+        u = make_float2(f[0], f[1]); tu = f[2]; plens = make_float2(f[3], f[4]);
+        c.index = sample; c.dim = 5;
+    } else if (R.sampler.kind == PBRT_B200_SAMPLER_SOBOL) {
+        c.index = sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, sample, x - R.sampler.sb[0], y - R.sampler.sb[1]);
         // sobol_sample_float (lowdiscrepancy.rs:549-569) for the five dimensions in ONE walk over the set bits of the index,
         // reading 5 adjacent columns of the bit-transposed matrices; dims 0/1 then get SobolSampler::sample_dimension's
         // pixel remap (sobol.rs:69-87).  Same XOR sums as the per-dimension loops => identical values.
@@ -583,6 +627,7 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
         u = make_float2(f[0], f[1]); tu = f[2]; plens = make_float2(f[3], f[4]);
         c.dim = 5;
     } else {
+        c.index = halton_index(R.sampler, sample, x, y);
         u = get_2d(R.sampler, c);
         tu = get_1d(R.sampler, c);
         plens = get_2d(R.sampler, c);
@@ -1046,6 +1091,80 @@ __global__ void __launch_bounds__(256) k_light_distrib_gather(RenderDev R, const
         }
         voxel_out[3 * i] = vx; voxel_out[3 * i + 1] = vy; voxel_out[3 * i + 2] = vz;
         for (uint32_t j = 0; j < nl; ++j) func_out[(size_t)i * nl + j] = func ? func[j] : -1.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sampler pre-pass and Sobol' table builders
+// ---------------------------------------------------------------------------
+// The eight dimensions a hit path is about to consume, for paths the Sobol' tables do not serve (see PathSampler<false>):
+// Halton (scrambled radical inverses), and Sobol' dimensions past the tables (deep paths when the table size was capped).
+// Keeps the radical-inverse loops and the Sobol' bit walk out of the shade kernels (1 900 of the matte kernel's 9 950 SASS
+// instructions were Halton code that a Sobol' render never runs).
+__global__ void __launch_bounds__(256) k_sample_block(RenderDev R, int parity) {
+    const uint32_t n = R.cnt->n_path;
+    const uint32_t* q = R.q_path[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t id = q[i];
+        if (R.hit_bin[id] == Q_MISS) continue;
+        SampleCursor c;
+        c.dim = R.s_dim[id];
+        if (sobol_tab_covers(R.sampler, c.dim)) continue;
+        const uint32_t pxy = R.pixel[id];
+        c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
+        c.index = R.s_index[id];
+        if (R.sampler.vdims)  // table mode: the slot holds the sample number
+            c.index = sobol_interval_to_index(R.sampler, (uint32_t)R.sampler.log2_resolution, c.index, (int)(pxy & 0xffffu), (int)(pxy >> 16));
+        SampleBlock b;
+        sample_block(R.sampler, c, b);
+        R.u8[2 * id] = make_float4(b.u[0], b.u[1], b.u[2], b.u[3]);
+        R.u8[2 * id + 1] = make_float4(b.u[4], b.u[5], b.u[6], b.u[7]);
+    }
+}
+
+// XOR of the generator-matrix columns of dimensions d0..d0+3 over the set bits of `a` (sobol_sample_float's inner loop)
+PB_D uint4 sobol_bits4(const uint32_t* sobol_t, unsigned long long a, uint32_t d0) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    a &= (1ull << 52) - 1ull;  // SOBOL_MATRIX_SIZE columns; the reference indexes past the table (panics) beyond that
+    while (a != 0) {
+        const int bit = __ffsll((long long)a) - 1;
+        a &= a - 1;
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(sobol_t + (uint32_t)bit * 1024u + d0));
+        v.x ^= m.x; v.y ^= m.y; v.z ^= m.z; v.w ^= m.w;
+    }
+    return v;
+}
+// vp[pixel][d]: one thread per (pixel, 4 dimensions), dimensions fastest so that a warp writes contiguous rows
+__global__ void __launch_bounds__(256) k_sobol_table_pixels(SamplerDev S, uint32_t* vp, uint32_t npix) {
+    const uint32_t groups = S.vstride / 4u;
+    const unsigned long long total = (unsigned long long)npix * groups;
+    const unsigned long long* VI = S.vdc_inv + (S.log2_resolution - 1) * 52;
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t pix = (uint32_t)(t / groups), g = (uint32_t)(t % groups);
+        const uint32_t px = pix % S.sbw, py = pix / S.sbw;
+        unsigned long long b = ((unsigned long long)px << S.log2_resolution) | (unsigned long long)py, ip = 0;
+        for (int c = 0; b != 0; b >>= 1, ++c)
+            if (b & 1) ip ^= __ldg(VI + c);
+        reinterpret_cast<uint4*>(vp)[t] = sobol_bits4(S.sobol_t, ip, 4u * g);
+    }
+}
+// vs[s - s_begin][d]
+__global__ void __launch_bounds__(256) k_sobol_table_samples(SamplerDev S, uint32_t* vs, uint32_t s_begin, uint32_t n_samples) {
+    const uint32_t groups = S.vstride / 4u;
+    const unsigned long long total = (unsigned long long)n_samples * groups;
+    const uint32_t m = (uint32_t)S.log2_resolution;
+    const unsigned long long* V = S.vdc + (m - 1) * 52;
+    const unsigned long long* VI = S.vdc_inv + (m - 1) * 52;
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long frame = s_begin + (uint32_t)(t / groups);
+        const uint32_t g = (uint32_t)(t % groups);
+        unsigned long long delta = 0, is = frame << (2u * m);
+        unsigned long long f = frame;
+        for (int c = 0; f != 0; f >>= 1, ++c)
+            if (f & 1) delta ^= __ldg(V + c);
+        for (int c = 0; delta != 0; delta >>= 1, ++c)
+            if (delta & 1) is ^= __ldg(VI + c);
+        reinterpret_cast<uint4*>(vs)[t] = sobol_bits4(S.sobol_t, is, 4u * g);
     }
 }
 
@@ -1557,7 +1676,9 @@ struct RenderBuffers {  // all path-state arrays and queues sub-allocated from O
     size_t block_bytes = 0;
     uint32_t capacity = 0;
     RenderDev dev;
-    ~RenderBuffers() { pool_free(block, block_bytes); }
+    void* u8_block = nullptr;   // RenderDev::u8, allocated on first need (Halton, capped Sobol' tables)
+    size_t u8_bytes = 0;
+    ~RenderBuffers() { pool_free(block, block_bytes); if (u8_block) pool_free(u8_block, u8_bytes); }
 };
 
 // Resources that depend only on the DEVICE, shared by every scene rendered on it and kept for the life of the process:
@@ -1571,6 +1692,9 @@ struct DeviceShared {
     uint32_t* sobol32 = nullptr; uint32_t* sobol_t = nullptr; unsigned long long* vdc = nullptr; unsigned long long* vdc_inv = nullptr;
     unsigned long long sobol_hash = 0;
     float* filter_table = nullptr;
+    // Sobol' sample tables (SamplerDev::vp / vs), pooled blocks; vp is rebuilt only when its key changes
+    uint32_t* vp = nullptr; size_t vp_block = 0; unsigned long long vp_key[4] = {0, 0, 0, 0};
+    uint32_t* vs = nullptr; size_t vs_block = 0;
     struct Progress { unsigned long long cursor; uint32_t n_path; uint32_t pad; };
     Progress* prog = nullptr;            // pinned, PB_PROG_RING entries
     std::vector<cudaEvent_t> events;     // pool, grown on demand
@@ -1663,8 +1787,10 @@ template <typename T> int to_device(std::vector<std::pair<void*, size_t>>& owner
     PB_CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return PBRT_B200_OK;
 }
-template <typename T> int to_device_once(const std::vector<T>& h, T** d) {  // device-shared tables: plain cudaMalloc, never freed
-    PB_CUDA_TRY(cudaMalloc((void**)d, h.size() * sizeof(T)));
+template <typename T> int to_device_once(const std::vector<T>& h, T** d) {  // device-shared tables: never freed (pool_alloc: trims the cache and retries)
+    size_t got = 0;
+    *d = reinterpret_cast<T*>(pool_alloc(h.size() * sizeof(T), &got));
+    if (!*d) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the sampler tables");
     PB_CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return PBRT_B200_OK;
 }
@@ -1794,10 +1920,15 @@ int prepare_scene_state(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, Sc
         if (h == 0) h = 1;
         if (sh->sobol_hash != h) {
             if (!sh->sobol32) {
-                PB_CUDA_TRY(cudaMalloc((void**)&sh->sobol32, 1024 * 52 * 4));
-                PB_CUDA_TRY(cudaMalloc((void**)&sh->sobol_t, 1024 * 52 * 4));
-                PB_CUDA_TRY(cudaMalloc((void**)&sh->vdc, 25 * 52 * 8));
-                PB_CUDA_TRY(cudaMalloc((void**)&sh->vdc_inv, 26 * 52 * 8));
+                size_t got = 0;
+                sh->sobol32 = reinterpret_cast<uint32_t*>(pool_alloc(1024 * 52 * 4, &got));
+                sh->sobol_t = reinterpret_cast<uint32_t*>(pool_alloc(1024 * 52 * 4, &got));
+                sh->vdc = reinterpret_cast<unsigned long long*>(pool_alloc(25 * 52 * 8, &got));
+                sh->vdc_inv = reinterpret_cast<unsigned long long*>(pool_alloc(26 * 52 * 8, &got));
+                if (!sh->sobol32 || !sh->sobol_t || !sh->vdc || !sh->vdc_inv) {
+                    sh->sobol32 = nullptr;  // (the partial allocations stay with the process: 426 KB at most, once)
+                    return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the Sobol' tables");
+                }
             }
             PB_CUDA_TRY(cudaDeviceSynchronize());
             std::vector<uint32_t> tr(1024 * 52);
@@ -1833,14 +1964,22 @@ int prepare_scene_state(pbrt_b200_scene* sc, const pbrt_b200_render_desc* rd, Sc
         if ((rc = to_device_once(sums, &sh->prime_sums))) return rc;
         sh->n_halton_dims = N;
     }
-    if (!sh->filter_table) PB_CUDA_TRY(cudaMalloc((void**)&sh->filter_table, 256 * sizeof(float)));
+    if (!sh->filter_table) {
+        size_t got = 0;
+        sh->filter_table = reinterpret_cast<float*>(pool_alloc(256 * sizeof(float), &got));
+        if (!sh->filter_table) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the filter table");
+    }
     PB_CUDA_TRY(cudaMemcpyAsync(sh->filter_table, rd->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice, 0));
     if (!sh->prog) PB_CUDA_TRY(cudaMallocHost((void**)&sh->prog, PB_PROG_RING * sizeof(DeviceShared::Progress)));
     *out = st;
     return PBRT_B200_OK;
 }
 
-int ensure_buffers(SceneRenderState* st, uint32_t capacity) {
+// *capacity_io: wanted slots in, slots obtained out.  When the path-state block does not fit (another scene, torch or NCCL
+// holds the memory) the capacity is halved down to 2^20 slots before the call gives up: fewer paths in flight are slower
+// (DESIGN.md s5), not wrong.
+int ensure_buffers(SceneRenderState* st, uint32_t* capacity_io) {
+    uint32_t capacity = *capacity_io;
     if (st->buffers && st->buffers->capacity >= capacity) return PBRT_B200_OK;
     if (st->buffers) cudaDeviceSynchronize();
     delete st->buffers;
@@ -1848,12 +1987,17 @@ int ensure_buffers(SceneRenderState* st, uint32_t capacity) {
     RenderBuffers* rb = st->buffers;
     RenderDev& d = rb->dev;
     std::memset(&d, 0, sizeof d);
-    const size_t c = capacity;
     // bytes per slot: ray 32, hit 16+4+4+1, L_eta 16, beta_st 16, pfilm 8, s_index 8, s_dim 4, pixel 4, sh_ray 32, sh_contrib 16, mis_ray 32,
     // mis_contrib 16, 6 + Q_COUNT index queues x 4
     const size_t per_slot = 32 + 16 + 4 + 4 + 1 + 16 + 16 + 8 + 8 + 4 + 4 + 32 + 16 + 32 + 16 + 4 * (6 + Q_COUNT);
-    const size_t need = per_slot * c + 256 * 40 + sizeof(Counters);
-    rb->block = pool_alloc(need, &rb->block_bytes);
+    for (;;) {
+        rb->block = pool_alloc(per_slot * capacity + 256 * 40 + sizeof(Counters), &rb->block_bytes);
+        if (rb->block || capacity <= (1u << 20)) break;
+        cudaGetLastError();
+        capacity = ((capacity / 2u) + 255u) & ~255u;
+    }
+    *capacity_io = capacity;
+    const size_t c = capacity;
     if (!rb->block) { delete st->buffers; st->buffers = nullptr; return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the path state"); }
     Arena A; A.base = reinterpret_cast<char*>(rb->block); A.size = rb->block_bytes;
     d.ray = A.take<float4>(2 * c); d.hit = A.take<uint4>(c); d.hit_b2 = A.take<float>(c); d.hit_inst = A.take<uint32_t>(c); d.hit_bin = A.take<uint8_t>(c);
@@ -1904,6 +2048,8 @@ extern "C" int pbrt_b200_light_distribution_lookup(pbrt_b200_scene* sc, uint32_t
     if (strategy > PBRT_B200_LIGHTS_SPATIAL) return fail(PBRT_B200_ERR_INVALID, "light_distribution_lookup: unknown strategy");
     if (n > 0x7fffffffull) return fail(PBRT_B200_ERR_INVALID, "light_distribution_lookup: batch too large");
     PB_CUDA_TRY(cudaSetDevice(sc->device));
+    // the scene's light tables are shared with pbrt_b200_render: same per-device lock
+    std::lock_guard<std::mutex> render_lock(device_shared(sc->device)->mu);
     SceneRenderState* st = nullptr;
     int rc = prepare_light_state(sc, strategy, flags, &st);
     if (rc) return rc;
@@ -1915,10 +2061,14 @@ extern "C" int pbrt_b200_light_distribution_lookup(pbrt_b200_scene* sc, uint32_t
     R.ld_func = st->ld_func; R.ld_cdf = st->ld_cdf; R.ld_func_int = st->ld_func_int;
     R.inf_distrib = st->inf; R.infinite_lights = st->inf_list; R.n_infinite = st->n_inf;
     R.sp = st->sp;
-    float* d_pts = nullptr; int* d_vox = nullptr; float* d_func = nullptr;
-    PB_CUDA_TRY(cudaMalloc((void**)&d_pts, n * 3 * sizeof(float)));
-    PB_CUDA_TRY(cudaMalloc((void**)&d_vox, n * 3 * sizeof(int)));
-    PB_CUDA_TRY(cudaMalloc((void**)&d_func, n * nl * sizeof(float)));
+    // one pooled scratch block: points, voxel coordinates, per-light values
+    struct Scratch { void* p = nullptr; size_t n = 0; ~Scratch() { if (p) { cudaDeviceSynchronize(); pool_free(p, n); } } } scratch;
+    const size_t need = Arena::padded(n * 3 * sizeof(float)) + Arena::padded(n * 3 * sizeof(int)) + Arena::padded(n * nl * sizeof(float)) + 1024;
+    scratch.p = pool_alloc(need, &scratch.n);
+    if (!scratch.p) return fail(PBRT_B200_ERR_CUDA, "light_distribution_lookup: out of device memory");
+    Arena SA; SA.base = reinterpret_cast<char*>(scratch.p); SA.size = scratch.n;
+    float* d_pts = SA.take<float>(n * 3); int* d_vox = SA.take<int>(n * 3); float* d_func = SA.take<float>(n * nl);
+    if (!d_func) return fail(PBRT_B200_ERR_CUDA, "light_distribution_lookup: scratch arena too small (internal error)");
     PB_CUDA_TRY(cudaMemcpy(d_pts, points, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
     if (R.sp.enabled) {
         if (st->sp_eager_pending) {
@@ -1935,7 +2085,6 @@ extern "C" int pbrt_b200_light_distribution_lookup(pbrt_b200_scene* sc, uint32_t
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(voxel_out, d_vox, n * 3 * sizeof(int), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(func_out, d_func, n * nl * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaFree(d_pts); cudaFree(d_vox); cudaFree(d_func);
     PB_CUDA_TRY(e);
     return PBRT_B200_OK;
 }
@@ -2012,7 +2161,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         if (capacity > fit) capacity = (uint32_t)(fit & ~255ull);
     }
     if (capacity == 0) capacity = 256;
-    if ((rc = ensure_buffers(st, capacity))) return rc;
+    if ((rc = ensure_buffers(st, &capacity))) return rc;
     lap("buffers");
     RenderDev R = st->buffers->dev;
     R.capacity = capacity;
@@ -2106,8 +2255,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (own_film) {
         film_dev = reinterpret_cast<float4*>(pool_alloc(npix * sizeof(float4), &film_block));
         if (!film_dev) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the film");
-        PB_CUDA_TRY(cudaMemsetAsync(film_dev, 0, npix * sizeof(float4), 0));
     } else film_dev = reinterpret_cast<float4*>(rgbw_out);
+    ZtRelease film_release{own_film ? film_dev : nullptr, film_block};  // every error return below gives the scratch film back (after a sync)
+    if (own_film) PB_CUDA_TRY(cudaMemsetAsync(film_dev, 0, npix * sizeof(float4), 0));
     R.film = film_dev;
 
     int sm_count = 148;
@@ -2137,6 +2287,51 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     auto mark = [&]() { cudaEventRecord(pool_event(ev_used++), stream); };  // pairs around the trace kernels
     const bool timing = stats != nullptr && !zt;  // tile-serial mode runs ~10^5 tiny iterations: no per-phase events
     uint64_t launches = 0;
+    // ---- Sobol' sample tables (sobol_tab_block) for the path integrator's global-sampler runs
+    bool sample_prepass = !zt && !R.rec.kind;  // k_sample_block serves every path the tables do not
+    R.u8 = nullptr;
+    if (!zt && !R.rec.kind && S.kind == PBRT_B200_SAMPLER_SOBOL && S.log2_resolution > 0 && !getenv("PBRT_B200_NO_SOBOL_TABLES")) {
+        const uint32_t sbw = (uint32_t)(sb[2] - sb[0]), sbh = (uint32_t)(sb[3] - sb[1]);
+        const uint32_t want = (uint32_t)std::min<long long>(1024, 5ll + 8ll * std::max(R.max_depth, 0));
+        uint32_t vdims = want;
+        const size_t budget = (size_t)4 << 30;  // the pixel table may take up to 4 GB; deeper dimensions then go through k_sample_block
+        while (vdims > 13u && (size_t)sbw * sbh * ((vdims + 3u) & ~3u) * 4u > budget) vdims -= 8u;
+        const uint32_t vstride = (vdims + 3u) & ~3u;
+        const size_t vp_need = (size_t)sbw * sbh * vstride * 4u;
+        const size_t vs_need = (size_t)std::max<uint32_t>(s_end - s_begin, 1u) * vstride * 4u;
+        if (vp_need <= budget && sbw <= 0xffffu && sbh <= 0xffffu) {
+            SamplerDev T = S;
+            T.vstride = vstride; T.sbw = sbw; T.vdims = vdims;
+            const unsigned long long key[4] = {sh->sobol_hash, ((unsigned long long)sbw << 32) | sbh, ((unsigned long long)S.log2_resolution << 32) | vstride, 1ull};
+            bool ok = true;
+            if (std::memcmp(key, sh->vp_key, sizeof key) != 0 || !sh->vp) {
+                if (sh->vp && sh->vp_block < vp_need) { pool_free(sh->vp, sh->vp_block); sh->vp = nullptr; }
+                if (!sh->vp) sh->vp = reinterpret_cast<uint32_t*>(pool_alloc(vp_need, &sh->vp_block));
+                if (sh->vp) {
+                    k_sobol_table_pixels<<<148 * 8, 256, 0, stream>>>(T, sh->vp, sbw * sbh);
+                    std::memcpy(sh->vp_key, key, sizeof key);
+                } else { cudaGetLastError(); std::memset(sh->vp_key, 0, sizeof sh->vp_key); ok = false; }
+            }
+            if (ok && (!sh->vs || sh->vs_block < vs_need)) {
+                if (sh->vs) pool_free(sh->vs, sh->vs_block);
+                sh->vs = reinterpret_cast<uint32_t*>(pool_alloc(vs_need, &sh->vs_block));
+                if (!sh->vs) { cudaGetLastError(); sh->vs_block = 0; ok = false; }
+            }
+            if (ok) {
+                k_sobol_table_samples<<<64, 256, 0, stream>>>(T, sh->vs, s_begin, s_end - s_begin);
+                S.vp = sh->vp; S.vs = sh->vs; S.vdims = vdims; S.vstride = vstride; S.sbw = sbw; S.vs_begin = s_begin;
+                sample_prepass = vdims < want;
+            }
+        }
+    }
+    if (sample_prepass) {
+        RenderBuffers* rb = st->buffers;
+        const size_t need = (size_t)capacity * 32u;
+        if (rb->u8_block && rb->u8_bytes < need) { cudaDeviceSynchronize(); pool_free(rb->u8_block, rb->u8_bytes); rb->u8_block = nullptr; }
+        if (!rb->u8_block) rb->u8_block = pool_alloc(need, &rb->u8_bytes);
+        if (!rb->u8_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the sample blocks");
+        R.u8 = reinterpret_cast<float4*>(rb->u8_block);
+    }
     PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
     if (st->sp_eager_pending) {  // every voxel's distribution, once per scene
         const uint32_t nv = (uint32_t)R.sp.nvox[0] * (uint32_t)R.sp.nvox[1] * (uint32_t)R.sp.nvox[2];
@@ -2217,6 +2412,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                     else k_rec_mis<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                     if (timing) mark();
                 } else {
+                if (sample_prepass) { k_sample_block<<<grid_small, 256, 0, stream>>>(R, parity); launches += 1; }
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
                 if (full) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
                 else launch_shade<false, false>(R, parity, grid_small, grid_shade, stream);
@@ -2289,7 +2485,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         size_t stage_bytes = 0;
         const size_t nfl = npix * 4, chunk = (size_t)1 << 20;  // floats per chunk (4 MB)
         float* stage = reinterpret_cast<float*>(pool_alloc_host(std::min(nfl, 2 * chunk) * sizeof(float), &stage_bytes));
-        if (!stage) { pool_free(film_dev, film_block); return fail(PBRT_B200_ERR_CUDA, "render: out of pinned host memory"); }
+        if (!stage) return fail(PBRT_B200_ERR_CUDA, "render: out of pinned host memory");
         const float* src = reinterpret_cast<const float*>(film_dev);
         cudaEvent_t done[2] = {pool_event(0), pool_event(1)};
         const size_t nchunks = (nfl + chunk - 1) / chunk;
@@ -2310,7 +2506,6 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
             }
         }
         pool_free_host(stage, stage_bytes);
-        pool_free(film_dev, film_block);
         PB_CUDA_TRY(e);
         lap("film d2h + merge");
     }

@@ -41,9 +41,8 @@ template <bool CLOSEST>
 PB_D bool triangle_test(f3 o, f3 dir, float t_max, f3 p0, f3 p1, f3 p2, int kx, int ky, int kz, float Sx, float Sy, float Sz,
                         float* t_out, float* b0_out, float* b1_out, float* b2_out) {
     f3 q0 = p0 - o, q1 = p1 - o, q2 = p2 - o;
-    f3 p0t(comp(q0, kx), comp(q0, ky), comp(q0, kz));
-    f3 p1t(comp(q1, kx), comp(q1, ky), comp(q1, kz));
-    f3 p2t(comp(q2, kx), comp(q2, ky), comp(q2, kz));
+    (void)kx; (void)ky;
+    f3 p0t = permute_kz(q0, kz), p1t = permute_kz(q1, kz), p2t = permute_kz(q2, kz);
     p0t.x += Sx * p0t.z; p0t.y += Sy * p0t.z;
     p1t.x += Sx * p1t.z; p1t.y += Sy * p1t.z;
     p2t.x += Sx * p2t.z; p2t.y += Sy * p2t.z;

@@ -67,7 +67,21 @@ PB_D f3 cross(f3 a, f3 b) {
 }
 PB_D float maxcomp(f3 a) { return fmaxf(a.x, fmaxf(a.y, a.z)); }
 PB_D f3 face_forward(f3 n, f3 v) { return dot(n, v) < 0.0f ? -n : n; }
-PB_D float comp(f3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// c ? a : b as ONE select instruction.  The ternary form of the axis permutations below was compiled to divergent branches
+// (BSSY / BRA / BSYNC around predicated moves): ncu attributed 20 % of k_trace_closest's warp instructions to comp()
+// (profiles/r02_trace_comp.md); selp keeps the triangle test straight-line.
+PB_D float selp(float a, float b, bool c) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"((int)c));
+    return r;
+}
+PB_D float comp(f3 a, int i) { return selp(a.x, selp(a.y, a.z, i == 1), i == 0); }
+// Triangle::intersect's permutation (triangle.rs:151-160): kz = largest |d| component, kx = kz + 1, ky = kx + 1 (mod 3), i.e. a
+// rotation of (x, y, z) chosen by kz alone: kz = 2 -> (x, y, z), kz = 0 -> (y, z, x), kz = 1 -> (z, x, y)
+PB_D f3 permute_kz(f3 v, int kz) {
+    const bool k0 = kz == 0, k1 = kz == 1;
+    return f3(selp(v.y, selp(v.z, v.x, k1), k0), selp(v.z, selp(v.x, v.y, k1), k0), selp(v.x, selp(v.y, v.z, k1), k0));
+}
 // geometry/vector.rs:589-600
 PB_D void coordinate_system(f3 v1, f3* v2, f3* v3) {
     if (fabsf(v1.x) > fabsf(v1.y)) *v2 = vdiv(f3(-v1.z, 0.0f, v1.x), sqrtf(v1.x * v1.x + v1.z * v1.z));

@@ -338,6 +338,12 @@ class Transform:
 # ---------------------------------------------------------------------------
 
 
+# world_end() builds accelerators with this callable when no `builder` is passed; None = pbrt_b200_bvh_build.  bench.py's
+# `--impl reference` arm points it at the oracle's builder so that the CPU arm never loads the product library (the two
+# builders are byte-identical: tests/test_host_bvh.py).
+DEFAULT_BVH_BUILDER = None
+
+
 def bvh_build(prim_bounds, max_prims=4, split_method="sah"):
     """BVHAccel::new (bvh.rs:145-198) via pbrt_b200_bvh_build -> (nodes, ordered)."""
     lib = load_library()
@@ -691,7 +697,7 @@ class SceneBuilder:
             fs.lights = np.array(self._lights, LIGHT_DTYPE)
         if self._cur_object is not None:
             raise B200Error("WorldEnd inside an object definition")
-        build = builder or bvh_build
+        build = builder or DEFAULT_BVH_BUILDER or bvh_build
         # ObjectInstance (api.rs:1663-1713): an object with more than one primitive gets its own accelerator, built with the
         # scene's accelerator parameters; TransformedPrimitive::world_bound = prim_to_world.motion_bounds(object bound)
         used, obj_tables, next_ci = {}, [], nprim
