@@ -255,6 +255,27 @@ void orc_bsdf_eval(const pbrt_b200_material* m, const float* wo, const float* wi
     out13[12] = (float)b.num_components(BSDF_ALL & ~BSDF_SPECULAR);
 }
 
+// n evaluations of the same material / wo: wi[3n], u[2n] -> out[13n] (orc_bsdf_eval's layout); for the Monte-Carlo property
+// tests of the shading half (white furnace, pdf normalisation, reciprocity: tests/test_oracle_shading_properties.py)
+void orc_bsdf_eval_batch(const pbrt_b200_material* m, const float* wo, const float* wi, const float* u, int flags, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; ++i) orc_bsdf_eval(m, wo, wi + 3 * i, u + 2 * i, flags, out + 13 * i);
+}
+// Light::sample_li for n sample points u[2n] from the reference point (p, n): out[8n] = {Li.rgb, wi.xyz, pdf, Light::pdf_li(wi)}
+int orc_light_sample_batch(const pbrt_b200_scene_desc* sdesc, int light, const float* ref_p, const float* ref_n, const float* u, uint64_t n, float* out) {
+    RenderScene scene;
+    scene.init_render(*sdesc);
+    if (light < 0 || (uint64_t)light >= sdesc->n_lights) return 1;
+    InteractionData ref;
+    ref.p = V3(ref_p[0], ref_p[1], ref_p[2]); ref.n = V3(ref_n[0], ref_n[1], ref_n[2]); ref.p_error = V3(0, 0, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        LightSample ls = light_sample_li(scene, light, ref, P2(u[2 * i], u[2 * i + 1]));
+        float* o = out + 8 * i;
+        o[0] = ls.Li.c[0]; o[1] = ls.Li.c[1]; o[2] = ls.Li.c[2]; o[3] = ls.wi.x; o[4] = ls.wi.y; o[5] = ls.wi.z; o[6] = ls.pdf;
+        o[7] = (ls.pdf > 0.0f) ? light_pdf_li(scene, light, ref, ls.wi) : 0.0f;
+    }
+    return 0;
+}
+
 // PerspectiveCamera::generate_ray for one camera sample -> o[3], d[3]
 void orc_generate_ray(const pbrt_b200_camera* c, const float* cs5, float* out6) {
     CameraSample cs; cs.pfilm = P2(cs5[0], cs5[1]); cs.time = cs5[2]; cs.plens = P2(cs5[3], cs5[4]);

@@ -138,6 +138,30 @@ def bsdf_eval(material_row, wo, wi, u, flags=31):
     return out
 
 
+def bsdf_eval_batch(material_row, wo, wi, u, flags=31):
+    """n evaluations for one material / wo: wi [n,3], u [n,2] -> [n,13] rows laid out like bsdf_eval's."""
+    m = np.array([material_row], dtype=_H().MATERIAL_DTYPE)
+    wo = np.ascontiguousarray(wo, np.float32)
+    wi = np.ascontiguousarray(wi, np.float32).reshape(-1, 3)
+    u = np.ascontiguousarray(u, np.float32).reshape(-1, 2)
+    assert len(wi) == len(u)
+    out = np.zeros((len(wi), 13), np.float32)
+    lib().orc_bsdf_eval_batch(ptr(m), ptr(wo), ptr(wi), ptr(u), int(flags), C.c_uint64(len(wi)), ptr(out))
+    return out
+
+
+def light_sample_batch(flat, light, ref_p, ref_n, u):
+    """Light::sample_li from (ref_p, ref_n) for u [n,2] -> [n,8] rows {Li.rgb, wi.xyz, pdf, pdf_li(wi)}."""
+    u = np.ascontiguousarray(u, np.float32).reshape(-1, 2)
+    out = np.zeros((len(u), 8), np.float32)
+    d = flat.desc()
+    rc = lib().orc_light_sample_batch(C.byref(d), int(light), ptr(np.ascontiguousarray(ref_p, np.float32)), ptr(np.ascontiguousarray(ref_n, np.float32)), ptr(u),
+                                      C.c_uint64(len(u)), ptr(out))
+    if rc:
+        raise ValueError("light index out of range")
+    return out
+
+
 def rel_mse(img, ref):
     """relMSE of SURVEY.md s8(d): mean over pixels/channels of (a-b)^2 / (b^2 + 1e-2)."""
     a, b = np.asarray(img, np.float64), np.asarray(ref, np.float64)

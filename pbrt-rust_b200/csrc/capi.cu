@@ -91,17 +91,22 @@ __global__ void __launch_bounds__(PB_TRACE_BLOCK) k_intersect_p_batch(DevScene s
 //   k_interior_*   : exclusive scan of "node is interior" -> index of each interior node in the fat-node array
 //   k_fat_nodes    : LinearBVHNode[] -> fat nodes (both child boxes in the parent), LAST flags on leaf records
 __global__ void __launch_bounds__(256) k_leaf_records(const pbrt_b200_prim* __restrict__ prims, uint32_t n, const uint32_t* __restrict__ tri_indices,
-                                                      const float* __restrict__ vertex_p, float4* __restrict__ tris) {
+                                                      const float* __restrict__ vertex_p, float4* __restrict__ tris, const float* __restrict__ vertex_n,
+                                                      const float* __restrict__ vertex_uv, float4* __restrict__ slot_n, float2* __restrict__ slot_uv) {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const pbrt_b200_prim p = prims[s];
         uint32_t fl = p.flags & PB_TRI_FLAGS_MASK;
         float4 v[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+        float4 nn[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+        float2 uu[3] = {make_float2(0, 0), make_float2(0, 0), make_float2(0, 0)};
         if (p.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
             const uint32_t* ix = tri_indices + 3ull * p.shape_index;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const float* vp = vertex_p + 3ull * ix[k];
                 v[k].x = vp[0]; v[k].y = vp[1]; v[k].z = vp[2];
+                if (slot_n) { const float* np = vertex_n + 3ull * ix[k]; nn[k] = make_float4(np[0], np[1], np[2], 0.0f); }
+                if (slot_uv) { const float* up = vertex_uv + 2ull * ix[k]; uu[k] = make_float2(up[0], up[1]); }
             }
         } else if (p.shape_kind == PBRT_B200_SHAPE_INSTANCE) {
             fl |= PB_TRI_INSTANCE;
@@ -112,6 +117,29 @@ __global__ void __launch_bounds__(256) k_leaf_records(const pbrt_b200_prim* __re
         v[1].w = __uint_as_float(fl);
         v[2].w = __uint_as_float(p.shape_index);
         tris[3ull * s] = v[0]; tris[3ull * s + 1] = v[1]; tris[3ull * s + 2] = v[2];
+        if (slot_n) { slot_n[3ull * s] = nn[0]; slot_n[3ull * s + 1] = nn[1]; slot_n[3ull * s + 2] = nn[2]; }
+        if (slot_uv) { slot_uv[3ull * s] = uu[0]; slot_uv[3ull * s + 1] = uu[1]; slot_uv[3ull * s + 2] = uu[2]; }
+    }
+}
+// DevScene::light_tris: vertices and normals of the triangle behind each diffuse area light
+__global__ void __launch_bounds__(128) k_light_tris(const pbrt_b200_light* __restrict__ lights, uint32_t n, const uint32_t* __restrict__ tri_indices,
+                                                    const float* __restrict__ vertex_p, const float* __restrict__ vertex_n, float4* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 r[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[k] = make_float4(0, 0, 0, 0);
+        const pbrt_b200_light l = lights[i];
+        if (l.type == PBRT_B200_LIGHT_DIFFUSE && l.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
+            const uint32_t* ix = tri_indices + 3ull * l.shape_index;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float* vp = vertex_p + 3ull * ix[k];
+                r[k] = make_float4(vp[0], vp[1], vp[2], 0.0f);
+                if (vertex_n) { const float* np = vertex_n + 3ull * ix[k]; r[3 + k] = make_float4(np[0], np[1], np[2], 0.0f); }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out[6ull * i + k] = r[k];
     }
 }
 
@@ -400,6 +428,7 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     add(12ull * nv); add(d->vertex_n ? 12ull * nv : 0); add(d->vertex_s ? 12ull * nv : 0); add(d->vertex_uv ? 8ull * nv : 0);
     add(12ull * nt); add(sizeof(pbrt_b200_sphere) * d->n_spheres); add(sizeof(pbrt_b200_material) * d->n_materials); add(sizeof(pbrt_b200_light) * d->n_lights);
     add(sizeof(DevInstance) * d->n_instances); add(4ull * d->n_objects); add(sizeof(DevScene));
+    add(d->vertex_n ? 48ull * np : 0); add(d->vertex_uv ? 24ull * np : 0); add(96ull * d->n_lights);  // slot_n, slot_uv, light_tris
     const size_t resident = need;
     add(sizeof(pbrt_b200_bvh_node) * nn); add(4ull * nn); add(4ull * nb);
     need += 4096;
@@ -446,6 +475,10 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     float4* quads = A.take<float4>(8ull * max_interior);
     float4* tris = A.take<float4>(3ull * np);
     ds.nodes = fat; ds.quads = quads; ds.tris = tris;
+    float4* slot_n = (d->vertex_n && np) ? A.take<float4>(3ull * np) : nullptr;
+    float2* slot_uv = (d->vertex_uv && np) ? A.take<float2>(3ull * np) : nullptr;
+    float4* light_tris = d->n_lights ? A.take<float4>(6ull * d->n_lights) : nullptr;
+    ds.slot_n = slot_n; ds.slot_uv = slot_uv; ds.light_tris = light_tris;
     const pbrt_b200_bvh_node* nodes_dev = nullptr;
     up(d->prims, sizeof(pbrt_b200_prim) * np, &ds.prims);
     up(d->vertex_p, 12ull * nv, &ds.vertex_p);
@@ -462,7 +495,12 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     lap("checks joined");
     ds.root_ref = root_ref;
     ds.n_fat = n_interior;
-    if (np && err == cudaSuccess) k_leaf_records<<<(unsigned)std::min<uint64_t>((np + 255) / 256, 148 * 16), 256, 0, stream>>>(ds.prims, (uint32_t)np, ds.tri_indices, ds.vertex_p, tris);
+    if (np && err == cudaSuccess)
+        k_leaf_records<<<(unsigned)std::min<uint64_t>((np + 255) / 256, 148 * 16), 256, 0, stream>>>(ds.prims, (uint32_t)np, ds.tri_indices, ds.vertex_p, tris, ds.vertex_n,
+                                                                                                       ds.vertex_uv, slot_n, slot_uv);
+    if (d->n_lights && err == cudaSuccess)
+        k_light_tris<<<(unsigned)std::min<uint64_t>((d->n_lights + 127) / 128, 148 * 8), 128, 0, stream>>>(ds.lights, (uint32_t)d->n_lights, ds.tri_indices, ds.vertex_p, ds.vertex_n,
+                                                                                                             light_tris);
     if (nn) {
         uint32_t* fat_index = A.take<uint32_t>(nn);
         uint32_t* block_sums = A.take<uint32_t>(nb);

@@ -156,6 +156,7 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
 }
 
 // One step of the depth-first recursion for every live camera sample: shade the hit of its current ray.
+#if !PB_EXACT_TU
 template <bool INST, bool ZT>
 __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_path;
@@ -322,6 +323,9 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
     }
 }
 
+#endif  // !PB_EXACT_TU
+
+#if PB_EXACT_TU
 struct RecShadowJob {
     RenderDev* R;
     PB_D bool load(uint32_t e, f3* o, f3* d, float* t_max) const {
@@ -373,5 +377,7 @@ __global__ void PB_TRACE_BOUNDS k_rec_mis(RenderDev R) {
     RecMisJob<INST> job{&R};
     trace_queue<false, INST>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
+
+#endif  // PB_EXACT_TU
 
 }  // namespace pb

@@ -40,6 +40,19 @@
 #define PB_TRACE_BOUNDS __launch_bounds__(PB_TRACE_BLOCK)
 #endif
 
+// This file is compiled TWICE (csrc/Makefile):
+//   render.o  (PB_EXACT_TU = 1, --fmad=false, IEEE division / square root): ray generation, traversal, film, light tables, the
+//             (0,2) megakernel and the host side -- everything whose arithmetic is pinned bit for bit against the oracle;
+//   shade.o   (shade.cu defines PB_TU_SHADE and includes this file; --use_fast_math): only k_shade / k_rec_shade and their
+//             launchers.  Shading is tolerance-parity by nature (libm differs from CUDA's transcendentals):
+//             there the ~200 IEEE divisions and square roots per path (8-10 SASS instructions each, with a slow-path call)
+//             become MUFU.RCP / MUFU.RSQ sequences and a*b+c contracts to FFMA.
+#ifdef PB_TU_SHADE
+#define PB_EXACT_TU 0
+#else
+#define PB_EXACT_TU 1
+#endif
+
 using namespace pb;
 
 namespace pb {
@@ -195,6 +208,9 @@ struct RenderDev {
     float4* sh_contrib;  // {rgb to add when unoccluded, -}
     float4* mis_ray;     // MIS ray (2 x float4)
     float4* mis_contrib; // {rgb factor (beta * f * |cos| * w / (scattpdf * lightselpdf)), light index bits}
+    int* sp_voxel;       // lazy SpatialLightDistribution: the voxel k_spatial_mark claimed for the slot's hit.  The shade kernels (fast-math
+                         // translation unit) would otherwise recompute the hit point with different roundings and, on a voxel boundary,
+                         // look up a voxel nobody built
     float4* u8;          // 2 x float4 per slot: the next eight sample dimensions, written by k_sample_block when the Sobol' tables
                          // do not serve the path (Halton; dimensions beyond the tables); nullptr when that cannot happen
     uint32_t* q_path[2];
@@ -459,10 +475,22 @@ template <> struct PathSampler<false> {
     SampleCursor c; SampleBlock sb;
     // The shade kernels carry no sampler arithmetic: either the Sobol' tables cover the block (two row reads), or the
     // pre-pass k_sample_block has left the eight values in R.u8 (Halton, Sobol' dimensions beyond the tables).
+    uint32_t pxy;
+    // Called first thing in shade_path: the slot's sampler state is loaded together with its ray and hit record, and the pixel's
+    // table row (a random 32..64-byte span of a table far larger than L2) is requested from HBM right away -- by the time the
+    // surface and the BSDF are set up it sits in L1, instead of being a third dependent DRAM round trip (queue -> state -> row)
+    // in the middle of the kernel (27 % of the matte kernel's stall samples, profiles/r02_ncu_shade.md).
+    PB_D void prefetch(const RenderDev& R, uint32_t id) {
+        c.index = R.s_index[id]; c.dim = R.s_dim[id]; pxy = R.pixel[id];
+        if (sobol_tab_covers(R.sampler, c.dim)) {
+            const uint32_t* a = R.sampler.vp + ((size_t)(pxy >> 16) * R.sampler.sbw + (pxy & 0xffffu)) * R.sampler.vstride + c.dim;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 7));
+        }
+    }
     PB_D void begin(const RenderDev& R, uint32_t id) {
-        c.index = R.s_index[id]; c.dim = R.s_dim[id];
         sb.used = 0;
-        if (sobol_tab_covers(R.sampler, c.dim)) sobol_tab_block(R.sampler, R.pixel[id], (uint32_t)c.index, c.dim, sb.u);
+        if (sobol_tab_covers(R.sampler, c.dim)) sobol_tab_block(R.sampler, pxy, (uint32_t)c.index, c.dim, sb.u);
         else {
             const float4 lo = R.u8[2 * id], hi = R.u8[2 * id + 1];
             sb.u[0] = lo.x; sb.u[1] = lo.y; sb.u[2] = lo.z; sb.u[3] = lo.w; sb.u[4] = hi.x; sb.u[5] = hi.y; sb.u[6] = hi.z; sb.u[7] = hi.w;
@@ -474,6 +502,7 @@ template <> struct PathSampler<false> {
 };
 template <> struct PathSampler<true> {
     ZtCursor z;
+    PB_D void prefetch(const RenderDev&, uint32_t) {}
     PB_D void begin(const RenderDev& R, uint32_t id) { z = zt_cursor(R, id); }  // slot == tile ordinal
     PB_D float get_1d() { return pb::get_1d(z); }
     PB_D float2 get_2d() { return pb::get_2d(z); }
@@ -651,6 +680,7 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     return true;
 }
 
+#if PB_EXACT_TU
 // Start of a render call: every path slot is free and carries no sample.
 __global__ void __launch_bounds__(256) k_init_slots(RenderDev R, uint32_t count) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
@@ -659,6 +689,8 @@ __global__ void __launch_bounds__(256) k_init_slots(RenderDev R, uint32_t count)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) R.cnt->n_dead = count;
 }
+#endif  // PB_EXACT_TU
+
 
 // ---------------------------------------------------------------------------
 // K2: closest-hit for path rays (persistent ray queue), K4: compaction by material
@@ -676,6 +708,7 @@ PB_D int store_closest_hit(const RenderDev& R, uint32_t id, const TravRay& r) {
     R.hit_bin[id] = (uint8_t)bin;
     return bin;
 }
+#if PB_EXACT_TU
 struct PathClosestJob {
     RenderDev* R; const uint32_t* q;
     PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
@@ -702,10 +735,19 @@ __global__ void __launch_bounds__(256) k_classify(RenderDev R, int parity) {
         bool valid = i < n;
         uint32_t id = valid ? q[i] : 0u;
         int bin = valid ? (int)R.hit_bin[id] : -1;
-#pragma unroll
-        for (int k = 0; k < Q_COUNT; ++k) queue_push(R.q_mat[k], &R.cnt->n_mat[k], id, bin == k);
+        // lanes of the same bin form a group (match.any); the lowest lane of every group reserves the group's span -- the
+        // atomics of all bins are in flight together (the per-bin queue_push loop paid up to seven dependent round trips)
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        const unsigned lane = threadIdx.x & 31u;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (valid && (int)lane == leader) base = atomicAdd(&R.cnt->n_mat[bin], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) R.q_mat[bin][base + __popc(peers & ((1u << lane) - 1u))] = id;
     }
 }
+#endif  // PB_EXACT_TU
+
 
 // ---------------------------------------------------------------------------
 // lights
@@ -740,17 +782,16 @@ struct LightSample { rgb Li; f3 wi; float pdf; f3 p1, p1_err, p1_n; };
 PB_D void triangle_light_sample(const DevScene& s, const pbrt_b200_light& l, f3 ref_p, float2 u, LightSample& r) {
     float su0 = sqrtf(u.x);
     float b0 = 1.0f - su0, b1 = u.y * su0;  // uniform_sample_triangle, sampling.rs:244-248
-    const uint32_t* idx = s.tri_indices + 3ull * l.shape_index;
-    uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
-    const float* P = s.vertex_p;
-    f3 p0(P[3 * i0], P[3 * i0 + 1], P[3 * i0 + 2]), p1(P[3 * i1], P[3 * i1 + 1], P[3 * i1 + 2]), p2(P[3 * i2], P[3 * i2 + 1], P[3 * i2 + 2]);
+    // the emitting triangle's vertices and normals, pre-gathered per light (DevScene::light_tris)
+    const float4* lt = s.light_tris + 6ull * (size_t)(&l - s.lights);
+    const float4 q0 = __ldg(lt), q1 = __ldg(lt + 1), q2 = __ldg(lt + 2);
+    f3 p0(q0.x, q0.y, q0.z), p1(q1.x, q1.y, q1.z), p2(q2.x, q2.y, q2.z);
     float b2 = 1.0f - b0 - b1;
     f3 p = p0 * b0 + p1 * b1 + p2 * b2;
     f3 n = normalize(cross(p1 - p0, p2 - p0));
     if ((l.shape_flags & PBRT_B200_PRIM_HAS_N) && s.vertex_n) {
-        const float* N = s.vertex_n;
-        f3 ns = f3(N[3 * i0], N[3 * i0 + 1], N[3 * i0 + 2]) * b0 + f3(N[3 * i1], N[3 * i1 + 1], N[3 * i1 + 2]) * b1 +
-                f3(N[3 * i2], N[3 * i2 + 1], N[3 * i2 + 2]) * b2;
+        const float4 n0 = __ldg(lt + 3), n1 = __ldg(lt + 4), n2 = __ldg(lt + 5);
+        f3 ns = f3(n0.x, n0.y, n0.z) * b0 + f3(n1.x, n1.y, n1.z) * b1 + f3(n2.x, n2.y, n2.z) * b2;
         n = face_forward(n, ns);
     } else if (((l.shape_flags & PBRT_B200_PRIM_REVERSE_ORIENTATION) != 0) != ((l.shape_flags & PBRT_B200_PRIM_SWAPS_HANDEDNESS) != 0)) {
         n = n * -1.0f;
@@ -919,10 +960,9 @@ PB_D void light_sample_li(const RenderDev& R, uint32_t li, f3 ref_p, float2 u, L
 // (Triangle::intersect with s = None) and converts to solid angle with the SIGNED cosine.
 PB_D float triangle_light_pdf_wi(const DevScene& s, const pbrt_b200_light& l, const Surf& ref, f3 wi) {
     f3 o = offset_ray_origin(ref.p, ref.p_error, ref.n, wi);
-    const uint32_t* idx = s.tri_indices + 3ull * l.shape_index;
-    const float* P = s.vertex_p;
-    uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
-    f3 p0(P[3 * i0], P[3 * i0 + 1], P[3 * i0 + 2]), p1(P[3 * i1], P[3 * i1 + 1], P[3 * i1 + 2]), p2(P[3 * i2], P[3 * i2 + 1], P[3 * i2 + 2]);
+    const float4* lt = s.light_tris + 6ull * (size_t)(&l - s.lights);
+    const float4 q0 = __ldg(lt), q1 = __ldg(lt + 1), q2 = __ldg(lt + 2);
+    f3 p0(q0.x, q0.y, q0.z), p1(q1.x, q1.y, q1.z), p2(q2.x, q2.y, q2.z);
     f3 ad = vabs(wi);
     int kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
     int kx = (kz + 1 == 3) ? 0 : kz + 1, ky = (kx + 1 == 3) ? 0 : kx + 1;
@@ -933,7 +973,7 @@ PB_D float triangle_light_pdf_wi(const DevScene& s, const pbrt_b200_light& l, co
     float2 uv0, uv1, uv2;
     fetch_uv(s, l.shape_flags, l.shape_index, &uv0, &uv1, &uv2);
     if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) return 0.0f;
-    Surf ls = triangle_surface(s, p0, p1, p2, l.shape_flags, l.shape_index, wi, b0, b1, b2, false);
+    Surf ls = triangle_surface(s, p0, p1, p2, l.shape_flags, l.shape_index, wi, b0, b1, b2, false, PB_NO_SLOT, lt + 3);
     f3 dd = ref.p - ls.p;
     float pdf = len2(dd) / (dot(ls.n, -wi) * l.area);
     if (isinf(pdf)) pdf = 0.0f;
@@ -981,6 +1021,7 @@ PB_D int spatial_voxel(const RenderDev& R, f3 p) {
     return (pi[2] * R.sp.nvox[1] + pi[1]) * R.sp.nvox[0] + pi[0];
 }
 
+#if PB_EXACT_TU
 // compute_dsitribution, lightdistrib.rs:152-228: one CTA per voxel; thread j owns lights j, j+blockDim, ... and walks the
 // 128 Halton points in order (same accumulation order as the reference); the sum / floor / cdf passes that the reference
 // does sequentially are done by one thread so the f32 roundings match.
@@ -1057,6 +1098,7 @@ __global__ void __launch_bounds__(256) k_spatial_mark(RenderDev R, int parity) {
         Surf si = surface_at_hit<true>(R.scene, hinst, h.x, f3(ra.x, ra.y, ra.z), f3(rb.x, rb.y, rb.z), __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w),
                                  R.hit_b2[id], &fl);
         int v = spatial_voxel(R, si.p);
+        R.sp_voxel[id] = v;
         if (R.sp.slot[v] != -1) continue;
         if (atomicCAS(R.sp.slot + v, -1, -2) == -1) {
             uint32_t sl = atomicAdd(R.sp.counters + 1, 1u);
@@ -1093,10 +1135,13 @@ __global__ void __launch_bounds__(256) k_light_distrib_gather(RenderDev R, const
         for (uint32_t j = 0; j < nl; ++j) func_out[(size_t)i * nl + j] = func ? func[j] : -1.0f;
     }
 }
+#endif  // PB_EXACT_TU
+
 
 // ---------------------------------------------------------------------------
 // sampler pre-pass and Sobol' table builders
 // ---------------------------------------------------------------------------
+#if PB_EXACT_TU
 // The eight dimensions a hit path is about to consume, for paths the Sobol' tables do not serve (see PathSampler<false>):
 // Halton (scrambled radical inverses), and Sobol' dimensions past the tables (deep paths when the table size was capped).
 // Keeps the radical-inverse loops and the Sobol' bit walk out of the shade kernels (1 900 of the matte kernel's 9 950 SASS
@@ -1167,6 +1212,8 @@ __global__ void __launch_bounds__(256) k_sobol_table_samples(SamplerDev S, uint3
         reinterpret_cast<uint4*>(vs)[t] = sobol_bits4(S.sobol_t, is, 4u * g);
     }
 }
+#endif  // PB_EXACT_TU
+
 
 // ---------------------------------------------------------------------------
 // K5/K6: shade
@@ -1209,6 +1256,8 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
         push_dead = true;
     } else {
         uint4 h = R.hit[id];
+        PathSampler<ZT> smp;
+        smp.prefetch(R, id);
         uint32_t fl;
         const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
         Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
@@ -1232,7 +1281,6 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
                 R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
                 push_next = true;
             } else {
-                PathSampler<ZT> smp;
                 smp.begin(R, id);
                 const int NONSPEC = BX_ALL & ~BX_SPECULAR;
                 // ---- uniform_sample_onelight + estimate_direct, integrator.rs:81-237
@@ -1241,7 +1289,7 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
                     // light_distrib.lookup(isect.p), path.rs:132
                     const float* ld_cdf = R.ld_cdf; const float* ld_func = R.ld_func; float ld_func_int = R.ld_func_int;
                     if (R.sp.enabled) {
-                        int sl = R.sp.slot[spatial_voxel(R, si.p)];
+                        int sl = R.sp.slot[(R.sp.lazy && !ZT) ? R.sp_voxel[id] : spatial_voxel(R, si.p)];  // (the megakernel has no mark pass)
                         if (sl >= 0) { ld_cdf = R.sp.cdf + (size_t)sl * (R.n_lights + 1); ld_func = R.sp.func + (size_t)sl * R.n_lights; ld_func_int = R.sp.func_int[sl]; }
                         else atomicExch(R.sp.counters + 2, 1u);  // cannot happen unless the slot table overflowed: the host fails the call
                     }
@@ -1338,6 +1386,7 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
     return ShadeOut{push_next, push_shadow, push_mis, push_dead, zero_rad};
 }
 
+#if !PB_EXACT_TU
 template <int BIN, bool INST, bool ZT>
 __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_mat[BIN];
@@ -1352,16 +1401,35 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
             o = shade_path<BIN, INST, ZT>(R, id);
         }
         {
-            unsigned zm = __ballot_sync(__activemask(), o.zero_rad);
-            if (zm && (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&R.cnt->zero_radiance, (unsigned long long)__popc(zm));
+            unsigned zm = __ballot_sync(0xffffffffu, o.zero_rad);
+            if (zm && (threadIdx.x & 31) == 0) atomicAdd(&R.cnt->zero_radiance, (unsigned long long)__popc(zm));
         }
-        queue_push(q_next, &R.cnt->n_next, id, o.push_next);
-        queue_push(R.q_shadow, &R.cnt->n_shadow, id, o.push_shadow);
-        queue_push(R.q_mis, &R.cnt->n_mis, id, o.push_mis);
-        queue_push(R.q_dead[parity], &R.cnt->n_dead, id, o.push_dead);
+        // the four appends of an iteration: lane 0 issues all the counter atomics back to back, THEN the bases are broadcast --
+        // one atomic round trip per iteration instead of four dependent ones (17 % of the matte kernel's stall samples sat on
+        // the first broadcast, profiles/r02_ncu_shade.md).  All 32 lanes are here: the loop runs over n rounded up to a warp.
+        {
+            const unsigned m0 = __ballot_sync(0xffffffffu, o.push_next), m1 = __ballot_sync(0xffffffffu, o.push_shadow);
+            const unsigned m2 = __ballot_sync(0xffffffffu, o.push_mis), m3 = __ballot_sync(0xffffffffu, o.push_dead);
+            const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            if (lane == 0) {
+                if (m0) b0 = atomicAdd(&R.cnt->n_next, (uint32_t)__popc(m0));
+                if (m1) b1 = atomicAdd(&R.cnt->n_shadow, (uint32_t)__popc(m1));
+                if (m2) b2 = atomicAdd(&R.cnt->n_mis, (uint32_t)__popc(m2));
+                if (m3) b3 = atomicAdd(&R.cnt->n_dead, (uint32_t)__popc(m3));
+            }
+            b0 = __shfl_sync(0xffffffffu, b0, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
+            b2 = __shfl_sync(0xffffffffu, b2, 0); b3 = __shfl_sync(0xffffffffu, b3, 0);
+            if (o.push_next) q_next[b0 + __popc(m0 & below)] = id;
+            if (o.push_shadow) R.q_shadow[b1 + __popc(m1 & below)] = id;
+            if (o.push_mis) R.q_mis[b2 + __popc(m2 & below)] = id;
+            if (o.push_dead) R.q_dead[parity][b3 + __popc(m3 & below)] = id;
+        }
     }
 }
+#endif  // !PB_EXACT_TU
 
+#if PB_EXACT_TU
 // ---------------------------------------------------------------------------
 // K3: shadow rays (VisibilityTester::unoccluded, core/light.rs:120-123)
 // ---------------------------------------------------------------------------
@@ -1434,9 +1502,38 @@ __global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
     trace_queue<false, INST>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
 
+#endif  // PB_EXACT_TU
 }  // namespace pb
 #include "recursive.cuh"
 namespace pb {
+
+// Launchers of the kernels that live in the other translation unit (shade.o, see the top of this file)
+void launch_shade_kernels(const RenderDev& R, int parity, bool full, int grid_small, int grid_shade, cudaStream_t stream);
+void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int grid_shade, cudaStream_t stream);
+#if !PB_EXACT_TU
+// one launch per material queue (sort/compact-by-material); INST selects the kernel family (trace.cuh, sphere lights)
+template <bool INST>
+static void launch_shade_family(const RenderDev& R, int parity, int grid_small, int grid_shade, cudaStream_t stream) {
+    k_shade<Q_MISS, INST, false><<<grid_small, 128, 0, stream>>>(R, parity);
+    k_shade<Q_MATTE, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_PLASTIC, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_MIRROR, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_GLASS, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_METAL, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    k_shade<Q_NOMAT, INST, false><<<grid_small, 128, 0, stream>>>(R, parity);
+}
+void launch_shade_kernels(const RenderDev& R, int parity, bool full, int grid_small, int grid_shade, cudaStream_t stream) {
+    if (full) launch_shade_family<true>(R, parity, grid_small, grid_shade, stream);
+    else launch_shade_family<false>(R, parity, grid_small, grid_shade, stream);
+}
+void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int grid_shade, cudaStream_t stream) {
+    if (zt) k_rec_shade<true, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+    else if (full) k_rec_shade<true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    else k_rec_shade<false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+}
+}  // namespace pb (shade.o ends here)
+#endif  // !PB_EXACT_TU
+#if PB_EXACT_TU
 
 // ---------------------------------------------------------------------------
 // K8: finished paths -> film
@@ -1473,8 +1570,19 @@ __global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, u
         if (regen) ok = gen_camera_path(R, cursor + i, id);
         unsigned m = __ballot_sync(0xffffffffu, ok);
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
-        queue_push(R.q_path[parity ^ 1], &R.cnt->n_next, id, ok);
-        queue_push(R.q_dead[parity ^ 1], &R.cnt->n_dead_next, id, regen && !ok);
+        {   // both appends behind one atomic round trip (see k_shade)
+            const bool again = regen && !ok;
+            const unsigned m1 = __ballot_sync(0xffffffffu, again);
+            const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+            uint32_t b0 = 0, b1 = 0;
+            if (lane == 0) {
+                if (m) b0 = atomicAdd(&R.cnt->n_next, (uint32_t)__popc(m));
+                if (m1) b1 = atomicAdd(&R.cnt->n_dead_next, (uint32_t)__popc(m1));
+            }
+            b0 = __shfl_sync(0xffffffffu, b0, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
+            if (ok) R.q_path[parity ^ 1][b0 + __popc(m & below)] = id;
+            if (again) R.q_dead[parity ^ 1][b1 + __popc(m1 & below)] = id;
+        }
     }
 }
 
@@ -1989,7 +2097,7 @@ int ensure_buffers(SceneRenderState* st, uint32_t* capacity_io) {
     std::memset(&d, 0, sizeof d);
     // bytes per slot: ray 32, hit 16+4+4+1, L_eta 16, beta_st 16, pfilm 8, s_index 8, s_dim 4, pixel 4, sh_ray 32, sh_contrib 16, mis_ray 32,
     // mis_contrib 16, 6 + Q_COUNT index queues x 4
-    const size_t per_slot = 32 + 16 + 4 + 4 + 1 + 16 + 16 + 8 + 8 + 4 + 4 + 32 + 16 + 32 + 16 + 4 * (6 + Q_COUNT);
+    const size_t per_slot = 32 + 16 + 4 + 4 + 1 + 16 + 16 + 8 + 8 + 4 + 4 + 32 + 16 + 32 + 16 + 4 * (6 + Q_COUNT) + 4;
     for (;;) {
         rb->block = pool_alloc(per_slot * capacity + 256 * 40 + sizeof(Counters), &rb->block_bytes);
         if (rb->block || capacity <= (1u << 20)) break;
@@ -2000,7 +2108,7 @@ int ensure_buffers(SceneRenderState* st, uint32_t* capacity_io) {
     const size_t c = capacity;
     if (!rb->block) { delete st->buffers; st->buffers = nullptr; return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the path state"); }
     Arena A; A.base = reinterpret_cast<char*>(rb->block); A.size = rb->block_bytes;
-    d.ray = A.take<float4>(2 * c); d.hit = A.take<uint4>(c); d.hit_b2 = A.take<float>(c); d.hit_inst = A.take<uint32_t>(c); d.hit_bin = A.take<uint8_t>(c);
+    d.ray = A.take<float4>(2 * c); d.hit = A.take<uint4>(c); d.hit_b2 = A.take<float>(c); d.hit_inst = A.take<uint32_t>(c); d.hit_bin = A.take<uint8_t>(c); d.sp_voxel = A.take<int>(c);
     d.L_eta = A.take<float4>(c); d.beta_st = A.take<float4>(c); d.pfilm = A.take<float2>(c);
     d.s_index = A.take<unsigned long long>(c); d.s_dim = A.take<uint32_t>(c); d.pixel = A.take<uint32_t>(c);
     d.sh_ray = A.take<float4>(2 * c); d.sh_contrib = A.take<float4>(c); d.mis_ray = A.take<float4>(2 * c); d.mis_contrib = A.take<float4>(c);
@@ -2028,17 +2136,6 @@ namespace {
 void launch_spatial_build(const RenderDev& R, uint32_t grid, cudaStream_t stream, int eager, uint32_t n_eager) {
     if (R.scene.n_sphere_lights) k_spatial_build<true><<<grid, 128, 0, stream>>>(R, eager, n_eager);
     else k_spatial_build<false><<<grid, 128, 0, stream>>>(R, eager, n_eager);
-}
-// one launch per material queue (sort/compact-by-material); INST / ZT select the kernel family (trace.cuh, PathSampler)
-template <bool INST, bool ZT>
-void launch_shade(const RenderDev& R, int parity, int grid_small, int grid_shade, cudaStream_t stream) {
-    k_shade<Q_MISS, INST, ZT><<<grid_small, 128, 0, stream>>>(R, parity);
-    k_shade<Q_MATTE, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
-    k_shade<Q_PLASTIC, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
-    k_shade<Q_MIRROR, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
-    k_shade<Q_GLASS, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
-    k_shade<Q_METAL, INST, ZT><<<grid_shade, 128, 0, stream>>>(R, parity);
-    k_shade<Q_NOMAT, INST, ZT><<<grid_small, 128, 0, stream>>>(R, parity);
 }
 }  // namespace
 
@@ -2401,9 +2498,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                     launches += 3;
                 }
                 if (R.rec.kind) {  // whitted / directlighting: one generic shade kernel, entry-indexed shadow and MIS rays
-                    if (zt) k_rec_shade<true, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    else if (full) k_rec_shade<true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-                    else k_rec_shade<false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+                    launch_rec_shade(R, parity, zt, full, grid_shade, stream);
                     if (timing) mark();
                     if (inst) k_rec_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                     else k_rec_shadow<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
@@ -2414,8 +2509,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 } else {
                 if (sample_prepass) { k_sample_block<<<grid_small, 256, 0, stream>>>(R, parity); launches += 1; }
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
-                if (full) launch_shade<true, false>(R, parity, grid_small, grid_shade, stream);
-                else launch_shade<false, false>(R, parity, grid_small, grid_shade, stream);
+                launch_shade_kernels(R, parity, full, grid_small, grid_shade, stream);
                 if (timing) mark();
                 if (inst) k_trace_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
                 else k_trace_shadow<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
@@ -2511,3 +2605,4 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     }
     return PBRT_B200_OK;
 }
+#endif  // PB_EXACT_TU

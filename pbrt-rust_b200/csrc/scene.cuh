@@ -54,6 +54,13 @@ struct DevScene {
     //  v0 = {p0.xyz, creation_index}  v1 = {p1.xyz, flags}  v2 = {p2.xyz, shape_index}
     const float4* tris;
     uint32_t n_slots;
+    // Shading-side companions of the leaf records, same slot order, so that a hit's normals / uvs are ONE dependent fetch
+    // away from the hit record instead of three (slot -> shape_index -> vertex indices -> per-vertex gathers):
+    //  slot_n[3 * slot + k] = {n_k.xyz, 0} (only when the scene has per-vertex normals), slot_uv[3 * slot + k] = uv_k
+    const float4* slot_n;
+    const float2* slot_uv;
+    // Triangle area lights: light_tris[6 * light + k] = {p_k.xyz, 0} (k < 3), {n_k.xyz, 0} (k >= 3); zeros for other lights
+    const float4* light_tris;
     const pbrt_b200_prim* prims;      // slot order
     const float* vertex_p;
     const float* vertex_n;

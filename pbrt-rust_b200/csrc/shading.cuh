@@ -41,10 +41,12 @@ struct Surf {
 
 // Triangle::intersect tail (shapes/triangle.rs:236-392) for the accepted hit.
 // shape_some mirrors the `s: Option<Arc<Shapes>>` argument (None from Shape::pdf_wi).
+// slot: the primitive's BVH slot when known (uvs pre-gathered, scene.cuh); nrm3: its three normals pre-gathered ({n.xyz, -} x 3:
+// DevScene::slot_n or ::light_tris) or nullptr to gather them through the index buffer.
 PB_D Surf triangle_surface(const DevScene& s, f3 p0, f3 p1, f3 p2, uint32_t flags, uint32_t shape_index, f3 ray_d, float b0, float b1, float b2,
-                           bool shape_some) {
+                           bool shape_some, uint32_t slot = PB_NO_SLOT, const float4* nrm3 = nullptr) {
     float2 uv0, uv1, uv2;
-    fetch_uv(s, flags, shape_index, &uv0, &uv1, &uv2);
+    fetch_uv(s, flags, shape_index, &uv0, &uv1, &uv2, slot);
     float2 duv02 = make_float2(uv0.x - uv2.x, uv0.y - uv2.y), duv12 = make_float2(uv1.x - uv2.x, uv1.y - uv2.y);
     f3 dp02 = p0 - p2, dp12 = p1 - p2;
     float determinant = duv02.x * duv12.y - duv02.y * duv12.x;
@@ -74,10 +76,17 @@ PB_D Surf triangle_surface(const DevScene& s, f3 p0, f3 p1, f3 p2, uint32_t flag
     si.wo = -ray_d;  // triangle.rs:296: not normalised
     bool has_n = (flags & PBRT_B200_PRIM_HAS_N) && s.vertex_n, has_s = (flags & PBRT_B200_PRIM_HAS_S) && s.vertex_s;
     if (has_n || has_s) {
-        const uint32_t* idx = s.tri_indices + 3ull * shape_index;
-        uint32_t i0 = idx[0], i1 = idx[1], i2 = idx[2];
+        uint32_t i0 = 0, i1 = 0, i2 = 0;
+        if (has_s || (has_n && !nrm3)) {
+            const uint32_t* idx = s.tri_indices + 3ull * shape_index;
+            i0 = idx[0]; i1 = idx[1]; i2 = idx[2];
+        }
         f3 ns;
-        if (has_n) {
+        if (has_n && nrm3) {
+            const float4 n0 = __ldg(nrm3), n1 = __ldg(nrm3 + 1), n2 = __ldg(nrm3 + 2);
+            ns = f3(n0.x, n0.y, n0.z) * b0 + f3(n1.x, n1.y, n1.z) * b1 + f3(n2.x, n2.y, n2.z) * b2;
+            ns = (len2(ns) > 0.0f) ? normalize(ns) : si.n;
+        } else if (has_n) {
             const float* N = s.vertex_n;
             ns = f3(N[3 * i0], N[3 * i0 + 1], N[3 * i0 + 2]) * b0 + f3(N[3 * i1], N[3 * i1 + 1], N[3 * i1 + 2]) * b1 +
                  f3(N[3 * i2], N[3 * i2 + 1], N[3 * i2 + 2]) * b2;
@@ -143,7 +152,8 @@ PB_D Surf surface_at(const DevScene& s, uint32_t slot, f3 ray_o, f3 ray_d, float
     uint32_t fl = __float_as_uint(v1.w);
     *flags_out = fl;
     if (fl & PB_TRI_SPHERE) return sphere_surface(s.spheres + __float_as_uint(v2.w), ray_o, ray_d, t);
-    return triangle_surface(s, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), fl, __float_as_uint(v2.w), ray_d, b0, b1, b2, true);
+    return triangle_surface(s, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), fl, __float_as_uint(v2.w), ray_d, b0, b1, b2, true, slot,
+                            s.slot_n ? s.slot_n + 3ull * slot : nullptr);
 }
 
 // Hit inside an instanced object: TransformedPrimitive::intersect (primitive.rs:58-80) -- the object's interaction is

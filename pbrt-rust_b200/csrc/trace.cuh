@@ -25,6 +25,15 @@
 #ifndef PB_PREFETCH_FAR
 #define PB_PREFETCH_FAR 0
 #endif
+#ifndef PB_COOP_TRAVERSAL
+#define PB_COOP_TRAVERSAL 0 /* 1: persistent ray queues walk the quad nodes warp-cooperatively, loop decisions are full-mask votes (trav_run_quad_coop).
+                               Measured on B200 (gpurun_out/r2d_ab.log): camera batch 4590 -> 4372 Mrays/s, S3 step 42.1 -> 43.2 ms, hits bit-identical:
+                               forcing the warp to converge removes the overlap of the leaf fetches of some lanes with the node fetches of others */
+#endif
+#ifndef PB_POSTPONE_LEAF
+#define PB_POSTPONE_LEAF 0  /* cooperative walk only: a lane that reaches a leaf parks it and keeps descending while the warp is still searching.
+                               Measured: camera batch 4202 Mrays/s, S3 step 47.8 ms (speculative descents under the stale t_max + 16 more registers) */
+#endif
 #include "scene.cuh"
 #include "vecmath.cuh"
 
@@ -99,8 +108,15 @@ static __device__ __noinline__ bool triangle_bogus(f3 p0, f3 p1, f3 p2, float2 u
     return false;
 }
 
-PB_D void fetch_uv(const DevScene& s, uint32_t flags, uint32_t shape_index, float2* uv0, float2* uv1, float2* uv2) {
+#define PB_NO_SLOT 0xffffffffu
+// slot != PB_NO_SLOT: the primitive's BVH slot (uvs pre-gathered in slot order, scene.cuh); otherwise through the index buffer
+PB_D void fetch_uv(const DevScene& s, uint32_t flags, uint32_t shape_index, float2* uv0, float2* uv1, float2* uv2, uint32_t slot = PB_NO_SLOT) {
     if ((flags & PBRT_B200_PRIM_HAS_UV) && s.vertex_uv) {
+        if (slot != PB_NO_SLOT && s.slot_uv) {
+            const float2* u = s.slot_uv + 3ull * slot;
+            *uv0 = __ldg(u); *uv1 = __ldg(u + 1); *uv2 = __ldg(u + 2);
+            return;
+        }
         const uint32_t* idx = s.tri_indices + 3ull * shape_index;
         const float2* uv = reinterpret_cast<const float2*>(s.vertex_uv);
         *uv0 = uv[idx[0]]; *uv1 = uv[idx[1]]; *uv2 = uv[idx[2]];
@@ -250,6 +266,8 @@ struct TravRay {
     f3 o, d, inv;
     float t_max, Sx, Sy, Sz;
     uint32_t cur;    // node / leaf reference being visited, or PB_DONE
+    uint32_t pend;   // quad walk with PB_POSTPONE_LEAF: the leaf reached but not yet tested, or PB_DONE
+    float cur_tmin;  // tmin of `cur`'s box as computed when it was stacked / chosen (re-validates a leaf reached under a stale t_max)
     int sp;
     int kx, ky, kz;
     bool ngx, ngy, ngz, found;
@@ -266,6 +284,8 @@ struct TravRay {
     float2 nox, noy, noz, ivx, ivy, ivz;  // {-o, -o} and {1/d, 1/d} per axis for slab_fast2
 #endif
 };
+
+PB_D bool trav_done(const TravRay& r) { return r.cur == PB_DONE && r.pend == PB_DONE; }  // nothing left to visit, no parked leaf
 
 // root_ref / root_box: the accelerator to walk (the scene's aggregate or an instanced object's BVH); root_box == nullptr
 // for a one-primitive object, which the reference intersects directly (no accelerator, no bounds test)
@@ -302,6 +322,7 @@ PB_D void trav_init_at(TravRay& r, f3 o, f3 d, float t_max, uint32_t root_ref, c
     r.t_max = t_max;
     r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.b0 = r.hit.b1 = r.hit.b2 = 0.0f; r.hit.inst = PBRT_B200_NO_HIT;
     r.found = false; r.sp = 0;
+    r.pend = PB_DONE; r.cur_tmin = -PB_INF;
     r.cur_inst = PBRT_B200_NO_HIT; r.inst_found = false;
     trav_set_ray(r, o, d);
     r.cur = trav_enter_root(r, root_ref, rb);
@@ -331,7 +352,7 @@ PB_D void xf_ray(const float* M, f3 o, f3 d, float t_max, f3* o_out, f3* d_out, 
         while ((r).sp > 0) {                                            \
             --(r).sp;                                                   \
             uint2 e__ = (stack)[(r).sp];                                \
-            if (__uint_as_float(e__.y) < (r).t_max) { (r).cur = e__.x; break; } \
+            if (__uint_as_float(e__.y) < (r).t_max) { (r).cur = e__.x; (r).cur_tmin = __uint_as_float(e__.y); break; } \
         }                                                               \
     } while (0)
 
@@ -465,7 +486,7 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
                     h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
                     if (!ANY && h) {
                         float2 uv0, uv1, uv2;
-                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2);
+                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2, slot);
                         if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) h = false;
                     }
                 }
@@ -526,9 +547,44 @@ PB_D void quad_step(const DevScene& s, TravRay& r, uint2* stack) {
     if (t2 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r2; ntm = t2; }
     if (t1 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r1; ntm = t1; }
     if (t0 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r0; ntm = t0; }
-    if (nref != PB_DONE) r.cur = nref;
+    if (nref != PB_DONE) { r.cur = nref; r.cur_tmin = ntm; }
     else PB_TRAV_POP(r, stack);
 }
+// Every primitive of leaf `first_slot`, in order (bvh.rs:730-736).  Returns true when an any-hit ray is finished.
+template <bool ANY>
+PB_D bool quad_leaf_run(const DevScene& s, TravRay& r, uint32_t first_slot) {
+    uint32_t slot = first_slot;
+    uint32_t fl;
+    do {
+        const float4* tp = s.tris + 3ull * slot;
+        float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+        fl = __float_as_uint(v1.w);
+        float t, b0, b1, b2;
+        bool h;
+        if (fl & PB_TRI_SPHERE) {
+            h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
+            b0 = b1 = b2 = 0.0f;
+        } else {
+            f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
+            h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
+            if (!ANY && h) {
+                float2 uv0, uv1, uv2;
+                fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2, slot);
+                if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) h = false;
+            }
+        }
+        if (h) {
+            r.found = true;
+            r.hit.slot = slot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2;
+            if (ANY) return true;
+            r.t_max = t;  // primitive.rs:137
+        }
+        ++slot;
+    } while (!(fl & PB_TRI_LAST));
+    return false;
+}
+
+// Per-lane form (any subset of a warp may call it: the (0,2) megakernel, the one-ray `traverse`): while-while.
 template <bool ANY>
 PB_D void trav_run_quad(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
     while (r.cur != PB_DONE) {
@@ -538,38 +594,66 @@ PB_D void trav_run_quad(const DevScene& s, TravRay& r, uint2* stack, int yield_b
         }
         if (r.cur == PB_DONE) break;
         if (r.cur & PB_LEAF_BIT) {
-            uint32_t slot = r.cur & ~PB_LEAF_BIT;
-            uint32_t fl;
-            do {
-                const float4* tp = s.tris + 3ull * slot;
-                float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-                fl = __float_as_uint(v1.w);
-                float t, b0, b1, b2;
-                bool h;
-                if (fl & PB_TRI_SPHERE) {
-                    h = sphere_test(s.spheres + __float_as_uint(v2.w), r.o, r.d, r.t_max, &t);
-                    b0 = b1 = b2 = 0.0f;
-                } else {
-                    f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
-                    h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
-                    if (!ANY && h) {
-                        float2 uv0, uv1, uv2;
-                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2);
-                        if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) h = false;
-                    }
-                }
-                if (h) {
-                    r.found = true;
-                    r.hit.slot = slot; r.hit.t = t; r.hit.b0 = b0; r.hit.b1 = b1; r.hit.b2 = b2;
-                    if (ANY) { r.cur = PB_DONE; r.sp = 0; break; }
-                    r.t_max = t;  // primitive.rs:137
-                }
-                ++slot;
-            } while (!(fl & PB_TRI_LAST));
-            if (ANY && r.found) break;
+            if (quad_leaf_run<ANY>(s, r, r.cur & ~PB_LEAF_BIT)) { r.cur = PB_DONE; r.sp = 0; break; }
             PB_TRAV_POP(r, stack);
         }
         if (yield_below > 0 && __popc(__activemask()) < yield_below) break;
+    }
+}
+
+// WARP-COOPERATIVE form for the persistent ray queues: ALL 32 lanes of the warp call it together (lanes without a ray ride
+// along, predicated off) and every loop decision is a full-mask vote, so the two hot bodies really run converged.  ncu on the
+// per-lane form (whose loop exits the compiler does not reconverge: lanes that reach a leaf run ahead into the triangle
+// test while the others keep descending) measured 5 of 32 lanes active in the triangle test and 18 in the node step
+// (profiles/r02_trace_lanes.md).
+//
+// PB_POSTPONE_LEAF: a lane that reaches a leaf parks it in `pend` and goes on with the traversal (pop, descend) while
+// the rest of the warp is still searching, instead of idling; the leaf body runs when fewer than `interior_min` lanes are
+// still looking for their first leaf.  Exactness (same leaves, same order, same t_max at every test as the reference):
+// t_max changes only in the leaf body and a lane parks at most one leaf, so a parked leaf was validated against the t_max
+// the reference would have used.  What the lane does while a leaf is parked happens under a STALE (larger) t_max, which
+// can only admit more boxes: every stack entry is re-checked against the current t_max when popped (as before), and a
+// leaf reached meanwhile waits in `cur` until the parked leaf has been tested, then is re-checked with its own box tmin
+// (`cur_tmin`); tmin is monotone down the tree (see the quad-node note above), so a leaf that passes implies that every
+// box on the way to it passes.  Leaves are found in depth-first order and tested first-in first-out: ties break as in
+// the reference.
+template <bool ANY>
+PB_D void trav_run_quad_coop(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
+    const unsigned FULL = 0xffffffffu;
+    const int min_searching = interior_min > 0 ? interior_min : 1;
+    for (;;) {
+        // ---- node steps until fewer than `min_searching` lanes are still looking for a leaf
+        for (;;) {
+            if (!(r.cur & PB_LEAF_BIT)) quad_step<ANY>(s, r, stack);
+#if PB_POSTPONE_LEAF
+            if (r.pend == PB_DONE && (r.cur & PB_LEAF_BIT) && r.cur != PB_DONE) { r.pend = r.cur; PB_TRAV_POP(r, stack); }
+            const bool searching = r.pend == PB_DONE && !(r.cur & PB_LEAF_BIT);
+#else
+            const bool searching = !(r.cur & PB_LEAF_BIT);
+#endif
+            if (__popc(__ballot_sync(FULL, searching)) < min_searching) break;
+        }
+        // ---- leaf bodies, converged
+#if PB_POSTPONE_LEAF
+        if (r.pend != PB_DONE) {
+            const uint32_t leaf = r.pend & ~PB_LEAF_BIT;
+            r.pend = PB_DONE;
+            if (quad_leaf_run<ANY>(s, r, leaf)) { r.cur = PB_DONE; r.sp = 0; }
+        }
+        __syncwarp(FULL);
+        // a second leaf reached under the stale t_max: re-validate, park it, move on
+        if ((r.cur & PB_LEAF_BIT) && r.cur != PB_DONE) {
+            if (ANY || r.cur_tmin < r.t_max) r.pend = r.cur;
+            PB_TRAV_POP(r, stack);
+        }
+#else
+        if ((r.cur & PB_LEAF_BIT) && r.cur != PB_DONE) {
+            if (quad_leaf_run<ANY>(s, r, r.cur & ~PB_LEAF_BIT)) { r.cur = PB_DONE; r.sp = 0; }
+            else PB_TRAV_POP(r, stack);
+        }
+#endif
+        const int alive = __popc(__ballot_sync(FULL, !trav_done(r)));
+        if (alive == 0 || alive < yield_below) break;
     }
 }
 
@@ -644,7 +728,7 @@ PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit)
                     h = triangle_test<!ANY>(o, d, t_max, p0, p1, p2, kx, ky, kz, Sx, Sy, Sz, &t, &b0, &b1, &b2);
                     if (!ANY && h) {
                         float2 uv0, uv1, uv2;
-                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2);
+                        fetch_uv(s, fl, __float_as_uint(v2.w), &uv0, &uv1, &uv2, slot);
                         if (triangle_bogus(p0, p1, p2, uv0, uv1, uv2)) h = false;
                     }
                 }
@@ -705,7 +789,7 @@ template <bool ANY, bool INST, typename Job>
 PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_counter, TraceTune tune = TraceTune{PB_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN}) {
     uint2 stack[PB_STACK_SIZE(INST)];
     TravRay r;
-    r.cur = PB_DONE; r.sp = 0; r.found = false;
+    r.cur = PB_DONE; r.pend = PB_DONE; r.sp = 0; r.found = false;
     uint32_t ray_idx = 0xffffffffu;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
     bool exhausted = false;                // warp-uniform
@@ -713,9 +797,9 @@ PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_c
     const unsigned lt_mask = (1u << lane) - 1u;
     for (;;) {
         __syncwarp();
-        if (r.cur == PB_DONE && ray_idx != 0xffffffffu) { job.store(ray_idx, r); ray_idx = 0xffffffffu; }
+        if (trav_done(r) && ray_idx != 0xffffffffu) { job.store(ray_idx, r); ray_idx = 0xffffffffu; }
         __syncwarp();
-        unsigned need = __ballot_sync(0xffffffffu, r.cur == PB_DONE);
+        unsigned need = __ballot_sync(0xffffffffu, trav_done(r));
         while (need && !exhausted) {
             if (pool_next == pool_end) {
                 uint32_t b = 0;
@@ -732,13 +816,22 @@ PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_c
                 ray_idx = pool_next + rank;
                 f3 o, d; float t_max = 0.0f;
                 if (job.load(ray_idx, &o, &d, &t_max)) trav_init(s, r, o, d, t_max);
-                else { r.cur = PB_DONE; r.sp = 0; r.found = false; r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.inst = PBRT_B200_NO_HIT; }
+                else { r.cur = PB_DONE; r.pend = PB_DONE; r.sp = 0; r.found = false; r.hit.slot = PBRT_B200_NO_HIT; r.hit.t = t_max; r.hit.inst = PBRT_B200_NO_HIT; }
             }
             unsigned took = __ballot_sync(0xffffffffu, take);
             pool_next += __popc(took);
             need &= ~took;
         }
         if (__all_sync(0xffffffffu, ray_idx == 0xffffffffu)) break;
+#if PB_QUAD_NODES && PB_COOP_TRAVERSAL
+        if (!INST) {
+            // rays with a zero direction component take the NaN-exact binary walk (rare): run them to completion first
+            if (r.nan_possible && !trav_done(r)) trav_run_impl<ANY, true, false>(s, r, stack, 0, 0);
+            __syncwarp();
+            trav_run_quad_coop<ANY>(s, r, stack, exhausted ? 0 : tune.refill_below, tune.interior_min);
+            continue;
+        }
+#endif
         trav_run<ANY, INST>(s, r, stack, exhausted ? 0 : tune.refill_below, tune.interior_min);
     }
 }

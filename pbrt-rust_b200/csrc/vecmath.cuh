@@ -60,11 +60,16 @@ PB_D float len(f3 a) { return sqrtf(len2(a)); }
 PB_D f3 normalize(f3 a) { return vdiv(a, len(a)); }
 PB_D f3 vabs(f3 a) { return f3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
 // geometry/vector.rs:339-353: f64 products, then narrowed
+#ifdef PB_TU_SHADE
+// shade.o (tolerance-parity shading, see render.cu): plain f32
+PB_D f3 cross(f3 a, f3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+#else
 PB_D f3 cross(f3 a, f3 b) {
     double ax = a.x, ay = a.y, az = a.z, bx = b.x, by = b.y, bz = b.z;
     return f3((float)(__dsub_rn(__dmul_rn(ay, bz), __dmul_rn(az, by))), (float)(__dsub_rn(__dmul_rn(az, bx), __dmul_rn(ax, bz))),
               (float)(__dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx))));
 }
+#endif
 PB_D float maxcomp(f3 a) { return fmaxf(a.x, fmaxf(a.y, a.z)); }
 PB_D f3 face_forward(f3 n, f3 v) { return dot(n, v) < 0.0f ? -n : n; }
 // c ? a : b as ONE select instruction.  The ternary form of the axis permutations below was compiled to divergent branches
