@@ -342,7 +342,7 @@ struct RecShadowJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_rec_shadow(RenderDev R) {
     RecShadowJob job{&R};
-    trace_queue<true, INST>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
+    trace_queue<true, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
 }
 
 template <bool INST>
@@ -375,7 +375,7 @@ struct RecMisJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_rec_mis(RenderDev R) {
     RecMisJob<INST> job{&R};
-    trace_queue<false, INST>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
+    trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
 
 #endif  // PB_EXACT_TU

@@ -606,9 +606,15 @@ PB_D void generate_ray(const pbrt_b200_camera& c, float2 pfilm, float time_u, fl
 PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t slot) {
     uint32_t p = (uint32_t)(item & 255u);
     unsigned long long rest = item >> 8;
-    uint32_t j = (uint32_t)(rest % R.n_tiles_sel);  // ordinal among the tiles this call owns
-    uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
-    uint32_t sample = (uint32_t)(rest / R.n_tiles_sel) + R.sample_begin;
+    uint32_t j, sample;  // ordinal among the tiles this call owns; sample number
+    if ((rest >> 32) == 0) {  // (always, short of 2^40 items in one call): one 32-bit division instead of two emulated 64-bit ones
+        const uint32_t r32 = (uint32_t)rest, qs = r32 / R.n_tiles_sel;
+        j = r32 - qs * R.n_tiles_sel; sample = qs + R.sample_begin;
+    } else {
+        j = (uint32_t)(rest % R.n_tiles_sel); sample = (uint32_t)(rest / R.n_tiles_sel) + R.sample_begin;
+    }
+    const uint32_t jg = j / R.tile_group;
+    uint32_t t = R.tile_begin + (jg * R.tile_mod + R.tile_rem) * R.tile_group + (j - jg * R.tile_group);
     bool valid = t < R.tile_end;
     int tx = t % R.ntx, ty = t / R.ntx;
     int x = R.sampler.sb[0] + tx * 16 + (int)(p & 15u);
@@ -723,27 +729,35 @@ struct PathClosestJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_closest(RenderDev R, int parity) {
     PathClosestJob job{&R, R.q_path[parity]};
-    trace_queue<false, INST>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path);
+    trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path);
 }
 
-// sort/compact-by-material: one warp-aggregated append per material queue
+// sort/compact-by-material.  Lanes of the same bin form a group (match.any) and the groups of the CTA's eight warps are
+// added up in shared memory: one atomicAdd per bin per 256 paths (the per-warp form waited on the atomic's round trip for 83 % of
+// its stall samples, profiles/r02_ncu_classify.md), queue order = path-queue order within a CTA's span.
 __global__ void __launch_bounds__(256) k_classify(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_path;
     const uint32_t* q = R.q_path[parity];
-    const uint32_t nround = (n + 31u) & ~31u;
+    const uint32_t nround = (n + 255u) & ~255u;  // CTA-uniform trip count (barriers inside)
+    __shared__ uint32_t s_cnt[8][Q_COUNT], s_base[Q_COUNT];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         bool valid = i < n;
         uint32_t id = valid ? q[i] : 0u;
         int bin = valid ? (int)R.hit_bin[id] : -1;
-        // lanes of the same bin form a group (match.any); the lowest lane of every group reserves the group's span -- the
-        // atomics of all bins are in flight together (the per-bin queue_push loop paid up to seven dependent round trips)
         const unsigned peers = __match_any_sync(0xffffffffu, bin);
-        const unsigned lane = threadIdx.x & 31u;
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (valid && (int)lane == leader) base = atomicAdd(&R.cnt->n_mat[bin], (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid) R.q_mat[bin][base + __popc(peers & ((1u << lane) - 1u))] = id;
+        if (lane < Q_COUNT) s_cnt[warp][lane] = 0;
+        __syncwarp();
+        if (valid && (int)lane == __ffs(peers) - 1) s_cnt[warp][bin] = (uint32_t)__popc(peers);
+        __syncthreads();
+        if (threadIdx.x < Q_COUNT) {
+            uint32_t sum = 0;
+            for (int w = 0; w < 8; ++w) { const uint32_t c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = sum; sum += c; }
+            s_base[threadIdx.x] = sum ? atomicAdd(&R.cnt->n_mat[threadIdx.x], sum) : 0u;
+        }
+        __syncthreads();
+        if (valid) R.q_mat[bin][s_base[bin] + s_cnt[warp][bin] + __popc(peers & ((1u << lane) - 1u))] = id;
+        __syncthreads();
     }
 }
 #endif  // PB_EXACT_TU
@@ -1455,7 +1469,7 @@ struct ShadowJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
     ShadowJob job{&R};
-    trace_queue<true, INST>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
+    trace_queue<true, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
 }
 
 // ---------------------------------------------------------------------------
@@ -1499,7 +1513,7 @@ struct MisJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
     MisJob<INST> job{&R};
-    trace_queue<false, INST>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
+    trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
 }
 
 #endif  // PB_EXACT_TU
@@ -1542,10 +1556,13 @@ void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int gr
 // camera sample of the call, so every iteration traces a full complement of rays instead of the dwindling tail of one wave.
 __global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, unsigned long long total_items) {
     const uint32_t n = R.cnt->n_dead;
-    const uint32_t nround = (n + 31u) & ~31u;
+    // every thread of a CTA runs the same number of iterations: the appends below are aggregated per CTA (two barriers per iteration)
+    const uint32_t nround = (n + 255u) & ~255u;
     const unsigned long long cursor = R.cnt->item_cursor;  // advanced by k_iter_end
     const unsigned long long remaining = total_items > cursor ? total_items - cursor : 0ull;
     const uint32_t* q = R.q_dead[parity];
+    __shared__ uint32_t s_cnt[8][2], s_base[2];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, below = (1u << lane) - 1u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         bool valid = i < n, has_sample = false;
         rgb L(0.0f);
@@ -1557,8 +1574,8 @@ __global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, u
         }
         if (has_sample) {
             float4 Le = R.L_eta[id];
-            L = rgb(Le.x, Le.y, Le.z);
             pf = R.pfilm[id];
+            L = rgb(Le.x, Le.y, Le.z);
             // integrator.rs:350-368: NaN / negative / infinite luminance => black
             float y = lum(L);
             if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
@@ -1568,21 +1585,25 @@ __global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, u
         film_add_sample(R, pf, L, has_sample);
         bool regen = valid && (unsigned long long)i < remaining, ok = false;
         if (regen) ok = gen_camera_path(R, cursor + i, id);
-        unsigned m = __ballot_sync(0xffffffffu, ok);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&R.cnt->camera_rays, (unsigned long long)__popc(m));
-        {   // both appends behind one atomic round trip (see k_shade)
-            const bool again = regen && !ok;
-            const unsigned m1 = __ballot_sync(0xffffffffu, again);
-            const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-            uint32_t b0 = 0, b1 = 0;
-            if (lane == 0) {
-                if (m) b0 = atomicAdd(&R.cnt->n_next, (uint32_t)__popc(m));
-                if (m1) b1 = atomicAdd(&R.cnt->n_dead_next, (uint32_t)__popc(m1));
-            }
-            b0 = __shfl_sync(0xffffffffu, b0, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
-            if (ok) R.q_path[parity ^ 1][b0 + __popc(m & below)] = id;
-            if (again) R.q_dead[parity ^ 1][b1 + __popc(m1 & below)] = id;
+        // Appends, aggregated per CTA: at the start of a wave every slot of the call regenerates (33 M camera paths on S3), and one
+        // atomicAdd per WARP on the single counter n_next serialised at its L2 slice -- 56 % of the kernel's stall samples, 4.2 of the
+        // 40 ms of a 16-spp step (profiles/r02_ncu_regen.md).  One atomic per 256 paths instead.
+        const bool again = regen && !ok;
+        const unsigned m = __ballot_sync(0xffffffffu, ok), m1 = __ballot_sync(0xffffffffu, again);
+        if (lane == 0) { s_cnt[warp][0] = (uint32_t)__popc(m); s_cnt[warp][1] = (uint32_t)__popc(m1); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            uint32_t sum = 0;
+            for (int w = 0; w < 8; ++w) { const uint32_t c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = sum; sum += c; }
+            uint32_t base = 0;
+            if (sum) base = atomicAdd(threadIdx.x == 0 ? &R.cnt->n_next : &R.cnt->n_dead_next, sum);
+            if (threadIdx.x == 0 && sum) atomicAdd(&R.cnt->camera_rays, (unsigned long long)sum);
+            s_base[threadIdx.x] = base;
         }
+        __syncthreads();
+        if (ok) R.q_path[parity ^ 1][s_base[0] + s_cnt[warp][0] + __popc(m & below)] = id;
+        if (again) R.q_dead[parity ^ 1][s_base[1] + s_cnt[warp][1] + __popc(m1 & below)] = id;
+        __syncthreads();  // s_cnt / s_base are rewritten by the next iteration
     }
 }
 
@@ -1707,7 +1728,8 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
     }
     unsigned long long n_camera = 0, n_closest = 0, n_shadow = 0, n_zero = 0, n_iter = 0;
     bool ok = zt_next_path(R, j, true);
-    uint2 stack[PB_STACK_SIZE(INST)];
+    uint2 stack_mem[PB_STACK_SIZE(INST)];
+    LocalStack stack{stack_mem};
     while (ok) {
         n_camera += 1;
         bool alive = true;

@@ -343,6 +343,34 @@ PB_D void xf_ray(const float* M, f3 o, f3 d, float t_max, f3* o_out, f3* d_out, 
     *o_out = o2; *d_out = d2; *t_max_out = t_max;
 }
 
+// Traversal stack.  LocalStack: a per-thread array (local memory, served by L1 when it hits).  HybridStack: the first
+// PB_SH_STACK levels live in SHARED memory ([level][thread], conflict-free), deeper levels overflow to the local array.
+// ncu on k_trace_closest (profiles/r02_ncu_trace.md): local loads -- the pops -- hit L1 only 63 % of the time, as often as the node
+// fetches they compete with for the cache, so a third of the pops paid an L2 round trip; a shared-memory level always answers in
+// ~29 cycles and takes the stack lines out of the L1 working set.
+// Measured on B200 (gpurun_out/r2f_ab.log; hits bit-identical in every variant): inside a frame 16 shared levels give S3 41.1 -> 40.5 ms
+// per 16-spp step (closest 16.4 -> 16.1, shadow 8.1 -> 7.8 ms); on isolated 2 M-ray batches the same change LOSES 4-5 % (camera batch
+// 4603 -> 4390 Mrays/s: the carve-out shrinks the L1 that a small batch's nodes otherwise fit in).  So the wavefront kernels take the
+// hybrid stack and the batch API keeps the local one (trace_queue's SH parameter).
+#ifndef PB_SH_STACK
+#define PB_SH_STACK 16
+#endif
+#ifndef PB_TRACE_BLOCK
+#define PB_TRACE_BLOCK 128 /* threads per CTA of every persistent ray-queue kernel (util.cuh) */
+#endif
+struct LocalStack {
+    uint2* loc;
+    PB_D void put(int i, uint2 e) const { loc[i] = e; }
+    PB_D uint2 get(int i) const { return loc[i]; }
+};
+template <int SH, int BLOCK>
+struct HybridStack {
+    uint2* sh;   // &shared[0][thread]; level l at sh[l * BLOCK]
+    uint2* loc;  // levels >= SH
+    PB_D void put(int i, uint2 e) const { if (i < SH) sh[i * BLOCK] = e; else loc[i - SH] = e; }
+    PB_D uint2 get(int i) const { return i < SH ? sh[i * BLOCK] : loc[i - SH]; }
+};
+
 #define PB_INST_EXIT 0xfffffffeu /* stack sentinel (leaf bit set): the instanced object's sub-tree is exhausted */
 
 // pop: the reference tests the popped node's box against the *current* t_max
@@ -351,19 +379,19 @@ PB_D void xf_ray(const float* M, f3 o, f3 d, float t_max, f3* o_out, f3* d_out, 
         (r).cur = PB_DONE;                                              \
         while ((r).sp > 0) {                                            \
             --(r).sp;                                                   \
-            uint2 e__ = (stack)[(r).sp];                                \
+            uint2 e__ = (stack).get((r).sp);                                \
             if (__uint_as_float(e__.y) < (r).t_max) { (r).cur = e__.x; (r).cur_tmin = __uint_as_float(e__.y); break; } \
         }                                                               \
     } while (0)
 
-template <bool ANY> PB_D void quad_step(const DevScene& s, TravRay& r, uint2* stack);  // defined below (quad nodes)
+template <bool ANY, typename STK> PB_D void quad_step(const DevScene& s, TravRay& r, STK stack);  // defined below (quad nodes)
 
 // Runs the ray until it finishes, or (when `yield_below` > 0) until fewer than `yield_below`
 // lanes of the warp are still traversing, so that the caller can refill idle lanes.
 // TOP: walking the scene's aggregate (leaf slots may be TransformedPrimitives); false inside an instanced object, where
 // ObjectInstance cannot appear (api.rs:1674-1677): one level of instancing, one sentinel on the stack at most.
-template <bool ANY, bool EXACT_NAN, bool TOP>
-PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
+template <bool ANY, bool EXACT_NAN, bool TOP, typename STK>
+PB_D void trav_run_impl(const DevScene& s, TravRay& r, STK stack, int yield_below, int interior_min) {
     while (r.cur != PB_DONE) {
         // ---- interior nodes
         while (!(r.cur & PB_LEAF_BIT)) {
@@ -422,7 +450,7 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
 #endif
             if (nhit) {
                 if (ANY ? fhit : fok) {
-                    stack[r.sp] = make_uint2(fref, __float_as_uint(ftmin)); ++r.sp;
+                    stack.put(r.sp, make_uint2(fref, __float_as_uint(ftmin))); ++r.sp;
 #if PB_PREFETCH_FAR
                     {
                         const void* pf = (fref & PB_LEAF_BIT) ? (const void*)(s.tris + 3ull * (fref & ~PB_LEAF_BIT)) : (const void*)(s.nodes + 4ull * fref);
@@ -466,8 +494,8 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
                         // nudge, t_max -= dt).  Left on the stack, in pop order: the object's nodes, the sentinel that
                         // restores the world ray, then the rest of this leaf.
                         const DevInstance* in = s.instances + __float_as_uint(v2.w);
-                        if (!(fl & PB_TRI_LAST)) { stack[r.sp] = make_uint2(PB_LEAF_BIT | (slot + 1), 0xff800000u); ++r.sp; }  // tmin = -inf: always resumed
-                        stack[r.sp] = make_uint2(PB_INST_EXIT, 0xff800000u); ++r.sp;
+                        if (!(fl & PB_TRI_LAST)) { stack.put(r.sp, make_uint2(PB_LEAF_BIT | (slot + 1), 0xff800000u)); ++r.sp; }  // tmin = -inf: always resumed
+                        stack.put(r.sp, make_uint2(PB_INST_EXIT, 0xff800000u)); ++r.sp;
                         r.wo = r.o; r.wd = r.d; r.world_t_max = r.t_max;
                         r.cur_inst = __float_as_uint(v2.w); r.inst_found = false;
                         f3 o2, d2;
@@ -520,8 +548,8 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, uint2* stack, int yield_b
 // slot inside each group by the child's axis), later ones are stacked behind earlier ones, and a stacked entry is
 // re-checked against the current t_max when popped, as in the binary walk.  Only for rays without zero direction
 // components (slab_fast's precondition; the others take the binary, NaN-exact walk).
-template <bool ANY>
-PB_D void quad_step(const DevScene& s, TravRay& r, uint2* stack) {
+template <bool ANY, typename STK>
+PB_D void quad_step(const DevScene& s, TravRay& r, STK stack) {
     const float4* np = s.quads + 8ull * r.cur;
     const float4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2), b0 = __ldg(np + 3), b1 = __ldg(np + 4), b2 = __ldg(np + 5), q6 = __ldg(np + 6), q7 = __ldg(np + 7);
     SlabPair pa = slab_fast2(r.ngx ? make_float2(a1.z, a1.w) : make_float2(a0.x, a0.y), r.ngy ? make_float2(a2.x, a2.y) : make_float2(a0.z, a0.w),
@@ -543,10 +571,24 @@ PB_D void quad_step(const DevScene& s, TravRay& r, uint2* stack) {
     const uint32_t r0 = g ? rBn : rAn, r1 = g ? rBf : rAf, r2 = g ? rAn : rBn, r3 = g ? rAf : rBf;
     // the first slot that passes is visited now; the others wait on the stack, nearest on top
     uint32_t nref = PB_DONE; float ntm = 0.0f;
+#if PB_PREFETCH_FAR
+    uint32_t top = PB_DONE;  // the entry left on top of the stack by this step: the next thing visited after the subtree entered now
+#define PB_QPUSH() do { stack.put(r.sp, make_uint2(nref, __float_as_uint(ntm))); ++r.sp; top = nref; } while (0)
+#else
+#define PB_QPUSH() do { stack.put(r.sp, make_uint2(nref, __float_as_uint(ntm))); ++r.sp; } while (0)
+#endif
     if (t3 < r.t_max) { nref = r3; ntm = t3; }
-    if (t2 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r2; ntm = t2; }
-    if (t1 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r1; ntm = t1; }
-    if (t0 < r.t_max) { if (nref != PB_DONE) { stack[r.sp] = make_uint2(nref, __float_as_uint(ntm)); ++r.sp; } nref = r0; ntm = t0; }
+    if (t2 < r.t_max) { if (nref != PB_DONE) PB_QPUSH(); nref = r2; ntm = t2; }
+    if (t1 < r.t_max) { if (nref != PB_DONE) PB_QPUSH(); nref = r1; ntm = t1; }
+    if (t0 < r.t_max) { if (nref != PB_DONE) PB_QPUSH(); nref = r0; ntm = t0; }
+#undef PB_QPUSH
+#if PB_PREFETCH_FAR
+    // A/B: request it into L1 now (ncu: 38 % of the node / leaf fetches miss L1)
+    if (top != PB_DONE) {
+        const void* pf = (top & PB_LEAF_BIT) ? (const void*)(s.tris + 3ull * (top & ~PB_LEAF_BIT)) : (const void*)(s.quads + 8ull * top);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+    }
+#endif
     if (nref != PB_DONE) { r.cur = nref; r.cur_tmin = ntm; }
     else PB_TRAV_POP(r, stack);
 }
@@ -585,8 +627,8 @@ PB_D bool quad_leaf_run(const DevScene& s, TravRay& r, uint32_t first_slot) {
 }
 
 // Per-lane form (any subset of a warp may call it: the (0,2) megakernel, the one-ray `traverse`): while-while.
-template <bool ANY>
-PB_D void trav_run_quad(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
+template <bool ANY, typename STK>
+PB_D void trav_run_quad(const DevScene& s, TravRay& r, STK stack, int yield_below, int interior_min) {
     while (r.cur != PB_DONE) {
         while (!(r.cur & PB_LEAF_BIT)) {
             quad_step<ANY>(s, r, stack);
@@ -617,8 +659,8 @@ PB_D void trav_run_quad(const DevScene& s, TravRay& r, uint2* stack, int yield_b
 // (`cur_tmin`); tmin is monotone down the tree (see the quad-node note above), so a leaf that passes implies that every
 // box on the way to it passes.  Leaves are found in depth-first order and tested first-in first-out: ties break as in
 // the reference.
-template <bool ANY>
-PB_D void trav_run_quad_coop(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min) {
+template <bool ANY, typename STK>
+PB_D void trav_run_quad_coop(const DevScene& s, TravRay& r, STK stack, int yield_below, int interior_min) {
     const unsigned FULL = 0xffffffffu;
     const int min_searching = interior_min > 0 ? interior_min : 1;
     for (;;) {
@@ -659,8 +701,8 @@ PB_D void trav_run_quad_coop(const DevScene& s, TravRay& r, uint2* stack, int yi
 
 // INST: the scene contains TransformedPrimitives.  Scenes without instancing run kernels compiled with INST = false, which
 // contain no trace of the instance path (measured on S3: the mere presence of the out-of-line call in the leaf loop costs 20%).
-template <bool ANY, bool INST>
-PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below, int interior_min = 0) {
+template <bool ANY, bool INST, typename STK>
+PB_D void trav_run(const DevScene& s, TravRay& r, STK stack, int yield_below, int interior_min = 0) {
     // with instances the ray changes along the way, so the NaN-free slab shortcut cannot be chosen once per ray: INST
     // kernels always evaluate the literal reference chain
     if (INST || r.nan_possible) trav_run_impl<ANY, true, INST>(s, r, stack, yield_below, interior_min);
@@ -674,7 +716,8 @@ PB_D void trav_run(const DevScene& s, TravRay& r, uint2* stack, int yield_below,
 // Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray, run to completion.
 template <bool ANY, bool INST = false>
 PB_D bool traverse(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit) {
-    uint2 stack[PB_STACK_SIZE(INST)];
+    uint2 stack_mem[PB_STACK_SIZE(INST)];
+    LocalStack stack{stack_mem};
     TravRay r;
     trav_init(s, r, o, d, t_max);
     trav_run<ANY, INST>(s, r, stack, 0);
@@ -785,9 +828,11 @@ PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit)
 #define PB_INTERIOR_MIN 16
 #endif
 struct TraceTune { int refill_below; int chunk; int interior_min; };
-template <bool ANY, bool INST, typename Job>
+template <bool ANY, bool INST, int SH = 0, typename Job>
 PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_counter, TraceTune tune = TraceTune{PB_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN}) {
-    uint2 stack[PB_STACK_SIZE(INST)];
+    uint2 stack_mem[PB_STACK_SIZE(INST)];
+    __shared__ uint2 stack_shared[SH > 0 ? SH : 1][PB_TRACE_BLOCK];
+    HybridStack<SH, PB_TRACE_BLOCK> stack{&stack_shared[0][threadIdx.x], stack_mem};  // SH == 0: every level in the local array
     TravRay r;
     r.cur = PB_DONE; r.pend = PB_DONE; r.sp = 0; r.found = false;
     uint32_t ray_idx = 0xffffffffu;
