@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--tiles", default="static", choices=["static", "dynamic"],
+                    help="N > 1: static interleaved tile groups, or dynamic stealing of super-tile ranges from the shared-memory work counter")
     ap.add_argument("--ref-spp", type=int, default=8, help="--impl reference: samples per pixel per step (bounded sample of the GPU arm's step)")
     return ap.parse_args()
 
@@ -64,10 +66,12 @@ def make_setup(pkg, name):
     return S.spheres_scene(), dict(), "S1: two spheres 400x400, maxdepth 5"
 
 
-def bench_config(desc, spp, world, pif):
+def bench_config(desc, spp, world, pif, tiles="static"):
     """`config` of the JSON line.  Both arms print the SAME dict (the reference arm runs on the GPU arm's config; what its bounded
     per-step sample is goes into its `cpu_baseline.sample`)."""
-    return {"workload": desc, "step": f"{spp} spp per GPU over the full frame ({spp * world} spp per step in total), tiles interleaved across ranks in groups of 8",
+    how = ("tiles interleaved across ranks in groups of 8" if tiles == "static" or world == 1 else
+           "ranks claim ranges of 8x8-tile super-tiles from a shared-memory work counter (guided self-scheduling)")
+    return {"workload": desc, "step": f"{spp} spp per GPU over the full frame ({spp * world} spp per step in total), {how}",
             "l2": "no explicit flush: per-step working set (2^26 path slots x ~300 B state + 110 MB scene + 33 MB film) exceeds the 126 MB L2",
             "paths_in_flight": pif or 1 << 26, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"}
 
@@ -190,7 +194,7 @@ def main():
         v = samples / dt
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": bench_config(desc, args.spp, args.gpus, args.paths_in_flight),
+                          "config": bench_config(desc, args.spp, args.gpus, args.paths_in_flight, args.tiles),
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nth, "kind": "port",
                                            "sample": f"{args.steps} steps, each {ref_spp} of the step's {args.spp} spp over the full {film.width}x{film.height} frame in one "
                                                      f"call = {samples} camera samples in {dt:.1f} s on {nth} threads (CPU oracle: the Rust reference cannot be built here)"},
@@ -215,14 +219,45 @@ def main():
     scene = pkg.Scene(setup.flat, device=local)
     film_t = torch.zeros((npix, 4), dtype=torch.float32, device="cuda")
     interleave = (8, world, rank) if world > 1 else None
+    D = importlib.import_module("pbrt-rust_b200.distributed")
+    dynamic = world > 1 and args.tiles == "dynamic"
+    queue = D.open_shared_queue(pkg.host, integ, dist=dist, min_chunk_tiles=64) if dynamic else None
+    frames = [0]
+
+    class Acc:  # the stats of a step = the sum over the render calls (claims) the rank made for it
+        FIELDS = ("camera_rays", "intersection_tests", "shadow_tests", "kernel_launches", "trace_closest_ms", "trace_any_ms", "device_ms", "shade_ms")
+
+        def __init__(self):
+            for f in self.FIELDS:
+                setattr(self, f, 0)
+            self.claims = 0
+
+        def add(self, st):
+            for f in self.FIELDS:
+                setattr(self, f, getattr(self, f) + getattr(st, f))
+            self.claims += 1
+
+    def render_step(sc, k):
+        """This rank's share of step k into film_t (zeroed), then the film reduce; static or dynamic tile assignment."""
+        acc = Acc()
+        sr = (k * spp_step, (k + 1) * spp_step)
+        film_t.zero_()
+        if dynamic:
+            def render_tiles(tile_range, il, sample_range, tile_order):
+                _, st = sc.render(integ, sample_range=sample_range, device_ptr=film_t.data_ptr(), tile_range=tile_range, tile_interleave=il, tile_order=tile_order,
+                                  paths_in_flight=args.paths_in_flight)
+                acc.add(st)
+            D.render_distributed(render_tiles, film_t, integ, dist=dist, dynamic=True, queue=queue, sample_range=sr, frame=frames[0])
+            frames[0] += 1
+        else:
+            _, st = sc.render(integ, sample_range=sr, device_ptr=film_t.data_ptr(), tile_interleave=interleave, paths_in_flight=args.paths_in_flight)
+            acc.add(st)
+            if world > 1:
+                dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+        return acc
 
     def step(k):
-        film_t.zero_()
-        _, st = scene.render(integ, sample_range=(k * spp_step, (k + 1) * spp_step), device_ptr=film_t.data_ptr(), tile_interleave=interleave,
-                             paths_in_flight=args.paths_in_flight)
-        if world > 1:
-            dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
-        return st
+        return render_step(scene, k)
 
     def sync():
         if world > 1:
@@ -236,13 +271,13 @@ def main():
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot = dict(camera=0, closest=0, shadow=0, launches=0, trace_closest_ms=0.0, trace_any_ms=0.0, device_ms=0.0, shade_ms=0.0)
+    tot = dict(camera=0, closest=0, shadow=0, launches=0, trace_closest_ms=0.0, trace_any_ms=0.0, device_ms=0.0, shade_ms=0.0, claims=0)
     e0.record()
     for k in range(args.steps):
         st = step(args.warmup + k)
         tot["camera"] += st.camera_rays; tot["closest"] += st.intersection_tests; tot["shadow"] += st.shadow_tests
         tot["launches"] += st.kernel_launches; tot["trace_closest_ms"] += st.trace_closest_ms; tot["trace_any_ms"] += st.trace_any_ms
-        tot["device_ms"] += st.device_ms; tot["shade_ms"] += st.shade_ms
+        tot["device_ms"] += st.device_ms; tot["shade_ms"] += st.shade_ms; tot["claims"] += st.claims
     e1.record()
     sync()
     ms = e0.elapsed_time(e1)
@@ -255,6 +290,15 @@ def main():
     else:
         camera, closest, shadow, launches = tot["camera"], tot["closest"], tot["shadow"], tot["launches"]
     value = camera / (ms * 1e-3)
+    per_rank = None
+    if world > 1:  # what each rank did inside the timed region: wall (CUDA events), busy (sum of its render calls), closest-hit kernel, claims
+        mine = torch.tensor([e0.elapsed_time(e1), tot["device_ms"], tot["trace_closest_ms"], tot["camera"], tot["claims"]], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rows = [r.tolist() for r in allr]
+        busy = [r[1] for r in rows]
+        per_rank = {"wall_ms": [r[0] for r in rows], "render_ms": busy, "trace_closest_ms": [r[2] for r in rows], "camera_samples": [int(r[3]) for r in rows],
+                    "render_calls": [int(r[4]) for r in rows], "imbalance": (max(busy) - min(busy)) / max(max(busy), 1e-9)}
 
     # ---- e2e: host buffers through the C ABI, scene upload + render + film download per step
     e2e = None
@@ -271,10 +315,7 @@ def main():
                 _, st = sc2.render(integ, rgbw=host_film, sample_range=(k * spp_step, (k + 1) * spp_step), paths_in_flight=args.paths_in_flight,
                                    flags=pkg.host.RENDER_OVERWRITE)  # render + film D2H into the caller's host buffer
             else:  # every rank renders its tiles; films summed to rank 0 over NCCL; rank 0 reads the image back
-                film_t.zero_()
-                _, st = sc2.render(integ, sample_range=(k * spp_step, (k + 1) * spp_step), device_ptr=film_t.data_ptr(), tile_interleave=interleave,
-                                   paths_in_flight=args.paths_in_flight)
-                dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+                st = render_step(sc2, k)
                 if rank == 0:
                     pinned_film.copy_(film_t, non_blocking=False)
             sc2.close()
@@ -369,9 +410,9 @@ def main():
                                      "lanes_per_inst": sc.get("lanes_per_inst"), "occupancy_pct": sc.get("occupancy_pct")}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": bench_config(desc, args.spp, world, args.paths_in_flight),
+               "config": bench_config(desc, args.spp, world, args.paths_in_flight, args.tiles),
                "mrays_per_s": (closest + shadow) / (ms * 1e-3) / 1e6, "rays_per_sample": (closest + shadow) / max(camera, 1),
-               "ray_batches": ray_batches, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+               "ray_batches": ray_batches, "per_rank": per_rank, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "kernel_ms": {"trace_closest": tot["trace_closest_ms"], "trace_shadow": tot["trace_any_ms"], "shade": tot["shade_ms"], "wavefront_total": tot["device_ms"]}}
         print(json.dumps(out), file=out_stream, flush=True)
     scene.close()

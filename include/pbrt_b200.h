@@ -305,7 +305,13 @@ typedef struct pbrt_b200_render_desc {
      * partitioning: tile t is rendered iff ((t - tile_begin) / tile_group) %
      * tile_mod == tile_rem.  0,0,0 => every tile (group 1, mod 1, rem 0).       */
     uint32_t tile_group, tile_mod, tile_rem;
-    uint32_t reserved;
+    /* Numbering of the tiles that [tile_begin, tile_end) refers to.  0: the reference's, row-major over the whole image
+     * (integrator.rs:274-279).  S > 0: super-tile major -- the image is cut into S x S-tile blocks (S = 8: 128 x 128 pixels),
+     * blocks row-major, tiles row-major inside a block, positions past the image edge are empty; the numbering then runs
+     * over ceil(ntx/S) * ceil(nty/S) * S * S positions (pbrt_b200_tile_positions).  Consecutive ranges are compact image
+     * regions, which is what a multi-GPU scheduler wants to hand out (coherent rays); every tile keeps its own sampler
+     * seed and pixels, so the image does not depend on the numbering.                                                  */
+    uint32_t tile_order;
 } pbrt_b200_render_desc;
 
 enum {
@@ -316,6 +322,28 @@ enum {
                                                 * the whole grid would fit (the mode used automatically for voxels x
                                                 * lights > 2^25; results are identical, lightdistrib.rs:231-340)    */
 };
+
+/* Number of positions of the tile numbering `tile_order` for a sample-bounds window of w x h pixels (= the number
+ * of tiles when tile_order is 0).                                                                                    */
+uint32_t pbrt_b200_tile_positions(int w, int h, uint32_t tile_order);
+
+/* ---- work counter shared between the processes that drive the GPUs of one box ------------------------------------
+ * The reference hands tiles to its worker threads through one shared queue (integrator.rs:291-296, rayon par_iter).
+ * With one process per GPU the queue head is a 64-bit counter in POSIX shared memory: every rank claims the next
+ * range of tile positions with one atomic fetch-add on host memory (no network round trip), renders it with
+ * pbrt_b200_render(tile_begin, tile_end, tile_order), and the films are summed once at the end.                   */
+typedef struct pbrt_b200_work_counter pbrt_b200_work_counter;
+/* create != 0: create (or reset) the named counter at 0; otherwise attach to an existing one.                       */
+int pbrt_b200_work_counter_open(const char* name, int create, pbrt_b200_work_counter** out);
+/* Atomically adds n and returns the PREVIOUS value (the first unit of the caller's claim).                            */
+uint64_t pbrt_b200_work_counter_fetch_add(pbrt_b200_work_counter* c, uint64_t n);
+/* Raises the counter to at least v (atomic max); returns the previous value.  A rank entering frame f calls it with the
+ * frame's base position: whoever arrives first moves the queue head there, nobody waits for anybody.                 */
+uint64_t pbrt_b200_work_counter_fetch_max(pbrt_b200_work_counter* c, uint64_t v);
+uint64_t pbrt_b200_work_counter_load(const pbrt_b200_work_counter* c);
+void pbrt_b200_work_counter_store(pbrt_b200_work_counter* c, uint64_t v);
+/* unlink != 0 also removes the name (the creator does that).                                                         */
+void pbrt_b200_work_counter_close(pbrt_b200_work_counter* c, int unlink_name);
 
 /* Counters mirroring the reference's stats (integrator.rs:36, scene.rs:14-15,
  * path.rs:24-25).                                                              */

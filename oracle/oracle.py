@@ -97,13 +97,13 @@ STAT_NAMES = ["camera_rays", "intersection_tests", "shadow_tests", "zero_radianc
               "any_nodes", "any_prims", "any_rays", "reserved"]
 
 
-def render(flat, integrator, nthreads=0, tile_range=None, sample_range=None, rgbw=None, tile_interleave=None):
+def render(flat, integrator, nthreads=0, tile_range=None, sample_range=None, rgbw=None, tile_interleave=None, tile_order=0):
     """SamplerIntegrator::render on the CPU oracle -> ({r,g,b,w} sums [npix,4], stats dict)."""
     film = integrator.film
     if rgbw is None:
         rgbw = np.zeros((film.height * film.width, 4), np.float32)
     sd = flat.desc()
-    rd = integrator.desc(tile_range, sample_range, tile_interleave=tile_interleave)
+    rd = integrator.desc(tile_range, sample_range, tile_interleave=tile_interleave, tile_order=tile_order)
     stats = np.zeros(12, np.uint64)
     lib().orc_render(C.byref(sd), C.byref(rd), ptr(rgbw), int(nthreads), ptr(stats))
     return rgbw, dict(zip(STAT_NAMES, (int(v) for v in stats)))

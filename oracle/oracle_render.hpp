@@ -682,7 +682,10 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
     const int* sb = rd.sampler.sample_bounds;
     const int tilesize = 16;
     int ntx = (sb[2] - sb[0] + tilesize - 1) / tilesize, nty = (sb[3] - sb[1] + tilesize - 1) / tilesize;
-    uint32_t tile_begin = rd.tile_begin, tile_end = rd.tile_end ? rd.tile_end : (uint32_t)(ntx * nty);
+    // pbrt_b200_render_desc.tile_order (include/pbrt_b200.h): 0 = the reference's row-major tile numbering; S = S x S-tile super-tiles
+    const uint32_t S = rd.tile_order, nstx = S ? (uint32_t)((ntx + (int)S - 1) / (int)S) : 0u, nsty = S ? (uint32_t)((nty + (int)S - 1) / (int)S) : 0u;
+    const uint32_t n_positions = S ? nstx * nsty * S * S : (uint32_t)(ntx * nty);
+    uint32_t tile_begin = rd.tile_begin, tile_end = rd.tile_end ? rd.tile_end : n_positions;
     uint32_t s_begin = rd.sample_begin, s_end = rd.sample_end ? rd.sample_end : 0xffffffffu;  // 0 => until start_next_sample() says stop
     FilmAccum acc; acc.init(&rd.film);
     std::mutex mu;
@@ -706,6 +709,11 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
                 if (((tile - tile_begin) / g) % m != rd.tile_rem) continue;
             }
             int tx = tile % ntx, ty = tile / ntx;
+            if (S) {
+                const uint32_t st = tile / (S * S), w = tile - st * (S * S);
+                tx = (int)((st % nstx) * S + w % S); ty = (int)((st / nstx) * S + w / S);
+                if (tx >= ntx || ty >= nty) continue;  // position past the image edge
+            }
             std::unique_ptr<Sampler> ts = base->clone((int64_t)ty * ntx + tx);
             int x0 = sb[0] + tx * tilesize, x1 = std::min(x0 + tilesize, sb[2]);
             int y0 = sb[1] + ty * tilesize, y1 = std::min(y0 + tilesize, sb[3]);

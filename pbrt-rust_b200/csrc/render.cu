@@ -191,6 +191,7 @@ struct RenderDev {
     int ntx, nty;
     uint32_t tile_begin, tile_end, n_tiles_sel, sample_begin, n_samples_sel;
     uint32_t tile_group, tile_mod, tile_rem;
+    uint32_t tile_order, nstx;  // pbrt_b200_render_desc.tile_order; super-tile columns
     // path state, SoA over `capacity` slots
     uint32_t capacity;
     float4* ray;         // 2 x float4 per slot: {o, t_max}, {d, time}
@@ -600,6 +601,14 @@ PB_D void generate_ray(const pbrt_b200_camera& c, float2 pfilm, float time_u, fl
 
 #define PB_NO_SAMPLE 0xffffffffu /* R.pixel[slot]: the slot carries no camera sample (nothing to add to the film) */
 
+// Position t of the call's tile numbering (pbrt_b200_render_desc.tile_order) -> tile coordinates; false past the image edge.
+PB_D bool tile_xy(const RenderDev& R, uint32_t t, int* tx, int* ty) {
+    if (R.tile_order == 0) { *tx = (int)(t % (uint32_t)R.ntx); *ty = (int)(t / (uint32_t)R.ntx); return true; }
+    const uint32_t S = R.tile_order, st = t / (S * S), w = t - st * (S * S);
+    *tx = (int)((st % R.nstx) * S + w % S); *ty = (int)((st / R.nstx) * S + w / S);
+    return *tx < R.ntx && *ty < R.nty;
+}
+
 // One camera sample into path slot `slot`: item = (sample, tile, pixel-in-tile), pixels of a tile contiguous
 // (x fastest, bounds.rs:263-276), tiles of the call in order, samples outermost.  Returns false when the item
 // falls outside the sample/pixel bounds (partial edge tiles) -- the slot then stays free.
@@ -615,8 +624,8 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     }
     const uint32_t jg = j / R.tile_group;
     uint32_t t = R.tile_begin + (jg * R.tile_mod + R.tile_rem) * R.tile_group + (j - jg * R.tile_group);
-    bool valid = t < R.tile_end;
-    int tx = t % R.ntx, ty = t / R.ntx;
+    int tx, ty;
+    bool valid = tile_xy(R, t, &tx, &ty) && t < R.tile_end;
     int x = R.sampler.sb[0] + tx * 16 + (int)(p & 15u);
     int y = R.sampler.sb[1] + ty * 16 + (int)(p >> 4);
     valid = valid && x < R.sampler.sb[2] && y < R.sampler.sb[3] && x >= R.pixel_bounds[0] && x < R.pixel_bounds[2] && y >= R.pixel_bounds[1] &&
@@ -1658,8 +1667,8 @@ __global__ void __launch_bounds__(128) k_zt_init(RenderDev R) {
             uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
             ZtTile* tp = R.zt.tiles + j;
             R.pixel[j] = PB_NO_SAMPLE;
-            if (t < R.tile_end) {
-                int tx = t % R.ntx, ty = t / R.ntx;
+            int tx, ty;
+            if (tile_xy(R, t, &tx, &ty) && t < R.tile_end) {
                 int x0 = R.sampler.sb[0] + tx * 16, y0 = R.sampler.sb[1] + ty * 16;
                 int x1 = min(x0 + 16, R.sampler.sb[2]), y1 = min(y0 + 16, R.sampler.sb[3]);
                 tp->x0 = x0; tp->y0 = y0; tp->w = (uint32_t)max(x1 - x0, 0); tp->npix = tp->w * (uint32_t)max(y1 - y0, 0);
@@ -1717,9 +1726,9 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
     uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
     ZtTile* tp = R.zt.tiles + j;
     R.pixel[j] = PB_NO_SAMPLE;
-    if (t >= R.tile_end) return;
+    int tx, ty;
+    if (!tile_xy(R, t, &tx, &ty) || t >= R.tile_end) return;
     {
-        int tx = t % R.ntx, ty = t / R.ntx;
         int x0 = R.sampler.sb[0] + tx * 16, y0 = R.sampler.sb[1] + ty * 16;
         int x1 = min(x0 + 16, R.sampler.sb[2]), y1 = min(y0 + 16, R.sampler.sb[3]);
         tp->x0 = x0; tp->y0 = y0; tp->w = (uint32_t)max(x1 - x0, 0); tp->npix = tp->w * (uint32_t)max(y1 - y0, 0);
@@ -2161,6 +2170,12 @@ void launch_spatial_build(const RenderDev& R, uint32_t grid, cudaStream_t stream
 }
 }  // namespace
 
+extern "C" uint32_t pbrt_b200_tile_positions(int w, int h, uint32_t tile_order) {
+    const uint32_t ntx = (uint32_t)((std::max(w, 0) + 15) / 16), nty = (uint32_t)((std::max(h, 0) + 15) / 16);
+    if (tile_order == 0) return ntx * nty;
+    return ((ntx + tile_order - 1) / tile_order) * ((nty + tile_order - 1) / tile_order) * tile_order * tile_order;
+}
+
 extern "C" int pbrt_b200_light_distribution_lookup(pbrt_b200_scene* sc, uint32_t strategy, uint32_t flags, const float* points, uint64_t n, int32_t* voxel_out,
                                                     float* func_out) {
     if (!sc || (n && (!points || !voxel_out || !func_out))) return fail(PBRT_B200_ERR_INVALID, "light_distribution_lookup: null argument");
@@ -2245,9 +2260,12 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     const int W = crop[2] - crop[0], Hh = crop[3] - crop[1];
     if (W <= 0 || Hh <= 0) return fail(PBRT_B200_ERR_INVALID, "render: empty crop window");
     int ntx = (sb[2] - sb[0] + 15) / 16, nty = (sb[3] - sb[1] + 15) / 16;
-    uint32_t tile_begin = rd->tile_begin, tile_end = rd->tile_end ? rd->tile_end : (uint32_t)(ntx * nty);
+    const uint32_t tile_order = rd->tile_order;
+    if (tile_order > 64) return fail(PBRT_B200_ERR_INVALID, "render: tile_order (super-tile edge in tiles) must be <= 64");
+    const uint32_t n_positions = pbrt_b200_tile_positions(sb[2] - sb[0], sb[3] - sb[1], tile_order);
+    uint32_t tile_begin = rd->tile_begin, tile_end = rd->tile_end ? rd->tile_end : n_positions;
     uint32_t s_begin = rd->sample_begin, s_end = rd->sample_end ? rd->sample_end : spp_eff;
-    if (tile_end > (uint32_t)(ntx * nty) || tile_begin > tile_end || s_begin > s_end || s_end > spp_eff)
+    if (tile_end > n_positions || tile_begin > tile_end || s_begin > s_end || s_end > spp_eff)
         return fail(PBRT_B200_ERR_INVALID, "render: tile/sample window out of range");
     uint32_t tile_group = rd->tile_group ? rd->tile_group : 1u, tile_mod = rd->tile_mod ? rd->tile_mod : 1u, tile_rem = rd->tile_rem;
     if (tile_rem >= tile_mod) return fail(PBRT_B200_ERR_INVALID, "render: tile_rem must be < tile_mod");
@@ -2325,6 +2343,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     R.ntx = ntx; R.nty = nty;
     R.tile_begin = tile_begin; R.tile_end = tile_end; R.n_tiles_sel = n_tiles_sel; R.sample_begin = s_begin; R.n_samples_sel = s_end - s_begin;
     R.tile_group = tile_group; R.tile_mod = tile_mod; R.tile_rem = tile_rem;
+    R.tile_order = tile_order; R.nstx = tile_order ? (uint32_t)((ntx + (int)tile_order - 1) / (int)tile_order) : 0u;
 
     // DirectLightingIntegrator::preprocess (directlighting.rs:61-76) with nsamples() == 1 for every light
     const uint32_t rec_n_arrays = ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL ? (uint32_t)R.max_depth * R.n_lights * 2u : 0u;

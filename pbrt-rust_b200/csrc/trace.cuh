@@ -285,6 +285,7 @@ struct TravRay {
 #endif
 };
 
+PB_D bool lane0_of_warp() { return (threadIdx.x & 31u) == 0u; }
 PB_D bool trav_done(const TravRay& r) { return r.cur == PB_DONE && r.pend == PB_DONE; }  // nothing left to visit, no parked leaf
 
 // root_ref / root_box: the accelerator to walk (the scene's aggregate or an instanced object's BVH); root_box == nullptr
@@ -823,6 +824,17 @@ PB_D bool traverse_ifif(const DevScene& s, f3 o, f3 d, float t_max, RayHit* hit)
 //     bool load(uint32_t idx, f3* o, f3* d, float* t_max)
 //     void store(uint32_t idx, const TravRay& r)
 #define PB_FETCH_CHUNK 32   /* tools/trace_ab.py: larger chunks cost coherent rays 25-45% */
+// Refill latency.  A warp's refill is one atomicAdd on a single global counter -- ~1 M of them per 33 M-ray launch, one every ~5 ns
+// against the ~4 ns the L2 slice needs per same-address atomic (profiles/r02_ncu_regen.md) -- whose round trip the whole warp waits
+// for.  Two ways around it were tried and BOTH measured slower on B200 (hits bit-identical; gpurun_out/r2j_ab.log, r2k_ab.log):
+//   * PB_FETCH_AHEAD = 1: lane 0 reserves the NEXT chunk while the current one is traversed (one chunk of look-ahead per warp):
+//     S3 step 35.8 -> 37.2 ms, camera batch 4424 -> 4244 Mrays/s;
+//   * reserving 4 / 8 chunks per global atomic and parking the extra ones in shared memory for the sibling warps: 35.8 -> 37.6 / 40.1 ms.
+// Both widen the band of the ray queue that is in flight at any moment; the queue is in path order (neighbouring pixels, then
+// neighbouring hit points), and the traversal's cache hit rates live off that locality more than they suffer from the refill wait.
+#ifndef PB_FETCH_AHEAD
+#define PB_FETCH_AHEAD 0
+#endif
 #define PB_REFILL_BELOW 24
 #ifndef PB_INTERIOR_MIN
 #define PB_INTERIOR_MIN 16
@@ -837,6 +849,10 @@ PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_c
     r.cur = PB_DONE; r.pend = PB_DONE; r.sp = 0; r.found = false;
     uint32_t ray_idx = 0xffffffffu;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
+#if PB_FETCH_AHEAD
+    uint32_t ahead = 0;
+    if (lane0_of_warp()) ahead = atomicAdd(fetch_counter, (uint32_t)tune.chunk);
+#endif
     bool exhausted = false;                // warp-uniform
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -848,7 +864,13 @@ PB_D void trace_queue(const DevScene& s, Job& job, uint32_t n, uint32_t* fetch_c
         while (need && !exhausted) {
             if (pool_next == pool_end) {
                 uint32_t b = 0;
+#if PB_FETCH_AHEAD
+                // the chunk reserved when the previous one was taken (its atomic has had a whole chunk's traversal to complete);
+                // the reservation for the refill after this one goes out now
+                if (lane == 0) { b = ahead; ahead = atomicAdd(fetch_counter, (uint32_t)tune.chunk); }
+#else
                 if (lane == 0) b = atomicAdd(fetch_counter, (uint32_t)tune.chunk);
+#endif
                 b = __shfl_sync(0xffffffffu, b, 0);
                 if (b >= n) { exhausted = true; break; }
                 pool_next = b; pool_end = min(b + (uint32_t)tune.chunk, n);

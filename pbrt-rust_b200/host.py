@@ -98,7 +98,7 @@ class RenderDesc(C.Structure):
     _fields_ = [("camera", CameraDesc), ("film", FilmDesc), ("sampler", SamplerDesc), ("integrator", IntegratorDesc),
                 ("tile_begin", C.c_uint32), ("tile_end", C.c_uint32), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
                 ("paths_in_flight", C.c_uint32), ("flags", C.c_uint32),
-                ("tile_group", C.c_uint32), ("tile_mod", C.c_uint32), ("tile_rem", C.c_uint32), ("reserved", C.c_uint32)]
+                ("tile_group", C.c_uint32), ("tile_mod", C.c_uint32), ("tile_rem", C.c_uint32), ("tile_order", C.c_uint32)]
 
 
 class RenderStats(C.Structure):
@@ -113,7 +113,9 @@ RENDER_OVERWRITE = 4
 
 EXPORTS = ["pbrt_b200_last_error", "pbrt_b200_abi_version", "pbrt_b200_device_count", "pbrt_b200_bvh_build", "pbrt_b200_scene_create",
            "pbrt_b200_scene_destroy", "pbrt_b200_scene_world_bound", "pbrt_b200_intersect", "pbrt_b200_intersect_p", "pbrt_b200_intersect_dev",
-           "pbrt_b200_intersect_p_dev", "pbrt_b200_render", "pbrt_b200_film_resolve", "pbrt_b200_light_distribution_lookup", "pbrt_b200_release_cached_memory"]
+           "pbrt_b200_intersect_p_dev", "pbrt_b200_render", "pbrt_b200_film_resolve", "pbrt_b200_light_distribution_lookup", "pbrt_b200_release_cached_memory", "pbrt_b200_tile_positions",
+           "pbrt_b200_work_counter_open", "pbrt_b200_work_counter_fetch_add", "pbrt_b200_work_counter_fetch_max", "pbrt_b200_work_counter_load", "pbrt_b200_work_counter_store",
+           "pbrt_b200_work_counter_close"]
 
 
 class B200Error(RuntimeError):
@@ -147,6 +149,19 @@ def load_library():
     lib.pbrt_b200_film_resolve.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
     lib.pbrt_b200_release_cached_memory.restype = None
     lib.pbrt_b200_light_distribution_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.pbrt_b200_tile_positions.argtypes = [C.c_int, C.c_int, C.c_uint32]
+    lib.pbrt_b200_tile_positions.restype = C.c_uint32
+    lib.pbrt_b200_work_counter_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.pbrt_b200_work_counter_fetch_add.argtypes = [C.c_void_p, C.c_uint64]
+    lib.pbrt_b200_work_counter_fetch_add.restype = C.c_uint64
+    lib.pbrt_b200_work_counter_fetch_max.argtypes = [C.c_void_p, C.c_uint64]
+    lib.pbrt_b200_work_counter_fetch_max.restype = C.c_uint64
+    lib.pbrt_b200_work_counter_load.argtypes = [C.c_void_p]
+    lib.pbrt_b200_work_counter_load.restype = C.c_uint64
+    lib.pbrt_b200_work_counter_store.argtypes = [C.c_void_p, C.c_uint64]
+    lib.pbrt_b200_work_counter_store.restype = None
+    lib.pbrt_b200_work_counter_close.argtypes = [C.c_void_p, C.c_int]
+    lib.pbrt_b200_work_counter_close.restype = None
     _lib = lib
     return lib
 
@@ -331,6 +346,40 @@ class Transform:
         det = (m[0, 0] * (m[1, 1] * m[2, 2] - m[1, 2] * m[2, 1]) - m[0, 1] * (m[1, 0] * m[2, 2] - m[1, 2] * m[2, 0]) +
                m[0, 2] * (m[1, 0] * m[2, 1] - m[1, 1] * m[2, 0]))
         return bool(det < 0)
+
+
+class WorkCounter:
+    """pbrt_b200_work_counter: a 64-bit counter in POSIX shared memory that the processes driving the GPUs of one box claim tile
+    ranges from (the reference's shared tile queue, integrator.rs:291-296).  Host-only: works without a GPU."""
+
+    def __init__(self, name, create):
+        self.lib, self.name, self.owner = load_library(), name, bool(create)
+        h = C.c_void_p()
+        _check(self.lib.pbrt_b200_work_counter_open(name.encode(), 1 if create else 0, C.byref(h)), "pbrt_b200_work_counter_open")
+        self.handle = h
+
+    def fetch_add(self, n):
+        return int(self.lib.pbrt_b200_work_counter_fetch_add(self.handle, C.c_uint64(int(n))))
+
+    def fetch_max(self, v):
+        return int(self.lib.pbrt_b200_work_counter_fetch_max(self.handle, C.c_uint64(int(v))))
+
+    def load(self):
+        return int(self.lib.pbrt_b200_work_counter_load(self.handle))
+
+    def store(self, v):
+        self.lib.pbrt_b200_work_counter_store(self.handle, C.c_uint64(int(v)))
+
+    def close(self):
+        if self.handle:
+            self.lib.pbrt_b200_work_counter_close(self.handle, 1 if self.owner else 0)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------
@@ -917,8 +966,9 @@ class PathIntegrator:
             sb = (max(sb[0], x0), max(sb[1], y0), min(sb[2], x1), min(sb[3], y1))
         self.pixel_bounds = sb
 
-    def desc(self, tile_range=None, sample_range=None, paths_in_flight=0, flags=0, tile_interleave=None):
+    def desc(self, tile_range=None, sample_range=None, paths_in_flight=0, flags=0, tile_interleave=None, tile_order=0):
         d = RenderDesc()
+        d.tile_order = int(tile_order)  # 0: the reference's row-major tile numbering; S: S x S-tile super-tiles (pbrt_b200.h)
         d.camera, d.film, d.sampler = self.camera.desc(), self.film.desc(), self.sampler.desc(self.film)
         d.integrator.max_depth, d.integrator.rr_threshold = self.max_depth, self.rr_threshold
         d.integrator.pixel_bounds[:] = self.pixel_bounds
@@ -936,6 +986,15 @@ class PathIntegrator:
     def n_tiles(self):  # integrator.rs:274-279
         sb = self.film.sample_bounds
         return ((sb[2] - sb[0] + 15) // 16) * ((sb[3] - sb[1] + 15) // 16)
+
+    def n_tile_positions(self, tile_order=0):
+        """Length of the tile numbering `tile_order` (pbrt_b200_tile_positions): n_tiles() for 0, padded to whole super-tiles otherwise."""
+        sb = self.film.sample_bounds
+        ntx, nty = (sb[2] - sb[0] + 15) // 16, (sb[3] - sb[1] + 15) // 16
+        if not tile_order:
+            return ntx * nty
+        S = int(tile_order)
+        return ((ntx + S - 1) // S) * ((nty + S - 1) // S) * S * S
 
     def render(self, scene, **kw):
         """Integrator::render (integrator.rs:249-252) -> linear RGB image [h, w, 3]."""
@@ -1017,17 +1076,18 @@ class Scene:
                                                            C.c_uint64(len(pts)), _ptr(voxel), _ptr(func)), "pbrt_b200_light_distribution_lookup")
         return voxel, func[:, :nl]
 
-    def render(self, integrator, rgbw=None, tile_range=None, sample_range=None, paths_in_flight=0, device_ptr=None, tile_interleave=None, flags=0):
+    def render(self, integrator, rgbw=None, tile_range=None, sample_range=None, paths_in_flight=0, device_ptr=None, tile_interleave=None, flags=0,
+               tile_order=0):
         film = integrator.film
         stats = RenderStats()
         if device_ptr is not None:
-            d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE | flags, tile_interleave)
+            d = integrator.desc(tile_range, sample_range, paths_in_flight, RENDER_KEEP_ON_DEVICE | flags, tile_interleave, tile_order)
             _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), device_ptr, C.byref(stats)), "pbrt_b200_render")
             return None, stats
         if rgbw is None:  # fresh image: the library overwrites it (no zero fill, no read-modify-write on the host)
             rgbw = np.empty((film.height * film.width, 4), f32)
             flags |= RENDER_OVERWRITE
-        d = integrator.desc(tile_range, sample_range, paths_in_flight, flags, tile_interleave)
+        d = integrator.desc(tile_range, sample_range, paths_in_flight, flags, tile_interleave, tile_order)
         _check(self.lib.pbrt_b200_render(self.handle, C.byref(d), _ptr(rgbw), C.byref(stats)), "pbrt_b200_render")
         return rgbw, stats
 

@@ -69,6 +69,27 @@ def test_tile_and_sample_windows_sum_to_full_render(pkg, oracle, gpu_lib):
     assert np.allclose(acc[:, 3], full[:, 3], rtol=1e-5)
 
 
+def test_super_tile_numbering_windows(pkg, oracle, gpu_lib):
+    """pbrt_b200_render_desc.tile_order: ranges of the super-tile numbering (what the multi-GPU work counter hands out) cover the
+    frame exactly once -- partial edge tiles, positions past the image edge and the (0,2) sampler's per-tile seeds included."""
+    setup = pkg.scenes.small_mixed_scene()
+    for sampler_ in ("sobol", "02sequence"):
+        integ = setup.make_integrator(spp_=4, res=(200, 120), sampler_=sampler_)  # 13 x 8 tiles: not a multiple of the super-tile edge
+        sc = pkg.Scene(setup.flat)
+        full, st = sc.render(integ)
+        for S in (4, 8):
+            n = integ.n_tile_positions(S)
+            assert n == pkg.load_library().pbrt_b200_tile_positions(200, 120, S) and n > integ.n_tiles()
+            acc = np.zeros_like(full)
+            cams = 0
+            for tr in ((0, n // 5), (n // 5, n // 2 + 3), (n // 2 + 3, n)):
+                _, s2 = sc.render(integ, rgbw=acc, tile_range=tr, tile_order=S)
+                cams += s2.camera_rays
+            assert cams == st.camera_rays
+            assert np.allclose(acc, full, rtol=2e-5, atol=2e-5)
+        sc.close()
+
+
 def test_small_paths_in_flight(pkg, oracle, gpu_lib):
     """Many small waves (capacity << work) give the same image as one big wave."""
     setup = pkg.scenes.cornell_scene()
