@@ -4,6 +4,9 @@
   launches  <launches.csv> <out.md>       per-kernel totals and shares of a `--metrics gpu__time_duration.sum` pass
   kernels   <raw.csv> <out.md> [regex]    key counters of every captured launch of a `--set full` report
                                           (raw.csv = `ncu -i X.ncu-rep --page raw --csv`)
+  source    <src.csv[.gz]> <out.md> [N]   top N source lines of one launch by warp-stall samples, with their share of the warp
+                                          instructions and the average number of active lanes
+                                          (src.csv = `ncu -i X.ncu-rep --page source --csv --print-source cuda,sass`)
 """
 import collections
 import csv
@@ -82,5 +85,36 @@ def kernels(src, dst, pattern=None):
             f.write("| top stall reasons (warps stalled per issue) | " + ", ".join(f"{n} {v:.2f}" for v, n in st[:6]) + " |\n")
 
 
+def source(src, dst, top="40"):
+    import gzip
+    import io
+    text = gzip.open(src, "rt").read() if src.endswith(".gz") else open(src).read()
+    hdr, fname, kernel, items, tot, tot_inst, tot_thr = None, "", "", [], 0, 0, 0
+    for r in csv.reader(io.StringIO(text)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fname = r[1].split("/")[-1]
+        elif r[0] == "Function Name":
+            kernel = r[1]
+        elif r[0] == "Line No":
+            hdr = r
+            si, ii, ti = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+        elif hdr is not None and r[0] != "":
+            try:
+                n, ie, te = int(r[si]), int(r[ii]), int(r[ti])
+            except (ValueError, IndexError):
+                continue
+            tot += n; tot_inst += ie; tot_thr += te
+            items.append((n, ie, te, fname, r[0], r[1].strip()[:110].replace("|", "\\|")))
+    items.sort(reverse=True)
+    with open(dst, "w") as f:
+        f.write(f"ncu source page `{src}`: `{kernel}`\n\n{tot} stall samples, {tot_inst} warp instructions, {tot_thr / max(tot_inst, 1):.1f} active lanes per warp "
+                f"instruction on average (inlined callee lines are counted under every inlining frame, so shares can add up to more than 100 %)\n\n")
+        f.write("| stall samples | warp instr | lanes | line | source |\n|---:|---:|---:|---|---|\n")
+        for n, ie, te, fn, ln, text_ in items[:int(top)]:
+            f.write(f"| {100 * n / max(tot, 1):.1f}% | {100 * ie / max(tot_inst, 1):.1f}% | {te / max(ie, 1):.1f} | {fn}:{ln} | `{text_}` |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "kernels": kernels, "source": source}[sys.argv[1]](*sys.argv[2:])
