@@ -266,6 +266,13 @@ int validate(const pbrt_b200_scene_desc* d) {
     if (d->n_prims && !d->n_nodes) return fail(PBRT_B200_ERR_INVALID, "scene_create: primitives without a BVH (Accelerator \"bvh\" is required)");
     if (d->n_prims > 0x7ffffff0ull) return fail(PBRT_B200_ERR_INVALID, "scene_create: too many primitives");
     if (d->n_nodes > 0x7ffffff0ull) return fail(PBRT_B200_ERR_INVALID, "scene_create: too many BVH nodes");
+    // every table whose count is non-zero must be there: the checks below and the uploader dereference them
+    if (d->n_triangles && !d->tri_indices) return fail(PBRT_B200_ERR_INVALID, "scene_create: tri_indices is null");
+    if (d->n_vertices && !d->vertex_p) return fail(PBRT_B200_ERR_INVALID, "scene_create: vertex_p is null");
+    if (d->n_triangles && !d->n_vertices) return fail(PBRT_B200_ERR_INVALID, "scene_create: triangles without vertices");
+    if (d->n_spheres && !d->spheres) return fail(PBRT_B200_ERR_INVALID, "scene_create: spheres is null");
+    if (d->n_materials && !d->materials) return fail(PBRT_B200_ERR_INVALID, "scene_create: materials is null");
+    if (d->n_lights && !d->lights) return fail(PBRT_B200_ERR_INVALID, "scene_create: lights is null");
     for (uint64_t i = 0; i < d->n_prims; ++i) {
         const pbrt_b200_prim& p = d->prims[i];
         if (p.shape_kind == PBRT_B200_SHAPE_TRIANGLE) {
@@ -322,9 +329,14 @@ int check_node_range(const pbrt_b200_bvh_node* nodes, uint64_t nn, uint64_t n_pr
     *n_interior = 0;
     if (nn == 0) return PBRT_B200_OK;
     std::vector<uint8_t> depth(nn, 0);
+    // every node but the root must be reached exactly once: a DAG-shaped array (several interior nodes sharing a child) passes the
+    // per-node checks but has more interior nodes than a tree of nn nodes, and the device-side layout build sizes its arrays for a tree
+    std::vector<uint8_t> parents(nn, 0);
+    parents[0] = 1;
     uint32_t ni = 0;
     for (uint64_t i = 0; i < nn; ++i) {
         const pbrt_b200_bvh_node& n = nodes[i];
+        if (parents[i] != 1) return fail(PBRT_B200_ERR_INVALID, "scene_create: LinearBVHNode array is not a tree (a node is unreachable or has two parents)");
         if (n.n_prims != 0) {
             if ((uint64_t)n.offset + n.n_prims > n_prims)
                 return fail(PBRT_B200_ERR_INVALID, i == 0 ? "scene_create: root node refers past the primitive table" : "scene_create: malformed LinearBVHNode array");
@@ -335,6 +347,8 @@ int check_node_range(const pbrt_b200_bvh_node* nodes, uint64_t nn, uint64_t n_pr
         const int dd = depth[i] + 1;
         if (dd >= PB_STACK_DEPTH) return fail(PBRT_B200_ERR_INVALID, "scene_create: BVH deeper than the reference's 64-entry traversal stack");
         depth[c0] = depth[c1] = (uint8_t)dd;
+        if (parents[c0] < 2) parents[c0] += 1;
+        if (parents[c1] < 2) parents[c1] += 1;
         ++ni;
     }
     *n_interior = ni;

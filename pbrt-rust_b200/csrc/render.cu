@@ -2405,7 +2405,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     int grid_trace = sm_count * (trace_per_sm > 0 ? trace_per_sm : 1);  // persistent: exactly one resident wave
     // shade kernels keep 5 CTAs of 128 threads resident per SM (96-104 registers): 10 per SM = two full waves (8 left a
     // 3-CTA tail wave: -1.5 % on S3, gpurun_out/ab4.log)
-    int grid_shade = sm_count * 10, grid_small = sm_count * 4;
+    int grid_shade = sm_count * 20, grid_small = sm_count * 4;  // shade: 10 -> 20 CTAs per SM: 35.4 -> 35.2 ms per 16-spp S3 step (gpurun_out/r2o_grid.log)
     if (const char* e = getenv("PBRT_B200_GRID_SMALL")) grid_small = sm_count * std::max(1, atoi(e));  // A/B knobs (tools/ab_variants.sh)
     if (const char* e = getenv("PBRT_B200_GRID_SHADE")) grid_shade = sm_count * std::max(1, atoi(e));
     if (zt) {  // tile-serial: at most one path per tile in flight -- a few CTAs cover the queues

@@ -25,6 +25,13 @@
 #ifndef PB_PREFETCH_FAR
 #define PB_PREFETCH_FAR 0
 #endif
+#ifndef PB_LAZY_SHEAR
+#define PB_LAZY_SHEAR 0  /* 1: at instance boundaries the shear constants wait for the first triangle tested.  Measured on S4: +-0 (closest 230.7 -> 230.2 ms, shadow 69 -> 72 ms per 4-spp step) */
+#endif
+#ifndef PB_ANY_UNORDERED
+#define PB_ANY_UNORDERED 1  /* any-hit rays visit the four slots of a quad node in storage order: their answer does not depend on the order (t_max is
+                               constant), and the near / far selects are ~20 % of the node step.  B-shadow batch 4564 -> 4811 Mrays/s, occlusion bits identical */
+#endif
 #ifndef PB_COOP_TRAVERSAL
 #define PB_COOP_TRAVERSAL 0 /* 1: persistent ray queues walk the quad nodes warp-cooperatively, loop decisions are full-mask votes (trav_run_quad_coop).
                                Measured on B200 (gpurun_out/r2d_ab.log): camera batch 4590 -> 4372 Mrays/s, S3 step 42.1 -> 43.2 ms, hits bit-identical:
@@ -271,6 +278,7 @@ struct TravRay {
     int sp;
     int kx, ky, kz;
     bool ngx, ngy, ngz, found;
+    bool shear_ok;      // kz / Sx / Sy / Sz are valid for the current (o, d): see trav_set_ray<LAZY>
     uint32_t negmask;   // bit a set: the direction is negative along axis a
     bool nan_possible;  // a zero direction component: 0 * inf can appear in the slab test
     RayHit hit;
@@ -291,6 +299,22 @@ PB_D bool trav_done(const TravRay& r) { return r.cur == PB_DONE && r.pend == PB_
 // root_ref / root_box: the accelerator to walk (the scene's aggregate or an instanced object's BVH); root_box == nullptr
 // for a one-primitive object, which the reference intersects directly (no accelerator, no bounds test)
 // everything the box and triangle tests derive from (o, d) alone
+// ray-constant part of the watertight test (triangle.rs:151-165)
+PB_D void trav_set_shear(TravRay& r) {
+    const f3 d = r.d;
+    f3 ad = vabs(d);
+    r.kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
+    r.kx = (r.kz + 1 == 3) ? 0 : r.kz + 1;
+    r.ky = (r.kx + 1 == 3) ? 0 : r.kx + 1;
+    const float dpx = comp(d, r.kx), dpy = comp(d, r.ky), dpz = comp(d, r.kz);
+    r.Sx = -dpx / dpz; r.Sy = -dpy / dpz; r.Sz = 1.0f / dpz;
+    r.shear_ok = true;
+}
+// LAZY: leave the shear constants (three IEEE divisions) for the first triangle actually tested with this ray.  Used at
+// instance boundaries, where most rays that enter an object's box leave it again without reaching a leaf (S4: the six divisions
+// of the ray set-up at every instance entry and exit were 11 % of k_trace_closest<INST>'s warp instructions at 7 active lanes,
+// profiles/r02_s4_trace.md).
+template <bool LAZY = false>
 PB_D void trav_set_ray(TravRay& r, f3 o, f3 d) {
     r.o = o; r.d = d;
     r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -301,13 +325,8 @@ PB_D void trav_set_ray(TravRay& r, f3 o, f3 d) {
     r.nox = make_float2(-o.x, -o.x); r.noy = make_float2(-o.y, -o.y); r.noz = make_float2(-o.z, -o.z);
     r.ivx = make_float2(r.inv.x, r.inv.x); r.ivy = make_float2(r.inv.y, r.inv.y); r.ivz = make_float2(r.inv.z, r.inv.z);
 #endif
-    // ray-constant part of the watertight test (triangle.rs:151-165)
-    f3 ad = vabs(d);
-    r.kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
-    r.kx = (r.kz + 1 == 3) ? 0 : r.kz + 1;
-    r.ky = (r.kx + 1 == 3) ? 0 : r.kx + 1;
-    const float dpx = comp(d, r.kx), dpy = comp(d, r.ky), dpz = comp(d, r.kz);
-    r.Sx = -dpx / dpz; r.Sy = -dpy / dpz; r.Sz = 1.0f / dpz;
+    if (LAZY) r.shear_ok = false;
+    else trav_set_shear(r);
 }
 // BVHAccel::intersect's first step: the root node's own bounds test (bvh.rs:724-727).  rb == nullptr: a one-primitive
 // object, which the reference intersects directly.
@@ -473,7 +492,7 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, STK stack, int yield_belo
         if (TOP && r.cur == PB_INST_EXIT) {
             // back in world space: r.t_max = ray.t_max when the object was hit (primitive.rs:72), the world value otherwise
             if (!r.inst_found) r.t_max = r.world_t_max;
-            trav_set_ray(r, r.wo, r.wd);
+            trav_set_ray<PB_LAZY_SHEAR != 0>(r, r.wo, r.wd);
             r.cur_inst = PBRT_B200_NO_HIT; r.inst_found = false;
             PB_TRAV_POP(r, stack);
             continue;
@@ -503,7 +522,7 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, STK stack, int yield_belo
                         float tm2;
                         xf_ray(in->world_to_prim, r.o, r.d, r.t_max, &o2, &d2, &tm2);
                         r.t_max = tm2;
-                        trav_set_ray(r, o2, d2);
+                        trav_set_ray<PB_LAZY_SHEAR != 0>(r, o2, d2);
                         r.cur = trav_enter_root(r, in->root_ref, (in->flags & PB_INST_HAS_BOX) ? in->root_box : nullptr);
                         entered = true;
                         break;
@@ -512,6 +531,7 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, STK stack, int yield_belo
                     b0 = b1 = b2 = 0.0f;
                 } else {
                     f3 p0(v0.x, v0.y, v0.z), p1(v1.x, v1.y, v1.z), p2(v2.x, v2.y, v2.z);
+                    if (TOP && PB_LAZY_SHEAR && !r.shear_ok) trav_set_shear(r);
                     h = triangle_test<!ANY>(r.o, r.d, r.t_max, p0, p1, p2, r.kx, r.ky, r.kz, r.Sx, r.Sy, r.Sz, &t, &b0, &b1, &b2);
                     if (!ANY && h) {
                         float2 uv0, uv1, uv2;
@@ -568,8 +588,15 @@ PB_D void quad_step(const DevScene& s, TravRay& r, STK stack) {
     const float tAn = sA ? tA1 : tA0, tAf = sA ? tA0 : tA1, tBn = sB ? tB1 : tB0, tBf = sB ? tB0 : tB1;
     const uint32_t rAn = __float_as_uint(sA ? q6.y : q6.x), rAf = __float_as_uint(sA ? q6.x : q6.y);
     const uint32_t rBn = __float_as_uint(sB ? q6.w : q6.z), rBf = __float_as_uint(sB ? q6.z : q6.w);
+#if PB_ANY_UNORDERED
+    // A/B: an any-hit ray's answer does not depend on the visiting order (t_max never changes): slots in storage order, no selects
+    const float t0 = ANY ? tA0 : (g ? tBn : tAn), t1 = ANY ? tA1 : (g ? tBf : tAf), t2 = ANY ? tB0 : (g ? tAn : tBn), t3 = ANY ? tB1 : (g ? tAf : tBf);
+    const uint32_t r0 = ANY ? __float_as_uint(q6.x) : (g ? rBn : rAn), r1 = ANY ? __float_as_uint(q6.y) : (g ? rBf : rAf),
+                   r2 = ANY ? __float_as_uint(q6.z) : (g ? rAn : rBn), r3 = ANY ? __float_as_uint(q6.w) : (g ? rAf : rBf);
+#else
     const float t0 = g ? tBn : tAn, t1 = g ? tBf : tAf, t2 = g ? tAn : tBn, t3 = g ? tAf : tBf;
     const uint32_t r0 = g ? rBn : rAn, r1 = g ? rBf : rAf, r2 = g ? rAn : rBn, r3 = g ? rAf : rBf;
+#endif
     // the first slot that passes is visited now; the others wait on the stack, nearest on top
     uint32_t nref = PB_DONE; float ntm = 0.0f;
 #if PB_PREFETCH_FAR

@@ -637,6 +637,14 @@ class SceneBuilder:
             if kw.get("mapname"):
                 raise B200Error("image-mapped infinite lights are outside the hot path")
             r["type"], r["L"], r["n_samples"] = LIGHT_INFINITE, rgb("L", 1.0) * sc, max(int(kw.get("samples", 1)), 1)
+            # infinite.rs:128-156 takes sampled directions through light_to_world / world_to_light.  With the constant map of the hot path
+            # the radiance does not depend on the direction, so the estimator stays unbiased under any CTM, but the 2x2 sin(theta)
+            # importance map is not rotation invariant: under a non-identity CTM the reference draws a different sample set than
+            # the identity-frame sampling done here (per-sample parity is lost, the expectation is not).  Say so instead of staying silent.
+            if not np.allclose(self.ctm.m, np.eye(4, dtype=f32), atol=1e-6):
+                import warnings
+                warnings.warn('LightSource "infinite" under a non-identity CTM: directions are sampled in the world frame (the reference samples in the '
+                              "light's frame, infinite.rs:128-156); the image is unbiased but not sample-for-sample identical to the reference's")
         else:
             raise B200Error(f'LightSource "{name}" is outside the hot path (point, spot, distant, infinite, diffuse area)')
         self._lights.append(r)

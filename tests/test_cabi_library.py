@@ -60,6 +60,48 @@ def test_invalid_arguments_are_reported(pkg):
     assert lib.pbrt_b200_film_resolve(None, 4, C.c_float(1.0), None) != 0
 
 
+def test_malformed_scene_tables_are_rejected_on_the_host(pkg):
+    """pbrt_b200_scene_create validates the tables before anything reaches the device (so this runs without a GPU): null tables with a
+    non-zero count, and a LinearBVHNode array that is not a tree -- interior nodes sharing a child pass every per-node check, but the
+    device-side layout build sizes its arrays for a tree."""
+    lib = pkg.load_library()
+    H = pkg.host
+
+    def rc_of(flat, mutate):
+        d = flat.desc()
+        keep = mutate(d, flat)  # keep any replacement arrays alive until the call returns
+        out = C.c_void_p()
+        rc = lib.pbrt_b200_scene_create(C.byref(d), 0, C.byref(out))
+        if rc == 0:
+            lib.pbrt_b200_scene_destroy(out)
+        del keep
+        return rc, lib.pbrt_b200_last_error().decode()
+
+    flat = pkg.scenes.small_mixed_scene().flat
+    for field in ("tri_indices", "vertex_p", "materials", "lights"):
+        def null_it(d, f, field=field):
+            setattr(d, field, None)
+        rc, msg = rc_of(flat, null_it)
+        assert rc == 1 and field in msg, (field, rc, msg)  # PBRT_B200_ERR_INVALID
+
+    def dag(d, f):
+        # a chain of interior nodes that all take the LAST node (a leaf) as their second child: every node has c1 > c0, in range, axis ok
+        nodes = f.nodes.copy()
+        nn = len(nodes)
+        assert nn >= 8
+        last = nn - 1
+        assert nodes[last]["n_prims"] != 0
+        for i in range(nn - 2):
+            nodes[i]["n_prims"] = 0
+            nodes[i]["offset"] = last
+            nodes[i]["axis"] = 0
+        d.nodes = nodes.ctypes.data
+        return nodes
+
+    rc, msg = rc_of(flat, dag)
+    assert rc == 1 and ("not a tree" in msg or "malformed" in msg or "deeper" in msg), (rc, msg)
+
+
 def test_film_resolve_matches_oracle(pkg, oracle):
     """Film::write_image arithmetic (film.rs:217-264) is host code in the product library: compare with the oracle."""
     rng = np.random.RandomState(0)
