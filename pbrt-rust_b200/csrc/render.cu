@@ -47,6 +47,9 @@
 //             launchers.  Shading is tolerance-parity by nature (libm differs from CUDA's transcendentals):
 //             there the ~200 IEEE divisions and square roots per path (8-10 SASS instructions each, with a slow-path call)
 //             become MUFU.RCP / MUFU.RSQ sequences and a*b+c contracts to FFMA.
+#ifndef PB_SAMPLES_INNER
+#define PB_SAMPLES_INNER 1
+#endif
 #ifdef PB_TU_SHADE
 #define PB_EXACT_TU 0
 #else
@@ -521,16 +524,26 @@ PB_D void film_atomic_add(float4* film, uint32_t pix, float4 v, bool active) {
     int lane = threadIdx.x & 31;
     int leader = __ffs(peers) - 1;
     if (peers != (1u << lane)) {
-        // segmented reduction over the peer set (rare: only with filters wider than a pixel)
-        float4 acc = v;
-        unsigned rest = peers & ~(1u << leader);
-        // every peer publishes; leader gathers
-        for (unsigned m = rest; m; m &= m - 1) {
-            int src = __ffs(m) - 1;
-            float x = __shfl_sync(peers, v.x, src), y = __shfl_sync(peers, v.y, src), z = __shfl_sync(peers, v.z, src), w = __shfl_sync(peers, v.w, src);
-            if (lane == leader) { acc.x += x; acc.y += y; acc.z += z; acc.w += w; }
+        const int len = __popc(peers), rel = lane - leader;
+        if ((peers >> leader) == (len == 32 ? 0xffffffffu : ((1u << len) - 1u))) {
+            // a contiguous run of lanes (consecutive samples of one pixel: the common case with samples innermost): tree reduction,
+            // every element reaches the run's first lane exactly once
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float x = __shfl_down_sync(peers, v.x, off), y = __shfl_down_sync(peers, v.y, off), z = __shfl_down_sync(peers, v.z, off), w = __shfl_down_sync(peers, v.w, off);
+                if (rel + off < len) { v.x += x; v.y += y; v.z += z; v.w += w; }
+            }
+        } else {
+            // scattered peers (filters wider than a pixel): every peer publishes, the leader gathers
+            float4 acc = v;
+            unsigned rest = peers & ~(1u << leader);
+            for (unsigned m = rest; m; m &= m - 1) {
+                int src = __ffs(m) - 1;
+                float x = __shfl_sync(peers, v.x, src), y = __shfl_sync(peers, v.y, src), z = __shfl_sync(peers, v.z, src), w = __shfl_sync(peers, v.w, src);
+                if (lane == leader) { acc.x += x; acc.y += y; acc.z += z; acc.w += w; }
+            }
+            v = acc;
         }
-        v = acc;
     }
     if (lane == leader) atomicAdd(film + pix, v);
 }
@@ -609,19 +622,32 @@ PB_D bool tile_xy(const RenderDev& R, uint32_t t, int* tx, int* ty) {
     return *tx < R.ntx && *ty < R.nty;
 }
 
-// One camera sample into path slot `slot`: item = (sample, tile, pixel-in-tile), pixels of a tile contiguous
-// (x fastest, bounds.rs:263-276), tiles of the call in order, samples outermost.  Returns false when the item
-// falls outside the sample/pixel bounds (partial edge tiles) -- the slot then stays free.
+// One camera sample into path slot `slot`.  Returns false when the item falls outside the sample/pixel bounds (partial edge
+// tiles) -- the slot then stays free.  Item order (PB_SAMPLES_INNER): (tile, pixel-in-tile, sample) with the samples of the call
+// INNERMOST, so the 32 lanes of a warp carry consecutive samples of ONE pixel (when the call has >= 32 of them): their camera
+// rays walk the same nodes (one L1 wavefront per load instead of one per lane), hit the same few triangles, read the same pixel row
+// of the sampler table, and their film contributions collapse into one atomic per warp.  The alternative (samples outermost:
+// a warp = 32 neighbouring pixels of one sample) was round 1's order.  Every sample is an independent function of (pixel, sample
+// number), so the image does not depend on the order (only the film's f32 summation order does).
 PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t slot) {
-    uint32_t p = (uint32_t)(item & 255u);
+    uint32_t p, j, sample;  // pixel in tile; ordinal among the tiles this call owns; sample number
+#if PB_SAMPLES_INNER
+    {
+        unsigned long long pp;  // tile-pixel ordinal
+        if ((item >> 32) == 0) { const uint32_t i32 = (uint32_t)item, q = i32 / R.n_samples_sel; sample = i32 - q * R.n_samples_sel + R.sample_begin; pp = q; }
+        else { pp = item / R.n_samples_sel; sample = (uint32_t)(item - pp * R.n_samples_sel) + R.sample_begin; }
+        p = (uint32_t)(pp & 255u); j = (uint32_t)(pp >> 8);
+    }
+#else
+    p = (uint32_t)(item & 255u);
     unsigned long long rest = item >> 8;
-    uint32_t j, sample;  // ordinal among the tiles this call owns; sample number
     if ((rest >> 32) == 0) {  // (always, short of 2^40 items in one call): one 32-bit division instead of two emulated 64-bit ones
         const uint32_t r32 = (uint32_t)rest, qs = r32 / R.n_tiles_sel;
         j = r32 - qs * R.n_tiles_sel; sample = qs + R.sample_begin;
     } else {
         j = (uint32_t)(rest % R.n_tiles_sel); sample = (uint32_t)(rest / R.n_tiles_sel) + R.sample_begin;
     }
+#endif
     const uint32_t jg = j / R.tile_group;
     uint32_t t = R.tile_begin + (jg * R.tile_mod + R.tile_rem) * R.tile_group + (j - jg * R.tile_group);
     int tx, ty;
