@@ -72,8 +72,8 @@ def bench_config(desc, spp, world, pif, tiles="static"):
     how = ("tiles interleaved across ranks in groups of 8" if tiles == "static" or world == 1 else
            "ranks claim ranges of 8x8-tile super-tiles from a shared-memory work counter (guided self-scheduling)")
     return {"workload": desc, "step": f"{spp} spp per GPU over the full frame ({spp * world} spp per step in total), {how}",
-            "l2": "no explicit flush: per-step working set (2^26 path slots x ~300 B state + 110 MB scene + 33 MB film) exceeds the 126 MB L2",
-            "paths_in_flight": pif or 1 << 26, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"}
+            "l2": "no explicit flush: per-step working set (2^27 path slots x ~270 B state + 700 MB scene and sampler tables + 33 MB film) exceeds the 126 MB L2",
+            "paths_in_flight": pif or 1 << 27, "film_reduce": "NCCL reduce(sum) to rank 0 per step" if world > 1 else "none"}
 
 
 class ClockSampler:

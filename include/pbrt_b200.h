@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PBRT_B200_ABI_VERSION 3
+#define PBRT_B200_ABI_VERSION 4
 
 enum {
     PBRT_B200_OK = 0,
@@ -199,7 +199,8 @@ enum { PBRT_B200_LIGHTS_UNIFORM = 0, PBRT_B200_LIGHTS_POWER = 1, PBRT_B200_LIGHT
  * `"directlighting"` (src/integrators/directlighting.rs, strategy "one" or "all") or `"whitted"`
  * (src/integrators/whitted.rs).  0 = path keeps descriptors written before the field existed valid.         */
 enum { PBRT_B200_INTEGRATOR_PATH = 0, PBRT_B200_INTEGRATOR_DIRECT_ONE = 1, PBRT_B200_INTEGRATOR_DIRECT_ALL = 2,
-       PBRT_B200_INTEGRATOR_WHITTED = 3 };
+       PBRT_B200_INTEGRATOR_WHITTED = 3,
+       PBRT_B200_INTEGRATOR_VOLPATH = 4 /* `Integrator "volpath"` (src/integrators/volpath.rs:82-262) with homogeneous media */ };
 
 /* = PathIntegrator (src/integrators/path.rs:32-40,228-249); max_depth and pixel_bounds mean the same for
  * DirectLightingIntegrator (directlighting.rs:27-39,122-157) and WhittedIntegrator (whitted.rs), which ignore
@@ -210,7 +211,25 @@ typedef struct pbrt_b200_integrator {
     int32_t  pixel_bounds[4];
     uint32_t light_sample_strategy;
     uint32_t kind;                   /* PBRT_B200_INTEGRATOR_*                        */
+    int32_t  camera_medium;          /* ABI v4: medium the camera sits in (Camera.medium, camera.rs; index into
+                                      * pbrt_b200_scene_desc.media) or -1; only the volpath integrator looks at it   */
+    uint32_t reserved;
 } pbrt_b200_integrator;
+
+/* = HomogeneousMedium (src/media/homogeneous.rs:10-27) with its HenyeyGreenstein phase function (medium.rs:172-200). 32 B. */
+typedef struct pbrt_b200_medium {
+    float sigma_a[3];
+    float sigma_s[3];                /* sigma_t = sigma_a + sigma_s is formed on use, as HomogeneousMedium::new does */
+    float g;
+    float pad;
+} pbrt_b200_medium;
+
+/* = MediumInterface of a GeometricPrimitive (src/core/medium.rs:131-160, primitive.rs:105-150): indices into `media`, -1 = none.
+ * A row whose two sides differ is a medium transition; other rows inherit the medium of the ray that hits them.        */
+typedef struct pbrt_b200_medium_interface {
+    int32_t inside;
+    int32_t outside;
+} pbrt_b200_medium_interface;
 
 /* Flattened Scene (src/core/scene.rs:23-29 + what hangs off it).              */
 typedef struct pbrt_b200_scene_desc {
@@ -234,6 +253,10 @@ typedef struct pbrt_b200_scene_desc {
     const pbrt_b200_object *objects;     uint64_t n_objects;
     const pbrt_b200_instance *instances; uint64_t n_instances;
     uint64_t n_top_nodes, n_top_prims;   /* Scene.aggregate: nodes[0, n_top_nodes), prims[0, n_top_prims)          */
+    /* ABI v4: participating media (MakeNamedMedium / MediumInterface, api.rs).  prim_media has one row per `prims` row
+     * (same order) or is NULL when no primitive carries a medium interface.                                           */
+    const pbrt_b200_medium *media;       uint64_t n_media;
+    const pbrt_b200_medium_interface *prim_media;
 } pbrt_b200_scene_desc;
 
 typedef struct pbrt_b200_scene pbrt_b200_scene; /* opaque; owns device memory */

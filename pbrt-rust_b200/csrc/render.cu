@@ -47,6 +47,12 @@
 //             launchers.  Shading is tolerance-parity by nature (libm differs from CUDA's transcendentals):
 //             there the ~200 IEEE divisions and square roots per path (8-10 SASS instructions each, with a slow-path call)
 //             become MUFU.RCP / MUFU.RSQ sequences and a*b+c contracts to FFMA.
+// Refill threshold of the wavefront trace kernels (lanes whose ray has finished are refilled once fewer than this many are still
+// traversing).  Swept at 64 spp with runtime knobs (gpurun_out/r2q_tune.log): 16 -> 132.4 ms per step, 20 -> 133.2, 24 -> 134.7, 28 -> 136.5,
+// 32 -> 141.0; interior_min 16 stays the best of 0 / 8 / 12 / 16 / 20 / 24.  (Compile-time constants: the runtime knobs cost 3 %.)
+#ifndef PB_WF_REFILL_BELOW
+#define PB_WF_REFILL_BELOW 16
+#endif
 #ifndef PB_SAMPLES_INNER
 #define PB_SAMPLES_INNER 1
 #endif
@@ -764,7 +770,7 @@ struct PathClosestJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_closest(RenderDev R, int parity) {
     PathClosestJob job{&R, R.q_path[parity]};
-    trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path);
+    trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
 
 // sort/compact-by-material.  Lanes of the same bin form a group (match.any) and the groups of the CTA's eight warps are
@@ -1504,7 +1510,7 @@ struct ShadowJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
     ShadowJob job{&R};
-    trace_queue<true, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow);
+    trace_queue<true, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
 
 // ---------------------------------------------------------------------------
@@ -1548,7 +1554,7 @@ struct MisJob {
 template <bool INST>
 __global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
     MisJob<INST> job{&R};
-    trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis);
+    trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
 
 #endif  // PB_EXACT_TU
@@ -2303,7 +2309,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
 
     // default 2^26 slots (~20 GB of path state on a 180 GB part): measured on S3, 2^21 -> 360 M samples/s, 2^23 -> 480, 2^24 -> 549,
     // 2^25 -> 600 (634 with this round's kernels), 2^26 -> 659, 2^27 -> 655 (fewer, fuller iterations; gpurun_out/ab18.log)
-    uint32_t capacity = rd->paths_in_flight ? rd->paths_in_flight : (1u << 26);
+    // round 2 (samples innermost, faster streaming kernels): 2^26 -> 117.1 ms per 64-spp S3 step, 2^27 -> 115.0 ms (gpurun_out/r2r_refill.log): default 2^27
+    // (~36 GB of path state; ensure_buffers halves it when that does not fit)
+    uint32_t capacity = rd->paths_in_flight ? rd->paths_in_flight : (1u << 27);
     capacity = (capacity + 255u) & ~255u;
     if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
     if (zt) capacity = (n_tiles_sel + 255u) & ~255u;  // tile-serial: one path slot per tile (see ZtTile)

@@ -48,6 +48,8 @@ assert NODE_DTYPE.itemsize == 32 and PRIM_DTYPE.itemsize == 24 and SPHERE_DTYPE.
 assert MATERIAL_DTYPE.itemsize == 48 and LIGHT_DTYPE.itemsize == 136 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16
 
 SHAPE_TRIANGLE, SHAPE_SPHERE, SHAPE_INSTANCE = 0, 1, 2
+MEDIUM_DTYPE = np.dtype([("sigma_a", "<f4", 3), ("sigma_s", "<f4", 3), ("g", "<f4"), ("pad", "<f4")])                      # pbrt_b200_medium
+MEDIUM_INTERFACE_DTYPE = np.dtype([("inside", "<i4"), ("outside", "<i4")])                                                   # pbrt_b200_medium_interface
 OBJECT_DTYPE = np.dtype([("node_offset", "<u8"), ("n_nodes", "<u8"), ("prim_offset", "<u8"), ("n_prims", "<u8")])
 INSTANCE_DTYPE = np.dtype([("prim_to_world", "<f4", 16), ("world_to_prim", "<f4", 16), ("object", "<u4"), ("pad", "<u4", 3)])
 assert OBJECT_DTYPE.itemsize == 32 and INSTANCE_DTYPE.itemsize == 144
@@ -71,7 +73,8 @@ class SceneDesc(C.Structure):
                 ("lights", C.c_void_p), ("n_lights", C.c_uint64),
                 ("objects", C.c_void_p), ("n_objects", C.c_uint64),
                 ("instances", C.c_void_p), ("n_instances", C.c_uint64),
-                ("n_top_nodes", C.c_uint64), ("n_top_prims", C.c_uint64)]
+                ("n_top_nodes", C.c_uint64), ("n_top_prims", C.c_uint64),
+                ("media", C.c_void_p), ("n_media", C.c_uint64), ("prim_media", C.c_void_p)]
 
 
 class CameraDesc(C.Structure):
@@ -91,7 +94,7 @@ class SamplerDesc(C.Structure):
 
 class IntegratorDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4), ("light_sample_strategy", C.c_uint32),
-                ("kind", C.c_uint32)]
+                ("kind", C.c_uint32), ("camera_medium", C.c_int32), ("reserved", C.c_uint32)]
 
 
 class RenderDesc(C.Structure):
@@ -425,7 +428,7 @@ class FlatScene:
 
     def desc(self):
         d = SceneDesc()
-        d.abi_version = 3
+        d.abi_version = 4
         d.nodes, d.n_nodes = _ptr(self.nodes), len(self.nodes)
         d.prims, d.n_prims = _ptr(self.prims), len(self.prims)
         d.vertex_p, d.n_vertices = _ptr(self.vertex_p), len(self.vertex_p)
@@ -437,6 +440,12 @@ class FlatScene:
         d.objects, d.n_objects = _ptr(self.objects), len(self.objects)
         d.instances, d.n_instances = _ptr(self.instances), len(self.instances)
         d.n_top_nodes, d.n_top_prims = self.n_top_nodes, self.n_top_prims
+        media = getattr(self, "media", None)
+        prim_media = getattr(self, "prim_media", None)
+        if media is not None and len(media):
+            d.media, d.n_media = _ptr(media), len(media)
+        if prim_media is not None and len(prim_media):
+            d.prim_media = _ptr(prim_media)
         return d
 
     @property
