@@ -676,6 +676,10 @@ inline void setup_job(RenderJob& job, const pbrt_b200_scene_desc& sdesc, const p
         job.ip.spatial = std::make_shared<SpatialLightDistribution>(&job.scene, 64);
 }
 
+}  // namespace orc
+#include "oracle_volpath.hpp"
+namespace orc {
+
 // SamplerIntegrator::render, src/core/integrator.rs:263-403.  rgbw is ADDED to.
 inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounters* total) {
     const pbrt_b200_render_desc& rd = job.rd;
@@ -691,6 +695,7 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
     std::mutex mu;
     std::atomic<uint32_t> next(tile_begin);
     std::vector<RenderCounters> rcs(nthreads);
+    const bool trace_samples = getenv("ORC_TRACE_SAMPLES") != nullptr;  // debugging aid: one line per camera sample on stderr
     auto worker = [&](int tid) {
         RenderCounters& rc = rcs[tid];
         std::unique_ptr<Sampler> base = make_sampler(rd.sampler, job.tables);
@@ -731,7 +736,11 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
                         CameraSample cs = ts->get_camera_sample(x, y);
                         Ray ray = generate_ray(rd.camera, cs);
                         rc.camera_rays++;
-                        Spectrum L = ipl.kind == PBRT_B200_INTEGRATOR_PATH ? path_li(job.scene, ipl, ray, *ts, rc) : recursive_li(job.scene, ipl, ray, *ts, rc, 0);
+                        Spectrum L = ipl.kind == PBRT_B200_INTEGRATOR_PATH ? path_li(job.scene, ipl, ray, *ts, rc)
+                                     : ipl.kind == PBRT_B200_INTEGRATOR_VOLPATH ? volpath_li(job.scene, ipl, ray, rd.integrator.camera_medium, *ts, rc)
+                                                                                : recursive_li(job.scene, ipl, ray, *ts, rc, 0);
+                        if (trace_samples) fprintf(stderr, "orc sample %d %d %llu L %.9g %.9g %.9g ntests %llu\n", x, y, (unsigned long long)ts->current_pixel_sample_index,
+                                                   L.c[0], L.c[1], L.c[2], (unsigned long long)rc.intersection_tests + rc.shadow_tests);
                         if (L.has_nans()) L = Spectrum(0.0f);                 // integrator.rs:350-368
                         else if (L.y() < -1.0e-5f) L = Spectrum(0.0f);
                         else if (std::isinf(L.y())) L = Spectrum(0.0f);

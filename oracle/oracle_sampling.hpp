@@ -140,6 +140,10 @@ struct GlobalSampler : Sampler {
     size_t array_2d_offset = 0;
     virtual uint64_t get_index_for_sample(uint64_t sample_num) = 0;
     virtual Float sample_dimension(uint64_t index, size_t dim) const = 0;
+    // Dimensions the sampler's tables hold (1024 Sobol' matrices, 1000 primes).  The reference indexes past them and panics; the oracle
+    // and the CUDA path both hand out 0.5 from there on, so that a very deep path ends the same way on both sides.
+    virtual size_t dim_limit() const = 0;
+    Float dim_value(uint64_t index, size_t dim) const { return dim < dim_limit() ? sample_dimension(index, dim) : 0.5f; }
     void request_2d_array(int n) override { samples_2d_array_sizes.push_back(n); }
     // get_2d_array, sampler.rs:149-166.  global_start_pixel! (sampler.rs:268-303) fills every array for every sample of the
     // pixel up front: element j of array i is sample_dimension(get_index_for_sample(j), 5 + 2i [+1]) -- a pure function of
@@ -181,14 +185,14 @@ struct GlobalSampler : Sampler {
     }
     Float get_1d() override {
         if (dimension >= ARRAY_START_DIM && dimension < array_end_dim) dimension = array_end_dim;
-        Float r = sample_dimension(interval_sample_index, dimension);
+        Float r = dim_value(interval_sample_index, dimension);
         dimension += 1;
         return r;
     }
     P2 get_2d() override {
         if (dimension + 1 >= ARRAY_START_DIM && dimension < array_end_dim) dimension = array_end_dim;
-        Float y = sample_dimension(interval_sample_index, dimension + 1);
-        Float x = sample_dimension(interval_sample_index, dimension);
+        Float y = dim_value(interval_sample_index, dimension + 1);
+        Float x = dim_value(interval_sample_index, dimension);
         dimension += 2;
         return P2(x, y);
     }
@@ -232,6 +236,7 @@ struct SobolSampler : GlobalSampler {
         log2_resolution = log2_int(resolution);
     }
     uint64_t get_index_for_sample(uint64_t n) override { return sobol_interval_to_index(T, (uint32_t)log2_resolution, n, px - sb[0], py - sb[1]); }
+    size_t dim_limit() const override { return 1024; }  // NUM_SOBOL_DIMENSIONS
     Float sample_dimension(uint64_t index, size_t dim) const override {
         Float s = sobol_sample_float(T, index, dim, 0);
         if (dim == 0 || dim == 1) {

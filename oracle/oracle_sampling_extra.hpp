@@ -119,6 +119,7 @@ struct HaltonSampler : GlobalSampler {
         }
         return offset_for_current_pixel + n * sample_stride;
     }
+    size_t dim_limit() const override { return 1000; }  // PRIME_TABLE_SIZE, lowdiscrepancy.rs:9
     Float sample_dimension(uint64_t index, size_t dim) const override {
         const HaltonTables& T = HaltonTables::get();
         if (dim == 0) return radical_inverse(0, index >> (uint64_t)base_exponents[0]);

@@ -82,12 +82,14 @@ class _GraphicsState:
         self.area_light = ""
         self.area_light_params = PS.ParamSet()
         self.reverse_orientation = False
+        self.current_inside_medium = self.current_outside_medium = ""  # api.rs:340-341
 
     def clone(self):
         g = _GraphicsState()
         g.float_textures, g.spectrum_textures, g.named_materials = dict(self.float_textures), dict(self.spectrum_textures), dict(self.named_materials)
         g.current_material, g.area_light, g.area_light_params = self.current_material, self.area_light, self.area_light_params
         g.reverse_orientation = self.reverse_orientation
+        g.current_inside_medium, g.current_outside_medium = self.current_inside_medium, self.current_outside_medium
         return g
 
 
@@ -203,18 +205,45 @@ class API:
             self.ro["camera"] = (name, params)
             self.ro["camera_to_world"] = self.ctm.inverse()
             self.named_coordinate_system["name"] = self.ro["camera_to_world"]  # sic, api.rs:1210 (pbrt-v3 says "camera")
+            # the camera's medium is resolved in make_camera (api.rs:302-320) from the graphics state AT WorldEnd (RenderOptions::make_camera is
+            # called from make_integrator), where the attribute stack is back at its outermost level
 
     def include(self, name):  # api.rs:1198-1201
         from . import pbrtparser
 
         pbrtparser.parse_file(os.path.abspath(PS.resolve_filename(name)), self)
 
-    def make_named_medium(self, name, params):
-        raise B200Error("MakeNamedMedium: participating media are outside the PathIntegrator hot path (SURVEY.md §8 f4: volpath)")
+    def make_named_medium(self, name, params):  # api.rs:1211-1241 + make_medium :706-760
+        ty = params.find_one_string("type", "")
+        if not ty:
+            self._error('No parameter string "type" found in MakeNamedMedium')
+            return
+        if ty == "heterogeneous":
+            raise B200Error('Medium "heterogeneous" (GridDensityMedium) is outside the hot path (homogeneous)')
+        if ty != "homogeneous":
+            warnings.warn(f'Medium "{ty}" unknown.')
+            return
+        preset = params.find_one_string("preset", "")
+        if preset:
+            raise B200Error("MakeNamedMedium presets (get_medium_scattering_properties) are outside the hot path: give sigma_a / sigma_s")
+        scale = float(params.find_one_float("scale", 1.0))
+        g = float(params.find_one_float("g", 0.0))
+        siga = params.find_one_spectrum("sigma_a", np.array([0.0011, 0.0024, 0.014], f32))
+        sigs = params.find_one_spectrum("sigma_s", np.array([2.55, 3.21, 3.77], f32))
+        params.report_unused()
+        self.builder.make_named_medium(name, type=ty, sigma_a=siga, sigma_s=sigs, g=g, scale=scale)
 
-    def medium_interface(self, inside, outside):
-        if inside or outside:
-            raise B200Error("MediumInterface: participating media are outside the PathIntegrator hot path (SURVEY.md §8 f4: volpath)")
+    def _medium_names(self):  # create_medium_interface, api.rs:382-403: an undefined name is logged and stands for no medium
+        out = []
+        for n in (self.gs.current_inside_medium, self.gs.current_outside_medium):
+            if n and n not in self.builder._media_index:
+                self._error(f'Named medium "{n}" undefined')
+                n = ""
+            out.append(n)
+        return tuple(out)
+
+    def medium_interface(self, inside, outside):  # api.rs:1243-1258
+        self.gs.current_inside_medium, self.gs.current_outside_medium = inside, outside
         self.have_scattering_media = True
 
     # --- world block -----------------------------------------------------------------------------
@@ -411,6 +440,7 @@ class API:
             return
         b = self.builder
         b.ctm, b.reverse_orientation = self.ctm, self.gs.reverse_orientation
+        b._medium_names = self._medium_names()
         kw = self._shape_arguments(name, params)
         if kw is None:
             return  # make_shapes returned no shape: nothing else happens (api.rs:1518-1520)
@@ -622,9 +652,9 @@ class API:
         camera = self._make_camera(film)
         sampler = self._make_sampler()
         name, p = self.ro["integrator"]
-        if name not in ("path", "directlighting", "whitted"):
+        if name not in ("path", "directlighting", "whitted", "volpath"):
             if name in KNOWN_INTEGRATORS:
-                raise B200Error(f'Integrator "{name}" is outside the device path ("path", "directlighting", "whitted"; SURVEY.md §8 f4 lists volpath next)')
+                raise B200Error(f'Integrator "{name}" is outside the device path ("path", "volpath", "directlighting", "whitted")')
             raise B200Error(f'Integrator "{name}" unknown.')
         maxdepth = p.find_one_int("maxdepth", 5)  # path.rs:225-253, directlighting.rs:125, whitted.rs:111
         pb = p.find_int("pixelbounds")
@@ -638,6 +668,13 @@ class API:
             rr = float(p.find_one_float("rrthreshold", 1.0))
             strategy = p.find_one_string("lightsamplestrategy", "spatial")
             integ = H.PathIntegrator(camera, film, sampler, maxdepth=maxdepth, rrthreshold=rr, lightsamplestrategy=strategy, pixelbounds=pixelbounds)
+        elif name == "volpath":  # volpath.rs:224-262; Camera.medium = the outside medium of the graphics state make_camera sees (api.rs:256)
+            rr = float(p.find_one_float("rrthreshold", 1.0))
+            strategy = p.find_one_string("lightsamplestrategy", "spatial")
+            self.builder._medium_names = self._medium_names()
+            cam_medium = self.builder.camera_medium()
+            integ = H.VolPathIntegrator(camera, film, sampler, maxdepth=maxdepth, rrthreshold=rr, lightsamplestrategy=strategy, pixelbounds=pixelbounds,
+                                        camera_medium=cam_medium)
         elif name == "directlighting":  # directlighting.rs:146-156
             st = p.find_one_string("strategy", "all")
             if st not in ("one", "all"):
@@ -666,7 +703,7 @@ class API:
         max_prims = ap.find_one_int("maxnodeprims", 4)
         ap.report_unused()
         flat = self.builder.world_end(max_prims=max_prims, split_method=split)
-        if self.have_scattering_media:
+        if self.have_scattering_media and name != "volpath":
             warnings.warn(f'Scene has scattering media but "{name}" integrator doesn\'t support volume scattering.')
         return RenderJob(flat, integ, filename, (split, max_prims))
 

@@ -309,6 +309,21 @@ int validate(const pbrt_b200_scene_desc* d) {
     } else if (d->n_instances) {
         return fail(PBRT_B200_ERR_INVALID, "scene_create: instances without objects");
     }
+    if (d->n_media && !d->media) return fail(PBRT_B200_ERR_INVALID, "scene_create: media is null");
+    if (d->n_media > 0x7fffffffull) return fail(PBRT_B200_ERR_INVALID, "scene_create: too many media");
+    for (uint64_t i = 0; i < d->n_media; ++i) {
+        const pbrt_b200_medium& m = d->media[i];
+        for (int k = 0; k < 3; ++k)
+            if (!(m.sigma_a[k] >= 0.0f) || !(m.sigma_s[k] >= 0.0f) || !(m.sigma_a[k] + m.sigma_s[k] < INFINITY))
+                return fail(PBRT_B200_ERR_INVALID, "scene_create: medium coefficients must be finite and non-negative");
+        if (!(m.g > -1.0f && m.g < 1.0f)) return fail(PBRT_B200_ERR_INVALID, "scene_create: medium g must lie in (-1, 1)");
+    }
+    if (d->prim_media)
+        for (uint64_t i = 0; i < d->n_prims; ++i) {
+            const pbrt_b200_medium_interface& mi = d->prim_media[i];
+            if (mi.inside < -1 || mi.outside < -1 || mi.inside >= (int64_t)d->n_media || mi.outside >= (int64_t)d->n_media)
+                return fail(PBRT_B200_ERR_INVALID, "scene_create: medium interface index out of range");
+        }
     for (uint64_t i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type > PBRT_B200_MAT_METAL) return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: material outside the hot path");
     for (uint64_t i = 0; i < d->n_lights; ++i) {
@@ -443,6 +458,7 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     add(12ull * nt); add(sizeof(pbrt_b200_sphere) * d->n_spheres); add(sizeof(pbrt_b200_material) * d->n_materials); add(sizeof(pbrt_b200_light) * d->n_lights);
     add(sizeof(DevInstance) * d->n_instances); add(4ull * d->n_objects); add(sizeof(DevScene));
     add(d->vertex_n ? 48ull * np : 0); add(d->vertex_uv ? 24ull * np : 0); add(96ull * d->n_lights);  // slot_n, slot_uv, light_tris
+    add(sizeof(pbrt_b200_medium) * d->n_media); add(d->prim_media ? sizeof(pbrt_b200_medium_interface) * np : 0);
     const size_t resident = need;
     add(sizeof(pbrt_b200_bvh_node) * nn); add(4ull * nn); add(4ull * nb);
     need += 4096;
@@ -504,6 +520,9 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     up(d->spheres, sizeof(pbrt_b200_sphere) * d->n_spheres, &ds.spheres);
     up(d->materials, sizeof(pbrt_b200_material) * d->n_materials, &ds.materials);
     up(d->lights, sizeof(pbrt_b200_light) * d->n_lights, &ds.lights);
+    up(d->media, sizeof(pbrt_b200_medium) * d->n_media, &ds.media);
+    up(d->prim_media, d->prim_media ? sizeof(pbrt_b200_medium_interface) * np : 0, &ds.prim_media);
+    ds.n_media = (uint32_t)d->n_media;
     lap("h2d staged");
     if ((rc = join_checks())) { pbrt_b200_scene_destroy(sc); return rc; }
     lap("checks joined");

@@ -333,6 +333,9 @@ PB_D float halton_dimension(const SamplerDev& S, unsigned long long index, uint3
 }
 
 struct SampleCursor { unsigned long long index; uint32_t dim; int px, py; };  // absolute pixel
+// Dimensions the tables hold: 1024 Sobol' matrices, PRIME_TABLE_SIZE primes.  The reference indexes past them and panics; here (and in the
+// oracle) deeper dimensions read 0.5.
+PB_D uint32_t sampler_dim_limit(const SamplerDev& S) { return S.kind == PBRT_B200_SAMPLER_SOBOL ? 1024u : S.n_halton_dims; }
 PB_D float sample_dimension(const SamplerDev& S, const SampleCursor& c, uint32_t dim) {
     return S.kind == PBRT_B200_SAMPLER_SOBOL ? sobol_dimension(S, c.index, dim, c.px, c.py) : halton_dimension(S, c.index, dim);
 }
@@ -365,7 +368,7 @@ PB_D void sample_block(const SamplerDev& S, const SampleCursor& c, SampleBlock& 
         for (int k = 0; k < 8; ++k) b.u[k] = fminf((float)v[k] * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
     } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) b.u[k] = (c.dim + k < 1024u) ? sample_dimension(S, c, c.dim + k) : 0.5f;
+        for (int k = 0; k < 8; ++k) b.u[k] = (c.dim + k < sampler_dim_limit(S)) ? sample_dimension(S, c, c.dim + k) : 0.5f;
     }
 }
 PB_D float block_pick(const SampleBlock& b, uint32_t k) {
@@ -518,6 +521,73 @@ template <> struct PathSampler<true> {
     PB_D float2 get_2d() { return pb::get_2d(z); }
     PB_D void end(const RenderDev&, uint32_t) {}
 };
+
+// The volpath megakernel's sampler (k_vol_mega): GlobalSampler::get_1d / get_2d evaluated one dimension at a time, because the number
+// of dimensions a path segment consumes depends on whether the ray travels in a medium (2 more) and on what it meets.
+struct DirectSampler {
+    SampleCursor c; const SamplerDev* S;
+    PB_D void prefetch(const RenderDev& R, uint32_t id) {
+        const uint32_t pxy = R.pixel[id];
+        c.index = R.s_index[id]; c.dim = R.s_dim[id];
+        c.px = (int)(pxy & 0xffffu) + R.sampler.sb[0]; c.py = (int)(pxy >> 16) + R.sampler.sb[1];
+        S = &R.sampler;
+    }
+    PB_D void begin(const RenderDev&, uint32_t) {}
+    PB_D float dim_value(uint32_t d) const { return d < sampler_dim_limit(*S) ? sample_dimension(*S, c, d) : 0.5f; }
+    PB_D float get_1d() { float r = dim_value(c.dim); c.dim += 1; return r; }
+    PB_D float2 get_2d() { float y = dim_value(c.dim + 1), x = dim_value(c.dim); c.dim += 2; return make_float2(x, y); }
+    PB_D void end(const RenderDev& R, uint32_t id) { R.s_dim[id] = c.dim; }
+};
+template <bool ZT, bool VOL> struct SamplerSel { using type = PathSampler<ZT>; };
+template <bool ZT> struct SamplerSel<ZT, true> { using type = DirectSampler; };
+
+// Per-path state of the volpath integrator that the surface path integrator does not have (kept by the megakernel thread that owns
+// the path): the medium the path ray travels in, and what the two transmittance loops of estimate_direct need to continue through
+// material-less surfaces (VisibilityTester::tr, light.rs:125-150; Scene::intersect_tr, scene.rs:68-87).
+struct VolState {
+    int medium;            // Ray.medium of the path ray (-1: vacuum)
+    int sh_medium;         // ... of the shadow ray's first segment
+    int mis_medium;        // ... of the BSDF / phase-sampled ray's first segment
+    f3 p1, p1_err, p1_n;   // VisibilityTester.p1: where the shadow segments are re-aimed
+    f3 mi_p;               // the sampled MediumInteraction
+};
+// MediumInterface of an intersection (primitive.rs:134-140) and Interaction::get_medium_vec (interaction.rs:54-66)
+struct VolInterface { int inside, outside; };
+PB_D VolInterface vol_hit_interface(const DevScene& s, uint32_t slot, int ray_medium) {
+    VolInterface mi{ray_medium, ray_medium};  // MediumInterface::new(ray.medium)
+    if (s.prim_media) {
+        const pbrt_b200_medium_interface pm = s.prim_media[slot];
+        if (pm.inside != pm.outside) { mi.inside = pm.inside; mi.outside = pm.outside; }  // is_medium_transition
+    }
+    return mi;
+}
+PB_D int vol_medium_for(const VolInterface& mi, f3 n, f3 w) { return dot(w, n) > 0.0f ? mi.outside : mi.inside; }
+// phase_hg and HenyeyGreenstein::sample_p, medium.rs:162-221
+PB_D float phase_hg(float cos_theta, float g) {
+    float denom = 1.0f + g * g + 2.0f * g * cos_theta;
+    return PB_INV_4PI * (1.0f - g * g) / (denom * sqrtf(denom));
+}
+PB_D float hg_sample_p(float g, f3 wo, f3* wi, float2 u) {
+    float cos_theta;
+    if (fabsf(g) < 1.0e-3f) cos_theta = 1.0f - 2.0f * u.x;
+    else {
+        float sqr = (1.0f - g * g) / (1.0f + g - 2.0f * g * u.x);
+        cos_theta = -(1.0f + g * g - sqr * sqr) / (2.0f * g);
+    }
+    float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+    float phi = 2.0f * PB_PI * u.y;
+    f3 v1, v2;
+    coordinate_system(wo, &v1, &v2);
+    *wi = v1 * sin_theta * cosf(phi) + v2 * sin_theta * sinf(phi) + wo * cos_theta;  // spherical_direction_basis, geometry.rs:36-38
+    return phase_hg(cos_theta, g);
+}
+PB_D rgb medium_sigma_t(const pbrt_b200_medium& m) { return rgb3(m.sigma_a) + rgb3(m.sigma_s); }
+// HomogeneousMedium::tr, homogeneous.rs:30-33
+PB_D rgb medium_tr(const pbrt_b200_medium& m, f3 d, float t_max) {
+    const rgb st = medium_sigma_t(m);
+    const float dist = fminf(t_max * len(d), PB_FLT_MAX);
+    return rgb(expf(-st.r * dist), expf(-st.g * dist), expf(-st.b * dist));
+}
 
 // ---------------------------------------------------------------------------
 // film: FilmTile::add_sample (core/film.rs:292-331) with warp-aggregated atomics
@@ -1288,8 +1358,11 @@ template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT =
 // One path of a material queue: PathIntegrator::li from the hit to the next ray (path.rs:104-214).  Shared by the wavefront
 // kernel k_shade and the tile-serial megakernel k_zt_mega.
 struct ShadeOut { bool push_next, push_shadow, push_mis, push_dead, zero_rad; };
-template <int BIN, bool INST, bool ZT>
-PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
+// VOL: VolPathIntegrator::li's surface branch (volpath.rs:134-189) -- the same vertex, except that the light is sampled whatever the
+// BSDF's lobes are (no num_components test), rays carry a medium (`vs`), and a material-less surface LOWERS the bounce count
+// (`bounces -= 1; continue` skips the loop's increment; at 0 the usize wraps and the path ends at its next depth test).
+template <int BIN, bool INST, bool ZT, bool VOL = false>
+PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id, VolState* vs = nullptr) {
     constexpr int KM = BinKinds<BIN>::KM;
     (void)KM;
     bool push_next = false, push_shadow = false, push_mis = false, push_dead = false, zero_rad = false;
@@ -1311,7 +1384,7 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
         push_dead = true;
     } else {
         uint4 h = R.hit[id];
-        PathSampler<ZT> smp;
+        typename SamplerSel<ZT, VOL>::type smp;
         smp.prefetch(R, id);
         uint32_t fl;
         const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
@@ -1322,6 +1395,8 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
             const pbrt_b200_light& al = R.scene.lights[pr.area_light];
             if (al.two_sided || dot(si.n, -rd) > 0.0f) L = L + rgb3(al.L) * beta;
         }
+        VolInterface vmi{-1, -1};
+        if (VOL) vmi = vol_hit_interface(R.scene, h.x, vs->medium);
         if (bounces >= (uint32_t)R.max_depth) {
             R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
             push_dead = true;
@@ -1334,17 +1409,22 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
                 f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
                 store_ray(R.ray, id, o, rd, PB_INF, time);
                 R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                if (VOL) {  // volpath.rs:131-135
+                    vs->medium = vol_medium_for(vmi, si.n, rd);
+                    bounces = (bounces - 1u) & 0xffffu;
+                    R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(bounces | (specular_bounce ? 0x10000u : 0u)));
+                }
                 push_next = true;
             } else {
                 smp.begin(R, id);
                 const int NONSPEC = BX_ALL & ~BX_SPECULAR;
                 // ---- uniform_sample_onelight + estimate_direct, integrator.rs:81-237
-                if (bsdf_count(bsdf, NONSPEC) > 0 && R.n_lights > 0) {
+                if ((VOL || bsdf_count(bsdf, NONSPEC) > 0) && R.n_lights > 0) {
                     float u1 = smp.get_1d();
                     // light_distrib.lookup(isect.p), path.rs:132
                     const float* ld_cdf = R.ld_cdf; const float* ld_func = R.ld_func; float ld_func_int = R.ld_func_int;
                     if (R.sp.enabled) {
-                        int sl = R.sp.slot[(R.sp.lazy && !ZT) ? R.sp_voxel[id] : spatial_voxel(R, si.p)];  // (the megakernel has no mark pass)
+                        int sl = R.sp.slot[(R.sp.lazy && !ZT && !VOL) ? R.sp_voxel[id] : spatial_voxel(R, si.p)];  // (the megakernels have no mark pass)
                         if (sl >= 0) { ld_cdf = R.sp.cdf + (size_t)sl * (R.n_lights + 1); ld_func = R.sp.func + (size_t)sl * R.n_lights; ld_func_int = R.sp.func_int[sl]; }
                         else atomicExch(R.sp.counters + 2, 1u);  // cannot happen unless the slot table overflowed: the host fails the call
                     }
@@ -1371,6 +1451,7 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
                                 rgb add = beta * (Ld / selpdf);
                                 store_ray(R.sh_ray, id, o, d, 1.0f - PB_SHADOW_EPSILON, time);
                                 R.sh_contrib[id] = make_float4(add.r, add.g, add.b, 0.f);
+                                if (VOL) { vs->sh_medium = vol_medium_for(vmi, si.n, d); vs->p1 = ls.p1; vs->p1_err = ls.p1_err; vs->p1_n = ls.p1_n; }
                                 push_shadow = true;
                                 zero = false;
                             }
@@ -1393,6 +1474,7 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
                                     rgb fac = beta * (f * weight / scattpdf / selpdf);
                                     store_ray(R.mis_ray, id, o, wi, PB_INF, time);
                                     R.mis_contrib[id] = make_float4(fac.r, fac.g, fac.b, __uint_as_float(ln));
+                                    if (VOL) vs->mis_medium = vol_medium_for(vmi, si.n, wi);
                                     push_mis = true;
                                     zero = false;
                                 }
@@ -1426,6 +1508,7 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id) {
                     }
                     if (alive) {
                         store_ray(R.ray, id, o, wi, PB_INF, time);
+                        if (VOL) vs->medium = vol_medium_for(vmi, si.n, wi);
                         bounces += 1;
                         R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(bounces | (specular_bounce ? 0x10000u : 0u)));
                         push_next = true;
@@ -1822,6 +1905,304 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
         ok = zt_next_path(R, j, false);
     }
     atomicAdd(&R.cnt->camera_rays, n_camera); atomicAdd(&R.cnt->closest_rays, n_closest); atomicAdd(&R.cnt->shadow_rays, n_shadow);
+    atomicAdd(&R.cnt->zero_radiance, n_zero); atomicMax(&R.cnt->iterations, n_iter);
+}
+
+
+// ---------------------------------------------------------------------------
+// VolPathIntegrator (src/integrators/volpath.rs:82-221) with homogeneous media: one kernel, a thread per path
+// ---------------------------------------------------------------------------
+// A volumetric path is a chain of data-dependent loops -- medium sampling in front of every vertex, the two transmittance loops of
+// estimate_direct (VisibilityTester::tr, Scene::intersect_tr) that walk through any number of material-less boundaries, a sample
+// stream whose length depends on which of them ran -- so it is written as the reference writes it: one thread owns a path from its
+// camera sample to the film, claims the next camera sample when it is done (warp-aggregated fetch-add on the call's item cursor),
+// and calls the same traversal (exact TU) and shading functions as the surface path integrator.  Path state lives in the slot
+// arrays of RenderDev (slot = global thread index), the volume-only state in the thread (VolState).
+
+// FilmTile::add_sample without the warp aggregation of film_add_sample (the lanes of this kernel are not converged)
+PB_D void film_add_sample_lane(const RenderDev& R, float2 pfilm, rgb L) {
+    const float rx = R.filter_radius[0], ry = R.filter_radius[1];
+    const float ly = lum(L);
+    if (ly > R.max_sample_luminance) L = L * rgb(R.max_sample_luminance / ly);
+    const float dx = pfilm.x - 0.5f, dy = pfilm.y - 0.5f;
+    const int p0x = max((int)ceilf(dx - rx), R.crop[0]), p0y = max((int)ceilf(dy - ry), R.crop[1]);
+    const int p1x = min((int)floorf(dx + rx) + 1, R.crop[2]), p1y = min((int)floorf(dy + ry) + 1, R.crop[3]);
+    const int width = R.crop[2] - R.crop[0];
+    for (int y = p0y; y < p1y; ++y)
+        for (int x = p0x; x < p1x; ++x) {
+            float fx = fabsf(((float)x - dx) * R.inv_filter_radius[0] * 16.0f);
+            float fy = fabsf(((float)y - dy) * R.inv_filter_radius[1] * 16.0f);
+            int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
+            float fw = __ldg(R.filter_table + iy * 16 + ix);
+            rgb c = L * rgb(1.0f) * rgb(fw);
+            atomicAdd(R.film + (size_t)(y - R.crop[1]) * width + (x - R.crop[0]), make_float4(c.r, c.g, c.b, fw));
+        }
+}
+
+// HomogeneousMedium::sample (homogeneous.rs:35-72) in front of the vertex the path ray of slot `id` has just found, then volpath.rs:114.
+// Returns 0: no medium interaction (go on with the surface / the miss), 1: interaction sampled at vs->mi_p, 2: beta is black.
+PB_D int vol_sample_medium(const RenderDev& R, uint32_t id, VolState* vs, bool found, float t_hit) {
+    float4 bs = R.beta_st[id];
+    rgb beta(bs.x, bs.y, bs.z);
+    bool sampled = false;
+    if (vs->medium >= 0) {
+        const float4 ra = R.ray[2 * id], rb = R.ray[2 * id + 1];
+        const f3 o(ra.x, ra.y, ra.z), d(rb.x, rb.y, rb.z);
+        const float t_max = found ? t_hit : ra.w;  // Scene::intersect leaves the hit distance in ray.t_max
+        DirectSampler smp;
+        smp.prefetch(R, id);
+        const pbrt_b200_medium m = R.scene.media[vs->medium];
+        const rgb st = medium_sigma_t(m), ss = rgb3(m.sigma_s);
+        const int channel = min((int)(smp.get_1d() * 3.0f), 2);
+        const float stc = channel == 0 ? st.r : (channel == 1 ? st.g : st.b);
+        const float dist = -logf(1.0f - smp.get_1d()) / stc;
+        const float dl = len(d);
+        const float t = fminf(dist / dl, t_max);
+        sampled = t < t_max;
+        if (sampled) vs->mi_p = o + d * t;
+        const float tt = fminf(t, PB_FLT_MAX);
+        const rgb Tr(expf((-st.r * tt) * dl), expf((-st.g * tt) * dl), expf((-st.b * tt) * dl));
+        const rgb density = sampled ? st * Tr : Tr;
+        float pdf = 0.0f;
+        pdf += density.r; pdf += density.g; pdf += density.b;
+        pdf *= 1.0f / 3.0f;
+        if (pdf == 0.0f) pdf = 1.0f;
+        beta = beta * (sampled ? Tr * ss / pdf : Tr / pdf);
+        R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, bs.w);
+        smp.end(R, id);
+    }
+    if (is_black(beta)) return 2;
+    return sampled ? 1 : 0;
+}
+
+// The medium branch of VolPathIntegrator::li (volpath.rs:117-133): uniform_sample_onelight / estimate_direct with the phase function
+// in the BSDF's place (integrator.rs:140-146,183-188), then HenyeyGreenstein::sample_p for the next direction.
+template <bool INST>
+static __device__ __noinline__ ShadeOut vol_shade_medium(const RenderDev* Rp, uint32_t id, VolState* vs) {
+    const RenderDev& R = *Rp;
+    ShadeOut out{false, false, false, false, false};
+    const float4 rb = R.ray[2 * id + 1];
+    const f3 rd(rb.x, rb.y, rb.z);
+    const float time = rb.w;
+    float4 Le = R.L_eta[id], bs = R.beta_st[id];
+    rgb beta(bs.x, bs.y, bs.z);
+    uint32_t st = __float_as_uint(bs.w);
+    uint32_t bounces = st & 0xffffu;
+    if (bounces >= (uint32_t)R.max_depth) { out.push_dead = true; return out; }
+    DirectSampler smp;
+    smp.prefetch(R, id);
+    const f3 p = vs->mi_p, wo = -rd, zero(0.f, 0.f, 0.f);
+    const float g = R.scene.media[vs->medium].g;
+    if (R.n_lights > 0) {
+        float u1 = smp.get_1d();
+        const float* ld_cdf = R.ld_cdf; const float* ld_func = R.ld_func; float ld_func_int = R.ld_func_int;
+        if (R.sp.enabled) {
+            int sl = R.sp.slot[spatial_voxel(R, p)];
+            if (sl >= 0) { ld_cdf = R.sp.cdf + (size_t)sl * (R.n_lights + 1); ld_func = R.sp.func + (size_t)sl * R.n_lights; ld_func_int = R.sp.func_int[sl]; }
+            else atomicExch(R.sp.counters + 2, 1u);
+        }
+        uint32_t ln = find_interval_cdf(ld_cdf, (int)R.n_lights + 1, u1);
+        float selpdf = ld_func_int > 0.0f ? ld_func[ln] / (ld_func_int * (float)R.n_lights) : 0.0f;
+        bool zero_rad = true;
+        if (selpdf != 0.0f) {
+            float2 ulight = smp.get_2d();
+            float2 uscatt = smp.get_2d();
+            const pbrt_b200_light& light = R.scene.lights[ln];
+            bool delta = is_delta_light(light);
+            LightSample ls;
+            light_sample_li<INST>(R, ln, p, ulight, ls, zero, zero);
+            if (ls.pdf > 0.0f && !is_black(ls.Li)) {
+                float ph = phase_hg(dot(wo, ls.wi), g);
+                if (ph != 0.0f) {
+                    f3 o = offset_ray_origin(p, zero, zero, ls.p1 - p);
+                    f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
+                    f3 d = tg - o;
+                    rgb f(ph);
+                    rgb Ld = delta ? f * ls.Li / ls.pdf : f * ls.Li * power_heuristic(ls.pdf, ph) / ls.pdf;
+                    rgb add = beta * (Ld / selpdf);
+                    store_ray(R.sh_ray, id, o, d, 1.0f - PB_SHADOW_EPSILON, time);
+                    R.sh_contrib[id] = make_float4(add.r, add.g, add.b, 0.f);
+                    vs->sh_medium = vs->medium; vs->p1 = ls.p1; vs->p1_err = ls.p1_err; vs->p1_n = ls.p1_n;
+                    out.push_shadow = true;
+                    zero_rad = false;
+                }
+            }
+            if (!delta) {
+                f3 wi(0.f, 0.f, 0.f);
+                float ph = hg_sample_p(g, wo, &wi, uscatt);
+                if (ph != 0.0f && ph > 0.0f) {
+                    Surf ref;
+                    ref.p = p; ref.p_error = zero; ref.n = zero; ref.wo = wo; ref.sh_n = zero; ref.sh_dpdu = zero;
+                    float lpdf = light_pdf_li<INST>(R, ln, ref, wi);
+                    if (lpdf != 0.0f) {
+                        float weight = power_heuristic(ph, lpdf);
+                        rgb fac = beta * (rgb(ph) * weight / ph / selpdf);
+                        store_ray(R.mis_ray, id, offset_ray_origin(p, zero, zero, wi), wi, PB_INF, time);
+                        R.mis_contrib[id] = make_float4(fac.r, fac.g, fac.b, __uint_as_float(ln));
+                        vs->mis_medium = vs->medium;
+                        out.push_mis = true;
+                        zero_rad = false;
+                    }
+                }
+            }
+        }
+        out.zero_rad = zero_rad;
+    }
+    // volpath.rs:127-132: new direction from the phase function; the ray stays in the medium
+    f3 wi(0.f, 0.f, 0.f);
+    hg_sample_p(g, wo, &wi, smp.get_2d());
+    store_ray(R.ray, id, offset_ray_origin(p, zero, zero, wi), wi, PB_INF, time);
+    bool alive = true;
+    {   // Russian roulette, volpath.rs:206-214 (specular_bounce = false)
+        rgb rrbeta = beta * Le.w;
+        float mc = max_comp(rrbeta);
+        if (mc < R.rr_threshold && bounces > 3) {
+            float qv = fmaxf(1.0f - mc, 0.05f);
+            if (smp.get_1d() < qv) alive = false;
+            else beta = beta / (1.0f - qv);
+        }
+    }
+    smp.end(R, id);
+    if (alive) {
+        bounces += 1;
+        R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(bounces));
+        out.push_next = true;
+    } else out.push_dead = true;
+    return out;
+}
+
+template <int BIN, bool INST>
+static __device__ __noinline__ ShadeOut vol_shade(const RenderDev* Rp, uint32_t id, VolState* vs) { return shade_path<BIN, INST, false, true>(*Rp, id, vs); }
+
+#define PB_VOL_SEGMENT_CAP 4096u   /* transmittance loops: boundaries crossed by one shadow / MIS ray before it is given up (hang guard) */
+#define PB_VOL_VERTEX_CAP 65536u   /* path loop: boundary crossings lower the bounce count, so max_depth alone does not bound it */
+template <bool INST>
+__global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* Rdev, unsigned long long total_items, int camera_medium) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // slot
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long n_camera = 0, n_closest = 0, n_zero = 0, n_iter = 0;
+    uint2 stack_mem[PB_STACK_SIZE(INST)];
+    LocalStack stack{stack_mem};
+    VolState vs;
+    for (;;) {
+        // claim the next camera sample: the lanes that arrive together share one fetch-add
+        unsigned long long item;
+        {
+            const unsigned m = __activemask();
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(&R.cnt->item_cursor, (unsigned long long)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            item = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+        }
+        if (item >= total_items) break;
+        if (!gen_camera_path(R, item, j)) continue;
+        n_camera += 1;
+        vs.medium = camera_medium;
+        bool alive = true;
+        uint32_t vertices = 0;
+        while (alive && vertices++ < PB_VOL_VERTEX_CAP) {
+            n_iter += 1;
+            TravRay r;
+            {
+                float4 a = R.ray[2 * j], b = R.ray[2 * j + 1];
+                trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+                trav_run<false, INST>(R.scene, r, stack, 0);
+                n_closest += 1;
+            }
+            const int bin = store_closest_hit(R, j, r);
+            const int ms = vol_sample_medium(R, j, &vs, r.found, r.hit.t);
+            if (ms == 2) break;  // volpath.rs:114
+            ShadeOut o;
+            if (ms == 1) o = vol_shade_medium<INST>(Rdev, j, &vs);
+            else switch (bin) {
+                case Q_MATTE: o = vol_shade<Q_MATTE, INST>(Rdev, j, &vs); break;
+                case Q_PLASTIC: o = vol_shade<Q_PLASTIC, INST>(Rdev, j, &vs); break;
+                case Q_MIRROR: o = vol_shade<Q_MIRROR, INST>(Rdev, j, &vs); break;
+                case Q_GLASS: o = vol_shade<Q_GLASS, INST>(Rdev, j, &vs); break;
+                case Q_METAL: o = vol_shade<Q_METAL, INST>(Rdev, j, &vs); break;
+                case Q_NOMAT: o = vol_shade<Q_NOMAT, INST>(Rdev, j, &vs); break;
+                default: o = vol_shade<Q_MISS, INST>(Rdev, j, &vs); break;
+            }
+            if (o.zero_rad) n_zero += 1;
+            if (o.push_shadow) {  // VisibilityTester::tr, light.rs:125-150
+                float4 a = R.sh_ray[2 * j], b = R.sh_ray[2 * j + 1];
+                f3 ro(a.x, a.y, a.z), rdir(b.x, b.y, b.z);
+                float t_max = a.w;
+                int med = vs.sh_medium;
+                rgb Tr(1.0f);
+                bool blocked = false;
+                for (uint32_t seg = 0;; ++seg) {
+                    if (seg >= PB_VOL_SEGMENT_CAP) { blocked = true; break; }
+                    trav_init(R.scene, r, ro, rdir, t_max);
+                    trav_run<false, INST>(R.scene, r, stack, 0);
+                    n_closest += 1;
+                    if (r.found && R.scene.prims[r.hit.slot].material >= 0) { blocked = true; break; }
+                    if (med >= 0) Tr = Tr * medium_tr(R.scene.media[med], rdir, r.found ? r.hit.t : t_max);
+                    if (!r.found) break;
+                    uint32_t fl;
+                    Surf si = surface_at_hit<INST>(R.scene, r.hit.inst, r.hit.slot, ro, rdir, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
+                    const VolInterface mi = vol_hit_interface(R.scene, r.hit.slot, med);
+                    const f3 o2 = offset_ray_origin(si.p, si.p_error, si.n, vs.p1 - si.p);  // spawn_rayto_interaction, interaction.rs:46-52
+                    const f3 tg = offset_ray_origin(vs.p1, vs.p1_err, vs.p1_n, o2 - vs.p1);
+                    rdir = tg - o2; ro = o2; t_max = 1.0f - PB_SHADOW_EPSILON;
+                    med = vol_medium_for(mi, si.n, rdir);
+                }
+                if (!blocked) {
+                    float4 c = R.sh_contrib[j], L = R.L_eta[j];
+                    L.x += c.x * Tr.r; L.y += c.y * Tr.g; L.z += c.z * Tr.b;
+                    R.L_eta[j] = L;
+                }
+            }
+            if (o.push_mis) {  // Scene::intersect_tr, scene.rs:68-87, then integrator.rs:218-232
+                float4 a = R.mis_ray[2 * j], b = R.mis_ray[2 * j + 1];
+                f3 ro(a.x, a.y, a.z);
+                const f3 rdir(b.x, b.y, b.z);
+                int med = vs.mis_medium;
+                const float4 c = R.mis_contrib[j];
+                const uint32_t ln = __float_as_uint(c.w);
+                rgb Tr(1.0f), li(0.0f);
+                for (uint32_t seg = 0; seg < PB_VOL_SEGMENT_CAP; ++seg) {
+                    trav_init(R.scene, r, ro, rdir, PB_INF);
+                    trav_run<false, INST>(R.scene, r, stack, 0);
+                    n_closest += 1;
+                    if (med >= 0) Tr = Tr * medium_tr(R.scene.media[med], rdir, r.found ? r.hit.t : PB_INF);
+                    if (!r.found) {
+                        const pbrt_b200_light& l = R.scene.lights[ln];
+                        if (l.type == PBRT_B200_LIGHT_INFINITE) li = rgb3(l.L);
+                        break;
+                    }
+                    const pbrt_b200_prim pr = R.scene.prims[r.hit.slot];
+                    uint32_t fl;
+                    Surf si = surface_at_hit<INST>(R.scene, r.hit.inst, r.hit.slot, ro, rdir, r.hit.t, r.hit.b0, r.hit.b1, r.hit.b2, &fl);
+                    if (pr.material >= 0) {
+                        if (pr.area_light == (int)ln) {
+                            const pbrt_b200_light& al = R.scene.lights[ln];
+                            if (al.two_sided || dot(si.n, -rdir) > 0.0f) li = rgb3(al.L);
+                        }
+                        break;
+                    }
+                    const VolInterface mi = vol_hit_interface(R.scene, r.hit.slot, med);
+                    ro = offset_ray_origin(si.p, si.p_error, si.n, rdir);
+                    med = vol_medium_for(mi, si.n, rdir);
+                }
+                if (!is_black(li)) {
+                    float4 L = R.L_eta[j];
+                    L.x += c.x * li.r * Tr.r; L.y += c.y * li.g * Tr.g; L.z += c.z * li.b * Tr.b;
+                    R.L_eta[j] = L;
+                }
+            }
+            alive = o.push_next;
+        }
+        float4 Le = R.L_eta[j];
+        rgb L(Le.x, Le.y, Le.z);
+        float y = lum(L);  // integrator.rs:350-368
+        if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
+        else if (y < -1.0e-5f) L = rgb(0.0f);
+        else if (isinf(y)) L = rgb(0.0f);
+        film_add_sample_lane(R, R.pfilm[j], L);
+    }
+    atomicAdd(&R.cnt->camera_rays, n_camera); atomicAdd(&R.cnt->closest_rays, n_closest);
     atomicAdd(&R.cnt->zero_radiance, n_zero); atomicMax(&R.cnt->iterations, n_iter);
 }
 
@@ -2268,8 +2649,16 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     }
     if (rd->integrator.light_sample_strategy > PBRT_B200_LIGHTS_SPATIAL) return fail(PBRT_B200_ERR_INVALID, "render: unknown light_sample_strategy");
     const uint32_t ikind = rd->integrator.kind;
-    if (ikind > PBRT_B200_INTEGRATOR_WHITTED) return fail(PBRT_B200_ERR_INVALID, "render: unknown integrator kind");
-    if (ikind != PBRT_B200_INTEGRATOR_PATH && (rd->integrator.max_depth < 1 || rd->integrator.max_depth > 64))
+    if (ikind > PBRT_B200_INTEGRATOR_VOLPATH) return fail(PBRT_B200_ERR_INVALID, "render: unknown integrator kind");
+    const bool vol = ikind == PBRT_B200_INTEGRATOR_VOLPATH;
+    const bool path_like = ikind == PBRT_B200_INTEGRATOR_PATH || vol;  // no recursion state
+    if (vol) {
+        if (zt) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: volpath needs the sobol or halton sampler");
+        if (rd->integrator.camera_medium < -1 || rd->integrator.camera_medium >= (int64_t)sc->dev.n_media)
+            return fail(PBRT_B200_ERR_INVALID, "render: camera_medium out of range");
+        if (rd->integrator.max_depth > 0xfff0) return fail(PBRT_B200_ERR_INVALID, "render: volpath maxdepth too large");
+    }
+    if (!path_like && (rd->integrator.max_depth < 1 || rd->integrator.max_depth > 64))
         return fail(PBRT_B200_ERR_INVALID, "render: directlighting / whitted need 1 <= maxdepth <= 64");
     PB_CUDA_TRY(cudaSetDevice(sc->device));
     int rc;
@@ -2316,7 +2705,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if ((unsigned long long)capacity > total_items) capacity = (uint32_t)((total_items + 255ull) & ~255ull);
     if (zt) capacity = (n_tiles_sel + 255u) & ~255u;  // tile-serial: one path slot per tile (see ZtTile)
     // recursive integrators: per slot a stack of max_depth frames and up to `eps` shadow + MIS entries; keep that state <= 6 GB
-    uint32_t rec_eps = ikind == PBRT_B200_INTEGRATOR_PATH ? 0u : (ikind == PBRT_B200_INTEGRATOR_DIRECT_ONE ? 1u : std::max<uint32_t>(sc->dev.n_lights, 1u));
+    uint32_t rec_eps = path_like ? 0u : (ikind == PBRT_B200_INTEGRATOR_DIRECT_ONE ? 1u : std::max<uint32_t>(sc->dev.n_lights, 1u));
     uint32_t rec_multi = 0;
     if (ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {  // one shadow + one MIS entry per light SAMPLE (uniform_sample_all_lights, integrator.rs:63-74)
         unsigned long long tot = 0;
@@ -2325,14 +2714,26 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         rec_eps = (uint32_t)std::max<unsigned long long>(tot, 1ull);
         if (rec_multi && zt) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting \"all\" with multi-sample lights needs the sobol or halton sampler");
     }
-    const size_t rec_per_slot = ikind == PBRT_B200_INTEGRATOR_PATH ? 0 : 8 + (size_t)rd->integrator.max_depth * 48 + (size_t)rec_eps * (48 + 52);
+    const size_t rec_per_slot = path_like ? 0 : 8 + (size_t)rd->integrator.max_depth * 48 + (size_t)rec_eps * (48 + 52);
     if (rec_per_slot) {
         const unsigned long long fit = (6ull << 30) / rec_per_slot;
         if (fit < 256) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: too many lights for one whitted / directlighting \"all\" surface evaluation");
         if (capacity > fit) capacity = (uint32_t)(fit & ~255ull);
     }
+    // volpath: one slot per thread of the megakernel's single resident wave
+    int vol_grid = 0;
+    if (vol) {
+        int smc = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, sc->device);
+        if (sc->dev.n_instances || sc->dev.n_sphere_lights) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<true>, 64, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<false>, 64, 0);
+        const unsigned long long want = (total_items + 63ull) / 64ull;
+        vol_grid = (int)std::max<unsigned long long>(1ull, std::min<unsigned long long>((unsigned long long)smc * (unsigned long long)std::max(per_sm, 1), want));
+        capacity = ((uint32_t)vol_grid * 64u + 255u) & ~255u;
+    }
     if (capacity == 0) capacity = 256;
     if ((rc = ensure_buffers(st, &capacity))) return rc;
+    if (vol && capacity < (uint32_t)vol_grid * 64u) vol_grid = (int)(capacity / 64u);
     lap("buffers");
     RenderDev R = st->buffers->dev;
     R.capacity = capacity;
@@ -2398,7 +2799,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     struct ZtRelease { void* p; size_t n; ~ZtRelease() { if (p) { cudaDeviceSynchronize(); pool_free(p, n); } } } zt_release{zt_block, zt_bytes};
     std::memset(&R.rec, 0, sizeof R.rec);
     void* rec_block = nullptr; size_t rec_bytes = 0;
-    if (ikind != PBRT_B200_INTEGRATOR_PATH) {
+    if (!path_like) {
         RecDev& rec = R.rec;
         rec.kind = ikind; rec.stack_depth = (uint32_t)R.max_depth; rec.entries_per_slot = rec_eps; rec.multi = rec_multi;
         if (ikind == PBRT_B200_INTEGRATOR_DIRECT_ALL) {
@@ -2460,9 +2861,9 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     const bool timing = stats != nullptr && !zt;  // tile-serial mode runs ~10^5 tiny iterations: no per-phase events
     uint64_t launches = 0;
     // ---- Sobol' sample tables (sobol_tab_block) for the path integrator's global-sampler runs
-    bool sample_prepass = !zt && !R.rec.kind;  // k_sample_block serves every path the tables do not
+    bool sample_prepass = !zt && !R.rec.kind && !vol;  // k_sample_block serves every path the tables do not
     R.u8 = nullptr;
-    if (!zt && !R.rec.kind && S.kind == PBRT_B200_SAMPLER_SOBOL && S.log2_resolution > 0 && !getenv("PBRT_B200_NO_SOBOL_TABLES")) {
+    if (!zt && !R.rec.kind && !vol && S.kind == PBRT_B200_SAMPLER_SOBOL && S.log2_resolution > 0 && !getenv("PBRT_B200_NO_SOBOL_TABLES")) {
         const uint32_t sbw = (uint32_t)(sb[2] - sb[0]), sbh = (uint32_t)(sb[3] - sb[1]);
         const uint32_t want = (uint32_t)std::min<long long>(1024, 5ll + 8ll * std::max(R.max_depth, 0));
         uint32_t vdims = want;
@@ -2511,8 +2912,24 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         PB_CUDA_TRY(cudaGetLastError());
         st->sp_eager_pending = false;
     }
+    if (vol && R.sp.enabled && R.sp.lazy)
+        return fail(PBRT_B200_ERR_UNSUPPORTED, "render: volpath with lightsamplestrategy \"spatial\" needs the eagerly built voxel table (voxels x lights <= 2^25)");
     PB_CUDA_TRY(cudaEventRecord(ev0, stream));
-    if (zt ? n_tiles_sel > 0 : total_items > 0) {
+    if (vol) {
+        if (total_items > 0) {
+            // R in device memory for the out-of-line shade calls (as k_zt_mega)
+            size_t rdev_bytes = 0;
+            RenderDev* rdev = reinterpret_cast<RenderDev*>(pool_alloc(sizeof(RenderDev), &rdev_bytes));
+            if (!rdev) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory");
+            ZtRelease rdev_release{rdev, rdev_bytes};
+            PB_CUDA_TRY(cudaMemcpyAsync(rdev, &R, sizeof(RenderDev), cudaMemcpyHostToDevice, stream));
+            if (sc->dev.n_instances || sc->dev.n_sphere_lights) k_vol_mega<true><<<vol_grid, 64, 0, stream>>>(R, rdev, total_items, rd->integrator.camera_medium);
+            else k_vol_mega<false><<<vol_grid, 64, 0, stream>>>(R, rdev, total_items, rd->integrator.camera_medium);
+            launches += 1;
+            PB_CUDA_TRY(cudaGetLastError());
+            PB_CUDA_TRY(cudaStreamSynchronize(stream));  // rdev is released at the end of this block
+        }
+    } else if (zt ? n_tiles_sel > 0 : total_items > 0) {
         // Persistent wavefront: all `capacity` slots start free; each iteration traces every live path one segment,
         // shades, resolves shadow/MIS rays, then k_finish_regen retires finished paths and refills their slots.
         // The host never waits on the batch it has just submitted: after every batch of `poll` iterations the queue

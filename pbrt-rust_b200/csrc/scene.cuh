@@ -79,6 +79,10 @@ struct DevScene {
     uint32_t n_lights;
     uint32_t n_sphere_lights;  // diffuse area lights whose shape is a sphere: render.cu picks the kernel family that samples them
     uint32_t n_materials;
+    // Participating media (volpath): HomogeneousMedium rows and the MediumInterface of every primitive row (nullptr: no media)
+    const pbrt_b200_medium* media;
+    const pbrt_b200_medium_interface* prim_media;
+    uint32_t n_media;
     // Scene::new preprocessing (scene.rs:32-52, distant.rs:53-60)
     float world_center[3];
     float world_radius;

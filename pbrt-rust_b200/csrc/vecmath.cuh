@@ -15,6 +15,8 @@ namespace pb {
 #define PB_PI_OVER2 1.57079632679489661923f
 #define PB_PI_OVER4 0.78539816339744830961f
 #define PB_INV_PI 0.31830988618379067154f
+#define PB_INV_4PI 0.07957747154594766788f
+#define PB_FLT_MAX 3.402823466e+38f
 #define PB_SHADOW_EPSILON 0.0001f
 #define PB_MACHINE_EPSILON 5.9604644775390625e-8f /* f32::EPSILON * 0.5 = 2^-24 */
 #define PB_ONE_MINUS_EPSILON 0.99999994f          /* 0x1.fffffep-1, core/rng.rs:4 */

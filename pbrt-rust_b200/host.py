@@ -58,7 +58,7 @@ MAT_MATTE, MAT_PLASTIC, MAT_MIRROR, MAT_GLASS, MAT_METAL = range(5)
 LIGHT_POINT, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_DIFFUSE, LIGHT_INFINITE = range(5)
 SAMPLER_SOBOL, SAMPLER_HALTON, SAMPLER_ZEROTWO = range(3)
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = range(3)
-INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED = range(4)
+INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED, INTEGRATOR_VOLPATH = range(5)
 SPLIT = {"sah": 0, "middle": 2, "equal": 3}
 
 
@@ -425,6 +425,8 @@ class FlatScene:
         self.objects = np.zeros(0, OBJECT_DTYPE)
         self.instances = np.zeros(0, INSTANCE_DTYPE)
         self.n_top_nodes = self.n_top_prims = 0  # 0 = all of nodes / prims (no object instancing)
+        self.media = np.zeros(0, MEDIUM_DTYPE)       # HomogeneousMedium rows (volpath)
+        self.prim_media = None                       # MediumInterface per `prims` row, or None
 
     def desc(self):
         d = SceneDesc()
@@ -440,12 +442,12 @@ class FlatScene:
         d.objects, d.n_objects = _ptr(self.objects), len(self.objects)
         d.instances, d.n_instances = _ptr(self.instances), len(self.instances)
         d.n_top_nodes, d.n_top_prims = self.n_top_nodes, self.n_top_prims
-        media = getattr(self, "media", None)
-        prim_media = getattr(self, "prim_media", None)
-        if media is not None and len(media):
-            d.media, d.n_media = _ptr(media), len(media)
-        if prim_media is not None and len(prim_media):
-            d.prim_media = _ptr(prim_media)
+        if len(self.media):
+            d.media, d.n_media = _ptr(self.media), len(self.media)
+        if self.prim_media is not None and len(self.prim_media):
+            if len(self.prim_media) != len(self.prims):
+                raise B200Error("FlatScene.prim_media must have one row per primitive row")
+            d.prim_media = _ptr(self.prim_media)
         return d
 
     @property
@@ -485,6 +487,10 @@ class SceneBuilder:
         self._lights = []
         self.any_n = self.any_s = self.any_uv = False
         self._objects, self._instances, self._cur_object = {}, [], None
+        # participating media (api.rs:1211-1258): named media are global (RenderOptions), the current interface is graphics state
+        self._media, self._media_index = [], {}
+        self._medium_names = ("", "")   # (inside, outside) of GraphicsState
+        self._pmedia = []               # one [n,2] int32 block per entry of self._prims: MediumInterface of each primitive row
         self.log = []  # every directive in call order (scenefile.py turns it back into a .pbrt file)
 
     # --- object instancing (api.rs:1593-1713) ---------------------------------
@@ -493,15 +499,15 @@ class SceneBuilder:
         self._push()
         if self._cur_object is not None:
             raise B200Error("ObjectBegin called inside of instance definition")
-        self._objects[name] = {"prims": [], "bounds": []}
+        self._objects[name] = {"prims": [], "bounds": [], "pmedia": []}
         self._cur_object = name
-        self._top = (self._prims, self._bounds)
-        self._prims, self._bounds = self._objects[name]["prims"], self._objects[name]["bounds"]
+        self._top = (self._prims, self._bounds, self._pmedia)
+        self._prims, self._bounds, self._pmedia = self._objects[name]["prims"], self._objects[name]["bounds"], self._objects[name]["pmedia"]
 
     def object_end(self):
         if self._cur_object is None:
             raise B200Error("ObjectEnd called outside of instance definition")
-        self._prims, self._bounds = self._top
+        self._prims, self._bounds, self._pmedia = self._top
         self._cur_object = None
         self._pop()
         self.log.append(("ObjectEnd",))
@@ -518,14 +524,52 @@ class SceneBuilder:
         row["shape_kind"], row["shape_index"], row["material"], row["area_light"] = SHAPE_INSTANCE, len(self._instances), -1, -1
         self._instances.append((name, self.ctm))
         self._prims.append(row)
+        self._pmedia.append(np.full((1, 2), -1, np.int32))  # a TransformedPrimitive carries no interface; its GeometricPrimitives do
         self._bounds.append(None)  # TransformedPrimitive::world_bound needs the object's BVH: filled in by world_end
 
     # --- graphics state ---------------------------------------------------
     def _push(self):
-        self._stack.append((self.ctm, self._material, self._area_light, self.reverse_orientation))
+        self._stack.append((self.ctm, self._material, self._area_light, self.reverse_orientation, self._medium_names))
 
     def _pop(self):
-        self.ctm, self._material, self._area_light, self.reverse_orientation = self._stack.pop()
+        self.ctm, self._material, self._area_light, self.reverse_orientation, self._medium_names = self._stack.pop()
+
+    # --- participating media (api.rs:706-760,1211-1258) -----------------------
+    def make_named_medium(self, name, type="homogeneous", sigma_a=(0.0011, 0.0024, 0.014), sigma_s=(2.55, 3.21, 3.77), g=0.0, scale=1.0, preset=""):
+        """MakeNamedMedium (api.rs:1211-1241 -> make_medium :706-760): defaults as there; sigma_a / sigma_s are multiplied by `scale`."""
+        self.log.append(("MakeNamedMedium", name, {"type": type, "sigma_a": tuple(np.asarray(sigma_a, f32).reshape(-1).tolist()) if not np.isscalar(sigma_a) else sigma_a,
+                                                   "sigma_s": tuple(np.asarray(sigma_s, f32).reshape(-1).tolist()) if not np.isscalar(sigma_s) else sigma_s,
+                                                   "g": g, "scale": scale}))
+        if type != "homogeneous":
+            raise B200Error(f'Medium "{type}" is outside the hot path (homogeneous)')
+        if preset:
+            raise B200Error("named medium presets (get_medium_scattering_properties) are outside the hot path: give sigma_a / sigma_s")
+        r = np.zeros(1, MEDIUM_DTYPE)[0]
+        sa = np.full(3, sigma_a, f32) if np.isscalar(sigma_a) else np.asarray(sigma_a, f32)
+        ss = np.full(3, sigma_s, f32) if np.isscalar(sigma_s) else np.asarray(sigma_s, f32)
+        r["sigma_a"], r["sigma_s"], r["g"] = sa * f32(scale), ss * f32(scale), g
+        self._media_index[name] = len(self._media)  # HashMap::insert replaces the entry; primitives created earlier keep the old Arc
+        self._media.append(r)
+
+    def medium_interface(self, inside, outside=""):
+        """MediumInterface (api.rs:1243-1258): names of the media inside / outside the shapes that follow ("" = none)."""
+        self.log.append(("MediumInterface", inside, outside))
+        self._medium_names = (inside, outside)
+
+    def medium_index(self, name):
+        """Row of `name` in FlatScene.media, -1 for "" (create_medium_interface, api.rs:382-403: an undefined name is an error there and None)."""
+        if not name:
+            return -1
+        if name not in self._media_index:
+            raise B200Error(f'Named medium "{name}" undefined')
+        return self._media_index[name]
+
+    def camera_medium(self):
+        """Camera.medium: the OUTSIDE medium current at the Camera directive (api.rs:256,302-320 pass create_medium_interface().outside)."""
+        return self.medium_index(self._medium_names[1])
+
+    def _cur_pmedia(self, n):
+        return np.tile(np.array([[self.medium_index(self._medium_names[0]), self.medium_index(self._medium_names[1])]], np.int32), (n, 1))
 
     def attribute_begin(self):
         self.log.append(("AttributeBegin",))
@@ -712,6 +756,7 @@ class SceneBuilder:
             self._lights.extend(list(lights))
             rows["area_light"] = np.arange(first, first + nt, dtype=np.int32)
         self._prims.append(rows)
+        self._pmedia.append(self._cur_pmedia(nt))
 
     def _sphere(self, radius=1.0):  # sphere.rs:397-432 (full sphere)
         o2w = self.ctm
@@ -740,6 +785,7 @@ class SceneBuilder:
             self._lights.append(light)
         self._spheres.append(r)
         self._prims.append(row)
+        self._pmedia.append(self._cur_pmedia(1))
 
     # --- WorldEnd: make_scene (api.rs:244-251) -------------------------------
     def world_end(self, max_prims=4, split_method="sah", builder=None):
@@ -772,17 +818,19 @@ class SceneBuilder:
                 continue
             o = self._objects[name]
             oprims = np.concatenate(o["prims"])
+            opm = np.concatenate(o["pmedia"])
             obounds = np.ascontiguousarray(np.concatenate(o["bounds"]), f32)
             oprims["creation_index"] = np.arange(next_ci, next_ci + len(oprims), dtype=np.uint32)
             next_ci += len(oprims)
             if len(oprims) > 1:
                 onodes, oorder = build(obounds, max_prims, split_method)
                 oprims = oprims[oorder]
+                opm = opm[oorder]
                 wb = onodes[0]["bounds"].copy()
             else:
                 onodes, wb = np.zeros(0, NODE_DTYPE), obounds[0].copy()
             used[name] = len(obj_tables)
-            obj_tables.append((onodes, np.ascontiguousarray(oprims), wb))
+            obj_tables.append((onodes, np.ascontiguousarray(oprims), wb, opm))
         if nprim:
             for k, bnd in enumerate(self._bounds):
                 if bnd is None:
@@ -796,14 +844,17 @@ class SceneBuilder:
             fs.nodes = nodes
             fs.prims = np.ascontiguousarray(prims[ordered])
             fs.prim_bounds = bounds
+            pmedia = [np.concatenate(self._pmedia)[ordered]]
+        else:
+            pmedia = [np.zeros((0, 2), np.int32)]
         if obj_tables:
             fs.n_top_nodes, fs.n_top_prims = len(fs.nodes), len(fs.prims)
             objs = np.zeros(len(obj_tables), OBJECT_DTYPE)
             all_nodes, all_prims = [fs.nodes], [fs.prims]
             noff, poff = len(fs.nodes), len(fs.prims)
-            for k, (onodes, oprims, _) in enumerate(obj_tables):
+            for k, (onodes, oprims, _, opm) in enumerate(obj_tables):
                 objs[k] = (noff, len(onodes), poff, len(oprims))
-                all_nodes.append(onodes); all_prims.append(oprims)
+                all_nodes.append(onodes); all_prims.append(oprims); pmedia.append(opm)
                 noff += len(onodes); poff += len(oprims)
             fs.nodes = np.ascontiguousarray(np.concatenate(all_nodes))
             fs.prims = np.ascontiguousarray(np.concatenate(all_prims))
@@ -812,6 +863,11 @@ class SceneBuilder:
             for k, (name, ctm) in enumerate(self._instances):
                 inst[k]["prim_to_world"], inst[k]["world_to_prim"], inst[k]["object"] = ctm.m.reshape(-1), ctm.m_inv.reshape(-1), used[name]
             fs.instances = inst
+        if self._media:
+            fs.media = np.array(self._media, MEDIUM_DTYPE)
+            pm = np.concatenate(pmedia)
+            if len(pm) and (pm >= 0).any():
+                fs.prim_media = np.ascontiguousarray(pm.view(MEDIUM_INTERFACE_DTYPE).reshape(-1))
         return fs
 
 
@@ -991,6 +1047,7 @@ class PathIntegrator:
         d.integrator.pixel_bounds[:] = self.pixel_bounds
         d.integrator.light_sample_strategy = self.STRATEGY[self.light_sample_strategy]
         d.integrator.kind = self.kind
+        d.integrator.camera_medium = int(getattr(self, "camera_medium", -1))
         if tile_range:
             d.tile_begin, d.tile_end = tile_range
         if sample_range:
@@ -1029,6 +1086,17 @@ class DirectLightingIntegrator(PathIntegrator):
             strategy = "all"  # directlighting.rs:149-152: unknown strategies fall back to "all" with a warning
         self.strategy = strategy
         self.kind = INTEGRATOR_DIRECT_ALL if strategy == "all" else INTEGRATOR_DIRECT_ONE
+
+
+class VolPathIntegrator(PathIntegrator):
+    """VolPathIntegrator + create_volpath_integrator (src/integrators/volpath.rs:36-80,224-262): the path integrator's parameters, plus
+    the medium the camera sits in (Camera.medium = the outside medium current at the Camera directive: SceneBuilder.camera_medium())."""
+    name = "volpath"
+    kind = INTEGRATOR_VOLPATH
+
+    def __init__(self, camera, film, sampler, maxdepth=5, rrthreshold=1.0, lightsamplestrategy="spatial", pixelbounds=None, camera_medium=-1):
+        super().__init__(camera, film, sampler, maxdepth=maxdepth, rrthreshold=rrthreshold, lightsamplestrategy=lightsamplestrategy, pixelbounds=pixelbounds)
+        self.camera_medium = int(camera_medium)
 
 
 class WhittedIntegrator(PathIntegrator):

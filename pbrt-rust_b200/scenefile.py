@@ -49,7 +49,9 @@ def _params(kind, name, kw):
             out.append(f'"bool {k}" ["{"true" if v else "false"}"]')
         elif k in ("from", "to"):
             out.append(f'"point {k}" [{_nums(v)}]')
-        elif k in _RGB_KEYS or (k == "eta" and name == "metal"):
+        elif k == "scale" and kind == "MakeNamedMedium":
+            out.append(f'"float scale" [{_num(v)}]')
+        elif k in _RGB_KEYS or k in ("sigma_a", "sigma_s") or (k == "eta" and name == "metal"):
             out.append(f'"rgb {k}" [{_rgb(v)}]')
         elif k == "samples":
             out.append(f'"integer samples" [{int(v)}]')
@@ -96,7 +98,7 @@ def write_pbrt(path, flat, integrator, ply_min_vertices=64):
         sp += f' "integer dimensions" [{samp.dimensions}]'
     L.append(f'Sampler "{_SAMPLER_NAMES[samp.kind]}" {sp}')
     ip = [f'"integer maxdepth" [{integrator.max_depth}]']
-    if integrator.name == "path":
+    if integrator.name in ("path", "volpath"):
         ip += [f'"float rrthreshold" [{_num(integrator.rr_threshold)}]', f'"string lightsamplestrategy" "{integrator.light_sample_strategy}"']
     elif integrator.name == "directlighting":
         ip.append(f'"string strategy" "{integrator.strategy}"')
@@ -120,6 +122,10 @@ def write_pbrt(path, flat, integrator, ply_min_vertices=64):
             L.append(f"{pad}{k} {_nums(e[1:])}")
         elif k == "ConcatTransform":
             L.append(f"{pad}ConcatTransform [{_nums(e[1].m.T)}]")
+        elif k == "MakeNamedMedium":
+            L.append(f'{pad}MakeNamedMedium "{e[1]}" {_params(k, e[1], e[2])}'.rstrip())
+        elif k == "MediumInterface":
+            L.append(f'{pad}MediumInterface "{e[1]}" "{e[2]}"')
         elif k in ("Material", "LightSource", "AreaLightSource"):
             L.append(f'{pad}{k} "{e[1]}" {_params(k, e[1], e[2])}'.rstrip())
         elif k == "Shape":
@@ -149,6 +155,11 @@ def write_pbrt(path, flat, integrator, ply_min_vertices=64):
             raise H.B200Error(f"scenefile: cannot serialise {k}")
         if k in ("AttributeBegin", "ObjectBegin"):
             ind += 1
+    cam_medium = int(getattr(integrator, "camera_medium", -1))
+    if integrator.name == "volpath":
+        # Camera.medium is the OUTSIDE medium of the graphics state at WorldEnd (api.rs:1736-1739 -> make_camera): state it last
+        names = [e[1] for e in flat.source_log if e[0] == "MakeNamedMedium"]
+        L.append(f'MediumInterface "" "{names[cam_medium] if cam_medium >= 0 else ""}"')
     L.append("WorldEnd")
     with open(path, "w") as f:
         f.write("\n".join(L) + "\n")

@@ -329,6 +329,78 @@ def glass_knot_scene(nu=2048, nv=512, xres=1024, yres=1024, spp=2048, maxdepth=3
     return SceneSetup(f"S5-glass-knot-{len(I) + 4}", flat, make, "glass torus knot, caustic light, maxdepth 32")
 
 
+def fog_box_scene(xres=128, yres=128, spp=16, maxdepth=5, sampler="sobol", camera_in_fog=True, instanced=False):
+    """Participating media for the volpath integrator: a closed box of matte walls filled with a thin homogeneous medium
+    ("haze", the camera sits in it), a dense forward-scattering medium ("smoke", g = 0.6) inside a material-less cube (a pure medium
+    boundary, Material "none"), a glass sphere whose inside is a coloured absorbing medium ("dye"), a mirror quad, one quad area light and
+    one point light.  Every medium-transition rule of primitive.rs:134-140 and both transmittance loops (VisibilityTester::tr through the
+    material-less cube, Scene::intersect_tr) are on the light paths of this scene.  `instanced`: the smoke cube is an ObjectInstance."""
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.0, -3.4, 1.0), (0.0, 0.0, 0.9), (0, 0, 1))
+    b.make_named_medium("haze", sigma_a=(0.01, 0.012, 0.02), sigma_s=(0.12, 0.12, 0.14), g=0.1, scale=1.0)
+    b.make_named_medium("smoke", sigma_a=(0.3, 0.3, 0.3), sigma_s=(2.5, 2.6, 2.8), g=0.6, scale=1.5)
+    b.make_named_medium("dye", sigma_a=(0.2, 1.5, 2.5), sigma_s=(0.05, 0.05, 0.05), g=0.0)
+    outer = "haze" if camera_in_fog else ""
+    b.medium_interface("", outer)  # the outermost state: what Camera.medium resolves to at WorldEnd
+
+    def wall(col, *pts, mat="matte", **kw):
+        b.material(mat, **({"Kd": col} if mat == "matte" else kw))
+        P, I = quad(*pts)
+        b.shape("trianglemesh", P=P, indices=I)
+
+    # the floor is created under the outermost state (inside "", outside haze): a transition -- rays leaving on its normal side (+z) are in the haze
+    wall((0.7, 0.7, 0.7), (-2, -4, 0), (2, -4, 0), (2, 2, 0), (-2, 2, 0))        # floor (normal +z)
+    b.attribute_begin()
+    b.medium_interface(outer, outer)  # both sides the same medium: NOT a transition, the ray keeps its medium (primitive.rs:138)
+    wall((0.7, 0.7, 0.7), (-2, -4, 2.5), (-2, 2, 2.5), (2, 2, 2.5), (2, -4, 2.5))  # ceiling
+    wall((0.7, 0.7, 0.7), (-2, 2, 0), (2, 2, 0), (2, 2, 2.5), (-2, 2, 2.5))      # back
+    wall((0.6, 0.1, 0.1), (-2, -4, 0), (-2, 2, 0), (-2, 2, 2.5), (-2, -4, 2.5))  # left
+    wall((0.1, 0.5, 0.15), (2, -4, 0), (2, -4, 2.5), (2, 2, 2.5), (2, 2, 0))     # right
+    wall((0.7, 0.7, 0.7), (-2, -4, 0), (-2, -4, 2.5), (2, -4, 2.5), (2, -4, 0))  # behind the camera
+    wall(None, (-1.9, 1.2, 0.4), (-1.2, 1.95, 0.4), (-1.2, 1.95, 1.9), (-1.9, 1.2, 1.9), mat="mirror", Kr=0.9)
+    b.attribute_end()
+    b.attribute_begin()
+    b.medium_interface(outer, outer)
+    b.area_light_source("diffuse", L=(14, 13, 11))
+    b.material("matte", Kd=0.0)
+    P, I = quad((-0.5, -0.5, 2.49), (-0.5, 0.5, 2.49), (0.5, 0.5, 2.49), (0.5, -0.5, 2.49))
+    b.shape("trianglemesh", P=P, indices=I)
+    b.attribute_end()
+    b.light_source("point", **{"from": (1.4, -1.5, 1.4), "I": (3.0, 3.0, 3.5)})
+    # dense smoke inside a material-less cube
+    b.attribute_begin()
+    b.medium_interface("smoke", outer)
+    b.material("none")
+    P, I = box_mesh((-1.2, -0.2, 0.05), (-0.2, 0.8, 1.05))
+    if instanced:
+        b.object_begin("smokebox")
+        b.shape("trianglemesh", P=P, indices=I)
+        b.object_end()
+        b.object_instance("smokebox")
+    else:
+        b.shape("trianglemesh", P=P, indices=I)
+    b.attribute_end()
+    # glass sphere filled with dye
+    b.attribute_begin()
+    b.medium_interface("dye", outer)
+    b.material("glass", index=1.5)
+    b.translate(0.8, 0.1, 0.55)
+    b.shape("sphere", radius=0.5)
+    b.attribute_end()
+    cam_medium = b.camera_medium()
+    flat = b.world_end()
+
+    def make(spp_=spp, res=(xres, yres), maxdepth_=maxdepth, sampler_=sampler, strategy="uniform", filt="box", rrthreshold=1.0, integrator="volpath"):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=55.0)
+        if integrator == "path":
+            return H.PathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy, rrthreshold=rrthreshold)
+        return H.VolPathIntegrator(cam, film, H.Sampler(sampler_, spp_), maxdepth=maxdepth_, lightsamplestrategy=strategy, rrthreshold=rrthreshold,
+                                   camera_medium=cam_medium)
+
+    return SceneSetup("V1-fog-box", flat, make, "matte box in haze, smoke cube (material-less boundary), dye-filled glass sphere, mirror; volpath")
+
+
 def small_mixed_scene(n=24, seed=5):
     """Test-sized scene touching every material/light/shape kind on the hot path."""
     b = H.SceneBuilder()

@@ -238,7 +238,8 @@ def test_out_of_scope_features_fail_loudly():
                  'Camera "orthographic"\nWorldBegin\nWorldEnd',
                  'WorldBegin\nTexture "t" "color" "checkerboard"\nMaterial "matte" "texture Kd" "t"\nWorldEnd',
                  'WorldBegin\nLightSource "infinite" "string mapname" "env.exr"\nWorldEnd', 'Sampler "random"\nWorldBegin\nWorldEnd',
-                 'WorldBegin\nMediumInterface "a" "b"\nWorldEnd'):
+                 'WorldBegin\nMakeNamedMedium "m" "string type" "heterogeneous"\nWorldEnd',
+                 'WorldBegin\nMakeNamedMedium "m" "string type" "homogeneous" "string preset" "Skin1"\nWorldEnd'):
         with pytest.raises(pkg.B200Error):
             pkg.pbrt_parse_string(text)
 
