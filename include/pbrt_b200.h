@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PBRT_B200_ABI_VERSION 4
+#define PBRT_B200_ABI_VERSION 5
 
 enum {
     PBRT_B200_OK = 0,
@@ -121,7 +121,10 @@ enum {
     PBRT_B200_MAT_PLASTIC = 1, /* src/materials/plastic.rs:34-69 a=Kd b=Ks f0=roughness   */
     PBRT_B200_MAT_MIRROR = 2,  /* src/materials/mirror.rs:23-41  a=Kr                      */
     PBRT_B200_MAT_GLASS = 3,   /* src/materials/glass.rs:35-92   a=Kr b=Kt f0=urough f1=vrough f2=index */
-    PBRT_B200_MAT_METAL = 4    /* src/materials/metal.rs:78-112  a=eta b=k f0=urough f1=vrough */
+    PBRT_B200_MAT_METAL = 4,   /* src/materials/metal.rs:78-112  a=eta b=k f0=urough f1=vrough */
+    /* ABI v5: parameters live in material_ext[] only (the row is always `textured`) */
+    PBRT_B200_MAT_UBER = 5,     /* src/materials/uber.rs:41-112      s0..4 = Kd Ks Kr Kt opacity, f0/f1 = u/v roughness, f2 = eta */
+    PBRT_B200_MAT_SUBSTRATE = 6 /* src/materials/substrate.rs:34-62  s0 = Kd, s1 = Ks, f0 = nu, f1 = nv (FresnelBlend)           */
 };
 
 typedef struct pbrt_b200_material {
@@ -130,8 +133,75 @@ typedef struct pbrt_b200_material {
     float a[3];
     float b[3];
     float f0, f1, f2;
-    float pad;
+    uint32_t textured;  /* ABI v5: 1 = parameters (texture programs, bump map) come from material_ext[same index] */
 } pbrt_b200_material; /* 48 bytes */
+
+/* ---- textures (ABI v5; src/core/texture.rs, src/textures/, src/core/mipmap.rs) ------------------------------------
+ * A texture expression (an `Arc<Textures>` tree: scale(mix(imagemap, checkerboard(..)), ..)) is handed over flattened in
+ * POSTFIX order: operands first, the operator last; evaluation is a walk over the program with a small value stack.  Texture
+ * evaluation has no side effects, so evaluating both operands of a checkerboard and selecting gives the reference's value.
+ * Float textures carry their value in all three channels (the arithmetic is channel-wise either way).                     */
+enum {
+    PBRT_B200_TEX_CONSTANT = 0,       /* textures/constant.rs: v[0..2]                                                   */
+    PBRT_B200_TEX_SCALE = 1,          /* textures/scaled.rs: pops tex2, tex1 -> tex1 * tex2                             */
+    PBRT_B200_TEX_MIX = 2,            /* textures/mix.rs: pops amount, tex2, tex1 -> tex1 * (1 - amt) + tex2 * amt       */
+    PBRT_B200_TEX_BILERP = 3,         /* textures/biler.rs: v = v00 v01 v10 v11 (3 floats each), 2D mapping               */
+    PBRT_B200_TEX_IMAGEMAP = 4,       /* textures/imagemap.rs:165-175 -> MIPMap::lookup2 (mipmap.rs:228-269), 2D mapping  */
+    PBRT_B200_TEX_UV = 5,             /* textures/uv.rs, 2D mapping                                                       */
+    PBRT_B200_TEX_CHECKERBOARD2D = 6, /* textures/checkerboard.rs:28-73: pops tex2, tex1; flags AA_CLOSEDFORM            */
+    PBRT_B200_TEX_CHECKERBOARD3D = 7, /* textures/checkerboard.rs:88-100: pops tex2, tex1; m = world_to_texture          */
+    PBRT_B200_TEX_DOTS = 8,           /* textures/dots.rs: pops `inside`, `outside` (struct field names), 2D mapping     */
+    PBRT_B200_TEX_FBM = 9,            /* textures/fbm.rs: v[0] = omega, v[1] = octaves; m = world_to_texture             */
+    PBRT_B200_TEX_WRINKLED = 10,      /* textures/wrinkled.rs: likewise (turbulence)                                      */
+    PBRT_B200_TEX_MARBLE = 11,        /* textures/marble.rs: v[0] = omega, v[1] = octaves, v[2] = scale, v[3] = variation */
+    PBRT_B200_TEX_WINDY = 12          /* textures/windy.rs                                                                */
+};
+enum { PBRT_B200_MAP_UV = 0,          /* UVMapping2D, texture.rs:137-162: m[0..3] = su sv du dv                          */
+       PBRT_B200_MAP_SPHERICAL = 1,   /* SphericalMapping2D :164-207: m = world_to_texture (row-major Transform.m)        */
+       PBRT_B200_MAP_CYLINDRICAL = 2, /* CylindricalMapping2D :209-251: m = world_to_texture                              */
+       PBRT_B200_MAP_PLANAR = 3 };    /* PlannarMapping2D :253-283: m[0..2] = vs, m[3..5] = vt, m[6] = ds, m[7] = dt       */
+enum { PBRT_B200_TEX_AA_CLOSEDFORM = 1u << 0 }; /* Checkerboard2DTexture AAMethod::ClosedForm                            */
+
+typedef struct pbrt_b200_texnode {
+    uint32_t kind;      /* PBRT_B200_TEX_*                                                */
+    uint32_t mapping;   /* PBRT_B200_MAP_* for the kinds with a 2D mapping                */
+    uint32_t flags;
+    uint32_t image;     /* IMAGEMAP: index into mipmaps[]                                 */
+    float v[12];
+    float m[16];
+} pbrt_b200_texnode; /* 128 bytes */
+
+enum { PBRT_B200_WRAP_REPEAT = 0, PBRT_B200_WRAP_BLACK = 1, PBRT_B200_WRAP_CLAMP = 2 };
+
+/* = MIPMap<T> (src/core/mipmap.rs:58-69) after MIPMap::new (:76-198): the pyramid the host built (resampled to a power of two,
+ * box-filtered levels), levels back to back, each row-major [t][s] with `channels` floats per texel (1 = ImageTextureFloat,
+ * 3 = ImageTextureRGB).  Level l is max(1, width >> l) x max(1, height >> l).                                              */
+typedef struct pbrt_b200_mipmap {
+    const float *texels;
+    uint32_t n_levels;
+    uint32_t channels;
+    uint32_t width, height;       /* level 0 (a power of two each)                          */
+    uint32_t wrap;                /* PBRT_B200_WRAP_*                                       */
+    uint32_t do_trilinear;
+    float    max_anisotropy;
+    uint32_t pad;
+} pbrt_b200_mipmap; /* 40 bytes */
+
+/* A texture-valued material parameter: textures[first, first + count) is its postfix program; count == 0: the constant. */
+typedef struct pbrt_b200_texref { uint32_t first, count; } pbrt_b200_texref;
+
+/* Parameters of a `textured` material row, by slot (s = spectrum, f = float):
+ *   matte s0=Kd f0=sigma | plastic s0=Kd s1=Ks f0=roughness | mirror s0=Kr | glass s0=Kr s1=Kt f0=urough f1=vrough f2=index
+ *   metal s0=eta s1=k f0=urough f1=vrough (the host resolves the `roughness` fallback, metal.rs:88-97) | uber, substrate: above.
+ * bump.count > 0: Material::bump (src/core/material.rs:46-87) runs first, as in every compute_scattering_functions.        */
+typedef struct pbrt_b200_material_ext {
+    pbrt_b200_texref s_tex[5];
+    float            s_const[5][3];
+    pbrt_b200_texref f_tex[3];
+    float            f_const[3];
+    pbrt_b200_texref bump;
+    uint32_t pad[4];
+} pbrt_b200_material_ext; /* 160 bytes */
 
 enum {
     PBRT_B200_LIGHT_POINT = 0,    /* src/lights/point.rs:30-97    pos, I=L            */
@@ -257,6 +327,10 @@ typedef struct pbrt_b200_scene_desc {
      * (same order) or is NULL when no primitive carries a medium interface.                                           */
     const pbrt_b200_medium *media;       uint64_t n_media;
     const pbrt_b200_medium_interface *prim_media;
+    /* ABI v5: textures.  material_ext has one row per `materials` row or is NULL when no row is `textured`. */
+    const pbrt_b200_texnode *textures;   uint64_t n_textures;
+    const pbrt_b200_mipmap *mipmaps;     uint64_t n_mipmaps;
+    const pbrt_b200_material_ext *material_ext;
 } pbrt_b200_scene_desc;
 
 typedef struct pbrt_b200_scene pbrt_b200_scene; /* opaque; owns device memory */

@@ -276,6 +276,22 @@ int orc_light_sample_batch(const pbrt_b200_scene_desc* sdesc, int light, const f
     return 0;
 }
 
+// Texture::evaluate of the program textures[first, first + count) at n interaction points.  in[16 * i]: p(3) uv(2) dpdx(3) dpdy(3)
+// dudx dvdx dudy dvdy, one pad -> out[3 * i] (float textures: the value in every channel)
+void orc_texture_eval(const pbrt_b200_scene_desc* sdesc, uint32_t first, uint32_t count, uint64_t n, const float* in, float* out) {
+    SceneView sv;
+    sv.init(*sdesc);
+    pbrt_b200_texref ref{first, count};
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* q = in + 16 * i;
+        SurfaceInteraction si;
+        si.p = V3(q[0], q[1], q[2]); si.uv = P2(q[3], q[4]); si.dpdx = V3(q[5], q[6], q[7]); si.dpdy = V3(q[8], q[9], q[10]);
+        si.dudx = q[11]; si.dvdx = q[12]; si.dudy = q[13]; si.dvdy = q[14];
+        Spectrum v = tex_eval(sv, ref, si);
+        out[3 * i] = v.c[0]; out[3 * i + 1] = v.c[1]; out[3 * i + 2] = v.c[2];
+    }
+}
+
 // PerspectiveCamera::generate_ray for one camera sample -> o[3], d[3]
 void orc_generate_ray(const pbrt_b200_camera* c, const float* cs5, float* out6) {
     CameraSample cs; cs.pfilm = P2(cs5[0], cs5[1]); cs.time = cs5[2]; cs.plens = P2(cs5[3], cs5[4]);

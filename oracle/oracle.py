@@ -162,6 +162,22 @@ def light_sample_batch(flat, light, ref_p, ref_n, u):
     return out
 
 
+def texture_eval(flat, texref, p, uv=None, dpdx=None, dpdy=None, duv=None):
+    """Texture::evaluate of the flattened program `texref` = (first, count) at points p [n,3] (uv [n,2], dpdx / dpdy [n,3],
+    duv [n,4] = dudx dvdx dudy dvdy; zeros when omitted) -> [n,3]."""
+    p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)
+    n = len(p)
+    q = np.zeros((n, 16), np.float32)
+    q[:, 0:3] = p
+    for lo, hi, v in ((3, 5, uv), (5, 8, dpdx), (8, 11, dpdy), (11, 15, duv)):
+        if v is not None:
+            q[:, lo:hi] = np.asarray(v, np.float32).reshape(-1, hi - lo)
+    out = np.zeros((n, 3), np.float32)
+    d = flat.desc()
+    lib().orc_texture_eval(C.byref(d), C.c_uint32(int(texref[0])), C.c_uint32(int(texref[1])), C.c_uint64(n), ptr(q), ptr(out))
+    return out
+
+
 def rel_mse(img, ref):
     """relMSE of SURVEY.md s8(d): mean over pixels/channels of (a-b)^2 / (b^2 + 1e-2)."""
     a, b = np.asarray(img, np.float64), np.asarray(ref, np.float64)

@@ -487,6 +487,11 @@ struct SurfaceInteraction {
     V3 sh_n, sh_dpdu, sh_dpdv;  // Shading{n,dpdu,dpdv}
     Float time = 0;
     uint32_t slot = PBRT_B200_NO_HIT;
+    // what textures, bump mapping and the specular ray differentials read
+    V3 dndu, dndv, sh_dndu, sh_dndv;
+    V3 dpdx, dpdy;                              // compute_differentials, interaction.rs:269-342
+    Float dudx = 0, dvdx = 0, dudy = 0, dvdy = 0;
+    bool shape_some = false, shape_flip = false;  // `shape` is Some / reverse_orientation ^ transform_swapshandedness
 };
 
 // SurfaceInteraction::new, interaction.rs:186-232.  `flip` = shape is Some and
@@ -499,6 +504,17 @@ inline SurfaceInteraction si_new(V3 p, V3 p_error, P2 uv, V3 wo, V3 dpdu, V3 dpd
     si.n = n; si.time = time; si.p_error = p_error; si.wo = normalize(wo); si.p = p; si.uv = uv;
     si.dpdu = dpdu; si.dpdv = dpdv; si.sh_dpdu = dpdu; si.sh_dpdv = dpdv;
     return si;
+}
+
+// SurfaceInteraction::set_shading_geometry, interaction.rs:234-255
+inline void set_shading_geometry(SurfaceInteraction& si, V3 dpdus, V3 dpdvs, V3 dndus, V3 dndvs, bool orientation_is_authoritative) {
+    si.sh_n = normalize(cross(dpdus, dpdvs));
+    if (si.shape_some) {
+        if (si.shape_flip) si.sh_n = -si.sh_n;
+        if (orientation_is_authoritative) si.n = face_forward(si.n, si.sh_n);
+        else si.sh_n = face_forward(si.sh_n, si.n);
+    }
+    si.sh_dpdu = dpdus; si.sh_dpdv = dpdvs; si.sh_dndu = dndus; si.sh_dndv = dndvs;
 }
 
 // Triangle::intersect tail, triangle.rs:236-392, for the accepted hit.
@@ -530,6 +546,7 @@ inline SurfaceInteraction triangle_interaction(const SceneView& s, const pbrt_b2
     bool ro = pr.flags & PBRT_B200_PRIM_REVERSE_ORIENTATION, sh = pr.flags & PBRT_B200_PRIM_SWAPS_HANDEDNESS;
     bool flip = ro ^ sh;
     SurfaceInteraction isect = si_new(phit, perror, uvhit, -r.d, dpdu, dpdv, r.time, shape_some && flip);
+    isect.shape_some = shape_some; isect.shape_flip = flip;
     V3 nn = normalize(cross(dp02, dp12));
     isect.n = nn; isect.sh_n = nn;
     isect.wo = -r.d;  // triangle.rs:296 (NOT normalised)
@@ -549,14 +566,22 @@ inline SurfaceInteraction triangle_interaction(const SceneView& s, const pbrt_b2
         V3 ts = cross(ss, ns);
         if (length_squared(ts) > 0.0f) { ts = normalize(ts); ss = cross(ts, ns); }
         else coordinate_system(ns, &ss, &ts);
-        if (ro) ts = -ts;
-        // set_shading_geometry(ss, ts, .., true), interaction.rs:234-255
-        isect.sh_n = normalize(cross(ss, ts));
-        if (shape_some) {
-            if (flip) isect.sh_n = -isect.sh_n;
-            isect.n = face_forward(isect.n, isect.sh_n);  // orientation_is_authoritative
+        // dndu / dndv of the interpolated normal, triangle.rs:339-377
+        V3 dndu, dndv;
+        if (has_n) {
+            V3 dn1 = s.N(vi[0]) - s.N(vi[2]), dn2 = s.N(vi[1]) - s.N(vi[2]);
+            Float det = duv02.x * duv12.y - duv02.y * duv12.x;
+            if (std::fabs(det) < 1.0e-8f) {
+                V3 dn = cross(s.N(vi[2]) - s.N(vi[0]), s.N(vi[1]) - s.N(vi[0]));
+                if (length_squared(dn) != 0.0f) coordinate_system(dn, &dndu, &dndv);
+            } else {
+                Float invdet = 1.0f / det;
+                dndu = (dn1 * duv12.y - dn2 * duv02.y) * invdet;
+                dndv = (dn1 * -duv12.x + dn2 * duv02.x) * invdet;
+            }
         }
-        isect.sh_dpdu = ss; isect.sh_dpdv = ts;
+        if (ro) ts = -ts;
+        set_shading_geometry(isect, ss, ts, dndu, dndv, true);  // interaction.rs:234-255
     }
     return isect;
 }
@@ -581,10 +606,21 @@ inline SurfaceInteraction sphere_interaction(const pbrt_b200_sphere& sp, const R
     Float cos_phi = p_hit.x * inv_radius, sin_phi = p_hit.y * inv_radius;
     V3 dpdu(-phi_max * p_hit.y, phi_max * p_hit.x, 0.0f);
     V3 dpdv = V3(p_hit.z * cos_phi, p_hit.z * sin_phi, -sp.radius * std::sin(theta)) * (theta_max - theta_min);
+    // dndu / dndv from the fundamental forms, sphere.rs:166-184
+    V3 d2pduu = V3(p_hit.x, p_hit.y, 0.0f) * -phi_max * phi_max;
+    V3 d2pduv = V3(-sin_phi, cos_phi, 0.0f) * (theta_max - theta_min) * p_hit.z * phi_max;
+    V3 d2pdvv = V3(p_hit.x, p_hit.y, p_hit.z) * -(theta_max - theta_min) * (theta_max - theta_min);
+    Float E = dot(dpdu, dpdu), F = dot(dpdu, dpdv), G = dot(dpdv, dpdv);
+    V3 Nn = normalize(cross(dpdu, dpdv));
+    Float e = dot(Nn, d2pduu), f = dot(Nn, d2pduv), g = dot(Nn, d2pdvv);
+    Float inv_EGF2 = 1.0f / (E * G - F * F);
+    V3 dndu = dpdu * (f * F - e * G) * inv_EGF2 + dpdv * (e * F - f * E) * inv_EGF2;
+    V3 dndv = dpdu * (g * F - f * G) * inv_EGF2 + dpdv * (f * F - g * E) * inv_EGF2;
     V3 p_error = vabs(p_hit) * gamma(5);
     SurfaceInteraction s = si_new(p_hit, p_error, P2(u, v), -ray.d, dpdu, dpdv, ray.time, false);
     // transform_surface_interaction
     SurfaceInteraction ret;
+    ret.dndu = ret.sh_dndu = m4_normal(w2o, dndu); ret.dndv = ret.sh_dndv = m4_normal(w2o, dndv);
     ret.p = m4_point_abs_error(o2w, s.p, s.p_error, &ret.p_error);
     ret.n = normalize(m4_normal(w2o, s.n));
     ret.wo = normalize(m4_vector(o2w, s.wo));
@@ -607,6 +643,9 @@ inline SurfaceInteraction m4_surface_interaction(const M4& m, const M4& m_inv, c
     ret.sh_n = normalize(m4_normal(m_inv, s.sh_n));
     ret.sh_dpdu = m4_vector(m, s.sh_dpdu); ret.sh_dpdv = m4_vector(m, s.sh_dpdv);
     ret.sh_n = face_forward(ret.sh_n, ret.n);
+    ret.dndu = m4_normal(m_inv, s.dndu); ret.dndv = m4_normal(m_inv, s.dndv);
+    ret.sh_dndu = m4_normal(m_inv, s.sh_dndu); ret.sh_dndv = m4_normal(m_inv, s.sh_dndv);
+    ret.shape_some = s.shape_some; ret.shape_flip = s.shape_flip;
     ret.slot = s.slot;
     return ret;
 }

@@ -199,6 +199,9 @@ struct Ray {
     Float t_max, time;
     Ray() : t_max(INFINITY_F), time(0) {}
     Ray(V3 o_, V3 d_, Float tm, Float ti) : o(o_), d(d_), t_max(tm), time(ti) {}
+    // RayDifferential (ray.rs:18-42): `diff` is Some; has_differentials is true whenever it is
+    bool has_diff = false;
+    V3 rxo, rxd, ryo, ryd;
 };
 
 // bounds.rs:559-580

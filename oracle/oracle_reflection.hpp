@@ -52,6 +52,8 @@ inline bool refract(V3 wi, V3 n, Float eta, V3* wt) {
     return true;
 }
 inline bool same_hemisphere(V3 w, V3 wp) { return w.z * wp.z > 0.0f; }
+inline Float spherical_theta(V3 v) { return std::acos(clamp(v.z, -1.0f, 1.0f)); }                        // geometry.rs:40-43
+inline Float spherical_phi(V3 v) { Float p = std::atan2(v.y, v.x); return p < 0.0f ? p + 2.0f * PI : p; }  // geometry.rs:45-54
 
 // reflection.rs:29-52
 inline Float fr_dielectric(Float cos_thetai, Float etai, Float etat) {
@@ -155,7 +157,8 @@ struct TrowbridgeReitz {
 };
 
 // ---- BxDFs (closed set reachable from the five hot materials)
-enum BxKind { BX_LAMBERT, BX_OREN_NAYAR, BX_SPEC_REFL_NOOP, BX_FRESNEL_SPECULAR, BX_MICRO_REFL, BX_MICRO_TRANS, BX_SPEC_REFL, BX_SPEC_TRANS };
+enum BxKind { BX_LAMBERT, BX_OREN_NAYAR, BX_SPEC_REFL_NOOP, BX_FRESNEL_SPECULAR, BX_MICRO_REFL, BX_MICRO_TRANS, BX_SPEC_REFL, BX_SPEC_TRANS,
+              BX_FRESNEL_BLEND /* r = Rd, t = Rs; substrate.rs */ };
 enum FresnelKind { FR_DIELECTRIC, FR_CONDUCTOR };
 
 struct BxDF {
@@ -217,6 +220,17 @@ struct BxDF {
                        std::fabs(distrib.d(wh) * distrib.g(wo, wi) * eta * eta * abs_dot(wi, wh) * abs_dot(wo, wh) * factor * factor /
                                  (cos_thetai * cos_thetao * sqrt_denom * sqrt_denom));
             }
+            case BX_FRESNEL_BLEND: {  // reflection.rs:1167-1185
+                auto pow5 = [](Float v) { return (v * v) * (v * v) * v; };
+                Spectrum diffuse = r * (Spectrum(1.0f) - t) * (28.0f / (23.0f * PI)) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wi))) *
+                                   (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wo)));
+                V3 wh = wi + wo;
+                if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return Spectrum(0.0f);
+                wh = normalize(wh);
+                Spectrum schlick = t + (Spectrum(1.0f) - t) * pow5(1.0f - dot(wi, wh));  // schlick_fresnel, :1157-1161
+                Spectrum specular = schlick * (distrib.d(wh) / (4.0f * abs_dot(wi, wh) * std::fmax(abs_cos_theta(wi), abs_cos_theta(wo))));
+                return diffuse + specular;
+            }
         }
         return Spectrum(0.0f);
     }
@@ -239,6 +253,12 @@ struct BxDF {
                 Float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
                 Float dwh_dwi = std::fabs(eta * eta * dot(wi, wh)) / (sqrt_denom * sqrt_denom);
                 return distrib.pdf(wo, wh) * dwh_dwi;
+            }
+            case BX_FRESNEL_BLEND: {  // reflection.rs:1212-1218
+                if (!same_hemisphere(wo, wi)) return 0.0f;
+                V3 wh = normalize(wo + wi);
+                Float pdf_wh = distrib.pdf(wo, wh);
+                return 0.5f * (abs_cos_theta(wi) * INV_PI + pdf_wh / (4.0f * dot(wo, wh)));
             }
         }
         return 0.0f;
@@ -290,6 +310,20 @@ struct BxDF {
                 *pdf_ = 1.0f - F;
                 return ft / abs_cos_theta(*wi);
             }
+            case BX_FRESNEL_BLEND: {  // reflection.rs:1187-1210
+                if (u.x < 0.5f) {
+                    u.x = std::fmin(2.0f * u.x, ONE_MINUS_EPSILON);
+                    *wi = cosine_sample_hemisphere(u);
+                    if (wo.z < 0.0f) wi->z *= -1.0f;
+                } else {
+                    u.x = std::fmin(2.0f * (u.x - 0.5f), ONE_MINUS_EPSILON);
+                    V3 wh = distrib.sample_wh(wo, u);
+                    *wi = reflect(wo, wh);
+                    if (!same_hemisphere(wo, *wi)) return Spectrum(0.0f);
+                }
+                *pdf_ = pdf(wo, *wi);
+                return f(wo, *wi);
+            }
             case BX_MICRO_REFL: {  // reflection.rs:1005-1019
                 if (wo.z == 0.0f) return Spectrum(0.0f);
                 V3 wh = distrib.sample_wh(wo, u);
@@ -318,7 +352,7 @@ struct BSDF {
     Float eta = 1;
     V3 ns, ng, ss, ts;
     int n_bxdfs = 0;
-    BxDF bxdfs[2];
+    BxDF bxdfs[5];  // uber adds up to five (uber.rs:41-112)
     bool valid = false;  // si.bsdf is Some
 
     void init(const SurfaceInteraction& si, Float eta_) {  // BSDF::new

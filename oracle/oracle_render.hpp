@@ -6,6 +6,7 @@
 #include <atomic>
 #include <mutex>
 #include "oracle_reflection.hpp"
+#include "oracle_texture.hpp"
 #include "oracle_sampling.hpp"
 
 namespace orc {
@@ -52,8 +53,6 @@ struct Distribution2D {
     }
 };
 
-inline Float spherical_theta(V3 v) { return std::acos(clamp(v.z, -1.0f, 1.0f)); }                        // geometry.rs:40-43
-inline Float spherical_phi(V3 v) { Float p = std::atan2(v.y, v.x); return p < 0.0f ? p + 2.0f * PI : p; }  // geometry.rs:45-54
 
 struct RenderScene : SceneView {
     V3 world_center; Float world_radius = 0;   // Light::preprocess (distant.rs:53-60, infinite.rs:104-111)
@@ -476,7 +475,8 @@ inline Spectrum path_li(const RenderScene& s, const IntegratorParams& ip, Ray ra
         if (!found || bounces >= ip.max_depth) break;
         BSDF bsdf;
         int mat = s.d.prims[h.slot].material;
-        if (mat >= 0) compute_scattering_functions(s.d.materials[mat], isect, &bsdf);
+        (void)mat;
+        scattering_functions(s, ray, h.slot, isect, &bsdf, true);  // isect.compute_scattering_functions(&ray, ..), path.rs:123
         if (!bsdf.valid) {  // path.rs:124-129
             ray = spawn_ray(isect.p, isect.p_error, isect.n, ray.d, isect.time);
             continue;
@@ -511,11 +511,14 @@ inline Spectrum path_li(const RenderScene& s, const IntegratorParams& ip, Ray ra
     return L;
 }
 
-// PerspectiveCamera::generate_ray_differential (main ray only), src/cameras/perspective.rs:120-179
-inline Ray generate_ray(const pbrt_b200_camera& c, const CameraSample& cs) {
+// PerspectiveCamera::generate_ray_differential, src/cameras/perspective.rs:120-179; dx_camera / dy_camera :64-70.
+// `spp` > 0 applies Ray::scale_differential(1 / sqrt(spp)) the way the render loop does (integrator.rs:341, ray.rs:34-41).
+inline Ray generate_ray(const pbrt_b200_camera& c, const CameraSample& cs, uint32_t spp = 0) {
     M4 r2c = m4_from(c.raster_to_camera), c2w = m4_from(c.camera_to_world);
     V3 pcamera = m4_point(r2c, V3(cs.pfilm.x, cs.pfilm.y, 0.0f));
     Ray r(V3(0, 0, 0), normalize(pcamera), INFINITY_F, 0.0f);
+    V3 p2t = m4_point(r2c, V3(0, 0, 0));
+    V3 dx_camera = m4_point(r2c, V3(1, 0, 0)) - p2t, dy_camera = m4_point(r2c, V3(0, 1, 0)) - p2t;
     if (c.lens_radius > 0.0f) {
         P2 pl = concentric_sample_disk(cs.plens);
         pl = P2(pl.x * c.lens_radius, pl.y * c.lens_radius);
@@ -523,9 +526,32 @@ inline Ray generate_ray(const pbrt_b200_camera& c, const CameraSample& cs) {
         V3 pfocus = r.o + r.d * ft;
         r.o = V3(pl.x, pl.y, 0.0f);
         r.d = normalize(pfocus - r.o);
+        V3 dx = normalize(pcamera + dx_camera);
+        ft = c.focal_distance / dx.z;
+        pfocus = V3(0, 0, 0) + dx * ft;
+        r.rxo = V3(pl.x, pl.y, 0.0f);
+        r.rxd = normalize(pfocus - r.rxo);
+        V3 dy = normalize(pcamera + dy_camera);
+        ft = c.focal_distance / dy.z;
+        pfocus = V3(0, 0, 0) + dy * ft;
+        r.ryo = V3(pl.x, pl.y, 0.0f);
+        r.ryd = normalize(pfocus - r.ryo);
+    } else {
+        r.rxo = r.o; r.ryo = r.o;
+        r.rxd = normalize(pcamera + dx_camera);
+        r.ryd = normalize(pcamera + dy_camera);
     }
     r.time = lerp(cs.time, c.shutter_open, c.shutter_close);
-    return m4_ray(c2w, r);
+    Ray w = m4_ray(c2w, r);  // Transform::transform_ray carries the differentials over (transform.rs:562-572)
+    w.has_diff = true;
+    w.rxo = m4_point(c2w, r.rxo); w.ryo = m4_point(c2w, r.ryo);
+    w.rxd = m4_vector(c2w, r.rxd); w.ryd = m4_vector(c2w, r.ryd);
+    if (spp > 0) {
+        Float sc = 1.0f / std::sqrt((Float)spp);
+        w.rxo = w.o + (w.rxo - w.o) * sc; w.ryo = w.o + (w.ryo - w.o) * sc;
+        w.rxd = w.d + (w.rxd - w.d) * sc; w.ryd = w.d + (w.ryd - w.d) * sc;
+    }
+    return w;
 }
 
 // FilmTile::add_sample, src/core/film.rs:292-331, accumulating straight into the film-sized
@@ -603,7 +629,8 @@ inline Spectrum recursive_li(const RenderScene& s, const IntegratorParams& ip, R
     SurfaceInteraction isect = make_interaction(s, r0, h);
     BSDF bsdf;
     int mat = s.d.prims[h.slot].material;
-    if (mat >= 0) compute_scattering_functions(s.d.materials[mat], isect, &bsdf, false);
+    (void)mat;
+    scattering_functions(s, ray, h.slot, isect, &bsdf, false);
     if (!bsdf.valid) return recursive_li(s, ip, spawn_ray(isect.p, isect.p_error, isect.n, ray.d, isect.time), sampler, rc, depth);
     V3 wo = isect.wo;
     L += surface_le(s, isect, wo);
@@ -639,6 +666,28 @@ inline Spectrum recursive_li(const RenderScene& s, const IntegratorParams& ip, R
             Spectrum f = bsdf.sample_f(wo, &wi, sampler.get_2d(), &pdf, (pass == 0 ? BSDF_REFLECTION : BSDF_TRANSMISSION) | BSDF_SPECULAR, &st);
             if (pdf > 0.0f && !f.is_black() && abs_dot(wi, isect.sh_n) != 0.0f) {
                 Ray rd = spawn_ray(isect.p, isect.p_error, isect.n, wi, isect.time);
+                if (ray.has_diff) {  // `if let Some(ref diff) = r.diff`, integrator.rs:427-452 / 476-513
+                    V3 ns = isect.sh_n;
+                    rd.has_diff = true;
+                    rd.rxo = isect.p + isect.dpdx; rd.ryo = isect.p + isect.dpdy;
+                    V3 dndx = isect.sh_dndu * isect.dudx + isect.sh_dndv * isect.dvdx;
+                    V3 dndy = isect.sh_dndu * isect.dudy + isect.sh_dndv * isect.dvdy;
+                    V3 dwodx = -ray.rxd - wo, dwody = -ray.ryd - wo;
+                    Float ddndx = dot(dwodx, ns) + dot(wo, dndx), ddndy = dot(dwody, ns) + dot(wo, dndy);
+                    if (pass == 0) {
+                        rd.rxd = wi - dwodx + (dndx * dot(wo, ns) + ns * ddndx) * 2.0f;
+                        rd.ryd = wi - dwody + (dndy * dot(wo, ns) + ns * ddndy) * 2.0f;
+                    } else {
+                        Float eta = bsdf.eta;
+                        V3 w = -wo;
+                        if (dot(wo, ns) < 0.0f) eta = 1.0f / eta;  // (the reference inverts eta but does not negate ns, :493-497)
+                        Float mu = eta * dot(w, ns) - dot(wi, ns);
+                        Float dmudx = (eta - (eta * eta * dot(w, ns)) / dot(wi, ns)) * ddndx;
+                        Float dmudy = (eta - (eta * eta * dot(w, ns)) / dot(wi, ns)) * ddndy;
+                        rd.rxd = wi + dwodx * eta - (dndx * mu + ns * dmudx);
+                        rd.ryd = wi + dwody * eta - (dndy * mu + ns * dmudy);
+                    }
+                }
                 Spectrum Li = recursive_li(s, ip, rd, sampler, rc, depth + 1);
                 if (pass == 0) L += f * Li * abs_dot(wi, isect.sh_n) / pdf;
                 else L += f * Li * (abs_dot(wi, isect.sh_n) / pdf);
@@ -734,7 +783,7 @@ inline void render(const RenderJob& job, float* rgbw, int nthreads, RenderCounte
                     while (more) {
                         if (ts->current_pixel_sample_index >= s_end) break;
                         CameraSample cs = ts->get_camera_sample(x, y);
-                        Ray ray = generate_ray(rd.camera, cs);
+                        Ray ray = generate_ray(rd.camera, cs, rd.sampler.samples_per_pixel);
                         rc.camera_rays++;
                         Spectrum L = ipl.kind == PBRT_B200_INTEGRATOR_PATH ? path_li(job.scene, ipl, ray, *ts, rc)
                                      : ipl.kind == PBRT_B200_INTEGRATOR_VOLPATH ? volpath_li(job.scene, ipl, ray, rd.integrator.camera_medium, *ts, rc)

@@ -252,7 +252,8 @@ inline Spectrum volpath_li(const RenderScene& s, const IntegratorParams& ip, Ray
             if (!found || bounces >= max_depth) break;
             BSDF bsdf;
             int mat = s.d.prims[h.slot].material;
-            if (mat >= 0) compute_scattering_functions(s.d.materials[mat], isect, &bsdf);
+            (void)mat;
+            scattering_functions(s, ray.r, h.slot, isect, &bsdf, true);
             VolInterface mif = hit_interface(s, h.slot, ray.medium);
             if (!bsdf.valid) {  // volpath.rs:131-135
                 V3 d = ray.r.d;

@@ -26,13 +26,14 @@ import numpy as np
 from . import host as H
 from . import paramset as PS
 from . import spectrum as S
+from . import textures as TX
 from .host import B200Error, Transform
 
 f32 = np.float32
 
 KNOWN_MATERIALS = ("matte", "plastic", "fourier", "disney", "mirror", "glass", "hair", "translucent", "metal", "substrate", "subsurface",
                    "kdsubsurface", "uber", "mix")  # api.rs:601-639
-HOT_PATH_MATERIALS = ("matte", "plastic", "mirror", "glass", "metal")
+HOT_PATH_MATERIALS = ("matte", "plastic", "mirror", "glass", "metal", "uber", "substrate")
 KNOWN_SHAPES = ("sphere", "cylinder", "disk", "cone", "paraboloid", "hyperboloid", "curve", "trianglemesh", "plymesh", "heightfield", "loopsubdiv",
                 "nurbs")  # api.rs:562-585
 KNOWN_INTEGRATORS = ("whitted", "directlighting", "path", "volpath", "bdpt", "mlt", "ambientocclusion", "sppm")  # api.rs:277-289
@@ -294,33 +295,95 @@ class API:
         table = self.gs.float_textures if ty == "float" else self.gs.spectrum_textures
         if name in table:
             warnings.warn(f'Texture "{name}" being redefined')
-        if texname == "constant":  # textures/constant.rs:24-34
-            table[name] = tp.find_float("value", 1.0) if ty == "float" else tp.find_spectrum("value", 1.0)
-        elif texname == "scale":  # textures/scale.rs: tex1 * tex2, constant when both operands are
-            if ty == "float":
-                table[name] = f32(tp.get_floattexture("tex1", 1.0) * tp.get_floattexture("tex2", 1.0))
-            else:
-                table[name] = (tp.get_spectrumtexture("tex1", 1.0) * tp.get_spectrumtexture("tex2", 1.0)).astype(f32)
-        elif texname == "imagemap" and not os.path.isfile(tp.geo.find_one_filename("filename", "")):
-            # ImageTexture::get_texture, imagemap.rs:136-142: an image that cannot be read becomes a 1x1 grey (0.5) texture, converted
-            # like any texel (:71-98: inverse gamma for .png / .tga unless "gamma" says otherwise, times "scale") -- a constant
-            fn = tp.geo.find_one_filename("filename", "")
-            warnings.warn(f'Creating a constant grey texture to replace "{fn}".')
-            scale = tp.find_float("scale", 1.0)
-            gamma = tp.find_bool("gamma", fn.lower().endswith((".tga", ".png")))
-            g = f32(0.5)
-            if gamma:  # inverse_gamma_correct, pbrt.rs:218-222 (0.5 > 0.04045)
-                g = f32(np.power(f32(f32(g + f32(0.055)) * f32(1.0) / f32(1.055)), f32(2.4)))
-            # float textures convert the luminance of the grey texel (0.212671 + 0.715160 + 0.072169 = 1.0 in f32 here)
-            y = f32(f32(0.212671) * f32(0.5) + f32(0.715160) * f32(0.5) + f32(0.072169) * f32(0.5))
-            if ty == "float":
-                gy = f32(np.power(f32(f32(y + f32(0.055)) * f32(1.0) / f32(1.055)), f32(2.4))) if gamma else y
-                table[name] = f32(scale * gy)
-            else:
-                table[name] = np.full(3, g * scale, f32)
-        else:
-            table[name] = PS.UnsupportedTexture(name, texname)  # an error when a material refers to it
+        tex = self._make_texture(ty == "float", texname, tp)
+        if tex is not None:
+            table[name] = tex
         params.looked_up.update((b, n) for b in params.BUCKETS for n in getattr(params, b))
+
+    def _mapping2d(self, tp):  # get_mapping2d, texture.rs:433-463
+        ty = tp.find_string("mapping", "uv")
+        if ty == "uv":
+            return TX.Mapping2D.uv(tp.find_float("uscale", 1.0), tp.find_float("vscale", 1.0), tp.find_float("udelta", 0.0), tp.find_float("vdelta", 0.0))
+        if ty == "planar":
+            return TX.Mapping2D.planar(tp.find_vector3f("v1", (1.0, 0.0, 0.0)), tp.find_vector3f("v2", (0.0, 1.0, 0.0)), tp.find_float("udelta", 0.0),
+                                       tp.find_float("vdelta", 0.0))
+        if ty == "spherical":
+            return TX.Mapping2D.spherical(self.ctm.inverse())
+        if ty == "cylindrical":
+            return TX.Mapping2D.cylindrical(self.ctm.inverse())
+        self._error(f'2D texture mapping "{ty}" unknown')
+        return TX.Mapping2D.uv()
+
+    def _make_texture(self, is_float, texname, tp):
+        """make_float_texture / make_spectrum_texture, api.rs:656-704 -> constant (f32 scalar / RGB), textures.Tex, or None.
+        Constant operands fold (same f32 arithmetic the per-hit evaluation would do)."""
+        one = (lambda v: f32(v)) if is_float else (lambda v: np.full(3, v, f32))
+        get = tp.get_floattexture if is_float else tp.get_spectrumtexture
+        findv = tp.find_float if is_float else tp.find_spectrum
+        t2w = self.ctm  # IdentityMapping3D::new(t2w) keeps tex-to-world AS world_to_texture (fbm.rs:29, checkerboard.rs:135); 2D mappings invert it
+        if texname == "constant":  # textures/constant.rs:24-34
+            return findv("value", 1.0)
+        if texname == "scale":  # textures/scaled.rs:35-53
+            a, b = get("tex1", 1.0), get("tex2", 1.0)
+            if not TX.is_texture(a) and not TX.is_texture(b):
+                return f32(a * b) if is_float else (a * b).astype(f32)
+            return TX.Tex.scale(a, b)
+        if texname == "mix":  # textures/mix.rs:37-52
+            a, b, amt = get("tex1", 0.0), get("tex2", 1.0), tp.get_floattexture("amount", 0.5)
+            if not any(TX.is_texture(x) for x in (a, b, amt)):
+                r = np.asarray(a, f32) * f32(f32(1.0) - amt) + np.asarray(b, f32) * f32(amt)
+                return f32(r) if is_float else r.astype(f32)
+            return TX.Tex.mix(a, b, amt)
+        if texname == "bilerp":  # textures/biler.rs:38-55
+            m = self._mapping2d(tp)
+            return TX.Tex.bilerp(m, findv("v00", 0.0), findv("v01", 1.0), findv("v10", 0.0), findv("v11", 1.0))
+        if texname == "imagemap":  # textures/imagemap.rs:178-234
+            m = self._mapping2d(tp)
+            max_aniso, trilerp = tp.find_float("maxanisotropy", 8.0), tp.find_bool("trilinear", False)
+            wrap = tp.find_string("wrap", "repeat")
+            wrap = wrap if wrap in ("black", "clamp") else "repeat"
+            scale = tp.find_float("scale", 1.0)
+            fn = tp.find_filename("filename", "")
+            gamma = tp.find_bool("gamma", fn.lower().endswith((".tga", ".png")))
+            if not os.path.isfile(fn):
+                # ImageTexture::get_texture, imagemap.rs:136-142: an image that cannot be read becomes a 1x1 grey (0.5) texture, converted
+                # like any texel (:71-98).  Every lookup of a 1x1 pyramid returns that texel: the texture is folded into a constant
+                warnings.warn(f'Creating a constant grey texture to replace "{fn}".')
+                texel = TX.convert_texels(np.full((1, 1, 3), 0.5, f32), is_float, float(scale), gamma)[0, 0]
+                return f32(texel[0]) if is_float else texel.astype(f32)
+            mip = TX.image_mipmap(fn, is_float, trilerp, max_aniso, wrap, float(scale), gamma)
+            return TX.Tex.imagemap(m, mip)
+        if texname == "uv":  # textures/uv.rs:36-44
+            return None if is_float else TX.Tex.uv(self._mapping2d(tp))
+        if texname == "checkerboard":  # textures/checkerboard.rs:102-180 (the dimension is read from an INTEGER parameter called "mapping")
+            dim = tp.find_int("mapping", 2)
+            if dim not in (2, 3):
+                self._error(f"{dim} dimensional checkerboard texture not supported")
+                return None
+            a, b = get("tex1", 1.0), get("tex2", 0.0)
+            if dim == 3:
+                return TX.Tex.checkerboard3d(t2w, a, b)
+            m = self._mapping2d(tp)
+            aa = tp.find_string("aamode", "none")
+            if aa not in ("none", "closedform"):
+                warnings.warn(f'Antialiasing mode "{aa}" not understood by Checkerboard2DTexture; using "closedform"')
+                aa = "closedform"
+            return TX.Tex.checkerboard(m, a, b, aa)
+        if texname == "dots":  # textures/dots.rs:59-70: DotsTexture::new(map, inside, outside) fills (outside, inside) -- the two are swapped, kept
+            m = self._mapping2d(tp)
+            inside, outside = get("inside", 1.0), get("outside", 0.0)
+            return TX.Tex.dots(m, outside=inside, inside=outside)
+        if texname in ("fbm", "wrinkled"):  # textures/fbm.rs:30-44, wrinkled.rs:32-46
+            octaves, omega = tp.find_int("octaves", 8), tp.find_float("roughness", 0.5)
+            return (TX.Tex.fbm if texname == "fbm" else TX.Tex.wrinkled)(t2w, octaves, omega)
+        if texname == "marble":  # textures/marble.rs:78-82
+            if is_float:
+                return None
+            return TX.Tex.marble(t2w, tp.find_int("octaves", 8), tp.find_float("roughness", 0.5), tp.find_float("scale", 1.0), tp.find_float("variation", 0.2))
+        if texname == "windy":  # textures/windy.rs:30-41
+            return TX.Tex.windy(t2w)
+        warnings.warn(f'{"Float" if is_float else "Spectrum"} texture "{texname}" unknown.')
+        return None
 
     # --- materials (api.rs:595-654,1391-1460; src/materials/*.rs create_*) ----------------------------
     def _make_material(self, name, mp):
@@ -331,31 +394,53 @@ class API:
             warnings.warn(f'Material "{name}" unknown. Using "matte".')
             name = "matte"
         if name not in HOT_PATH_MATERIALS:
-            raise B200Error(f'Material "{name}" is outside the PathIntegrator hot path (matte, plastic, mirror, glass, metal; SURVEY.md §8 f3)')
-        if mp.get_floattexture_ornull("bumpmap") is not None:
-            raise B200Error("bump mapping is outside the hot path (SURVEY.md §8 f3)")
+            raise B200Error(f'Material "{name}" is outside the device path (matte, plastic, mirror, glass, metal, uber, substrate; SURVEY.md §8 f3)')
         kw = {}
+
+        def keep(v):  # a constant stays a number, a texture tree stays a tree
+            return v if TX.is_texture(v) else (f32(v) if np.ndim(v) == 0 else v)
+
         if name == "matte":  # matte.rs:55-61
-            kw["Kd"], kw["sigma"] = mp.get_spectrumtexture("Kd", 0.5), mp.get_floattexture("sigma", 0.0)
+            kw["Kd"], kw["sigma"] = mp.get_spectrumtexture("Kd", 0.5), keep(mp.get_floattexture("sigma", 0.0))
         elif name == "plastic":  # plastic.rs:72-80
             kw["Kd"], kw["Ks"] = mp.get_spectrumtexture("Kd", 0.25), mp.get_spectrumtexture("Ks", 0.25)
-            kw["roughness"], kw["remaproughness"] = mp.get_floattexture("roughness", 0.1), mp.find_bool("remaproughness", True)
+            kw["roughness"] = keep(mp.get_floattexture("roughness", 0.1))
         elif name == "mirror":  # mirror.rs:44-49
             kw["Kr"] = mp.get_spectrumtexture("Kr", 0.9)
-        elif name == "glass":  # glass.rs:95-108
-            kw["Kr"], kw["Kt"] = mp.get_spectrumtexture("Kr", 1.0), mp.get_spectrumtexture("Kt", 1.0)
-            eta = mp.get_floattexture_ornull("eta")
-            kw["eta"] = f32(eta) if eta is not None else mp.get_floattexture("index", 1.5)
-            kw["uroughness"], kw["vroughness"] = mp.get_floattexture("uroughness", 0.0), mp.get_floattexture("vroughness", 0.0)
-            kw["remaproughness"] = mp.find_bool("remaproughness", True)
+        elif name in ("glass", "uber"):  # glass.rs:95-108, uber.rs:114-128
+            if name == "glass":
+                kw["Kr"], kw["Kt"] = mp.get_spectrumtexture("Kr", 1.0), mp.get_spectrumtexture("Kt", 1.0)
+            else:
+                kw["Kd"], kw["Ks"] = mp.get_spectrumtexture("Kd", 0.25), mp.get_spectrumtexture("Ks", 0.25)
+                kw["Kr"], kw["Kt"] = mp.get_spectrumtexture("Kr", 0.0), mp.get_spectrumtexture("Kt", 0.0)
+                kw["roughness"] = keep(mp.get_floattexture("roughness", 0.1))
+            if name == "glass":
+                eta = mp.get_floattexture_ornull("eta")
+                kw["eta"] = keep(eta) if eta is not None else keep(mp.get_floattexture("index", 1.5))
+                kw["uroughness"], kw["vroughness"] = keep(mp.get_floattexture("uroughness", 0.0)), keep(mp.get_floattexture("vroughness", 0.0))
+            else:
+                for key in ("uroughness", "vroughness"):
+                    v = mp.get_floattexture_ornull(key)
+                    if v is not None:
+                        kw[key] = keep(v)
+                eta = mp.get_floattexture_ornull("eta")
+                kw["eta"] = keep(eta) if eta is not None else keep(mp.get_floattexture("index", 1.5))
+                kw["opacity"] = mp.get_spectrumtexture("opacity", 1.0)
         elif name == "metal":  # metal.rs:115-125
             cn, ck = S.copper()
             kw["eta"], kw["k"] = mp.get_spectrumtexture("eta", cn), mp.get_spectrumtexture("k", ck)
-            kw["roughness"] = mp.get_floattexture("roughness", 0.01)
+            kw["roughness"] = keep(mp.get_floattexture("roughness", 0.01))
             for key in ("uroughness", "vroughness"):
                 v = mp.get_floattexture_ornull(key)
                 if v is not None:
-                    kw[key] = f32(v)
+                    kw[key] = keep(v)
+        elif name == "substrate":  # substrate.rs:64-71
+            kw["Kd"], kw["Ks"] = mp.get_spectrumtexture("Kd", 0.5), mp.get_spectrumtexture("Ks", 0.5)
+            kw["uroughness"], kw["vroughness"] = keep(mp.get_floattexture("uroughness", 0.1)), keep(mp.get_floattexture("vroughness", 0.1))
+        bump = mp.get_floattexture_ornull("bumpmap")
+        if bump is not None:
+            kw["bumpmap"] = bump
+        if name in ("plastic", "glass", "metal", "uber", "substrate"):
             kw["remaproughness"] = mp.find_bool("remaproughness", True)
         mp.report_unused()
         return H.SceneBuilder._mat_row(name, **kw)

@@ -259,6 +259,22 @@ __global__ void k_single_prim_last(const uint32_t* __restrict__ slots, uint32_t 
 
 namespace {
 
+// The uploader sizes its copies from the mipmap rows, so these are checked before anything is staged.
+int validate_mipmaps(const pbrt_b200_scene_desc* d) {
+    if (d->n_mipmaps && !d->mipmaps) return fail(PBRT_B200_ERR_INVALID, "scene_create: mipmaps is null");
+    if (d->n_mipmaps > 0x7fffffffull) return fail(PBRT_B200_ERR_INVALID, "scene_create: too many mipmaps");
+    for (uint64_t i = 0; i < d->n_mipmaps; ++i) {
+        const pbrt_b200_mipmap& m = d->mipmaps[i];
+        if (!m.texels || (m.channels != 1 && m.channels != 3) || m.width == 0 || m.height == 0 || (m.width & (m.width - 1)) || (m.height & (m.height - 1)) ||
+            m.wrap > PBRT_B200_WRAP_CLAMP)
+            return fail(PBRT_B200_ERR_INVALID, "scene_create: malformed mipmap (power-of-two level 0, 1 or 3 channels)");
+        uint32_t big = m.width > m.height ? m.width : m.height, levels = 1;
+        while (big > 1) { big >>= 1; levels += 1; }
+        if (m.n_levels != levels) return fail(PBRT_B200_ERR_INVALID, "scene_create: mipmap n_levels must be 1 + log2(max(width, height))");
+    }
+    return PBRT_B200_OK;
+}
+
 int validate(const pbrt_b200_scene_desc* d) {
     if (d->abi_version != PBRT_B200_ABI_VERSION) return fail(PBRT_B200_ERR_INVALID, "scene_create: abi_version mismatch");
     if (d->n_prims && !d->prims) return fail(PBRT_B200_ERR_INVALID, "scene_create: prims is null");
@@ -324,8 +340,44 @@ int validate(const pbrt_b200_scene_desc* d) {
             if (mi.inside < -1 || mi.outside < -1 || mi.inside >= (int64_t)d->n_media || mi.outside >= (int64_t)d->n_media)
                 return fail(PBRT_B200_ERR_INVALID, "scene_create: medium interface index out of range");
         }
-    for (uint64_t i = 0; i < d->n_materials; ++i)
-        if (d->materials[i].type > PBRT_B200_MAT_METAL) return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: material outside the hot path");
+    for (uint64_t i = 0; i < d->n_materials; ++i) {
+        const pbrt_b200_material& m = d->materials[i];
+        if (m.type > PBRT_B200_MAT_SUBSTRATE) return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: material outside the device path");
+        if (m.type > PBRT_B200_MAT_METAL && !m.textured) return fail(PBRT_B200_ERR_INVALID, "scene_create: uber / substrate rows keep their parameters in material_ext (textured = 1)");
+        if (m.textured && !d->material_ext) return fail(PBRT_B200_ERR_INVALID, "scene_create: a textured material without material_ext");
+    }
+    // textures: every program must be a well-formed postfix expression over existing nodes and images
+    if (d->n_textures && !d->textures) return fail(PBRT_B200_ERR_INVALID, "scene_create: textures is null");
+    if (d->n_textures > 0x7fffffffull) return fail(PBRT_B200_ERR_INVALID, "scene_create: too many textures");
+    for (uint64_t i = 0; i < d->n_textures; ++i) {
+        const pbrt_b200_texnode& n = d->textures[i];
+        if (n.kind > PBRT_B200_TEX_WINDY || n.mapping > PBRT_B200_MAP_PLANAR) return fail(PBRT_B200_ERR_INVALID, "scene_create: unknown texture kind / mapping");
+        if (n.kind == PBRT_B200_TEX_IMAGEMAP && n.image >= d->n_mipmaps) return fail(PBRT_B200_ERR_INVALID, "scene_create: texture image index out of range");
+    }
+    if (d->material_ext) {
+        auto check = [&](const pbrt_b200_texref& r) -> bool {  // stack discipline of one program
+            if (r.count == 0) return true;
+            if ((uint64_t)r.first + r.count > d->n_textures) return false;
+            int depth = 0;
+            for (uint32_t k = 0; k < r.count; ++k) {
+                const uint32_t kind = d->textures[r.first + k].kind;
+                const int pops = kind == PBRT_B200_TEX_MIX ? 3 : (kind == PBRT_B200_TEX_SCALE || kind == PBRT_B200_TEX_CHECKERBOARD2D || kind == PBRT_B200_TEX_CHECKERBOARD3D ||
+                                                                  kind == PBRT_B200_TEX_DOTS) ? 2 : 0;
+                if (depth < pops) return false;
+                depth += 1 - pops;
+                if (depth > 8) return false;  // PB_TEX_STACK
+            }
+            return depth == 1;
+        };
+        for (uint64_t i = 0; i < d->n_materials; ++i) {
+            if (!d->materials[i].textured) continue;
+            const pbrt_b200_material_ext& x = d->material_ext[i];
+            bool ok = check(x.bump);
+            for (int k = 0; k < 5; ++k) ok = ok && check(x.s_tex[k]);
+            for (int k = 0; k < 3; ++k) ok = ok && check(x.f_tex[k]);
+            if (!ok) return fail(PBRT_B200_ERR_INVALID, "scene_create: malformed texture program (range, operand count or more than 8 stacked operands)");
+        }
+    }
     for (uint64_t i = 0; i < d->n_lights; ++i) {
         const pbrt_b200_light& l = d->lights[i];
         if (l.type > PBRT_B200_LIGHT_INFINITE) return fail(PBRT_B200_ERR_UNSUPPORTED, "scene_create: light type outside the hot path");
@@ -424,6 +476,7 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     if (d->abi_version != PBRT_B200_ABI_VERSION) return fail(PBRT_B200_ERR_INVALID, "scene_create: abi_version mismatch");
     if (d->n_prims && !d->prims) return fail(PBRT_B200_ERR_INVALID, "scene_create: prims is null");
     if (d->n_nodes && !d->nodes) return fail(PBRT_B200_ERR_INVALID, "scene_create: nodes is null");
+    if (int rcm = validate_mipmaps(d)) return rcm;
     // The table checks (index ranges, BVH structure and depth: ~10 ms for 10^6 primitives) run on two worker threads
     // while this thread stages the tables into HBM; nothing on the device dereferences an index before they have passed.
     int rc = PBRT_B200_OK, rc_v = PBRT_B200_OK, rc_n = PBRT_B200_OK;
@@ -459,6 +512,14 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     add(sizeof(DevInstance) * d->n_instances); add(4ull * d->n_objects); add(sizeof(DevScene));
     add(d->vertex_n ? 48ull * np : 0); add(d->vertex_uv ? 24ull * np : 0); add(96ull * d->n_lights);  // slot_n, slot_uv, light_tris
     add(sizeof(pbrt_b200_medium) * d->n_media); add(d->prim_media ? sizeof(pbrt_b200_medium_interface) * np : 0);
+    auto mip_floats = [](const pbrt_b200_mipmap& m) {
+        size_t n = 0;
+        for (uint32_t l = 0; l < m.n_levels; ++l) n += (size_t)std::max(1u, m.width >> l) * std::max(1u, m.height >> l) * m.channels;
+        return n;
+    };
+    add(sizeof(pbrt_b200_texnode) * d->n_textures); add(sizeof(pbrt_b200_mipmap) * d->n_mipmaps);
+    add(d->material_ext ? sizeof(pbrt_b200_material_ext) * d->n_materials : 0);
+    for (uint64_t i = 0; i < d->n_mipmaps; ++i) add(4 * mip_floats(d->mipmaps[i]));
     const size_t resident = need;
     add(sizeof(pbrt_b200_bvh_node) * nn); add(4ull * nn); add(4ull * nb);
     need += 4096;
@@ -523,6 +584,17 @@ extern "C" int pbrt_b200_scene_create(const pbrt_b200_scene_desc* d, int device,
     up(d->media, sizeof(pbrt_b200_medium) * d->n_media, &ds.media);
     up(d->prim_media, d->prim_media ? sizeof(pbrt_b200_medium_interface) * np : 0, &ds.prim_media);
     ds.n_media = (uint32_t)d->n_media;
+    up(d->textures, sizeof(pbrt_b200_texnode) * d->n_textures, &ds.textures);
+    up(d->material_ext, d->material_ext ? sizeof(pbrt_b200_material_ext) * d->n_materials : 0, &ds.material_ext);
+    ds.n_textures = (uint32_t)d->n_textures; ds.n_mipmaps = (uint32_t)d->n_mipmaps;
+    std::vector<pbrt_b200_mipmap> mips(d->mipmaps, d->mipmaps + d->n_mipmaps);  // rows with their texel pointers moved to the device
+    for (auto& m : mips) {
+        const float* dev_texels = nullptr;
+        up(m.texels, 4 * mip_floats(m), &dev_texels);
+        m.texels = dev_texels;
+    }
+    up(mips.data(), sizeof(pbrt_b200_mipmap) * mips.size(), &ds.mipmaps);
+    if (err == cudaSuccess && !mips.empty()) err = cudaStreamSynchronize(stream);  // `mips` is a local: its copy must have been read
     lap("h2d staged");
     if ((rc = join_checks())) { pbrt_b200_scene_destroy(sc); return rc; }
     lap("checks joined");

@@ -108,8 +108,8 @@ template <> struct RecSampler<true> {
 
 // estimate_direct (integrator.rs:109-237, handle_media = false, specular = false): the light-sampled half becomes a
 // shadow entry, the BSDF-sampled half a MIS entry; `scale` = 1 / (light selection pdf).
-template <bool INST>
-PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, const Bsdf& bsdf, uint32_t ln, float2 ulight, float2 uscatt, rgb beta,
+template <bool INST, int KM = KM_ALL, class B>
+PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, const B& bsdf, uint32_t ln, float2 ulight, float2 uscatt, rgb beta,
                               float inv_selpdf, float time) {
     const int NONSPEC = BX_ALL & ~BX_SPECULAR;
     const pbrt_b200_light& light = R.scene.lights[ln];
@@ -118,8 +118,8 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
     light_sample_li<INST>(R, ln, si.p, ulight, ls, si.p_error, si.n);
     float scattpdf = 0.0f;
     if (ls.pdf > 0.0f && !is_black(ls.Li)) {
-        rgb f = bsdf_f<KM_ALL>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
-        scattpdf = bsdf_pdf<KM_ALL>(bsdf, si.wo, ls.wi, NONSPEC);
+        rgb f = bsdf_f<KM>(bsdf, si.wo, ls.wi, NONSPEC) * absdot(ls.wi, si.sh_n);
+        scattpdf = bsdf_pdf<KM>(bsdf, si.wo, ls.wi, NONSPEC);
         if (!is_black(f)) {
             f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
             f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
@@ -133,7 +133,7 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
     if (!delta) {
         f3 wi(0.f, 0.f, 0.f);
         int stype = 0;
-        rgb f = bsdf_sample<KM_ALL>(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
+        rgb f = bsdf_sample<KM>(bsdf, si.wo, &wi, uscatt, &scattpdf, NONSPEC, &stype);
         f = f * absdot(wi, si.sh_n);
         if (!is_black(f) && scattpdf > 0.0f) {
             float weight = 1.0f;
@@ -157,8 +157,12 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
 
 // One step of the depth-first recursion for every live camera sample: shade the hit of its current ray.
 #if !PB_EXACT_TU
-template <bool INST, bool ZT>
+// TEX: the scene has textured materials (texture.cuh) -- every surface then gets its full interaction and its ray differentials
+// (compute_scattering_functions always runs compute_differentials, interaction.rs:258-267), and specular_reflect / specular_transmit
+// hand differentials on to the rays they spawn (integrator.rs:427-452, 476-513).
+template <bool INST, bool ZT, bool TEX>
 __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
+    constexpr int KM = TEX ? KM_TEX : KM_ALL;
     const uint32_t n = R.cnt->n_path;
     const uint32_t* q = R.q_path[parity];
     uint32_t* q_next = R.q_path[parity ^ 1];
@@ -175,6 +179,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
             float4 bs = R.beta_st[id];
             rgb beta(bs.x, bs.y, bs.z), Ladd(0.0f);
             uint32_t depth = __float_as_uint(bs.w) & 0xffffu;
+            bool has_diff = TEX && (__float_as_uint(bs.w) & PB_ST_HAS_DIFF) != 0u;
             RecSampler<ZT> smp;
             smp.begin(R, id);
             uint32_t sp = R.rec.sp[id];
@@ -188,14 +193,28 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                 uint4 h = R.hit[id];
                 uint32_t fl;
                 const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
-                Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
+                Surf si;
+                SurfX sx;
+                RayDiff rdf;
+                rdf.has = false;
+                if (TEX) {
+                    surface_full(R.scene.self_dev, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &si, &sx, &fl);
+                    rdf = load_diff(R.rdiff, id, has_diff);
+                } else si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
                 const pbrt_b200_prim pr = R.scene.prims[h.x];
-                Bsdf bsdf;
+                BsdfN<TEX ? 5 : 2> bsdf;
                 bsdf.valid = false;
-                if (pr.material >= 0) material_bsdf<-1, false>(R.scene.materials[pr.material], si, bsdf);
+                if (pr.material >= 0) {
+                    if (TEX && R.scene.materials[pr.material].textured) material_bsdf_tex<false>(R.scene.self_dev, pr.material, &si, &sx, &rdf, &bsdf);
+                    else {
+                        if (TEX) compute_differentials(si, sx, rdf);
+                        material_bsdf<-1, false>(R.scene.materials[pr.material], si, bsdf);
+                    }
+                }
                 if (!bsdf.valid) {  // same depth, nothing drawn from the sampler (whitted.rs:76-80, directlighting.rs:91-94)
                     f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
                     store_ray(R.ray, id, o, rd, PB_INF, time);
+                    has_diff = false;  // spawn_ray: no differentials
                     push_next = true;
                 } else {
                     if (pr.area_light >= 0) {  // isect.le(wo)
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                             LightSample ls;
                             light_sample_li<INST>(R, li, si.p, u, ls, si.p_error, si.n);
                             if (is_black(ls.Li) || ls.pdf == 0.0f) continue;
-                            rgb f = bsdf_f<KM_ALL>(bsdf, si.wo, ls.wi, BX_ALL);
+                            rgb f = bsdf_f<KM>(bsdf, si.wo, ls.wi, BX_ALL);
                             if (is_black(f)) continue;
                             f3 o = offset_ray_origin(si.p, si.p_error, si.n, ls.p1 - si.p);
                             f3 tg = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, o - ls.p1);
@@ -230,19 +249,19 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                                         for (uint32_t k = 0; k < ns; ++k) {
                                             ulight = smp.array_element(R, a0, sn, ns, k);
                                             uscatt = smp.array_element(R, a0 + 1u, sn, ns, k);
-                                            rec_estimate_direct<INST>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f / (float)ns, time);
+                                            rec_estimate_direct<INST, KM>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f / (float)ns, time);
                                         }
                                         continue;
                                     }
                                     smp.arr = R.rec.n_arrays;  // requests exhausted: get_2d_array returns None from here on
                                     ulight = smp.get_2d(R); uscatt = smp.get_2d(R);
-                                    rec_estimate_direct<INST>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f, time);
+                                    rec_estimate_direct<INST, KM>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f, time);
                                     continue;
                                 }
                                 bool hl = smp.get_2d_array(R, &ulight);
                                 bool hs = smp.get_2d_array(R, &uscatt);
                                 if (!hl || !hs) { ulight = smp.get_2d(R); uscatt = smp.get_2d(R); }
-                                rec_estimate_direct<INST>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f, time);
+                                rec_estimate_direct<INST, KM>(R, id, si, bsdf, li, ulight, uscatt, beta, 1.0f, time);
                             }
                         } else {  // uniform_sample_onelight without a distribution, integrator.rs:81-106
                             float u1 = smp.get_1d(R);
@@ -252,7 +271,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                             float lightpdf = 1.0f / (float)nl;
                             float2 ulight = smp.get_2d(R);
                             float2 uscatt = smp.get_2d(R);
-                            rec_estimate_direct<INST>(R, id, si, bsdf, ln, ulight, uscatt, beta, 1.0f / lightpdf, time);
+                            rec_estimate_direct<INST, KM>(R, id, si, bsdf, ln, ulight, uscatt, beta, 1.0f / lightpdf, time);
                         }
                     }
                     pop = true;
@@ -262,33 +281,60 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                         f3 wir(0.f, 0.f, 0.f), wit(0.f, 0.f, 0.f);
                         float pdfr = 0.0f, pdft = 0.0f;
                         int st = 0;
-                        rgb fr = bsdf_sample<KM_ALL>(bsdf, si.wo, &wir, ur, &pdfr, BX_REFLECTION | BX_SPECULAR, &st);
+                        rgb fr = bsdf_sample<KM>(bsdf, si.wo, &wir, ur, &pdfr, BX_REFLECTION | BX_SPECULAR, &st);
                         const bool okr = pdfr > 0.0f && !is_black(fr) && absdot(wir, si.sh_n) != 0.0f;
                         // specular_transmit (integrator.rs:457-520): a specular lobe ignores its sample, so the direction and
                         // weight are known now; the two dimensions are drawn when the reference draws them (after the
                         // reflection sub-tree)
-                        rgb ft = bsdf_sample<KM_ALL>(bsdf, si.wo, &wit, make_float2(0.0f, 0.0f), &pdft, BX_TRANSMISSION | BX_SPECULAR, &st);
-                        const bool okt = pdft > 0.0f && !is_black(ft) && absdot(wit, si.sh_n) != 0.0f;
+                        rgb ft = bsdf_sample<KM>(bsdf, si.wo, &wit, make_float2(0.0f, 0.0f), &pdft, BX_TRANSMISSION | BX_SPECULAR, &st);
+                        bool okt = pdft > 0.0f && !is_black(ft) && absdot(wit, si.sh_n) != 0.0f;
                         rgb beta_t = okt ? beta * (ft * (absdot(wit, si.sh_n) / pdft)) : rgb(0.0f);
                         f3 ot = okt ? offset_ray_origin(si.p, si.p_error, si.n, wit) : f3(0.f, 0.f, 0.f);
+                        // uber with partial opacity holds TWO specular transmission lobes (uber.rs:52-56,102-106): the sample's first
+                        // dimension picks one (BSDF::sample_f), so both candidates are prepared and the choice is made when the sample is drawn
+                        const bool two = TEX && bsdf_count(bsdf, BX_TRANSMISSION | BX_SPECULAR) == 2;
+                        f3 wit2(0.f, 0.f, 0.f), ot2(0.f, 0.f, 0.f);
+                        rgb beta_t2(0.0f);
+                        bool okt2 = false;
+                        if (two) {
+                            float pdf2 = 0.0f;
+                            rgb ft2 = bsdf_sample<KM>(bsdf, si.wo, &wit2, make_float2(0.75f, 0.0f), &pdf2, BX_TRANSMISSION | BX_SPECULAR, &st);
+                            okt2 = pdf2 > 0.0f && !is_black(ft2) && absdot(wit2, si.sh_n) != 0.0f;
+                            if (okt2) { beta_t2 = beta * (ft2 * (absdot(wit2, si.sh_n) / pdf2)); ot2 = offset_ray_origin(si.p, si.p_error, si.n, wit2); }
+                        }
+                        const size_t FS = (size_t)R.capacity * D;  // second-candidate frames live one stack array further
+                        // a spawned ray has differentials iff its parent has (`if let Some(ref diff) = r.diff`)
                         if (okr) {
                             if (sp < D) {
                                 const size_t fi = (size_t)id * D + sp;
                                 R.rec.st_ray[2 * fi] = make_float4(ot.x, ot.y, ot.z, okt ? 1.0f : 0.0f);
                                 R.rec.st_ray[2 * fi + 1] = make_float4(wit.x, wit.y, wit.z, time);
-                                R.rec.st_beta[fi] = make_float4(beta_t.r, beta_t.g, beta_t.b, __uint_as_float(depth + 1u));
+                                R.rec.st_beta[fi] = make_float4(beta_t.r, beta_t.g, beta_t.b,
+                                                                __uint_as_float((depth + 1u) | (has_diff ? PB_ST_HAS_DIFF : 0u) | (two ? PB_ST_TWO_LOBES : 0u)));
+                                if (TEX && has_diff && okt) store_diff(R.rec.st_diff, fi, specular_differentials(si, sx, rdf, si.wo, wit, bsdf.eta, true));
+                                if (two) {
+                                    R.rec.st_ray[2 * (fi + FS)] = make_float4(ot2.x, ot2.y, ot2.z, okt2 ? 1.0f : 0.0f);
+                                    R.rec.st_ray[2 * (fi + FS) + 1] = make_float4(wit2.x, wit2.y, wit2.z, time);
+                                    R.rec.st_beta[fi + FS] = make_float4(beta_t2.r, beta_t2.g, beta_t2.b, 0.0f);
+                                    if (has_diff && okt2) store_diff(R.rec.st_diff, fi + FS, specular_differentials(si, sx, rdf, si.wo, wit2, bsdf.eta, true));
+                                }
                                 sp += 1;
                             }
                             beta = beta * (fr * absdot(wir, si.sh_n) / pdfr);
                             f3 o = offset_ray_origin(si.p, si.p_error, si.n, wir);
                             store_ray(R.ray, id, o, wir, PB_INF, time);
+                            if (TEX && has_diff) store_diff(R.rdiff, id, specular_differentials(si, sx, rdf, si.wo, wir, bsdf.eta, false));
                             depth += 1;
                             push_next = true; pop = false;
                         } else {
-                            smp.skip_2d(R);  // specular_transmit's get_2d
+                            if (two) {  // specular_transmit's get_2d: its first dimension picks the lobe
+                                const float2 u2 = smp.get_2d(R);
+                                if (floorf(u2.x * 2.0f) >= 1.0f) { okt = okt2; beta_t = beta_t2; ot = ot2; wit = wit2; }
+                            } else smp.skip_2d(R);
                             if (okt) {
                                 beta = beta_t;
                                 store_ray(R.ray, id, ot, wit, PB_INF, time);
+                                if (TEX && has_diff) store_diff(R.rdiff, id, specular_differentials(si, sx, rdf, si.wo, wit, bsdf.eta, true));
                                 depth += 1;
                                 push_next = true; pop = false;
                             }
@@ -302,19 +348,31 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
                     sp -= 1;
                     const size_t fi = (size_t)id * D + sp;
                     float4 a = R.rec.st_ray[2 * fi], b = R.rec.st_ray[2 * fi + 1], w = R.rec.st_beta[fi];
-                    smp.skip_2d(R);
+                    const uint32_t wbits = __float_as_uint(w.w);
+                    size_t fsel = fi;
+                    if (TEX && (wbits & PB_ST_TWO_LOBES)) {
+                        const float2 u2 = smp.get_2d(R);
+                        if (floorf(u2.x * 2.0f) >= 1.0f) {
+                            fsel = fi + (size_t)R.capacity * D;
+                            a = R.rec.st_ray[2 * fsel]; b = R.rec.st_ray[2 * fsel + 1];
+                            const float4 w2 = R.rec.st_beta[fsel];
+                            w.x = w2.x; w.y = w2.y; w.z = w2.z;
+                        }
+                    } else smp.skip_2d(R);
                     if (a.w != 0.0f) {
                         R.ray[2 * id] = make_float4(a.x, a.y, a.z, PB_INF);
                         R.ray[2 * id + 1] = b;
                         beta = rgb(w.x, w.y, w.z);
-                        depth = __float_as_uint(w.w);
+                        depth = __float_as_uint(w.w) & 0xffffu;
+                        has_diff = TEX && (__float_as_uint(w.w) & PB_ST_HAS_DIFF) != 0u;
+                        if (has_diff) { R.rdiff[3 * (size_t)id] = R.rec.st_diff[3 * fsel]; R.rdiff[3 * (size_t)id + 1] = R.rec.st_diff[3 * fsel + 1]; R.rdiff[3 * (size_t)id + 2] = R.rec.st_diff[3 * fsel + 2]; }
                         push_next = true;
                     }
                 }
                 if (!push_next) push_dead = true;
             }
             if (!is_black(Ladd)) rec_atomic_add(R.L_eta, id, Ladd);
-            R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(depth));
+            R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(depth | (has_diff ? PB_ST_HAS_DIFF : 0u)));
             smp.end(R, id);
             R.rec.sp[id] = sp;
         }

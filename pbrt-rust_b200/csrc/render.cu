@@ -25,6 +25,7 @@
 #include "scene.cuh"
 #include "shading.cuh"
 #include "trace.cuh"
+#include "texture.cuh"
 #include "util.cuh"
 
 // occupancy knobs (min resident CTAs per SM in __launch_bounds__), A/B-measured with tools/step_diag.py on S3: shade 5/6/8 CTAs
@@ -66,7 +67,9 @@ using namespace pb;
 
 namespace pb {
 
-enum { Q_MATTE = 0, Q_PLASTIC = 1, Q_MIRROR = 2, Q_GLASS = 3, Q_METAL = 4, Q_NOMAT = 5, Q_MISS = 6, Q_COUNT = 7 };
+enum { Q_MATTE = 0, Q_PLASTIC = 1, Q_MIRROR = 2, Q_GLASS = 3, Q_METAL = 4, Q_NOMAT = 5, Q_MISS = 6,
+       Q_TEX = 7,  // `textured` material rows (texture.cuh): texture-valued parameters, bump maps, uber, substrate
+       Q_COUNT = 8 };
 
 struct Counters {
     uint32_t n_path;          // rays to trace this iteration
@@ -169,6 +172,7 @@ struct RecDev {
     float4* e_mis_ray;
     float4* e_mis_contrib;      // {rgb factor, light index bits}
     uint32_t* e_mis_slot;
+    float4* st_diff;            // [capacity * stack_depth * 3] ray differentials of the stacked rays (textured scenes only, else nullptr)
 };
 
 struct RenderDev {
@@ -221,6 +225,8 @@ struct RenderDev {
     int* sp_voxel;       // lazy SpatialLightDistribution: the voxel k_spatial_mark claimed for the slot's hit.  The shade kernels (fast-math
                          // translation unit) would otherwise recompute the hit point with different roundings and, on a voxel boundary,
                          // look up a voxel nobody built
+    float4* rdiff;       // 3 x float4 per slot: RayDifferential of the slot's ray (texture.cuh store_diff), valid while PB_ST_HAS_DIFF is set in
+                         // beta_st.w; nullptr unless the scene has textured materials
     float4* u8;          // 2 x float4 per slot: the next eight sample dimensions, written by k_sample_block when the Sobol' tables
                          // do not serve the path (Halton; dimensions beyond the tables); nullptr when that cannot happen
     uint32_t* q_path[2];
@@ -688,6 +694,43 @@ PB_D void generate_ray(const pbrt_b200_camera& c, float2 pfilm, float time_u, fl
     *o_out = ow; *d_out = dw;
 }
 
+#define PB_ST_TWO_LOBES 0x40000u /* a stacked specular_transmit frame with two candidate lobes (recursive.cuh) */
+#define PB_ST_HAS_DIFF 0x20000u /* beta_st.w: the slot's ray carries differentials (a camera ray, or a specular bounce of one under whitted / directlighting) */
+// The differential half of PerspectiveCamera::generate_ray_differential (cameras/perspective.rs:144-176; dx_camera / dy_camera :64-70),
+// then Ray::scale_differential(1 / sqrt(spp)) as the render loop applies it (integrator.rs:341, ray.rs:34-41).  o / d: the world ray.
+static __device__ __noinline__ void camera_differentials(const pbrt_b200_camera* cp, float2 pfilm, float2 plens, f3 o, f3 d, uint32_t spp, float4* out, size_t slot) {
+    const pbrt_b200_camera& c = *cp;
+    const f3 pc = xf_point(c.raster_to_camera, f3(pfilm.x, pfilm.y, 0.0f));
+    const f3 p2t = xf_point(c.raster_to_camera, f3(0.f, 0.f, 0.f));
+    const f3 dxc = xf_point(c.raster_to_camera, f3(1.f, 0.f, 0.f)) - p2t, dyc = xf_point(c.raster_to_camera, f3(0.f, 1.f, 0.f)) - p2t;
+    RayDiff r;
+    r.has = true;
+    if (c.lens_radius > 0.0f) {
+        float2 pl = concentric_disk(plens);
+        pl.x *= c.lens_radius; pl.y *= c.lens_radius;
+        f3 dx = normalize(pc + dxc);
+        float ft = c.focal_distance / dx.z;
+        f3 pfocus = dx * ft;
+        r.rxo = f3(pl.x, pl.y, 0.0f);
+        r.rxd = normalize(pfocus - r.rxo);
+        f3 dy = normalize(pc + dyc);
+        ft = c.focal_distance / dy.z;
+        pfocus = dy * ft;
+        r.ryo = f3(pl.x, pl.y, 0.0f);
+        r.ryd = normalize(pfocus - r.ryo);
+    } else {
+        r.rxo = r.ryo = f3(0.f, 0.f, 0.f);
+        r.rxd = normalize(pc + dxc);
+        r.ryd = normalize(pc + dyc);
+    }
+    r.rxo = xf_point(c.camera_to_world, r.rxo); r.ryo = xf_point(c.camera_to_world, r.ryo);
+    r.rxd = xf_vector(c.camera_to_world, r.rxd); r.ryd = xf_vector(c.camera_to_world, r.ryd);
+    const float sc = 1.0f / sqrtf((float)spp);
+    r.rxo = o + (r.rxo - o) * sc; r.ryo = o + (r.ryo - o) * sc;
+    r.rxd = d + (r.rxd - d) * sc; r.ryd = d + (r.ryd - d) * sc;
+    store_diff(out, slot, r);
+}
+
 #define PB_NO_SAMPLE 0xffffffffu /* R.pixel[slot]: the slot carries no camera sample (nothing to add to the film) */
 
 // Position t of the call's tile numbering (pbrt_b200_render_desc.tile_order) -> tile coordinates; false past the image edge.
@@ -785,7 +828,8 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     R.ray[2 * slot] = make_float4(o.x, o.y, o.z, PB_INF);
     R.ray[2 * slot + 1] = make_float4(d.x, d.y, d.z, time);
     R.L_eta[slot] = make_float4(0.f, 0.f, 0.f, 1.0f);
-    R.beta_st[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
+    R.beta_st[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(R.rdiff ? PB_ST_HAS_DIFF : 0u));
+    if (R.rdiff) camera_differentials(&R.camera, pfilm, plens, o, d, R.sampler.spp, R.rdiff, slot);
     R.pfilm[slot] = pfilm;
     R.s_index[slot] = c.index;
     R.s_dim[slot] = c.dim;
@@ -820,7 +864,8 @@ PB_D int store_closest_hit(const RenderDev& R, uint32_t id, const TravRay& r) {
     int bin = Q_MISS;
     if (r.found) {
         int m = R.scene.prims[r.hit.slot].material;
-        bin = m < 0 ? Q_NOMAT : (int)R.scene.materials[m].type;
+        if (m < 0) bin = Q_NOMAT;
+        else { const pbrt_b200_material& mr = R.scene.materials[m]; bin = mr.textured ? Q_TEX : (int)mr.type; }
     }
     R.hit_bin[id] = (uint8_t)bin;
     return bin;
@@ -1348,12 +1393,13 @@ PB_D void store_ray(float4* rays, uint32_t id, f3 o, f3 d, float t_max, float ti
     rays[2 * id + 1] = make_float4(d.x, d.y, d.z, time);
 }
 
-template <int BIN> struct BinKinds { static constexpr int KM = KM_ALL, MAT = -1; };
-template <> struct BinKinds<Q_MATTE> { static constexpr int KM = KM_MATTE, MAT = PBRT_B200_MAT_MATTE; };
-template <> struct BinKinds<Q_PLASTIC> { static constexpr int KM = KM_PLASTIC, MAT = PBRT_B200_MAT_PLASTIC; };
-template <> struct BinKinds<Q_MIRROR> { static constexpr int KM = KM_MIRROR, MAT = PBRT_B200_MAT_MIRROR; };
-template <> struct BinKinds<Q_GLASS> { static constexpr int KM = KM_GLASS, MAT = PBRT_B200_MAT_GLASS; };
-template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT = PBRT_B200_MAT_METAL; };
+template <int BIN> struct BinKinds { static constexpr int KM = KM_ALL, MAT = -1, NL = 2; };
+template <> struct BinKinds<Q_MATTE> { static constexpr int KM = KM_MATTE, MAT = PBRT_B200_MAT_MATTE, NL = 2; };
+template <> struct BinKinds<Q_PLASTIC> { static constexpr int KM = KM_PLASTIC, MAT = PBRT_B200_MAT_PLASTIC, NL = 2; };
+template <> struct BinKinds<Q_MIRROR> { static constexpr int KM = KM_MIRROR, MAT = PBRT_B200_MAT_MIRROR, NL = 2; };
+template <> struct BinKinds<Q_GLASS> { static constexpr int KM = KM_GLASS, MAT = PBRT_B200_MAT_GLASS, NL = 2; };
+template <> struct BinKinds<Q_METAL> { static constexpr int KM = KM_METAL, MAT = PBRT_B200_MAT_METAL, NL = 2; };
+template <> struct BinKinds<Q_TEX> { static constexpr int KM = KM_TEX, MAT = -1, NL = 5; };
 
 // One path of a material queue: PathIntegrator::li from the hit to the next ray (path.rs:104-214).  Shared by the wavefront
 // kernel k_shade and the tile-serial megakernel k_zt_mega.
@@ -1388,7 +1434,10 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id, VolState* vs = nullptr
         smp.prefetch(R, id);
         uint32_t fl;
         const uint32_t hinst = (INST && R.scene.n_instances) ? R.hit_inst[id] : PBRT_B200_NO_HIT;
-        Surf si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
+        Surf si;
+        SurfX sx;
+        if (BIN == Q_TEX) surface_full(R.scene.self_dev, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &si, &sx, &fl);
+        else si = surface_at_hit<INST>(R.scene, hinst, h.x, ro, rd, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), R.hit_b2[id], &fl);
         const pbrt_b200_prim pr = R.scene.prims[h.x];
         // SurfaceInteraction::le, interaction.rs:344-349 + AreaLight::l, diffuse.rs:68-75
         if ((bounces == 0 || specular_bounce) && pr.area_light >= 0) {
@@ -1401,14 +1450,19 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id, VolState* vs = nullptr
             R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
             push_dead = true;
         } else {
-            Bsdf bsdf;
+            BsdfN<BinKinds<BIN>::NL> bsdf;
             bsdf.valid = false;
-            if (BIN != Q_NOMAT && BIN != Q_MISS) material_bsdf<BinKinds<BIN>::MAT>(R.scene.materials[pr.material], si, bsdf);
+            if (BIN == Q_TEX) {
+                const RayDiff rdf = load_diff(R.rdiff, id, R.rdiff != nullptr && (st & PB_ST_HAS_DIFF) != 0u);
+                material_bsdf_tex<true>(R.scene.self_dev, pr.material, &si, &sx, &rdf, &bsdf);
+            } else if (BIN != Q_NOMAT && BIN != Q_MISS) material_bsdf<BinKinds<BIN>::MAT>(R.scene.materials[pr.material], si, bsdf);
             if (!bsdf.valid) {
                 // path.rs:124-129: skip the surface, bounces NOT incremented
                 f3 o = offset_ray_origin(si.p, si.p_error, si.n, rd);
                 store_ray(R.ray, id, o, rd, PB_INF, time);
                 R.L_eta[id] = make_float4(L.r, L.g, L.b, etascale);
+                if (!VOL && R.rdiff && (st & PB_ST_HAS_DIFF))  // the spawned ray has no differentials (interaction.rs:32-37)
+                    R.beta_st[id] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(st & ~PB_ST_HAS_DIFF));
                 if (VOL) {  // volpath.rs:131-135
                     vs->medium = vol_medium_for(vmi, si.n, rd);
                     bounces = (bounces - 1u) & 0xffffu;
@@ -1659,15 +1713,19 @@ static void launch_shade_family(const RenderDev& R, int parity, int grid_small, 
     k_shade<Q_GLASS, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
     k_shade<Q_METAL, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
     k_shade<Q_NOMAT, INST, false><<<grid_small, 128, 0, stream>>>(R, parity);
+    if (INST && R.scene.material_ext) k_shade<Q_TEX, true, false><<<grid_shade, 128, 0, stream>>>(R, parity);  // textured scenes run the full-featured family
 }
 void launch_shade_kernels(const RenderDev& R, int parity, bool full, int grid_small, int grid_shade, cudaStream_t stream) {
     if (full) launch_shade_family<true>(R, parity, grid_small, grid_shade, stream);
     else launch_shade_family<false>(R, parity, grid_small, grid_shade, stream);
 }
 void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int grid_shade, cudaStream_t stream) {
-    if (zt) k_rec_shade<true, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-    else if (full) k_rec_shade<true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-    else k_rec_shade<false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    if (R.scene.material_ext) {
+        if (zt) k_rec_shade<true, true, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+        else k_rec_shade<true, false, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+    } else if (zt) k_rec_shade<true, true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    else if (full) k_rec_shade<true, false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    else k_rec_shade<false, false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
 }
 }  // namespace pb (shade.o ends here)
 #endif  // !PB_EXACT_TU
@@ -1767,7 +1825,8 @@ PB_D bool zt_next_path(const RenderDev& R, uint32_t j, bool first) {
     R.ray[2 * j] = make_float4(o.x, o.y, o.z, PB_INF);
     R.ray[2 * j + 1] = make_float4(d.x, d.y, d.z, time);
     R.L_eta[j] = make_float4(0.f, 0.f, 0.f, 1.0f);
-    R.beta_st[j] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
+    R.beta_st[j] = make_float4(1.f, 1.f, 1.f, __uint_as_float(R.rdiff ? PB_ST_HAS_DIFF : 0u));
+    if (R.rdiff) camera_differentials(&R.camera, pfilm, plens, o, d, R.zt.spp, R.rdiff, j);
     R.pfilm[j] = pfilm;
     R.pixel[j] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
     if (R.rec.kind) { R.rec.sp[j] = 0; R.rec.arr[j] = 0; }
@@ -1875,6 +1934,7 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
                 case Q_GLASS: o = zt_shade<Q_GLASS, INST>(Rdev, j); break;
                 case Q_METAL: o = zt_shade<Q_METAL, INST>(Rdev, j); break;
                 case Q_NOMAT: o = zt_shade<Q_NOMAT, INST>(Rdev, j); break;
+                case Q_TEX: o = zt_shade<Q_TEX, INST>(Rdev, j); break;
                 default: o = zt_shade<Q_MISS, INST>(Rdev, j); break;
             }
             if (o.zero_rad) n_zero += 1;
@@ -2122,6 +2182,7 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
                 case Q_GLASS: o = vol_shade<Q_GLASS, INST>(Rdev, j, &vs); break;
                 case Q_METAL: o = vol_shade<Q_METAL, INST>(Rdev, j, &vs); break;
                 case Q_NOMAT: o = vol_shade<Q_NOMAT, INST>(Rdev, j, &vs); break;
+                case Q_TEX: o = vol_shade<Q_TEX, INST>(Rdev, j, &vs); break;
                 default: o = vol_shade<Q_MISS, INST>(Rdev, j, &vs); break;
             }
             if (o.zero_rad) n_zero += 1;
@@ -2230,7 +2291,9 @@ struct RenderBuffers {  // all path-state arrays and queues sub-allocated from O
     RenderDev dev;
     void* u8_block = nullptr;   // RenderDev::u8, allocated on first need (Halton, capped Sobol' tables)
     size_t u8_bytes = 0;
-    ~RenderBuffers() { pool_free(block, block_bytes); if (u8_block) pool_free(u8_block, u8_bytes); }
+    void* diff_block = nullptr; // RenderDev::rdiff, allocated on first need (scenes with textured materials)
+    size_t diff_bytes = 0;
+    ~RenderBuffers() { pool_free(block, block_bytes); if (u8_block) pool_free(u8_block, u8_bytes); if (diff_block) pool_free(diff_block, diff_bytes); }
 };
 
 // Resources that depend only on the DEVICE, shared by every scene rendered on it and kept for the life of the process:
@@ -2714,7 +2777,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         rec_eps = (uint32_t)std::max<unsigned long long>(tot, 1ull);
         if (rec_multi && zt) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting \"all\" with multi-sample lights needs the sobol or halton sampler");
     }
-    const size_t rec_per_slot = path_like ? 0 : 8 + (size_t)rd->integrator.max_depth * 48 + (size_t)rec_eps * (48 + 52);
+    const size_t rec_per_slot = path_like ? 0 : 8 + (size_t)rd->integrator.max_depth * (sc->dev.material_ext ? 2 * (48 + 48) : 48) + (size_t)rec_eps * (48 + 52);
     if (rec_per_slot) {
         const unsigned long long fit = (6ull << 30) / rec_per_slot;
         if (fit < 256) return fail(PBRT_B200_ERR_UNSUPPORTED, "render: too many lights for one whitted / directlighting \"all\" surface evaluation");
@@ -2725,7 +2788,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (vol) {
         int smc = 148, per_sm = 1;
         cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, sc->device);
-        if (sc->dev.n_instances || sc->dev.n_sphere_lights) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<true>, 64, 0);
+        if (sc->dev.n_instances || sc->dev.n_sphere_lights || sc->dev.material_ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<true>, 64, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<false>, 64, 0);
         const unsigned long long want = (total_items + 63ull) / 64ull;
         vol_grid = (int)std::max<unsigned long long>(1ull, std::min<unsigned long long>((unsigned long long)smc * (unsigned long long)std::max(per_sm, 1), want));
@@ -2808,16 +2871,19 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 return fail(PBRT_B200_ERR_UNSUPPORTED, "render: directlighting \"all\" needs more Sobol' dimensions than the 1024 the tables hold (the reference panics)");
         }
         const size_t c = capacity, e = c * rec_eps;
-        const size_t need = Arena::padded(4 * c) * 3 + Arena::padded(32 * c * rec.stack_depth) + Arena::padded(16 * c * rec.stack_depth) + Arena::padded(32 * e) * 2 +
-                            Arena::padded(16 * e) * 2 + Arena::padded(4 * e) + 4096;
+        const bool textured = sc->dev.material_ext != nullptr;
+        const size_t fr = textured ? 2 : 1;  // textured scenes: two candidate frames per stack level (uber's two specular transmission lobes)
+        const size_t need = Arena::padded(4 * c) * 3 + Arena::padded(32 * c * rec.stack_depth * fr) + Arena::padded(16 * c * rec.stack_depth * fr) + Arena::padded(32 * e) * 2 +
+                            Arena::padded(16 * e) * 2 + Arena::padded(4 * e) + (textured ? Arena::padded(48 * c * rec.stack_depth * fr) : 0) + 4096;
         rec_block = pool_alloc(need, &rec_bytes);
         if (!rec_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the recursion state");
         Arena A; A.base = reinterpret_cast<char*>(rec_block); A.size = rec_bytes;
         rec.sp = A.take<uint32_t>(c); rec.arr = A.take<uint32_t>(c); rec.sample_num = A.take<uint32_t>(c);
-        rec.st_ray = A.take<float4>(2 * c * rec.stack_depth); rec.st_beta = A.take<float4>(c * rec.stack_depth);
+        rec.st_ray = A.take<float4>(2 * c * rec.stack_depth * fr); rec.st_beta = A.take<float4>(c * rec.stack_depth * fr);
         rec.e_sh_ray = A.take<float4>(2 * e); rec.e_sh_contrib = A.take<float4>(e);
         rec.e_mis_ray = A.take<float4>(2 * e); rec.e_mis_contrib = A.take<float4>(e); rec.e_mis_slot = A.take<uint32_t>(e);
-        if (!rec.e_mis_slot) { pool_free(rec_block, rec_bytes); return fail(PBRT_B200_ERR_CUDA, "render: recursion arena too small (internal error)"); }
+        if (textured) rec.st_diff = A.take<float4>(3 * c * rec.stack_depth * fr);
+        if (!rec.e_mis_slot || (textured && !rec.st_diff)) { pool_free(rec_block, rec_bytes); return fail(PBRT_B200_ERR_CUDA, "render: recursion arena too small (internal error)"); }
     }
     ZtRelease rec_release{rec_block, rec_bytes};
     // film buffer: device pointer supplied, or a scratch film that is added back to the host buffer
@@ -2905,6 +2971,15 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         if (!rb->u8_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the sample blocks");
         R.u8 = reinterpret_cast<float4*>(rb->u8_block);
     }
+    R.rdiff = nullptr;
+    if (sc->dev.material_ext) {  // textured materials: every path slot carries its ray's differentials
+        RenderBuffers* rb = st->buffers;
+        const size_t need = (size_t)capacity * 48u;
+        if (rb->diff_block && rb->diff_bytes < need) { cudaDeviceSynchronize(); pool_free(rb->diff_block, rb->diff_bytes); rb->diff_block = nullptr; }
+        if (!rb->diff_block) rb->diff_block = pool_alloc(need, &rb->diff_bytes);
+        if (!rb->diff_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the ray differentials");
+        R.rdiff = reinterpret_cast<float4*>(rb->diff_block);
+    }
     PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
     if (st->sp_eager_pending) {  // every voxel's distribution, once per scene
         const uint32_t nv = (uint32_t)R.sp.nvox[0] * (uint32_t)R.sp.nvox[1] * (uint32_t)R.sp.nvox[2];
@@ -2923,7 +2998,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
             if (!rdev) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory");
             ZtRelease rdev_release{rdev, rdev_bytes};
             PB_CUDA_TRY(cudaMemcpyAsync(rdev, &R, sizeof(RenderDev), cudaMemcpyHostToDevice, stream));
-            if (sc->dev.n_instances || sc->dev.n_sphere_lights) k_vol_mega<true><<<vol_grid, 64, 0, stream>>>(R, rdev, total_items, rd->integrator.camera_medium);
+            if (sc->dev.n_instances || sc->dev.n_sphere_lights || sc->dev.material_ext) k_vol_mega<true><<<vol_grid, 64, 0, stream>>>(R, rdev, total_items, rd->integrator.camera_medium);
             else k_vol_mega<false><<<vol_grid, 64, 0, stream>>>(R, rdev, total_items, rd->integrator.camera_medium);
             launches += 1;
             PB_CUDA_TRY(cudaGetLastError());
@@ -2944,7 +3019,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         const bool drained_waves = !zt && capacity >= (1u << 22);
         unsigned long long iter = 0, batch = 0;
         const bool inst = sc->dev.n_instances != 0;                 // trace kernels: two-level walk
-        const bool full = inst || sc->dev.n_sphere_lights != 0;     // shade kernels: + instanced surfaces, sphere area lights
+        const bool full = inst || sc->dev.n_sphere_lights != 0 || sc->dev.material_ext != nullptr;  // shade kernels: + instanced surfaces, sphere area lights, textures
         // (0,2)-sequence + PathIntegrator: the whole call is one kernel, a thread per tile (k_zt_mega, always the full-featured
         // family: one instantiation); the recursive integrators keep the wavefront tile-serial form
         const bool zt_mega = zt && !R.rec.kind;

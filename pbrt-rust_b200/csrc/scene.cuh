@@ -83,6 +83,12 @@ struct DevScene {
     const pbrt_b200_medium* media;
     const pbrt_b200_medium_interface* prim_media;
     uint32_t n_media;
+    // Textures (texture.cuh): postfix programs, MIPMap pyramids (texel pointers are device pointers) and the parameter rows of the
+    // `textured` materials; all nullptr when the scene has none (render.cu then never launches a Q_TEX kernel)
+    const pbrt_b200_texnode* textures;
+    const pbrt_b200_mipmap* mipmaps;
+    const pbrt_b200_material_ext* material_ext;
+    uint32_t n_textures, n_mipmaps;
     // Scene::new preprocessing (scene.rs:32-52, distant.rs:53-60)
     float world_center[3];
     float world_radius;

@@ -317,7 +317,8 @@ PB_D f3 tr_sample_wh(TRDist t, f3 wo, float2 u) {
 // ---- lobes (closed set; BxDFType bits as in reflection.rs:181-190)
 enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16, BX_ALL = 31 };
 enum LobeKind { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR = 1, LOBE_MIRROR = 2, LOBE_FRESNEL_SPECULAR = 3, LOBE_MICRO_REFL_DIEL = 4, LOBE_MICRO_REFL_COND = 5, LOBE_MICRO_TRANS = 6,
-                LOBE_SPEC_REFL_DIEL = 7, LOBE_SPEC_TRANS = 8 };  // glass without allow_multiple_lobes (whitted / directlighting), glass.rs:69-84
+                LOBE_SPEC_REFL_DIEL = 7, LOBE_SPEC_TRANS = 8,  // glass without allow_multiple_lobes (whitted / directlighting), glass.rs:69-84; uber
+                LOBE_FRESNEL_BLEND = 9 };  // substrate (reflection.rs:1141-1222): c0 = Rd, c1 = Rs
 
 struct Lobe {
     int kind, type;
@@ -331,6 +332,7 @@ PB_D bool lobe_matches(const Lobe& l, int flags) { return (l.type & flags) == l.
 // KM = compile-time mask of the lobe kinds a material can produce (1 << LobeKind): the shade kernel of one
 // material bin carries only that material's BxDF code (smaller kernels, fewer registers); KM_ALL = generic.
 #define KM_ALL 0x1ff
+#define KM_TEX 0x3ff /* the texture-parameterised materials add uber's lobes and substrate's FresnelBlend (texture.cuh) */
 #define KM_HAS(k) ((KM & (1 << (k))) != 0)
 enum { KM_MATTE = (1 << LOBE_LAMBERT) | (1 << LOBE_OREN_NAYAR), KM_PLASTIC = (1 << LOBE_LAMBERT) | (1 << LOBE_MICRO_REFL_DIEL), KM_MIRROR = 1 << LOBE_MIRROR,
        KM_GLASS = (1 << LOBE_FRESNEL_SPECULAR) | (1 << LOBE_MICRO_REFL_DIEL) | (1 << LOBE_MICRO_TRANS), KM_METAL = 1 << LOBE_MICRO_REFL_COND };
@@ -382,6 +384,17 @@ PB_D rgb lobe_f(const Lobe& l, f3 wo, f3 wi) {
             return (rgb(1.0f) - F) * l.c0 *
                    fabsf(tr_d(l.tr, wh) * tr_g(l.tr, wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor / (cti * cto * sd * sd));
         }
+        case LOBE_FRESNEL_BLEND: {  // reflection.rs:1167-1185
+            if (!KM_HAS(LOBE_FRESNEL_BLEND)) break;
+            float a = 1.0f - 0.5f * fabsf(wi.z), b = 1.0f - 0.5f * fabsf(wo.z);
+            rgb diffuse = l.c0 * (rgb(1.0f) - l.c1) * (28.0f / (23.0f * PB_PI)) * (1.0f - (a * a) * (a * a) * a) * (1.0f - (b * b) * (b * b) * b);
+            f3 wh = wi + wo;
+            if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return rgb(0.0f);
+            wh = normalize(wh);
+            float c = 1.0f - dot(wi, wh);
+            rgb schlick = l.c1 + (rgb(1.0f) - l.c1) * ((c * c) * (c * c) * c);
+            return diffuse + schlick * (tr_d(l.tr, wh) / (4.0f * absdot(wi, wh) * fmaxf(fabsf(wi.z), fabsf(wo.z))));
+        }
     }
     return rgb(0.0f);
 }
@@ -407,6 +420,12 @@ PB_D float lobe_pdf(const Lobe& l, f3 wo, f3 wi) {
             float sd = dot(wo, wh) + eta * dot(wi, wh);
             float dwh = fabsf(eta * eta * dot(wi, wh)) / (sd * sd);
             return tr_pdf(l.tr, wo, wh) * dwh;
+        }
+        case LOBE_FRESNEL_BLEND: {  // reflection.rs:1212-1218
+            if (!KM_HAS(LOBE_FRESNEL_BLEND)) break;
+            if (!same_hemi(wo, wi)) return 0.0f;
+            f3 wh = normalize(wo + wi);
+            return 0.5f * (fabsf(wi.z) * PB_INV_PI + tr_pdf(l.tr, wo, wh) / (4.0f * dot(wo, wh)));
         }
     }
     return 0.0f;
@@ -484,28 +503,50 @@ PB_D rgb lobe_sample(const Lobe& l, f3 wo, f3* wi, float2 u, float* pdf, int* st
             *pdf = lobe_pdf<KM>(l, wo, *wi);
             return lobe_f<KM>(l, wo, *wi);
         }
+        case LOBE_FRESNEL_BLEND: {  // reflection.rs:1187-1210
+            if (!KM_HAS(LOBE_FRESNEL_BLEND)) break;
+            if (u.x < 0.5f) {
+                u.x = fminf(2.0f * u.x, PB_ONE_MINUS_EPSILON);
+                *wi = cosine_hemisphere(u);
+                if (wo.z < 0.0f) wi->z *= -1.0f;
+            } else {
+                u.x = fminf(2.0f * (u.x - 0.5f), PB_ONE_MINUS_EPSILON);
+                f3 wh = tr_sample_wh(l.tr, wo, u);
+                *wi = reflect_about(wo, wh);
+                if (!same_hemi(wo, *wi)) return rgb(0.0f);
+            }
+            *pdf = lobe_pdf<KM>(l, wo, *wi);
+            return lobe_f<KM>(l, wo, *wi);
+        }
     }
     return rgb(0.0f);
 }
 
 // ---- BSDF, core/reflection.rs:1496-1689
-struct Bsdf {
+template <int NL>
+struct BsdfN {
     float eta;
     f3 ns, ng, ss, ts;
     int n;
-    Lobe lobe[2];
+    Lobe lobe[NL];
     bool valid;  // si.bsdf is Some
 };
-PB_D void bsdf_init(Bsdf& b, const Surf& si, float eta) {
+using Bsdf = BsdfN<2>;   // the five hot materials add at most two lobes
+using BsdfX = BsdfN<5>;  // uber adds up to five (uber.rs:41-112)
+template <class B>
+PB_D void bsdf_init(B& b, const Surf& si, float eta) {
     b.eta = eta; b.ns = si.sh_n; b.ss = normalize(si.sh_dpdu); b.ng = si.n; b.ts = cross(b.ns, b.ss); b.n = 0; b.valid = true;
 }
-PB_D f3 to_local(const Bsdf& b, f3 v) { return f3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
-PB_D f3 to_world(const Bsdf& b, f3 v) {
+template <class B>
+PB_D f3 to_local(const B& b, f3 v) { return f3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+template <class B>
+PB_D f3 to_world(const B& b, f3 v) {
     return f3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z, b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
-PB_D int bsdf_count(const Bsdf& b, int flags) { int c = 0; for (int i = 0; i < b.n; ++i) c += lobe_matches(b.lobe[i], flags) ? 1 : 0; return c; }
-template <int KM = KM_ALL>
-PB_D rgb bsdf_f(const Bsdf& b, f3 wow, f3 wiw, int flags) {
+template <class B>
+PB_D int bsdf_count(const B& b, int flags) { int c = 0; for (int i = 0; i < b.n; ++i) c += lobe_matches(b.lobe[i], flags) ? 1 : 0; return c; }
+template <int KM = KM_ALL, class B>
+PB_D rgb bsdf_f(const B& b, f3 wow, f3 wiw, int flags) {
     f3 wi = to_local(b, wiw), wo = to_local(b, wow);
     if (wo.z == 0.0f) return rgb(0.0f);
     bool refl = dot(wiw, b.ng) * dot(wow, b.ng) > 0.0f;
@@ -516,8 +557,8 @@ PB_D rgb bsdf_f(const Bsdf& b, f3 wow, f3 wiw, int flags) {
     }
     return res;
 }
-template <int KM = KM_ALL>
-PB_D float bsdf_pdf(const Bsdf& b, f3 wow, f3 wiw, int flags) {
+template <int KM = KM_ALL, class B>
+PB_D float bsdf_pdf(const B& b, f3 wow, f3 wiw, int flags) {
     if (b.n == 0) return 0.0f;
     f3 wo = to_local(b, wow), wi = to_local(b, wiw);
     if (wo.z == 0.0f) return 0.0f;
@@ -528,8 +569,8 @@ PB_D float bsdf_pdf(const Bsdf& b, f3 wow, f3 wiw, int flags) {
     return m > 0 ? p / (float)m : 0.0f;
 }
 // *pdf / *stype in-out as in the reference (path.rs initialises pdf = 0, flags = 0).
-template <int KM = KM_ALL>
-PB_D rgb bsdf_sample(const Bsdf& b, f3 wow, f3* wiw, float2 u, float* pdf, int flags, int* stype) {
+template <int KM = KM_ALL, class B>
+PB_D rgb bsdf_sample(const B& b, f3 wow, f3* wiw, float2 u, float* pdf, int flags, int* stype) {
     int m = bsdf_count(b, flags);
     if (m == 0) { *pdf = 0.0f; *stype = 0; return rgb(0.0f); }
     float fm = (float)m;
@@ -570,8 +611,8 @@ PB_D rgb bsdf_sample(const Bsdf& b, f3 wow, f3* wiw, float2 u, float* pdf, int f
 // bump, mode = Radiance).  MULTI = allow_multiple_lobes: true from path.rs:123, false from whitted.rs:75 and
 // directlighting.rs:90 (only glass looks at it).
 // MAT >= 0: the material type is known at compile time (the shade kernel of that bin).
-template <int MAT = -1, bool MULTI = true>
-PB_D void material_bsdf(const pbrt_b200_material& m, const Surf& si, Bsdf& b) {
+template <int MAT = -1, bool MULTI = true, class BS>
+PB_D void material_bsdf(const pbrt_b200_material& m, const Surf& si, BS& b) {
     b.valid = false; b.n = 0;
     rgb A = rgb_clamp0(rgb3(m.a)), B = rgb_clamp0(rgb3(m.b));
     switch (MAT >= 0 ? (uint32_t)MAT : m.type) {

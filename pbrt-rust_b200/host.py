@@ -19,6 +19,8 @@ from pathlib import Path
 
 import numpy as np
 
+from . import textures as T
+
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libpbrt_b200.so"
 TABLES_PATH = _HERE / "tables" / "sobol_tables.npz"
@@ -38,7 +40,7 @@ class BvhNode(C.Structure):
 NODE_DTYPE = np.dtype([("bounds", "<f4", 6), ("offset", "<u4"), ("n_prims", "<u2"), ("axis", "u1"), ("pad", "u1")])
 PRIM_DTYPE = np.dtype([("shape_kind", "<u4"), ("shape_index", "<u4"), ("material", "<i4"), ("area_light", "<i4"), ("flags", "<u4"), ("creation_index", "<u4")])
 SPHERE_DTYPE = np.dtype([("object_to_world", "<f4", 16), ("world_to_object", "<f4", 16), ("radius", "<f4"), ("flags", "<u4"), ("pad", "<f4", 2)])
-MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("remap_roughness", "<u4"), ("a", "<f4", 3), ("b", "<f4", 3), ("f0", "<f4"), ("f1", "<f4"), ("f2", "<f4"), ("pad", "<f4")])
+MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("remap_roughness", "<u4"), ("a", "<f4", 3), ("b", "<f4", 3), ("f0", "<f4"), ("f1", "<f4"), ("f2", "<f4"), ("textured", "<u4")])
 LIGHT_DTYPE = np.dtype([("type", "<u4"), ("two_sided", "<u4"), ("L", "<f4", 3), ("pos", "<f4", 3), ("dir", "<f4", 3), ("shape_kind", "<u4"),
                         ("shape_index", "<u4"), ("shape_flags", "<u4"), ("area", "<f4"), ("cos_total_width", "<f4"), ("cos_falloff_start", "<f4"),
                         ("world_to_light", "<f4", 16), ("n_samples", "<u4")])
@@ -54,7 +56,7 @@ OBJECT_DTYPE = np.dtype([("node_offset", "<u8"), ("n_nodes", "<u8"), ("prim_offs
 INSTANCE_DTYPE = np.dtype([("prim_to_world", "<f4", 16), ("world_to_prim", "<f4", 16), ("object", "<u4"), ("pad", "<u4", 3)])
 assert OBJECT_DTYPE.itemsize == 32 and INSTANCE_DTYPE.itemsize == 144
 PRIM_REVERSE_ORIENTATION, PRIM_SWAPS_HANDEDNESS, PRIM_HAS_N, PRIM_HAS_S, PRIM_HAS_UV = 1, 2, 4, 8, 16
-MAT_MATTE, MAT_PLASTIC, MAT_MIRROR, MAT_GLASS, MAT_METAL = range(5)
+MAT_MATTE, MAT_PLASTIC, MAT_MIRROR, MAT_GLASS, MAT_METAL, MAT_UBER, MAT_SUBSTRATE = range(7)
 LIGHT_POINT, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_DIFFUSE, LIGHT_INFINITE = range(5)
 SAMPLER_SOBOL, SAMPLER_HALTON, SAMPLER_ZEROTWO = range(3)
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = range(3)
@@ -74,7 +76,8 @@ class SceneDesc(C.Structure):
                 ("objects", C.c_void_p), ("n_objects", C.c_uint64),
                 ("instances", C.c_void_p), ("n_instances", C.c_uint64),
                 ("n_top_nodes", C.c_uint64), ("n_top_prims", C.c_uint64),
-                ("media", C.c_void_p), ("n_media", C.c_uint64), ("prim_media", C.c_void_p)]
+                ("media", C.c_void_p), ("n_media", C.c_uint64), ("prim_media", C.c_void_p),
+                ("textures", C.c_void_p), ("n_textures", C.c_uint64), ("mipmaps", C.c_void_p), ("n_mipmaps", C.c_uint64), ("material_ext", C.c_void_p)]
 
 
 class CameraDesc(C.Structure):
@@ -427,10 +430,22 @@ class FlatScene:
         self.n_top_nodes = self.n_top_prims = 0  # 0 = all of nodes / prims (no object instancing)
         self.media = np.zeros(0, MEDIUM_DTYPE)       # HomogeneousMedium rows (volpath)
         self.prim_media = None                       # MediumInterface per `prims` row, or None
+        self.textures = np.zeros(0, T.TEXNODE_DTYPE)  # postfix texture programs (ABI v5)
+        self.mipmaps = np.zeros(0, T.MIPMAP_DTYPE)    # rows point into the MipMap objects kept in mipmap_objects
+        self.mipmap_objects = []
+        self.material_ext = None                      # one MATERIAL_EXT row per material row when any is textured
 
     def desc(self):
         d = SceneDesc()
-        d.abi_version = 4
+        d.abi_version = 5
+        if len(self.textures):
+            d.textures, d.n_textures = _ptr(self.textures), len(self.textures)
+        if len(self.mipmaps):
+            d.mipmaps, d.n_mipmaps = _ptr(self.mipmaps), len(self.mipmaps)
+        if self.material_ext is not None:
+            if len(self.material_ext) != len(self.materials):
+                raise B200Error("FlatScene.material_ext must have one row per material row")
+            d.material_ext = _ptr(self.material_ext)
         d.nodes, d.n_nodes = _ptr(self.nodes), len(self.nodes)
         d.prims, d.n_prims = _ptr(self.prims), len(self.prims)
         d.vertex_p, d.n_vertices = _ptr(self.vertex_p), len(self.vertex_p)
@@ -465,6 +480,22 @@ def _tri_area(p0, p1, p2):
 # tools/copper_rgb.py against the reference's CIE tables (src/core/cie.rs)
 COPPER_N = (0.19999069, 0.92208463, 1.09987593)
 COPPER_K = (3.90463543, 2.44763327, 2.13765264)
+
+
+TEX_STACK_LIMIT = 8  # PB_TEX_STACK in csrc/texture.cuh
+
+
+class TexturedMaterial:
+    """A material row whose parameters come from pbrt_b200_material_ext: texture trees, a bump map, or uber / substrate."""
+
+    def __init__(self, name, row, spectra, floats, bump):
+        self.name, self.row, self.spectra, self.floats, self.bump = name, row, spectra, floats, bump
+
+    def key(self):
+        def k(x):
+            return x.key() if T.is_texture(x) else np.asarray(x, f32).tobytes()
+
+        return (self.row.tobytes(), tuple(k(x) for x in self.spectra), tuple(k(x) for x in self.floats), self.bump.key() if self.bump is not None else None)
 
 
 class SceneBuilder:
@@ -600,34 +631,69 @@ class SceneBuilder:
         self.ctm = self.ctm * t
 
     # --- materials (src/materials/*.rs create_* defaults) -------------------
+    # parameter slots of pbrt_b200_material_ext, per material: (spectrum slots, float slots)
+    MATERIAL_SLOTS = {"matte": (("Kd",), ("sigma",)), "plastic": (("Kd", "Ks"), ("roughness",)), "mirror": (("Kr",), ()),
+                      "glass": (("Kr", "Kt"), ("uroughness", "vroughness", "eta")), "metal": (("eta", "k"), ("uroughness", "vroughness")),
+                      "uber": (("Kd", "Ks", "Kr", "Kt", "opacity"), ("uroughness", "vroughness", "eta")),
+                      "substrate": (("Kd", "Ks"), ("uroughness", "vroughness"))}
+    MATERIAL_TYPES = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "mirror": MAT_MIRROR, "glass": MAT_GLASS, "metal": MAT_METAL, "uber": MAT_UBER,
+                      "substrate": MAT_SUBSTRATE}
+
     @staticmethod
     def _mat_row(name, **kw):
-        r = np.zeros(1, MATERIAL_DTYPE)[0]
-        r["remap_roughness"] = 1 if kw.get("remaproughness", True) else 0
-
-        def rgb(key, default):
-            v = kw.get(key, default)
-            return np.full(3, v, f32) if np.isscalar(v) else np.asarray(v, f32)
-
-        if name == "matte":
-            r["type"], r["a"], r["f0"] = MAT_MATTE, rgb("Kd", 0.5), kw.get("sigma", 0.0)
-        elif name == "plastic":
-            r["type"], r["a"], r["b"], r["f0"] = MAT_PLASTIC, rgb("Kd", 0.25), rgb("Ks", 0.25), kw.get("roughness", 0.1)
-        elif name == "mirror":
-            r["type"], r["a"] = MAT_MIRROR, rgb("Kr", 0.9)
-        elif name == "glass":
-            r["type"], r["a"], r["b"] = MAT_GLASS, rgb("Kr", 1.0), rgb("Kt", 1.0)
-            r["f0"], r["f1"] = kw.get("uroughness", 0.0), kw.get("vroughness", 0.0)
-            r["f2"] = kw.get("eta", kw.get("index", 1.5))
-        elif name == "metal":
-            r["type"], r["a"], r["b"] = MAT_METAL, rgb("eta", COPPER_N), rgb("k", COPPER_K)
-            rough = kw.get("roughness", 0.01)
-            r["f0"], r["f1"] = kw.get("uroughness", rough), kw.get("vroughness", rough)
-        elif name in ("none", ""):
+        """-> MATERIAL_DTYPE row (every parameter constant, one of the five hot materials) | TexturedMaterial | None.
+        Parameter values are constants (scalar / RGB) or textures.Tex trees; "bumpmap" is a float texture."""
+        if name in ("none", ""):
             return None
-        else:
-            raise B200Error(f'Material "{name}" is outside the hot path (matte, plastic, mirror, glass, metal)')
-        return r
+        if name not in SceneBuilder.MATERIAL_SLOTS:
+            raise B200Error(f'Material "{name}" is outside the device path (matte, plastic, mirror, glass, metal, uber, substrate)')
+        # create_* defaults (matte.rs:55-61, plastic.rs:72-80, mirror.rs:44-49, glass.rs:95-108, metal.rs:115-125, uber.rs:114-128,
+        # substrate.rs:64-71); metal / uber fall back from u/vroughness to `roughness` (metal.rs:88-97, uber.rs:78-87)
+        v = dict(kw)
+        if name == "matte":
+            v.setdefault("Kd", 0.5); v.setdefault("sigma", 0.0)
+        elif name == "plastic":
+            v.setdefault("Kd", 0.25); v.setdefault("Ks", 0.25); v.setdefault("roughness", 0.1)
+        elif name == "mirror":
+            v.setdefault("Kr", 0.9)
+        elif name == "glass":
+            v.setdefault("Kr", 1.0); v.setdefault("Kt", 1.0); v.setdefault("uroughness", 0.0); v.setdefault("vroughness", 0.0)
+            v.setdefault("eta", v.get("index", 1.5))
+        elif name == "metal":
+            v.setdefault("eta", COPPER_N); v.setdefault("k", COPPER_K)
+            rough = v.get("roughness", 0.01)
+            v.setdefault("uroughness", rough); v.setdefault("vroughness", rough)
+        elif name == "uber":
+            v.setdefault("Kd", 0.25); v.setdefault("Ks", 0.25); v.setdefault("Kr", 0.0); v.setdefault("Kt", 0.0); v.setdefault("opacity", 1.0)
+            rough = v.get("roughness", 0.1)
+            v.setdefault("uroughness", rough); v.setdefault("vroughness", rough)
+            v.setdefault("eta", v.get("index", 1.5))
+        elif name == "substrate":
+            v.setdefault("Kd", 0.5); v.setdefault("Ks", 0.5); v.setdefault("uroughness", 0.1); v.setdefault("vroughness", 0.1)
+        sslots, fslots = SceneBuilder.MATERIAL_SLOTS[name]
+        bump = v.get("bumpmap")
+        if bump is not None and not T.is_texture(bump):
+            bump = T.Tex.constant(bump)
+        r = np.zeros(1, MATERIAL_DTYPE)[0]
+        r["type"] = SceneBuilder.MATERIAL_TYPES[name]
+        r["remap_roughness"] = 1 if v.get("remaproughness", True) else 0
+        textured = bump is not None or name in ("uber", "substrate") or any(T.is_texture(v[k]) for k in sslots + fslots)
+
+        def rgb(x):
+            return np.zeros(3, f32) if T.is_texture(x) else (np.full(3, x, f32) if np.isscalar(x) or np.ndim(x) == 0 else np.asarray(x, f32))
+
+        def flt(x):
+            return f32(0.0) if T.is_texture(x) else f32(x)
+
+        if name not in ("uber", "substrate"):
+            for field, key in zip(("a", "b"), sslots):
+                r[field] = rgb(v[key])
+            for field, key in zip(("f0", "f1", "f2"), fslots):
+                r[field] = flt(v[key])
+        if not textured:
+            return r
+        r["textured"] = 1
+        return TexturedMaterial(name, r, [v[k] for k in sslots], [v[k] for k in fslots], bump)
 
     def material(self, name, **kw):
         self.log.append(("Material", name, kw))
@@ -636,11 +702,42 @@ class SceneBuilder:
     def _material_id(self):
         if self._material is None:
             return -1
-        key = self._material.tobytes()
+        key = self._material.key() if isinstance(self._material, TexturedMaterial) else self._material.tobytes()
         if key not in self._mat_index:
             self._mat_index[key] = len(self._materials)
-            self._materials.append(self._material.copy())
+            self._materials.append(self._material if isinstance(self._material, TexturedMaterial) else self._material.copy())
         return self._mat_index[key]
+
+    def _material_tables(self, fs):
+        """materials[] (+ material_ext[], textures[], mipmaps[] when a row is textured) of the flat scene."""
+        if not self._materials:
+            return
+        fs.materials = np.array([m.row if isinstance(m, TexturedMaterial) else m for m in self._materials], MATERIAL_DTYPE)
+        if not any(isinstance(m, TexturedMaterial) for m in self._materials):
+            return
+        tabs = T.TextureTables()
+        ext = np.zeros(len(self._materials), T.MATERIAL_EXT_DTYPE)
+        for i, m in enumerate(self._materials):
+            if not isinstance(m, TexturedMaterial):
+                continue
+            for k, val in enumerate(m.spectra):
+                if T.is_texture(val):
+                    ext[i]["s_tex"][k] = tabs.program(val)
+                else:
+                    ext[i]["s_const"][k] = np.full(3, val, f32) if np.isscalar(val) or np.ndim(val) == 0 else np.asarray(val, f32)
+            for k, val in enumerate(m.floats):
+                if T.is_texture(val):
+                    ext[i]["f_tex"][k] = tabs.program(val)
+                else:
+                    ext[i]["f_const"][k] = f32(val)
+            if m.bump is not None:
+                ext[i]["bump"] = tabs.program(m.bump)
+        fs.material_ext = ext
+        fs.textures = tabs.node_array()
+        fs.mipmap_objects = list(tabs.mipmaps)
+        fs.mipmaps = tabs.mipmap_array()
+        if tabs.max_depth > TEX_STACK_LIMIT:
+            raise B200Error(f"texture expressions nest deeper than the device's value stack ({TEX_STACK_LIMIT} operands)")
 
     # --- lights ------------------------------------------------------------
     def area_light_source(self, name="diffuse", L=(1, 1, 1), scale=1.0, twosided=False, samples=1):  # diffuse.rs:178-195
@@ -803,8 +900,7 @@ class SceneBuilder:
                 fs.vertex_uv = np.ascontiguousarray(np.concatenate(self._UV), f32)
         if self._spheres:
             fs.spheres = np.array(self._spheres, SPHERE_DTYPE)
-        if self._materials:
-            fs.materials = np.array(self._materials, MATERIAL_DTYPE)
+        self._material_tables(fs)
         if self._lights:
             fs.lights = np.array(self._lights, LIGHT_DTYPE)
         if self._cur_object is not None:

@@ -231,8 +231,8 @@ class UnsupportedTexture:
 class TextureParams:
     """paramset.rs:443-610: shape parameters shadow the material's; textures resolve by name.
 
-    Only constant textures exist on this path (SURVEY.md §8 f3 keeps image maps / procedural textures for a
-    later round), so a texture resolves to its constant value: f32 for float textures, RGB for spectrum ones.
+    A texture resolves to a constant (f32 for float textures, RGB for spectrum ones) when its whole expression is constant,
+    otherwise to a textures.Tex tree.
     """
 
     def __init__(self, geo, mat, float_textures, spectrum_textures):
@@ -249,6 +249,15 @@ class TextureParams:
 
     def find_spectrum(self, n, d):
         return self.geo.find_one_spectrum(n, self.mat.find_one_spectrum(n, d))
+
+    def find_int(self, n, d):
+        return self.geo.find_one_int(n, self.mat.find_one_int(n, d))
+
+    def find_vector3f(self, n, d):
+        return np.asarray(self.geo._find_one("vector3fs", n, self.mat._find_one("vector3fs", n, d)), f32)
+
+    def find_filename(self, n, d):
+        return self.geo.find_one_filename(n, self.mat.find_one_filename(n, d))
 
     def _tex_or_null(self, n, find, table, kind):
         name = self.geo.find_texture(n, "")
@@ -282,10 +291,14 @@ class TextureParams:
 
     def get_spectrumtexture(self, n, d):
         v = self.get_spectrumtexture_ornull(n)
+        if v is not None and not isinstance(v, np.ndarray) and not np.isscalar(v):
+            return v  # a textures.Tex tree
         return np.asarray(d if v is None else v, f32) if not np.isscalar(d) or v is not None else np.full(3, d, f32)
 
     def get_floattexture(self, n, d):
         v = self.get_floattexture_ornull(n)
+        if v is not None and not np.isscalar(v) and not isinstance(v, np.ndarray):
+            return v  # a textures.Tex tree
         return f32(d if v is None else v)
 
     def report_unused(self):

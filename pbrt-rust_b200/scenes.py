@@ -401,6 +401,129 @@ def fog_box_scene(xres=128, yres=128, spp=16, maxdepth=5, sampler="sobol", camer
     return SceneSetup("V1-fog-box", flat, make, "matte box in haze, smoke cube (material-less boundary), dye-filled glass sphere, mirror; volpath")
 
 
+def _test_image(w=96, h=64, channels=3):
+    """A small deterministic image (NOT a power of two: MIPMap::new resamples it): stripes, a ramp and a few bright texels."""
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.zeros((h, w, 3), f32)
+    img[..., 0] = 0.15 + 0.6 * ((x // 6) % 2)
+    img[..., 1] = 0.1 + 0.8 * (y / f32(h - 1))
+    img[..., 2] = 0.25 + 0.5 * (((x + y) // 9) % 2)
+    img[(x % 17 == 3) & (y % 11 == 5)] = (2.5, 2.0, 1.5)
+    return img if channels == 3 else img.mean(axis=2, keepdims=True).astype(f32)
+
+
+def textured_scene(xres=160, yres=120, spp=8, maxdepth=5, sampler="sobol", instanced=True):
+    """SURVEY.md s8 f3 in one scene: every texture kind (image maps with EWA and trilinear filtering under the three wrap modes, 2D / 3D
+    checkerboards, dots, fbm, wrinkled, marble, windy, uv, bilerp, scale, mix), every mapping (uv, planar, spherical, cylindrical, 3D),
+    float and spectrum textures as parameters of all seven materials (incl. uber with an opacity texture and substrate), bump maps on a
+    sphere and on a triangle mesh with per-vertex normals, and a textured object instance.  Rendered by the path, volpath, whitted and
+    directlighting integrators (ray differentials through the mirror and the glass sphere only exist under the latter two)."""
+    from . import textures as T
+    Tex, M2 = T.Tex, T.Mapping2D
+    b = H.SceneBuilder()
+    cam_w2c = H.Transform.look_at((0.3, 2.4, 6.2), (0.0, 0.6, 0.0), (0, 1, 0))
+    rgb_img = T.MipMap(_test_image(), do_trilinear=False, max_anisotropy=8.0, wrap="repeat")
+    tri_img = T.MipMap(_test_image(64, 64), do_trilinear=True, wrap="clamp")
+    flt_img = T.MipMap(_test_image(40, 24, channels=1), do_trilinear=False, max_anisotropy=4.0, wrap="black")
+
+    def tex3(sc):
+        # noise() takes `floor(x) as usize` (texture.rs:332-334): a negative coordinate saturates to cell 0 with a negative offset and the
+        # quintic weights explode (mirrored, tests/test_oracle_textures.py) -- so the scene keeps its 3D textures in the positive octant
+        return H.Transform.translate((40.0, 40.0, 40.0)) * H.Transform.scale(sc, sc, sc)
+
+    b.light_source("point", **{"from": (-3.0, 4.5, 3.0), "I": (30.0, 28.0, 26.0)})
+    b.light_source("distant", **{"from": (2, 6, 4), "to": (0, 0, 0), "L": (1.2, 1.2, 1.3)})
+    b.attribute_begin()
+    b.area_light_source("diffuse", L=(9, 9, 8))
+    b.material("matte", Kd=0.0)
+    P, I = quad((1.0, 4.0, -1.0), (2.2, 4.0, -1.0), (2.2, 4.0, 0.2), (1.0, 4.0, 0.2))
+    b.shape("trianglemesh", P=P, indices=I)
+    b.attribute_end()
+    # ground: EWA-filtered image map through the mesh's uv ("st"), scaled so that it minifies towards the horizon
+    P, I = quad((-12, 0, -14), (12, 0, -14), (12, 0, 8), (-12, 0, 8))
+    uvq = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], f32)
+    b.material("matte", Kd=Tex.imagemap(M2.uv(12.0, 11.0, 0.25, 0.1), rgb_img), sigma=Tex.mix(0.0, 40.0, Tex.fbm(tex3(0.7), 4, 0.6)))
+    b.shape("trianglemesh", P=P, indices=I, uv=uvq)
+    # back wall: closed-form antialiased checkerboard (planar mapping) of marble and a constant
+    P, I = quad((-7, 0, -6), (7, 0, -6), (7, 6, -6), (-7, 6, -6))
+    marble = Tex.marble(tex3(1.5), 6, 0.5, 1.2, 0.3)
+    b.material("matte", Kd=Tex.checkerboard(M2.planar((0.8, 0, 0), (0, 0.8, 0), 0.1, 0.2), marble, np.array([0.15, 0.3, 0.55], f32), "closedform"))
+    b.shape("trianglemesh", P=P, indices=I)
+    # plastic sphere: uv checkerboard as Kd, dots as roughness, wrinkled bump map
+    b.attribute_begin()
+    b.translate(-2.3, 1.0, 0.2)
+    b.material("plastic", Kd=Tex.checkerboard(M2.uv(10.0, 6.0), np.array([0.8, 0.2, 0.15], f32), Tex.uv(M2.uv(3.0, 3.0)), "none"),
+               Ks=0.3, roughness=Tex.dots(M2.uv(14.0, 9.0), outside=0.05, inside=0.4), bumpmap=Tex.scale(Tex.wrinkled(tex3(3.0), 5, 0.55), 0.05))
+    b.shape("sphere", radius=1.0)
+    b.attribute_end()
+    # uber sphere: opacity from a 3D checkerboard (partly see-through), Kd spherical image map, Kr / Kt constants
+    b.attribute_begin()
+    b.translate(0.0, 0.9, 1.6)
+    b.material("uber", Kd=Tex.imagemap(M2.spherical(H.Transform.translate((0.0, 0.9, 1.6)).inverse()), tri_img), Ks=0.2, Kr=0.15, Kt=0.1,
+               opacity=Tex.checkerboard3d(tex3(2.5), np.array([1.0, 1.0, 1.0], f32), np.array([0.25, 0.35, 0.3], f32)), roughness=0.08, index=1.4)
+    b.shape("sphere", radius=0.9)
+    b.attribute_end()
+    # substrate on a triangle mesh with per-vertex normals and uvs: trilinear image map as Kd, float image map as bump
+    Pm, Im, Nm = displaced_sphere(40, 20, radius=0.9, amplitude=0.05)[:3]
+    th = np.arctan2(Pm[:, 2], Pm[:, 0]).astype(f32)
+    uvm = np.stack([(th / f32(2 * np.pi) + f32(0.5)), np.clip(Pm[:, 1] / f32(1.9) + f32(0.5), 0, 1)], axis=1).astype(f32)
+    b.attribute_begin()
+    b.translate(2.4, 1.0, 0.3)
+    b.material("substrate", Kd=Tex.imagemap(M2.uv(3.0, 2.0), tri_img), Ks=np.array([0.05, 0.06, 0.05], f32), uroughness=0.1,
+               vroughness=Tex.mix(0.02, 0.3, Tex.imagemap(M2.uv(2.0, 2.0), flt_img)), bumpmap=Tex.scale(Tex.imagemap(M2.uv(4.0, 4.0, 0.1, 0.0), flt_img), 0.08))
+    b.shape("trianglemesh", P=Pm, indices=Im, N=Nm, uv=uvm)
+    b.attribute_end()
+    # glass sphere with a bilerp tint on Kt; a mirror quad whose Kr is a windy spectrum texture; a metal box with a textured roughness
+    b.attribute_begin()
+    b.translate(-0.9, 0.55, 3.2)
+    b.material("glass", Kr=1.0, Kt=Tex.bilerp(M2.uv(), (1.0, 0.9, 0.8), (0.8, 1.0, 0.85), (0.85, 0.85, 1.0), (1.0, 1.0, 1.0)), index=1.5)
+    b.shape("sphere", radius=0.55)
+    b.attribute_end()
+    P, I = quad((3.2, 0.0, -3.5), (6.0, 0.0, -1.0), (6.0, 3.0, -1.0), (3.2, 3.0, -3.5))
+    b.material("mirror", Kr=Tex.mix(0.55, 0.95, Tex.windy(tex3(0.8))))
+    b.shape("trianglemesh", P=P, indices=I)
+    P, I = box_mesh((-5.5, 0.0, -3.0), (-4.0, 1.6, -1.5))
+    b.material("metal", roughness=Tex.checkerboard(M2.cylindrical(H.Transform.translate((-4.75, 0.0, -2.25)).inverse()), 0.01, 0.25, "none"))
+    b.shape("trianglemesh", P=P, indices=I)
+    # a textured object, instanced twice (the second one rotated and scaled)
+    Pb, Ib = box_mesh((-0.4, 0.0, -0.4), (0.4, 0.8, 0.4))
+    crate = Tex.scale(Tex.imagemap(M2.planar((1.1, 0, 0), (0, 1.1, 0.4)), rgb_img), np.array([0.9, 0.8, 0.7], f32))
+    if instanced:
+        b.object_begin("crate")
+        b.material("matte", Kd=crate)
+        b.shape("trianglemesh", P=Pb, indices=Ib)
+        b.object_end()
+        for k, (tx, tz, rot, sc) in enumerate(((1.2, 3.4, 25.0, 1.0), (3.6, 2.4, -40.0, 1.3))):
+            b.attribute_begin()
+            b.translate(tx, 0.0, tz)
+            b.rotate(rot, 0, 1, 0)
+            b.scale(sc, sc, sc)
+            b.object_instance("crate")
+            b.attribute_end()
+    else:
+        b.attribute_begin()
+        b.translate(1.2, 0.0, 3.4)
+        b.material("matte", Kd=crate)
+        b.shape("trianglemesh", P=Pb, indices=Ib)
+        b.attribute_end()
+    flat = b.world_end()
+    flat.keepalive = (rgb_img, tri_img, flt_img)
+
+    def make(spp_=spp, res=(xres, yres), maxdepth_=maxdepth, sampler_=sampler, strategy="power", integrator="path", filt="box", lensradius=0.0):
+        film = H.Film(res[0], res[1], filt)
+        cam = H.PerspectiveCamera(film, cam_w2c.inverse(), fov=42.0, lensradius=lensradius, focaldistance=6.5)
+        smp = H.Sampler(sampler_, spp_)
+        if integrator == "path":
+            return H.PathIntegrator(cam, film, smp, maxdepth=maxdepth_, lightsamplestrategy=strategy)
+        if integrator == "volpath":
+            return H.VolPathIntegrator(cam, film, smp, maxdepth=maxdepth_, lightsamplestrategy=strategy)
+        if integrator == "whitted":
+            return H.WhittedIntegrator(cam, film, smp, maxdepth=maxdepth_)
+        return H.DirectLightingIntegrator(cam, film, smp, maxdepth=maxdepth_, strategy=integrator.split(":")[1] if ":" in integrator else "all")
+
+    return SceneSetup("T1-textures", flat, make, "every texture kind / mapping / textured material, bump maps, a textured instance")
+
+
 def small_mixed_scene(n=24, seed=5):
     """Test-sized scene touching every material/light/shape kind on the hot path."""
     b = H.SceneBuilder()

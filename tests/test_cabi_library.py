@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert not missing, f"libpbrt_b200.so lacks {missing}"
     assert sorted(pkg.host.EXPORTS) == declared_symbols(), "host.EXPORTS and the header disagree"
     # v2: object instancing tables in pbrt_b200_scene_desc; v3: pbrt_b200_light.n_samples; v4: media tables, integrator.camera_medium
-    assert lib.pbrt_b200_abi_version() == 4
+    assert lib.pbrt_b200_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header(pkg):

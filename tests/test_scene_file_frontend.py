@@ -234,9 +234,9 @@ def test_api_state_rules():
 
 
 def test_out_of_scope_features_fail_loudly():
-    for text in ('Integrator "sppm"\nWorldBegin\nWorldEnd', 'WorldBegin\nMaterial "uber"\nWorldEnd', 'WorldBegin\nShape "cylinder"\nWorldEnd',
+    for text in ('Integrator "sppm"\nWorldBegin\nWorldEnd', 'WorldBegin\nMaterial "disney"\nWorldEnd', 'WorldBegin\nShape "cylinder"\nWorldEnd',
                  'Camera "orthographic"\nWorldBegin\nWorldEnd',
-                 'WorldBegin\nTexture "t" "color" "checkerboard"\nMaterial "matte" "texture Kd" "t"\nWorldEnd',
+                 'WorldBegin\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] "texture alpha" "t"\nWorldEnd',
                  'WorldBegin\nLightSource "infinite" "string mapname" "env.exr"\nWorldEnd', 'Sampler "random"\nWorldBegin\nWorldEnd',
                  'WorldBegin\nMakeNamedMedium "m" "string type" "heterogeneous"\nWorldEnd',
                  'WorldBegin\nMakeNamedMedium "m" "string type" "homogeneous" "string preset" "Skin1"\nWorldEnd'):
@@ -258,10 +258,14 @@ def test_textures_that_are_declared_but_unused_and_missing_image_maps(tmp_path):
     m = job.flat.materials
     g = ((0.5 + 0.055) / 1.055) ** 2.4
     assert np.allclose(m[0]["a"], 2 * g, rtol=1e-6) and np.allclose(m[1]["a"], 0.5) and abs(m[1]["f0"] - g) < 1e-6
-    (tmp_path / "real.png").write_bytes(b"\x89PNG\r\n")  # a file that exists would have to be decoded and filtered: refused when used
-    with pytest.raises(pkg.B200Error):
-        pkg.pbrt_parse_string('WorldBegin\nTexture "a" "color" "imagemap" "string filename" "real.png"\nMaterial "matte" "texture Kd" "a"\nWorldEnd',
-                              search_dir=str(tmp_path))
+    # a file that exists but cannot be decoded is the same grey texel, kept as a 1x1 image map (imagemap.rs:136-142)
+    (tmp_path / "real.png").write_bytes(b"\x89PNG\r\n")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        job = pkg.pbrt_parse_string('WorldBegin\nTexture "a" "color" "imagemap" "string filename" "real.png"\nMaterial "matte" "texture Kd" "a"\nShape "sphere"\nWorldEnd',
+                                    search_dir=str(tmp_path)).jobs[0]
+    assert len(job.flat.mipmaps) == 1 and job.flat.mipmaps[0]["width"] == 1 and job.flat.materials[0]["textured"] == 1
+    assert np.allclose(job.flat.mipmap_objects[0].texels, g, rtol=1e-6)
 
 
 def test_include_resolves_against_the_scene_directory(tmp_path):
