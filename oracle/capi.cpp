@@ -239,11 +239,17 @@ void orc_distribution1d(const float* func, int n, float u, int mode, float* out3
 
 // BSDF of material `m` on a canonical frame (n = +z, dpdu = +x): f, pdf and sample_f.
 // in: wo[3], wi[3], u[2].  out: f[3], pdf, sampled f[3], sampled wi[3], sampled pdf, sampled flags, ncomp(non-specular)
-void orc_bsdf_eval(const pbrt_b200_material* m, const float* wo, const float* wi, const float* u, int flags, float* out13) {
+// `x` (may be null): the row's pbrt_b200_material_ext with constant parameters only -- how uber and substrate are reached
+void orc_bsdf_eval_ext(const pbrt_b200_material* m, const pbrt_b200_material_ext* x, const float* wo, const float* wi, const float* u, int flags, float* out13) {
     SurfaceInteraction si;
     si.n = si.sh_n = V3(0, 0, 1); si.dpdu = si.sh_dpdu = V3(1, 0, 0); si.dpdv = si.sh_dpdv = V3(0, 1, 0);
     BSDF b;
-    compute_scattering_functions(*m, si, &b);
+    if (x) {
+        SceneView sv;
+        std::memset(&sv.d, 0, sizeof sv.d);
+        sv.d.materials = m; sv.d.n_materials = 1; sv.d.material_ext = x;
+        compute_scattering_functions_ext(sv, 0, si, &b, true);
+    } else compute_scattering_functions(*m, si, &b);
     for (int i = 0; i < 13; ++i) out13[i] = 0.0f;
     if (!b.valid) { out13[12] = -1.0f; return; }
     V3 WO(wo[0], wo[1], wo[2]), WI(wi[0], wi[1], wi[2]);
@@ -257,8 +263,22 @@ void orc_bsdf_eval(const pbrt_b200_material* m, const float* wo, const float* wi
 
 // n evaluations of the same material / wo: wi[3n], u[2n] -> out[13n] (orc_bsdf_eval's layout); for the Monte-Carlo property
 // tests of the shading half (white furnace, pdf normalisation, reciprocity: tests/test_oracle_shading_properties.py)
+void orc_bsdf_eval(const pbrt_b200_material* m, const float* wo, const float* wi, const float* u, int flags, float* out13) {
+    orc_bsdf_eval_ext(m, nullptr, wo, wi, u, flags, out13);
+}
 void orc_bsdf_eval_batch(const pbrt_b200_material* m, const float* wo, const float* wi, const float* u, int flags, uint64_t n, float* out) {
     for (uint64_t i = 0; i < n; ++i) orc_bsdf_eval(m, wo, wi + 3 * i, u + 2 * i, flags, out + 13 * i);
+}
+void orc_bsdf_eval_batch_ext(const pbrt_b200_material* m, const pbrt_b200_material_ext* x, const float* wo, const float* wi, const float* u, int flags, uint64_t n,
+                             float* out) {
+    for (uint64_t i = 0; i < n; ++i) orc_bsdf_eval_ext(m, x, wo, wi + 3 * i, u + 2 * i, flags, out + 13 * i);
+}
+// PerspectiveCamera::generate_ray_differential + scale_differential(1 / sqrt(spp)) (spp = 0: unscaled) -> o d rxo rxd ryo ryd
+void orc_generate_ray_differential(const pbrt_b200_camera* c, const float* cs5, uint32_t spp, float* out18) {
+    CameraSample cs; cs.pfilm = P2(cs5[0], cs5[1]); cs.time = cs5[2]; cs.plens = P2(cs5[3], cs5[4]);
+    Ray r = generate_ray(*c, cs, spp);
+    const V3 v[6] = {r.o, r.d, r.rxo, r.rxd, r.ryo, r.ryd};
+    for (int k = 0; k < 6; ++k) { out18[3 * k] = v[k].x; out18[3 * k + 1] = v[k].y; out18[3 * k + 2] = v[k].z; }
 }
 // Light::sample_li for n sample points u[2n] from the reference point (p, n): out[8n] = {Li.rgb, wi.xyz, pdf, Light::pdf_li(wi)}
 int orc_light_sample_batch(const pbrt_b200_scene_desc* sdesc, int light, const float* ref_p, const float* ref_n, const float* u, uint64_t n, float* out) {

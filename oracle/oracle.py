@@ -139,15 +139,40 @@ def bsdf_eval(material_row, wo, wi, u, flags=31):
 
 
 def bsdf_eval_batch(material_row, wo, wi, u, flags=31):
-    """n evaluations for one material / wo: wi [n,3], u [n,2] -> [n,13] rows laid out like bsdf_eval's."""
-    m = np.array([material_row], dtype=_H().MATERIAL_DTYPE)
+    """n evaluations for one material / wo: wi [n,3], u [n,2] -> [n,13] rows laid out like bsdf_eval's.
+    `material_row`: a MATERIAL_DTYPE row, or a host.TexturedMaterial whose parameters are all constants (uber, substrate)."""
+    H = _H()
+    ext = None
+    if isinstance(material_row, H.TexturedMaterial):
+        T = importlib.import_module("pbrt-rust_b200.textures")
+        tm = material_row
+        ext = np.zeros(1, T.MATERIAL_EXT_DTYPE)
+        for k, v in enumerate(tm.spectra):
+            ext[0]["s_const"][k] = np.full(3, v, np.float32) if np.ndim(v) == 0 else np.asarray(v, np.float32)
+        for k, v in enumerate(tm.floats):
+            ext[0]["f_const"][k] = np.float32(v)
+        assert tm.bump is None
+        material_row = tm.row
+    m = np.array([material_row], dtype=H.MATERIAL_DTYPE)
     wo = np.ascontiguousarray(wo, np.float32)
     wi = np.ascontiguousarray(wi, np.float32).reshape(-1, 3)
     u = np.ascontiguousarray(u, np.float32).reshape(-1, 2)
     assert len(wi) == len(u)
     out = np.zeros((len(wi), 13), np.float32)
-    lib().orc_bsdf_eval_batch(ptr(m), ptr(wo), ptr(wi), ptr(u), int(flags), C.c_uint64(len(wi)), ptr(out))
+    if ext is None:
+        lib().orc_bsdf_eval_batch(ptr(m), ptr(wo), ptr(wi), ptr(u), int(flags), C.c_uint64(len(wi)), ptr(out))
+    else:
+        lib().orc_bsdf_eval_batch_ext(ptr(m), ptr(ext), ptr(wo), ptr(wi), ptr(u), int(flags), C.c_uint64(len(wi)), ptr(out))
     return out
+
+
+def generate_ray_differential(camera, pfilm, time=0.0, plens=(0.0, 0.0), spp=0):
+    """-> [6,3]: o, d, rx_origin, rx_direction, ry_origin, ry_direction of the camera ray through `pfilm`."""
+    cd = camera.desc()
+    cs = np.array([pfilm[0], pfilm[1], time, plens[0], plens[1]], np.float32)
+    out = np.zeros(18, np.float32)
+    lib().orc_generate_ray_differential(C.byref(cd), ptr(cs), C.c_uint32(int(spp)), ptr(out))
+    return out.reshape(6, 3)
 
 
 def light_sample_batch(flat, light, ref_p, ref_n, u):

@@ -156,7 +156,7 @@ PB_D void rec_estimate_direct(const RenderDev& R, uint32_t id, const Surf& si, c
 }
 
 // One step of the depth-first recursion for every live camera sample: shade the hit of its current ray.
-#if !PB_EXACT_TU
+#if PB_SHADE_TU
 // TEX: the scene has textured materials (texture.cuh) -- every surface then gets its full interaction and its ray differentials
 // (compute_scattering_functions always runs compute_differentials, interaction.rs:258-267), and specular_reflect / specular_transmit
 // hand differentials on to the rays they spawn (integrator.rs:427-452, 476-513).
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(128) k_rec_shade(RenderDev R, int parity) {
     }
 }
 
-#endif  // !PB_EXACT_TU
+#endif  // PB_SHADE_TU
 
 #if PB_EXACT_TU
 struct RecShadowJob {

@@ -57,11 +57,20 @@
 #ifndef PB_SAMPLES_INNER
 #define PB_SAMPLES_INNER 1
 #endif
-#ifdef PB_TU_SHADE
+// Three translation units from this one source (csrc/Makefile): render.o (PB_EXACT_TU: everything but the kernels below, host side
+// included), shade.o (PB_TU_SHADE, --use_fast_math: k_shade / k_rec_shade) and mega.o (PB_TU_MEGA, exact flags: the one-kernel forms
+// k_zt_mega / k_vol_mega, whose out-of-line shade bodies are 2 minutes of ptxas on their own -- a separate unit compiles in parallel).
+#if defined(PB_TU_SHADE)
 #define PB_EXACT_TU 0
+#define PB_MEGA_TU 0
+#elif defined(PB_TU_MEGA)
+#define PB_EXACT_TU 0
+#define PB_MEGA_TU 1
 #else
 #define PB_EXACT_TU 1
+#define PB_MEGA_TU 0
 #endif
+#define PB_SHADE_TU (!PB_EXACT_TU && !PB_MEGA_TU)
 
 using namespace pb;
 
@@ -1578,7 +1587,7 @@ PB_D ShadeOut shade_path(const RenderDev& R, uint32_t id, VolState* vs = nullptr
     return ShadeOut{push_next, push_shadow, push_mis, push_dead, zero_rad};
 }
 
-#if !PB_EXACT_TU
+#if PB_SHADE_TU
 template <int BIN, bool INST, bool ZT>
 __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_mat[BIN];
@@ -1619,9 +1628,9 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
         }
     }
 }
-#endif  // !PB_EXACT_TU
+#endif  // PB_SHADE_TU
 
-#if PB_EXACT_TU
+#if PB_EXACT_TU || PB_MEGA_TU
 // ---------------------------------------------------------------------------
 // K3: shadow rays (VisibilityTester::unoccluded, core/light.rs:120-123)
 // ---------------------------------------------------------------------------
@@ -1631,6 +1640,7 @@ PB_D void shadow_unoccluded(const RenderDev& R, uint32_t id) {  // the light sam
     L.x += c.x; L.y += c.y; L.z += c.z;
     R.L_eta[id] = L;
 }
+#if PB_EXACT_TU
 struct ShadowJob {
     RenderDev* R;
     PB_D bool load(uint32_t i, f3* o, f3* d, float* t_max) const {
@@ -1649,6 +1659,7 @@ __global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
     ShadowJob job{&R};
     trace_queue<true, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
+#endif  // PB_EXACT_TU
 
 // ---------------------------------------------------------------------------
 // K7: MIS rays (estimate_direct's BSDF-sampled branch, integrator.rs:205-234)
@@ -1677,6 +1688,7 @@ PB_D void mis_resolve(const RenderDev& R, uint32_t id, const TravRay& r) {
         R.L_eta[id] = L;
     }
 }
+#if PB_EXACT_TU
 template <bool INST>
 struct MisJob {
     RenderDev* R;
@@ -1693,8 +1705,9 @@ __global__ void PB_TRACE_BOUNDS k_trace_mis(RenderDev R) {
     MisJob<INST> job{&R};
     trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_mis, &R.cnt->fetch_mis, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
-
 #endif  // PB_EXACT_TU
+
+#endif  // PB_EXACT_TU || PB_MEGA_TU
 }  // namespace pb
 #include "recursive.cuh"
 namespace pb {
@@ -1702,7 +1715,11 @@ namespace pb {
 // Launchers of the kernels that live in the other translation unit (shade.o, see the top of this file)
 void launch_shade_kernels(const RenderDev& R, int parity, bool full, int grid_small, int grid_shade, cudaStream_t stream);
 void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int grid_shade, cudaStream_t stream);
-#if !PB_EXACT_TU
+// ... and in mega.o
+void launch_zt_mega(const RenderDev& R, const RenderDev* rdev, uint32_t lanes, uint32_t nblk, cudaStream_t stream);
+void launch_vol_mega(const RenderDev& R, const RenderDev* rdev, unsigned long long total_items, int camera_medium, bool full, int grid, cudaStream_t stream);
+int vol_mega_blocks_per_sm(bool full);
+#if PB_SHADE_TU
 // one launch per material queue (sort/compact-by-material); INST selects the kernel family (trace.cuh, sphere lights)
 template <bool INST>
 static void launch_shade_family(const RenderDev& R, int parity, int grid_small, int grid_shade, cudaStream_t stream) {
@@ -1728,7 +1745,8 @@ void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int gr
     else k_rec_shade<false, false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
 }
 }  // namespace pb (shade.o ends here)
-#endif  // !PB_EXACT_TU
+#endif  // PB_SHADE_TU
+#if PB_EXACT_TU || PB_MEGA_TU
 #if PB_EXACT_TU
 
 // ---------------------------------------------------------------------------
@@ -1789,6 +1807,7 @@ __global__ void __launch_bounds__(256) k_finish_regen(RenderDev R, int parity, u
     }
 }
 
+#endif  // PB_EXACT_TU
 // ---- (0,2)-sequence: tile-serial sample generation (the pixel / sample loops of integrator.rs:320-380 per tile)
 // Advances tile `j` (slot == tile ordinal) to its next camera sample and writes the path into the slot.  `first`: the tile
 // has not started (start_pixel of its first pixel is due).  Returns false when the tile is finished.
@@ -1832,6 +1851,7 @@ PB_D bool zt_next_path(const RenderDev& R, uint32_t j, bool first) {
     if (R.rec.kind) { R.rec.sp[j] = 0; R.rec.arr[j] = 0; }
     return true;
 }
+#if PB_EXACT_TU
 // tile j of the call -> tile number, clipped bounds, generator (sampler.clone(seed = tile.y * ntiles.x + tile.x), integrator.rs:302-303)
 __global__ void __launch_bounds__(128) k_zt_init(RenderDev R) {
     const uint32_t n = R.n_tiles_sel;
@@ -1884,6 +1904,8 @@ __global__ void __launch_bounds__(128) k_finish_zt(RenderDev R, int parity) {
     }
 }
 
+#endif  // PB_EXACT_TU
+#if PB_MEGA_TU
 // The (0,2)-sequence sampler under the PathIntegrator, one kernel: a tile's paths are inherently serial (every draw of
 // every path advances the tile's PCG32), so the wavefront form spends its time launching 13 kernels per path segment for a
 // few hundred threads.  Here ONE thread per tile (one warp per CTA, lane 0 working) walks its tile's pixels, samples and
@@ -2182,7 +2204,7 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
                 case Q_GLASS: o = vol_shade<Q_GLASS, INST>(Rdev, j, &vs); break;
                 case Q_METAL: o = vol_shade<Q_METAL, INST>(Rdev, j, &vs); break;
                 case Q_NOMAT: o = vol_shade<Q_NOMAT, INST>(Rdev, j, &vs); break;
-                case Q_TEX: o = vol_shade<Q_TEX, INST>(Rdev, j, &vs); break;
+                case Q_TEX: if (INST) { o = vol_shade<Q_TEX, true>(Rdev, j, &vs); break; }  // textured scenes run the full-featured family (launch_vol_mega)
                 default: o = vol_shade<Q_MISS, INST>(Rdev, j, &vs); break;
             }
             if (o.zero_rad) n_zero += 1;
@@ -2267,6 +2289,23 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
     atomicAdd(&R.cnt->zero_radiance, n_zero); atomicMax(&R.cnt->iterations, n_iter);
 }
 
+void launch_zt_mega(const RenderDev& R, const RenderDev* rdev, uint32_t lanes, uint32_t nblk, cudaStream_t stream) {
+    k_zt_mega<true><<<nblk, 32, 0, stream>>>(R, rdev, lanes);
+}
+void launch_vol_mega(const RenderDev& R, const RenderDev* rdev, unsigned long long total_items, int camera_medium, bool full, int grid, cudaStream_t stream) {
+    if (full) k_vol_mega<true><<<grid, 64, 0, stream>>>(R, rdev, total_items, camera_medium);
+    else k_vol_mega<false><<<grid, 64, 0, stream>>>(R, rdev, total_items, camera_medium);
+}
+int vol_mega_blocks_per_sm(bool full) {
+    int per_sm = 1;
+    if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<true>, 64, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<false>, 64, 0);
+    return per_sm;
+}
+}  // namespace pb (mega.o ends here)
+#endif  // PB_MEGA_TU
+#endif  // PB_EXACT_TU || PB_MEGA_TU
+#if PB_EXACT_TU
 // single-thread bookkeeping between iterations: roll queue counters, accumulate stats
 __global__ void k_iter_end(Counters* c, unsigned long long total_items) {
     c->closest_rays += (unsigned long long)c->n_path + c->n_mis;
@@ -2788,8 +2827,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (vol) {
         int smc = 148, per_sm = 1;
         cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, sc->device);
-        if (sc->dev.n_instances || sc->dev.n_sphere_lights || sc->dev.material_ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<true>, 64, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<false>, 64, 0);
+        per_sm = vol_mega_blocks_per_sm(sc->dev.n_instances || sc->dev.n_sphere_lights || sc->dev.material_ext);
         const unsigned long long want = (total_items + 63ull) / 64ull;
         vol_grid = (int)std::max<unsigned long long>(1ull, std::min<unsigned long long>((unsigned long long)smc * (unsigned long long)std::max(per_sm, 1), want));
         capacity = ((uint32_t)vol_grid * 64u + 255u) & ~255u;
@@ -2998,8 +3036,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
             if (!rdev) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory");
             ZtRelease rdev_release{rdev, rdev_bytes};
             PB_CUDA_TRY(cudaMemcpyAsync(rdev, &R, sizeof(RenderDev), cudaMemcpyHostToDevice, stream));
-            if (sc->dev.n_instances || sc->dev.n_sphere_lights || sc->dev.material_ext) k_vol_mega<true><<<vol_grid, 64, 0, stream>>>(R, rdev, total_items, rd->integrator.camera_medium);
-            else k_vol_mega<false><<<vol_grid, 64, 0, stream>>>(R, rdev, total_items, rd->integrator.camera_medium);
+            launch_vol_mega(R, rdev, total_items, rd->integrator.camera_medium, sc->dev.n_instances || sc->dev.n_sphere_lights || sc->dev.material_ext, vol_grid, stream);
             launches += 1;
             PB_CUDA_TRY(cudaGetLastError());
             PB_CUDA_TRY(cudaStreamSynchronize(stream));  // rdev is released at the end of this block
@@ -3030,7 +3067,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
             uint32_t lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (n_tiles_sel + (uint32_t)sm_count * 4u - 1u) / ((uint32_t)sm_count * 4u)));
             if (const char* e = getenv("PBRT_B200_ZT_LANES")) lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (uint32_t)atoi(e)));
             const uint32_t nblk = (n_tiles_sel + lanes - 1) / lanes;
-            k_zt_mega<true><<<nblk, 32, 0, stream>>>(R, zt_rdev, lanes);
+            launch_zt_mega(R, zt_rdev, lanes, nblk, stream);
             launches += 1;
         }
         for (unsigned long long wave_begin = 0; !zt_mega && wave_begin < (zt ? 1ull : total_items);) {

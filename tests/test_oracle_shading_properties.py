@@ -34,6 +34,10 @@ MATERIALS = [
     ("metal", dict(roughness=0.3), False, None),
     ("metal", dict(uroughness=0.2, vroughness=0.4), False, None),
     ("glass", dict(uroughness=0.3, vroughness=0.3), True, None),
+    # FresnelBlend (substrate.rs, reflection.rs:1141-1222) and uber's lobe set (uber.rs:41-112; opaque, no specular lobes here)
+    ("substrate", dict(Kd=(0.5, 0.4, 0.3), Ks=(0.2, 0.25, 0.3), uroughness=0.3, vroughness=0.3), False, None),
+    ("substrate", dict(Kd=0.5, Ks=0.5, uroughness=0.2, vroughness=0.5), False, None),
+    ("uber", dict(Kd=(0.3, 0.4, 0.5), Ks=0.3, roughness=0.3, index=1.5), False, None),
 ]
 WOS = [(0.0, 0.0, 1.0), (0.5, 0.2, 0.8), (-0.7, 0.3, 0.4)]
 
@@ -108,7 +112,7 @@ def test_white_furnace(pkg, oracle, mat):
         assert (np.abs(albedo - brute) <= np.maximum(0.01, 4.0 * se)).all(), (name, kw, wo, albedo, brute, se)
 
 
-@pytest.mark.parametrize("mat", [0, 1, 2, 4, 5])
+@pytest.mark.parametrize("mat", [0, 1, 2, 4, 5, 7, 8, 9])
 def test_reciprocity_of_reflection(pkg, oracle, mat):
     name, kw, _, _ = MATERIALS[mat]
     row = pkg.host.SceneBuilder._mat_row(name, **kw)
