@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=64, help="camera samples per pixel per step and per GPU")
-    ap.add_argument("--scene", default="s3", choices=["s3", "cornell", "spheres", "s3small", "s4", "s5"])
+    ap.add_argument("--scene", default="s3", choices=["s3", "cornell", "spheres", "s3small", "s4", "s5", "t1"])
     ap.add_argument("--paths-in-flight", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -61,6 +61,9 @@ def make_setup(pkg, name):
         return S.foliage_field_scene(), dict(), "S4: 2000 instances x 10,000-triangle plant (20M instanced triangles), 9800 point + 200 triangle area lights, power light sampling, 3840x2160, Sobol, maxdepth 5"
     if name == "s5":
         return S.glass_knot_scene(nu=4096, nv=640), dict(), "S5: 5,242,884-triangle glass torus-knot mesh, maxdepth 32, Russian roulette, 1024x1024, Sobol"
+    if name == "t1":
+        return S.textured_scene(xres=1920, yres=1080), dict(), ("T1: the textured test scene (every texture kind and mapping, EWA / trilinear image maps, bump maps, uber + substrate, "
+                                                                 "a textured instance), 1920x1080, Sobol, maxdepth 5 -- SURVEY s8 f3, not a BASELINE config")
     if name == "cornell":
         return S.cornell_scene(), dict(), "S2: Cornell box 1024x1024, maxdepth 8, gaussian filter"
     return S.spheres_scene(), dict(), "S1: two spheres 400x400, maxdepth 5"
@@ -308,9 +311,28 @@ def main():
                           if a is not None) + sum(a.nbytes for a in (setup.flat.vertex_n, setup.flat.vertex_uv, setup.flat.vertex_s) if a is not None)
         n_e2e = max(1, min(args.steps, 4))
         pinned_film = torch.empty((npix, 4), dtype=torch.float32).pin_memory() if world > 1 else None
+        # the step's inputs live in PINNED host memory (the bench contract's wording): the scene tables are copied once, outside the timed
+        # region, into page-locked buffers, and the film comes back into one; pbrt_b200_scene_create's cudaMemcpyAsync calls then run at
+        # PCIe speed instead of through the runtime's pageable staging
+        keep = []
+
+        def pinned(a):
+            if a is None or a.nbytes == 0:
+                return a
+            t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+            keep.append(t)
+            v = t.numpy().view(a.dtype).reshape(a.shape)
+            v[...] = a
+            return v
+
+        import copy
+        flat_e2e = copy.copy(setup.flat)
+        for name in ("nodes", "prims", "vertex_p", "vertex_n", "vertex_s", "vertex_uv", "tri_indices", "spheres", "materials", "lights", "objects", "instances", "media", "prim_media"):
+            setattr(flat_e2e, name, pinned(getattr(flat_e2e, name)))
+        host_film = pinned(host_film)
 
         def e2e_step(k):
-            sc2 = pkg.Scene(setup.flat, device=local)  # host scene tables -> HBM
+            sc2 = pkg.Scene(flat_e2e, device=local)  # host scene tables -> HBM
             if world == 1:
                 _, st = sc2.render(integ, rgbw=host_film, sample_range=(k * spp_step, (k + 1) * spp_step), paths_in_flight=args.paths_in_flight,
                                    flags=pkg.host.RENDER_OVERWRITE)  # render + film D2H into the caller's host buffer
@@ -335,7 +357,7 @@ def main():
             sm = ev.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             dt, cam = mx[0].item(), sm[1].item()
         e2e = {"value": cam / dt, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(host_film.nbytes),
-               "note": f"{n_e2e} steps after 1 warm-up; each = pbrt_b200_scene_create (host scene tables -> HBM, pageable host memory as handed over by the scene API) + render"
+               "note": f"{n_e2e} steps after 1 warm-up; each = pbrt_b200_scene_create (host scene tables in pinned host memory -> HBM) + render"
                        + (" + NCCL film reduce to rank 0" if world > 1 else "") + " + film download to host + scene destroy; host wall clock"}
 
     # ---- Mrays/s on fixed ray batches through the batch C ABI (BASELINE.json metric (i); SURVEY.md s8(d) B-diff / B-shadow)

@@ -1593,14 +1593,39 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_mat[BIN];
     const uint32_t* q = R.q_mat[BIN];
     uint32_t* q_next = R.q_path[parity ^ 1];
-    const uint32_t nround = (n + 31u) & ~31u;
+    // Q_TEX: the trip count is CTA-uniform (barriers inside, see below)
+    const uint32_t nround = BIN == Q_TEX ? ((n + 127u) & ~127u) : ((n + 31u) & ~31u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         ShadeOut o = {false, false, false, false, false};
         uint32_t id = 0;
-        if (i < n) {
-            id = q[i];
-            o = shade_path<BIN, INST, ZT>(R, id);
+        bool valid = i < n;
+        if (valid) id = q[i];
+        if (BIN == Q_TEX) {
+            // The textured bin holds every textured material of the scene, and each one runs its own texture programs: a warp whose
+            // lanes carry different materials executes them one after the other (ncu, T1 scene: 8 of 32 lanes active per instruction
+            // after the first bounce).  The CTA's 128 paths are therefore sorted by material first (bitonic sort of material << 7 | lane
+            // in shared memory): warps become uniform wherever the queue section holds runs of >= 32 paths of one material.
+            __shared__ uint32_t s_key[128], s_id[128];
+            const uint32_t t = threadIdx.x;
+            uint32_t key = 0xffffff80u | t;  // invalid entries sort last
+            if (valid) key = (((uint32_t)R.scene.prims[R.hit[id].x].material & 0x1ffffffu) << 7) | t;
+            s_key[t] = key; s_id[t] = id;
+            __syncthreads();
+            for (uint32_t k = 2; k <= 128u; k <<= 1)
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    const uint32_t p = t ^ j;
+                    if (p > t) {
+                        const uint32_t a = s_key[t], b = s_key[p];
+                        if (((t & k) == 0u) == (a > b)) { s_key[t] = b; s_key[p] = a; }
+                    }
+                    __syncthreads();
+                }
+            const uint32_t mine = s_key[t];
+            valid = mine < 0xffffff80u;
+            id = s_id[mine & 127u];
+            __syncthreads();  // the next trip overwrites the arrays
         }
+        if (valid) o = shade_path<BIN, INST, ZT>(R, id);
         {
             unsigned zm = __ballot_sync(0xffffffffu, o.zero_rad);
             if (zm && (threadIdx.x & 31) == 0) atomicAdd(&R.cnt->zero_radiance, (unsigned long long)__popc(zm));
@@ -3182,6 +3207,17 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         // the caller's buffer while the next one is in flight
         size_t stage_bytes = 0;
         const size_t nfl = npix * 4, chunk = (size_t)1 << 20;  // floats per chunk (4 MB)
+        if (rd->flags & PBRT_B200_RENDER_OVERWRITE) {
+            // a page-locked destination takes the film in one DMA transfer, no staging and no host copy
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, rgbw_out) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+                PB_CUDA_TRY(cudaMemcpyAsync(rgbw_out, film_dev, nfl * sizeof(float), cudaMemcpyDeviceToHost, stream));
+                PB_CUDA_TRY(cudaStreamSynchronize(stream));
+                lap("film d2h (pinned)");
+                return PBRT_B200_OK;
+            }
+            cudaGetLastError();  // (an unregistered host pointer reports cudaErrorInvalidValue on old drivers)
+        }
         float* stage = reinterpret_cast<float*>(pool_alloc_host(std::min(nfl, 2 * chunk) * sizeof(float), &stage_bytes));
         if (!stage) return fail(PBRT_B200_ERR_CUDA, "render: out of pinned host memory");
         const float* src = reinterpret_cast<const float*>(film_dev);

@@ -252,10 +252,19 @@ PB_D float noise_weight(float t) { float t3 = t * t * t, t4 = t3 * t; return 6.0
 PB_D float lerpf(float t, float a, float b) { return a * (1.0f - t) + b * t; }
 // `x.floor() as usize`: NaN / negative -> 0, saturating above (what Rust's cast does); returns the float the reference subtracts
 PB_D unsigned long long f2u_sat(float f) { return (f != f || f <= 0.0f) ? 0ull : (f >= 1.8446744e19f ? 0xffffffffffffffffull : (unsigned long long)f); }
+// cell = `floor(v) as usize`: (the float the reference subtracts, cell & 255).  Below 2^31 the cast is exact in 32 bits; above, a float is
+// a multiple of 256 (low bits 0) until the cast saturates at 2^64 (all ones: 255)
+PB_D float noise_cell(float f, int* cell) {
+    if (!(f > 0.0f)) { *cell = 0; return 0.0f; }                  // NaN / negative saturate to 0
+    if (f < 2147483648.0f) { const int i = (int)f; *cell = i & 255; return (float)i; }
+    if (f >= 1.8446744e19f) { *cell = 255; return 1.8446744e19f; }
+    *cell = 0;
+    return f;
+}
 static __device__ __noinline__ float noise3(float x, float y, float z) {
-    const unsigned long long ixu = f2u_sat(floorf(x)), iyu = f2u_sat(floorf(y)), izu = f2u_sat(floorf(z));
-    const float dx = x - (float)ixu, dy = y - (float)iyu, dz = z - (float)izu;
-    const int ix = (int)(ixu & 255u), iy = (int)(iyu & 255u), iz = (int)(izu & 255u);
+    int ix, iy, iz;
+    const float fx = noise_cell(floorf(x), &ix), fy = noise_cell(floorf(y), &iy), fz = noise_cell(floorf(z), &iz);
+    const float dx = x - fx, dy = y - fy, dz = z - fz;
     float w000 = noise_grad(ix, iy, iz, dx, dy, dz), w100 = noise_grad(ix + 1, iy, iz, dx - 1.0f, dy, dz);
     float w010 = noise_grad(ix, iy + 1, iz, dx, dy - 1.0f, dz), w110 = noise_grad(ix + 1, iy + 1, iz, dx - 1.0f, dy - 1.0f, dz);
     float w001 = noise_grad(ix, iy, iz + 1, dx, dy, dz - 1.0f), w101 = noise_grad(ix + 1, iy, iz + 1, dx - 1.0f, dy, dz - 1.0f);
@@ -289,31 +298,42 @@ PB_D float turbulence(f3 p, f3 dpdx, f3 dpdy, float omega, int max_octaves) {  /
 
 // ---- MIPMap, core/mipmap.rs:202-391 -----------------------------------------------------------------------------------------------
 PB_D int mip_res(uint32_t r, int l) { return max(1, (int)(r >> l)); }
-PB_D rgb mip_texel(const pbrt_b200_mipmap& m, int level, long long s, long long t) {  // :301-321
-    const long long u = mip_res(m.width, level), v = mip_res(m.height, level);
-    if (m.wrap == PBRT_B200_WRAP_REPEAT) { s = ((s % u) + u) % u; t = ((t % v) + v) % v; }
-    else if (m.wrap == PBRT_B200_WRAP_CLAMP) { s = min(max(s, 0ll), u - 1); t = min(max(t, 0ll), v - 1); }
-    else if (s < 0 || s >= u || t < 0 || t >= v) return rgb(0.0f);
-    size_t off = 0;
-    for (int i = 0; i < level; ++i) off += (size_t)mip_res(m.width, i) * mip_res(m.height, i);
-    const float* p = m.texels + (off + (size_t)t * u + s) * m.channels;
+// One level of a pyramid: resolution (powers of two), float offset of its first texel
+struct MipLevel { int u, v; uint32_t off; };
+PB_D MipLevel mip_level(const pbrt_b200_mipmap& m, int level) {
+    MipLevel L;
+    uint32_t off = 0;
+    for (int i = 0; i < level; ++i) off += (uint32_t)mip_res(m.width, i) * (uint32_t)mip_res(m.height, i);
+    L.u = mip_res(m.width, level); L.v = mip_res(m.height, level); L.off = off;
+    return L;
+}
+// float -> texel coordinate (the reference's `as isize`), kept in 32 bits: coordinates beyond +-2^30 texels -- a texture coordinate of
+// ten thousand image widths at the finest level -- are clamped there instead of wrapping exactly
+PB_D int mip_coord(float f) { return (int)fminf(fmaxf(f, -1073741824.0f), 1073741824.0f); }
+PB_D rgb mip_texel(const pbrt_b200_mipmap& m, const MipLevel& L, int s, int t) {  // :301-321
+    if (m.wrap == PBRT_B200_WRAP_REPEAT) { s &= L.u - 1; t &= L.v - 1; }  // mod_ of a power of two (two's complement: also for negatives)
+    else if (m.wrap == PBRT_B200_WRAP_CLAMP) { s = min(max(s, 0), L.u - 1); t = min(max(t, 0), L.v - 1); }
+    else if (s < 0 || s >= L.u || t < 0 || t >= L.v) return rgb(0.0f);
+    const float* p = m.texels + (size_t)(L.off + (uint32_t)t * (uint32_t)L.u + (uint32_t)s) * m.channels;
     return m.channels == 1 ? rgb(__ldg(p)) : rgb(__ldg(p), __ldg(p + 1), __ldg(p + 2));
 }
 PB_D rgb mip_triangle(const pbrt_b200_mipmap& m, int level, float2 st) {  // :323-335
     level = min(max(level, 0), (int)m.n_levels - 1);
-    float s = st.x * (float)mip_res(m.width, level) - 0.5f, t = st.y * (float)mip_res(m.height, level) - 0.5f;
+    const MipLevel L = mip_level(m, level);
+    float s = st.x * (float)L.u - 0.5f, t = st.y * (float)L.v - 0.5f;
     float fs = floorf(s), ft = floorf(t);
-    long long s0 = (long long)fs, t0 = (long long)ft;
+    int s0 = mip_coord(fs), t0 = mip_coord(ft);
     float ds = s - fs, dt = t - ft;
-    rgb tmp1 = mip_texel(m, level, s0 + 1, t0 + 1) * (ds * dt);
-    rgb tmp2 = mip_texel(m, level, s0 + 1, t0) * (ds * (1.0f - dt));
-    rgb tmp3 = mip_texel(m, level, s0, t0 + 1) * ((1.0f - ds) * dt);
-    rgb tmp4 = mip_texel(m, level, s0, t0) * ((1.0f - ds) * (1.0f - dt));
+    rgb tmp1 = mip_texel(m, L, s0 + 1, t0 + 1) * (ds * dt);
+    rgb tmp2 = mip_texel(m, L, s0 + 1, t0) * (ds * (1.0f - dt));
+    rgb tmp3 = mip_texel(m, L, s0, t0 + 1) * ((1.0f - ds) * dt);
+    rgb tmp4 = mip_texel(m, L, s0, t0) * ((1.0f - ds) * (1.0f - dt));
     return tmp4 + tmp3 + tmp2 + tmp1;
 }
 PB_D rgb mip_ewa(const pbrt_b200_mipmap& m, int level, float2 st, float2 d0, float2 d1) {  // :337-391
-    if (level >= (int)m.n_levels) return mip_texel(m, (int)m.n_levels - 1, 0, 0);
-    const float ur = (float)mip_res(m.width, level), vr = (float)mip_res(m.height, level);
+    if (level >= (int)m.n_levels) return mip_texel(m, mip_level(m, (int)m.n_levels - 1), 0, 0);
+    const MipLevel L = mip_level(m, level);
+    const float ur = (float)L.u, vr = (float)L.v;
     st.x = st.x * ur - 0.5f; st.y = st.y * vr - 0.5f;
     d0.x *= ur; d0.y *= vr; d1.x *= ur; d1.y *= vr;
     float A = d0.y * d0.y + d1.y * d1.y + 1.0f;
@@ -324,19 +344,19 @@ PB_D rgb mip_ewa(const pbrt_b200_mipmap& m, int level, float2 st, float2 d0, flo
     float det = -B * B + 4.0f * A * C;
     float idet = 1.0f / det;
     float usq = sqrtf(det * C), vsq = sqrtf(det * A);
-    long long s0 = (long long)ceilf(st.x - 2.0f * idet * usq), s1 = (long long)floorf(st.x + 2.0f * idet * usq);
-    long long t0 = (long long)ceilf(st.y - 2.0f * idet * vsq), t1 = (long long)floorf(st.y + 2.0f * idet * vsq);
+    const int s0 = mip_coord(ceilf(st.x - 2.0f * idet * usq)), s1 = mip_coord(floorf(st.x + 2.0f * idet * usq));
+    const int t0 = mip_coord(ceilf(st.y - 2.0f * idet * vsq)), t1 = mip_coord(floorf(st.y + 2.0f * idet * vsq));
     rgb sum(0.0f);
     float sum_w = 0.0f;
-    for (long long it = t0; it <= t1; ++it) {
+    for (int it = t0; it <= t1; ++it) {
         float tt = (float)it - st.y;
-        for (long long is = s0; is <= s1; ++is) {
+        for (int is = s0; is <= s1; ++is) {
             float ss = (float)is - st.x;
             float r2 = A * ss * ss + B * ss * tt + C * tt * tt;
             if (r2 < 1.0f) {
                 int index = min((int)f2u_sat(r2 * 128.0f), 127);
                 float wgt = expf(-2.0f * ((float)index / 127.0f)) - expf(-2.0f);  // WEIGHT_LUT, :40-50
-                sum = sum + mip_texel(m, level, is, it) * wgt;
+                sum = sum + mip_texel(m, L, is, it) * wgt;
                 sum_w += wgt;
             }
         }
@@ -350,7 +370,7 @@ static __device__ __noinline__ rgb mip_lookup(const pbrt_b200_mipmap* mp, float2
         float width = fmaxf(fmaxf(fabsf(d0.x), fabsf(d0.y)), fmaxf(fabsf(d1.x), fabsf(d1.y)));
         float level = (float)(L - 1) + log2f(fmaxf(width, 1.0e-8f));
         if (level < 0.0f) return mip_triangle(m, 0, st);
-        if (level >= (float)(L - 1)) return mip_texel(m, L - 1, 0, 0);
+        if (level >= (float)(L - 1)) return mip_texel(m, mip_level(m, L - 1), 0, 0);
         float il = floorf(level), delta = level - il;
         return mip_triangle(m, (int)il, st) * (1.0f - delta) + mip_triangle(m, (int)il + 1, st) * delta;
     }

@@ -103,6 +103,98 @@ def test_malformed_scene_tables_are_rejected_on_the_host(pkg):
     assert rc == 1 and ("not a tree" in msg or "malformed" in msg or "deeper" in msg), (rc, msg)
 
 
+def test_bvh_structure_check_fast_path_and_general_pass_agree(pkg):
+    """scene_create checks the LinearBVHNode array with a segmented pre-order scan (four host threads, stitched like matched
+    parentheses) and falls back to the general pass for arrays that are trees but not in pre-order.  Valid arrays of every size -- below
+    and above the multi-segment threshold -- must pass (rc = NO_DEVICE here, never INVALID), and every mutation must be caught."""
+    lib = pkg.load_library()
+    H = pkg.host
+    rng = np.random.default_rng(11)
+
+    def create(nodes, n_prims):
+        fs = H.FlatScene()
+        fs.nodes = np.ascontiguousarray(nodes)
+        fs.prims = np.zeros(n_prims, H.PRIM_DTYPE)
+        fs.prims["shape_kind"] = 1  # spheres: no index buffers needed
+        fs.prims["material"] = -1
+        fs.prims["area_light"] = -1
+        fs.spheres = np.zeros(1, H.SPHERE_DTYPE)
+        d = fs.desc()
+        out = C.c_void_p()
+        rc = lib.pbrt_b200_scene_create(C.byref(d), 0, C.byref(out))
+        if rc == 0:
+            lib.pbrt_b200_scene_destroy(out)
+        return rc, lib.pbrt_b200_last_error().decode()
+
+    ok = (0, 2)  # created (GPU box) or "no CUDA device" (here): the tables passed
+    for n in (3, 1000, 70_000):
+        c = rng.uniform(-10, 10, (n, 3)).astype(np.float32)
+        nodes, order = H.bvh_build(np.concatenate([c - 0.01, c + 0.01], axis=1), 4, "sah")
+        rc, msg = create(nodes, n)
+        assert rc in ok, (n, rc, msg)
+        if n < 1000:
+            continue
+        interior = np.flatnonzero(nodes["n_prims"] == 0)
+        leaves = np.flatnonzero(nodes["n_prims"] != 0)
+        for trial in range(6):
+            bad = nodes.copy()
+            if trial == 0:
+                bad[interior[len(interior) // 2]]["offset"] += 1            # second child off by one: two parents / unreachable node
+            elif trial == 1:
+                bad[interior[-1]]["offset"] = len(nodes) + 5                 # child out of range
+            elif trial == 2:
+                bad[leaves[len(leaves) // 3]]["offset"] = n                  # leaf refers past the primitive table
+            elif trial == 3:
+                bad[interior[len(interior) // 3]]["axis"] = 3
+            elif trial == 4:
+                bad[leaves[len(leaves) // 2]]["n_prims"] = 0                 # a leaf turned into an interior node with a stale offset
+                bad[leaves[len(leaves) // 2]]["offset"] = 1
+            else:
+                bad = bad[:-1]                                               # the array ends inside a sub-tree
+            rc, msg = create(bad, n)
+            assert rc == 1, (n, trial, rc, msg)
+    # a valid tree that is NOT in pre-order (sub-tree of node 1 = {1, 2, 4}): accepted through the general pass
+    t = np.zeros(5, H.NODE_DTYPE)
+    t[0]["offset"], t[1]["offset"] = 3, 4
+    for leaf, first in ((2, 0), (3, 1), (4, 2)):
+        t[leaf]["n_prims"], t[leaf]["offset"] = 1, first
+    rc, msg = create(t, 3)
+    assert rc in ok, (rc, msg)
+
+    # depth: the traversal stacks one far child per level, 64 entries (bvh.rs:722).  A right-leaning chain keeps the number of PENDING second
+    # children at one, so a check that looked at the stack height instead of the depth would pass it
+    def chain(depth, tail_nodes=None):
+        rows = []
+        for k in range(depth):  # interior k: first child = leaf 2k+1, second child = interior 2k+2
+            rows.append((0, 2 * k + 2))
+            rows.append((1, 0))
+        rows.append((1, 0))
+        a = np.zeros(len(rows), H.NODE_DTYPE)
+        for i, (np_, off) in enumerate(rows):
+            a[i]["n_prims"], a[i]["offset"] = np_, off
+        return a
+
+    assert create(chain(63), 1)[0] in ok
+    rc, msg = create(chain(64), 1)
+    assert rc == 1 and "deeper" in msg, (rc, msg)
+    # ... and the same two chains hanging off the far end of a big balanced tree (several scan segments)
+    c = rng.uniform(-10, 10, (70_000, 3)).astype(np.float32)
+    big, _ = H.bvh_build(np.concatenate([c - 0.01, c + 0.01], axis=1), 4, "sah")
+    last_leaf = len(big) - 1
+    assert big[last_leaf]["n_prims"] != 0
+    d0 = 0  # depth of the last leaf = number of interior nodes whose sub-tree contains it
+    i = 0
+    while big[i]["n_prims"] == 0:
+        d0 += 1
+        i = int(big[i]["offset"])  # the last node is always reached through second children
+    for extra, want_ok in ((63 - d0, True), (64 - d0, False)):
+        tail = chain(extra)
+        tail["offset"][tail["n_prims"] == 0] += last_leaf
+        both = np.concatenate([big[:last_leaf], tail])
+        rc, msg = create(both, 70_000)
+        assert (rc in ok) == want_ok, (extra, rc, msg)
+
+
 def test_film_resolve_matches_oracle(pkg, oracle):
     """Film::write_image arithmetic (film.rs:217-264) is host code in the product library: compare with the oracle."""
     rng = np.random.RandomState(0)

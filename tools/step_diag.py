@@ -9,7 +9,7 @@ import os
 SCENE = os.environ.get("DIAG_SCENE", "s3")
 SPP = int(os.environ.get("DIAG_SPP", "16"))
 setup = {"s3": P.scenes.displaced_sphere_scene, "s4": P.scenes.foliage_field_scene, "cornell": P.scenes.cornell_scene,
-         "s5": lambda: P.scenes.glass_knot_scene(nu=4096, nv=640)}[SCENE]()
+         "s5": lambda: P.scenes.glass_knot_scene(nu=4096, nv=640), "t1": lambda: P.scenes.textured_scene(xres=1920, yres=1080)}[SCENE]()
 integ = setup.make_integrator(spp_=SPP * 16)
 film = integ.film
 sc = P.Scene(setup.flat)
