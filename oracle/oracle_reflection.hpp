@@ -352,8 +352,9 @@ struct BSDF {
     Float eta = 1;
     V3 ns, ng, ss, ts;
     int n_bxdfs = 0;
-    BxDF bxdfs[5];  // uber adds up to five (uber.rs:41-112)
+    union { BxDF bxdfs[5]; };  // uber adds up to five (uber.rs:41-112); a union member is not default-constructed: only added lobes are ever written
     bool valid = false;  // si.bsdf is Some
+    BSDF() {}
 
     void init(const SurfaceInteraction& si, Float eta_) {  // BSDF::new
         eta = eta_; ns = si.sh_n; ss = normalize(si.sh_dpdu); ng = si.n; ts = cross(ns, ss); n_bxdfs = 0; valid = true;
