@@ -310,13 +310,22 @@ def test_reference_scene_files_lex_and_parse():
     m = PLY.read_ply(str(REF_SCENES / "geometry" / "mesh_00001.ply"))  # the 88k-triangle caustic glass mesh
     assert m["P"].shape == (44034, 3) and m["indices"].shape == (88064, 3) and m["N"].shape == (44034, 3)
     # the same geometry with the path integrator: flattens, BVH builds, every triangle is referenced exactly once
+    # (its materials -- glass and uber -- are on the device path since round 2; only the sppm integrator is not)
     text = (REF_SCENES / "caustic-glass.pbrt").read_text().replace('Integrator "sppm" "integer numiterations" [10000] "float radius" .075',
-                                                                   'Integrator "path"').replace('Material "uber"', 'Material "plastic"')
-    text = text.replace('"float index" [ 1 ] ', "").replace('"rgb Kt" [ 0 0 0 ]', "").replace('"rgb opacity" [ 1 1 1 ]', "")
+                                                                   'Integrator "path" "integer maxdepth" [4]\nSampler "sobol" "integer pixelsamples" [1]')
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         job = pkg.pbrt_parse_string(text, search_dir=str(REF_SCENES)).jobs[0]
     assert len(job.flat.tri_indices) == 88064 + 2 and len(job.flat.lights) == 2
+    assert job.flat.materials["type"].tolist() == [pkg.host.MAT_GLASS, pkg.host.MAT_UBER] and job.flat.materials["textured"].tolist() == [0, 1]
+    ext = job.flat.material_ext[1]
+    assert np.allclose(ext["s_const"][0], 0.64) and np.allclose(ext["s_const"][1], 0.1) and np.allclose(ext["s_const"][4], 1.0)
+    assert np.allclose(ext["f_const"], [0.010408, 0.010408, 1.0]) and len(job.flat.textures) == 0
+    # the oracle renders it (a 48-tile strip of the 700 x 1000 frame, 1 spp): finite, lit
+    from oracle import oracle as O
+    nt = job.integrator.n_tiles()
+    rgbw, st = O.render(job.flat, job.integrator, tile_range=(nt // 2, nt // 2 + 48))
+    assert np.isfinite(rgbw).all() and st["camera_rays"] > 10000 and rgbw[:, :3].sum() > 0
     tri = job.flat.prims[job.flat.prims["shape_kind"] == pkg.host.SHAPE_TRIANGLE]
     assert sorted(tri["shape_index"].tolist()) == list(range(88066))
     assert job.film.full_resolution == (700, 1000) and job.film.scale == 1.5
