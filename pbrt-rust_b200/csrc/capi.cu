@@ -266,8 +266,8 @@ int validate_mipmaps(const pbrt_b200_scene_desc* d) {
     for (uint64_t i = 0; i < d->n_mipmaps; ++i) {
         const pbrt_b200_mipmap& m = d->mipmaps[i];
         if (!m.texels || (m.channels != 1 && m.channels != 3) || m.width == 0 || m.height == 0 || (m.width & (m.width - 1)) || (m.height & (m.height - 1)) ||
-            m.wrap > PBRT_B200_WRAP_CLAMP)
-            return fail(PBRT_B200_ERR_INVALID, "scene_create: malformed mipmap (power-of-two level 0, 1 or 3 channels)");
+            m.wrap > PBRT_B200_WRAP_CLAMP || !(m.max_anisotropy >= 0.0f))
+            return fail(PBRT_B200_ERR_INVALID, "scene_create: malformed mipmap (power-of-two level 0, 1 or 3 channels, max_anisotropy >= 0)");
         uint32_t big = m.width > m.height ? m.width : m.height, levels = 1;
         while (big > 1) { big >>= 1; levels += 1; }
         if (m.n_levels != levels) return fail(PBRT_B200_ERR_INVALID, "scene_create: mipmap n_levels must be 1 + log2(max(width, height))");

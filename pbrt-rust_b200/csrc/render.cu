@@ -707,8 +707,9 @@ PB_D void generate_ray(const pbrt_b200_camera& c, float2 pfilm, float time_u, fl
 #define PB_ST_HAS_DIFF 0x20000u /* beta_st.w: the slot's ray carries differentials (a camera ray, or a specular bounce of one under whitted / directlighting) */
 // The differential half of PerspectiveCamera::generate_ray_differential (cameras/perspective.rs:144-176; dx_camera / dy_camera :64-70),
 // then Ray::scale_differential(1 / sqrt(spp)) as the render loop applies it (integrator.rs:341, ray.rs:34-41).  o / d: the world ray.
-static __device__ __noinline__ void camera_differentials(const pbrt_b200_camera* cp, float2 pfilm, float2 plens, f3 o, f3 d, uint32_t spp, float4* out, size_t slot) {
-    const pbrt_b200_camera& c = *cp;
+// (inlined on purpose: an out-of-line call would take the address of the kernel parameter `R.camera`, and ptxas then copies the whole
+// parameter block into a 1.3 KB local-memory frame in every thread of k_finish_regen -- textured scene or not)
+PB_D void camera_differentials(const pbrt_b200_camera& c, float2 pfilm, float2 plens, f3 o, f3 d, uint32_t spp, float4* out, size_t slot) {
     const f3 pc = xf_point(c.raster_to_camera, f3(pfilm.x, pfilm.y, 0.0f));
     const f3 p2t = xf_point(c.raster_to_camera, f3(0.f, 0.f, 0.f));
     const f3 dxc = xf_point(c.raster_to_camera, f3(1.f, 0.f, 0.f)) - p2t, dyc = xf_point(c.raster_to_camera, f3(0.f, 1.f, 0.f)) - p2t;
@@ -838,7 +839,7 @@ PB_D bool gen_camera_path(const RenderDev& R, unsigned long long item, uint32_t 
     R.ray[2 * slot + 1] = make_float4(d.x, d.y, d.z, time);
     R.L_eta[slot] = make_float4(0.f, 0.f, 0.f, 1.0f);
     R.beta_st[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(R.rdiff ? PB_ST_HAS_DIFF : 0u));
-    if (R.rdiff) camera_differentials(&R.camera, pfilm, plens, o, d, R.sampler.spp, R.rdiff, slot);
+    if (R.rdiff) camera_differentials(R.camera, pfilm, plens, o, d, R.sampler.spp, R.rdiff, slot);
     R.pfilm[slot] = pfilm;
     R.s_index[slot] = c.index;
     R.s_dim[slot] = c.dim;
@@ -1870,7 +1871,7 @@ PB_D bool zt_next_path(const RenderDev& R, uint32_t j, bool first) {
     R.ray[2 * j + 1] = make_float4(d.x, d.y, d.z, time);
     R.L_eta[j] = make_float4(0.f, 0.f, 0.f, 1.0f);
     R.beta_st[j] = make_float4(1.f, 1.f, 1.f, __uint_as_float(R.rdiff ? PB_ST_HAS_DIFF : 0u));
-    if (R.rdiff) camera_differentials(&R.camera, pfilm, plens, o, d, R.zt.spp, R.rdiff, j);
+    if (R.rdiff) camera_differentials(R.camera, pfilm, plens, o, d, R.zt.spp, R.rdiff, j);
     R.pfilm[j] = pfilm;
     R.pixel[j] = (uint32_t)(x - R.sampler.sb[0]) | ((uint32_t)(y - R.sampler.sb[1]) << 16);
     if (R.rec.kind) { R.rec.sp[j] = 0; R.rec.arr[j] = 0; }

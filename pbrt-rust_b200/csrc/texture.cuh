@@ -8,6 +8,7 @@
 namespace pb {
 
 #define PB_TEX_STACK 8 /* operands of one postfix texture program (host.py: TEX_STACK_LIMIT) */
+#define PB_EWA_MAX_SPAN 2048 /* texels per axis one EWA lookup may scan (mip_ewa) */
 
 // RayDifferential (core/geometry/ray.rs:18-42) of the ray that hit the surface
 struct RayDiff {
@@ -242,14 +243,25 @@ static __device__ const unsigned char c_noise_perm[512] = {
     228, 251, 34, 242, 193, 238, 210, 144, 12, 191, 179, 162, 241, 81, 51, 145, 235, 249, 14, 239, 107, 49, 192, 214, 31, 181, 199, 106, 157, 184, 84,
     204, 176, 115, 121, 50, 45, 127, 4, 150, 254, 138, 236, 205, 93, 222, 114, 67, 29, 24, 72, 243, 141, 128, 195, 78, 66, 215, 61, 156, 180};
 
+// The noise functions are written with __fmul_rn / __fadd_rn: this file is compiled with --use_fast_math (shade.o), which contracts a * b + c,
+// and a bump map differentiates its texture numerically over a pixel footprint (material.rs:46-87: (displace(p + du dpdu) - displace(p)) / du
+// with du ~ 1e-4 at 1080p).  Rounding that differs from the CPU's per evaluation is noise of ~1e-7 / du in the slope -- enough to turn the
+// shading normal by 1e-4 rad and flip a grazing same_hemisphere test once in 10^4 samples (T1 at 1920x1080: relMSE 1.4e-3 from eight
+// pixels).  With separately rounded operations the three evaluations are the SAME function of their (slightly different) arguments and the
+// differences cancel to first order: relMSE back to the 1e-6 range (tests/test_gpu_textures.py::test_textured_scene_at_bench_resolution).
+PB_D float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+PB_D float add_rn(float a, float b) { return __fadd_rn(a, b); }
 PB_D float noise_grad(int x, int y, int z, float dx, float dy, float dz) {
     int h = c_noise_perm[c_noise_perm[c_noise_perm[x] + y] + z] & 15;
     float u = (h < 8 || h == 12 || h == 13) ? dx : dy;
     float v = (h < 4 || h == 12 || h == 13) ? dy : dz;
     return ((h & 1) ? -u : u) + ((h & 2) ? -v : v);
 }
-PB_D float noise_weight(float t) { float t3 = t * t * t, t4 = t3 * t; return 6.0f * t4 * t - 15.0f * t4 + 10.0f * t3; }
-PB_D float lerpf(float t, float a, float b) { return a * (1.0f - t) + b * t; }
+PB_D float noise_weight(float t) {
+    const float t3 = mul_rn(mul_rn(t, t), t), t4 = mul_rn(t3, t);
+    return add_rn(add_rn(mul_rn(mul_rn(6.0f, t4), t), -mul_rn(15.0f, t4)), mul_rn(10.0f, t3));
+}
+PB_D float lerpf(float t, float a, float b) { return add_rn(mul_rn(a, add_rn(1.0f, -t)), mul_rn(b, t)); }
 // `x.floor() as usize`: NaN / negative -> 0, saturating above (what Rust's cast does); returns the float the reference subtracts
 PB_D unsigned long long f2u_sat(float f) { return (f != f || f <= 0.0f) ? 0ull : (f >= 1.8446744e19f ? 0xffffffffffffffffull : (unsigned long long)f); }
 // cell = `floor(v) as usize`: (the float the reference subtracts, cell & 255).  Below 2^31 the cast is exact in 32 bits; above, a float is
@@ -264,7 +276,7 @@ PB_D float noise_cell(float f, int* cell) {
 static __device__ __noinline__ float noise3(float x, float y, float z) {
     int ix, iy, iz;
     const float fx = noise_cell(floorf(x), &ix), fy = noise_cell(floorf(y), &iy), fz = noise_cell(floorf(z), &iz);
-    const float dx = x - fx, dy = y - fy, dz = z - fz;
+    const float dx = add_rn(x, -fx), dy = add_rn(y, -fy), dz = add_rn(z, -fz);
     float w000 = noise_grad(ix, iy, iz, dx, dy, dz), w100 = noise_grad(ix + 1, iy, iz, dx - 1.0f, dy, dz);
     float w010 = noise_grad(ix, iy + 1, iz, dx, dy - 1.0f, dz), w110 = noise_grad(ix + 1, iy + 1, iz, dx - 1.0f, dy - 1.0f, dz);
     float w001 = noise_grad(ix, iy, iz + 1, dx, dy, dz - 1.0f), w101 = noise_grad(ix + 1, iy, iz + 1, dx - 1.0f, dy, dz - 1.0f);
@@ -273,15 +285,21 @@ static __device__ __noinline__ float noise3(float x, float y, float z) {
     float x00 = lerpf(wx, w000, w100), x10 = lerpf(wx, w010, w110), x01 = lerpf(wx, w001, w101), x11 = lerpf(wx, w011, w111);
     return lerpf(wz, lerpf(wy, x00, x10), lerpf(wy, x01, x11));
 }
-PB_D float smooth_step(float mn, float mx, float v) { float t = clampf((v - mn) / (mx - mn), 0.0f, 1.0f); return t * t * (-2.0f * t + 3.0f); }
+PB_D float smooth_step(float mn, float mx, float v) {
+    const float t = clampf(__fdiv_rn(add_rn(v, -mn), add_rn(mx, -mn)), 0.0f, 1.0f);
+    return mul_rn(mul_rn(t, t), add_rn(mul_rn(-2.0f, t), 3.0f));
+}
 PB_D float fbm(f3 p, f3 dpdx, f3 dpdy, float omega, int max_octaves) {  // texture.rs:384-405
     float l2 = fmaxf(len2(dpdx), len2(dpdy));
     float n = clampf(-1.0f - 0.5f * (logf(l2) * 1.442695040888963387004650940071f), 0.0f, (float)max_octaves);
     int nint = (int)f2u_sat(floorf(n));
     float sum = 0.0f, lambda = 1.0f, o = 1.0f;
-    for (int i = 0; i < nint; ++i) { sum += o * noise3(p.x * lambda, p.y * lambda, p.z * lambda); lambda *= 1.99f; o *= omega; }
+    for (int i = 0; i < nint; ++i) {
+        sum = add_rn(sum, mul_rn(o, noise3(mul_rn(p.x, lambda), mul_rn(p.y, lambda), mul_rn(p.z, lambda))));
+        lambda = mul_rn(lambda, 1.99f); o = mul_rn(o, omega);
+    }
     float npartial = n - (float)nint;
-    sum += o * smooth_step(0.3f, 0.7f, npartial) * noise3(p.x * lambda, p.y * lambda, p.z * lambda);
+    sum = add_rn(sum, mul_rn(mul_rn(o, smooth_step(0.3f, 0.7f, npartial)), noise3(mul_rn(p.x, lambda), mul_rn(p.y, lambda), mul_rn(p.z, lambda))));
     return sum;
 }
 PB_D float turbulence(f3 p, f3 dpdx, f3 dpdy, float omega, int max_octaves) {  // texture.rs:407-437 (`o + |noise|` as written there)
@@ -289,10 +307,13 @@ PB_D float turbulence(f3 p, f3 dpdx, f3 dpdy, float omega, int max_octaves) {  /
     float n = clampf(-1.0f - 0.5f * log2f(l2), 0.0f, (float)max_octaves);
     int nint = (int)f2u_sat(floorf(n));
     float sum = 0.0f, lambda = 1.0f, o = 1.0f;
-    for (int i = 0; i < nint; ++i) { sum += o + fabsf(noise3(p.x * lambda, p.y * lambda, p.z * lambda)); lambda *= 1.99f; o *= omega; }
+    for (int i = 0; i < nint; ++i) {
+        sum = add_rn(sum, add_rn(o, fabsf(noise3(mul_rn(p.x, lambda), mul_rn(p.y, lambda), mul_rn(p.z, lambda)))));
+        lambda = mul_rn(lambda, 1.99f); o = mul_rn(o, omega);
+    }
     float npartial = n - (float)nint;
-    sum += o + lerpf(smooth_step(0.3f, 0.7f, npartial), 0.2f, fabsf(noise3(p.x * lambda, p.y * lambda, p.z * lambda)));
-    for (int i = nint; i < max_octaves; ++i) { sum += o * 0.2f; o *= omega; }
+    sum = add_rn(sum, add_rn(o, lerpf(smooth_step(0.3f, 0.7f, npartial), 0.2f, fabsf(noise3(mul_rn(p.x, lambda), mul_rn(p.y, lambda), mul_rn(p.z, lambda))))));
+    for (int i = nint; i < max_octaves; ++i) { sum = add_rn(sum, mul_rn(o, 0.2f)); o = mul_rn(o, omega); }
     return sum;
 }
 
@@ -320,15 +341,16 @@ PB_D rgb mip_texel(const pbrt_b200_mipmap& m, const MipLevel& L, int s, int t) {
 PB_D rgb mip_triangle(const pbrt_b200_mipmap& m, int level, float2 st) {  // :323-335
     level = min(max(level, 0), (int)m.n_levels - 1);
     const MipLevel L = mip_level(m, level);
-    float s = st.x * (float)L.u - 0.5f, t = st.y * (float)L.v - 0.5f;
-    float fs = floorf(s), ft = floorf(t);
+    const float s = add_rn(mul_rn(st.x, (float)L.u), -0.5f), t = add_rn(mul_rn(st.y, (float)L.v), -0.5f);
+    const float fs = floorf(s), ft = floorf(t);
     int s0 = mip_coord(fs), t0 = mip_coord(ft);
-    float ds = s - fs, dt = t - ft;
-    rgb tmp1 = mip_texel(m, L, s0 + 1, t0 + 1) * (ds * dt);
-    rgb tmp2 = mip_texel(m, L, s0 + 1, t0) * (ds * (1.0f - dt));
-    rgb tmp3 = mip_texel(m, L, s0, t0 + 1) * ((1.0f - ds) * dt);
-    rgb tmp4 = mip_texel(m, L, s0, t0) * ((1.0f - ds) * (1.0f - dt));
-    return tmp4 + tmp3 + tmp2 + tmp1;
+    const float ds = add_rn(s, -fs), dt = add_rn(t, -ft);
+    // separately rounded, like the noise functions: image maps are bump maps too
+    const rgb a = mip_texel(m, L, s0 + 1, t0 + 1), b = mip_texel(m, L, s0 + 1, t0), c = mip_texel(m, L, s0, t0 + 1), d = mip_texel(m, L, s0, t0);
+    const float w1 = mul_rn(ds, dt), w2 = mul_rn(ds, add_rn(1.0f, -dt)), w3 = mul_rn(add_rn(1.0f, -ds), dt), w4 = mul_rn(add_rn(1.0f, -ds), add_rn(1.0f, -dt));
+    return rgb(add_rn(add_rn(add_rn(mul_rn(d.r, w4), mul_rn(c.r, w3)), mul_rn(b.r, w2)), mul_rn(a.r, w1)),
+               add_rn(add_rn(add_rn(mul_rn(d.g, w4), mul_rn(c.g, w3)), mul_rn(b.g, w2)), mul_rn(a.g, w1)),
+               add_rn(add_rn(add_rn(mul_rn(d.b, w4), mul_rn(c.b, w3)), mul_rn(b.b, w2)), mul_rn(a.b, w1)));
 }
 PB_D rgb mip_ewa(const pbrt_b200_mipmap& m, int level, float2 st, float2 d0, float2 d1) {  // :337-391
     if (level >= (int)m.n_levels) return mip_texel(m, mip_level(m, (int)m.n_levels - 1), 0, 0);
@@ -344,8 +366,13 @@ PB_D rgb mip_ewa(const pbrt_b200_mipmap& m, int level, float2 st, float2 d0, flo
     float det = -B * B + 4.0f * A * C;
     float idet = 1.0f / det;
     float usq = sqrtf(det * C), vsq = sqrtf(det * A);
-    const int s0 = mip_coord(ceilf(st.x - 2.0f * idet * usq)), s1 = mip_coord(floorf(st.x + 2.0f * idet * usq));
-    const int t0 = mip_coord(ceilf(st.y - 2.0f * idet * vsq)), t1 = mip_coord(floorf(st.y + 2.0f * idet * vsq));
+    int s0 = mip_coord(ceilf(st.x - 2.0f * idet * usq)), s1 = mip_coord(floorf(st.x + 2.0f * idet * usq));
+    int t0 = mip_coord(ceilf(st.y - 2.0f * idet * vsq)), t1 = mip_coord(floorf(st.y + 2.0f * idet * vsq));
+    // The level is chosen so that the minor axis is about a texel and the major axis at most max_anisotropy times that: tens of texels.
+    // Non-finite differentials (overflowed derivatives) would make the reference scan 2^64 texels; a kernel must not: PB_EWA_MAX_SPAN
+    // texels per axis, centred on the lookup point, is the most one lookup scans
+    if (s1 - s0 > PB_EWA_MAX_SPAN) { const int c = mip_coord(st.x); s0 = c - PB_EWA_MAX_SPAN / 2; s1 = c + PB_EWA_MAX_SPAN / 2; }
+    if (t1 - t0 > PB_EWA_MAX_SPAN) { const int c = mip_coord(st.y); t0 = c - PB_EWA_MAX_SPAN / 2; t1 = c + PB_EWA_MAX_SPAN / 2; }
     rgb sum(0.0f);
     float sum_w = 0.0f;
     for (int it = t0; it <= t1; ++it) {

@@ -88,6 +88,23 @@ def test_depth_of_field_filters_and_a_baked_instance(pkg, oracle, gpu_lib):
     assert (d < 1e-3).mean() > 0.85
 
 
+def test_textured_scene_at_bench_resolution(pkg, oracle, gpu_lib):
+    """T1 at 1920x1080 (what `bench.py --scene t1` times): a strip of 64 tiles through the image centre at 4 spp against the oracle --
+    camera-ray footprints at this resolution select other MIP levels than the small renders above."""
+    setup = pkg.scenes.textured_scene(xres=1920, yres=1080, spp=4)
+    integ = setup.make_integrator()
+    nt = integ.n_tiles()
+    crop = (nt // 2 - 32, nt // 2 + 32)
+    sc = pkg.Scene(setup.flat)
+    got, st = sc.render(integ, tile_range=crop)
+    sc.close()
+    want, ost = oracle.render(setup.flat, integ, tile_range=crop)
+    m = want[:, 3] > 0
+    assert m.sum() >= 60 * 256 and np.array_equal(got[:, 3] > 0, m) and st.camera_rays == ost["camera_rays"]
+    err = oracle.rel_mse(oracle.film_resolve(got[m], 1.0), oracle.film_resolve(want[m], 1.0))
+    assert err <= REL_MSE_TOL, f"relMSE {err:.3e}"
+
+
 def test_the_reference_texture_scene_renders_like_the_oracle(pkg, oracle, gpu_lib):
     """src/scenes/spheres-differentials-texfilt.pbrt: directlighting, (0,2)-sequence sampler, an EWA-filtered image map on the ground seen
     directly, in a mirror sphere and through a glass sphere (specular_reflect / specular_transmit differentials, integrator.rs:409-520)."""
