@@ -42,6 +42,46 @@ def test_struct_layouts_match_the_header(pkg):
             assert lib.pbrt_b200_struct_size(name.encode()) == py, name
 
 
+def test_struct_layouts_match_what_a_c_compiler_sees(pkg, tmp_path):
+    """include/pbrt_b200.h compiled as C by gcc: sizeof / offsetof of every struct that crosses the boundary equal the numpy dtypes and
+    ctypes Structures the Python host fills (a field added on one side only shifts everything behind it silently)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    H = pkg.host
+    T = __import__("importlib").import_module("pbrt-rust_b200.textures")
+    structs = {"pbrt_b200_bvh_node": H.NODE_DTYPE, "pbrt_b200_prim": H.PRIM_DTYPE, "pbrt_b200_sphere": H.SPHERE_DTYPE, "pbrt_b200_material": H.MATERIAL_DTYPE,
+               "pbrt_b200_light": H.LIGHT_DTYPE, "pbrt_b200_ray": H.RAY_DTYPE, "pbrt_b200_hit": H.HIT_DTYPE, "pbrt_b200_object": H.OBJECT_DTYPE,
+               "pbrt_b200_instance": H.INSTANCE_DTYPE, "pbrt_b200_medium": H.MEDIUM_DTYPE, "pbrt_b200_medium_interface": H.MEDIUM_INTERFACE_DTYPE,
+               "pbrt_b200_texnode": T.TEXNODE_DTYPE, "pbrt_b200_mipmap": T.MIPMAP_DTYPE, "pbrt_b200_texref": T.TEXREF_DTYPE,
+               "pbrt_b200_material_ext": T.MATERIAL_EXT_DTYPE}
+    cstructs = {"pbrt_b200_scene_desc": H.SceneDesc, "pbrt_b200_render_desc": H.RenderDesc, "pbrt_b200_render_stats": H.RenderStats,
+                "pbrt_b200_camera": H.CameraDesc, "pbrt_b200_film": H.FilmDesc, "pbrt_b200_sampler": H.SamplerDesc, "pbrt_b200_integrator": H.IntegratorDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for name, dt in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field in dt.names:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    for name, cs in cstructs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cs._fields_:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines.append("return 0; }")
+    (tmp_path / "abi.c").write_text("\n".join(lines))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(tmp_path / "abi"), str(tmp_path / "abi.c")], check=True)
+    out = dict(l.split() for l in subprocess.run([str(tmp_path / "abi")], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, dt in structs.items():
+        assert int(out[name]) == dt.itemsize, name
+        for field in dt.names:
+            assert int(out[f"{name}.{field}"]) == dt.fields[field][1], (name, field)
+    for name, cs in cstructs.items():
+        assert int(out[name]) == C.sizeof(cs), name
+        for field, _ in cs._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(cs, field).offset, (name, field)
+
+
 def test_no_cpu_fallback_without_a_device(pkg):
     lib = pkg.load_library()
     if lib.pbrt_b200_device_count() > 0:
