@@ -6,9 +6,10 @@ systems, named materials, object instancing), same parameter names and defaults 
 functions.  `WorldEnd` does what `API::world_end` does up to the call of `Integrator::render`
 (api.rs:1715-1747): it flattens the scene into the tables of `pbrt_b200_scene_desc`, builds the BVH through
 `pbrt_b200_bvh_build` and assembles film / camera / sampler / integrator; the result is a `RenderJob` whose
-`render(device)` runs the CUDA path.  Anything the device path does not implement (other integrators, shapes,
-materials, image textures, media, non-perspective cameras) raises `B200Error` naming the feature: there is no
-CPU fallback and no silent substitution.
+`render(device)` runs the CUDA path.  Anything the device path does not implement (other integrators, shapes and
+materials, alpha cut-outs, grid media, image-mapped infinite lights, non-perspective cameras) raises `B200Error` naming the
+feature: there is no CPU fallback and no silent substitution.  Textures (every class of src/textures/, image maps through
+MIPMap pyramids), bump maps, `uber` / `substrate` and homogeneous media are on the device path since round 2.
 
 Reference behaviours kept on purpose (each cited where it is implemented): `Camera` registers the camera space
 under the name "name", not "camera" (api.rs:1210); `ActiveTransform` never restricts which transform a
@@ -499,7 +500,7 @@ class API:
                            to=params.find_one_point3f("to", (0, 0, 1)), **{"from": params.find_one_point3f("from", (0, 0, 0))})
         elif name in ("infinite", "exinfinite"):  # infinite.rs:243-262
             if params.find_one_filename("mapname", ""):
-                raise B200Error("image-mapped infinite lights are outside the hot path (SURVEY.md §8 f3)")
+                raise B200Error("image-mapped infinite lights are outside the device path (constant-radiance infinite lights only)")
             ns = params.find_one_int("samples", params.find_one_int("nsamples", 1))  # infinite.rs:249-250
             if self.opts["quick_render"]:
                 ns = max(1, ns // 4)
@@ -608,7 +609,7 @@ class API:
     def _reject_alpha(self, params):
         for key in ("alpha", "shadowalpha"):
             if params.find_texture(key, "") or params.find_one_float(key, 1.0) == 0.0:
-                raise B200Error(f'"{key}" cut-out textures are outside the hot path (SURVEY.md §8 f3)')
+                raise B200Error(f'"{key}" cut-out textures are outside the device path')
 
     # --- object instancing (api.rs:1630-1713) -------------------------------------------------------
     def object_begin(self, name):

@@ -215,19 +215,6 @@ class ParamSet:
                     warnings.warn(f'Parameter "{name}" not used{where}')
 
 
-class UnsupportedTexture:
-    """A texture the scene file declared but the device path cannot evaluate: an error only if a material uses it (the
-    reference's own spheres scene declares a checkerboard it never references)."""
-
-    def __init__(self, name, texname):
-        self.name, self.texname = name, texname
-
-    def error(self):
-        from .host import B200Error
-        return B200Error(f'Texture "{self.name}" ("{self.texname}"): only constant-valued textures exist on the device path; image maps and '
-                         "procedural textures are SURVEY.md §8 f3")
-
-
 class TextureParams:
     """paramset.rs:443-610: shape parameters shadow the material's; textures resolve by name.
 
@@ -277,8 +264,6 @@ class TextureParams:
             if not name:
                 return None
         if name in table:
-            if isinstance(table[name], UnsupportedTexture):
-                raise table[name].error()
             return table[name]
         warnings.warn(f'Couldn\'t find {kind} texture named "{name}" for parameter "{n}"')
         return None
