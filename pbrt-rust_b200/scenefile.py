@@ -16,6 +16,7 @@ import os
 import numpy as np
 
 from . import host as H
+from . import textures as T
 from .plymesh import write_ply
 
 f32 = np.float32
@@ -45,6 +46,9 @@ def _params(kind, name, kw):
     for k, v in kw.items():
         if v is None:
             continue
+        if T.is_texture(v):
+            raise H.B200Error(f'write_pbrt: parameter "{k}" of {kind} "{name}" is a texture tree built through the Python API; the writer emits '
+                              "constants only (textured scenes come from scene files, not the other way round)")
         if isinstance(v, (bool, np.bool_)):
             out.append(f'"bool {k}" ["{"true" if v else "false"}"]')
         elif k in ("from", "to"):
