@@ -897,6 +897,23 @@ __global__ void PB_TRACE_BOUNDS k_trace_closest(RenderDev R, int parity) {
     PathClosestJob job{&R, R.q_path[parity]};
     trace_queue<false, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
+// Min resident CTAs per SM of the INSTANCED closest-hit / any-hit kernels (explicit specialisations: the plain kernels keep the compiler's
+// own choice, 72 registers; note that __launch_bounds__(n, 1) is NOT "no constraint" -- it lets ptxas take 126 registers there).  Left to
+// itself ptxas gives the two-level walk 96 / 80 registers = 5 / 6 CTAs of 128 threads; on S4 (gpurun_out/r2_s4_minb.log, 4-spp 4K step):
+// default 303.9 ms, 6 CTAs (80 regs, closest only) 288.8, 7 CTAs (72 regs, both, 6-92 B of spills) 285.2, 8 CTAs (64 regs) 309.6.
+#ifndef PB_TRACE_MINB_INST
+#define PB_TRACE_MINB_INST 7
+#endif
+#ifndef PB_TRACE_MINB_INST_ANY
+#define PB_TRACE_MINB_INST_ANY 7
+#endif
+#if PB_TRACE_MINB_INST > 0
+template <>
+__global__ void __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB_INST) k_trace_closest<true>(RenderDev R, int parity) {
+    PathClosestJob job{&R, R.q_path[parity]};
+    trace_queue<false, true, PB_SH_STACK>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
+}
+#endif
 
 // sort/compact-by-material.  Lanes of the same bin form a group (match.any) and the groups of the CTA's eight warps are
 // added up in shared memory: one atomicAdd per bin per 256 paths (the per-warp form waited on the atomic's round trip for 83 % of
@@ -1685,6 +1702,13 @@ __global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
     ShadowJob job{&R};
     trace_queue<true, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
+#if PB_TRACE_MINB_INST_ANY > 0
+template <>
+__global__ void __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB_INST_ANY) k_trace_shadow<true>(RenderDev R) {
+    ShadowJob job{&R};
+    trace_queue<true, true, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
+}
+#endif
 #endif  // PB_EXACT_TU
 
 // ---------------------------------------------------------------------------
