@@ -41,7 +41,7 @@
 #define PB_TRACE_BOUNDS __launch_bounds__(PB_TRACE_BLOCK)
 #endif
 
-// This file is compiled TWICE (csrc/Makefile):
+// This file is compiled THREE times (csrc/Makefile; mega.o -- the one-kernel forms -- is described where PB_MEGA_TU is defined below):
 //   render.o  (PB_EXACT_TU = 1, --fmad=false, IEEE division / square root): ray generation, traversal, film, light tables, the
 //             (0,2) megakernel and the host side -- everything whose arithmetic is pinned bit for bit against the oracle;
 //   shade.o   (shade.cu defines PB_TU_SHADE and includes this file; --use_fast_math): only k_shade / k_rec_shade and their
