@@ -907,6 +907,13 @@ __global__ void PB_TRACE_BOUNDS k_trace_closest(RenderDev R, int parity) {
 #ifndef PB_TRACE_MINB_INST_ANY
 #define PB_TRACE_MINB_INST_ANY 7
 #endif
+#ifdef PB_TRACE_MINB_PLAIN  /* A/B knob: the plain closest-hit kernel alone */
+template <>
+__global__ void __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB_PLAIN) k_trace_closest<false>(RenderDev R, int parity) {
+    PathClosestJob job{&R, R.q_path[parity]};
+    trace_queue<false, false, PB_SH_STACK>(R.scene, job, R.cnt->n_path, &R.cnt->fetch_path, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
+}
+#endif
 #if PB_TRACE_MINB_INST > 0
 template <>
 __global__ void __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB_INST) k_trace_closest<true>(RenderDev R, int parity) {
@@ -1702,6 +1709,13 @@ __global__ void PB_TRACE_BOUNDS k_trace_shadow(RenderDev R) {
     ShadowJob job{&R};
     trace_queue<true, INST, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
 }
+#ifdef PB_TRACE_MINB_PLAIN_ANY  /* A/B knob (profiles/r02_ab_logs.md): the plain any-hit kernel alone */
+template <>
+__global__ void __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB_PLAIN_ANY) k_trace_shadow<false>(RenderDev R) {
+    ShadowJob job{&R};
+    trace_queue<true, false, PB_SH_STACK>(R.scene, job, R.cnt->n_shadow, &R.cnt->fetch_shadow, TraceTune{PB_WF_REFILL_BELOW, PB_FETCH_CHUNK, PB_INTERIOR_MIN});
+}
+#endif
 #if PB_TRACE_MINB_INST_ANY > 0
 template <>
 __global__ void __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB_INST_ANY) k_trace_shadow<true>(RenderDev R) {
@@ -2992,6 +3006,11 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     int trace_per_sm = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_per_sm, sc->dev.n_instances ? k_trace_closest<true> : k_trace_closest<false>, PB_TRACE_BLOCK, 0);
     int grid_trace = sm_count * (trace_per_sm > 0 ? trace_per_sm : 1);  // persistent: exactly one resident wave
+    // ... of EACH kernel: the any-hit and MIS kernels have their own register allocation, hence their own number of resident CTAs
+    int shadow_per_sm = trace_per_sm, mis_per_sm = trace_per_sm;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadow_per_sm, sc->dev.n_instances ? k_trace_shadow<true> : k_trace_shadow<false>, PB_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mis_per_sm, sc->dev.n_instances ? k_trace_mis<true> : k_trace_mis<false>, PB_TRACE_BLOCK, 0);
+    int grid_shadow = sm_count * (shadow_per_sm > 0 ? shadow_per_sm : 1), grid_mis = sm_count * (mis_per_sm > 0 ? mis_per_sm : 1);
     // shade kernels keep 5 CTAs of 128 threads resident per SM (96-104 registers): 10 per SM = two full waves (8 left a
     // 3-CTA tail wave: -1.5 % on S3, gpurun_out/ab4.log)
     int grid_shade = sm_count * 20, grid_small = sm_count * 4;  // shade: 10 -> 20 CTAs per SM: 35.4 -> 35.2 ms per 16-spp S3 step (gpurun_out/r2o_grid.log)
@@ -3000,6 +3019,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
     if (zt) {  // tile-serial: at most one path per tile in flight -- a few CTAs cover the queues
         const int need = (int)((capacity + 127u) / 128u);
         grid_trace = std::min(grid_trace, need); grid_shade = std::min(grid_shade, need); grid_small = std::min(grid_small, need);
+        grid_shadow = std::min(grid_shadow, need); grid_mis = std::min(grid_mis, need);
     }
 
     cudaStream_t stream = 0;
@@ -3165,11 +3185,11 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
                 launch_shade_kernels(R, parity, full, grid_small, grid_shade, stream);
                 if (timing) mark();
-                if (inst) k_trace_shadow<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
-                else k_trace_shadow<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                if (inst) k_trace_shadow<true><<<grid_shadow, PB_TRACE_BLOCK, 0, stream>>>(R);
+                else k_trace_shadow<false><<<grid_shadow, PB_TRACE_BLOCK, 0, stream>>>(R);
                 if (timing) mark();
-                if (inst) k_trace_mis<true><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
-                else k_trace_mis<false><<<grid_trace, PB_TRACE_BLOCK, 0, stream>>>(R);
+                if (inst) k_trace_mis<true><<<grid_mis, PB_TRACE_BLOCK, 0, stream>>>(R);
+                else k_trace_mis<false><<<grid_mis, PB_TRACE_BLOCK, 0, stream>>>(R);
                 if (timing) mark();
                 }
                 if (zt) k_finish_zt<<<grid_small, 128, 0, stream>>>(R, parity);
