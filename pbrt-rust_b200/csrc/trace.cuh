@@ -25,6 +25,14 @@
 #ifndef PB_PREFETCH_FAR
 #define PB_PREFETCH_FAR 0
 #endif
+#ifndef PB_CQUAD
+#define PB_CQUAD 0  /* 1 (A/B, VERDICT n1): COMPRESSED quad nodes -- 64 B instead of 128: the four child boxes as 8-bit planes on a per-node power-of-two
+                       grid anchored at the node's lower corner (the CWBVH encoding of Ylitie et al. 2017, four wide), decoded in ray space with one
+                       FFMA per plane; the boxes are conservative (floor / ceil plus one quantum of slack), the visiting order is the reference's.
+                       Measured on B200 (profiles/r02_cquad.md): 8 M hit records bit-identical, camera batch -9 %, bounce batch -6 %, shadow batch -11 %,
+                       S3 frame -5.5 % (closest 14.4 -> 15.8 ms): the 77 MB of full-precision quad nodes already live in L2, the decode is serial work in
+                       front of the slab test, and the looser boxes are entered more often.  2: the same with the PRMT decode (see quad_step). */
+#endif
 #ifndef PB_LAZY_SHEAR
 #define PB_LAZY_SHEAR 0  /* 1: at instance boundaries the shear constants wait for the first triangle tested.  Measured on S4: +-0 (closest 230.7 -> 230.2 ms, shadow 69 -> 72 ms per 4-spp step) */
 #endif
@@ -571,6 +579,55 @@ PB_D void trav_run_impl(const DevScene& s, TravRay& r, STK stack, int yield_belo
 // components (slab_fast's precondition; the others take the binary, NaN-exact walk).
 template <bool ANY, typename STK>
 PB_D void quad_step(const DevScene& s, TravRay& r, STK stack) {
+#if PB_CQUAD
+    // {lower corner, ex | ey << 8 | ez << 16 | meta << 24}, {refs}, {lo.x[4], lo.y[4], lo.z[4], hi.x[4]}, {hi.y[4], hi.z[4], -, -}
+    const float4* np = s.cquads + 4ull * r.cur;
+    const float4 hd = __ldg(np), q6 = __ldg(np + 1), qa = __ldg(np + 2), qb = __ldg(np + 3);
+    const uint32_t hb = __float_as_uint(hd.w);
+    // plane = corner + q * 2^e  ->  t = q * (2^e / d) + (corner - o) / d : one FFMA per plane (f32x2: two children per issue slot)
+    const float ax = __uint_as_float((hb & 0xffu) << 23) * r.ivx.x, ay = __uint_as_float(((hb >> 8) & 0xffu) << 23) * r.ivy.x, az = __uint_as_float(((hb >> 16) & 0xffu) << 23) * r.ivz.x;
+#if PB_CQUAD == 2
+    // decode variant: a byte becomes the float 2^23 + q with one PRMT (I2F.U8 runs on the quarter-rate conversion pipe) and the 2^23 is folded into the
+    // constant term.  Faster than I2F (profiles/r02_cquad.md) but the fold's rounding (up to half a quantum) is not covered at the corner planes, which
+    // have no slack below q = 0: 27-388 of 2 M hit records differ.  Kept for the timing only.
+    const float bx = __fmaf_rn(-8388608.0f, ax, (hd.x + r.nox.x) * r.ivx.x), by = __fmaf_rn(-8388608.0f, ay, (hd.y + r.noy.x) * r.ivy.x),
+                bz = __fmaf_rn(-8388608.0f, az, (hd.z + r.noz.x) * r.ivz.x);
+#else
+    const float bx = (hd.x + r.nox.x) * r.ivx.x, by = (hd.y + r.noy.x) * r.ivy.x, bz = (hd.z + r.noz.x) * r.ivz.x;
+#endif
+    const float2 Ax = make_float2(ax, ax), Ay = make_float2(ay, ay), Az = make_float2(az, az), Bx = make_float2(bx, bx), By = make_float2(by, by), Bz = make_float2(bz, bz);
+    const uint32_t lox = __float_as_uint(qa.x), loy = __float_as_uint(qa.y), loz = __float_as_uint(qa.z), hix = __float_as_uint(qa.w), hiy = __float_as_uint(qb.x), hiz = __float_as_uint(qb.y);
+    const uint32_t wnx = r.ngx ? hix : lox, wny = r.ngy ? hiy : loy, wnz = r.ngz ? hiz : loz, wfx = r.ngx ? lox : hix, wfy = r.ngy ? loy : hiy, wfz = r.ngz ? loz : hiz;
+#if PB_CQUAD == 2
+#define PB_Q01(w) make_float2(__uint_as_float(__byte_perm((w), 0x4B000000u, 0x7540)), __uint_as_float(__byte_perm((w), 0x4B000000u, 0x7541)))
+#define PB_Q23(w) make_float2(__uint_as_float(__byte_perm((w), 0x4B000000u, 0x7542)), __uint_as_float(__byte_perm((w), 0x4B000000u, 0x7543)))
+#else
+#define PB_Q01(w) make_float2((float)((w) & 0xffu), (float)(((w) >> 8) & 0xffu))
+#define PB_Q23(w) make_float2((float)(((w) >> 16) & 0xffu), (float)((w) >> 24))
+#endif
+    const float wdn = 1.0f + 2.0f * gamma_n(3);
+    const float2 widen = make_float2(wdn, wdn);
+    SlabPair pa, pb;
+    {
+        const float2 tx0 = __ffma2_rn(PB_Q01(wnx), Ax, Bx), ty0 = __ffma2_rn(PB_Q01(wny), Ay, By), tz0 = __ffma2_rn(PB_Q01(wnz), Az, Bz);
+        const float2 tx1 = __fmul2_rn(__ffma2_rn(PB_Q01(wfx), Ax, Bx), widen), ty1 = __fmul2_rn(__ffma2_rn(PB_Q01(wfy), Ay, By), widen), tz1 = __fmul2_rn(__ffma2_rn(PB_Q01(wfz), Az, Bz), widen);
+        pa.tmin0 = fmaxf(fmaxf(tx0.x, ty0.x), tz0.x); pa.tmin1 = fmaxf(fmaxf(tx0.y, ty0.y), tz0.y);
+        const float m0 = fminf(fminf(tx1.x, ty1.x), tz1.x), m1 = fminf(fminf(tx1.y, ty1.y), tz1.y);
+        pa.ok0 = (pa.tmin0 <= m0) && (m0 > 0.0f) && __float_as_uint(q6.x) != PB_REF_NONE;
+        pa.ok1 = (pa.tmin1 <= m1) && (m1 > 0.0f) && __float_as_uint(q6.y) != PB_REF_NONE;
+    }
+    {
+        const float2 tx0 = __ffma2_rn(PB_Q23(wnx), Ax, Bx), ty0 = __ffma2_rn(PB_Q23(wny), Ay, By), tz0 = __ffma2_rn(PB_Q23(wnz), Az, Bz);
+        const float2 tx1 = __fmul2_rn(__ffma2_rn(PB_Q23(wfx), Ax, Bx), widen), ty1 = __fmul2_rn(__ffma2_rn(PB_Q23(wfy), Ay, By), widen), tz1 = __fmul2_rn(__ffma2_rn(PB_Q23(wfz), Az, Bz), widen);
+        pb.tmin0 = fmaxf(fmaxf(tx0.x, ty0.x), tz0.x); pb.tmin1 = fmaxf(fmaxf(tx0.y, ty0.y), tz0.y);
+        const float m0 = fminf(fminf(tx1.x, ty1.x), tz1.x), m1 = fminf(fminf(tx1.y, ty1.y), tz1.y);
+        pb.ok0 = (pb.tmin0 <= m0) && (m0 > 0.0f) && __float_as_uint(q6.z) != PB_REF_NONE;
+        pb.ok1 = (pb.tmin1 <= m1) && (m1 > 0.0f) && __float_as_uint(q6.w) != PB_REF_NONE;
+    }
+#undef PB_Q01
+#undef PB_Q23
+    const float4 q7 = make_float4(__uint_as_float(hb >> 24), 0.0f, 0.0f, 0.0f);
+#else
     const float4* np = s.quads + 8ull * r.cur;
     const float4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2), b0 = __ldg(np + 3), b1 = __ldg(np + 4), b2 = __ldg(np + 5), q6 = __ldg(np + 6), q7 = __ldg(np + 7);
     SlabPair pa = slab_fast2(r.ngx ? make_float2(a1.z, a1.w) : make_float2(a0.x, a0.y), r.ngy ? make_float2(a2.x, a2.y) : make_float2(a0.z, a0.w),
@@ -581,6 +638,7 @@ PB_D void quad_step(const DevScene& s, TravRay& r, STK stack) {
                              r.ngz ? make_float2(b2.z, b2.w) : make_float2(b1.x, b1.y), r.ngx ? make_float2(b0.x, b0.y) : make_float2(b1.z, b1.w),
                              r.ngy ? make_float2(b0.z, b0.w) : make_float2(b2.x, b2.y), r.ngz ? make_float2(b1.x, b1.y) : make_float2(b2.z, b2.w),
                              r.nox, r.noy, r.noz, r.ivx, r.ivy, r.ivz);
+#endif
     const float tA0 = pa.ok0 ? pa.tmin0 : PB_INF, tA1 = pa.ok1 ? pa.tmin1 : PB_INF, tB0 = pb.ok0 ? pb.tmin0 : PB_INF, tB1 = pb.ok1 ? pb.tmin1 : PB_INF;
     const uint32_t meta = __float_as_uint(q7.x);
     const bool g = (r.negmask >> (meta & 3u)) & 1u, sA = (r.negmask >> ((meta >> 2) & 3u)) & 1u, sB = (r.negmask >> ((meta >> 4) & 3u)) & 1u;

@@ -57,7 +57,11 @@ def run(rays, anyhit, reps=10):
     e0.record()
     for _ in range(reps): f(dr.data_ptr(), m, dh.data_ptr())
     e1.record(); torch.cuda.synchronize()
-    return m / (e0.elapsed_time(e1) / reps) / 1e3, zlib.crc32(dh.cpu().numpy().tobytes())
+    out = dh.cpu().numpy()
+    if os.environ.get("AB_DUMP"):  # hit records of this build, for a record-by-record comparison between two builds
+        run.n = getattr(run, "n", 0) + 1
+        if run.n <= 4: np.save(f"{os.environ['AB_DUMP']}_{run.n}_{len(rays)}_{int(anyhit)}.npy", out)  # cam, bounce1, shadow, shadow-any of the first config
+    return m / (e0.elapsed_time(e1) / reps) / 1e3, zlib.crc32(out.tobytes())
 
 configs = [(f"refill<{rb} interior_min {im}", {1: rb, 4: im}) for rb in (24,) for im in (0, 4, 8, 12, 16, 20, 24)]
 configs += [(f"refill<{rb} interior_min {im}", {1: rb, 4: im}) for rb in (16, 28) for im in (0, 12)]
