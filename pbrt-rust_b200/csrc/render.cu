@@ -234,6 +234,7 @@ struct RenderDev {
     int* sp_voxel;       // lazy SpatialLightDistribution: the voxel k_spatial_mark claimed for the slot's hit.  The shade kernels (fast-math
                          // translation unit) would otherwise recompute the hit point with different roundings and, on a voxel boundary,
                          // look up a voxel nobody built
+    uint32_t* tex_sort;  // textured scenes: {count[n_materials], cursor[n_materials]} of the per-iteration counting sort of the Q_TEX queue (k_tex_*)
     float4* rdiff;       // 3 x float4 per slot: RayDifferential of the slot's ray (texture.cuh store_diff), valid while PB_ST_HAS_DIFF is set in
                          // beta_st.w; nullptr unless the scene has textured materials
     float4* u8;          // 2 x float4 per slot: the next eight sample dimensions, written by k_sample_block when the Sobol' tables
@@ -1618,38 +1619,14 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     const uint32_t n = R.cnt->n_mat[BIN];
     const uint32_t* q = R.q_mat[BIN];
     uint32_t* q_next = R.q_path[parity ^ 1];
-    // Q_TEX: the trip count is CTA-uniform (barriers inside, see below)
-    const uint32_t nround = BIN == Q_TEX ? ((n + 127u) & ~127u) : ((n + 31u) & ~31u);
+    // Q_TEX reads its queue ordered by material (k_tex_count / k_tex_scan / k_tex_scatter below wrote it to the path queue that k_classify has consumed)
+    if (BIN == Q_TEX) q = R.q_path[parity];
+    const uint32_t nround = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         ShadeOut o = {false, false, false, false, false};
         uint32_t id = 0;
-        bool valid = i < n;
+        const bool valid = i < n;
         if (valid) id = q[i];
-        if (BIN == Q_TEX) {
-            // The textured bin holds every textured material of the scene, and each one runs its own texture programs: a warp whose
-            // lanes carry different materials executes them one after the other (ncu, T1 scene: 8 of 32 lanes active per instruction
-            // after the first bounce).  The CTA's 128 paths are therefore sorted by material first (bitonic sort of material << 7 | lane
-            // in shared memory): warps become uniform wherever the queue section holds runs of >= 32 paths of one material.
-            __shared__ uint32_t s_key[128], s_id[128];
-            const uint32_t t = threadIdx.x;
-            uint32_t key = 0xffffff80u | t;  // invalid entries sort last
-            if (valid) key = (((uint32_t)R.scene.prims[R.hit[id].x].material & 0x1ffffffu) << 7) | t;
-            s_key[t] = key; s_id[t] = id;
-            __syncthreads();
-            for (uint32_t k = 2; k <= 128u; k <<= 1)
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    const uint32_t p = t ^ j;
-                    if (p > t) {
-                        const uint32_t a = s_key[t], b = s_key[p];
-                        if (((t & k) == 0u) == (a > b)) { s_key[t] = b; s_key[p] = a; }
-                    }
-                    __syncthreads();
-                }
-            const uint32_t mine = s_key[t];
-            valid = mine < 0xffffff80u;
-            id = s_id[mine & 127u];
-            __syncthreads();  // the next trip overwrites the arrays
-        }
         if (valid) o = shade_path<BIN, INST, ZT>(R, id);
         {
             unsigned zm = __ballot_sync(0xffffffffu, o.zero_rad);
@@ -1676,6 +1653,54 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
             if (o.push_mis) R.q_mis[b2 + __popc(m2 & below)] = id;
             if (o.push_dead) R.q_dead[parity][b3 + __popc(m3 & below)] = id;
         }
+    }
+}
+
+// The textured bin holds every textured material of the scene and each one runs its own texture programs: a warp whose lanes carry different
+// materials executes them one after the other (ncu, T1 scene: 8 of 32 lanes active per instruction after the first bounce; 13 with the CTA-local
+// sort this pass replaces, whose barriers held 30 % of the stall samples -- profiles/r02_textures.md).  A counting sort of the WHOLE queue by
+// material makes every warp uniform but the ones that straddle two materials: count, exclusive scan (which also re-zeroes the counts), scatter.
+// Groups of equal material inside a warp (match.any) issue one atomic each.
+PB_D uint32_t tex_sort_key(const RenderDev& R, uint32_t id) { return (uint32_t)R.scene.prims[R.hit[id].x].material; }
+__global__ void __launch_bounds__(256) k_tex_count(RenderDev R) {
+    const uint32_t n = R.cnt->n_mat[Q_TEX], nround = (n + 31u) & ~31u;
+    const uint32_t* q = R.q_mat[Q_TEX];
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        const uint32_t key = i < n ? tex_sort_key(R, q[i]) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (i < n && lane == (unsigned)__ffs(peers) - 1u) atomicAdd(&R.tex_sort[key], (uint32_t)__popc(peers));
+    }
+}
+__global__ void __launch_bounds__(32) k_tex_scan(RenderDev R) {
+    const uint32_t nm = R.scene.n_materials;
+    uint32_t* count = R.tex_sort;
+    uint32_t* cursor = R.tex_sort + nm;
+    const unsigned lane = threadIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nm; base += 32u) {
+        const uint32_t m = base + lane;
+        const uint32_t c = m < nm ? count[m] : 0u;
+        uint32_t inc = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += t; }
+        if (m < nm) { cursor[m] = carry + inc - c; count[m] = 0u; }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+__global__ void __launch_bounds__(256) k_tex_scatter(RenderDev R, int parity) {
+    const uint32_t n = R.cnt->n_mat[Q_TEX], nround = (n + 31u) & ~31u, nm = R.scene.n_materials;
+    const uint32_t* q = R.q_mat[Q_TEX];
+    uint32_t* out = R.q_path[parity];  // consumed by k_classify: free until the next iteration's k_finish_regen
+    const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        const uint32_t id = i < n ? q[i] : 0u;
+        const uint32_t key = i < n ? tex_sort_key(R, id) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const unsigned leader = (unsigned)__ffs(peers) - 1u;
+        uint32_t base = 0;
+        if (i < n && lane == leader) base = atomicAdd(&R.tex_sort[nm + key], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, (int)leader);
+        if (i < n) out[base + (uint32_t)__popc(peers & below)] = id;
     }
 }
 #endif  // PB_SHADE_TU
@@ -1794,7 +1819,12 @@ static void launch_shade_family(const RenderDev& R, int parity, int grid_small, 
     k_shade<Q_GLASS, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
     k_shade<Q_METAL, INST, false><<<grid_shade, 128, 0, stream>>>(R, parity);
     k_shade<Q_NOMAT, INST, false><<<grid_small, 128, 0, stream>>>(R, parity);
-    if (INST && R.scene.material_ext) k_shade<Q_TEX, true, false><<<grid_shade, 128, 0, stream>>>(R, parity);  // textured scenes run the full-featured family
+    if (INST && R.scene.material_ext) {  // textured scenes run the full-featured family
+        k_tex_count<<<grid_small, 256, 0, stream>>>(R);
+        k_tex_scan<<<1, 32, 0, stream>>>(R);
+        k_tex_scatter<<<grid_small, 256, 0, stream>>>(R, parity);
+        k_shade<Q_TEX, true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    }
 }
 void launch_shade_kernels(const RenderDev& R, int parity, bool full, int grid_small, int grid_shade, cudaStream_t stream) {
     if (full) launch_shade_family<true>(R, parity, grid_small, grid_shade, stream);
@@ -3080,13 +3110,17 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         R.u8 = reinterpret_cast<float4*>(rb->u8_block);
     }
     R.rdiff = nullptr;
+    R.tex_sort = nullptr;
     if (sc->dev.material_ext) {  // textured materials: every path slot carries its ray's differentials
         RenderBuffers* rb = st->buffers;
-        const size_t need = (size_t)capacity * 48u;
+        const size_t sort_bytes = 8u * (size_t)sc->dev.n_materials;  // k_tex_count / k_tex_scan: counts (zero between iterations) + cursors
+        const size_t need = (size_t)capacity * 48u + sort_bytes;
         if (rb->diff_block && rb->diff_bytes < need) { cudaDeviceSynchronize(); pool_free(rb->diff_block, rb->diff_bytes); rb->diff_block = nullptr; }
         if (!rb->diff_block) rb->diff_block = pool_alloc(need, &rb->diff_bytes);
         if (!rb->diff_block) return fail(PBRT_B200_ERR_CUDA, "render: out of device memory for the ray differentials");
         R.rdiff = reinterpret_cast<float4*>(rb->diff_block);
+        R.tex_sort = reinterpret_cast<uint32_t*>(static_cast<char*>(rb->diff_block) + (size_t)capacity * 48u);
+        PB_CUDA_TRY(cudaMemsetAsync(R.tex_sort, 0, sort_bytes, stream));
     }
     PB_CUDA_TRY(cudaMemsetAsync(R.cnt, 0, sizeof(Counters), stream));
     if (st->sp_eager_pending) {  // every voxel's distribution, once per scene
@@ -3184,6 +3218,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
                 if (sample_prepass) { k_sample_block<<<grid_small, 256, 0, stream>>>(R, parity); launches += 1; }
                 k_classify<<<grid_small, 256, 0, stream>>>(R, parity);
                 launch_shade_kernels(R, parity, full, grid_small, grid_shade, stream);
+                if (R.tex_sort) launches += 3;  // k_tex_count / k_tex_scan / k_tex_scatter
                 if (timing) mark();
                 if (inst) k_trace_shadow<true><<<grid_shadow, PB_TRACE_BLOCK, 0, stream>>>(R);
                 else k_trace_shadow<false><<<grid_shadow, PB_TRACE_BLOCK, 0, stream>>>(R);
