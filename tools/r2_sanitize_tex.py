@@ -1,5 +1,5 @@
 """Small textured + volumetric renders for compute-sanitizer (memcheck / racecheck): every new kernel path of the round --
-k_shade<Q_TEX> (wavefront, with its shared-memory sort), k_rec_shade<.., TEX> (two-candidate frames, differentials), k_zt_mega and
+k_shade<Q_TEX> behind its whole-queue counting sort (k_tex_count, k_tex_scan, k_tex_scatter), k_rec_shade<.., TEX> (two-candidate frames, differentials), k_zt_mega and
 k_vol_mega with the textured case, k_vol_mega on the fog box."""
 import importlib, sys
 sys.path.insert(0, '.')
