@@ -2260,24 +2260,34 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
     uint2 stack_mem[PB_STACK_SIZE(INST)];
     LocalStack stack{stack_mem};
     VolState vs;
+    // ONE flat loop, a path vertex per trip: a lane whose path has ended claims its next camera sample at the top of the following trip, so the
+    // warp stays full and every lane is in the same phase of a vertex (trace, medium / surface shade, shadow walk, MIS walk).  The nested form
+    // (a path loop inside a sample loop) reconverged only when the warp's LONGEST path had ended: lanes idled for the rest of it.
+    bool have = false, exhausted = false, alive = false;
+    uint32_t vertices = 0;
     for (;;) {
-        // claim the next camera sample: the lanes that arrive together share one fetch-add
-        unsigned long long item;
-        {
-            const unsigned m = __activemask();
-            const int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(&R.cnt->item_cursor, (unsigned long long)__popc(m));
-            base = __shfl_sync(m, base, leader);
-            item = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+        {   // lanes without a path share one fetch-add
+            const bool need = !have && !exhausted;
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (need) {
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(&R.cnt->item_cursor, (unsigned long long)__popc(m));
+                base = __shfl_sync(m, base, leader);
+                const unsigned long long item = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+                if (item >= total_items) exhausted = true;
+                else if (gen_camera_path(R, item, j)) {
+                    n_camera += 1;
+                    vs.medium = camera_medium;
+                    have = true; alive = true; vertices = 0;
+                }
+            }
         }
-        if (item >= total_items) break;
-        if (!gen_camera_path(R, item, j)) continue;
-        n_camera += 1;
-        vs.medium = camera_medium;
-        bool alive = true;
-        uint32_t vertices = 0;
-        while (alive && vertices++ < PB_VOL_VERTEX_CAP) {
+        if (!__any_sync(0xffffffffu, have || !exhausted)) break;
+        if (have) {
+            if (vertices++ >= PB_VOL_VERTEX_CAP) alive = false;
+        }
+        if (have && alive) {
             n_iter += 1;
             TravRay r;
             {
@@ -2288,9 +2298,9 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
             }
             const int bin = store_closest_hit(R, j, r);
             const int ms = vol_sample_medium(R, j, &vs, r.found, r.hit.t);
-            if (ms == 2) break;  // volpath.rs:114
-            ShadeOut o;
-            if (ms == 1) o = vol_shade_medium<INST>(Rdev, j, &vs);
+            ShadeOut o = {false, false, false, false, false};  // ms == 2: the path ends here (volpath.rs:114)
+            if (ms == 2) {}
+            else if (ms == 1) o = vol_shade_medium<INST>(Rdev, j, &vs);
             else switch (bin) {
                 case Q_MATTE: o = vol_shade<Q_MATTE, INST>(Rdev, j, &vs); break;
                 case Q_PLASTIC: o = vol_shade<Q_PLASTIC, INST>(Rdev, j, &vs); break;
@@ -2371,13 +2381,16 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
             }
             alive = o.push_next;
         }
-        float4 Le = R.L_eta[j];
-        rgb L(Le.x, Le.y, Le.z);
-        float y = lum(L);  // integrator.rs:350-368
-        if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
-        else if (y < -1.0e-5f) L = rgb(0.0f);
-        else if (isinf(y)) L = rgb(0.0f);
-        film_add_sample_lane(R, R.pfilm[j], L);
+        if (have && !alive) {
+            float4 Le = R.L_eta[j];
+            rgb L(Le.x, Le.y, Le.z);
+            float y = lum(L);  // integrator.rs:350-368
+            if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
+            else if (y < -1.0e-5f) L = rgb(0.0f);
+            else if (isinf(y)) L = rgb(0.0f);
+            film_add_sample_lane(R, R.pfilm[j], L);
+            have = false;
+        }
     }
     atomicAdd(&R.cnt->camera_rays, n_camera); atomicAdd(&R.cnt->closest_rays, n_closest);
     atomicAdd(&R.cnt->zero_radiance, n_zero); atomicMax(&R.cnt->iterations, n_iter);
