@@ -2005,6 +2005,7 @@ __global__ void __launch_bounds__(128) k_finish_zt(RenderDev R, int parity) {
 // few hundred threads.  Here ONE thread per tile (one warp per CTA, lane 0 working) walks its tile's pixels, samples and
 // bounces start to finish -- camera sample, closest hit, shade, shadow ray, MIS ray, film -- with the same device
 // functions, in the same order per tile, hence the same random stream and the same image as the wavefront form.
+PB_D void film_add_sample_lane(const RenderDev& R, float2 pfilm, rgb L);  // defined with k_vol_mega below
 template <int BIN, bool INST>
 static __device__ __noinline__ ShadeOut zt_shade(const RenderDev* Rp, uint32_t id) { return shade_path<BIN, INST, true>(*Rp, id); }
 template <bool INST>
@@ -2029,10 +2030,12 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
     bool ok = zt_next_path(R, j, true);
     uint2 stack_mem[PB_STACK_SIZE(INST)];
     LocalStack stack{stack_mem};
+    // ONE flat loop, a path vertex per trip (as k_vol_mega below): a lane whose path has ended goes on to its tile's next sample in the same
+    // trip count as its neighbours' next vertex, instead of waiting at the end of a nested path loop for the warp's longest path.  Measured +-0
+    // here (cornell 512x512: 2.9 -> 3.1 M samples/s, textured 640x480: 2.7 -> 2.6): this kernel is latency of one serial chain per tile.
+    if (ok) n_camera += 1;
     while (ok) {
-        n_camera += 1;
-        bool alive = true;
-        while (alive) {
+        {
             n_iter += 1;
             TravRay r;
             {
@@ -2068,7 +2071,7 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
                 n_closest += 1;
                 mis_resolve<INST>(R, j, r);
             }
-            alive = o.push_next;
+            if (o.push_next) continue;
         }
         // finished path -> film (integrator.rs:350-368 sanity rule), then the tile's next sample
         float4 Le = R.L_eta[j];
@@ -2077,8 +2080,9 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
         if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
         else if (y < -1.0e-5f) L = rgb(0.0f);
         else if (isinf(y)) L = rgb(0.0f);
-        film_add_sample(R, R.pfilm[j], L, true);
+        film_add_sample_lane(R, R.pfilm[j], L);
         ok = zt_next_path(R, j, false);
+        if (ok) n_camera += 1;
     }
     atomicAdd(&R.cnt->camera_rays, n_camera); atomicAdd(&R.cnt->closest_rays, n_closest); atomicAdd(&R.cnt->shadow_rays, n_shadow);
     atomicAdd(&R.cnt->zero_radiance, n_zero); atomicMax(&R.cnt->iterations, n_iter);
