@@ -71,6 +71,9 @@
 #define PB_MEGA_TU 0
 #endif
 #define PB_SHADE_TU (!PB_EXACT_TU && !PB_MEGA_TU)
+#ifndef PB_VOL_BLOCK
+#define PB_VOL_BLOCK 512  /* threads per CTA of k_vol_mega.  > 64: the CTA's warps pass the phases of a trip together (barriers between them): see the kernel */
+#endif
 
 using namespace pb;
 
@@ -2254,10 +2257,16 @@ static __device__ __noinline__ ShadeOut vol_shade_medium(const RenderDev* Rp, ui
 template <int BIN, bool INST>
 static __device__ __noinline__ ShadeOut vol_shade(const RenderDev* Rp, uint32_t id, VolState* vs) { return shade_path<BIN, INST, false, true>(*Rp, id, vs); }
 
+#define PB_VOL_PHASED (PB_VOL_BLOCK > 64)
+#if PB_VOL_PHASED
+#define PB_VOL_SYNC() __syncthreads()
+#else
+#define PB_VOL_SYNC() ((void)0)
+#endif
 #define PB_VOL_SEGMENT_CAP 4096u   /* transmittance loops: boundaries crossed by one shadow / MIS ray before it is given up (hang guard) */
 #define PB_VOL_VERTEX_CAP 65536u   /* path loop: boundary crossings lower the bounce count, so max_depth alone does not bound it */
 template <bool INST>
-__global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* Rdev, unsigned long long total_items, int camera_medium) {
+__global__ void __launch_bounds__(PB_VOL_BLOCK) k_vol_mega(RenderDev R, const RenderDev* Rdev, unsigned long long total_items, int camera_medium) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // slot
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long n_camera = 0, n_closest = 0, n_zero = 0, n_iter = 0;
@@ -2287,22 +2296,33 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
                 }
             }
         }
+        // ncu on the 64-thread form: issue slots 7 % busy, 52 of 57 stall cycles per instruction are `no_instruction` -- sixteen warps per SM each
+        // somewhere else in 100s of KB of code miss the instruction cache all the time.  One 512-thread CTA per SM whose warps pass the phases of a
+        // trip TOGETHER (barriers between trace / shade / shadow walk / MIS walk) keeps the SM inside one region of the code at a time.
+#if PB_VOL_PHASED
+        if (!__syncthreads_or(have || !exhausted)) break;
+#else
         if (!__any_sync(0xffffffffu, have || !exhausted)) break;
+#endif
         if (have) {
             if (vertices++ >= PB_VOL_VERTEX_CAP) alive = false;
         }
+        int bin = Q_MISS, ms = 2;
+        TravRay r;
         if (have && alive) {
             n_iter += 1;
-            TravRay r;
             {
                 float4 a = R.ray[2 * j], b = R.ray[2 * j + 1];
                 trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
                 trav_run<false, INST>(R.scene, r, stack, 0);
                 n_closest += 1;
             }
-            const int bin = store_closest_hit(R, j, r);
-            const int ms = vol_sample_medium(R, j, &vs, r.found, r.hit.t);
-            ShadeOut o = {false, false, false, false, false};  // ms == 2: the path ends here (volpath.rs:114)
+            bin = store_closest_hit(R, j, r);
+            ms = vol_sample_medium(R, j, &vs, r.found, r.hit.t);
+        }
+        PB_VOL_SYNC();
+        ShadeOut o = {false, false, false, false, false};  // ms == 2: the path ends here (volpath.rs:114)
+        if (have && alive) {
             if (ms == 2) {}
             else if (ms == 1) o = vol_shade_medium<INST>(Rdev, j, &vs);
             else switch (bin) {
@@ -2316,6 +2336,9 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
                 default: o = vol_shade<Q_MISS, INST>(Rdev, j, &vs); break;
             }
             if (o.zero_rad) n_zero += 1;
+        }
+        PB_VOL_SYNC();
+        if (have && alive) {
             if (o.push_shadow) {  // VisibilityTester::tr, light.rs:125-150
                 float4 a = R.sh_ray[2 * j], b = R.sh_ray[2 * j + 1];
                 f3 ro(a.x, a.y, a.z), rdir(b.x, b.y, b.z);
@@ -2345,6 +2368,9 @@ __global__ void __launch_bounds__(64) k_vol_mega(RenderDev R, const RenderDev* R
                     R.L_eta[j] = L;
                 }
             }
+        }
+        PB_VOL_SYNC();
+        if (have && alive) {
             if (o.push_mis) {  // Scene::intersect_tr, scene.rs:68-87, then integrator.rs:218-232
                 float4 a = R.mis_ray[2 * j], b = R.mis_ray[2 * j + 1];
                 f3 ro(a.x, a.y, a.z);
@@ -2404,13 +2430,13 @@ void launch_zt_mega(const RenderDev& R, const RenderDev* rdev, uint32_t lanes, u
     k_zt_mega<true><<<nblk, 32, 0, stream>>>(R, rdev, lanes);
 }
 void launch_vol_mega(const RenderDev& R, const RenderDev* rdev, unsigned long long total_items, int camera_medium, bool full, int grid, cudaStream_t stream) {
-    if (full) k_vol_mega<true><<<grid, 64, 0, stream>>>(R, rdev, total_items, camera_medium);
-    else k_vol_mega<false><<<grid, 64, 0, stream>>>(R, rdev, total_items, camera_medium);
+    if (full) k_vol_mega<true><<<grid, PB_VOL_BLOCK, 0, stream>>>(R, rdev, total_items, camera_medium);
+    else k_vol_mega<false><<<grid, PB_VOL_BLOCK, 0, stream>>>(R, rdev, total_items, camera_medium);
 }
 int vol_mega_blocks_per_sm(bool full) {
     int per_sm = 1;
-    if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<true>, 64, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<false>, 64, 0);
+    if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<true>, PB_VOL_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vol_mega<false>, PB_VOL_BLOCK, 0);
     return per_sm;
 }
 }  // namespace pb (mega.o ends here)
@@ -2939,13 +2965,13 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
         int smc = 148, per_sm = 1;
         cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, sc->device);
         per_sm = vol_mega_blocks_per_sm(sc->dev.n_instances || sc->dev.n_sphere_lights || sc->dev.material_ext);
-        const unsigned long long want = (total_items + 63ull) / 64ull;
+        const unsigned long long want = (total_items + (unsigned long long)PB_VOL_BLOCK - 1ull) / (unsigned long long)PB_VOL_BLOCK;
         vol_grid = (int)std::max<unsigned long long>(1ull, std::min<unsigned long long>((unsigned long long)smc * (unsigned long long)std::max(per_sm, 1), want));
-        capacity = ((uint32_t)vol_grid * 64u + 255u) & ~255u;
+        capacity = ((uint32_t)vol_grid * (uint32_t)PB_VOL_BLOCK + 255u) & ~255u;
     }
     if (capacity == 0) capacity = 256;
     if ((rc = ensure_buffers(st, &capacity))) return rc;
-    if (vol && capacity < (uint32_t)vol_grid * 64u) vol_grid = (int)(capacity / 64u);
+    if (vol && capacity < (uint32_t)vol_grid * (uint32_t)PB_VOL_BLOCK) vol_grid = (int)(capacity / (uint32_t)PB_VOL_BLOCK);
     lap("buffers");
     RenderDev R = st->buffers->dev;
     R.capacity = capacity;
