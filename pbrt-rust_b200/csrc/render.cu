@@ -71,6 +71,9 @@
 #define PB_MEGA_TU 0
 #endif
 #define PB_SHADE_TU (!PB_EXACT_TU && !PB_MEGA_TU)
+#ifndef PB_ZT_WARPS
+#define PB_ZT_WARPS 4u    /* warps per CTA of k_zt_mega (the host aims at ~4 warps per SM: one CTA), phases of a trip passed together */
+#endif
 #ifndef PB_VOL_BLOCK
 #define PB_VOL_BLOCK 512  /* threads per CTA of k_vol_mega.  > 64: the CTA's warps pass the phases of a trip together (barriers between them): see the kernel */
 #endif
@@ -2012,43 +2015,47 @@ PB_D void film_add_sample_lane(const RenderDev& R, float2 pfilm, rgb L);  // def
 template <int BIN, bool INST>
 static __device__ __noinline__ ShadeOut zt_shade(const RenderDev* Rp, uint32_t id) { return shade_path<BIN, INST, true>(*Rp, id); }
 template <bool INST>
-__global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rdev, uint32_t lanes) {
-    // `lanes` tiles per warp: 1 when there are few tiles (pure latency), more when one-lane warps would fill the issue slots
-    if (threadIdx.x >= lanes) return;
-    const uint32_t j = blockIdx.x * lanes + threadIdx.x;
-    if (j >= R.n_tiles_sel) return;
-    uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
-    ZtTile* tp = R.zt.tiles + j;
-    R.pixel[j] = PB_NO_SAMPLE;
-    int tx, ty;
-    if (!tile_xy(R, t, &tx, &ty) || t >= R.tile_end) return;
-    {
-        int x0 = R.sampler.sb[0] + tx * 16, y0 = R.sampler.sb[1] + ty * 16;
-        int x1 = min(x0 + 16, R.sampler.sb[2]), y1 = min(y0 + 16, R.sampler.sb[3]);
-        tp->x0 = x0; tp->y0 = y0; tp->w = (uint32_t)max(x1 - x0, 0); tp->npix = tp->w * (uint32_t)max(y1 - y0, 0);
-        tp->pixel_idx = 0; tp->sample_idx = 0; tp->cur1d = 0; tp->cur2d = 0;
-        zt_set_sequence(*tp, (unsigned long long)((long long)ty * R.ntx + tx));
-    }
+__global__ void __launch_bounds__(32 * PB_ZT_WARPS) k_zt_mega(RenderDev R, const RenderDev* Rdev, uint32_t lanes) {
+    // `lanes` tiles per warp: 1 when there are few tiles (pure latency), more when one-lane warps would fill the issue slots.  The warps of a CTA pass
+    // the phases of a trip together (barriers between them), as k_vol_mega's do and for the same reason: the instruction cache.
+    const uint32_t warp = threadIdx.x >> 5, ln = threadIdx.x & 31u;
+    const uint32_t j = (blockIdx.x * (blockDim.x >> 5) + warp) * lanes + ln;
     unsigned long long n_camera = 0, n_closest = 0, n_shadow = 0, n_zero = 0, n_iter = 0;
-    bool ok = zt_next_path(R, j, true);
+    bool ok = false;
+    if (ln < lanes && j < R.n_tiles_sel) {
+        uint32_t t = R.tile_begin + ((j / R.tile_group) * R.tile_mod + R.tile_rem) * R.tile_group + (j % R.tile_group);
+        ZtTile* tp = R.zt.tiles + j;
+        R.pixel[j] = PB_NO_SAMPLE;
+        int tx, ty;
+        if (tile_xy(R, t, &tx, &ty) && t < R.tile_end) {
+            int x0 = R.sampler.sb[0] + tx * 16, y0 = R.sampler.sb[1] + ty * 16;
+            int x1 = min(x0 + 16, R.sampler.sb[2]), y1 = min(y0 + 16, R.sampler.sb[3]);
+            tp->x0 = x0; tp->y0 = y0; tp->w = (uint32_t)max(x1 - x0, 0); tp->npix = tp->w * (uint32_t)max(y1 - y0, 0);
+            tp->pixel_idx = 0; tp->sample_idx = 0; tp->cur1d = 0; tp->cur2d = 0;
+            zt_set_sequence(*tp, (unsigned long long)((long long)ty * R.ntx + tx));
+            ok = zt_next_path(R, j, true);
+        }
+    }
     uint2 stack_mem[PB_STACK_SIZE(INST)];
     LocalStack stack{stack_mem};
-    // ONE flat loop, a path vertex per trip (as k_vol_mega below): a lane whose path has ended goes on to its tile's next sample in the same
-    // trip count as its neighbours' next vertex, instead of waiting at the end of a nested path loop for the warp's longest path.  Measured +-0
-    // here (cornell 512x512: 2.9 -> 3.1 M samples/s, textured 640x480: 2.7 -> 2.6): this kernel is latency of one serial chain per tile.
+    // ONE flat loop, a path vertex per trip: a lane whose path has ended goes on to its tile's next sample in the same trip count as its
+    // neighbours' next vertex, instead of waiting at the end of a nested path loop for the warp's longest path.
     if (ok) n_camera += 1;
-    while (ok) {
-        {
+    for (;;) {
+        if (!__syncthreads_or(ok)) break;
+        int bin = Q_MISS;
+        TravRay r;
+        if (ok) {
             n_iter += 1;
-            TravRay r;
-            {
-                float4 a = R.ray[2 * j], b = R.ray[2 * j + 1];
-                trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
-                trav_run<false, INST>(R.scene, r, stack, 0);
-                n_closest += 1;
-            }
-            const int bin = store_closest_hit(R, j, r);
-            ShadeOut o;
+            float4 a = R.ray[2 * j], b = R.ray[2 * j + 1];
+            trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+            trav_run<false, INST>(R.scene, r, stack, 0);
+            n_closest += 1;
+            bin = store_closest_hit(R, j, r);
+        }
+        __syncthreads();
+        ShadeOut o = {false, false, false, false, false};
+        if (ok) {
             switch (bin) {
                 case Q_MATTE: o = zt_shade<Q_MATTE, INST>(Rdev, j); break;
                 case Q_PLASTIC: o = zt_shade<Q_PLASTIC, INST>(Rdev, j); break;
@@ -2060,32 +2067,35 @@ __global__ void __launch_bounds__(32) k_zt_mega(RenderDev R, const RenderDev* Rd
                 default: o = zt_shade<Q_MISS, INST>(Rdev, j); break;
             }
             if (o.zero_rad) n_zero += 1;
-            if (o.push_shadow) {
-                float4 a = R.sh_ray[2 * j], b = R.sh_ray[2 * j + 1];
-                trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
-                trav_run<true, INST>(R.scene, r, stack, 0);
-                n_shadow += 1;
-                if (!r.found) shadow_unoccluded(R, j);
-            }
-            if (o.push_mis) {
-                float4 a = R.mis_ray[2 * j], b = R.mis_ray[2 * j + 1];
-                trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
-                trav_run<false, INST>(R.scene, r, stack, 0);
-                n_closest += 1;
-                mis_resolve<INST>(R, j, r);
-            }
-            if (o.push_next) continue;
         }
-        // finished path -> film (integrator.rs:350-368 sanity rule), then the tile's next sample
-        float4 Le = R.L_eta[j];
-        rgb L(Le.x, Le.y, Le.z);
-        float y = lum(L);
-        if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
-        else if (y < -1.0e-5f) L = rgb(0.0f);
-        else if (isinf(y)) L = rgb(0.0f);
-        film_add_sample_lane(R, R.pfilm[j], L);
-        ok = zt_next_path(R, j, false);
-        if (ok) n_camera += 1;
+        __syncthreads();
+        if (ok && o.push_shadow) {
+            float4 a = R.sh_ray[2 * j], b = R.sh_ray[2 * j + 1];
+            trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+            trav_run<true, INST>(R.scene, r, stack, 0);
+            n_shadow += 1;
+            if (!r.found) shadow_unoccluded(R, j);
+        }
+        __syncthreads();
+        if (ok && o.push_mis) {
+            float4 a = R.mis_ray[2 * j], b = R.mis_ray[2 * j + 1];
+            trav_init(R.scene, r, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+            trav_run<false, INST>(R.scene, r, stack, 0);
+            n_closest += 1;
+            mis_resolve<INST>(R, j, r);
+        }
+        if (ok && !o.push_next) {
+            // finished path -> film (integrator.rs:350-368 sanity rule), then the tile's next sample
+            float4 Le = R.L_eta[j];
+            rgb L(Le.x, Le.y, Le.z);
+            float y = lum(L);
+            if (L.r != L.r || L.g != L.g || L.b != L.b) L = rgb(0.0f);
+            else if (y < -1.0e-5f) L = rgb(0.0f);
+            else if (isinf(y)) L = rgb(0.0f);
+            film_add_sample_lane(R, R.pfilm[j], L);
+            ok = zt_next_path(R, j, false);
+            if (ok) n_camera += 1;
+        }
     }
     atomicAdd(&R.cnt->camera_rays, n_camera); atomicAdd(&R.cnt->closest_rays, n_closest); atomicAdd(&R.cnt->shadow_rays, n_shadow);
     atomicAdd(&R.cnt->zero_radiance, n_zero); atomicMax(&R.cnt->iterations, n_iter);
@@ -2427,7 +2437,7 @@ __global__ void __launch_bounds__(PB_VOL_BLOCK) k_vol_mega(RenderDev R, const Re
 }
 
 void launch_zt_mega(const RenderDev& R, const RenderDev* rdev, uint32_t lanes, uint32_t nblk, cudaStream_t stream) {
-    k_zt_mega<true><<<nblk, 32, 0, stream>>>(R, rdev, lanes);
+    k_zt_mega<true><<<nblk, 32 * PB_ZT_WARPS, 0, stream>>>(R, rdev, lanes);
 }
 void launch_vol_mega(const RenderDev& R, const RenderDev* rdev, unsigned long long total_items, int camera_medium, bool full, int grid, cudaStream_t stream) {
     if (full) k_vol_mega<true><<<grid, PB_VOL_BLOCK, 0, stream>>>(R, rdev, total_items, camera_medium);
@@ -3213,7 +3223,7 @@ extern "C" int pbrt_b200_render(pbrt_b200_scene* sc, const pbrt_b200_render_desc
             // 8-16 lanes 11.2 M (1: 6.1, 32: 10.8); 32640 tiles -> 32 lanes 23.8 M (1: 6.5)
             uint32_t lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (n_tiles_sel + (uint32_t)sm_count * 4u - 1u) / ((uint32_t)sm_count * 4u)));
             if (const char* e = getenv("PBRT_B200_ZT_LANES")) lanes = std::min<uint32_t>(32u, std::max<uint32_t>(1u, (uint32_t)atoi(e)));
-            const uint32_t nblk = (n_tiles_sel + lanes - 1) / lanes;
+            const uint32_t nblk = (n_tiles_sel + lanes * PB_ZT_WARPS - 1) / (lanes * PB_ZT_WARPS);
             launch_zt_mega(R, zt_rdev, lanes, nblk, stream);
             launches += 1;
         }
