@@ -33,7 +33,10 @@
 #ifdef PB_SHADE_MINB
 #define PB_SHADE_BOUNDS __launch_bounds__(128, PB_SHADE_MINB)
 #else
-#define PB_SHADE_BOUNDS __launch_bounds__(128)
+#define PB_SHADE_BOUNDS __launch_bounds__(BIN == Q_TEX ? PB_TEX_BLOCK : 128)
+#endif
+#ifndef PB_TEX_BLOCK
+#define PB_TEX_BLOCK 512  /* threads per CTA of k_shade<Q_TEX>: one CTA per SM whose warps start every path together (see k_shade) */
 #endif
 #ifdef PB_TRACE_MINB
 #define PB_TRACE_BOUNDS __launch_bounds__(PB_TRACE_BLOCK, PB_TRACE_MINB)
@@ -1627,8 +1630,13 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     uint32_t* q_next = R.q_path[parity ^ 1];
     // Q_TEX reads its queue ordered by material (k_tex_count / k_tex_scan / k_tex_scatter below wrote it to the path queue that k_classify has consumed)
     if (BIN == Q_TEX) q = R.q_path[parity];
-    const uint32_t nround = (n + 31u) & ~31u;
+    // Q_TEX: 22 k instructions of texture interpreter, noise and EWA code -- ncu had 28 of 34 stall cycles per issued instruction on `no_instruction`
+    // (instruction-cache misses) at 11 % issue-slot use.  Its CTA is the whole SM (PB_TEX_BLOCK threads at 128 registers) and its warps start every
+    // path TOGETHER (barrier at the top of a trip; the queue is sorted by material, so they run the same programs): they fetch the same lines at
+    // about the same time.  The trip count is CTA-uniform for the barrier.
+    const uint32_t nround = BIN == Q_TEX ? ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x : ((n + 31u) & ~31u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        if (BIN == Q_TEX) __syncthreads();
         ShadeOut o = {false, false, false, false, false};
         uint32_t id = 0;
         const bool valid = i < n;
@@ -1829,7 +1837,9 @@ static void launch_shade_family(const RenderDev& R, int parity, int grid_small, 
         k_tex_count<<<grid_small, 256, 0, stream>>>(R);
         k_tex_scan<<<1, 32, 0, stream>>>(R);
         k_tex_scatter<<<grid_small, 256, 0, stream>>>(R, parity);
-        k_shade<Q_TEX, true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+        static int tex_grid = 0;  // one CTA per SM
+        if (!tex_grid) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&tex_grid, cudaDevAttrMultiProcessorCount, dev); tex_grid = std::max(tex_grid, 1); }
+        k_shade<Q_TEX, true, false><<<tex_grid, PB_TEX_BLOCK, 0, stream>>>(R, parity);
     }
 }
 void launch_shade_kernels(const RenderDev& R, int parity, bool full, int grid_small, int grid_shade, cudaStream_t stream) {
