@@ -1634,9 +1634,13 @@ __global__ void PB_SHADE_BOUNDS k_shade(RenderDev R, int parity) {
     // (instruction-cache misses) at 11 % issue-slot use.  Its CTA is the whole SM (PB_TEX_BLOCK threads at 128 registers) and its warps start every
     // path TOGETHER (barrier at the top of a trip; the queue is sorted by material, so they run the same programs): they fetch the same lines at
     // about the same time.  The trip count is CTA-uniform for the barrier.
-    const uint32_t nround = BIN == Q_TEX ? ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x : ((n + 31u) & ~31u);
+#ifndef PB_SHADE_SYNC
+#define PB_SHADE_SYNC 0  /* A/B: the same barrier in every bin's kernel (128-thread CTAs) */
+#endif
+    const bool lockstep = BIN == Q_TEX || PB_SHADE_SYNC;
+    const uint32_t nround = lockstep ? ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x : ((n + 31u) & ~31u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
-        if (BIN == Q_TEX) __syncthreads();
+        if (lockstep) __syncthreads();
         ShadeOut o = {false, false, false, false, false};
         uint32_t id = 0;
         const bool valid = i < n;
