@@ -35,6 +35,9 @@
 #else
 #define PB_SHADE_BOUNDS __launch_bounds__(BIN == Q_TEX ? PB_TEX_BLOCK : 128)
 #endif
+#ifndef PB_REC_TEX_BLOCK
+#define PB_REC_TEX_BLOCK 384  /* threads per CTA of k_rec_shade<.., TEX> (168 registers: one CTA per SM) */
+#endif
 #ifndef PB_TEX_BLOCK
 #define PB_TEX_BLOCK 512  /* threads per CTA of k_shade<Q_TEX>: one CTA per SM whose warps start every path together (see k_shade) */
 #endif
@@ -1852,8 +1855,10 @@ void launch_shade_kernels(const RenderDev& R, int parity, bool full, int grid_sm
 }
 void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int grid_shade, cudaStream_t stream) {
     if (R.scene.material_ext) {
-        if (zt) k_rec_shade<true, true, true><<<grid_shade, 128, 0, stream>>>(R, parity);
-        else k_rec_shade<true, false, true><<<grid_shade, 128, 0, stream>>>(R, parity);
+        static int tex_grid = 0;  // one CTA per SM
+        if (!tex_grid) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&tex_grid, cudaDevAttrMultiProcessorCount, dev); tex_grid = std::max(tex_grid, 1); }
+        if (zt) k_rec_shade<true, true, true><<<tex_grid, PB_REC_TEX_BLOCK, 0, stream>>>(R, parity);
+        else k_rec_shade<true, false, true><<<tex_grid, PB_REC_TEX_BLOCK, 0, stream>>>(R, parity);
     } else if (zt) k_rec_shade<true, true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
     else if (full) k_rec_shade<true, false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
     else k_rec_shade<false, false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
