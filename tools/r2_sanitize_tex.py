@@ -1,4 +1,4 @@
-"""Small textured + volumetric renders for compute-sanitizer (memcheck / racecheck): every new kernel path of the round --
+"""Small textured + volumetric renders for compute-sanitizer (memcheck / racecheck / synccheck): every new kernel path of the round --
 k_shade<Q_TEX> behind its whole-queue counting sort (k_tex_count, k_tex_scan, k_tex_scatter), k_rec_shade<.., TEX> (two-candidate frames, differentials), k_zt_mega and
 k_vol_mega with the textured case, k_vol_mega on the fog box."""
 import importlib, sys
