@@ -35,6 +35,9 @@
 #else
 #define PB_SHADE_BOUNDS __launch_bounds__(BIN == Q_TEX ? PB_TEX_BLOCK : 128)
 #endif
+#ifndef PB_REC_LOCKSTEP
+#define PB_REC_LOCKSTEP 1  /* the plain k_rec_shade kernels (35 k instructions, 168 registers) phase-locked like the textured one */
+#endif
 #ifndef PB_REC_TEX_BLOCK
 #define PB_REC_TEX_BLOCK 384  /* threads per CTA of k_rec_shade<.., TEX> (168 registers: one CTA per SM) */
 #endif
@@ -1859,9 +1862,14 @@ void launch_rec_shade(const RenderDev& R, int parity, bool zt, bool full, int gr
         if (!tex_grid) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&tex_grid, cudaDevAttrMultiProcessorCount, dev); tex_grid = std::max(tex_grid, 1); }
         if (zt) k_rec_shade<true, true, true><<<tex_grid, PB_REC_TEX_BLOCK, 0, stream>>>(R, parity);
         else k_rec_shade<true, false, true><<<tex_grid, PB_REC_TEX_BLOCK, 0, stream>>>(R, parity);
-    } else if (zt) k_rec_shade<true, true, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-    else if (full) k_rec_shade<true, false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
-    else k_rec_shade<false, false, false><<<grid_shade, 128, 0, stream>>>(R, parity);
+    } else {
+        static int rec_grid = 0;  // PB_REC_LOCKSTEP: one CTA per SM
+        if (!rec_grid) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&rec_grid, cudaDevAttrMultiProcessorCount, dev); rec_grid = std::max(rec_grid, 1); }
+        const int g = PB_REC_LOCKSTEP ? rec_grid : grid_shade, b = PB_REC_LOCKSTEP ? PB_REC_TEX_BLOCK : 128;
+        if (zt) k_rec_shade<true, true, false><<<g, b, 0, stream>>>(R, parity);
+        else if (full) k_rec_shade<true, false, false><<<g, b, 0, stream>>>(R, parity);
+        else k_rec_shade<false, false, false><<<g, b, 0, stream>>>(R, parity);
+    }
 }
 }  // namespace pb (shade.o ends here)
 #endif  // PB_SHADE_TU
